@@ -1,0 +1,123 @@
+// Host-side launch helper + small epilogue utilities for gemm_tc_kernel.
+#pragma once
+#include "gemm_tc.cuh"
+#include "host_util.h"
+
+namespace pigan {
+
+constexpr int kFmtF16 = 0;  // tcgen05 kind::f16 operand format codes
+constexpr int kFmtBF16 = 1;
+
+template <class Cfg, class Epi, int AB_FMT = kFmtF16>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g,
+                const typename Epi::Params& ep, cudaStream_t st, int max_ctas = 0) {
+  auto kern = gemm_tc_kernel<Cfg, Epi, AB_FMT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PIGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int units = g.num_m_tiles * g.num_n_groups * g.k_splits;
+  if (units <= 0) return PIGAN_OK;
+  int ctas = sm_count();
+  if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  const int grid = units < ctas ? units : ctas;
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, g, ep);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// TN operands: A [M,K] (box 128 x 64), B [N,K] (box BLOCK_N x 64).
+template <class Cfg>
+int make_tn_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int m, int k, int lda, const void* b,
+                 int n, int ldb) {
+  PIGAN_TRY(make_tmap_f16_2d(ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, kBlockK, kBlockM));
+  PIGAN_TRY(make_tmap_f16_2d(tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, kBlockK, Cfg::BLOCK_N));
+  return PIGAN_OK;
+}
+// NT operands: A [Kd,M], B [Kd,N]; both loaded as boxes of 64 k-rows x 64 columns.
+inline int make_nt_maps(CUtensorMap* ta, CUtensorMap* tb, const void* a, int kd_a, int m, int lda,
+                        const void* b, int kd_b, int n, int ldb) {
+  PIGAN_TRY(make_tmap_f16_2d(ta, a, (uint64_t)m, (uint64_t)kd_a, (uint64_t)lda, 64, kBlockK));
+  PIGAN_TRY(make_tmap_f16_2d(tb, b, (uint64_t)n, (uint64_t)kd_b, (uint64_t)ldb, 64, kBlockK));
+  return PIGAN_OK;
+}
+
+template <class Cfg>
+GemmShape make_shape(int m, int n, int k, int k_splits = 1, int b_wrap_rows = 0) {
+  GemmShape g;
+  g.M = m;
+  g.N = n;
+  g.num_m_tiles = ceil_div(m, kBlockM);
+  g.num_n_groups = ceil_div(n, Cfg::ACC_COLS);
+  g.num_k_blocks = ceil_div(k, kBlockK);
+  g.k_splits = k_splits < 1 ? 1 : (k_splits > g.num_k_blocks ? g.num_k_blocks : k_splits);
+  g.b_wrap_k_blocks = b_wrap_rows / kBlockK;
+  return g;
+}
+
+// ------------------------------------------------------------------ device-side epilogue helpers
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 32 consecutive fp32 values -> 32 fp16 at dst (64 B, 16-byte aligned)
+__device__ __forceinline__ void store_f16x32(__half* dst, const float* v) {
+  uint4* p = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+    p[i] = u;
+  }
+}
+__device__ __forceinline__ void store_f16x16(__half* dst, const float* v) {
+  uint4* p = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u;
+    u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
+    p[i] = u;
+  }
+}
+// 32 consecutive fp16 values at src (64 B aligned to 16) -> fp32
+__device__ __forceinline__ void load_f16x32(const __half* src, float* v) {
+  const uint4* p = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(p + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[8 * i + 2 * j] = f.x;
+      v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+
+// Butterfly "transpose-reduce": every lane holds 32 per-column values of its own row; afterwards lane l
+// holds the sum over the warp's 32 rows of column l.  31 shuffles + adds instead of 32*5.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      // keep the half of the columns this lane stays responsible for, send the other half
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+}  // namespace pigan

@@ -1,0 +1,218 @@
+// Persistent warp-specialised tcgen05 GEMM used by every hidden-layer contraction of the hot path
+// (reference: nn.Linear forward/backward in core/models/{generator,discriminator,forward_model}.py).
+//
+//   TN mode  (MN_MAJOR = false):  D[M,N] = A[M,K] * B[N,K]^T      A,B fp16, K contiguous ("K-major")
+//            forward layers (A = activations, B = weight [out,in]) and dX (B = weight^T copy).
+//   NT mode  (MN_MAJOR = true):   D[M,N] = A[Kd,M]^T * B[Kd,N]    reduction over rows (the batch)
+//            dW = dY^T * X with split-K over CTAs; operands are read as stored, no transposes.
+//
+// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM -> registers -> fused math -> global).  Operand tiles go through a
+// STAGES-deep TMA/mbarrier ring in 128B-swizzled shared memory; fp32 accumulators live in TMEM and
+// are double-buffered when they fit (2 * ACC_TILES * BLOCK_N <= 512 columns) so the epilogue of
+// unit i overlaps the MMAs of unit i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace pigan {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // 64 halves = 128 B = one swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+
+struct GemmShape {
+  int M;                // valid output rows
+  int N;                // valid output columns
+  int num_m_tiles;      // ceil(M / 128)
+  int num_n_groups;     // ceil(N / (ACC_TILES * BLOCK_N))
+  int num_k_blocks;     // ceil(K / 64)
+  int k_splits;         // >= 1; units = m_tiles * n_groups * k_splits
+  int b_wrap_k_blocks;  // NT mode: B operand row block index is taken modulo this (0 = off)
+};
+
+struct UnitInfo {
+  int m_tile, n_group, kb_begin, kb_end, split;
+};
+
+__device__ __forceinline__ UnitInfo decode_unit(const GemmShape& g, int u) {
+  UnitInfo w;
+  const int tiles = g.num_m_tiles * g.num_n_groups;
+  const int tile = u % tiles;
+  w.split = u / tiles;
+  w.m_tile = tile / g.num_n_groups;
+  w.n_group = tile % g.num_n_groups;
+  w.kb_begin = (int)(((long long)w.split * g.num_k_blocks) / g.k_splits);
+  w.kb_end = (int)(((long long)(w.split + 1) * g.num_k_blocks) / g.k_splits);
+  return w;
+}
+
+template <int BLOCK_N_, int ACC_TILES_, int STAGES_, bool MN_MAJOR_>
+struct GemmCfg {
+  static constexpr int BLOCK_N = BLOCK_N_;
+  static constexpr int ACC_TILES = ACC_TILES_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr bool MN_MAJOR = MN_MAJOR_;
+  static constexpr int ACC_COLS = BLOCK_N * ACC_TILES;
+  static constexpr int ACC_BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
+  static constexpr int B_TILE_BYTES = BLOCK_N * kBlockK * 2;
+  // keep every stage base 1024-B aligned (swizzle atom)
+  static constexpr int B_TILE_ALLOC = (B_TILE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = kATileBytes + B_TILE_ALLOC;
+  static constexpr int TX_BYTES = kATileBytes + B_TILE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(!MN_MAJOR || BLOCK_N % 64 == 0, "NT mode loads B in 64-wide boxes");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+// Epilogue contract (all static, called by the 128 epilogue threads):
+//   struct Params;  struct State;                       // State lives in registers across units
+//   init(State&)                                         // before the unit loop
+//   unit(const Params&, State&, const GemmShape&, const UnitInfo&, uint32_t tmem_acc, int q, int lane)
+//        tmem_acc = TMEM address of this unit's first accumulator column, lane field already set
+//        to this warp's 32-lane quarter; row handled by the thread = m_tile*128 + q*32 + lane.
+//   finish(const Params&, State&, int q, int lane)       // after the loop
+template <class Cfg, class Epi, int AB_FMT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmShape g, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = g.num_m_tiles * g.num_n_groups * g.k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const UnitInfo w = decode_unit(g, u);
+        for (int t = 0; t < Cfg::ACC_TILES; ++t) {
+          const int n0 = (w.n_group * Cfg::ACC_TILES + t) * Cfg::BLOCK_N;
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::TX_BYTES);
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sb = sa + kATileBytes;
+            if constexpr (!Cfg::MN_MAJOR) {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, w.m_tile * kBlockM);
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+            } else {
+              const int kb_b = g.b_wrap_k_blocks ? (kb % g.b_wrap_k_blocks) : kb;
+#pragma unroll
+              for (int i = 0; i < kBlockM / 64; ++i)
+                tma_load_2d(sa + i * 8192, &tmap_a, full_bar(stage), w.m_tile * kBlockM + i * 64,
+                            kb * kBlockK);
+#pragma unroll
+              for (int j = 0; j < Cfg::BLOCK_N / 64; ++j)
+                tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n0 + j * 64, kb_b * kBlockK);
+            }
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc =
+          umma_idesc_f16(kBlockM, Cfg::BLOCK_N, AB_FMT, Cfg::MN_MAJOR ? 1 : 0, Cfg::MN_MAJOR ? 1 : 0);
+      constexpr uint32_t lbo = Cfg::MN_MAJOR ? 8192u : 16u;
+      constexpr uint32_t kstep = Cfg::MN_MAJOR ? 2048u : 32u;  // bytes per UMMA_K step
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        const UnitInfo w = decode_unit(g, u);
+        const int buf = it % Cfg::ACC_BUFS;
+        const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        tc_fence_after();
+        for (int t = 0; t < Cfg::ACC_TILES; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS + t * Cfg::BLOCK_N);
+          for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t da = umma_desc_sw128(sa + k * kstep, lbo, 1024);
+              const uint64_t db = umma_desc_sw128(sb + k * kstep, lbo, 1024);
+              umma_f16(d_tmem, da, db, idesc, (kb > w.kb_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    typename Epi::State st;
+    Epi::init(st);
+    int it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      const UnitInfo w = decode_unit(g, u);
+      const int buf = it % Cfg::ACC_BUFS;
+      const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS);
+      Epi::unit(ep, st, g, w, tacc, q, lane);
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+    Epi::finish(ep, st, q, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace pigan

@@ -1,0 +1,49 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting without exceptions
+// across the ABI, cached device properties, TMA tensor-map construction.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pigan_b200.h"
+
+namespace pigan {
+
+void set_last_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define PIGAN_CUDA_OK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::pigan::fail(PIGAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+  } while (0)
+
+#define PIGAN_CHECK_ARG(cond)                                                            \
+  do {                                                                                   \
+    if (!(cond))                                                                         \
+      return ::pigan::fail(PIGAN_ERR_INVALID, "invalid argument: %s (%s:%d)", #cond,     \
+                           __FILE__, __LINE__);                                          \
+  } while (0)
+
+#define PIGAN_TRY(expr)                                                                  \
+  do {                                                                                   \
+    int _s = (expr);                                                                     \
+    if (_s != PIGAN_OK) return _s;                                                       \
+  } while (0)
+
+int sm_count();  // multiprocessors of the current device (cached per device)
+
+// Row-major 2-D fp16 tensor [outer, inner] with row pitch ld_elems; box = [box_outer, box_inner],
+// 128B swizzle (box_inner * 2 bytes must be <= 128), zero fill out of bounds.
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
+                     uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace pigan

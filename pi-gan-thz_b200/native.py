@@ -1,0 +1,101 @@
+"""ctypes binding of libpigan_b200.so — the only way host code reaches the CUDA kernels.
+
+There is no fallback: if the library is missing (and cannot be built because nvcc is absent) importing
+this module raises, and every compute entry point fails loudly without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpigan_b200.so")
+
+PIGAN_OK = 0
+
+
+class PiganError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pigan_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_pigan_build", os.path.join(_HERE, "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_vp = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f32 = C.c_float
+
+
+class PiganDims(C.Structure):
+    _fields_ = [
+        ("spectrum_dim", _i32),
+        ("param_dim", _i32),
+        ("metrics_dim", _i32),
+        ("g_hidden", _i32 * 2),
+        ("d_hidden", _i32 * 2),
+        ("f_hidden", _i32 * 5),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/pigan_b200.h declares must appear here
+SIGNATURES = {
+    "pigan_abi_version": (_i32, []),
+    "pigan_last_error": (C.c_char_p, []),
+    "pigan_default_dims": (None, [C.POINTER(PiganDims)]),
+    "pigan_generator_param_count": (_i64, [C.POINTER(PiganDims)]),
+    "pigan_discriminator_param_count": (_i64, [C.POINTER(PiganDims)]),
+    "pigan_forward_model_param_count": (_i64, [C.POINTER(PiganDims)]),
+    "pigan_generator_bn_buffer_count": (_i64, [C.POINTER(PiganDims)]),
+    "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "pigan_debug_gemm_tn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "pigan_debug_gemm_nt": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+}
+
+
+def _bind() -> None:
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+
+def last_error() -> str:
+    return (lib.pigan_last_error() or b"").decode()
+
+
+def check(code: int) -> None:
+    if code != PIGAN_OK:
+        raise PiganError(code, last_error())
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def default_dims() -> PiganDims:
+    d = PiganDims()
+    lib.pigan_default_dims(C.byref(d))
+    return d
