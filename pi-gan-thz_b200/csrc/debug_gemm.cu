@@ -1,20 +1,26 @@
-// Test hooks: run the tcgen05 GEMM core with trivial epilogues so tests/ can compare it with a plain
-// fp32 matmul of the same fp16 operands.  Exercises every tile configuration the layers use.
-#include "gemm_launch.cuh"
+// Test hooks: run the tcgen05 GEMM core with a trivial fp32 epilogue (every tile configuration the
+// layers use) and with the production store / weight-gradient epilogues, so tests/ can compare them with a
+// plain fp32 matmul of the same fp16 operands.
+#include "epilogues.cuh"
 
 namespace pigan {
 
-template <class Cfg>
-struct EpiStoreF32 {
+// MODE 0: fp32 direct store; 1: no TMEM access (pipeline probe); 2: TMEM loads only (probe)
+template <class Cfg, int MODE>
+struct EpiDebug {
   struct Params {
     float* c;
     int ldc;
   };
-  struct State {};
-  __device__ static void init(State&) {}
-  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w,
-                              uint32_t tacc, int q, int lane) {
-    const int row = w.m_tile * kBlockM + q * 32 + lane;
+  static constexpr int SMEM_BYTES = 0;
+  struct State {
+    float acc;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) { st.acc = 0.f; }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    if constexpr (MODE == 1) return;
+    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
 #pragma unroll 1
     for (int t = 0; t < Cfg::ACC_TILES; ++t) {
       const int n0 = (w.n_group * Cfg::ACC_TILES + t) * Cfg::BLOCK_N;
@@ -23,7 +29,10 @@ struct EpiStoreF32 {
         float v[16];
         tmem_ld16(tacc + t * Cfg::BLOCK_N + c, v);
         tmem_ld_wait();
-        if (row < g.M) {
+        if constexpr (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) st.acc += v[i];
+        } else if (row < g.M) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (n0 + c + i < g.N) p.c[(size_t)row * p.ldc + n0 + c + i] = v[i];
@@ -31,46 +40,38 @@ struct EpiStoreF32 {
       }
     }
   }
-  __device__ static void finish(const Params&, State&, int, int) {}
-};
-
-template <class Cfg>
-struct EpiAtomicAddF32 {
-  struct Params {
-    float* c;
-    int ldc;
-  };
-  struct State {};
-  __device__ static void init(State&) {}
-  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w,
-                              uint32_t tacc, int q, int lane) {
-    const int row = w.m_tile * kBlockM + q * 32 + lane;
-#pragma unroll 1
-    for (int t = 0; t < Cfg::ACC_TILES; ++t) {
-      const int n0 = (w.n_group * Cfg::ACC_TILES + t) * Cfg::BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
-        float v[32];
-        tmem_ld32(tacc + t * Cfg::BLOCK_N + c, v);
-        tmem_ld_wait();
-        if (row < g.M) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + c + i < g.N) atomicAdd(p.c + (size_t)row * p.ldc + n0 + c + i, v[i]);
-        }
-      }
-    }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    if constexpr (MODE != 0) p.c[blockIdx.x * 256 + cx.group * 128 + cx.tid] = st.acc;
   }
-  __device__ static void finish(const Params&, State&, int, int) {}
 };
 
-template <class Cfg>
+template <class Cfg, int MODE>
 static int run_tn(const void* a, const void* b, float* c, int m, int n, int k, cudaStream_t st) {
   CUtensorMap ta, tb;
   PIGAN_TRY(make_tn_maps<Cfg>(&ta, &tb, a, m, k, k, b, n, k));
   GemmShape g = make_shape<Cfg>(m, n, k);
-  typename EpiStoreF32<Cfg>::Params ep{c, n};
-  return launch_gemm<Cfg, EpiStoreF32<Cfg>>(ta, tb, g, ep, st);
+  typename EpiDebug<Cfg, MODE>::Params ep{c, n};
+  return launch_gemm<Cfg, EpiDebug<Cfg, MODE>>(ta, tb, g, ep, st);
+}
+
+template <bool BIAS, bool LRELU, bool RS>
+static int run_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out,
+                      float* rowstats, int m, int n, int k, cudaStream_t st) {
+  using Cfg = GemmCfg<256, 1, 3, false>;
+  using Epi = EpiStore<Cfg, BIAS, LRELU, RS>;
+  CUtensorMap ta, tb, tx;
+  PIGAN_TRY(make_tn_maps<Cfg>(&ta, &tb, a, m, k, k, b, n, k));
+  GemmShape g = make_shape<Cfg>(m, n, k);
+  if (a_tail) {
+    PIGAN_TRY(make_tmap_f16_2d(&tx, a_tail, 64, (uint64_t)m, 64, kBlockK, kBlockM));
+    g.a_tail = 1;
+  }
+  typename Epi::Params ep;
+  PIGAN_TRY(make_tmap_f16_2d(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n, 64, kBlockM));
+  ep.bias = bias;
+  ep.rowstats = rowstats;
+  ep.n_tiles = g.num_n_groups;
+  return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
 }
 
 }  // namespace pigan
@@ -82,24 +83,48 @@ extern "C" int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32
   PIGAN_CHECK_ARG(a && b && c && m > 0 && n > 0 && k > 0 && k % 8 == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (variant) {
-    case 0: return run_tn<GemmCfg<256, 1, 4, false>>(a, b, c, m, n, k, st);
-    case 1: return run_tn<GemmCfg<256, 2, 4, false>>(a, b, c, m, n, k, st);
-    case 2: return run_tn<GemmCfg<144, 2, 4, false>>(a, b, c, m, n, k, st);
-    case 3: return run_tn<GemmCfg<128, 1, 4, false>>(a, b, c, m, n, k, st);
+    case 0: return run_tn<GemmCfg<256, 1, 4, false>, 0>(a, b, c, m, n, k, st);
+    case 1: return run_tn<GemmCfg<256, 2, 4, false>, 0>(a, b, c, m, n, k, st);
+    case 2: return run_tn<GemmCfg<144, 2, 4, false>, 0>(a, b, c, m, n, k, st);
+    case 3: return run_tn<GemmCfg<128, 1, 4, false>, 0>(a, b, c, m, n, k, st);
+    case 10: return run_tn<GemmCfg<256, 1, 4, false>, 1>(a, b, c, m, n, k, st);
+    case 11: return run_tn<GemmCfg<256, 1, 4, false>, 2>(a, b, c, m, n, k, st);
+    case 12: return run_tn<GemmCfg<256, 1, 3, false>, 1>(a, b, c, m, n, k, st);
     default: return fail(PIGAN_ERR_INVALID, "unknown gemm variant %d", variant);
   }
 }
 
-extern "C" int pigan_debug_gemm_nt(const void* a, const void* b, float* c, int32_t kd, int32_t m, int32_t n,
-                                   int32_t k_splits, int32_t b_wrap_rows, void* stream) {
+extern "C" int pigan_debug_linear(const void* a, const void* a_tail, const void* b, const float* bias,
+                                  void* out_f16, float* rowstats, int32_t m, int32_t n, int32_t k,
+                                  int32_t leaky, void* stream) {
+  PIGAN_CHECK_ARG(a && b && out_f16 && m > 0 && n > 0 && k > 0 && k % 8 == 0 && n % 8 == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool rs = rowstats != nullptr;
+  if (bias && leaky && rs) return run_linear<true, true, true>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias && leaky) return run_linear<true, true, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias && rs) return run_linear<true, false, true>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias) return run_linear<true, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (leaky) return run_linear<false, true, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  return run_linear<false, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+}
+
+extern "C" int pigan_debug_gemm_nt(const void* a, const void* b, const void* b_tail, float* c, int32_t kd,
+                                   int32_t m, int32_t n, int32_t k_splits, int32_t b_wrap_rows,
+                                   int32_t tail_from_row, int32_t n_valid, int32_t bias_col, float* db,
+                                   void* stream) {
   PIGAN_CHECK_ARG(a && b && c && m > 0 && n > 0 && kd > 0 && m % 8 == 0 && n % 8 == 0);
-  PIGAN_CHECK_ARG(b_wrap_rows % kBlockK == 0);
+  PIGAN_CHECK_ARG(b_wrap_rows % kBlockK == 0 && tail_from_row % kBlockK == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   using Cfg = GemmCfg<256, 1, 4, true>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tx;
   const int kd_b = b_wrap_rows > 0 ? b_wrap_rows : kd;
   PIGAN_TRY(make_nt_maps(&ta, &tb, a, kd, m, m, b, kd_b, n, n));
   GemmShape g = make_shape<Cfg>(m, n, kd, k_splits, b_wrap_rows);
-  EpiAtomicAddF32<Cfg>::Params ep{c, n};
-  return launch_gemm<Cfg, EpiAtomicAddF32<Cfg>>(ta, tb, g, ep, st);
+  if (b_tail) {
+    PIGAN_TRY(make_tmap_f16_2d(&tx, b_tail, 64, (uint64_t)(kd - tail_from_row), 64, 64, kBlockK));
+    g.b_tail_from_kb = tail_from_row / kBlockK;
+  }
+  EpiWeightGrad<Cfg>::Params ep{c, n_valid > 0 ? n_valid : n, n_valid > 0 ? n_valid : n, 1.0f, bias_col, db};
+  if (n_valid > 0) ep.ld = n_valid;
+  return launch_gemm<Cfg, EpiWeightGrad<Cfg>>(ta, tb, g, ep, st, 0, b_tail ? &tx : nullptr);
 }

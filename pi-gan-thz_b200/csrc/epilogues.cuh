@@ -1,0 +1,471 @@
+// Fused epilogues of the tcgen05 GEMM.  One thread owns one output row of the 128-row tile and walks
+// its accumulator columns out of TMEM in chunks of 32; fp16 outputs are staged through 128B-swizzled
+// shared memory and written with TMA stores (coalesced, clipped at the tensor bounds).
+//
+// Measured on B200 these K<=1024 layers are bound by epilogue issue slots, not by the tensor pipe, so
+// the epilogues are kept to a few instructions per element: per-column constants are fetched with
+// uniform 128-bit loads from zero-padded arrays (no bounds checks), reductions over the batch (column
+// sums) are left to the streaming kernels in elementwise.cu where a thread owns a column, and the first
+// layers' bias / parameter columns ride inside the MMA (spare K columns of the spectrum tile).
+//
+// Gradient tensors stored in fp16 are pre-multiplied by the gradient scale GS (= global batch size) so
+// 1/B-sized values stay in fp16's normal range; parameter gradients are un-scaled when accumulated.
+#pragma once
+#include "gemm_launch.cuh"
+
+namespace pigan {
+
+constexpr int kStageBytes = 16384;  // one [128 x 64] fp16 sub-tile
+constexpr int kEpiStagingBytes = 2 * kStageBytes;
+constexpr float kLeaky = 0.2f;
+
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kLeaky * x); }  // valid for slope < 1
+__device__ __forceinline__ float lrelu_slope_from_out(float z) { return z > 0.f ? 1.f : kLeaky; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 32 consecutive per-column constants (uniform across the warp) as 8 float4 loads.
+__device__ __forceinline__ void load_cols32(const float* __restrict__ base, float* out) {
+  const float4* p = reinterpret_cast<const float4*>(base);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 t = __ldg(p + k);
+    out[4 * k + 0] = t.x;
+    out[4 * k + 1] = t.y;
+    out[4 * k + 2] = t.z;
+    out[4 * k + 3] = t.w;
+  }
+}
+
+// Double-buffered staging of [128 x 64] fp16 sub-tiles for TMA stores (one instance per epilogue group).
+struct Stager {
+  uint32_t cnt;
+  __device__ __forceinline__ void init() { cnt = 0; }
+  __device__ __forceinline__ uint32_t acquire(const EpiCtx& cx) {
+    if (cx.tid == 0) tma_store_wait_read<1>();  // the store that used this buffer two commits ago is done
+    epi_bar_sync(cx, 0);
+    return cx.smem + (cnt & 1u) * kStageBytes;
+  }
+  // 32 values of this thread's row -> columns [32h, 32h+32) of the sub-tile (128B-swizzled rows)
+  __device__ __forceinline__ static void put32(uint32_t buf, int r, int h, const float* v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = h * 4 + i;
+      const uint32_t addr = buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                   "r"(pack_half2(v[8 * i + 0], v[8 * i + 1])), "r"(pack_half2(v[8 * i + 2], v[8 * i + 3])),
+                   "r"(pack_half2(v[8 * i + 4], v[8 * i + 5])), "r"(pack_half2(v[8 * i + 6], v[8 * i + 7]))
+                   : "memory");
+    }
+  }
+  __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const CUtensorMap* m, int col0,
+                                         int row0) {
+    fence_proxy_async_smem();
+    epi_bar_sync(cx, 1);
+    if (cx.tid == 0) {
+      tma_store_2d(m, buf, col0, row0);
+      tma_store_commit();
+    }
+    ++cnt;
+  }
+  __device__ __forceinline__ static void drain(const EpiCtx& cx) {
+    if (cx.tid == 0) tma_store_wait<0>();
+  }
+};
+
+// =====================================================================================================
+// out = fp16(act(acc + bias)).  Linear layers of G (generator.py:18,21), F (forward_model.py:30-56) and
+// the plain dX products of the backward pass.  ROWSTATS also emits per-row (sum, sum of squares) of the
+// stored value over this tile's columns — the LayerNorm partials the consumer merges
+// (forward_model.py:31-53).  `bias` must be zero-padded to a multiple of BLOCK_N.
+// =====================================================================================================
+template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS>
+struct EpiStore {
+  static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "EpiStore tile shape");
+  struct Params {
+    CUtensorMap out;
+    const float* bias;
+    float* rowstats;  // [M][n_tiles][2]
+    int n_tiles;
+  };
+  static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  struct State {
+    Stager stg;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) { st.stg.init(); }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int n0 = w.n_group * Cfg::BLOCK_N;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
+      const uint32_t buf = st.stg.acquire(cx);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = sub * 64 + h * 32;
+        float v[32];
+        tmem_ld32(tacc + c, v);
+        if constexpr (BIAS) {
+          float b[32];
+          load_cols32(p.bias + n0 + c, b);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += b[i];
+        } else {
+          tmem_ld_wait();
+        }
+        if constexpr (LRELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+        }
+        if constexpr (ROWSTATS) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s1 += v[i];
+            s2 = fmaf(v[i], v[i], s2);
+          }
+        }
+        Stager::put32(buf, r, h, v);
+      }
+      st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
+    }
+    if constexpr (ROWSTATS) {
+      const int row = w.m_tile * kBlockM + r;
+      if (row < g.M)
+        *reinterpret_cast<float2*>(p.rowstats + ((size_t)row * p.n_tiles + w.n_group) * 2) = make_float2(s1, s2);
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+};
+
+// =====================================================================================================
+// Discriminator layers 2+3 + BCE (discriminator.py:24-27, loss.py:17, train_pigan.py:127-137,152-154):
+// z2 = LeakyReLU(acc + b2) is stored (fp16) for the backward pass; logit = z2.w3 + b3; p = sigmoid(logit);
+// BCELoss against a per-row label (label_a for rows < rows_a, label_b after) summed into loss_sum; the
+// gradient wrt the logit (autograd's BCE + sigmoid backward, scaled by GS) goes to dlogit[row].
+// N must equal BLOCK_N = 256 (one tile holds the whole row).
+// =====================================================================================================
+template <class Cfg>
+struct EpiDiscL2 {
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1, "EpiDiscL2 needs the whole row in one tile");
+  struct Params {
+    CUtensorMap z2;       // [rows, 256] fp16 out (may be unused: store_z2 = 0)
+    const float* b2;      // [256]
+    const float* w3;      // [256]
+    const float* b3;      // [1]
+    float label_a, label_b;
+    int rows_a;
+    int row_gap_begin, row_gap_end;  // rows in [gap_begin, gap_end) are padding between the two halves
+    float inv_batch;      // 1 / global batch (loss mean)
+    float grad_mult;      // GS / global batch
+    double* loss_sum;     // += sum over rows of BCE * inv_batch
+    float* dlogit;        // [rows] out (scaled) or null
+    float* prob_out;      // [rows] optional
+    int store_z2;
+  };
+  static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  struct State {
+    Stager stg;
+    float loss;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) {
+    st.stg.init();
+    st.loss = 0.f;
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int row = w.m_tile * kBlockM + r;
+    const bool valid = row < g.M && !(row >= p.row_gap_begin && row < p.row_gap_end);
+    float logit = 0.f;
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+      uint32_t buf = 0;
+      if (p.store_z2) buf = st.stg.acquire(cx);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = sub * 64 + h * 32;
+        float v[32], b[32], w3[32];
+        tmem_ld32(tacc + c, v);
+        load_cols32(p.b2 + c, b);
+        load_cols32(p.w3 + c, w3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = lrelu(v[i] + b[i]);
+          logit = fmaf(v[i], w3[i], logit);
+        }
+        if (p.store_z2) Stager::put32(buf, r, h, v);
+      }
+      if (p.store_z2) st.stg.commit(cx, buf, &p.z2, sub * 64, w.m_tile * kBlockM);
+    }
+    if (valid) {
+      logit += __ldg(p.b3);
+      const float prob = 1.f / (1.f + expf(-logit));
+      const float y = row < p.rows_a ? p.label_a : p.label_b;
+      // nn.BCELoss forward (log clamped at -100) and autograd's backward (denominator clamped at 1e-12)
+      const float lp = fmaxf(logf(prob), -100.f);
+      const float l1p = fmaxf(log1pf(-prob), -100.f);
+      st.loss += -(y * lp + (1.f - y) * l1p) * p.inv_batch;
+      const float pq = prob * (1.f - prob);
+      if (p.dlogit) p.dlogit[row] = (prob - y) / fmaxf(pq, 1e-12f) * pq * p.grad_mult;
+      if (p.prob_out) p.prob_out[row] = prob;
+    } else if (row < g.M && p.dlogit) {
+      p.dlogit[row] = 0.f;
+    }
+  }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    const float l = warp_sum(st.loss);
+    if (cx.lane == 0 && l != 0.f && p.loss_sum) atomicAdd(p.loss_sum, (double)l);
+    Stager::drain(cx);
+  }
+};
+
+// =====================================================================================================
+// dX through an in-place LeakyReLU (autograd of discriminator.py:23): out = acc * slope(sign of the saved
+// activation z).  Used for dH1 = (dH2.W2) * LeakyReLU'(z1) in the D-step.
+// =====================================================================================================
+template <class Cfg>
+struct EpiLeakyMaskStore {
+  static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "tile shape");
+  struct Params {
+    CUtensorMap out;
+    const __half* z;  // [M, ldz] saved activations
+    int ldz;
+  };
+  static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  struct State {
+    Stager stg;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) { st.stg.init(); }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int row = w.m_tile * kBlockM + r;
+    const int n0 = w.n_group * Cfg::BLOCK_N;
+    const bool valid = row < g.M;
+    const __half* zrow = p.z + (size_t)(valid ? row : 0) * p.ldz + n0;
+#pragma unroll 1
+    for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
+      const uint32_t buf = st.stg.acquire(cx);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = sub * 64 + h * 32;
+        float v[32], z[32];
+        tmem_ld32(tacc + c, v);
+        load_f16x32(zrow + c, z);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= lrelu_slope_from_out(z[i]);
+        Stager::put32(buf, r, h, v);
+      }
+      st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+};
+
+// =====================================================================================================
+// G-step gradient into the 4 parameter inputs of D (train_pigan.py:183 through discriminator.py:22,38):
+// dParams[r][j] += sum_c (dH2.W2)[r][c] * LeakyReLU'(z1[r][c]) * W1p[c][j].  dH1 itself is never stored.
+// `wp` is [Npad][4] fp32, zero-padded.
+// =====================================================================================================
+template <class Cfg>
+struct EpiDiscParamGrad {
+  static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N % 32 == 0, "tile shape");
+  struct Params {
+    const __half* z;   // [M, ldz]
+    int ldz;
+    const float* wp;   // [Npad][4]
+    float* dparams;    // [M,4] += (scaled by GS)
+  };
+  static constexpr int SMEM_BYTES = 0;
+  struct State {};
+  __device__ static void init(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
+    const int n0 = w.n_group * Cfg::BLOCK_N;
+    const bool valid = row < g.M;
+    const __half* zrow = p.z + (size_t)(valid ? row : 0) * p.ldz + n0;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
+      float v[32], z[32];
+      tmem_ld32(tacc + c, v);
+      load_f16x32(zrow + c, z);
+      tmem_ld_wait();
+      const float4* wq = reinterpret_cast<const float4*>(p.wp) + n0 + c;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float gz = v[i] * lrelu_slope_from_out(z[i]);
+        const float4 w4 = __ldg(wq + i);
+        a0 = fmaf(gz, w4.x, a0);
+        a1 = fmaf(gz, w4.y, a1);
+        a2 = fmaf(gz, w4.z, a2);
+        a3 = fmaf(gz, w4.w, a3);
+      }
+    }
+    if (valid) {
+      atomicAdd(p.dparams + (size_t)row * 4 + 0, a0);
+      atomicAdd(p.dparams + (size_t)row * 4 + 1, a1);
+      atomicAdd(p.dparams + (size_t)row * 4 + 2, a2);
+      atomicAdd(p.dparams + (size_t)row * 4 + 3, a3);
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+};
+
+// =====================================================================================================
+// Forward-model output layer fused with everything the step derives from it without ever writing the
+// [B,258] output (forward_model.py:56,74-75; train_pigan.py:159-170; loss.py:51-56,82-101;
+// unified_evaluator.py:387): reconstruction MSE vs the real spectrum, metric MSE, mean squared second
+// difference (maxwell), the two LC terms and d(LC)/d(params), per-row reconstruction error for
+// candidate scoring, optional fp32 dump of the output for ForwardModel.forward.
+// Tile: 2 accumulators of 144 columns = 288 >= 258, one thread sees its whole output row.
+// =====================================================================================================
+template <class Cfg>
+struct EpiFwdOut {
+  static_assert(Cfg::BLOCK_N == 144 && Cfg::ACC_TILES == 2, "EpiFwdOut tile shape");
+  struct Params {
+    const float* bias;            // [288] zero-padded
+    int S, Mt;
+    const float* target_spec;     // [M,S] fp32 or null
+    const float* target_metrics;  // [M,Mt] or null
+    const float* p_norm;          // [M,4] generator output (LC loss) or null
+    double* sums;                 // [0]=sum (recon-x)^2 [1]=sum (pm-m)^2 [2]=sum d2^2 [3]=sum lc1 [4]=sum lc2
+    float* dp_lc;                 // [M,4] d(lambda_lc * LC)/dp * GS  or null
+    float lc_grad_mult;           // lambda_lc * GS / global batch
+    float* out_full;              // [M,S+Mt] fp32 or null
+    float* row_err;               // [M] mean_j (x - recon)^2 or null
+    int f1_idx, f2_idx;
+  };
+  static constexpr int SMEM_BYTES = 0;
+  struct State {
+    float s_rec, s_met, s_mx, s_lc1, s_lc2;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) {
+    st.s_rec = st.s_met = st.s_mx = st.s_lc1 = st.s_lc2 = 0.f;
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
+    const bool valid = row < g.M;
+    const int OUT = p.S + p.Mt;
+    float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
+    float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
+    const float* xs = p.target_spec ? p.target_spec + (size_t)(valid ? row : 0) * p.S : nullptr;
+    const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 288; j0 += 16) {
+      float v[16];
+      tmem_ld16(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
+      tmem_ld_wait();
+      if (!valid || j0 >= OUT) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int j = j0 + i;
+        if (j < OUT) {
+          const float o = v[i] + __ldg(p.bias + j);
+          if (p.out_full) p.out_full[(size_t)row * OUT + j] = o;
+          if (j < p.S) {
+            if (xs) {
+              const float d = o - __ldg(xs + j);
+              rec = fmaf(d, d, rec);
+            }
+            if (j >= 2) {
+              const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
+              mx = fmaf(d2, d2, mx);
+            }
+            prev2 = prev1;
+            prev1 = o;
+          } else {
+            const int k = j - p.S;
+            if (ms) {
+              const float d = o - __ldg(ms + k);
+              met = fmaf(d, d, met);
+            }
+            if (k == p.f1_idx) f1 = o;
+            if (k == p.f2_idx) f2 = o;
+          }
+        }
+      }
+    }
+    if (!valid) return;
+    st.s_rec += rec;
+    st.s_met += met;
+    st.s_mx += mx;
+    if (p.row_err) p.row_err[row] = rec / (float)p.S;
+    if (p.p_norm) {
+      const float4 pn = __ldg(reinterpret_cast<const float4*>(p.p_norm) + row);
+      const float e1 = f1 - (0.4f * pn.x + 0.6f * pn.z);
+      const float e2 = f2 - (0.3f * pn.y + 0.7f * pn.w);
+      st.s_lc1 = fmaf(e1, e1, st.s_lc1);
+      st.s_lc2 = fmaf(e2, e2, st.s_lc2);
+      if (p.dp_lc) {
+        // d/dp of (f - th)^2 with f constant (no grad through F, train_pigan.py:156-157): -2 e dth/dp
+        const float m = -2.f * p.lc_grad_mult;
+        float4 o = make_float4(m * e1 * 0.4f, m * e2 * 0.3f, m * e1 * 0.6f, m * e2 * 0.7f);
+        *reinterpret_cast<float4*>(p.dp_lc + (size_t)row * 4) = o;
+      }
+    }
+  }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    float s[5] = {st.s_rec, st.s_met, st.s_mx, st.s_lc1, st.s_lc2};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float t = warp_sum(s[k]);
+      if (cx.lane == 0 && t != 0.f && p.sums) atomicAdd(p.sums + k, (double)t);
+    }
+  }
+};
+
+// =====================================================================================================
+// Split-K weight-gradient accumulation (autograd dW = dY^T X of every nn.Linear): fp32 atomics into the
+// flat gradient buffer, un-scaling by 1/GS, clipping to the real [out,in] extent.  `bias_col` (>= 0)
+// names the operand column that holds the constant 1 of the first layers: its product is the bias grad.
+// =====================================================================================================
+template <class Cfg>
+struct EpiWeightGrad {
+  static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N % 32 == 0, "tile shape");
+  struct Params {
+    float* dw;       // [M, ld]
+    int ld;
+    int n_valid;
+    float scale;     // 1 / GS
+    int bias_col;    // -1: none
+    float* db;       // [M]
+  };
+  static constexpr int SMEM_BYTES = 0;
+  struct State {};
+  __device__ static void init(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
+    const int n0 = w.n_group * Cfg::BLOCK_N;
+    const bool valid = row < g.M;
+    float* dst = p.dw + (size_t)(valid ? row : 0) * p.ld;
+#pragma unroll 1
+    for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
+      float v[32];
+      tmem_ld32(tacc + c, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = n0 + c + i;
+          if (col < p.n_valid) atomicAdd(dst + col, v[i] * p.scale);
+          else if (col == p.bias_col) atomicAdd(p.db + row, v[i] * p.scale);
+        }
+      }
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+};
+
+}  // namespace pigan

@@ -10,11 +10,13 @@ constexpr int kFmtBF16 = 1;
 
 template <class Cfg, class Epi, int AB_FMT = kFmtF16>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g,
-                const typename Epi::Params& ep, cudaStream_t st, int max_ctas = 0) {
+                const typename Epi::Params& ep, cudaStream_t st, int max_ctas = 0,
+                const CUtensorMap* tx = nullptr) {
   auto kern = gemm_tc_kernel<Cfg, Epi, AB_FMT>;
   static bool attr_done = false;
   if (!attr_done) {
-    PIGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PIGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES));
     attr_done = true;
   }
   const int units = g.num_m_tiles * g.num_n_groups * g.k_splits;
@@ -23,7 +25,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   const int grid = units < ctas ? units : ctas;
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(ta, tb, g, ep);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -54,6 +56,8 @@ GemmShape make_shape(int m, int n, int k, int k_splits = 1, int b_wrap_rows = 0)
   g.num_k_blocks = ceil_div(k, kBlockK);
   g.k_splits = k_splits < 1 ? 1 : (k_splits > g.num_k_blocks ? g.num_k_blocks : k_splits);
   g.b_wrap_k_blocks = b_wrap_rows / kBlockK;
+  g.a_tail = 0;
+  g.b_tail_from_kb = -1;
   return g;
 }
 

@@ -3,14 +3,20 @@
 //
 //   TN mode  (MN_MAJOR = false):  D[M,N] = A[M,K] * B[N,K]^T      A,B fp16, K contiguous ("K-major")
 //            forward layers (A = activations, B = weight [out,in]) and dX (B = weight^T copy).
+//            Optional "A tail": the last 64-wide k-block of A comes from a second tensor (tmap_x) — the
+//            spectrum tile whose spare columns carry the 4 structure parameters and a constant 1, so
+//            torch.cat + bias of D's first layer ride inside the MMA.
 //   NT mode  (MN_MAJOR = true):   D[M,N] = A[Kd,M]^T * B[Kd,N]    reduction over rows (the batch)
 //            dW = dY^T * X with split-K over CTAs; operands are read as stored, no transposes.
+//            Optional "B tail": for k-blocks >= b_tail_from_kb the last 64-column box of the last n-tile
+//            comes from tmap_x (fake-row tail of the spectrum tensor).
 //
-// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM -> registers -> fused math -> global).  Operand tiles go through a
-// STAGES-deep TMA/mbarrier ring in 128B-swizzled shared memory; fp32 accumulators live in TMEM and
-// are double-buffered when they fit (2 * ACC_TILES * BLOCK_N <= 512 columns) so the epilogue of
-// unit i overlaps the MMAs of unit i+1.
+// One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warps 2..5 and 6..9 = two epilogue groups (TMEM -> registers -> fused math -> smem -> TMA store).
+// Operand tiles go through a STAGES-deep TMA/mbarrier ring in 128B-swizzled shared memory; fp32
+// accumulators live in TMEM.  When two accumulator buffers fit (2*ACC_COLS <= 512) group e owns buffer e
+// and handles every second unit, so two epilogues overlap each other and the MMAs of later units —
+// measured on B200 the epilogue, not the tensor pipe, is what bounds these K<=1024 layers.
 #pragma once
 #include "ptx.cuh"
 
@@ -19,7 +25,7 @@ namespace pigan {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 halves = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
 struct GemmShape {
@@ -30,6 +36,8 @@ struct GemmShape {
   int num_k_blocks;     // ceil(K / 64)
   int k_splits;         // >= 1; units = m_tiles * n_groups * k_splits
   int b_wrap_k_blocks;  // NT mode: B operand row block index is taken modulo this (0 = off)
+  int a_tail;           // TN mode: last k-block of A is read from tmap_x at column 0
+  int b_tail_from_kb;   // NT mode: k-blocks >= this read the last B box of the last n-tile from tmap_x (<0 off)
 };
 
 struct UnitInfo {
@@ -61,27 +69,44 @@ struct GemmCfg {
   static constexpr int B_TILE_ALLOC = (B_TILE_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = kATileBytes + B_TILE_ALLOC;
   static constexpr int TX_BYTES = kATileBytes + B_TILE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(!MN_MAJOR || BLOCK_N % 64 == 0, "NT mode loads B in 64-wide boxes");
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-// Epilogue contract (all static, called by the 128 epilogue threads):
+// What an epilogue thread knows about itself.
+struct EpiCtx {
+  uint32_t smem;  // shared-memory address of this group's scratch region (Epi::SMEM_BYTES, 1024-aligned)
+  int tid;        // 0..127 within the epilogue group
+  int q;          // TMEM lane quarter of this warp (row in tile = q*32 + lane)
+  int lane;
+  int group;      // epilogue group 0/1
+};
+__device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
+}
+
+// Epilogue contract (all static, called by the 128 threads of an epilogue group):
 //   struct Params;  struct State;                       // State lives in registers across units
-//   init(State&)                                         // before the unit loop
-//   unit(const Params&, State&, const GemmShape&, const UnitInfo&, uint32_t tmem_acc, int q, int lane)
+//   static constexpr int SMEM_BYTES;                     // per-group scratch (multiple of 1024)
+//   init(const Params&, State&, const GemmShape&, const EpiCtx&)   // before the unit loop
+//   unit(const Params&, State&, const GemmShape&, const UnitInfo&, uint32_t tmem_acc, const EpiCtx&)
 //        tmem_acc = TMEM address of this unit's first accumulator column, lane field already set
 //        to this warp's 32-lane quarter; row handled by the thread = m_tile*128 + q*32 + lane.
-//   finish(const Params&, State&, int q, int lane)       // after the loop
+//   finish(const Params&, State&, const GemmShape&, const EpiCtx&)  // after the loop
 template <class Cfg, class Epi, int AB_FMT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmShape g, const typename Epi::Params ep) {
+               const __grid_constant__ CUtensorMap tmap_x, const GemmShape g,
+               const __grid_constant__ typename Epi::Params ep) {
+  static_assert(Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(Epi::SMEM_BYTES % 1024 == 0, "epilogue scratch must keep 1024-B alignment");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_smem = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
+  const uint32_t bar_base = epi_smem + 2 * Epi::SMEM_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
@@ -124,14 +149,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const UnitInfo w = decode_unit(g, u);
         for (int t = 0; t < Cfg::ACC_TILES; ++t) {
-          const int n0 = (w.n_group * Cfg::ACC_TILES + t) * Cfg::BLOCK_N;
+          const int nt = w.n_group * Cfg::ACC_TILES + t;
+          const int n0 = nt * Cfg::BLOCK_N;
           for (int kb = w.kb_begin; kb < w.kb_end; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(stage), Cfg::TX_BYTES);
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + kATileBytes;
             if constexpr (!Cfg::MN_MAJOR) {
-              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, w.m_tile * kBlockM);
+              if (g.a_tail && kb == g.num_k_blocks - 1)
+                tma_load_2d(sa, &tmap_x, full_bar(stage), 0, w.m_tile * kBlockM);
+              else
+                tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, w.m_tile * kBlockM);
               tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
             } else {
               const int kb_b = g.b_wrap_k_blocks ? (kb % g.b_wrap_k_blocks) : kb;
@@ -140,8 +169,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_2d(sa + i * 8192, &tmap_a, full_bar(stage), w.m_tile * kBlockM + i * 64,
                             kb * kBlockK);
 #pragma unroll
-              for (int j = 0; j < Cfg::BLOCK_N / 64; ++j)
-                tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n0 + j * 64, kb_b * kBlockK);
+              for (int j = 0; j < Cfg::BLOCK_N / 64; ++j) {
+                const bool tail = (g.b_tail_from_kb >= 0) && (kb >= g.b_tail_from_kb) &&
+                                  (j == Cfg::BLOCK_N / 64 - 1) && (nt == g.num_n_groups * Cfg::ACC_TILES - 1);
+                if (tail)
+                  tma_load_2d(sb + j * 8192, &tmap_x, full_bar(stage), 0, (kb - g.b_tail_from_kb) * kBlockK);
+                else
+                  tma_load_2d(sb + j * 8192, &tmap_b, full_bar(stage), n0 + j * 64, kb_b * kBlockK);
+              }
             }
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -187,23 +222,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================================================================== epilogue groups
+    EpiCtx cx;
+    cx.group = (warp - 2) >> 2;
+    cx.smem = epi_smem + cx.group * Epi::SMEM_BYTES;
+    cx.tid = threadIdx.x - 64 - 128 * cx.group;
+    cx.q = warp & 3;  // TMEM lane quarter this warp may access
+    cx.lane = lane;
     typename Epi::State st;
-    Epi::init(st);
+    Epi::init(ep, st, g, cx);
     int it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
-      const UnitInfo w = decode_unit(g, u);
       const int buf = it % Cfg::ACC_BUFS;
+      if ((Cfg::ACC_BUFS == 2 ? buf : 0) != cx.group) continue;  // group e owns accumulator buffer e
+      const UnitInfo w = decode_unit(g, u);
       const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS);
-      Epi::unit(ep, st, g, w, tacc, q, lane);
+      const uint32_t tacc = tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS);
+      Epi::unit(ep, st, g, w, tacc, cx);
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
-    Epi::finish(ep, st, q, lane);
+    Epi::finish(ep, st, g, cx);
   }
 
   tc_fence_before();

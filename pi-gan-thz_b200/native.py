@@ -61,7 +61,8 @@ SIGNATURES = {
     "pigan_generator_bn_buffer_count": (_i64, [C.POINTER(PiganDims)]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
     "pigan_debug_gemm_tn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "pigan_debug_gemm_nt": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "pigan_debug_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "pigan_debug_gemm_nt": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 

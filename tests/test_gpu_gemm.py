@@ -58,9 +58,79 @@ def test_gemm_nt(kd, m, n, splits, wrap):
     rows_b = wrap if wrap else kd
     b = (torch.randn(rows_b, n, device="cuda") * 0.1).half()
     c = torch.zeros(m, n, device="cuda", dtype=torch.float32)
-    native.check(native.lib.pigan_debug_gemm_nt(a.data_ptr(), b.data_ptr(), c.data_ptr(), kd, m, n, splits, wrap,
-                                                native.current_stream()))
+    native.check(native.lib.pigan_debug_gemm_nt(a.data_ptr(), b.data_ptr(), None, c.data_ptr(), kd, m, n, splits,
+                                                wrap, 0, 0, -1, None, native.current_stream()))
     torch.cuda.synchronize()
     bb = b if not wrap else b.repeat(kd // wrap, 1)
     ref = a.float().t() @ bb.float()
     assert _rel(c, ref) < 1e-5
+
+
+def test_gemm_nt_tail_and_bias_column():
+    """dW of D's first layer: dY^T [spectrum | params | 1 1]: fake rows take their last 64 columns from the tail
+    tensor, output clipped to 254 columns, the ones column yields the bias gradient."""
+    native = _native()
+    torch.manual_seed(99)
+    half_rows, m, n = 4096, 512, 256
+    kd = 2 * half_rows
+    a = (torch.randn(kd, m, device="cuda") * 0.1).half()
+    b = (torch.randn(half_rows, n, device="cuda") * 0.1).half()
+    b[:, 254:] = 1.0
+    tail = b[:, 192:].clone()
+    tail[:, 58:62] = (torch.randn(half_rows, 4, device="cuda") * 0.1).half()
+    c = torch.zeros(m, 254, device="cuda")
+    db = torch.zeros(m, device="cuda")
+    native.check(native.lib.pigan_debug_gemm_nt(a.data_ptr(), b.data_ptr(), tail.data_ptr(), c.data_ptr(), kd, m, n,
+                                                19, half_rows, half_rows, 254, 254, db.data_ptr(),
+                                                native.current_stream()))
+    torch.cuda.synchronize()
+    b_fake = b.clone()
+    b_fake[:, 192:] = tail
+    full = a.float().t() @ torch.cat([b, b_fake]).float()
+    assert _rel(c, full[:, :254]) < 1e-5
+    assert _rel(db, full[:, 254]) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k,bias,leaky,rs,tail", [
+    (128, 256, 64, False, False, False, False),
+    (4096, 512, 256, True, False, False, True),    # first layers: last k-block from the tail tensor
+    (4096, 1024, 512, True, False, True, False),   # LayerNorm row partials over 4 tiles
+    (65536, 512, 256, True, True, False, False),
+    (1000, 256, 512, True, False, True, False),    # ragged rows: TMA store clipping
+    (4096, 250, 256, False, False, False, False),  # ragged columns
+])
+def test_linear_epilogue(m, n, k, bias, leaky, rs, tail):
+    native = _native()
+    torch.manual_seed(77 + m + n + k)
+    a = (torch.randn(m, k, device="cuda") * 0.5).half()
+    b = (torch.randn(n, k, device="cuda") * 0.1).half()
+    nt = (n + 255) // 256
+    bias_t = None
+    if bias:
+        bias_t = torch.zeros(nt * 256, device="cuda")
+        bias_t[:n] = torch.randn(n, device="cuda")
+    a_tail = (torch.randn(m, 64, device="cuda") * 0.5).half() if tail else None
+    ld = (n + 7) // 8 * 8
+    out = torch.full((m, ld), float("nan"), device="cuda", dtype=torch.float16)
+    rowst = torch.zeros(m, nt, 2, device="cuda") if rs else None
+    native.check(native.lib.pigan_debug_linear(a.data_ptr(), native.ptr(a_tail), b.data_ptr(), native.ptr(bias_t),
+                                               out.data_ptr(), native.ptr(rowst), m, ld, k, int(leaky),
+                                               native.current_stream()))
+    torch.cuda.synchronize()
+    a_eff = a.clone()
+    if tail:
+        a_eff[:, -64:] = a_tail
+    ref = a_eff.float() @ b.float().t()
+    if bias:
+        ref = ref + bias_t[:n]
+    if leaky:
+        ref = torch.nn.functional.leaky_relu(ref, 0.2)
+    got = out[:, :n].float()
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 6e-4        # one fp16 rounding of the output
+    if rs:
+        v = torch.zeros(m, nt * 256, device="cuda")
+        v[:, :n] = ref
+        v = v.view(m, nt, 256)
+        assert _rel(rowst[..., 0], v.sum(2)) < 1e-4
+        assert _rel(rowst[..., 1], (v * v).sum(2)) < 1e-5
