@@ -75,6 +75,101 @@ int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s, const doub
                           float* out_metrics, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Engine: owns nothing but a view of the caller's workspace (activations, fp16 operand copies of the
+ * weights, reduction scratch).  One engine per process / GPU / stream; calls are not re-entrant on the
+ * same engine.  max_batch bounds the rows any later call may pass.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PiganEngine PiganEngine;
+
+size_t pigan_engine_workspace_bytes(const PiganDims* dims, int64_t max_batch);
+int pigan_engine_create(PiganEngine** out, const PiganDims* dims, int64_t max_batch, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int pigan_engine_destroy(PiganEngine* engine);
+/* Frozen forward surrogate: packs fp16 operand copies of model.{4,8,12,16,20}.weight once
+ * (forward_model_pretrained.pth layout, pretrain_fwd_model.py:148-150; train_pigan.py:374-377). */
+int pigan_engine_load_forward_model(PiganEngine* engine, const float* f_params, void* stream);
+
+/* Generator.forward (core/models/generator.py:28-33).  training != 0: BatchNorm uses batch statistics
+ * and updates bn_buffers / num_batches_tracked (one update); training == 0: running statistics.
+ *   spectrum [n,S] fp32  ->  out_params_norm [n,P] fp32 in (-1,1) */
+int pigan_generator_forward(PiganEngine* engine, const float* g_params, float* g_bn_buffers,
+                            int64_t* g_num_batches_tracked, const float* spectrum, int64_t n, int32_t training,
+                            float* out_params_norm, void* stream);
+/* Discriminator.forward (core/models/discriminator.py:30-39): spectrum [n,S], params [n,P] (raw 2.2..2.8)
+ * -> out_prob [n] (= [n,1]) */
+int pigan_discriminator_forward(PiganEngine* engine, const float* d_params, const float* spectrum,
+                                const float* params, int64_t n, float* out_prob, void* stream);
+/* ForwardModel.forward in eval mode (core/models/forward_model.py:62-76): params_norm [n,P] ->
+ * out [n, S+Mt] fp32 (columns [0,S) spectrum, [S,S+Mt) metrics, one buffer as in the reference) */
+int pigan_forward_model_forward(PiganEngine* engine, const float* params_norm, int64_t n, float* out,
+                                void* stream);
+
+/* One iteration of train_pigan's inner loop (core/train/train_pigan.py:114-187): D-step + G-step with the
+ * frozen surrogate, the 7 losses of :174-181 (weights = config/config.py:79-88), clip_grad_norm_(1.0) and
+ * Adam(betas 0.5/0.999) for both networks.  Phases let the host interleave the data-parallel all-reduces:
+ *   phase 0  G forward up to BatchNorm-1 statistics     -> reduce bn_sums[0 .. 2*h1)
+ *   phase 1  ... up to BatchNorm-2 statistics           -> reduce bn_sums[2*h1 .. 2*h1+2*h2)
+ *   phase 2  G head, D-step forward/backward            -> reduce d_grads, loss_sums
+ *   phase 3  D clip+Adam; G-step D/F forward, losses, head backward -> reduce bn_bwd_sums[0 .. 2*h2)
+ *   phase 4  BatchNorm-2 backward, dW2, dX              -> reduce bn_bwd_sums[2*h2 .. 2*h2+2*h1)
+ *   phase 5  BatchNorm-1 backward, dW1                  -> reduce g_grads, loss_sums
+ *   phase 6  G clip+Adam, loss finalisation
+ * With one process, pigan_train_step runs phases 0..6 back to back. */
+typedef struct PiganTrainArgs {
+  /* batch (device, fp32): the 5-tuple of MetamaterialDataset.__getitem__ minus the unused members */
+  const float* spectrum;      /* [B,S]  real_spectrum */
+  const float* params_denorm; /* [B,P]  real_params_denorm (raw 2.2..2.8) */
+  const float* metrics_norm;  /* [B,Mt] real_metrics_norm */
+  int64_t batch;              /* rows on this rank */
+  int64_t global_batch;       /* rows over all ranks (== batch without data parallelism) */
+  /* generator state */
+  float* g_params;
+  float* g_grads;
+  float* g_exp_avg;
+  float* g_exp_avg_sq;
+  float* g_bn_buffers;
+  int64_t* g_num_batches_tracked; /* [2] */
+  /* discriminator state */
+  float* d_params;
+  float* d_grads;
+  float* d_exp_avg;
+  float* d_exp_avg_sq;
+  /* optimiser (per call: schedulers run on the host per epoch, train_pigan.py:61-62,252-253) */
+  float lr_g, lr_d;
+  int64_t step; /* Adam step count t of this iteration, 1-based */
+  /* loss weights, cfg.LAMBDA_* */
+  float lambda_recon, lambda_physics_spectrum, lambda_physics_metrics, lambda_maxwell, lambda_lc,
+      lambda_param_range, lambda_bnn_kl;
+  int32_t f1_idx, f2_idx; /* dataset.metric_name_to_idx['f1'/'f2'] */
+  /* outputs */
+  float* losses; /* [9] device: d, g, adv, recon_spec, recon_metrics, maxwell, lc, param_range, bnn_kl */
+} PiganTrainArgs;
+
+int pigan_train_step(PiganEngine* engine, const PiganTrainArgs* args, void* stream);
+int pigan_train_step_phase(PiganEngine* engine, const PiganTrainArgs* args, int32_t phase, void* stream);
+/* Device buffers the host all-reduces between phases (fp32 unless noted); valid for the engine's lifetime. */
+float* pigan_engine_bn_sums(PiganEngine* engine);      /* [2*h1 + 2*h2]  sum, sumsq per BatchNorm */
+float* pigan_engine_bn_bwd_sums(PiganEngine* engine);  /* [2*h2 + 2*h1]  sum dy, sum dy*xhat */
+double* pigan_engine_loss_sums(PiganEngine* engine);   /* [16] fp64 */
+
+/* Inverse-design scoring — loop body of UnifiedEvaluator.evaluate_structural_prediction
+ * (core/evaluate/unified_evaluator.py:376-392): G(eval) -> range violations -> F(eval) -> per-candidate
+ * mean((x - recon)^2) -> 1/(1+err).  Candidates are either given (spectra [n,S]) or generated as
+ * target + sigma * noise (unified_evaluator.py:453-455) with noise [n,S] passed explicitly; in the second
+ * form the error is measured against `target` (the design goal).  Any output pointer may be NULL. */
+int pigan_score_candidates(PiganEngine* engine, const float* g_params, const float* g_bn_buffers,
+                           const float* spectra, const float* target, const float* noise, float sigma, int64_t n,
+                           float* out_params_norm, int32_t* out_violations, float* out_recon_error,
+                           float* out_consistency, void* stream);
+/* k smallest of scores[n] (k <= 4096, n < 2^32), ascending, ties by position; NaN sorts last.
+ * out_indices[i] = in_indices[pos] when in_indices is given (merging gathered shard results), else
+ * index_base + pos.  workspace: pigan_topk_workspace_bytes(n, k) bytes of device memory, 16-byte aligned. */
+size_t pigan_topk_workspace_bytes(int64_t n, int32_t k);
+int pigan_topk_smallest(const float* scores, const int64_t* in_indices, int64_t n, int32_t k, int64_t index_base,
+                        float* out_scores, int64_t* out_indices, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Test hooks for the tcgen05 GEMM core (not part of the reference surface; used by tests/ only).
  *   gemm_tn: C[M,N] fp32 = A[M,K] * B[N,K]^T       A,B fp16 row-major, K multiple of 8; `variant` picks
  *            the tile configuration (0: 256x1, 1: 256x2, 2: 144x2, 3: 128x1 accumulators; 10-12: probes

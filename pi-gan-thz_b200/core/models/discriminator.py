@@ -1,0 +1,33 @@
+"""Drop-in ``core.models.discriminator.Discriminator`` backed by the sm_100a engine.
+
+Reference contract (core/models/discriminator.py:6-39): forward(spectrum [B,S], params [B,P]) ->
+probability [B,1]; ``state_dict`` keys ``main.{0,2,4}.*`` with main.0.weight of shape [512, S+P]
+(spectrum columns first).  The concatenation is never materialised: the parameter columns ride in spare
+columns of the spectrum operand of the first tensor-core GEMM.
+"""
+import torch
+import torch.nn as nn
+
+from ._native import _pkg, check_input
+
+
+class Discriminator(nn.Module):
+    def __init__(self, input_spec_dim, input_param_dim):
+        super().__init__()
+        widths = (512, 256)
+        self.main = nn.Sequential(
+            nn.Linear(input_spec_dim + input_param_dim, widths[0]), nn.LeakyReLU(0.2, inplace=True),
+            nn.Linear(widths[0], widths[1]), nn.LeakyReLU(0.2, inplace=True),
+            nn.Linear(widths[1], 1), nn.Sigmoid())
+
+    def forward(self, spectrum, params):
+        if spectrum.dim() > 2:
+            spectrum = spectrum.view(spectrum.size(0), -1)
+        if params.dim() > 2:
+            params = params.view(params.size(0), -1)
+        check_input(self, spectrum, "spectrum")
+        check_input(self, params, "params")
+        eng, flat = _pkg()
+        st = flat.net_state(self, "discriminator")
+        engine = eng.get_engine(spectrum.device, spectrum.shape[0])
+        return engine.discriminator_forward(st.params.tensor(), spectrum, params)

@@ -1,6 +1,7 @@
-// Streaming (HBM-bound) kernels between the tensor-core GEMMs: casts, normalisation finalise/apply,
-// the K=4 / N=4 layers that are too thin for UMMA, reductions, clip + Adam, weight packing.
-// All of them read/write each element once with 16-byte vector accesses where the layout allows.
+// Streaming (HBM-bound) kernels between the tensor-core GEMMs: casts, normalisation statistics / apply,
+// the K=4 / N=4 layers that are too thin for UMMA, reductions over the batch (a thread owns columns here,
+// so per-column sums are register accumulations), clip + Adam, weight packing.
+// Every kernel reads/writes each element once with 16-byte vector accesses where the layout allows.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -8,47 +9,65 @@
 
 namespace pigan {
 
+constexpr float kParamCenter = 2.5f;  // structure parameters live in (2.2, 2.8): centred before the fp16 cast
+
+// ------------------------------------------------------------------------------------------ spectrum prep
+// cvec[j] = mean of x[0:rows_used, j] (j < S), 0 for S <= j < Kp.  Any constant row works (the shift is undone
+// in fp32 through the effective bias); the batch mean keeps the fp16 operand small.
+void launch_center_vec(const float* x, int64_t rows, int S, int rows_used, float* cvec, int Kp, cudaStream_t st);
+// xc[r, 0:S] = x[r] - cvec; xc[r, S:S+P] = params[r] - 2.5 (0 when params == null); xc[r, S+P : S+P+2] = 1
+void launch_cast_center(const float* x, const float* cvec, const float* params, __half* xc, int64_t rows, int S,
+                        int P, int Kp, cudaStream_t st);
+// candidate spectra x = target + sigma * noise (unified_evaluator.py:453-455), centred on cvec
+void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
+                              float* x_out, int64_t rows, int S, int P, int Kp, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------ weight packing
+// First layers (G: main.0, D: main.0): out[i, 0:S] = W[i, 0:S]; out[i, S:S+P] = W[i, S:S+P] (wp_cols = P) or 0;
+// out[i, S+P] = hi(b_eff), out[i, S+P+1] = lo(b_eff) with
+//   b_eff[i] = b[i] + sum_j cvec[j] W[i,j] + 2.5 * sum_e W[i, S+e]   (fp32; also written to b_eff_out)
+// bias_cols = 0 leaves the two bias columns zero (generator: the stored pre-BatchNorm value stays bias-free so
+// its fp16 rounding is relative to the batch spread, not to the constant offset; b_eff is applied in fp32).
+void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
+                             const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st);
+void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st);
+void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst,
+                           cudaStream_t st);
+// wp[i][e] = W[i, S+e] (fp32, [rows_pad][4], zero beyond rows)
+void launch_extract_wp(const float* w, int ld_src, int S, int P, float* wp, int rows, int rows_pad, cudaStream_t st);
+void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------ BatchNorm (G)
+// sum[c] += sum_r h[r,c], sumsq[c] += sum_r h[r,c]^2
+void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, cudaStream_t st);
 struct BnFinalizeArgs {
-  const float* colsum;    // sum over the (global) batch of the bias-free pre-activation
-  const float* colsumsq;
-  const float* bias_eff;  // constant added to every row (bias + centering correction)
+  const float* sum;       // sums over the (global) batch of the stored (bias-free) pre-activation
+  const float* sumsq;
+  const float* offset;    // per-column constant the stored value omits (effective bias): enters running_mean only
   const float* gamma;
   const float* beta;
-  float* running_mean;
+  float* running_mean;    // may be null
   float* running_var;
   long long* num_batches_tracked;
-  float* mean;   // out: batch mean of the full pre-activation
-  float* rstd;   // out
-  float* scale;  // out: gamma * rstd
-  float* shift;  // out: beta - mean * scale
+  float* mean;            // out: batch mean of the stored value
+  float* rstd;            // out
+  float* scale;           // out: gamma * rstd
+  float* bias;            // out: beta - mean * scale   (affine applied to the stored value)
   int C;
-  double n;          // global batch size
-  int num_updates;   // running-stat updates to apply (the reference runs G.forward twice per step, F8)
+  double n;               // global batch size
+  int num_updates;        // running-stat updates to apply (the reference runs G.forward twice per step, F8)
 };
-
-// spectrum centering / cast
-void launch_center_vec(const float* x, int64_t rows, int S, int rows_used, float* cvec, int Kp, cudaStream_t st);
-void launch_cast_center(const float* x, const float* cvec, __half* xc, int64_t rows, int S, int Kp, cudaStream_t st);
-void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
-                              int64_t rows, int S, int Kp, cudaStream_t st);
-// effective first-layer bias: out[i] = b[i] + sum_j c[j] * W[i*ld + j], j < S
-void launch_bias_eff(const float* w, int ld, int S, const float* b, const float* cvec, float* out, int rows,
-                     cudaStream_t st);
-// weight packing
-void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st);
-void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst, cudaStream_t st);
-void launch_extract_cols(const float* src, int ld_src, int col0, int ncols, float* dst, int rows, cudaStream_t st);
-
-// BatchNorm (generator)
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st);
-void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta, float* scale,
-                           float* shift, int C, cudaStream_t st);
-void launch_bn_relu_apply(const __half* h, const float* scale, const float* shift, __half* a, int64_t rows, int C,
+// eval mode: y = gamma * (h + offset - running_mean) / sqrt(running_var + eps) + beta = scale * h + bias
+void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta,
+                           const float* offset, float* scale, float* bias, int C, cudaStream_t st);
+void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias, __half* a, int64_t rows, int C,
                           cudaStream_t st);
-// generator head: a2 = relu(bn2(h2)); p = tanh(a2 W3^T + b3); pden = denormalize(p); side operand rows for D
-void launch_g_head_fwd(const __half* h2, const float* scale, const float* shift, const float* w3, const float* b3,
-                       float* p_out, float* pden_out, const float* p_real, __half* paug, int64_t rows, int C,
-                       cudaStream_t st);
+// generator head: a2 = relu(bn2(h2)); p = tanh(a2 W3^T + b3); pden = denormalize(p); also builds the fake-row
+// tail of the spectrum operand (copy of xc[:, Kp-64:Kp] with the parameter columns replaced by pden - 2.5)
+void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
+                       float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
+                       int Kp, int S, cudaStream_t st);
 struct GHeadBwdArgs {
   const float* p;         // [B,4] tanh output
   const float* dpden;     // [B,4] dL/dPden * GS (may be null)
@@ -56,11 +75,11 @@ struct GHeadBwdArgs {
   float range_mult;       // lambda_range * GS / (4 * global batch)
   const __half* h2;       // [B,C]
   const float* scale;     // BN2 affine
-  const float* shift;
+  const float* bias;
   const float* mean;
   const float* rstd;
   const float* w3;        // [4,C]
-  __half* dy2;            // out [B,C] (scaled)
+  __half* dy2;            // out [B,C] (scaled, already masked by ReLU)
   float* dw3;             // [4,C] += (unscaled)
   float* db3;             // [4]   +=
   float* sum_dy;          // [C] += (scaled)
@@ -71,10 +90,16 @@ struct GHeadBwdArgs {
   int C;
 };
 void launch_g_head_bwd(const GHeadBwdArgs& a, cudaStream_t st);
-// dX = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)); bias / gamma / beta gradients
+// relu-masked column sums for the BatchNorm backward: dy = da * [scale*h+bias > 0]
+void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
+                         const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
+                         cudaStream_t st);
 struct BnBwdArgs {
   const __half* dy;   // [B,C] scaled
   const __half* h;    // [B,C]
+  int relu_mask;      // 1: dy still needs the ReLU mask (recomputed from h)
+  const float* scale;
+  const float* bias;
   const float* mean;
   const float* rstd;
   const float* gamma;
@@ -82,8 +107,8 @@ struct BnBwdArgs {
   const float* sum_dyx;
   __half* dh;         // out [B,C] scaled (may alias dy)
   float* dbias;       // [C] += sum dh / GS
-  float* dgamma;      // [C] = sum_dyx / GS
-  float* dbeta;       // [C] = sum_dy / GS
+  float* dgamma;      // [C] += sum_dyx / GS   (written by block 0)
+  float* dbeta;       // [C] += sum_dy / GS
   double inv_n;       // 1 / global batch
   float inv_gs;
   int64_t rows;
@@ -91,13 +116,20 @@ struct BnBwdArgs {
 };
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
 
-// forward model
+// ------------------------------------------------------------------------------------------ discriminator
+// dh2[r,c] = dlogit[r] * w3[c] * LeakyReLU'(z2[r,c]); dw3[c] += sum_r dlogit[r] z2[r,c] / GS;
+// db2[c] += sum_r dh2[r,c] / GS; db3 += sum_r dlogit[r] / GS   (discriminator.py:24-26 backward)
+void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
+                     float* db3, int64_t rows, int C, float inv_gs, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------ forward model
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,
                  int64_t rows, int C, cudaStream_t st);
-void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, int tile_cols, const float* gamma,
-                           const float* beta, int64_t rows, int N, cudaStream_t st);
+// in place: h = LeakyReLU(LayerNorm(h)) with per-row (sum, sumsq) partials over n_tiles column tiles
+void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const float* gamma, const float* beta,
+                           int64_t rows, int N, cudaStream_t st);
 
-// optimiser
+// ------------------------------------------------------------------------------------------ optimiser
 void launch_sumsq(const float* g, int64_t n, double* out, cudaStream_t st);
 struct AdamArgs {
   float* p;
@@ -112,20 +144,22 @@ struct AdamArgs {
 };
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st);
 // rank-1 fix-ups of first-layer weight gradients: dw[i*ld + j] += db[i] * cvec[j] (j < S);
-// dw[i*ld + S + e] += pcenter * db[i] (e < P)
-void launch_dw_fixup(float* dw, int ld, int S, const float* db, const float* cvec, int P, float pcenter, int rows,
+// dw[i*ld + S + e] += 2.5 * db[i] (e < P)
+void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,
                      cudaStream_t st);
 
 struct LossFinalizeArgs {
-  const double* sums;  // see engine.cu kSum* indices
+  const double* sums;  // engine.cu kSum* indices
   float* out9;         // loss_history order
   double batch;        // global batch
-  int S, Mt;
+  int S, Mt, P;
   float lam_recon, lam_phys_spec, lam_phys_metrics, lam_maxwell, lam_lc, lam_range, lam_kl;
 };
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st);
 
-// candidate scoring helpers
-void launch_count_violations(const float* p, int64_t rows, int P, int32_t* out, cudaStream_t st);
+// ------------------------------------------------------------------------------------------ scoring
+// violations[r] = #{j : p[r,j] < 0 or p[r,j] > 1}; consistency[r] = 1 / (1 + err[r])  (unified_evaluator.py:380,391)
+void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
+                         float* consistency, cudaStream_t st);
 
 }  // namespace pigan

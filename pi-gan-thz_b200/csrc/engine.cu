@@ -1,0 +1,645 @@
+// Host orchestration of the hot path: workspace carving, weight packing, and the kernel sequences behind
+// the C ABI (Generator/Discriminator/ForwardModel forward, the PI-GAN train step of
+// core/train/train_pigan.py:114-187 in seven phases, candidate scoring of
+// core/evaluate/unified_evaluator.py:376-392).  No host<->device synchronisation anywhere: every call only
+// enqueues work on the caller's stream, so a step can be captured in a CUDA graph.
+#include <new>
+
+#include "elementwise.cuh"
+#include "epilogues.cuh"
+#include "layout.h"
+
+namespace pigan {
+
+namespace {
+
+constexpr int kKp = 256;  // spectrum operand width (S + P + 2 spare columns <= 256)
+using CfgS = GemmCfg<256, 1, 3, false>;   // store epilogues (2 x 32 KB staging)
+using CfgP = GemmCfg<256, 1, 4, false>;   // no staging
+using CfgO = GemmCfg<144, 2, 4, false>;   // forward-model output layer
+using CfgW = GemmCfg<256, 1, 4, true>;    // weight gradients
+
+// loss_sums indices (fp64)
+enum { kSumD = 0, kSumAdv = 1, kSumRec = 2, kSumMet = 3, kSumMaxwell = 4, kSumLc1 = 5, kSumLc2 = 6, kSumRange = 7,
+       kSumGradD = 8, kSumGradG = 9, kNumSums = 16 };
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+}  // namespace pigan
+
+using namespace pigan;
+
+struct PiganEngine {
+  PiganDims d;
+  GenLayout gl;
+  DiscLayout dl;
+  FwdLayout fl;
+  int64_t max_batch, bp;  // bp = max_batch rounded up to 128: row offset of the fake half in stacked tensors
+  size_t ws_bytes;
+  bool f_loaded = false;
+  const float* f_params = nullptr;
+
+  // fp16 activations
+  __half *xc, *tail_f, *g_h1, *g_a1, *g_h2, *d_z1, *d_z2, *d_dh2, *d_dh1, *f_a1, *f_a2, *f_a3, *f_a4, *f_a5,
+      *g_dy2, *g_da1;
+  // fp16 weights
+  __half *g_w1h, *g_w2h, *g_w2th, *d_w1h, *d_w2h, *d_w2th, *f_wh[6];
+  // fp32 scratch
+  float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
+  float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
+  float *mean1, *rstd1, *scale1, *bias1, *mean2, *rstd2, *scale2, *bias2;
+  float *f_bias_out;                   // [288] zero padded
+  double* sums;
+
+  PiganEngine(const PiganDims& dims) : d(dims), gl(dims), dl(dims), fl(dims) {}
+
+  size_t carve(void* ws) {
+    Carver c(ws);
+    const int64_t B = bp;
+    const int H1 = gl.H1, H2 = gl.H2, D1 = dl.H1, D2 = dl.H2;
+    xc = c.take<__half>(B * kKp);
+    tail_f = c.take<__half>(B * 64);
+    g_h1 = c.take<__half>(B * H1);
+    g_a1 = c.take<__half>(B * H1);
+    g_h2 = c.take<__half>(B * H2);
+    d_z1 = c.take<__half>(2 * B * D1);
+    d_z2 = c.take<__half>(2 * B * D2);
+    d_dh2 = c.take<__half>(2 * B * D2);
+    d_dh1 = c.take<__half>(2 * B * D1);
+    f_a1 = c.take<__half>(B * fl.H[0]);
+    f_a2 = c.take<__half>(B * fl.H[1]);
+    f_a3 = c.take<__half>(B * fl.H[2]);
+    f_a4 = c.take<__half>(B * fl.H[3]);
+    f_a5 = c.take<__half>(B * fl.H[4]);
+    g_dy2 = c.take<__half>(B * H2);
+    g_da1 = c.take<__half>(B * H1);
+    g_w1h = c.take<__half>((size_t)H1 * kKp);
+    g_w2h = c.take<__half>((size_t)H2 * H1);
+    g_w2th = c.take<__half>((size_t)H1 * H2);
+    d_w1h = c.take<__half>((size_t)D1 * kKp);
+    d_w2h = c.take<__half>((size_t)D2 * D1);
+    d_w2th = c.take<__half>((size_t)D1 * D2);
+    f_wh[0] = nullptr;
+    int in = fl.H[0];
+    for (int i = 1; i < 6; ++i) {
+      const int out = i < 5 ? fl.H[i] : fl.OUT;
+      f_wh[i] = c.take<__half>((size_t)out * in);
+      in = out;
+    }
+    p = c.take<float>(B * 4);
+    pden = c.take<float>(B * 4);
+    dpden = c.take<float>(B * 4);
+    dp_lc = c.take<float>(B * 4);
+    dlogit = c.take<float>(2 * B);
+    prob = c.take<float>(2 * B);
+    row_err = c.take<float>(B);
+    f_rowstats = c.take<float>(B * 8 * 2);
+    cvec = c.take<float>(kKp);
+    g_beff = c.take<float>(H1);
+    d_beff = c.take<float>(D1);
+    d_wp = c.take<float>((size_t)D1 * 4);
+    bn_sums = c.take<float>(2 * H1 + 2 * H2);
+    bn_bwd_sums = c.take<float>(2 * H1 + 2 * H2);
+    mean1 = c.take<float>(H1); rstd1 = c.take<float>(H1); scale1 = c.take<float>(H1); bias1 = c.take<float>(H1);
+    mean2 = c.take<float>(H2); rstd2 = c.take<float>(H2); scale2 = c.take<float>(H2); bias2 = c.take<float>(H2);
+    f_bias_out = c.take<float>(288);
+    sums = c.take<double>(kNumSums);
+    return (c.off + 255) & ~size_t(255);
+  }
+};
+
+namespace pigan {
+namespace {
+
+int check_dims(const PiganDims& d) {
+  if (!dims_are_default(d))
+    return fail(PIGAN_ERR_UNSUPPORTED,
+                "this build implements the reference widths only (S=250, P=4, Mt=8, G 512/256, D 512/256, "
+                "F 256/512/1024/512/256)");
+  return PIGAN_OK;
+}
+
+template <class Cfg, class Epi>
+int run_tn(typename Epi::Params& ep, const __half* a, int64_t m, int k, int lda, const __half* b, int n, int ldb,
+           cudaStream_t st, const __half* a_tail = nullptr) {
+  CUtensorMap ta, tb, tx;
+  PIGAN_TRY(make_tn_maps<Cfg>(&ta, &tb, a, (int)m, k, lda, b, n, ldb));
+  GemmShape g = make_shape<Cfg>((int)m, n, k);
+  if (a_tail) {
+    PIGAN_TRY(make_tmap_f16_2d(&tx, a_tail, 64, (uint64_t)m, 64, kBlockK, kBlockM));
+    g.a_tail = 1;
+  }
+  return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
+}
+
+int out_map(CUtensorMap* m, __half* ptr, int64_t rows, int cols, int ld) {
+  return make_tmap_f16_2d(m, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld, 64, kBlockM);
+}
+
+// out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
+template <bool BIAS, bool LRELU, bool RS>
+int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
+                 float* rowstats, cudaStream_t st, const __half* a_tail = nullptr) {
+  using Epi = EpiStore<CfgS, BIAS, LRELU, RS>;
+  typename Epi::Params ep;
+  PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+  ep.bias = bias;
+  ep.rowstats = rowstats;
+  ep.n_tiles = ceil_div(n, 256);
+  return run_tn<CfgS, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
+}
+
+// dw[m_out, ld] += (1/gs) * a[kd, m_out]^T b[.., n]
+int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t b_rows, int n, float* dw, int ld,
+                int n_valid, float inv_gs, int bias_col, float* db, int64_t wrap_rows, const __half* b_tail,
+                int64_t tail_from_row, cudaStream_t st) {
+  CUtensorMap ta, tb, tx;
+  PIGAN_TRY(make_nt_maps(&ta, &tb, a, (int)kd, m_out, m_out, b, (int)b_rows, n, n));
+  const int tiles = ceil_div(m_out, kBlockM) * ceil_div(n, 256);
+  int splits = sm_count() / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  GemmShape g = make_shape<CfgW>(m_out, n, (int)kd, splits, (int)wrap_rows);
+  if (b_tail) {
+    PIGAN_TRY(make_tmap_f16_2d(&tx, b_tail, 64, (uint64_t)(kd - tail_from_row), 64, 64, kBlockK));
+    g.b_tail_from_kb = (int)(tail_from_row / kBlockK);
+  }
+  EpiWeightGrad<CfgW>::Params ep{dw, ld, n_valid, inv_gs, bias_col, db};
+  return launch_gemm<CfgW, EpiWeightGrad<CfgW>>(ta, tb, g, ep, st, 0, b_tail ? &tx : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------ generator
+// spectrum prep: centring vector, fp16 operand with [params | 1 1] in the spare columns
+int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n, cudaStream_t st) {
+  launch_center_vec(x, n, e->gl.S, (int)(n < 4096 ? n : 4096), e->cvec, kKp, st);
+  launch_cast_center(x, e->cvec, params, e->xc, n, e->gl.S, e->gl.P, kKp, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStream_t st) {
+  const GenLayout& L = e->gl;
+  launch_pack_first_layer(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, kKp, e->g_beff, L.H1, st);
+  launch_cast_pad(gp + L.w2, L.H1, L.H1, e->g_w2h, L.H1, L.H2, st);
+  if (need_backward) launch_transpose_cast(gp + L.w2, L.H2, L.H1, L.H1, e->g_w2th, L.H2, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cudaStream_t st) {
+  const DiscLayout& L = e->dl;
+  launch_pack_first_layer(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, kKp, e->d_beff, L.H1, st);
+  launch_cast_pad(dp + L.w2, L.H1, L.H1, e->d_w2h, L.H1, L.H2, st);
+  if (need_backward) {
+    launch_transpose_cast(dp + L.w2, L.H2, L.H1, L.H1, e->d_w2th, L.H2, st);
+    launch_extract_wp(dp + L.w1, L.IN, L.S, L.P, e->d_wp, L.H1, L.H1, st);
+  }
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// G layer 1 -> h1 (pre-BN product WITHOUT its constant bias: see launch_pack_first_layer)
+int g_layer1(PiganEngine* e, int64_t n, cudaStream_t st) {
+  return linear_store<false, false, false>(e->xc, n, kKp, e->g_w1h, e->gl.H1, nullptr, e->g_h1, nullptr, st);
+}
+int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st) {
+  launch_bn_relu_apply(e->g_h1, e->scale1, e->bias1, e->g_a1, n, e->gl.H1, st);
+  (void)gp;
+  return linear_store<false, false, false>(e->g_a1, n, e->gl.H1, e->g_w2h, e->gl.H2, nullptr, e->g_h2, nullptr, st);
+}
+void g_bn_stats(PiganEngine* e, int which, int64_t n, cudaStream_t st) {
+  const int H1 = e->gl.H1, H2 = e->gl.H2;
+  if (which == 1) launch_colstats(e->g_h1, n, H1, e->bn_sums, e->bn_sums + H1, st);
+  else launch_colstats(e->g_h2, n, H2, e->bn_sums + 2 * H1, e->bn_sums + 2 * H1 + H2, st);
+}
+void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offset, float* bn_buffers,
+                   int64_t* nbt, double n_global, int num_updates, cudaStream_t st) {
+  const GenLayout& L = e->gl;
+  BnFinalizeArgs a;
+  if (which == 1) {
+    a.sum = e->bn_sums; a.sumsq = e->bn_sums + L.H1; a.offset = offset;
+    a.gamma = gp + L.bn1_w; a.beta = gp + L.bn1_b;
+    a.running_mean = bn_buffers ? bn_buffers + L.rm1 : nullptr;
+    a.running_var = bn_buffers ? bn_buffers + L.rv1 : nullptr;
+    a.num_batches_tracked = nbt ? reinterpret_cast<long long*>(nbt) : nullptr;
+    a.mean = e->mean1; a.rstd = e->rstd1; a.scale = e->scale1; a.bias = e->bias1; a.C = L.H1;
+  } else {
+    a.sum = e->bn_sums + 2 * L.H1; a.sumsq = e->bn_sums + 2 * L.H1 + L.H2; a.offset = offset;
+    a.gamma = gp + L.bn2_w; a.beta = gp + L.bn2_b;
+    a.running_mean = bn_buffers ? bn_buffers + L.rm2 : nullptr;
+    a.running_var = bn_buffers ? bn_buffers + L.rv2 : nullptr;
+    a.num_batches_tracked = nbt ? reinterpret_cast<long long*>(nbt) + 1 : nullptr;
+    a.mean = e->mean2; a.rstd = e->rstd2; a.scale = e->scale2; a.bias = e->bias2; a.C = L.H2;
+  }
+  a.n = n_global;
+  a.num_updates = num_updates;
+  launch_bn_finalize(a, st);
+}
+
+// ------------------------------------------------------------------------------------------ discriminator
+// z1 rows [row0, row0+n) = LeakyReLU([xc | tail] . w1h^T)   (bias and parameter columns inside the MMA)
+int d_layer1(PiganEngine* e, int64_t n, int64_t row0, bool fake, cudaStream_t st) {
+  return linear_store<false, true, false>(e->xc, n, kKp, e->d_w1h, e->dl.H1, nullptr, e->d_z1 + row0 * e->dl.H1,
+                                          nullptr, st, fake ? e->tail_f : nullptr);
+}
+
+struct DL2Opts {
+  int64_t rows;          // rows of z1 / z2 processed (incl. the gap)
+  int64_t rows_a;        // rows < rows_a carry label_a
+  float label_a, label_b;
+  int64_t gap_begin, gap_end;
+  double global_batch;
+  double* loss_sum;
+  float* prob_out;
+  bool store_z2, want_dlogit;
+};
+int d_layer2(PiganEngine* e, const float* dp, const DL2Opts& o, cudaStream_t st) {
+  using Epi = EpiDiscL2<CfgS>;
+  const DiscLayout& L = e->dl;
+  Epi::Params ep;
+  PIGAN_TRY(out_map(&ep.z2, e->d_z2, o.rows, L.H2, L.H2));
+  ep.b2 = dp + L.b2;
+  ep.w3 = dp + L.w3;
+  ep.b3 = dp + L.b3;
+  ep.label_a = o.label_a;
+  ep.label_b = o.label_b;
+  ep.rows_a = (int)o.rows_a;
+  ep.row_gap_begin = (int)o.gap_begin;
+  ep.row_gap_end = (int)o.gap_end;
+  ep.inv_batch = (float)(1.0 / o.global_batch);
+  ep.grad_mult = 1.0f;  // GS == global batch
+  ep.loss_sum = o.loss_sum;
+  ep.dlogit = o.want_dlogit ? e->dlogit : nullptr;
+  ep.prob_out = o.prob_out;
+  ep.store_z2 = o.store_z2 ? 1 : 0;
+  return run_tn<CfgS, Epi>(ep, e->d_z1, o.rows, L.H1, L.H1, e->d_w2h, L.H2, L.H1, st);
+}
+
+// ------------------------------------------------------------------------------------------ forward model
+struct FOutOpts {
+  const float* target_spec;
+  int target_ld;
+  const float* target_metrics;
+  const float* p_norm;
+  double* sums;
+  float* dp_lc;
+  float lc_grad_mult;
+  float* out_full;
+  float* row_err;
+  int f1_idx, f2_idx;
+};
+int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o, cudaStream_t st) {
+  if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
+  const FwdLayout& L = e->fl;
+  const float* fp = e->f_params;
+  launch_f_l1(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_a1, n, L.H[0], st);
+  __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
+  for (int i = 1; i < 5; ++i) {
+    PIGAN_TRY((linear_store<true, false, true>(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], acts[i],
+                                               e->f_rowstats, st)));
+    launch_ln_lrelu_apply(acts[i], e->f_rowstats, ceil_div(L.H[i], 256), fp + L.ln_w[i], fp + L.ln_b[i], n, L.H[i],
+                          st);
+  }
+  using Epi = EpiFwdOut<CfgO>;
+  Epi::Params ep;
+  ep.bias = e->f_bias_out;
+  ep.S = L.S;
+  ep.Mt = L.Mt;
+  ep.target_spec = o.target_spec;
+  ep.target_ld = o.target_ld;
+  ep.target_metrics = o.target_metrics;
+  ep.p_norm = o.p_norm;
+  ep.sums = o.sums;
+  ep.dp_lc = o.dp_lc;
+  ep.lc_grad_mult = o.lc_grad_mult;
+  ep.out_full = o.out_full;
+  ep.row_err = o.row_err;
+  ep.f1_idx = o.f1_idx;
+  ep.f2_idx = o.f2_idx;
+  PIGAN_TRY((run_tn<CfgO, Epi>(ep, e->f_a5, n, L.H[4], L.H[4], e->f_wh[5], L.OUT, L.H[4], st)));
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ train phases
+int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t st) {
+  const GenLayout& G = e->gl;
+  const DiscLayout& D = e->dl;
+  const int64_t B = a.batch;
+  const int64_t BP = round_up(B, 128);  // fake half starts here in the stacked D tensors
+  const double NG = (double)a.global_batch;
+  const float inv_gs = (float)(1.0 / NG);  // gradient scale GS = global batch
+  float* gp = a.g_params;
+  float* dp = a.d_params;
+
+  switch (phase) {
+    case 0: {
+      PIGAN_CUDA_OK(cudaMemsetAsync(a.g_grads, 0, G.total * sizeof(float), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(a.d_grads, 0, D.total * sizeof(float), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(e->sums, 0, kNumSums * sizeof(double), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_bwd_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(e->dpden, 0, (size_t)B * 4 * sizeof(float), st));
+      PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
+      PIGAN_TRY(pack_generator(e, gp, true, st));
+      PIGAN_TRY(g_layer1(e, B, st));
+      g_bn_stats(e, 1, B, st);
+      break;
+    }
+    case 1: {
+      // the reference calls G.forward twice per step in train mode (train_pigan.py:131,148): same batch
+      // statistics, running statistics updated twice
+      g_bn_finalize(e, 1, gp, e->g_beff, a.g_bn_buffers, a.g_num_batches_tracked, NG, 2, st);
+      PIGAN_TRY(g_layer2(e, gp, B, st));
+      g_bn_stats(e, 2, B, st);
+      break;
+    }
+    case 2: {
+      g_bn_finalize(e, 2, gp, gp + G.b2, a.g_bn_buffers, a.g_num_batches_tracked, NG, 2, st);
+      launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, e->p, e->pden, e->xc, e->tail_f, B, G.H2,
+                        kKp, G.S, st);
+      // ---- D-step (train_pigan.py:123-143)
+      PIGAN_TRY(pack_discriminator(e, dp, true, st));
+      PIGAN_TRY(d_layer1(e, B, 0, false, st));
+      PIGAN_TRY(d_layer1(e, B, BP, true, st));
+      DL2Opts o{BP + B, BP, 0.9f, 0.1f, B, BP, NG, e->sums + kSumD, nullptr, true, true};
+      PIGAN_TRY(d_layer2(e, dp, o, st));
+      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, a.d_grads + D.w3, a.d_grads + D.b2, a.d_grads + D.b3,
+                      BP + B, D.H2, inv_gs, st);
+      {
+        using Epi = EpiLeakyMaskStore<CfgS>;
+        Epi::Params ep;
+        PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
+        ep.z = e->d_z1;
+        ep.ldz = D.H1;
+        PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+      }
+      PIGAN_TRY(weight_grad(e->d_dh2, BP + B, D.H2, e->d_z1, BP + B, D.H1, a.d_grads + D.w2, D.H1, D.H1, inv_gs, -1,
+                            nullptr, 0, nullptr, 0, st));
+      PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
+                            a.d_grads + D.b1, BP, e->tail_f, BP, st));
+      launch_dw_fixup(a.d_grads + D.w1, D.IN, D.S, D.P, a.d_grads + D.b1, e->cvec, D.H1, st);
+      break;
+    }
+    case 3: {
+      launch_sumsq(a.d_grads, D.total, e->sums + kSumGradD, st);
+      AdamArgs ad{dp, a.d_grads, a.d_exp_avg, a.d_exp_avg_sq, D.total, a.lr_d, 0.5f, 0.999f, 1e-8f,
+                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradD, 1.0f};
+      launch_clip_adam(ad, st);
+      // ---- G-step (train_pigan.py:145-187) against the updated discriminator
+      PIGAN_TRY(pack_discriminator(e, dp, true, st));
+      PIGAN_TRY(d_layer1(e, B, 0, true, st));
+      DL2Opts o{B, B, 1.0f, 1.0f, 0, 0, NG, e->sums + kSumAdv, nullptr, true, true};
+      PIGAN_TRY(d_layer2(e, dp, o, st));
+      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, st);
+      {
+        using Epi = EpiDiscParamGrad<CfgP>;
+        Epi::Params ep{e->d_z1, D.H1, e->d_wp, e->dpden};
+        PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+      }
+      FOutOpts fo{a.spectrum, G.S, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
+                  a.f1_idx, a.f2_idx};
+      PIGAN_TRY(f_forward(e, e->p, B, fo, st));
+      GHeadBwdArgs hb;
+      hb.p = e->p; hb.dpden = e->dpden; hb.dp_lc = e->dp_lc;
+      hb.range_mult = a.lambda_param_range / (float)G.P;
+      hb.h2 = e->g_h2; hb.scale = e->scale2; hb.bias = e->bias2; hb.mean = e->mean2; hb.rstd = e->rstd2;
+      hb.w3 = gp + G.w3; hb.dy2 = e->g_dy2; hb.dw3 = a.g_grads + G.w3; hb.db3 = a.g_grads + G.b3;
+      hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = e->sums + kSumRange;
+      hb.inv_gs = inv_gs; hb.rows = B; hb.C = G.H2;
+      launch_g_head_bwd(hb, st);
+      break;
+    }
+    case 4: {
+      BnBwdArgs bb;
+      bb.dy = e->g_dy2; bb.h = e->g_h2; bb.relu_mask = 0;
+      bb.scale = e->scale2; bb.bias = e->bias2; bb.mean = e->mean2; bb.rstd = e->rstd2; bb.gamma = gp + G.bn2_w;
+      bb.sum_dy = e->bn_bwd_sums; bb.sum_dyx = e->bn_bwd_sums + G.H2;
+      bb.dh = e->g_dy2; bb.dbias = a.g_grads + G.b2; bb.dgamma = a.g_grads + G.bn2_w; bb.dbeta = a.g_grads + G.bn2_b;
+      bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H2;
+      launch_bn_bwd_apply(bb, st);
+      PIGAN_TRY(weight_grad(e->g_dy2, B, G.H2, e->g_a1, B, G.H1, a.g_grads + G.w2, G.H1, G.H1, inv_gs, -1, nullptr, 0,
+                            nullptr, 0, st));
+      PIGAN_TRY((linear_store<false, false, false>(e->g_dy2, B, G.H2, e->g_w2th, G.H1, nullptr, e->g_da1, nullptr, st)));
+      launch_bn_bwd_stats(e->g_da1, e->g_h1, e->scale1, e->bias1, e->mean1, e->rstd1, e->bn_bwd_sums + 2 * G.H2,
+                          e->bn_bwd_sums + 2 * G.H2 + G.H1, B, G.H1, st);
+      break;
+    }
+    case 5: {
+      BnBwdArgs bb;
+      bb.dy = e->g_da1; bb.h = e->g_h1; bb.relu_mask = 1;
+      bb.scale = e->scale1; bb.bias = e->bias1; bb.mean = e->mean1; bb.rstd = e->rstd1; bb.gamma = gp + G.bn1_w;
+      bb.sum_dy = e->bn_bwd_sums + 2 * G.H2; bb.sum_dyx = e->bn_bwd_sums + 2 * G.H2 + G.H1;
+      bb.dh = e->g_da1; bb.dbias = nullptr; bb.dgamma = a.g_grads + G.bn1_w; bb.dbeta = a.g_grads + G.bn1_b;
+      bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H1;
+      launch_bn_bwd_apply(bb, st);
+      PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, kKp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
+                            a.g_grads + G.b1, 0, nullptr, 0, st));
+      launch_dw_fixup(a.g_grads + G.w1, G.S, G.S, 0, a.g_grads + G.b1, e->cvec, G.H1, st);
+      break;
+    }
+    case 6: {
+      launch_sumsq(a.g_grads, G.total, e->sums + kSumGradG, st);
+      AdamArgs ad{gp, a.g_grads, a.g_exp_avg, a.g_exp_avg_sq, G.total, a.lr_g, 0.5f, 0.999f, 1e-8f,
+                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradG, 1.0f};
+      launch_clip_adam(ad, st);
+      if (a.losses) {
+        LossFinalizeArgs lf{e->sums, a.losses, NG, G.S, e->fl.Mt, G.P, a.lambda_recon, a.lambda_physics_spectrum,
+                            a.lambda_physics_metrics, a.lambda_maxwell, a.lambda_lc, a.lambda_param_range,
+                            a.lambda_bnn_kl};
+        launch_loss_finalize(lf, st);
+      }
+      break;
+    }
+    default:
+      return fail(PIGAN_ERR_INVALID, "train phase %d out of range", phase);
+  }
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
+  PIGAN_CHECK_ARG(e != nullptr && a != nullptr);
+  PIGAN_CHECK_ARG(a->batch >= 2 && a->batch <= e->max_batch && a->global_batch >= a->batch);
+  PIGAN_CHECK_ARG(a->spectrum && a->params_denorm && a->metrics_norm);
+  PIGAN_CHECK_ARG(a->g_params && a->g_grads && a->g_exp_avg && a->g_exp_avg_sq);
+  PIGAN_CHECK_ARG(a->d_params && a->d_grads && a->d_exp_avg && a->d_exp_avg_sq);
+  PIGAN_CHECK_ARG(a->step >= 1);
+  PIGAN_CHECK_ARG(a->f1_idx >= 0 && a->f1_idx < e->fl.Mt && a->f2_idx >= 0 && a->f2_idx < e->fl.Mt);
+  return PIGAN_OK;
+}
+
+}  // namespace
+}  // namespace pigan
+
+// =============================================================================================== C ABI
+extern "C" size_t pigan_engine_workspace_bytes(const PiganDims* dims, int64_t max_batch) {
+  PiganDims d;
+  if (dims) d = *dims; else pigan_default_dims(&d);
+  if (!dims_are_default(d) || max_batch < 1) return 0;
+  PiganEngine e(d);
+  e.max_batch = max_batch;
+  e.bp = round_up(max_batch, 128);
+  return e.carve(nullptr);
+}
+
+extern "C" int pigan_engine_create(PiganEngine** out, const PiganDims* dims, int64_t max_batch, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  PIGAN_CHECK_ARG(out != nullptr && workspace != nullptr && max_batch >= 1);
+  PiganDims d;
+  if (dims) d = *dims; else pigan_default_dims(&d);
+  PIGAN_TRY(check_dims(d));
+  if (sm_count() <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0)
+    return fail(PIGAN_ERR_INVALID, "workspace must be 256-byte aligned");
+  PiganEngine* e = new (std::nothrow) PiganEngine(d);
+  if (!e) return fail(PIGAN_ERR_INVALID, "out of host memory");
+  e->max_batch = max_batch;
+  e->bp = round_up(max_batch, 128);
+  const size_t need = e->carve(nullptr);
+  if (workspace_bytes < need) {
+    delete e;
+    return fail(PIGAN_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  }
+  e->ws_bytes = e->carve(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // zero once: padding rows/columns of the operand tensors are read (and multiplied by zeros) but never written
+  cudaError_t err = cudaMemsetAsync(workspace, 0, need, st);
+  if (err != cudaSuccess) {
+    delete e;
+    return fail(PIGAN_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_engine_destroy(PiganEngine* e) {
+  delete e;
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, void* stream) {
+  PIGAN_CHECK_ARG(e != nullptr && fp != nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FwdLayout& L = e->fl;
+  int in = L.H[0];
+  for (int i = 1; i < 6; ++i) {
+    const int out = i < 5 ? L.H[i] : L.OUT;
+    launch_cast_pad(fp + L.w[i], in, in, e->f_wh[i], in, out, st);
+    in = out;
+  }
+  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  e->f_params = fp;
+  e->f_loaded = true;
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* bn, int64_t* nbt, const float* x,
+                                       int64_t n, int32_t training, float* out, void* stream) {
+  PIGAN_CHECK_ARG(e && gp && x && out && n >= 1 && n <= e->max_batch);
+  PIGAN_CHECK_ARG(training ? n >= 2 : bn != nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GenLayout& G = e->gl;
+  PIGAN_TRY(prep_spectrum(e, x, nullptr, n, st));
+  PIGAN_TRY(pack_generator(e, gp, false, st));
+  PIGAN_TRY(g_layer1(e, n, st));
+  if (training) {
+    PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+    g_bn_stats(e, 1, n, st);
+    g_bn_finalize(e, 1, gp, e->g_beff, bn, nbt, (double)n, 1, st);
+  } else {
+    launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
+  }
+  PIGAN_TRY(g_layer2(e, gp, n, st));
+  if (training) {
+    g_bn_stats(e, 2, n, st);
+    g_bn_finalize(e, 2, gp, gp + G.b2, bn, nbt, (double)n, 1, st);
+  } else {
+    launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+  }
+  launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, out, nullptr, e->xc, nullptr, n, G.H2, kKp,
+                    G.S, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_discriminator_forward(PiganEngine* e, const float* dp, const float* x, const float* params,
+                                           int64_t n, float* out_prob, void* stream) {
+  PIGAN_CHECK_ARG(e && dp && x && params && out_prob && n >= 1 && n <= e->max_batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PIGAN_TRY(prep_spectrum(e, x, params, n, st));
+  PIGAN_TRY(pack_discriminator(e, dp, false, st));
+  PIGAN_TRY(d_layer1(e, n, 0, false, st));
+  DL2Opts o{n, n, 1.0f, 1.0f, 0, 0, (double)n, nullptr, out_prob, false, false};
+  PIGAN_TRY(d_layer2(e, dp, o, st));
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_forward_model_forward(PiganEngine* e, const float* p_norm, int64_t n, float* out,
+                                           void* stream) {
+  PIGAN_CHECK_ARG(e && p_norm && out && n >= 1 && n <= e->max_batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FOutOpts fo{nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, out, nullptr, 0, 1};
+  return f_forward(e, p_norm, n, fo, st);
+}
+
+extern "C" int pigan_train_step_phase(PiganEngine* e, const PiganTrainArgs* a, int32_t phase, void* stream) {
+  PIGAN_TRY(check_train_args(e, a));
+  return train_phase(e, *a, phase, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pigan_train_step(PiganEngine* e, const PiganTrainArgs* a, void* stream) {
+  PIGAN_TRY(check_train_args(e, a));
+  for (int ph = 0; ph <= 6; ++ph) PIGAN_TRY(train_phase(e, *a, ph, static_cast<cudaStream_t>(stream)));
+  return PIGAN_OK;
+}
+
+extern "C" float* pigan_engine_bn_sums(PiganEngine* e) { return e ? e->bn_sums : nullptr; }
+extern "C" float* pigan_engine_bn_bwd_sums(PiganEngine* e) { return e ? e->bn_bwd_sums : nullptr; }
+extern "C" double* pigan_engine_loss_sums(PiganEngine* e) { return e ? e->sums : nullptr; }
+
+extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const float* bn, const float* spectra,
+                                      const float* target, const float* noise, float sigma, int64_t n,
+                                      float* out_p, int32_t* out_viol, float* out_err, float* out_cons,
+                                      void* stream) {
+  PIGAN_CHECK_ARG(e && gp && bn && n >= 1 && n <= e->max_batch);
+  PIGAN_CHECK_ARG((spectra != nullptr) != (target != nullptr && noise != nullptr));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GenLayout& G = e->gl;
+  if (spectra) {
+    PIGAN_TRY(prep_spectrum(e, spectra, nullptr, n, st));
+  } else {
+    // centre on the design target: the candidates differ from it by sigma * noise only
+    launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);
+    launch_cast_center_noise(target, noise, sigma, e->cvec, e->xc, nullptr, n, G.S, G.P, kKp, st);
+  }
+  PIGAN_TRY(pack_generator(e, gp, false, st));
+  PIGAN_TRY(g_layer1(e, n, st));
+  launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
+  PIGAN_TRY(g_layer2(e, gp, n, st));
+  launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+  float* p = out_p ? out_p : e->p;
+  launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, p, nullptr, e->xc, nullptr, n, G.H2, kKp,
+                    G.S, st);
+  float* err = out_err ? out_err : e->row_err;
+  FOutOpts fo{spectra ? spectra : target, spectra ? G.S : 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
+  PIGAN_TRY(f_forward(e, p, n, fo, st));
+  if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}

@@ -335,7 +335,8 @@ struct EpiFwdOut {
   struct Params {
     const float* bias;            // [288] zero-padded
     int S, Mt;
-    const float* target_spec;     // [M,S] fp32 or null
+    const float* target_spec;     // [M,S] fp32 (row pitch target_ld; 0 = one target row for all) or null
+    int target_ld;
     const float* target_metrics;  // [M,Mt] or null
     const float* p_norm;          // [M,4] generator output (LC loss) or null
     double* sums;                 // [0]=sum (recon-x)^2 [1]=sum (pm-m)^2 [2]=sum d2^2 [3]=sum lc1 [4]=sum lc2
@@ -359,7 +360,7 @@ struct EpiFwdOut {
     const int OUT = p.S + p.Mt;
     float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
     float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
-    const float* xs = p.target_spec ? p.target_spec + (size_t)(valid ? row : 0) * p.S : nullptr;
+    const float* xs = p.target_spec ? p.target_spec + (size_t)(valid ? row : 0) * p.target_ld : nullptr;
     const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
 #pragma unroll 1
     for (int j0 = 0; j0 < 288; j0 += 16) {

@@ -1,0 +1,168 @@
+"""Python host wrapper of the C-ABI engine (include/pigan_b200.h).  PyTorch is plumbing here: it owns the
+device memory and the stream; every computation goes through ``native.lib``."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import native
+from .native import PiganTrainArgs, check, lib
+
+LOSS_KEYS = ["d_losses", "g_losses", "adv_losses", "recon_spec_losses", "recon_metrics_losses", "maxwell_losses",
+             "lc_losses", "param_range_losses", "bnn_kl_losses"]
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"pigan_b200: {what} must live on a CUDA device — this path has no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Engine:
+    """One engine per (process, device).  ``max_batch`` bounds the rows of any later call."""
+
+    def __init__(self, max_batch: int, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pigan_b200: no CUDA device — the B200 path has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.max_batch = int(max_batch)
+        self.dims = native.default_dims()
+        with torch.cuda.device(self.device):
+            nbytes = lib.pigan_engine_workspace_bytes(C.byref(self.dims), self.max_batch)
+            if nbytes == 0:
+                raise native.PiganError(-3, "unsupported dimensions")
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            handle = C.c_void_p()
+            check(lib.pigan_engine_create(C.byref(handle), C.byref(self.dims), self.max_batch,
+                                          self.workspace.data_ptr(), nbytes, native.current_stream()))
+        self.handle = handle
+        self._f_params = None
+        self._topk_ws = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h and lib is not None:  # lib is None while the interpreter shuts down
+            lib.pigan_engine_destroy(h)
+            self.handle = None
+
+    # ------------------------------------------------------------------ weights
+    def load_forward_model(self, f_flat: torch.Tensor) -> None:
+        _require_cuda(f_flat, "forward-model parameters")
+        self._f_params = f_flat  # keep alive: the engine reads biases / norm weights from it
+        check(lib.pigan_engine_load_forward_model(self.handle, f_flat.data_ptr(), native.current_stream()))
+
+    # ------------------------------------------------------------------ module forwards
+    def generator_forward(self, g_flat, bn, nbt, spectrum, training: bool) -> torch.Tensor:
+        _require_cuda(spectrum, "spectrum")
+        x = _f32c(spectrum)
+        out = torch.empty(x.shape[0], self.dims.param_dim, device=x.device, dtype=torch.float32)
+        check(lib.pigan_generator_forward(self.handle, g_flat.data_ptr(), bn.data_ptr(), nbt.data_ptr(), x.data_ptr(),
+                                          x.shape[0], int(training), out.data_ptr(), native.current_stream()))
+        return out
+
+    def discriminator_forward(self, d_flat, spectrum, params) -> torch.Tensor:
+        _require_cuda(spectrum, "spectrum")
+        x, p = _f32c(spectrum), _f32c(params)
+        out = torch.empty(x.shape[0], 1, device=x.device, dtype=torch.float32)
+        check(lib.pigan_discriminator_forward(self.handle, d_flat.data_ptr(), x.data_ptr(), p.data_ptr(), x.shape[0],
+                                              out.data_ptr(), native.current_stream()))
+        return out
+
+    def forward_model_forward(self, params_norm) -> torch.Tensor:
+        _require_cuda(params_norm, "params_norm")
+        p = _f32c(params_norm)
+        out = torch.empty(p.shape[0], self.dims.spectrum_dim + self.dims.metrics_dim, device=p.device,
+                          dtype=torch.float32)
+        check(lib.pigan_forward_model_forward(self.handle, p.data_ptr(), p.shape[0], out.data_ptr(),
+                                              native.current_stream()))
+        return out
+
+    # ------------------------------------------------------------------ training
+    def make_train_args(self, **kw) -> PiganTrainArgs:
+        a = PiganTrainArgs()
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    def train_step(self, args: PiganTrainArgs) -> None:
+        check(lib.pigan_train_step(self.handle, C.byref(args), native.current_stream()))
+
+    def train_step_phase(self, args: PiganTrainArgs, phase: int) -> None:
+        check(lib.pigan_train_step_phase(self.handle, C.byref(args), phase, native.current_stream()))
+
+    def _wrap(self, ptr: int, n: int, dtype) -> torch.Tensor:
+        """Tensor view of an engine-owned scratch region (lives inside self.workspace)."""
+        off = ptr - self.workspace.data_ptr()
+        es = torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off:off + n * es].view(dtype)
+
+    def bn_sums(self) -> torch.Tensor:
+        n = 2 * (self.dims.g_hidden[0] + self.dims.g_hidden[1])
+        return self._wrap(lib.pigan_engine_bn_sums(self.handle), n, torch.float32)
+
+    def bn_bwd_sums(self) -> torch.Tensor:
+        n = 2 * (self.dims.g_hidden[0] + self.dims.g_hidden[1])
+        return self._wrap(lib.pigan_engine_bn_bwd_sums(self.handle), n, torch.float32)
+
+    def loss_sums(self) -> torch.Tensor:
+        return self._wrap(lib.pigan_engine_loss_sums(self.handle), 16, torch.float64)
+
+    # ------------------------------------------------------------------ scoring
+    def score_candidates(self, g_flat, bn, spectra=None, target=None, noise=None, sigma: float = 0.01,
+                         want_params=True) -> Dict[str, torch.Tensor]:
+        ref = spectra if spectra is not None else noise
+        _require_cuda(ref, "candidate spectra / noise")
+        n = ref.shape[0]
+        dev = ref.device
+        out_p = torch.empty(n, self.dims.param_dim, device=dev, dtype=torch.float32) if want_params else None
+        viol = torch.empty(n, device=dev, dtype=torch.int32)
+        err = torch.empty(n, device=dev, dtype=torch.float32)
+        cons = torch.empty(n, device=dev, dtype=torch.float32)
+        sp = _f32c(spectra) if spectra is not None else None
+        tg = _f32c(target).reshape(-1) if target is not None else None
+        nz = _f32c(noise) if noise is not None else None
+        check(lib.pigan_score_candidates(self.handle, g_flat.data_ptr(), bn.data_ptr(), native.ptr(sp), native.ptr(tg),
+                                         native.ptr(nz), float(sigma), n, native.ptr(out_p), viol.data_ptr(),
+                                         err.data_ptr(), cons.data_ptr(), native.current_stream()))
+        return {"params_norm": out_p, "violations": viol, "recon_error": err, "consistency": cons}
+
+
+def topk_smallest(scores: torch.Tensor, k: int, index_base: int = 0, in_indices: Optional[torch.Tensor] = None):
+    """k smallest scores (ascending) and their indices, on the device (csrc/topk.cu)."""
+    _require_cuda(scores, "scores")
+    s = _f32c(scores).reshape(-1)
+    n = s.numel()
+    nbytes = lib.pigan_topk_workspace_bytes(n, k)
+    if nbytes == 0:
+        raise native.PiganError(-1, f"k={k} out of range (1..4096)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=s.device)
+    out_s = torch.empty(k, device=s.device, dtype=torch.float32)
+    out_i = torch.empty(k, device=s.device, dtype=torch.int64)
+    idx = in_indices.contiguous() if in_indices is not None else None
+    check(lib.pigan_topk_smallest(s.data_ptr(), native.ptr(idx), n, k, int(index_base), out_s.data_ptr(),
+                                  out_i.data_ptr(), ws.data_ptr(), nbytes, native.current_stream()))
+    return out_s, out_i
+
+
+_ENGINES: Dict[int, Engine] = {}
+
+
+def get_engine(device, min_batch: int) -> Engine:
+    """Process-wide engine per device, grown (re-created) when a larger batch shows up."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    eng = _ENGINES.get(idx)
+    if eng is None or eng.max_batch < min_batch:
+        cap = max(int(min_batch), 1024)
+        if eng is not None:
+            cap = max(cap, 2 * eng.max_batch)
+        eng = Engine(cap, torch.device("cuda", idx))
+        _ENGINES[idx] = eng
+    return eng

@@ -50,6 +50,21 @@ class PiganDims(C.Structure):
     ]
 
 
+class PiganTrainArgs(C.Structure):
+    _fields_ = [
+        ("spectrum", _vp), ("params_denorm", _vp), ("metrics_norm", _vp),
+        ("batch", _i64), ("global_batch", _i64),
+        ("g_params", _vp), ("g_grads", _vp), ("g_exp_avg", _vp), ("g_exp_avg_sq", _vp),
+        ("g_bn_buffers", _vp), ("g_num_batches_tracked", _vp),
+        ("d_params", _vp), ("d_grads", _vp), ("d_exp_avg", _vp), ("d_exp_avg_sq", _vp),
+        ("lr_g", _f32), ("lr_d", _f32), ("step", _i64),
+        ("lambda_recon", _f32), ("lambda_physics_spectrum", _f32), ("lambda_physics_metrics", _f32),
+        ("lambda_maxwell", _f32), ("lambda_lc", _f32), ("lambda_param_range", _f32), ("lambda_bnn_kl", _f32),
+        ("f1_idx", _i32), ("f2_idx", _i32),
+        ("losses", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/pigan_b200.h declares must appear here
 SIGNATURES = {
     "pigan_abi_version": (_i32, []),
@@ -59,6 +74,21 @@ SIGNATURES = {
     "pigan_discriminator_param_count": (_i64, [C.POINTER(PiganDims)]),
     "pigan_forward_model_param_count": (_i64, [C.POINTER(PiganDims)]),
     "pigan_generator_bn_buffer_count": (_i64, [C.POINTER(PiganDims)]),
+    "pigan_engine_workspace_bytes": (C.c_size_t, [C.POINTER(PiganDims), _i64]),
+    "pigan_engine_create": (_i32, [C.POINTER(_vp), C.POINTER(PiganDims), _i64, _vp, C.c_size_t, _vp]),
+    "pigan_engine_destroy": (_i32, [_vp]),
+    "pigan_engine_load_forward_model": (_i32, [_vp, _vp, _vp]),
+    "pigan_generator_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "pigan_discriminator_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "pigan_forward_model_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "pigan_train_step": (_i32, [_vp, C.POINTER(PiganTrainArgs), _vp]),
+    "pigan_train_step_phase": (_i32, [_vp, C.POINTER(PiganTrainArgs), _i32, _vp]),
+    "pigan_engine_bn_sums": (_vp, [_vp]),
+    "pigan_engine_bn_bwd_sums": (_vp, [_vp]),
+    "pigan_engine_loss_sums": (_vp, [_vp]),
+    "pigan_score_candidates": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pigan_topk_workspace_bytes": (C.c_size_t, [_i64, _i32]),
+    "pigan_topk_smallest": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
     "pigan_debug_gemm_tn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "pigan_debug_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -1,0 +1,111 @@
+"""Native PI-GAN trainer state: flat parameter / gradient / Adam buffers, the C-ABI argument block and the
+data-parallel phase schedule.  Used by the drop-in ``core.train.train_pigan.train_pigan`` and by bench.py.
+
+Reference semantics reproduced (core/train/train_pigan.py:114-187): one D-step then one G-step per batch,
+label smoothing 0.9/0.1 (D) and 1.0 (G), frozen forward surrogate, the weighted loss of :174-181,
+clip_grad_norm_(1.0), Adam(betas=(0.5, 0.999)); BatchNorm running statistics advance twice per step (F8).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import engine as _engine
+from . import flat as _flat
+from . import native
+
+LOSS_KEYS = _engine.LOSS_KEYS
+
+
+class NativeTrainer:
+    def __init__(self, generator, discriminator, forward_model, device, max_batch: int, cfg=None,
+                 f1_idx: int = 0, f2_idx: int = 1, process_group=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("NativeTrainer needs a CUDA device — the B200 path has no CPU fallback")
+        self.g, self.d, self.f = generator, discriminator, forward_model
+        for m in (generator, discriminator, forward_model):
+            m.to(self.device)
+        self.gs = _flat.net_state(generator, "generator")
+        self.ds = _flat.net_state(discriminator, "discriminator")
+        self.fs = _flat.net_state(forward_model, "forward_model")
+        self.engine = _engine.Engine(max_batch, self.device)
+        self.engine.load_forward_model(self.fs.params.tensor())
+        gp, dp = self.gs.params.tensor(), self.ds.params.tensor()
+        self.g_grads, self.g_m, self.g_v = (torch.zeros_like(gp) for _ in range(3))
+        self.d_grads, self.d_m, self.d_v = (torch.zeros_like(dp) for _ in range(3))
+        self.losses = torch.zeros(9, device=self.device, dtype=torch.float32)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        lam = dict(lambda_recon=100.0, lambda_physics_spectrum=10.0, lambda_physics_metrics=1.0, lambda_maxwell=1.0,
+                   lambda_lc=1.0, lambda_param_range=0.1, lambda_bnn_kl=0.0)
+        if cfg is not None:
+            lam = dict(lambda_recon=cfg.LAMBDA_RECON, lambda_physics_spectrum=cfg.LAMBDA_PHYSICS_SPECTRUM,
+                       lambda_physics_metrics=cfg.LAMBDA_PHYSICS_METRICS, lambda_maxwell=cfg.LAMBDA_MAXWELL,
+                       lambda_lc=cfg.LAMBDA_LC, lambda_param_range=cfg.LAMBDA_PARAM_RANGE,
+                       lambda_bnn_kl=cfg.LAMBDA_BNN_KL)
+        self.lam = lam
+        self.f1_idx, self.f2_idx = int(f1_idx), int(f2_idx)
+        # expose gradients on the parameters the way autograd would (views of the flat buffers)
+        for p, gview in zip(self.gs.params._tensors(), self.gs.params.views_like(self.g_grads)):
+            p.grad = gview
+        for p, gview in zip(self.ds.params._tensors(), self.ds.params.views_like(self.d_grads)):
+            p.grad = gview
+
+    # ------------------------------------------------------------------
+    def _args(self, spectrum, params_denorm, metrics_norm, lr_g, lr_d):
+        gp, dp = self.gs.params.tensor(), self.ds.params.tensor()
+        B = spectrum.shape[0]
+        return self.engine.make_train_args(
+            spectrum=spectrum.data_ptr(), params_denorm=params_denorm.data_ptr(), metrics_norm=metrics_norm.data_ptr(),
+            batch=B, global_batch=B * self.world,
+            g_params=gp.data_ptr(), g_grads=self.g_grads.data_ptr(), g_exp_avg=self.g_m.data_ptr(),
+            g_exp_avg_sq=self.g_v.data_ptr(), g_bn_buffers=self.gs.bn.tensor().data_ptr(),
+            g_num_batches_tracked=self.gs.nbt.tensor().data_ptr(),
+            d_params=dp.data_ptr(), d_grads=self.d_grads.data_ptr(), d_exp_avg=self.d_m.data_ptr(),
+            d_exp_avg_sq=self.d_v.data_ptr(),
+            lr_g=float(lr_g), lr_d=float(lr_d), step=self.step_count,
+            f1_idx=self.f1_idx, f2_idx=self.f2_idx, losses=self.losses.data_ptr(), **self.lam)
+
+    def step(self, spectrum, params_denorm, metrics_norm, lr_g: float, lr_d: float) -> torch.Tensor:
+        """One D-step + G-step on device-resident fp32 tensors.  Returns the [9] device tensor of losses
+        (loss_history order); no host synchronisation happens here."""
+        for t, name in ((spectrum, "spectrum"), (params_denorm, "params_denorm"), (metrics_norm, "metrics_norm")):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError(f"NativeTrainer.step: {name} must be a contiguous fp32 CUDA tensor")
+        self.step_count += 1
+        args = self._args(spectrum, params_denorm, metrics_norm, lr_g, lr_d)
+        if self.world == 1:
+            self.engine.train_step(args)
+            return self.losses
+        # data-parallel schedule: the engine's phases with NCCL all-reduces of the batch-coupled sums between
+        # them (BatchNorm forward/backward statistics, gradients, loss sums) — include/pigan_b200.h
+        e = self.engine
+        h1, h2 = e.dims.g_hidden[0], e.dims.g_hidden[1]
+        bn, bnb, ls = e.bn_sums(), e.bn_bwd_sums(), e.loss_sums()
+        e.train_step_phase(args, 0)
+        dist.all_reduce(bn[:2 * h1], group=self.pg)
+        e.train_step_phase(args, 1)
+        dist.all_reduce(bn[2 * h1:], group=self.pg)
+        e.train_step_phase(args, 2)
+        dist.all_reduce(self.d_grads, group=self.pg)
+        e.train_step_phase(args, 3)
+        dist.all_reduce(bnb[:2 * h2], group=self.pg)
+        e.train_step_phase(args, 4)
+        dist.all_reduce(bnb[2 * h2:], group=self.pg)
+        e.train_step_phase(args, 5)
+        dist.all_reduce(self.g_grads, group=self.pg)
+        dist.all_reduce(ls[:8], group=self.pg)
+        e.train_step_phase(args, 6)
+        return self.losses
+
+    # ------------------------------------------------------------------ optimiser state for checkpoints
+    def export_optimizer_state(self, optimizer_g, optimizer_d) -> None:
+        """Fill torch.optim.Adam state dicts (step / exp_avg / exp_avg_sq per parameter) with views of the flat
+        moment buffers so optimizer.state_dict() matches what the reference checkpoints (train_pigan.py:287-294)."""
+        for opt, st, m, v in ((optimizer_g, self.gs, self.g_m, self.g_v), (optimizer_d, self.ds, self.d_m, self.d_v)):
+            for p, mv, vv in zip(st.params._tensors(), st.params.views_like(m), st.params.views_like(v)):
+                opt.state[p] = {"step": torch.tensor(float(self.step_count)), "exp_avg": mv, "exp_avg_sq": vv}
