@@ -1,0 +1,174 @@
+"""Pins the oracle (oracle/*.py, oracle/physics.c) against outputs of the reference itself (tests/golden/*.npz,
+made by tools/make_golden.py running /root/reference).  CPU only."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures
+from oracle import models as O
+from oracle import physics as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def _close(a, b, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------------------------------------ physics
+def test_physics_thz_trace_matches_reference():
+    g = _load("physics.npz")
+    f, t, i = g["thz_freq"], g["thz_t"], int(g["thz_idx"])
+    assert i == 79                                        # SURVEY 8(c) golden vector
+    out = P.peak_parameters(f, t, i)
+    np.testing.assert_array_equal(np.array(out), g["thz_out"])
+    _close(g["thz_out"], [0.85549998283386, 10.776454947437596, 0.4265215225838956], rtol=1e-14, atol=0)
+
+
+def test_physics_reference_generator_vector():
+    """np.random.seed(42); generate_single_terahertz_spectrum_and_params(...) from the survey."""
+    g = _load("physics.npz")
+    freq = np.linspace(0.5, 3.0, 250)
+    t = g["gen_spectrum"]
+    i = int(np.argmin(t))
+    assert i == 37
+    f1, q1, fom1 = P.peak_parameters(freq, t, i)
+    m = g["gen_metrics"]                                  # f1, f2, Q1, FoM1, S1, Q2, FoM2, S2
+    _close([f1, q1, fom1, P.sensitivity(f1, q1)], [m[0], m[2], m[3], m[4]], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("which", ["argmin", "given"])
+def test_physics_batch_python_and_c_match_reference(which):
+    g = _load("physics.npz")
+    spec, _, _, _ = fixtures.make_batch(256, seed=11)
+    spec = spec.numpy()
+    freq = np.linspace(0.5, 3.0, 250)
+    if which == "argmin":
+        pk, base, ref_idx, ref = None, 0.0, g["batch_idx"], g["batch_out"]
+    else:
+        pk, base, ref_idx, ref = g["batch_idx2"], -0.5, g["batch_idx2"], g["batch_out2"]
+    for fn in (P.physics_rows_python, P.physics_batch):
+        idx, out = fn(spec, freq, pk, base)
+        assert np.array_equal(idx, ref_idx)
+        np.testing.assert_array_equal(np.isnan(out[:, :3]), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        _close(out[:, :3][ok], ref[ok], rtol=1e-13, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ models
+def test_forward_passes_match_reference():
+    g = _load("forward.npz")
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(64, seed=7)
+    with torch.no_grad():
+        _close(O.generator_forward(copy.deepcopy(g_sd), spec, False).numpy(), g["g_eval"])
+        sd = copy.deepcopy(g_sd)
+        _close(O.generator_forward(sd, spec, True).numpy(), g["g_train"], rtol=2e-5, atol=2e-6)
+        for k in ("main.1.running_mean", "main.1.running_var", "main.4.running_mean", "main.4.running_var"):
+            _close(sd[k].numpy(), g["g_after_" + k])
+        assert int(sd["main.1.num_batches_tracked"]) == int(g["g_after_main.1.num_batches_tracked"]) == 4
+        _close(O.discriminator_forward(d_sd, spec, praw).numpy(), g["d_out"])
+        fs, fm = O.forward_model_forward(f_sd, pnorm)
+        _close(fs.numpy(), g["f_spec"], rtol=2e-5, atol=2e-5)
+        _close(fm.numpy(), g["f_metrics"], rtol=2e-5, atol=2e-5)
+        _close(O.denormalize_params(pnorm).numpy(), g["denorm"], rtol=0, atol=0)
+        _close(O.maxwell_equation_loss(fs), g["loss_maxwell"])
+        _close(O.lc_model_approx_loss(fm[:, 0:1], fm[:, 1:2], pnorm), g["loss_lc"])
+        _close(O.structural_param_range_loss(pnorm * 1.3), g["loss_range"])
+        _close(O.bce(O.discriminator_forward(d_sd, spec, praw), torch.full((64, 1), 0.9)), g["loss_bce"])
+        _close(O.mse(fs, spec), g["loss_mse"])
+
+
+def _batches(n, B, seed0):
+    out = []
+    for i in range(n):
+        spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=seed0 + i)
+        out.append((spec, praw, pnorm, None, mnorm))
+    return out
+
+
+def test_train_step_matches_reference_single_step():
+    """The oracle's D-step + G-step vs train_pigan itself (1 epoch x 1 batch): losses, raw gradients, weights."""
+    torch.set_num_threads(1)
+    g = _load("train_step.npz")
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    lr_g, lr_d = O.lr_generator(0, 1, 2e-4), O.lr_discriminator(0, 1, 2e-4)
+    losses, ex = O.train_step(g_sd, d_sd, f_sd, og, od, _batches(1, 64, 100)[0], lr_g, lr_d)
+    for k, v in losses.items():
+        _close(v, g["a_" + k][0], rtol=2e-5, atol=1e-7)
+    for tag, grads in (("g", ex["g_grads"]), ("d", ex["d_grads"])):
+        for name, gr in grads.items():
+            ref = g[f"a_grad_{tag}_{name}"]
+            got = gr.reshape(-1)[fixtures.sample_indices(gr.numel())].numpy()
+            scale = float(g[f"a_gradnorm_{tag}_{name}"]) / np.sqrt(gr.numel()) + 1e-12
+            assert np.max(np.abs(got - ref)) <= 2e-4 * scale + 1e-9, (tag, name)
+            _close(gr.norm().item(), g[f"a_gradnorm_{tag}_{name}"], rtol=1e-4, atol=1e-9)
+    # the survey's structural facts (F2, F8): BN stepped twice, biases before BN get ~zero gradient
+    assert int(g_sd["main.1.num_batches_tracked"]) == 3 + 2
+    assert float(g["a_gradnorm_g_main.0.bias"]) < 1e-6
+    for tag, sd in (("g", g_sd), ("d", d_sd)):
+        for name, t in sd.items():
+            ref = g[f"a_final_{tag}_{name}"]
+            got = t.reshape(-1)[fixtures.sample_indices(t.numel())].double().numpy()
+            # Adam's first step moves every weight by ~lr * sign(g): compare in units of lr
+            assert np.max(np.abs(got - ref)) <= 0.02 * 2e-4 + 1e-6 * np.max(np.abs(ref)), (tag, name)
+
+
+def test_train_loop_matches_reference_three_epochs():
+    """Schedulers (cosine / step), Adam bias correction over 6 steps, BatchNorm momentum: epoch-mean losses."""
+    torch.set_num_threads(1)
+    g = _load("train_step.npz")
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    batches = _batches(2, 64, 200)
+    hist = {k: [] for k in ("d_losses", "g_losses", "adv_losses", "recon_spec_losses", "lc_losses")}
+    for epoch in range(3):
+        acc = {k: 0.0 for k in hist}
+        for b in batches:
+            losses, _ = O.train_step(g_sd, d_sd, f_sd, og, od, b, O.lr_generator(epoch, 3, 2e-4),
+                                     O.lr_discriminator(epoch, 3, 2e-4))
+            for k in acc:
+                acc[k] += losses[k]
+        for k in acc:
+            hist[k].append(acc[k] / len(batches))
+    for k, v in hist.items():
+        _close(v, g["b_" + k], rtol=5e-4, atol=1e-6)
+    assert int(g_sd["main.4.num_batches_tracked"]) == 3 + 12
+    _close(g_sd["main.1.running_mean"].reshape(-1)[fixtures.sample_indices(512)].numpy(),
+           g["b_final_g_main.1.running_mean"], rtol=1e-3, atol=1e-4)
+
+
+def test_lr_schedules_match_torch():
+    import torch.optim as optim
+    from torch.optim.lr_scheduler import CosineAnnealingLR, StepLR
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    for T in (1, 3, 8, 500):
+        og, od = optim.Adam(p, lr=2e-4), optim.Adam(p, lr=2e-4)
+        sg, sd = CosineAnnealingLR(og, T_max=T, eta_min=2e-6), StepLR(od, step_size=max(1, T // 4), gamma=0.5)
+        for e in range(min(T, 12)):
+            _close(og.param_groups[0]["lr"], O.lr_generator(e, T, 2e-4), rtol=1e-12, atol=0)
+            _close(od.param_groups[0]["lr"], O.lr_discriminator(e, T, 2e-4), rtol=1e-12, atol=0)
+            og.step(); od.step(); sg.step(); sd.step()
+
+
+def test_scoring_matches_reference_evaluator():
+    g = _load("scoring.npz")
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    spec, _, _, _ = fixtures.make_batch(96, seed=31)
+    p, viol, err, cons = O.score_candidates(g_sd, f_sd, spec)
+    _close(p.numpy(), g["params"])
+    assert np.array_equal(viol.numpy(), g["violations"])
+    _close(err.numpy(), g["recon_error"], rtol=2e-5)
+    _close(cons.numpy(), g["consistency"], rtol=2e-5)
+    # aggregates printed by UnifiedEvaluator.evaluate_structural_prediction itself
+    _close((viol > 0).float().mean(), g["agg_param_range_violation_rate"])
+    _close(err.mean(), g["agg_reconstruction_error_mean"], rtol=1e-5)
+    _close(cons.numpy().std(), g["agg_consistency_score_std"], rtol=1e-4)

@@ -1,0 +1,186 @@
+"""Generates tests/golden/*.npz by running the REAL reference (/root/reference) on CPU.
+
+Run in the build container only (the reference is not present on the GPU box):
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+Weights and batches come from oracle/fixtures.py (numpy PCG64), so tests rebuild the same inputs and only
+outputs are stored.  What is pinned:
+  physics.npz      calculate_peak_parameters on dataset/THZ.txt, on the reference's own synthetic generator
+                   (np.random.seed(42)) and on 256 synthetic rows at their argmin
+  forward.npz      Generator (eval + train incl. BatchNorm buffer updates), Discriminator, ForwardModel outputs,
+                   denormalize_params, the six loss functions
+  train_step.npz   core.train.train_pigan.train_pigan itself: 1 epoch x 1 batch (per-step losses, raw gradients
+                   captured with hooks) and 3 epochs x 2 batches (schedulers, Adam t>1, BN momentum), sampled
+  scoring.npz      the evaluator loop (unified_evaluator.py:369-392) through UnifiedEvaluator itself with the
+                   plotting modules stubbed out
+"""
+import os
+import sys
+import tempfile
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.gridspec", "seaborn"):
+    sys.modules[mod] = MagicMock()
+
+import config.config as cfg  # reference config
+from core.models.generator import Generator
+from core.models.discriminator import Discriminator
+from core.models.forward_model import ForwardModel
+from core.utils import data_loader as ref_dl
+from core.utils import loss as ref_loss
+from core.train import train_pigan as ref_train
+
+from oracle import fixtures
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(1)  # fixed reduction order
+
+
+def ref_models(seed=42):
+    g_sd, d_sd, f_sd = fixtures.make_weights(seed)
+    G = Generator(250, 4); D = Discriminator(250, 4); F = ForwardModel(4, 250, 8)
+    G.load_state_dict(g_sd); D.load_state_dict(d_sd); F.load_state_dict(f_sd)
+    return G, D, F
+
+
+def physics():
+    rows = [l.split() for l in open(os.path.join(REF, "dataset", "THZ.txt"))
+            if l.strip() and l.split()[0].replace(".", "", 1).isdigit()]
+    a = np.array(rows, float)
+    f, t = a[:, 0], a[:, 1]
+    i = int(np.argmin(t))
+    thz = ref_dl.calculate_peak_parameters(f, t, i)
+    np.random.seed(42)
+    freq = np.linspace(0.5, 3.0, 250)
+    gen = ref_dl.generate_single_terahertz_spectrum_and_params(freq, 2.5, 2.5, 2.5, 2.5)
+    spec, _, _, _ = fixtures.make_batch(256, seed=11)
+    spec = spec.numpy()
+    idx = np.argmin(spec, axis=1)
+    out = np.array([ref_dl.calculate_peak_parameters(freq, spec[r].astype(np.float64), int(idx[r])) for r in range(256)])
+    # arbitrary peak indices and a non-zero baseline exercise the other branches
+    rng = np.random.Generator(np.random.PCG64(5))
+    idx2 = rng.integers(0, 250, size=256)
+    out2 = np.array([ref_dl.calculate_peak_parameters(freq, spec[r].astype(np.float64), int(idx2[r]), -0.5)
+                     for r in range(256)])
+    np.savez(os.path.join(OUT, "physics.npz"), thz_freq=f, thz_t=t, thz_idx=i, thz_out=np.array(thz),
+             gen_spectrum=gen[0], gen_metrics=np.array(gen[1:], dtype=np.float64),
+             batch_idx=idx.astype(np.int32), batch_out=out, batch_idx2=idx2.astype(np.int32), batch_out2=out2)
+    print("physics: THZ", i, thz)
+
+
+def forward():
+    G, D, F = ref_models()
+    spec, praw, pnorm, mnorm = fixtures.make_batch(64, seed=7)
+    res = {}
+    with torch.no_grad():
+        G.eval(); res["g_eval"] = G(spec).numpy()
+        G.train(); res["g_train"] = G(spec).numpy()
+        for k in ("main.1.running_mean", "main.1.running_var", "main.4.running_mean", "main.4.running_var",
+                  "main.1.num_batches_tracked"):
+            res["g_after_" + k] = G.state_dict()[k].numpy()
+        res["d_out"] = D(spec, praw).numpy()
+        F.eval()
+        fs, fm = F(pnorm)
+        res["f_spec"], res["f_metrics"] = fs.numpy(), fm.numpy()
+        ds = ref_dl.MetamaterialDataset("", load_data=False)
+        res["denorm"] = ref_dl.denormalize_params(pnorm, ds.param_ranges).numpy()
+        res["loss_maxwell"] = ref_loss.maxwell_equation_loss(fs, None, pnorm).numpy()
+        res["loss_lc"] = ref_loss.lc_model_approx_loss(fm[:, 0:1], fm[:, 1:2], pnorm).numpy()
+        res["loss_range"] = ref_loss.structural_param_range_loss(pnorm * 1.3).numpy()
+        res["loss_bce"] = ref_loss.criterion_bce()(D(spec, praw), torch.full((64, 1), 0.9)).numpy()
+        res["loss_mse"] = ref_loss.criterion_mse()(fs, spec).numpy()
+    np.savez(os.path.join(OUT, "forward.npz"), **res)
+    print("forward: g_eval[0]", res["g_eval"][0])
+
+
+def train_step():
+    res = {}
+    tmp = tempfile.mkdtemp()
+    cfg.CHECKPOINT_DIR = os.path.join(tmp, "ckpt")
+    cfg.SAVED_MODELS_DIR = os.path.join(tmp, "saved")
+    ds = ref_dl.MetamaterialDataset("", load_data=False)
+
+    def batches(n_batches, B, seed0):
+        out = []
+        for i in range(n_batches):
+            spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=seed0 + i)
+            out.append((spec, praw, pnorm, torch.zeros(B, 8), mnorm))
+        return out
+
+    # (a) one epoch, one batch: exact per-step losses + raw (unclipped) gradients through hooks
+    G, D, F = ref_models()
+    grads = {"g": {}, "d": {}}
+    for tag, net in (("g", G), ("d", D)):
+        for name, p in net.named_parameters():
+            def hook(gr, tag=tag, name=name):
+                if name not in grads[tag]:          # first call = D-step for D params, G-step for G params
+                    grads[tag][name] = gr.detach().clone()
+                return None
+            p.register_hook(hook)
+    hist = ref_train.train_pigan(batches(1, 64, 100), torch.device("cpu"), G, D, F, ds, num_epochs=1, log_interval=10)
+    for k, v in hist.items():
+        res["a_" + k] = np.array(v, dtype=np.float64)
+    for tag in ("g", "d"):
+        for name, gr in grads[tag].items():
+            res[f"a_grad_{tag}_{name}"] = gr.reshape(-1)[fixtures.sample_indices(gr.numel())].numpy()
+            res[f"a_gradnorm_{tag}_{name}"] = np.array(gr.norm().item())
+    for tag, net in (("g", G), ("d", D)):
+        for name, t in net.state_dict().items():
+            tt = t.reshape(-1).double() if t.is_floating_point() else t.reshape(-1)
+            res[f"a_final_{tag}_{name}"] = tt[fixtures.sample_indices(tt.numel())].numpy()
+
+    # (b) three epochs, two batches each: LR schedulers, Adam bias correction, BN momentum
+    G, D, F = ref_models()
+    hist = ref_train.train_pigan(batches(2, 64, 200), torch.device("cpu"), G, D, F, ds, num_epochs=3, log_interval=10)
+    for k, v in hist.items():
+        res["b_" + k] = np.array(v, dtype=np.float64)
+    for tag, net in (("g", G), ("d", D)):
+        for name, t in net.state_dict().items():
+            tt = t.reshape(-1).double() if t.is_floating_point() else t.reshape(-1)
+            res[f"b_final_{tag}_{name}"] = tt[fixtures.sample_indices(tt.numel())].numpy()
+    np.savez(os.path.join(OUT, "train_step.npz"), **res)
+    print("train_step: a losses", {k: v for k, v in res.items() if k.startswith("a_") and k.endswith("losses")})
+
+
+def scoring():
+    from torch.utils.data import Dataset
+    import core.evaluate.unified_evaluator as ue
+
+    G, D, F = ref_models()
+    G.eval(); F.eval()
+    spec, praw, pnorm, mnorm = fixtures.make_batch(96, seed=31)
+
+    class DS(Dataset):
+        param_ranges = {k: (2.2, 2.8) for k in ("r1", "r2", "w", "g")}
+        def __len__(self): return spec.shape[0]
+        def __getitem__(self, i): return spec[i], praw[i], pnorm[i], torch.zeros(8), mnorm[i]
+
+    ev = ue.UnifiedEvaluator.__new__(ue.UnifiedEvaluator)
+    ev.device = torch.device("cpu"); ev.generator = G; ev.forward_model = F; ev.discriminator = D; ev.dataset = DS()
+    np.random.seed(0)
+    agg = ev.evaluate_structural_prediction(num_samples=96)   # all 96 rows, permuted
+    res = {"agg_" + k: np.array(v, dtype=np.float64) for k, v in agg.items()}
+    with torch.no_grad():  # per-row values of the same loop body (:376-392)
+        p = G(spec)
+        res["params"] = p.numpy()
+        res["violations"] = torch.sum((p < 0) | (p > 1), dim=1).numpy()
+        rec, _ = F(p)
+        err = torch.mean((spec - rec) ** 2, dim=1)
+        res["recon_error"] = err.numpy()
+        res["consistency"] = (1.0 / (1.0 + err)).numpy()
+    np.savez(os.path.join(OUT, "scoring.npz"), **res)
+    print("scoring:", {k: float(v) for k, v in agg.items()})
+
+
+if __name__ == "__main__":
+    physics(); forward(); train_step(); scoring()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
