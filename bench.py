@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the PI-GAN-THz hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B]
+
+Native arm: one "step" is one D-step + G-step of train_pigan's inner loop (core/train/train_pigan.py:114-187) at
+batch B per GPU (default 65 536 = BASELINE config 2) on synthetic spectra of the dataset's shape, through the C ABI
+(libpigan_b200.so).  `value` = samples/s with the batch resident in HBM; `e2e` = the same step fed from pinned HOST
+buffers (H2D of the batch and D2H of the 9 losses inside the timed region).  The JSON line also carries the
+inverse-design scoring throughput (candidates/s, `scoring`), the roofline of the dominant kernel measured with CUDA
+events inside the timed region, a CPU baseline (the oracle port of the reference step on the host cores) and the
+clocks seen during the timed region.
+
+Reference arm (--impl reference): the reference's CPU PyTorch path — restated in oracle/models.py and pinned to the
+reference itself by tests/golden — timed on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pi-gan-thz_b200"))
+
+import torch
+
+# algorithmic work per unit: minimal necessary FLOPs
+FLOP_PER_TRAIN_SAMPLE = 7_465_984
+FLOP_PER_CANDIDATE = 3_275_776
+METRIC = "PI-GAN train samples/s"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": p.get("bf16_tflops_sustained", 1402.9), "tflops_burst": p.get("bf16_tflops", 1666.8),
+                "hbm_gbs": p.get("hbm_gbs", 6537.6), "source": "measured"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = sorted(sm)[len(sm) // 2:]           # upper half = samples under load
+        return {"sm_mhz": sorted(hi)[len(hi) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arms
+def cpu_train_baseline(batch: int, budget_s: float, threads: int):
+    """The oracle port of the reference train step (oracle/models.py, pinned to the reference by tests/golden)
+    on the host cores: returns (samples/s, steps timed)."""
+    from oracle import fixtures
+    from oracle import models as O
+    torch.set_num_threads(threads)
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(batch, seed=11)
+    b = (spec, praw, pnorm, None, mnorm)
+    O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)        # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 200:
+            break
+    return batch * n / el, n, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample per step."""
+    from oracle import fixtures
+    from oracle import models as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 4096
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(sample, seed=11)
+    b = (spec, praw, pnorm, None, mnorm)
+    steps = max(1, min(args.steps, 20))
+    for _ in range(max(1, min(args.warmup, 3))):
+        O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
+    el = time.perf_counter() - t0
+    v = sample * steps / el
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate), batch {args.batch} per GPU, "
+                               "S=250, reference widths", "sample_batch": sample},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of batch {sample} (oracle/models.py train_step, fp32, torch CPU)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch.distributed as dist
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from pigan_b200 import engine as E
+    from pigan_b200 import flat, scoring, synthetic
+    from pigan_b200.trainer import NativeTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+    peaks = read_peaks()
+
+    torch.manual_seed(42)
+    G, D, F = Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)
+    F.eval()
+    tr = NativeTrainer(G, D, F, dev, max_batch=B)
+    # inputs larger than L2: NSETS distinct batches (NSETS * 68.7 MB at B=65536 > 126 MB L2), rotated per step
+    NSETS = 4
+    sets = []
+    for i in range(NSETS):
+        sp, pr, _pn, mn = synthetic.make_batch(B, 250, seed=1000 * rank + i, device=dev)
+        sets.append((sp, pr, mn))
+    lr = 2e-4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        tr.step(*sets[i % NSETS], lr, lr)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, dominant kernel bracketed by events on the launch stream
+    DOMINANT = "f_hidden_gemm"
+    clocks = ClockSampler(local)
+    clocks.start()
+    tr.engine.profile_begin([DOMINANT])
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        tr.step(*sets[i % NSETS], lr, lr)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = E.launch_count() - l0
+    prof = tr.engine.profile_end()
+    clk = clocks.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * K / (ms * 1e-3)
+    losses = tr.losses.tolist()
+
+    # dominant kernel: the 4 hidden-layer GEMMs of the frozen surrogate (256->512->1024->512->256), 1 245 184 MAC/row
+    dom_cnt, dom_ms = prof.get(DOMINANT, (0, 0.0))
+    dom_flop_per_launch = 2 * (256 * 512 + 512 * 1024 + 1024 * 512 + 512 * 256) * B / 4.0
+    roof = None
+    if dom_cnt:
+        ach = dom_flop_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiStore> (forward-surrogate hidden layers)",
+                "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
+    step_tflops = FLOP_PER_TRAIN_SAMPLE * B * K / (ms * 1e-3) / 1e12
+
+    # ---- timed region 2: end to end from pinned host buffers through the public API (NativeTrainer.step)
+    host = []
+    for sp, pr, mn in sets:
+        host.append(tuple(x.cpu().pin_memory() for x in (sp, pr, mn)))
+    dbuf = [tuple(torch.empty_like(x) for x in sets[0]) for _ in range(2)]
+    loss_host = torch.empty(K, 9, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def h2d(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            for d, h in zip(dbuf[slot], host[i % NSETS]):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n, out):
+        for s in range(2):
+            freed[s].record(main)
+        h2d(0)
+        for i in range(n):
+            if i + 1 < n:
+                h2d(i + 1)
+            slot = i % 2
+            main.wait_event(ready[slot])
+            ls = tr.step(*dbuf[slot], lr, lr)
+            freed[slot].record(main)
+            out[i].copy_(ls, non_blocking=True)
+
+    e2e_loop(min(3, K), loss_host)
+    barrier()
+    e0.record()
+    e2e_loop(K, loss_host)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t.item())
+    h2d_bytes = sum(x.numel() * 4 for x in sets[0])
+    e2e = {"value": B * world * K / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": 36, "ms_per_step": ms2 / K}
+
+    # ---- inverse-design scoring (BASELINE config 4): candidates/s, sharded by candidate, final top-k gather
+    G.eval()
+    gs = flat.net_state(G, "generator")
+    chunk = min(B, 1 << 16)
+    designer = scoring.InverseDesigner(tr.engine, gs.params.tensor(), gs.bn.tensor(), chunk=chunk)
+    target = sets[0][0][0].clone()
+    n_cand = args.candidates * world
+    designer.search(target, 4 * chunk * world, k=1024)
+    barrier()
+    e0.record()
+    res = designer.search(target, n_cand, k=1024)
+    e1.record()
+    barrier()
+    ms3 = e0.elapsed_time(e1)
+    t = torch.tensor([ms3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms3 = float(t.item())
+    cand_s = n_cand / (ms3 * 1e-3)
+    score_info = {"metric": "inverse-design candidates/s", "value": cand_s, "unit": "candidates/s",
+                  "candidates": n_cand, "k": 1024, "ms": ms3, "best_recon_error": float(res["recon_error"][0]),
+                  "tensor_frac": cand_s * FLOP_PER_CANDIDATE / 1e12 / (peaks["tflops"] * world),
+                  "noise": "torch.randn per chunk (explicit noise tensor, SURVEY H7)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, n, el = cpu_train_baseline(4096, 12.0, cores)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{n} steps of batch 4096 in {el:.1f} s (oracle/models.py train_step, fp32, torch CPU)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
+            "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate, 7 losses, clip+Adam), "
+                                   f"batch {B} per GPU, S=250, reference widths",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": f"{NSETS} distinct input batches rotated ({NSETS * h2d_bytes / 1e6:.0f} MB > 126 MB L2)"},
+            "roofline": roof,
+            "step_roofline": {"bound": "tensor", "achieved": step_tflops / world, "peak": peaks["tflops"],
+                              "unit": "TFLOP/s", "frac": step_tflops / world / peaks["tflops"],
+                              "flop_per_sample": FLOP_PER_TRAIN_SAMPLE},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "scoring": score_info,
+            "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--candidates", type=int, default=1 << 23, help="candidates per GPU for the scoring line")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,10 @@ int pigan_abi_version(void);
 /* Thread-local, valid until the next failing call on the same thread. */
 const char* pigan_last_error(void);
 
+/* Number of CUDA kernels this library has launched in the calling process (all engines, all streams):
+ * bench.py reports the difference across its timed region as gpu_launches. */
+int64_t pigan_launch_count(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Network dimensions.  Defaults are the reference's hard-coded widths
  * (core/models/generator.py:17-26, discriminator.py:21-28, forward_model.py:28-60, config/config.py:38-55).
@@ -88,6 +92,13 @@ int pigan_engine_destroy(PiganEngine* engine);
 /* Frozen forward surrogate: packs fp16 operand copies of model.{4,8,12,16,20}.weight once
  * (forward_model_pretrained.pth layout, pretrain_fwd_model.py:148-150; train_pigan.py:374-377). */
 int pigan_engine_load_forward_model(PiganEngine* engine, const float* f_params, void* stream);
+
+/* Spectra are centred on a constant row before the fp16 cast of the first-layer operand (the shift is undone
+ * exactly, in fp32, through the layer's effective bias).  By default each call centres on the mean of its first
+ * rows.  Data-parallel training must use ONE row on all ranks — the BatchNorm sums the ranks exchange are sums of
+ * the centred pre-activations — so the host sets it here: center [S] fp32 device memory that stays valid while
+ * set; NULL restores the default. */
+int pigan_engine_set_spectrum_center(PiganEngine* engine, const float* center);
 
 /* Generator.forward (core/models/generator.py:28-33).  training != 0: BatchNorm uses batch statistics
  * and updates bn_buffers / num_batches_tracked (one update); training == 0: running statistics.
@@ -151,6 +162,14 @@ int pigan_train_step_phase(PiganEngine* engine, const PiganTrainArgs* args, int3
 float* pigan_engine_bn_sums(PiganEngine* engine);      /* [2*h1 + 2*h2]  sum, sumsq per BatchNorm */
 float* pigan_engine_bn_bwd_sums(PiganEngine* engine);  /* [2*h2 + 2*h1]  sum dy, sum dy*xhat */
 double* pigan_engine_loss_sums(PiganEngine* engine);   /* [16] fp64 */
+
+/* Optional instrumentation (replaces the reference's time.time() ETA bookkeeping, train_pigan.py:113,218, as
+ * the only timing hook): between _begin and _end every engine call records CUDA events on the caller's stream
+ * at the boundaries of its kernel sections.  sections_csv = NULL or "" records all sections, else only the
+ * comma-separated names.  _end synchronises on the recorded events and writes one line per section,
+ * "<name> <count> <total_ms>\n", NUL-terminated, into `report`.  Off by default. */
+int pigan_engine_profile_begin(PiganEngine* engine, const char* sections_csv);
+int pigan_engine_profile_end(PiganEngine* engine, char* report, size_t report_bytes);
 
 /* Inverse-design scoring — loop body of UnifiedEvaluator.evaluate_structural_prediction
  * (core/evaluate/unified_evaluator.py:376-392): G(eval) -> range violations -> F(eval) -> per-candidate

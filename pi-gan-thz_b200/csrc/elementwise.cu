@@ -1,5 +1,7 @@
 #include "elementwise.cuh"
 
+#include "host_util.h"
+
 #include <math.h>
 
 namespace pigan {
@@ -37,6 +39,11 @@ __device__ __forceinline__ void ld_f8(const float* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+__device__ __forceinline__ void zero8(float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+}
+constexpr int kUnroll = 4;  // rows a thread keeps in flight per loop trip in the streaming kernels
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -93,18 +100,18 @@ inline int grid_for_rows(int64_t rows, int rows_per_block, int max_blocks = 148 
 // ------------------------------------------------------------------------------------------ spectrum prep
 __global__ void center_vec_kernel(const float* __restrict__ x, int S, int rows_used, float* __restrict__ cvec,
                                   int Kp) {
-  __shared__ float sm[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 32
   const int col = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (col < S)
-    for (int r = ty; r < rows_used; r += 8) s += x[(size_t)r * S + col];
+    for (int r = ty; r < rows_used; r += 32) s += x[(size_t)r * S + col];
   sm[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && col < Kp) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    for (int k = 0; k < 32; ++k) t += sm[k][tx];
     cvec[col] = col < S ? t / (float)rows_used : 0.f;
   }
 }
@@ -112,7 +119,7 @@ __global__ void center_vec_kernel(const float* __restrict__ x, int S, int rows_u
 template <bool NOISE>
 __global__ void cast_center_kernel(const float* __restrict__ x, const float* __restrict__ noise, float sigma,
                                    const float* __restrict__ cvec, const float* __restrict__ params,
-                                   __half* __restrict__ xc, long long rows, int S, int P, int Kp) {
+                                   __half* __restrict__ xc, long long rows, int S, int P, int Kp, int vec2) {
   const int cpr = Kp >> 3;
   const long long total = rows * cpr;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -120,19 +127,44 @@ __global__ void cast_center_kernel(const float* __restrict__ x, const float* __r
     const long long row = idx / cpr;
     const int j0 = (int)(idx % cpr) * 8;
     float v[8];
+    if (vec2 && j0 + 8 <= S) {
+      // 8-byte vector loads: row pitch S*4 and j0*4 are multiples of 8 (vec2 = even S, 8-byte aligned bases)
+      float c[8];
+      ld_f8(cvec + j0, c);
+      const float2* src = reinterpret_cast<const float2*>((NOISE ? noise : x) + row * S + j0);
+      float2 t[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int j = j0 + i;
-      float t = 0.f;
-      if (j < S) {
-        if (NOISE) t = (x[j] + sigma * noise[row * S + j]) - cvec[j];
-        else t = x[row * S + j] - cvec[j];
-      } else if (j < S + P) {
-        t = params ? params[row * P + (j - S)] - kParamCenter : 0.f;
-      } else if (j < S + P + 2) {
-        t = 1.f;
+      for (int i = 0; i < 4; ++i) t[i] = __ldg(src + i);
+      if (NOISE) {
+        const float2* tg = reinterpret_cast<const float2*>(x + j0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 g = __ldg(tg + i);
+          v[2 * i] = (g.x + sigma * t[i].x) - c[2 * i];
+          v[2 * i + 1] = (g.y + sigma * t[i].y) - c[2 * i + 1];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[2 * i] = t[i].x - c[2 * i];
+          v[2 * i + 1] = t[i].y - c[2 * i + 1];
+        }
       }
-      v[i] = t;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i;
+        float t = 0.f;
+        if (j < S) {
+          if (NOISE) t = (x[j] + sigma * noise[row * S + j]) - cvec[j];
+          else t = x[row * S + j] - cvec[j];
+        } else if (j < S + P) {
+          t = params ? params[row * P + (j - S)] - kParamCenter : 0.f;
+        } else if (j < S + P + 2) {
+          t = 1.f;
+        }
+        v[i] = t;
+      }
     }
     st_h8(xc + row * Kp + j0, v);
   }
@@ -212,14 +244,22 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(const __half* __rest
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < rows; r += (long long)gridDim.x * m.rpb) {
-    float v[8];
-    ld_h8(h + r * C + m.ch * 8, v);
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
+    float v[kUnroll][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += v[i];
-      q[i] = fmaf(v[i], v[i], q[i]);
+    for (int u = 0; u < kUnroll; ++u) {  // independent loads in flight before any use
+      const long long r = r0 + u * stride;
+      if (r < rows) ld_h8(h + r * C + m.ch * 8, v[u]);
+      else zero8(v[u]);
     }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += v[u][i];
+        q[i] = fmaf(v[u][i], v[u][i], q[i]);
+      }
   }
   block_colsum_atomic(s, sum, m, 1.f, sm);
   block_colsum_atomic(q, sumsq, m, 1.f, sm);
@@ -288,9 +328,32 @@ __global__ void __launch_bounds__(kThreads) g_head_fwd_kernel(
     int C, int Kp, int S) {
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  // per-lane constants of the first 256-column slab stay in registers across rows
+  float sc0[8], bi0[8], wa0[8], wb0[8], wc0[8], wd0[8];
+  {
+    const int c = lane * 8;
+    ld_f8(scale + c, sc0);
+    ld_f8(bias + c, bi0);
+    ld_f8(w3 + c, wa0);
+    ld_f8(w3 + C + c, wb0);
+    ld_f8(w3 + 2 * C + c, wc0);
+    ld_f8(w3 + 3 * C + c, wd0);
+  }
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    for (int c = lane * 8; c < C; c += 256) {
+    {
+      float v[8];
+      ld_h8(h2 + row * C + lane * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = fmaxf(fmaf(sc0[i], v[i], bi0[i]), 0.f);
+        d0 = fmaf(a, wa0[i], d0);
+        d1 = fmaf(a, wb0[i], d1);
+        d2 = fmaf(a, wc0[i], d2);
+        d3 = fmaf(a, wd0[i], d3);
+      }
+    }
+    for (int c = 256 + lane * 8; c < C; c += 256) {
       float v[8], sc[8], bi[8], wa[8], wb[8], wc[8], wd[8];
       ld_h8(h2 + row * C + c, v);
       ld_f8(scale + c, sc);
@@ -332,6 +395,13 @@ __global__ void __launch_bounds__(kThreads) g_head_fwd_kernel(
   }
 }
 
+// Generator head backward (tanh, Linear(256,4), ReLU) fused with the BatchNorm-2 backward.  Two passes over h2
+// instead of storing the pre-projection gradient dy in fp16: BatchNorm's backward removes the batch-mean and
+// x-hat components of dy, which here carry most of its norm (the adversarial gradient pushes every sample the
+// same way), so rounding dy before the projection would be amplified in what survives it.
+//   APPLY = false: column sums of dy and dy*xhat, dW3, db3, range-loss sum
+//   APPLY = true : dh = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) -> fp16, db2, dgamma, dbeta
+template <bool APPLY>
 __global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
   __shared__ float sm[kThreads * 8];
   const ColMap m(a.C);
@@ -342,51 +412,95 @@ __global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
   ld_f8(a.rstd + m.ch * 8, rs);
 #pragma unroll
   for (int j = 0; j < 4; ++j) ld_f8(a.w3 + j * a.C + m.ch * 8, w[j]);
-  float dw[4][8], sdy[8], sdyx[8];
+  float dw[4][8], sdy[8], sdyx[8];  // APPLY: sdy accumulates dh (-> db2), sdyx/dw unused
+  float gr[8], m1[8], m2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     sdy[i] = sdyx[i] = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) dw[j][i] = 0.f;
   }
+  if (APPLY) {
+    ld_f8(a.gamma + m.ch * 8, gr);
+    ld_f8(a.sum_dy + m.ch * 8, m1);
+    ld_f8(a.sum_dyx + m.ch * 8, m2);
+    if (blockIdx.x == 0 && m.rg == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (a.dgamma) a.dgamma[m.ch * 8 + i] += m2[i] * a.inv_gs;
+        if (a.dbeta) a.dbeta[m.ch * 8 + i] += m1[i] * a.inv_gs;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      gr[i] *= rs[i];
+      m1[i] = (float)((double)m1[i] * a.inv_n);
+      m2[i] = (float)((double)m2[i] * a.inv_n);
+    }
+  }
   float db[4] = {0.f, 0.f, 0.f, 0.f};
   float range_acc = 0.f;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < a.rows; r += (long long)gridDim.x * m.rpb) {
-    const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.p) + r);
-    const float4 d4 = a.dpden ? __ldg(reinterpret_cast<const float4*>(a.dpden) + r) : z4;
-    const float4 l4 = a.dp_lc ? __ldg(reinterpret_cast<const float4*>(a.dp_lc) + r) : z4;
-    const float p[4] = {p4.x, p4.y, p4.z, p4.w};
-    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-    float dpre[4];
+  const long long stride = (long long)gridDim.x * m.rpb;
+  constexpr int U = 2;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += U * stride) {
+    float h[U][8];
+    float4 p4[U], d4[U], l4[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float lo = fmaxf(-p[j], 0.f), hi = fmaxf(p[j] - 1.f, 0.f);        // loss.py:121-123
-      const float dp = (0.5f * 0.6f) * dd[j] + ll[j] + (2.f * hi - 2.f * lo) * a.range_mult;
-      dpre[j] = dp * (1.f - p[j] * p[j]);                                      // tanh backward
-      if (m.ch == 0) {
-        db[j] += dpre[j];
-        range_acc += lo * lo + hi * hi;
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < a.rows) {
+        ld_h8(a.h2 + r * a.C + m.ch * 8, h[u]);
+        p4[u] = __ldg(reinterpret_cast<const float4*>(a.p) + r);
+        d4[u] = a.dpden ? __ldg(reinterpret_cast<const float4*>(a.dpden) + r) : z4;
+        l4[u] = a.dp_lc ? __ldg(reinterpret_cast<const float4*>(a.dp_lc) + r) : z4;
       }
     }
-    float h[8], dy[8];
-    ld_h8(a.h2 + r * a.C + m.ch * 8, h);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float act = fmaxf(fmaf(sc[i], h[i], bi[i]), 0.f);
-      float da = dpre[0] * w[0][i];
-      da = fmaf(dpre[1], w[1][i], da);
-      da = fmaf(dpre[2], w[2][i], da);
-      da = fmaf(dpre[3], w[3][i], da);
-      const float g = act > 0.f ? da : 0.f;
-      dy[i] = g;
-      sdy[i] += g;
-      sdyx[i] = fmaf(g, (h[i] - mu[i]) * rs[i], sdyx[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= a.rows) break;
+      const float p[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w};
+      const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+      const float ll[4] = {l4[u].x, l4[u].y, l4[u].z, l4[u].w};
+      float dpre[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dw[j][i] = fmaf(dpre[j], act, dw[j][i]);
+      for (int j = 0; j < 4; ++j) {
+        const float lo = fmaxf(-p[j], 0.f), hi = fmaxf(p[j] - 1.f, 0.f);        // loss.py:121-123
+        const float dp = (0.5f * 0.6f) * dd[j] + ll[j] + (2.f * hi - 2.f * lo) * a.range_mult;
+        dpre[j] = dp * (1.f - p[j] * p[j]);                                      // tanh backward
+        if (!APPLY && m.ch == 0) {
+          db[j] += dpre[j];
+          range_acc += lo * lo + hi * hi;
+        }
+      }
+      float out[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float act = fmaxf(fmaf(sc[i], h[u][i], bi[i]), 0.f);
+        float da = dpre[0] * w[0][i];
+        da = fmaf(dpre[1], w[1][i], da);
+        da = fmaf(dpre[2], w[2][i], da);
+        da = fmaf(dpre[3], w[3][i], da);
+        const float g = act > 0.f ? da : 0.f;
+        const float xh = (h[u][i] - mu[i]) * rs[i];
+        if (APPLY) {
+          const float dh = gr[i] * (g - m1[i] - xh * m2[i]);
+          out[i] = dh;
+          sdy[i] += dh;
+        } else {
+          sdy[i] += g;
+          sdyx[i] = fmaf(g, xh, sdyx[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dw[j][i] = fmaf(dpre[j], act, dw[j][i]);
+        }
+      }
+      if (APPLY) st_h8(a.dy2 + r * a.C + m.ch * 8, out);
     }
-    st_h8(a.dy2 + r * a.C + m.ch * 8, dy);
+  }
+  if (APPLY) {
+    block_colsum_atomic(sdy, a.dbias, m, a.inv_gs, sm);
+    return;
   }
   block_colsum_atomic(sdy, a.sum_dy, m, 1.f, sm);
   block_colsum_atomic(sdyx, a.sum_dyx, m, 1.f, sm);
@@ -414,16 +528,28 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(
   ld_f8(rstd + m.ch * 8, rs);
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < rows; r += (long long)gridDim.x * m.rpb) {
-    float g[8], x[8];
-    ld_h8(da + r * C + m.ch * 8, g);
-    ld_h8(h + r * C + m.ch * 8, x);
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
+    float g[kUnroll][8], x[kUnroll][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float dy = fmaf(sc[i], x[i], bi[i]) > 0.f ? g[i] : 0.f;
-      s1[i] += dy;
-      s2[i] = fmaf(dy, (x[i] - mu[i]) * rs[i], s2[i]);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < rows) {
+        ld_h8(da + r * C + m.ch * 8, g[u]);
+        ld_h8(h + r * C + m.ch * 8, x[u]);
+      } else {
+        zero8(g[u]);
+        zero8(x[u]);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dy = fmaf(sc[i], x[u][i], bi[i]) > 0.f ? g[u][i] : 0.f;
+        s1[i] += dy;
+        s2[i] = fmaf(dy, (x[u][i] - mu[i]) * rs[i], s2[i]);
+      }
   }
   block_colsum_atomic(s1, sum_dy, m, 1.f, sm);
   block_colsum_atomic(s2, sum_dyx, m, 1.f, sm);
@@ -454,20 +580,32 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(BnBwdArgs a) {
     m2[i] = (float)((double)m2[i] * a.inv_n);
     sdh[i] = 0.f;
   }
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < a.rows; r += (long long)gridDim.x * m.rpb) {
-    float g[8], x[8];
-    ld_h8(a.dy + r * a.C + m.ch * 8, g);
-    ld_h8(a.h + r * a.C + m.ch * 8, x);
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += kUnroll * stride) {
+    float g[kUnroll][8], x[kUnroll][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float dy = g[i];
-      if (a.relu_mask) dy = fmaf(sc[i], x[i], bi[i]) > 0.f ? dy : 0.f;
-      const float xh = (x[i] - mu[i]) * rs[i];
-      const float dh = gr[i] * (dy - m1[i] - xh * m2[i]);
-      g[i] = dh;
-      sdh[i] += dh;
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < a.rows) {
+        ld_h8(a.dy + r * a.C + m.ch * 8, g[u]);
+        ld_h8(a.h + r * a.C + m.ch * 8, x[u]);
+      }
     }
-    st_h8(a.dh + r * a.C + m.ch * 8, g);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= a.rows) break;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float dy = g[u][i];
+        if (a.relu_mask) dy = fmaf(sc[i], x[u][i], bi[i]) > 0.f ? dy : 0.f;
+        const float xh = (x[u][i] - mu[i]) * rs[i];
+        const float dh = gr[i] * (dy - m1[i] - xh * m2[i]);
+        g[u][i] = dh;
+        sdh[i] += dh;
+      }
+      st_h8(a.dh + r * a.C + m.ch * 8, g[u]);
+    }
   }
   block_colsum_atomic(sdh, a.dbias, m, a.inv_gs, sm);
 }
@@ -486,19 +624,32 @@ __global__ void __launch_bounds__(kThreads) d_l2_bwd_kernel(const __half* __rest
 #pragma unroll
   for (int i = 0; i < 8; ++i) sw[i] = sb[i] = 0.f;
   float s3 = 0.f;
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < rows; r += (long long)gridDim.x * m.rpb) {
-    const float dl = __ldg(dlogit + r);
-    float z[8], o[8];
-    ld_h8(z2 + r * C + m.ch * 8, z);
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
+    float z[kUnroll][8], dl[kUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float dh = dl * w[i] * (z[i] > 0.f ? 1.f : kSlope);
-      o[i] = dh;
-      sw[i] = fmaf(dl, z[i], sw[i]);
-      sb[i] += dh;
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < rows) {
+        dl[u] = __ldg(dlogit + r);
+        ld_h8(z2 + r * C + m.ch * 8, z[u]);
+      }
     }
-    st_h8(dh2 + r * C + m.ch * 8, o);
-    if (m.ch == 0) s3 += dl;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= rows) break;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dh = dl[u] * w[i] * (z[u][i] > 0.f ? 1.f : kSlope);
+        o[i] = dh;
+        sw[i] = fmaf(dl[u], z[u][i], sw[i]);
+        sb[i] += dh;
+      }
+      st_h8(dh2 + r * C + m.ch * 8, o);
+      if (m.ch == 0) s3 += dl[u];
+    }
   }
   if (dw3 != nullptr) {
     block_colsum_atomic(sw, dw3, m, inv_gs, sm);
@@ -659,114 +810,119 @@ __global__ void score_finish_kernel(const float* __restrict__ p, const float* __
 // =========================================================================================== launchers
 void launch_center_vec(const float* x, int64_t rows, int S, int rows_used, float* cvec, int Kp, cudaStream_t st) {
   if (rows_used > rows) rows_used = (int)rows;
-  center_vec_kernel<<<(Kp + 31) / 32, 256, 0, st>>>(x, S, rows_used, cvec, Kp);
+  note_launch(), center_vec_kernel<<<(Kp + 31) / 32, 1024, 0, st>>>(x, S, rows_used, cvec, Kp);
 }
 void launch_cast_center(const float* x, const float* cvec, const float* params, __half* xc, int64_t rows, int S,
                         int P, int Kp, cudaStream_t st) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
-  cast_center_kernel<false><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(x, nullptr, 0.f, cvec, params, xc, rows, S, P, Kp);
+  note_launch(), cast_center_kernel<false><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(x, nullptr, 0.f, cvec, params, xc, rows, S, P, Kp,
+                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) ? 1 : 0);
 }
 void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
                               float*, int64_t rows, int S, int P, int Kp, cudaStream_t st) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
-  cast_center_kernel<true><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp);
+  note_launch(), cast_center_kernel<true><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp,
+                                                                            (S % 2 == 0 && (reinterpret_cast<uintptr_t>(target) & 7) == 0 &&
+                                                                             (reinterpret_cast<uintptr_t>(noise) & 7) == 0) ? 1 : 0);
 }
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st) {
-  pack_first_layer_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, ld_src, S, P, wp_cols, bias_cols, b, cvec, out, Kp,
+  note_launch(), pack_first_layer_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, ld_src, S, P, wp_cols, bias_cols, b, cvec, out, Kp,
                                                           b_eff_out, rows);
 }
 void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st) {
   const long long total = (long long)rows * ld_dst;
   int grid = (int)((total + kThreads - 1) / kThreads);
   if (grid > 148 * 8) grid = 148 * 8;
-  cast_pad_kernel<<<grid, kThreads, 0, st>>>(src, ld_src, ncols, dst, ld_dst, rows);
+  note_launch(), cast_pad_kernel<<<grid, kThreads, 0, st>>>(src, ld_src, ncols, dst, ld_dst, rows);
 }
 void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst,
                            cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  transpose_cast_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst);
+  note_launch(), transpose_cast_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst);
 }
 void launch_extract_wp(const float* w, int ld_src, int S, int P, float* wp, int rows, int rows_pad, cudaStream_t st) {
-  extract_wp_kernel<<<(rows_pad * 4 + 255) / 256, 256, 0, st>>>(w, ld_src, S, P, wp, rows, rows_pad);
+  note_launch(), extract_wp_kernel<<<(rows_pad * 4 + 255) / 256, 256, 0, st>>>(w, ld_src, S, P, wp, rows, rows_pad);
 }
 void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStream_t st) {
-  copy_pad_f32_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
+  note_launch(), copy_pad_f32_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
 }
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  colstats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 4), kThreads, 0, st>>>(h, rows, C, sum, sumsq);
+  note_launch(), colstats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(h, rows, C, sum, sumsq);
 }
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
-  bn_finalize_kernel<<<(a.C + 255) / 256, 256, 0, st>>>(a);
+  note_launch(), bn_finalize_kernel<<<(a.C + 255) / 256, 256, 0, st>>>(a);
 }
 void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta,
                            const float* offset, float* scale, float* bias, int C, cudaStream_t st) {
-  bn_eval_affine_kernel<<<(C + 255) / 256, 256, 0, st>>>(rm, rv, gamma, beta, offset, scale, bias, C);
+  note_launch(), bn_eval_affine_kernel<<<(C + 255) / 256, 256, 0, st>>>(rm, rv, gamma, beta, offset, scale, bias, C);
 }
 void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias, __half* a, int64_t rows, int C,
                           cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  bn_relu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, scale, bias, a, rows, C);
+  note_launch(), bn_relu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, scale, bias, a, rows, C);
 }
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
-  g_head_fwd_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(h2, scale, bias, w3, b3, p_out, pden_out, xc,
+  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(h2, scale, bias, w3, b3, p_out, pden_out, xc,
                                                                      tail_fake, rows, C, Kp, S);
 }
-void launch_g_head_bwd(const GHeadBwdArgs& a, cudaStream_t st) {
+void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 8);
-  g_head_bwd_kernel<<<grid_for_rows(a.rows, rpb * 8, 148 * 2), kThreads, 0, st>>>(a);
+  const int grid = grid_for_rows(a.rows, rpb * 8, 148 * 8);
+  if (apply) note_launch(), g_head_bwd_kernel<true><<<grid, kThreads, 0, st>>>(a);
+  else note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
                          cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  bn_bwd_stats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 4), kThreads, 0, st>>>(da, h, scale, bias, mean, rstd,
+  note_launch(), bn_bwd_stats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(da, h, scale, bias, mean, rstd,
                                                                                 sum_dy, sum_dyx, rows, C);
 }
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 8);
-  bn_bwd_apply_kernel<<<grid_for_rows(a.rows, rpb * 8, 148 * 4), kThreads, 0, st>>>(a);
+  note_launch(), bn_bwd_apply_kernel<<<grid_for_rows(a.rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(a);
 }
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
                      float* db3, int64_t rows, int C, float inv_gs, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  d_l2_bwd_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 4), kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows,
+  note_launch(), d_l2_bwd_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows,
                                                                             C, inv_gs);
 }
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,
                  int64_t rows, int C, cudaStream_t st) {
-  f_l1_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(p, w1, b1, lnw, lnb, out, rows, C);
+  note_launch(), f_l1_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(p, w1, b1, lnw, lnb, out, rows, C);
 }
 void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const float* gamma, const float* beta,
                            int64_t rows, int N, cudaStream_t st) {
   const int rpb = kThreads / (N / 8);
-  ln_lrelu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, rowstats, n_tiles, gamma, beta, rows, N);
+  note_launch(), ln_lrelu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, rowstats, n_tiles, gamma, beta, rows, N);
 }
 void launch_sumsq(const float* g, int64_t n, double* out, cudaStream_t st) {
   int grid = (int)((n + kThreads * 4 - 1) / (kThreads * 4));
   if (grid > 148 * 2) grid = 148 * 2;
   if (grid < 1) grid = 1;
-  sumsq_kernel<<<grid, kThreads, 0, st>>>(g, n, out);
+  note_launch(), sumsq_kernel<<<grid, kThreads, 0, st>>>(g, n, out);
 }
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st) {
   int grid = (int)((a.n + kThreads - 1) / kThreads);
   if (grid > 148 * 8) grid = 148 * 8;
-  clip_adam_kernel<<<grid, kThreads, 0, st>>>(a);
+  note_launch(), clip_adam_kernel<<<grid, kThreads, 0, st>>>(a);
 }
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,
                      cudaStream_t st) {
   const int total = rows * (S + P);
-  dw_fixup_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw, ld, S, P, db, cvec, rows);
+  note_launch(), dw_fixup_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw, ld, S, P, db, cvec, rows);
 }
-void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { loss_finalize_kernel<<<1, 32, 0, st>>>(a); }
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { note_launch(), loss_finalize_kernel<<<1, 32, 0, st>>>(a); }
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st) {
-  score_finish_kernel<<<(int)((rows + 255) / 256), 256, 0, st>>>(p, err, rows, P, violations, consistency);
+  note_launch(), score_finish_kernel<<<(int)((rows + 255) / 256), 256, 0, st>>>(p, err, rows, P, violations, consistency);
 }
 
 }  // namespace pigan

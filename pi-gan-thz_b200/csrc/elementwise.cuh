@@ -79,7 +79,7 @@ struct GHeadBwdArgs {
   const float* mean;
   const float* rstd;
   const float* w3;        // [4,C]
-  __half* dy2;            // out [B,C] (scaled, already masked by ReLU)
+  __half* dy2;            // out [B,C] (apply pass): BatchNorm-2 input gradient dh2, scaled by GS
   float* dw3;             // [4,C] += (unscaled)
   float* db3;             // [4]   +=
   float* sum_dy;          // [C] += (scaled)
@@ -88,8 +88,15 @@ struct GHeadBwdArgs {
   float inv_gs;
   int64_t rows;
   int C;
+  // apply pass only
+  const float* gamma;     // BN2 weight
+  float* dbias;           // [C] += sum dh / GS   (main.3.bias)
+  float* dgamma;          // [C] += sum_dyx / GS
+  float* dbeta;           // [C] += sum_dy / GS
+  double inv_n;           // 1 / global batch
 };
-void launch_g_head_bwd(const GHeadBwdArgs& a, cudaStream_t st);
+// apply = false: statistics pass (sum_dy, sum_dyx, dw3, db3, range_sum); apply = true: writes dy2 (see kernel)
+void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st);
 // relu-masked column sums for the BatchNorm backward: dy = da * [scale*h+bias > 0]
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,

@@ -3,7 +3,11 @@
 // core/train/train_pigan.py:114-187 in seven phases, candidate scoring of
 // core/evaluate/unified_evaluator.py:376-392).  No host<->device synchronisation anywhere: every call only
 // enqueues work on the caller's stream, so a step can be captured in a CUDA graph.
+#include <string.h>
+
 #include <new>
+#include <string>
+#include <vector>
 
 #include "elementwise.cuh"
 #include "epilogues.cuh"
@@ -44,7 +48,43 @@ struct Carver {
 
 using namespace pigan;
 
+// Optional CUDA-event instrumentation of the kernel sequence (pigan_engine_profile_begin/_end): one event per
+// section boundary on the caller's stream; off by default, so the hot path records nothing.
+struct Prof {
+  bool on = false;
+  bool all = true;
+  std::vector<std::string> wanted;
+  std::vector<const char*> names;
+  struct Rec { int slot; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  int open_slot = -1;
+  cudaEvent_t open_ev = nullptr;
+  cudaEvent_t next_event() {
+    if (used == pool.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      pool.push_back(ev);
+    }
+    return pool[used++];
+  }
+  int slot_of(const char* name) {
+    for (size_t i = 0; i < names.size(); ++i)
+      if (names[i] == name || strcmp(names[i], name) == 0) return (int)i;
+    names.push_back(name);
+    return (int)names.size() - 1;
+  }
+  bool is_wanted(const char* name) const {
+    if (all) return true;
+    for (const auto& w : wanted)
+      if (w == name) return true;
+    return false;
+  }
+};
+
 struct PiganEngine {
+  Prof prof;
   PiganDims d;
   GenLayout gl;
   DiscLayout dl;
@@ -53,6 +93,7 @@ struct PiganEngine {
   size_t ws_bytes;
   bool f_loaded = false;
   const float* f_params = nullptr;
+  const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
 
   // fp16 activations
   __half *xc, *tail_f, *g_h1, *g_a1, *g_h2, *d_z1, *d_z2, *d_dh2, *d_dh1, *f_a1, *f_a2, *f_a3, *f_a4, *f_a5,
@@ -126,6 +167,21 @@ struct PiganEngine {
 namespace pigan {
 namespace {
 
+// Closes the open profiling section and opens `name` (nullptr: just close).
+void prof_mark(PiganEngine* e, const char* name, cudaStream_t st) {
+  Prof& p = e->prof;
+  if (!p.on) return;
+  int slot = -1;
+  if (name && p.is_wanted(name)) slot = p.slot_of(name);
+  if (p.open_slot < 0 && slot < 0) return;
+  cudaEvent_t ev = p.next_event();
+  cudaEventRecord(ev, st);
+  if (p.open_slot >= 0) p.recs.push_back({p.open_slot, p.open_ev, ev});
+  p.open_slot = slot;
+  p.open_ev = ev;
+}
+#define PM(name) prof_mark(e, name, st)
+
 int check_dims(const PiganDims& d) {
   if (!dims_are_default(d))
     return fail(PIGAN_ERR_UNSUPPORTED,
@@ -185,7 +241,9 @@ int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t
 // ------------------------------------------------------------------------------------------ generator
 // spectrum prep: centring vector, fp16 operand with [params | 1 1] in the spare columns
 int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n, cudaStream_t st) {
-  launch_center_vec(x, n, e->gl.S, (int)(n < 4096 ? n : 4096), e->cvec, kKp, st);
+  PM("prep_cast");
+  if (e->center != nullptr) launch_copy_pad_f32(e->center, e->gl.S, e->cvec, kKp, st);
+  else launch_center_vec(x, n, e->gl.S, (int)(n < 512 ? n : 512), e->cvec, kKp, st);
   launch_cast_center(x, e->cvec, params, e->xc, n, e->gl.S, e->gl.P, kKp, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
@@ -193,6 +251,7 @@ int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n
 
 int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStream_t st) {
   const GenLayout& L = e->gl;
+  PM("pack_weights");
   launch_pack_first_layer(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, kKp, e->g_beff, L.H1, st);
   launch_cast_pad(gp + L.w2, L.H1, L.H1, e->g_w2h, L.H1, L.H2, st);
   if (need_backward) launch_transpose_cast(gp + L.w2, L.H2, L.H1, L.H1, e->g_w2th, L.H2, st);
@@ -202,6 +261,7 @@ int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStre
 
 int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cudaStream_t st) {
   const DiscLayout& L = e->dl;
+  PM("pack_weights");
   launch_pack_first_layer(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, kKp, e->d_beff, L.H1, st);
   launch_cast_pad(dp + L.w2, L.H1, L.H1, e->d_w2h, L.H1, L.H2, st);
   if (need_backward) {
@@ -214,15 +274,19 @@ int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cuda
 
 // G layer 1 -> h1 (pre-BN product WITHOUT its constant bias: see launch_pack_first_layer)
 int g_layer1(PiganEngine* e, int64_t n, cudaStream_t st) {
+  PM("g_l1_gemm");
   return linear_store<false, false, false>(e->xc, n, kKp, e->g_w1h, e->gl.H1, nullptr, e->g_h1, nullptr, st);
 }
 int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st) {
+  PM("g_bn_relu_apply");
   launch_bn_relu_apply(e->g_h1, e->scale1, e->bias1, e->g_a1, n, e->gl.H1, st);
   (void)gp;
+  PM("g_l2_gemm");
   return linear_store<false, false, false>(e->g_a1, n, e->gl.H1, e->g_w2h, e->gl.H2, nullptr, e->g_h2, nullptr, st);
 }
 void g_bn_stats(PiganEngine* e, int which, int64_t n, cudaStream_t st) {
   const int H1 = e->gl.H1, H2 = e->gl.H2;
+  PM("g_bn_colstats");
   if (which == 1) launch_colstats(e->g_h1, n, H1, e->bn_sums, e->bn_sums + H1, st);
   else launch_colstats(e->g_h2, n, H2, e->bn_sums + 2 * H1, e->bn_sums + 2 * H1 + H2, st);
 }
@@ -247,12 +311,14 @@ void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offs
   }
   a.n = n_global;
   a.num_updates = num_updates;
+  PM("small");
   launch_bn_finalize(a, st);
 }
 
 // ------------------------------------------------------------------------------------------ discriminator
 // z1 rows [row0, row0+n) = LeakyReLU([xc | tail] . w1h^T)   (bias and parameter columns inside the MMA)
 int d_layer1(PiganEngine* e, int64_t n, int64_t row0, bool fake, cudaStream_t st) {
+  PM("d_l1_gemm");
   return linear_store<false, true, false>(e->xc, n, kKp, e->d_w1h, e->dl.H1, nullptr, e->d_z1 + row0 * e->dl.H1,
                                           nullptr, st, fake ? e->tail_f : nullptr);
 }
@@ -286,6 +352,7 @@ int d_layer2(PiganEngine* e, const float* dp, const DL2Opts& o, cudaStream_t st)
   ep.dlogit = o.want_dlogit ? e->dlogit : nullptr;
   ep.prob_out = o.prob_out;
   ep.store_z2 = o.store_z2 ? 1 : 0;
+  PM("d_l2_bce_gemm");
   return run_tn<CfgS, Epi>(ep, e->d_z1, o.rows, L.H1, L.H1, e->d_w2h, L.H2, L.H1, st);
 }
 
@@ -306,11 +373,14 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
   const FwdLayout& L = e->fl;
   const float* fp = e->f_params;
+  PM("f_l1");
   launch_f_l1(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_a1, n, L.H[0], st);
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
+    PM("f_hidden_gemm");
     PIGAN_TRY((linear_store<true, false, true>(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], acts[i],
                                                e->f_rowstats, st)));
+    PM("f_ln_apply");
     launch_ln_lrelu_apply(acts[i], e->f_rowstats, ceil_div(L.H[i], 256), fp + L.ln_w[i], fp + L.ln_b[i], n, L.H[i],
                           st);
   }
@@ -330,12 +400,31 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   ep.row_err = o.row_err;
   ep.f1_idx = o.f1_idx;
   ep.f2_idx = o.f2_idx;
+  PM("f_out_gemm");
   PIGAN_TRY((run_tn<CfgO, Epi>(ep, e->f_a5, n, L.H[4], L.H[4], e->f_wh[5], L.OUT, L.H[4], st)));
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ train phases
+// Generator head + BatchNorm-2 backward: same arguments for the statistics pass (phase 3) and the apply pass
+// (phase 4, after the data-parallel reduction of the column sums).
+GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
+  const GenLayout& G = e->gl;
+  const float inv_gs = (float)(1.0 / (double)a.global_batch);
+  float* gp = a.g_params;
+  GHeadBwdArgs hb;
+  hb.p = e->p; hb.dpden = e->dpden; hb.dp_lc = e->dp_lc;
+  hb.range_mult = a.lambda_param_range / (float)G.P;
+  hb.h2 = e->g_h2; hb.scale = e->scale2; hb.bias = e->bias2; hb.mean = e->mean2; hb.rstd = e->rstd2;
+  hb.w3 = gp + G.w3; hb.dy2 = e->g_dy2; hb.dw3 = a.g_grads + G.w3; hb.db3 = a.g_grads + G.b3;
+  hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = e->sums + kSumRange;
+  hb.inv_gs = inv_gs; hb.rows = a.batch; hb.C = G.H2;
+  hb.gamma = gp + G.bn2_w; hb.dbias = a.g_grads + G.b2; hb.dgamma = a.g_grads + G.bn2_w;
+  hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch;
+  return hb;
+}
+
 int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t st) {
   const GenLayout& G = e->gl;
   const DiscLayout& D = e->dl;
@@ -348,6 +437,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
 
   switch (phase) {
     case 0: {
+      PM("memset");
       PIGAN_CUDA_OK(cudaMemsetAsync(a.g_grads, 0, G.total * sizeof(float), st));
       PIGAN_CUDA_OK(cudaMemsetAsync(a.d_grads, 0, D.total * sizeof(float), st));
       PIGAN_CUDA_OK(cudaMemsetAsync(e->sums, 0, kNumSums * sizeof(double), st));
@@ -370,6 +460,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
     }
     case 2: {
       g_bn_finalize(e, 2, gp, gp + G.b2, a.g_bn_buffers, a.g_num_batches_tracked, NG, 2, st);
+      PM("g_head_fwd");
       launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, e->p, e->pden, e->xc, e->tail_f, B, G.H2,
                         kKp, G.S, st);
       // ---- D-step (train_pigan.py:123-143)
@@ -378,9 +469,11 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY(d_layer1(e, B, BP, true, st));
       DL2Opts o{BP + B, BP, 0.9f, 0.1f, B, BP, NG, e->sums + kSumD, nullptr, true, true};
       PIGAN_TRY(d_layer2(e, dp, o, st));
+      PM("d_l2_bwd");
       launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, a.d_grads + D.w3, a.d_grads + D.b2, a.d_grads + D.b3,
                       BP + B, D.H2, inv_gs, st);
       {
+        PM("d_dh1_gemm");
         using Epi = EpiLeakyMaskStore<CfgS>;
         Epi::Params ep;
         PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
@@ -388,14 +481,18 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
         ep.ldz = D.H1;
         PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
+      PM("d_dw2_gemm");
       PIGAN_TRY(weight_grad(e->d_dh2, BP + B, D.H2, e->d_z1, BP + B, D.H1, a.d_grads + D.w2, D.H1, D.H1, inv_gs, -1,
                             nullptr, 0, nullptr, 0, st));
+      PM("d_dw1_gemm");
       PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
                             a.d_grads + D.b1, BP, e->tail_f, BP, st));
+      PM("small");
       launch_dw_fixup(a.d_grads + D.w1, D.IN, D.S, D.P, a.d_grads + D.b1, e->cvec, D.H1, st);
       break;
     }
     case 3: {
+      PM("clip_adam");
       launch_sumsq(a.d_grads, D.total, e->sums + kSumGradD, st);
       AdamArgs ad{dp, a.d_grads, a.d_exp_avg, a.d_exp_avg_sq, D.total, a.lr_d, 0.5f, 0.999f, 1e-8f,
                   1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradD, 1.0f};
@@ -405,8 +502,10 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY(d_layer1(e, B, 0, true, st));
       DL2Opts o{B, B, 1.0f, 1.0f, 0, 0, NG, e->sums + kSumAdv, nullptr, true, true};
       PIGAN_TRY(d_layer2(e, dp, o, st));
+      PM("d_l2_bwd");
       launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, st);
       {
+        PM("d_paramgrad_gemm");
         using Epi = EpiDiscParamGrad<CfgP>;
         Epi::Params ep{e->d_z1, D.H1, e->d_wp, e->dpden};
         PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
@@ -414,27 +513,19 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       FOutOpts fo{a.spectrum, G.S, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
                   a.f1_idx, a.f2_idx};
       PIGAN_TRY(f_forward(e, e->p, B, fo, st));
-      GHeadBwdArgs hb;
-      hb.p = e->p; hb.dpden = e->dpden; hb.dp_lc = e->dp_lc;
-      hb.range_mult = a.lambda_param_range / (float)G.P;
-      hb.h2 = e->g_h2; hb.scale = e->scale2; hb.bias = e->bias2; hb.mean = e->mean2; hb.rstd = e->rstd2;
-      hb.w3 = gp + G.w3; hb.dy2 = e->g_dy2; hb.dw3 = a.g_grads + G.w3; hb.db3 = a.g_grads + G.b3;
-      hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = e->sums + kSumRange;
-      hb.inv_gs = inv_gs; hb.rows = B; hb.C = G.H2;
-      launch_g_head_bwd(hb, st);
+      PM("g_head_bwd");
+      launch_g_head_bwd(head_bwd_args(e, a), false, st);
       break;
     }
     case 4: {
-      BnBwdArgs bb;
-      bb.dy = e->g_dy2; bb.h = e->g_h2; bb.relu_mask = 0;
-      bb.scale = e->scale2; bb.bias = e->bias2; bb.mean = e->mean2; bb.rstd = e->rstd2; bb.gamma = gp + G.bn2_w;
-      bb.sum_dy = e->bn_bwd_sums; bb.sum_dyx = e->bn_bwd_sums + G.H2;
-      bb.dh = e->g_dy2; bb.dbias = a.g_grads + G.b2; bb.dgamma = a.g_grads + G.bn2_w; bb.dbeta = a.g_grads + G.bn2_b;
-      bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H2;
-      launch_bn_bwd_apply(bb, st);
+      PM("g_head_bwd");
+      launch_g_head_bwd(head_bwd_args(e, a), true, st);
+      PM("g_dw2_gemm");
       PIGAN_TRY(weight_grad(e->g_dy2, B, G.H2, e->g_a1, B, G.H1, a.g_grads + G.w2, G.H1, G.H1, inv_gs, -1, nullptr, 0,
                             nullptr, 0, st));
+      PM("g_da1_gemm");
       PIGAN_TRY((linear_store<false, false, false>(e->g_dy2, B, G.H2, e->g_w2th, G.H1, nullptr, e->g_da1, nullptr, st)));
+      PM("g_bn_bwd_stats");
       launch_bn_bwd_stats(e->g_da1, e->g_h1, e->scale1, e->bias1, e->mean1, e->rstd1, e->bn_bwd_sums + 2 * G.H2,
                           e->bn_bwd_sums + 2 * G.H2 + G.H1, B, G.H1, st);
       break;
@@ -446,13 +537,17 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       bb.sum_dy = e->bn_bwd_sums + 2 * G.H2; bb.sum_dyx = e->bn_bwd_sums + 2 * G.H2 + G.H1;
       bb.dh = e->g_da1; bb.dbias = nullptr; bb.dgamma = a.g_grads + G.bn1_w; bb.dbeta = a.g_grads + G.bn1_b;
       bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H1;
+      PM("g_bn_bwd_apply");
       launch_bn_bwd_apply(bb, st);
+      PM("g_dw1_gemm");
       PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, kKp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
                             a.g_grads + G.b1, 0, nullptr, 0, st));
+      PM("small");
       launch_dw_fixup(a.g_grads + G.w1, G.S, G.S, 0, a.g_grads + G.b1, e->cvec, G.H1, st);
       break;
     }
     case 6: {
+      PM("clip_adam");
       launch_sumsq(a.g_grads, G.total, e->sums + kSumGradG, st);
       AdamArgs ad{gp, a.g_grads, a.g_exp_avg, a.g_exp_avg_sq, G.total, a.lr_g, 0.5f, 0.999f, 1e-8f,
                   1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradG, 1.0f};
@@ -468,6 +563,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
     default:
       return fail(PIGAN_ERR_INVALID, "train phase %d out of range", phase);
   }
+  PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -528,6 +624,8 @@ extern "C" int pigan_engine_create(PiganEngine** out, const PiganDims* dims, int
 }
 
 extern "C" int pigan_engine_destroy(PiganEngine* e) {
+  if (e)
+    for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
   delete e;
   return PIGAN_OK;
 }
@@ -549,6 +647,12 @@ extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, 
   return PIGAN_OK;
 }
 
+extern "C" int pigan_engine_set_spectrum_center(PiganEngine* e, const float* center) {
+  PIGAN_CHECK_ARG(e != nullptr);
+  e->center = center;
+  return PIGAN_OK;
+}
+
 extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* bn, int64_t* nbt, const float* x,
                                        int64_t n, int32_t training, float* out, void* stream) {
   PIGAN_CHECK_ARG(e && gp && x && out && n >= 1 && n <= e->max_batch);
@@ -563,17 +667,23 @@ extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* b
     g_bn_stats(e, 1, n, st);
     g_bn_finalize(e, 1, gp, e->g_beff, bn, nbt, (double)n, 1, st);
   } else {
-    launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
+    PM("small");
+    PM("small");
+  launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
   }
   PIGAN_TRY(g_layer2(e, gp, n, st));
   if (training) {
     g_bn_stats(e, 2, n, st);
     g_bn_finalize(e, 2, gp, gp + G.b2, bn, nbt, (double)n, 1, st);
   } else {
-    launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+    PM("small");
+    PM("small");
+  launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
   }
+  PM("g_head_fwd");
   launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, out, nullptr, e->xc, nullptr, n, G.H2, kKp,
                     G.S, st);
+  PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -587,6 +697,7 @@ extern "C" int pigan_discriminator_forward(PiganEngine* e, const float* dp, cons
   PIGAN_TRY(d_layer1(e, n, 0, false, st));
   DL2Opts o{n, n, 1.0f, 1.0f, 0, 0, (double)n, nullptr, out_prob, false, false};
   PIGAN_TRY(d_layer2(e, dp, o, st));
+  PM(nullptr);
   return PIGAN_OK;
 }
 
@@ -595,7 +706,9 @@ extern "C" int pigan_forward_model_forward(PiganEngine* e, const float* p_norm, 
   PIGAN_CHECK_ARG(e && p_norm && out && n >= 1 && n <= e->max_batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FOutOpts fo{nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, out, nullptr, 0, 1};
-  return f_forward(e, p_norm, n, fo, st);
+  PIGAN_TRY(f_forward(e, p_norm, n, fo, st));
+  PM(nullptr);
+  return PIGAN_OK;
 }
 
 extern "C" int pigan_train_step_phase(PiganEngine* e, const PiganTrainArgs* a, int32_t phase, void* stream) {
@@ -606,6 +719,58 @@ extern "C" int pigan_train_step_phase(PiganEngine* e, const PiganTrainArgs* a, i
 extern "C" int pigan_train_step(PiganEngine* e, const PiganTrainArgs* a, void* stream) {
   PIGAN_TRY(check_train_args(e, a));
   for (int ph = 0; ph <= 6; ++ph) PIGAN_TRY(train_phase(e, *a, ph, static_cast<cudaStream_t>(stream)));
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_engine_profile_begin(PiganEngine* e, const char* sections_csv) {
+  PIGAN_CHECK_ARG(e != nullptr);
+  Prof& p = e->prof;
+  p.on = true;
+  p.recs.clear();
+  p.used = 0;
+  p.open_slot = -1;
+  p.wanted.clear();
+  p.all = (sections_csv == nullptr || sections_csv[0] == 0);
+  if (!p.all) {
+    std::string cur;
+    for (const char* c = sections_csv;; ++c) {
+      if (*c == ',' || *c == 0) {
+        if (!cur.empty()) p.wanted.push_back(cur);
+        cur.clear();
+        if (*c == 0) break;
+      } else {
+        cur.push_back(*c);
+      }
+    }
+  }
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_engine_profile_end(PiganEngine* e, char* report, size_t report_bytes) {
+  PIGAN_CHECK_ARG(e != nullptr && report != nullptr && report_bytes > 0);
+  Prof& p = e->prof;
+  p.on = false;
+  p.open_slot = -1;
+  std::vector<double> ms(p.names.size(), 0.0);
+  std::vector<long long> cnt(p.names.size(), 0);
+  for (const auto& r : p.recs) {
+    PIGAN_CUDA_OK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    PIGAN_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.slot] += t;
+    cnt[r.slot] += 1;
+  }
+  p.recs.clear();
+  p.used = 0;
+  std::string out;
+  char line[160];
+  for (size_t i = 0; i < p.names.size(); ++i) {
+    if (cnt[i] == 0) continue;
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", p.names[i], cnt[i], ms[i]);
+    out += line;
+  }
+  if (out.size() + 1 > report_bytes) return fail(PIGAN_ERR_WORKSPACE, "profile report needs %zu bytes", out.size() + 1);
+  memcpy(report, out.c_str(), out.size() + 1);
   return PIGAN_OK;
 }
 
@@ -625,21 +790,27 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
     PIGAN_TRY(prep_spectrum(e, spectra, nullptr, n, st));
   } else {
     // centre on the design target: the candidates differ from it by sigma * noise only
+    PM("prep_cast");
     launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);
     launch_cast_center_noise(target, noise, sigma, e->cvec, e->xc, nullptr, n, G.S, G.P, kKp, st);
   }
   PIGAN_TRY(pack_generator(e, gp, false, st));
   PIGAN_TRY(g_layer1(e, n, st));
+  PM("small");
   launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
   PIGAN_TRY(g_layer2(e, gp, n, st));
+  PM("small");
   launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
   float* p = out_p ? out_p : e->p;
+  PM("g_head_fwd");
   launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, p, nullptr, e->xc, nullptr, n, G.H2, kKp,
                     G.S, st);
   float* err = out_err ? out_err : e->row_err;
   FOutOpts fo{spectra ? spectra : target, spectra ? G.S : 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
   PIGAN_TRY(f_forward(e, p, n, fo, st));
+  PM("small");
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
+  PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

@@ -22,6 +22,15 @@ constexpr float kLeaky = 0.2f;
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kLeaky * x); }  // valid for slope < 1
 __device__ __forceinline__ float lrelu_slope_from_out(float z) { return z > 0.f ? 1.f : kLeaky; }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -346,7 +355,9 @@ struct EpiFwdOut {
     float* row_err;               // [M] mean_j (x - recon)^2 or null
     int f1_idx, f2_idx;
   };
-  static constexpr int SMEM_BYTES = 0;
+  // per-warp [32 rows][33] fp32 transposition buffer: global reads/writes of per-row data stay coalesced
+  // (lane <-> column) while the math keeps one thread per row (row = TMEM lane)
+  static constexpr int SMEM_BYTES = 17408;  // 4 warps * 32 * 33 * 4 B = 16896, rounded to 1 KB
   struct State {
     float s_rec, s_met, s_mx, s_lc1, s_lc2;
   };
@@ -355,46 +366,79 @@ struct EpiFwdOut {
   }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
-    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
+    const int row0 = w.m_tile * kBlockM + cx.q * 32;  // first row of this warp
+    const int row = row0 + cx.lane;
     const bool valid = row < g.M;
     const int OUT = p.S + p.Mt;
+    const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 33u * 4u);  // this warp's buffer
     float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
     float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
-    const float* xs = p.target_spec ? p.target_spec + (size_t)(valid ? row : 0) * p.target_ld : nullptr;
     const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
 #pragma unroll 1
-    for (int j0 = 0; j0 < 288; j0 += 16) {
-      float v[16];
-      tmem_ld16(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
-      tmem_ld_wait();
-      if (!valid || j0 >= OUT) continue;
+    for (int j0 = 0; j0 < 288; j0 += 32) {
+      float v[32];
+      tmem_ld32(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
+      float t[32];
+      const bool has_t = p.target_spec != nullptr && j0 < p.S;
+      if (has_t) {
+        // rows of this warp x columns [j0, j0+32): lane = column while loading, lane = row while reading back
+        const int col = j0 + cx.lane;
+        const bool col_ok = col < p.S;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int r = row0 + i;
+          float x = 0.f;
+          if (col_ok && r < g.M) x = __ldg(p.target_spec + (size_t)r * p.target_ld + col);
+          sts_f32(tb + (uint32_t)(i * 33 + cx.lane) * 4u, x);
+        }
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) t[i] = lds_f32(tb + (uint32_t)(cx.lane * 33 + i) * 4u);
+        __syncwarp();
+      }
+      float b[32];
+      load_cols32(p.bias + j0, b);
+      tmem_ld_wait();
+      if (j0 >= OUT) continue;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
         const int j = j0 + i;
-        if (j < OUT) {
-          const float o = v[i] + __ldg(p.bias + j);
-          if (p.out_full) p.out_full[(size_t)row * OUT + j] = o;
-          if (j < p.S) {
-            if (xs) {
-              const float d = o - __ldg(xs + j);
-              rec = fmaf(d, d, rec);
-            }
-            if (j >= 2) {
-              const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
-              mx = fmaf(d2, d2, mx);
-            }
-            prev2 = prev1;
-            prev1 = o;
-          } else {
-            const int k = j - p.S;
-            if (ms) {
-              const float d = o - __ldg(ms + k);
-              met = fmaf(d, d, met);
-            }
-            if (k == p.f1_idx) f1 = o;
-            if (k == p.f2_idx) f2 = o;
+        const float o = v[i] + b[i];
+        v[i] = o;
+        if (j < p.S) {
+          if (has_t) {
+            const float d = o - t[i];
+            rec = fmaf(d, d, rec);
+          }
+          if (j >= 2) {
+            const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
+            mx = fmaf(d2, d2, mx);
+          }
+          prev2 = prev1;
+          prev1 = o;
+        } else if (j < OUT) {
+          const int k = j - p.S;
+          if (ms) {
+            const float d = o - __ldg(ms + k);
+            met = fmaf(d, d, met);
+          }
+          if (k == p.f1_idx) f1 = o;
+          if (k == p.f2_idx) f2 = o;
+        }
+      }
+      if (p.out_full) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sts_f32(tb + (uint32_t)(cx.lane * 33 + i) * 4u, v[i]);
+        __syncwarp();
+        const int col = j0 + cx.lane;
+        if (col < OUT) {
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int r = row0 + i;
+            if (r < g.M) p.out_full[(size_t)r * OUT + col] = lds_f32(tb + (uint32_t)(i * 33 + cx.lane) * 4u);
           }
         }
+        __syncwarp();
       }
     }
     if (!valid) return;

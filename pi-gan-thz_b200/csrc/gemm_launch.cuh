@@ -25,7 +25,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   const int grid = units < ctas ? units : ctas;
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
+  note_launch(), kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

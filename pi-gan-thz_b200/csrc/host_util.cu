@@ -3,6 +3,8 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
+#include <atomic>
+
 namespace pigan {
 
 static thread_local std::string g_last_error;
@@ -18,6 +20,10 @@ int fail(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached_dev = -1;
@@ -68,6 +74,8 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 
 extern "C" int pigan_abi_version(void) { return PIGAN_ABI_VERSION; }
 extern "C" const char* pigan_last_error(void) { return pigan::g_last_error.c_str(); }
+namespace pigan { long long launch_count(); }
+extern "C" int64_t pigan_launch_count(void) { return pigan::launch_count(); }
 
 #include "layout.h"
 

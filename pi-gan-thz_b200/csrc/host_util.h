@@ -36,6 +36,7 @@ int fail(int code, const char* fmt, ...);
     if (_s != PIGAN_OK) return _s;                                                       \
   } while (0)
 
+void note_launch();          // every kernel launch of the library passes through here (pigan_launch_count)
 int sm_count();  // multiprocessors of the current device (cached per device)
 
 // Row-major 2-D fp16 tensor [outer, inner] with row pitch ld_elems; box = [box_outer, box_inner],

@@ -144,7 +144,7 @@ extern "C" int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s,
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   const int vpl = (s + 31) / 32;
 #define PIGAN_LAUNCH_PHYS(V)                                                                        \
-  physics_metrics_kernel<V><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx,    \
+  note_launch(), physics_metrics_kernel<V><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx,    \
                                                   baseline_transmission, out_idx, out_metrics)
   if (vpl <= 8) PIGAN_LAUNCH_PHYS(8);
   else if (vpl <= 16) PIGAN_LAUNCH_PHYS(16);

@@ -144,15 +144,15 @@ extern "C" int pigan_topk_smallest(const float* scores, const int64_t* in_indice
   const int cap = sm_count() * 8;
   if (cap <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (grid > cap) grid = cap;
-  topk_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
+  note_launch(), topk_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
   for (int pass = 0; pass < 8; ++pass) {
-    topk_hist_kernel<<<grid, 256, 0, st>>>(scores, (long long)n, pass, state, hist);
-    topk_pick_kernel<<<1, 256, 0, st>>>(state, hist, pass);
+    note_launch(), topk_hist_kernel<<<grid, 256, 0, st>>>(scores, (long long)n, pass, state, hist);
+    note_launch(), topk_pick_kernel<<<1, 256, 0, st>>>(state, hist, pass);
   }
-  topk_collect_kernel<<<grid, 256, 0, st>>>(scores, (long long)n, state, keys, k);
+  note_launch(), topk_collect_kernel<<<grid, 256, 0, st>>>(scores, (long long)n, state, keys, k);
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
-  topk_sort_kernel<<<1, 1024, n2 * sizeof(unsigned long long), st>>>(
+  note_launch(), topk_sort_kernel<<<1, 1024, n2 * sizeof(unsigned long long), st>>>(
       keys, k, scores, reinterpret_cast<const long long*>(in_indices), (long long)index_base, out_scores,
       reinterpret_cast<long long*>(out_indices));
   PIGAN_CUDA_OK(cudaGetLastError());

@@ -58,6 +58,14 @@ class Engine:
         self._f_params = f_flat  # keep alive: the engine reads biases / norm weights from it
         check(lib.pigan_engine_load_forward_model(self.handle, f_flat.data_ptr(), native.current_stream()))
 
+    def set_spectrum_center(self, center: Optional[torch.Tensor]) -> None:
+        """One centring row for every rank of a data-parallel job (see include/pigan_b200.h); None = per call."""
+        if center is not None:
+            _require_cuda(center, "center")
+            center = _f32c(center).reshape(-1)
+        self._center = center  # keep alive
+        check(lib.pigan_engine_set_spectrum_center(self.handle, native.ptr(center)))
+
     # ------------------------------------------------------------------ module forwards
     def generator_forward(self, g_flat, bn, nbt, spectrum, training: bool) -> torch.Tensor:
         _require_cuda(spectrum, "spectrum")
@@ -114,6 +122,21 @@ class Engine:
     def loss_sums(self) -> torch.Tensor:
         return self._wrap(lib.pigan_engine_loss_sums(self.handle), 16, torch.float64)
 
+    # ------------------------------------------------------------------ instrumentation
+    def profile_begin(self, sections=None) -> None:
+        csv = ",".join(sections).encode() if sections else None
+        check(lib.pigan_engine_profile_begin(self.handle, csv))
+
+    def profile_end(self) -> Dict[str, tuple]:
+        """{section: (count, total_ms)} measured with CUDA events on the launching stream."""
+        buf = C.create_string_buffer(16384)
+        check(lib.pigan_engine_profile_end(self.handle, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
     # ------------------------------------------------------------------ scoring
     def score_candidates(self, g_flat, bn, spectra=None, target=None, noise=None, sigma: float = 0.01,
                          want_params=True) -> Dict[str, torch.Tensor]:
@@ -149,6 +172,11 @@ def topk_smallest(scores: torch.Tensor, k: int, index_base: int = 0, in_indices:
     check(lib.pigan_topk_smallest(s.data_ptr(), native.ptr(idx), n, k, int(index_base), out_s.data_ptr(),
                                   out_i.data_ptr(), ws.data_ptr(), nbytes, native.current_stream()))
     return out_s, out_i
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by the native library in this process so far."""
+    return int(lib.pigan_launch_count())
 
 
 _ENGINES: Dict[int, Engine] = {}

@@ -69,6 +69,9 @@ class PiganTrainArgs(C.Structure):
 SIGNATURES = {
     "pigan_abi_version": (_i32, []),
     "pigan_last_error": (C.c_char_p, []),
+    "pigan_launch_count": (_i64, []),
+    "pigan_engine_profile_begin": (_i32, [_vp, C.c_char_p]),
+    "pigan_engine_profile_end": (_i32, [_vp, C.c_char_p, C.c_size_t]),
     "pigan_default_dims": (None, [C.POINTER(PiganDims)]),
     "pigan_generator_param_count": (_i64, [C.POINTER(PiganDims)]),
     "pigan_discriminator_param_count": (_i64, [C.POINTER(PiganDims)]),
@@ -78,6 +81,7 @@ SIGNATURES = {
     "pigan_engine_create": (_i32, [C.POINTER(_vp), C.POINTER(PiganDims), _i64, _vp, C.c_size_t, _vp]),
     "pigan_engine_destroy": (_i32, [_vp]),
     "pigan_engine_load_forward_model": (_i32, [_vp, _vp, _vp]),
+    "pigan_engine_set_spectrum_center": (_i32, [_vp, _vp]),
     "pigan_generator_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pigan_discriminator_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "pigan_forward_model_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),

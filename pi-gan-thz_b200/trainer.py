@@ -38,6 +38,7 @@ class NativeTrainer:
         self.d_grads, self.d_m, self.d_v = (torch.zeros_like(dp) for _ in range(3))
         self.losses = torch.zeros(9, device=self.device, dtype=torch.float32)
         self.step_count = 0
+        self._center = None
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         lam = dict(lambda_recon=100.0, lambda_physics_spectrum=10.0, lambda_physics_metrics=1.0, lambda_maxwell=1.0,
@@ -81,6 +82,12 @@ class NativeTrainer:
         if self.world == 1:
             self.engine.train_step(args)
             return self.losses
+        if self._center is None:
+            # one centring row on all ranks (the exchanged BatchNorm sums are sums of centred pre-activations)
+            c = spectrum[:512].mean(dim=0)
+            dist.all_reduce(c, group=self.pg)
+            self._center = c / self.world
+            self.engine.set_spectrum_center(self._center)
         # data-parallel schedule: the engine's phases with NCCL all-reduces of the batch-coupled sums between
         # them (BatchNorm forward/backward statistics, gradients, loss sums) — include/pigan_b200.h
         e = self.engine

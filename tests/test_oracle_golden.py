@@ -172,3 +172,29 @@ def test_scoring_matches_reference_evaluator():
     _close((viol > 0).float().mean(), g["agg_param_range_violation_rate"])
     _close(err.mean(), g["agg_reconstruction_error_mean"], rtol=1e-5)
     _close(cons.numpy().std(), g["agg_consistency_score_std"], rtol=1e-4)
+
+
+def test_bf16_autocast_reference_is_looser():
+    """Yard-stick for the GPU tolerances (tests/test_gpu_engine.py): the reference step under torch's own bf16
+    autocast deviates from its fp32 self by ~1e-2 on D gradients and several 1e-2 on G gradients — the '1e-3
+    relative (bf16)' class of north_star is the budget the fp16-operand CUDA path has to stay inside."""
+    torch.set_num_threads(4)
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(2048, seed=100)
+    b = (spec, praw, pnorm, None, mnorm)
+
+    def run(autocast):
+        g2, d2 = copy.deepcopy(g_sd), copy.deepcopy(d_sd)
+        og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                return O.train_step(g2, d2, f_sd, og, od, b, 2e-4, 2e-4)
+        return O.train_step(g2, d2, f_sd, og, od, b, 2e-4, 2e-4)
+
+    (_, e32), (_, e16) = run(False), run(True)
+
+    def rel(a, b_):
+        return float((a.double() - b_.double()).norm() / b_.double().norm())
+
+    assert rel(e16["d_grads"]["main.2.weight"].float(), e32["d_grads"]["main.2.weight"]) > 2e-3
+    assert rel(e16["g_grads"]["main.3.weight"].float(), e32["g_grads"]["main.3.weight"]) > 2e-3
