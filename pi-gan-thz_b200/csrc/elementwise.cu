@@ -43,7 +43,7 @@ __device__ __forceinline__ void zero8(float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
 }
-constexpr int kUnroll = 4;  // rows a thread keeps in flight per loop trip in the streaming kernels
+constexpr int kUnroll = 2;  // rows a thread keeps in flight per loop trip in the streaming kernels
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -62,19 +62,24 @@ struct ColMap {
     rg = threadIdx.x / cpr;
   }
 };
-// Sum acc8 over the block's row groups and add it to dst[ch*8 .. ch*8+8) (one atomic per column per block).
-__device__ __forceinline__ void block_colsum_atomic(const float* acc8, float* dst, const ColMap& m, float mult,
-                                                    float* sm) {
+// Sum acc8 over the block's row groups and store it to this block's row of the partial-sum scratch
+// (part = scratch + blockIdx.x * ld + array offset).  No atomics: thousands of same-line float atomics serialise
+// in L2 (measured ~3.7 ns each on B200, 70 us for one BatchNorm statistic); reduce_partials_kernel finishes the
+// sum in a fixed order, which also makes the batch statistics and gradients run-to-run deterministic.
+__device__ __forceinline__ void block_colsum_partial(const float* acc8, float* part, const ColMap& m, float* sm) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) sm[(m.rg * m.cpr + m.ch) * 8 + i] = acc8[i];
   __syncthreads();
-  if (m.rg == 0 && dst != nullptr) {
+  if (m.rg == 0) {
+    float t[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float t = 0.f;
-      for (int gq = 0; gq < m.rpb; ++gq) t += sm[(gq * m.cpr + m.ch) * 8 + i];
-      atomicAdd(dst + m.ch * 8 + i, t * mult);
+      t[i] = 0.f;
+      for (int gq = 0; gq < m.rpb; ++gq) t[i] += sm[(gq * m.cpr + m.ch) * 8 + i];
     }
+    float4* o = reinterpret_cast<float4*>(part + m.ch * 8);
+    o[0] = make_float4(t[0], t[1], t[2], t[3]);
+    o[1] = make_float4(t[4], t[5], t[6], t[7]);
   }
   __syncthreads();
 }
@@ -95,6 +100,34 @@ inline int grid_for_rows(int64_t rows, int rows_per_block, int max_blocks = 148 
   int64_t b = (rows + rows_per_block - 1) / rows_per_block;
   if (b < 1) b = 1;
   return (int)(b < max_blocks ? b : max_blocks);
+}
+
+// dst[c] += mult * sum_b part[b * ld + off + c] for up to 8 column segments (one block per 32 columns)
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(ReduceArgs a) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (col < a.ld)
+    for (int b = ty; b < a.nblocks; b += 32) s += a.part[(size_t)b * a.ld + col];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < a.ld) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][tx];
+    int off = 0;
+    for (int g = 0; g < a.nseg; ++g) {
+      if (col < off + a.seg[g].ncols) {
+        if (a.seg[g].dst) a.seg[g].dst[col - off] += a.seg[g].mult * t;
+        break;
+      }
+      off += a.seg[g].ncols;
+    }
+  }
+}
+void launch_reduce_partials(const ReduceArgs& a, cudaStream_t st) {
+  note_launch(), reduce_partials_kernel<<<(a.ld + 31) / 32, 1024, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------ spectrum prep
@@ -238,7 +271,7 @@ __global__ void copy_pad_f32_kernel(const float* __restrict__ src, int n, float*
 
 // ------------------------------------------------------------------------------------------ BatchNorm
 __global__ void __launch_bounds__(kThreads) colstats_kernel(const __half* __restrict__ h, long long rows, int C,
-                                                            float* __restrict__ sum, float* __restrict__ sumsq) {
+                                                            float* __restrict__ part) {
   __shared__ float sm[kThreads * 8];
   const ColMap m(C);
   float s[8], q[8];
@@ -261,8 +294,9 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(const __half* __rest
         q[i] = fmaf(v[u][i], v[u][i], q[i]);
       }
   }
-  block_colsum_atomic(s, sum, m, 1.f, sm);
-  block_colsum_atomic(q, sumsq, m, 1.f, sm);
+  part += (size_t)blockIdx.x * 2 * C;
+  block_colsum_partial(s, part, m, sm);
+  block_colsum_partial(q, part + C, m, sm);
 }
 
 __global__ void bn_finalize_kernel(BnFinalizeArgs a) {
@@ -499,13 +533,14 @@ __global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
     }
   }
   if (APPLY) {
-    block_colsum_atomic(sdy, a.dbias, m, a.inv_gs, sm);
+    block_colsum_partial(sdy, a.part + (size_t)blockIdx.x * a.C, m, sm);
     return;
   }
-  block_colsum_atomic(sdy, a.sum_dy, m, 1.f, sm);
-  block_colsum_atomic(sdyx, a.sum_dyx, m, 1.f, sm);
+  float* part = a.part + (size_t)blockIdx.x * 6 * a.C;
+  block_colsum_partial(sdy, part, m, sm);
+  block_colsum_partial(sdyx, part + a.C, m, sm);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) block_colsum_atomic(dw[j], a.dw3 + j * a.C, m, a.inv_gs, sm);
+  for (int j = 0; j < 4; ++j) block_colsum_partial(dw[j], part + (2 + j) * a.C, m, sm);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float t = block_sum(db[j], sm);
@@ -518,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
 __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(
     const __half* __restrict__ da, const __half* __restrict__ h, const float* __restrict__ scale,
     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ rstd,
-    float* __restrict__ sum_dy, float* __restrict__ sum_dyx, long long rows, int C) {
+    float* __restrict__ part, long long rows, int C) {
   __shared__ float sm[kThreads * 8];
   const ColMap m(C);
   float sc[8], bi[8], mu[8], rs[8], s1[8], s2[8];
@@ -551,8 +586,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(
         s2[i] = fmaf(dy, (x[u][i] - mu[i]) * rs[i], s2[i]);
       }
   }
-  block_colsum_atomic(s1, sum_dy, m, 1.f, sm);
-  block_colsum_atomic(s2, sum_dyx, m, 1.f, sm);
+  part += (size_t)blockIdx.x * 2 * C;
+  block_colsum_partial(s1, part, m, sm);
+  block_colsum_partial(s2, part + C, m, sm);
 }
 
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(BnBwdArgs a) {
@@ -607,7 +643,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(BnBwdArgs a) {
       st_h8(a.dh + r * a.C + m.ch * 8, g[u]);
     }
   }
-  block_colsum_atomic(sdh, a.dbias, m, a.inv_gs, sm);
+  if (a.dbias) block_colsum_partial(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
 }
 
 // ------------------------------------------------------------------------------------------ discriminator
@@ -616,7 +652,7 @@ __global__ void __launch_bounds__(kThreads) d_l2_bwd_kernel(const __half* __rest
                                                             const float* __restrict__ w3, __half* __restrict__ dh2,
                                                             float* __restrict__ dw3, float* __restrict__ db2,
                                                             float* __restrict__ db3, long long rows, int C,
-                                                            float inv_gs) {
+                                                            float inv_gs, float* __restrict__ part) {
   __shared__ float sm[kThreads * 8];
   const ColMap m(C);
   float w[8], sw[8], sb[8];
@@ -652,8 +688,9 @@ __global__ void __launch_bounds__(kThreads) d_l2_bwd_kernel(const __half* __rest
     }
   }
   if (dw3 != nullptr) {
-    block_colsum_atomic(sw, dw3, m, inv_gs, sm);
-    block_colsum_atomic(sb, db2, m, inv_gs, sm);
+    part += (size_t)blockIdx.x * 2 * C;
+    block_colsum_partial(sw, part, m, sm);
+    block_colsum_partial(sb, part + C, m, sm);
     const float t = block_sum(s3, sm);
     if (threadIdx.x == 0) atomicAdd(db3, t * inv_gs);
   }
@@ -849,9 +886,12 @@ void launch_extract_wp(const float* w, int ld_src, int S, int P, float* wp, int 
 void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStream_t st) {
   note_launch(), copy_pad_f32_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
 }
-void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, cudaStream_t st) {
+void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  note_launch(), colstats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(h, rows, C, sum, sumsq);
+  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  note_launch(), colstats_kernel<<<grid, kThreads, 0, st>>>(h, rows, C, part);
+  ReduceArgs r{part, grid, 2 * C, 2, {{sum, C, 1.f}, {sumsq, C, 1.f}}};
+  launch_reduce_partials(r, st);
 }
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
   note_launch(), bn_finalize_kernel<<<(a.C + 255) / 256, 256, 0, st>>>(a);
@@ -873,26 +913,46 @@ void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, 
 }
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 8);
-  const int grid = grid_for_rows(a.rows, rpb * 8, 148 * 8);
-  if (apply) note_launch(), g_head_bwd_kernel<true><<<grid, kThreads, 0, st>>>(a);
-  else note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
+  const int grid = grid_for_rows(a.rows, rpb * 8, kPartBlocks);
+  if (apply) {
+    note_launch(), g_head_bwd_kernel<true><<<grid, kThreads, 0, st>>>(a);
+    ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
+    launch_reduce_partials(r, st);
+  } else {
+    note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
+    ReduceArgs r{a.part, grid, 6 * a.C, 6,
+                 {{a.sum_dy, a.C, 1.f}, {a.sum_dyx, a.C, 1.f}, {a.dw3, a.C, a.inv_gs}, {a.dw3 + a.C, a.C, a.inv_gs},
+                  {a.dw3 + 2 * a.C, a.C, a.inv_gs}, {a.dw3 + 3 * a.C, a.C, a.inv_gs}}};
+    launch_reduce_partials(r, st);
+  }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
-                         cudaStream_t st) {
+                         float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  note_launch(), bn_bwd_stats_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(da, h, scale, bias, mean, rstd,
-                                                                                sum_dy, sum_dyx, rows, C);
+  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  note_launch(), bn_bwd_stats_kernel<<<grid, kThreads, 0, st>>>(da, h, scale, bias, mean, rstd, part, rows, C);
+  ReduceArgs r{part, grid, 2 * C, 2, {{sum_dy, C, 1.f}, {sum_dyx, C, 1.f}}};
+  launch_reduce_partials(r, st);
 }
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 8);
-  note_launch(), bn_bwd_apply_kernel<<<grid_for_rows(a.rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(a);
+  const int grid = grid_for_rows(a.rows, rpb * 8, kPartBlocks);
+  note_launch(), bn_bwd_apply_kernel<<<grid, kThreads, 0, st>>>(a);
+  if (a.dbias) {
+    ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
+    launch_reduce_partials(r, st);
+  }
 }
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
-                     float* db3, int64_t rows, int C, float inv_gs, cudaStream_t st) {
+                     float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  note_launch(), d_l2_bwd_kernel<<<grid_for_rows(rows, rpb * 8, 148 * 8), kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows,
-                                                                            C, inv_gs);
+  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  note_launch(), d_l2_bwd_kernel<<<grid, kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
+  if (dw3 != nullptr) {
+    ReduceArgs r{part, grid, 2 * C, 2, {{dw3, C, inv_gs}, {db2, C, inv_gs}}};
+    launch_reduce_partials(r, st);
+  }
 }
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,
                  int64_t rows, int C, cudaStream_t st) {

@@ -9,7 +9,25 @@
 
 namespace pigan {
 
-constexpr float kParamCenter = 2.5f;  // structure parameters live in (2.2, 2.8): centred before the fp16 cast
+constexpr float kParamCenter = 2.5f;
+
+// Batch reductions (column sums over all rows) are two-stage and atomic-free: each of at most kPartBlocks blocks
+// stores its partial column sums to one row of a scratch matrix, reduce_partials_kernel adds the rows in a fixed
+// order.  The engine provides kPartBlocks * kPartCols floats of scratch.
+constexpr int kPartBlocks = 148 * 4;
+constexpr int kPartCols = 6 * 512;
+struct ReduceSeg {
+  float* dst;   // dst[c] += mult * column sum (nullptr: skip)
+  int ncols;
+  float mult;
+};
+struct ReduceArgs {
+  const float* part;
+  int nblocks;
+  int ld;       // columns in use (sum of seg[].ncols)
+  int nseg;
+  ReduceSeg seg[8];
+};
 
 // ------------------------------------------------------------------------------------------ spectrum prep
 // cvec[j] = mean of x[0:rows_used, j] (j < S), 0 for S <= j < Kp.  Any constant row works (the shift is undone
@@ -39,7 +57,7 @@ void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStr
 
 // ------------------------------------------------------------------------------------------ BatchNorm (G)
 // sum[c] += sum_r h[r,c], sumsq[c] += sum_r h[r,c]^2
-void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, cudaStream_t st);
+void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st);
 struct BnFinalizeArgs {
   const float* sum;       // sums over the (global) batch of the stored (bias-free) pre-activation
   const float* sumsq;
@@ -94,13 +112,14 @@ struct GHeadBwdArgs {
   float* dgamma;          // [C] += sum_dyx / GS
   float* dbeta;           // [C] += sum_dy / GS
   double inv_n;           // 1 / global batch
+  float* part;            // partial-sum scratch (kPartBlocks x 6C floats)
 };
 // apply = false: statistics pass (sum_dy, sum_dyx, dw3, db3, range_sum); apply = true: writes dy2 (see kernel)
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st);
 // relu-masked column sums for the BatchNorm backward: dy = da * [scale*h+bias > 0]
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
-                         cudaStream_t st);
+                         float* part, cudaStream_t st);
 struct BnBwdArgs {
   const __half* dy;   // [B,C] scaled
   const __half* h;    // [B,C]
@@ -120,6 +139,7 @@ struct BnBwdArgs {
   float inv_gs;
   int64_t rows;
   int C;
+  float* part;        // partial-sum scratch (kPartBlocks x C floats)
 };
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
 
@@ -127,7 +147,7 @@ void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
 // dh2[r,c] = dlogit[r] * w3[c] * LeakyReLU'(z2[r,c]); dw3[c] += sum_r dlogit[r] z2[r,c] / GS;
 // db2[c] += sum_r dh2[r,c] / GS; db3 += sum_r dlogit[r] / GS   (discriminator.py:24-26 backward)
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
-                     float* db3, int64_t rows, int C, float inv_gs, cudaStream_t st);
+                     float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ forward model
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,

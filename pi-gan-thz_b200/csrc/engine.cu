@@ -20,7 +20,7 @@ namespace {
 constexpr int kKp = 256;  // spectrum operand width (S + P + 2 spare columns <= 256)
 using CfgS = GemmCfg<256, 1, 3, false>;   // store epilogues (2 x 32 KB staging)
 using CfgP = GemmCfg<256, 1, 4, false>;   // no staging
-using CfgO = GemmCfg<144, 2, 4, false>;   // forward-model output layer
+using CfgO = GemmCfg<144, 2, 2, false>;   // forward-model output layer (64 KB target tile in the epilogue)
 using CfgW = GemmCfg<256, 1, 4, true>;    // weight gradients
 
 // loss_sums indices (fp64)
@@ -101,6 +101,7 @@ struct PiganEngine {
   // fp16 weights
   __half *g_w1h, *g_w2h, *g_w2th, *d_w1h, *d_w2h, *d_w2th, *f_wh[6];
   // fp32 scratch
+  float *partials;                     // [kPartBlocks x kPartCols] two-stage batch reductions
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
   float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
   float *mean1, *rstd1, *scale1, *bias1, *mean2, *rstd2, *scale2, *bias2;
@@ -142,6 +143,7 @@ struct PiganEngine {
       f_wh[i] = c.take<__half>((size_t)out * in);
       in = out;
     }
+    partials = c.take<float>((size_t)kPartBlocks * kPartCols);
     p = c.take<float>(B * 4);
     pden = c.take<float>(B * 4);
     dpden = c.take<float>(B * 4);
@@ -287,8 +289,8 @@ int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st) {
 void g_bn_stats(PiganEngine* e, int which, int64_t n, cudaStream_t st) {
   const int H1 = e->gl.H1, H2 = e->gl.H2;
   PM("g_bn_colstats");
-  if (which == 1) launch_colstats(e->g_h1, n, H1, e->bn_sums, e->bn_sums + H1, st);
-  else launch_colstats(e->g_h2, n, H2, e->bn_sums + 2 * H1, e->bn_sums + 2 * H1 + H2, st);
+  if (which == 1) launch_colstats(e->g_h1, n, H1, e->bn_sums, e->bn_sums + H1, e->partials, st);
+  else launch_colstats(e->g_h2, n, H2, e->bn_sums + 2 * H1, e->bn_sums + 2 * H1 + H2, e->partials, st);
 }
 void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offset, float* bn_buffers,
                    int64_t* nbt, double n_global, int num_updates, cudaStream_t st) {
@@ -358,8 +360,7 @@ int d_layer2(PiganEngine* e, const float* dp, const DL2Opts& o, cudaStream_t st)
 
 // ------------------------------------------------------------------------------------------ forward model
 struct FOutOpts {
-  const float* target_spec;
-  int target_ld;
+  int target_mode;  // 0 none, 1 one fp32 row (e->cvec holds it, padded), 2 the centred fp16 operand e->xc + e->cvec
   const float* target_metrics;
   const float* p_norm;
   double* sums;
@@ -389,8 +390,10 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   ep.bias = e->f_bias_out;
   ep.S = L.S;
   ep.Mt = L.Mt;
-  ep.target_spec = o.target_spec;
-  ep.target_ld = o.target_ld;
+  ep.target_mode = o.target_mode;
+  ep.target_row = e->cvec;
+  ep.center = e->cvec;
+  PIGAN_TRY(make_tmap_f16_2d(&ep.tgt, e->xc, kKp, (uint64_t)n, kKp, 64, kBlockM));
   ep.target_metrics = o.target_metrics;
   ep.p_norm = o.p_norm;
   ep.sums = o.sums;
@@ -421,7 +424,7 @@ GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
   hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = e->sums + kSumRange;
   hb.inv_gs = inv_gs; hb.rows = a.batch; hb.C = G.H2;
   hb.gamma = gp + G.bn2_w; hb.dbias = a.g_grads + G.b2; hb.dgamma = a.g_grads + G.bn2_w;
-  hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch;
+  hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch; hb.part = e->partials;
   return hb;
 }
 
@@ -471,7 +474,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY(d_layer2(e, dp, o, st));
       PM("d_l2_bwd");
       launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, a.d_grads + D.w3, a.d_grads + D.b2, a.d_grads + D.b3,
-                      BP + B, D.H2, inv_gs, st);
+                      BP + B, D.H2, inv_gs, e->partials, st);
       {
         PM("d_dh1_gemm");
         using Epi = EpiLeakyMaskStore<CfgS>;
@@ -503,14 +506,14 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       DL2Opts o{B, B, 1.0f, 1.0f, 0, 0, NG, e->sums + kSumAdv, nullptr, true, true};
       PIGAN_TRY(d_layer2(e, dp, o, st));
       PM("d_l2_bwd");
-      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, st);
+      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, e->partials, st);
       {
         PM("d_paramgrad_gemm");
         using Epi = EpiDiscParamGrad<CfgP>;
         Epi::Params ep{e->d_z1, D.H1, e->d_wp, e->dpden};
         PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
-      FOutOpts fo{a.spectrum, G.S, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
+      FOutOpts fo{2, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
                   a.f1_idx, a.f2_idx};
       PIGAN_TRY(f_forward(e, e->p, B, fo, st));
       PM("g_head_bwd");
@@ -527,7 +530,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY((linear_store<false, false, false>(e->g_dy2, B, G.H2, e->g_w2th, G.H1, nullptr, e->g_da1, nullptr, st)));
       PM("g_bn_bwd_stats");
       launch_bn_bwd_stats(e->g_da1, e->g_h1, e->scale1, e->bias1, e->mean1, e->rstd1, e->bn_bwd_sums + 2 * G.H2,
-                          e->bn_bwd_sums + 2 * G.H2 + G.H1, B, G.H1, st);
+                          e->bn_bwd_sums + 2 * G.H2 + G.H1, B, G.H1, e->partials, st);
       break;
     }
     case 5: {
@@ -536,7 +539,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       bb.scale = e->scale1; bb.bias = e->bias1; bb.mean = e->mean1; bb.rstd = e->rstd1; bb.gamma = gp + G.bn1_w;
       bb.sum_dy = e->bn_bwd_sums + 2 * G.H2; bb.sum_dyx = e->bn_bwd_sums + 2 * G.H2 + G.H1;
       bb.dh = e->g_da1; bb.dbias = nullptr; bb.dgamma = a.g_grads + G.bn1_w; bb.dbeta = a.g_grads + G.bn1_b;
-      bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H1;
+      bb.inv_n = 1.0 / NG; bb.inv_gs = inv_gs; bb.rows = B; bb.C = G.H1; bb.part = e->partials;
       PM("g_bn_bwd_apply");
       launch_bn_bwd_apply(bb, st);
       PM("g_dw1_gemm");
@@ -705,7 +708,7 @@ extern "C" int pigan_forward_model_forward(PiganEngine* e, const float* p_norm, 
                                            void* stream) {
   PIGAN_CHECK_ARG(e && p_norm && out && n >= 1 && n <= e->max_batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  FOutOpts fo{nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.f, out, nullptr, 0, 1};
+  FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, out, nullptr, 0, 1};
   PIGAN_TRY(f_forward(e, p_norm, n, fo, st));
   PM(nullptr);
   return PIGAN_OK;
@@ -806,7 +809,8 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
   launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, p, nullptr, e->xc, nullptr, n, G.H2, kKp,
                     G.S, st);
   float* err = out_err ? out_err : e->row_err;
-  FOutOpts fo{spectra ? spectra : target, spectra ? G.S : 0, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
+  // per-candidate error against its own spectrum (given spectra) or against the design target (cvec = target)
+  FOutOpts fo{spectra ? 2 : 1, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
   PIGAN_TRY(f_forward(e, p, n, fo, st));
   PM("small");
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);

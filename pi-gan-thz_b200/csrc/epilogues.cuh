@@ -340,61 +340,96 @@ struct EpiDiscParamGrad {
 // =====================================================================================================
 template <class Cfg>
 struct EpiFwdOut {
-  static_assert(Cfg::BLOCK_N == 144 && Cfg::ACC_TILES == 2, "EpiFwdOut tile shape");
+  static_assert(Cfg::BLOCK_N == 144 && Cfg::ACC_TILES == 2 && Cfg::ACC_BUFS == 1, "EpiFwdOut tile shape");
   struct Params {
     const float* bias;            // [288] zero-padded
     int S, Mt;
-    const float* target_spec;     // [M,S] fp32 (row pitch target_ld; 0 = one target row for all) or null
-    int target_ld;
+    // reconstruction target, one of:
+    //   target_mode 1: one fp32 row for all candidates (target_row, zero-padded to 256)
+    //   target_mode 2: per-row spectra as the centred fp16 operand copy [M,256] (tgt map, 128 x 64 boxes)
+    //                  + the centring row (center, fp32, zero-padded to 256): x = fp16 + center
+    int target_mode;
+    const float* target_row;
+    CUtensorMap tgt;
+    const float* center;
     const float* target_metrics;  // [M,Mt] or null
     const float* p_norm;          // [M,4] generator output (LC loss) or null
     double* sums;                 // [0]=sum (recon-x)^2 [1]=sum (pm-m)^2 [2]=sum d2^2 [3]=sum lc1 [4]=sum lc2
     float* dp_lc;                 // [M,4] d(lambda_lc * LC)/dp * GS  or null
     float lc_grad_mult;           // lambda_lc * GS / global batch
-    float* out_full;              // [M,S+Mt] fp32 or null
+    float* out_full;              // [M,S+Mt] fp32 or null (target_mode must be 0 or 1: shares the staging area)
     float* row_err;               // [M] mean_j (x - recon)^2 or null
     int f1_idx, f2_idx;
   };
-  // per-warp [32 rows][33] fp32 transposition buffer: global reads/writes of per-row data stay coalesced
-  // (lane <-> column) while the math keeps one thread per row (row = TMEM lane)
-  static constexpr int SMEM_BYTES = 17408;  // 4 warps * 32 * 33 * 4 B = 16896, rounded to 1 KB
+  // [0, 64 KB): target tile, 4 swizzled [128 x 64] fp16 boxes (TMA), or the per-warp [32][33] fp32 transposition
+  // buffers of the out_full path; [64 KB, +8): mbarrier of the target loads
+  static constexpr int kTileBytes = 4 * kStageBytes;
+  static constexpr int SMEM_BYTES = kTileBytes + 1024;
   struct State {
     float s_rec, s_met, s_mx, s_lc1, s_lc2;
+    uint32_t tphase;
   };
-  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) {
+  __device__ static void issue_target(const Params& p, const EpiCtx& cx, int m_tile) {
+    const uint32_t bar = cx.smem + kTileBytes;
+    mbar_arrive_expect_tx(bar, kTileBytes);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) tma_load_2d(cx.smem + b * kStageBytes, &p.tgt, bar, b * 64, m_tile * kBlockM);
+  }
+  __device__ static void init(const Params& p, State& st, const GemmShape& g, const EpiCtx& cx) {
     st.s_rec = st.s_met = st.s_mx = st.s_lc1 = st.s_lc2 = 0.f;
+    st.tphase = 0;
+    if (cx.group != 0 || p.target_mode != 2) return;  // ACC_BUFS == 1: only group 0 ever sees a unit
+    if (cx.tid == 0) {
+      mbar_init(cx.smem + kTileBytes, 1);
+      fence_barrier_init();
+      if ((int)blockIdx.x < g.num_m_tiles) issue_target(p, cx, blockIdx.x);
+    }
+    epi_bar_sync(cx, 0);
   }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
+    const int rt = cx.q * 32 + cx.lane;               // row within the tile
     const int row0 = w.m_tile * kBlockM + cx.q * 32;  // first row of this warp
     const int row = row0 + cx.lane;
     const bool valid = row < g.M;
     const int OUT = p.S + p.Mt;
-    const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 33u * 4u);  // this warp's buffer
+    const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 33u * 4u);  // this warp's transposition buffer
     float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
     float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
     const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
+    if (p.target_mode == 2) {
+      mbar_wait(cx.smem + kTileBytes, st.tphase);
+      st.tphase ^= 1u;
+    }
 #pragma unroll 1
     for (int j0 = 0; j0 < 288; j0 += 32) {
       float v[32];
       tmem_ld32(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
       float t[32];
-      const bool has_t = p.target_spec != nullptr && j0 < p.S;
+      const bool has_t = p.target_mode != 0 && j0 < p.S;
       if (has_t) {
-        // rows of this warp x columns [j0, j0+32): lane = column while loading, lane = row while reading back
-        const int col = j0 + cx.lane;
-        const bool col_ok = col < p.S;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int r = row0 + i;
-          float x = 0.f;
-          if (col_ok && r < g.M) x = __ldg(p.target_spec + (size_t)r * p.target_ld + col);
-          sts_f32(tb + (uint32_t)(i * 33 + cx.lane) * 4u, x);
-        }
-        __syncwarp();
+        if (p.target_mode == 1) {
+          load_cols32(p.target_row + j0, t);
+        } else {
+          float c[32];
+          load_cols32(p.center + j0, c);
+          const uint32_t box = cx.smem + (uint32_t)(j0 >> 6) * kStageBytes + (uint32_t)rt * 128u;
+          const int h4 = ((j0 >> 5) & 1) * 4;  // first 16-byte chunk of this 32-column half
 #pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] = lds_f32(tb + (uint32_t)(cx.lane * 33 + i) * 4u);
-        __syncwarp();
+          for (int i = 0; i < 4; ++i) {
+            uint32_t u0, u1, u2, u3;
+            const uint32_t addr = box + (uint32_t)(((h4 + i) ^ (rt & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr) : "memory");
+            const uint32_t uu[4] = {u0, u1, u2, u3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[k]));
+              t[8 * i + 2 * k] = f.x + c[8 * i + 2 * k];
+              t[8 * i + 2 * k + 1] = f.y + c[8 * i + 2 * k + 1];
+            }
+          }
+        }
       }
       float b[32];
       load_cols32(p.bias + j0, b);
@@ -427,6 +462,7 @@ struct EpiFwdOut {
         }
       }
       if (p.out_full) {
+        // lane = row while writing to shared memory, lane = column while storing: coalesced global writes
 #pragma unroll
         for (int i = 0; i < 32; ++i) sts_f32(tb + (uint32_t)(cx.lane * 33 + i) * 4u, v[i]);
         __syncwarp();
@@ -440,6 +476,12 @@ struct EpiFwdOut {
         }
         __syncwarp();
       }
+    }
+    if (p.target_mode == 2) {
+      // everyone is done with the tile: fetch the next one while the MMAs of the next unit run
+      epi_bar_sync(cx, 0);
+      const int next = w.m_tile + (int)gridDim.x;
+      if (cx.tid == 0 && next < g.num_m_tiles) issue_target(p, cx, next);
     }
     if (!valid) return;
     st.s_rec += rec;

@@ -46,6 +46,7 @@ class InverseDesigner:
         if self.chunk > engine.max_batch:
             raise ValueError("chunk exceeds the engine's max_batch")
         self.pg = process_group
+        self.topk_fn = None          # CPU tests inject a torch top-k; None = pigan_topk_smallest
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank(process_group) if on else 0
         self.world = dist.get_world_size(process_group) if on else 1
@@ -95,4 +96,4 @@ class InverseDesigner:
         valid = torch.isfinite(allrows[:, 0])
         allrows = allrows[valid]
         return merge_topk(allrows[:, 0].float().contiguous(), allrows[:, 1].long().contiguous(),
-                          allrows[:, 2:6].float().contiguous(), k)
+                          allrows[:, 2:6].float().contiguous(), k, topk_fn=self.topk_fn)

@@ -19,6 +19,29 @@ from . import native
 LOSS_KEYS = _engine.LOSS_KEYS
 
 
+def dp_phase_plan(h1: int, h2: int):
+    """[(phase, [(buffer, slice or None)])]: what every rank all-reduces (sum) after each phase of
+    pigan_train_step_phase.  h1, h2 = the generator's hidden widths (BatchNorm-1 / BatchNorm-2 channels)."""
+    return [
+        (0, [("bn_sums", slice(0, 2 * h1))]),                       # BatchNorm-1 sum, sum of squares
+        (1, [("bn_sums", slice(2 * h1, 2 * h1 + 2 * h2))]),         # BatchNorm-2
+        (2, [("d_grads", None)]),                                   # discriminator gradients (before clip+Adam)
+        (3, [("bn_bwd_sums", slice(0, 2 * h2))]),                   # BatchNorm-2 backward: sum dy, sum dy*xhat
+        (4, [("bn_bwd_sums", slice(2 * h2, 2 * h2 + 2 * h1))]),     # BatchNorm-1 backward
+        (5, [("g_grads", None), ("loss_sums", slice(0, 8))]),       # generator gradients, loss numerators
+        (6, []),                                                    # clip+Adam(G), loss finalisation
+    ]
+
+
+def run_dp_step(run_phase, get_buffer, all_reduce, plan) -> None:
+    """One data-parallel step: engine phases in order, each followed by its all-reduces (in place, sum)."""
+    for phase, reductions in plan:
+        run_phase(phase)
+        for name, sl in reductions:
+            buf = get_buffer(name)
+            all_reduce(buf if sl is None else buf[sl])
+
+
 class NativeTrainer:
     def __init__(self, generator, discriminator, forward_model, device, max_batch: int, cfg=None,
                  f1_idx: int = 0, f2_idx: int = 1, process_group=None):
@@ -91,23 +114,18 @@ class NativeTrainer:
         # data-parallel schedule: the engine's phases with NCCL all-reduces of the batch-coupled sums between
         # them (BatchNorm forward/backward statistics, gradients, loss sums) — include/pigan_b200.h
         e = self.engine
-        h1, h2 = e.dims.g_hidden[0], e.dims.g_hidden[1]
-        bn, bnb, ls = e.bn_sums(), e.bn_bwd_sums(), e.loss_sums()
-        e.train_step_phase(args, 0)
-        dist.all_reduce(bn[:2 * h1], group=self.pg)
-        e.train_step_phase(args, 1)
-        dist.all_reduce(bn[2 * h1:], group=self.pg)
-        e.train_step_phase(args, 2)
-        dist.all_reduce(self.d_grads, group=self.pg)
-        e.train_step_phase(args, 3)
-        dist.all_reduce(bnb[:2 * h2], group=self.pg)
-        e.train_step_phase(args, 4)
-        dist.all_reduce(bnb[2 * h2:], group=self.pg)
-        e.train_step_phase(args, 5)
-        dist.all_reduce(self.g_grads, group=self.pg)
-        dist.all_reduce(ls[:8], group=self.pg)
-        e.train_step_phase(args, 6)
+        run_dp_step(lambda ph: e.train_step_phase(args, ph), self._buffer,
+                    lambda t: dist.all_reduce(t, group=self.pg),
+                    dp_phase_plan(e.dims.g_hidden[0], e.dims.g_hidden[1]))
         return self.losses
+
+    def _buffer(self, name: str) -> torch.Tensor:
+        """Device buffers the data-parallel schedule reduces (dp_phase_plan)."""
+        if name == "d_grads":
+            return self.d_grads
+        if name == "g_grads":
+            return self.g_grads
+        return getattr(self.engine, name)()
 
     # ------------------------------------------------------------------ optimiser state for checkpoints
     def export_optimizer_state(self, optimizer_g, optimizer_d) -> None:

@@ -134,9 +134,16 @@ def _check_grads(native_flat, st, ref_grads, skip=(), tol=TOL_GRAD):
     assert not bad, f"gradient mismatch {bad} (all: {worst})"
 
 
-@pytest.mark.parametrize("n", [4096, 16384])
-def test_train_step_gradients_match_oracle(n):
-    """Unclipped gradients of the D-step and the G-step (train_pigan.py:123-187), read between the phases."""
+@pytest.mark.parametrize("n,tol_g", [(4096, 1.2e-2), (16384, 6e-3), (65536, 3e-3)])
+def test_train_step_gradients_match_oracle(n, tol_g):
+    """Unclipped gradients of the D-step and the G-step (train_pigan.py:123-187), read between the phases.
+
+    The generator's lower-layer gradients are ill-conditioned with respect to the FORWARD values: rounding only the
+    input spectra to fp16 and otherwise computing in fp64 already moves main.0.weight's gradient by 4e-3 at B=4096
+    (ReLU/LeakyReLU mask flips, BatchNorm statistics and the discriminator's response; measured with a
+    quantisation-aware fp64 restatement, DESIGN.md "Precision"), while rounding every backward tensor to fp16 moves
+    it by 3e-5.  The deviation averages down with the batch size, hence the per-size tolerance; the reference's own
+    bf16-autocast path is at 5e-2..7e-2 on the same tensors (tests/test_oracle_golden.py)."""
     from oracle import fixtures
     from oracle import models as O
     g_sd, d_sd, f_sd = _weights()
@@ -151,7 +158,9 @@ def test_train_step_gradients_match_oracle(n):
     # G gradients: after phase 5.  main.0.bias / main.3.bias feed a BatchNorm: their true gradient is zero and the
     # reference itself holds only rounding noise there (|g| < 1e-6 in the golden file) -> compared in absolute terms
     tr, G, D, _ = _native_step(g_sd, d_sd, f_sd, batch, 2e-4, 2e-4, n, phases_until=5)
-    _check_grads(tr.g_grads.clone(), tr.gs, ex["g_grads"], skip=("main.0.bias", "main.3.bias"))
+    _check_grads(tr.g_grads.clone(), tr.gs, ex["g_grads"], skip=("main.0.bias", "main.3.bias"), tol=tol_g)
+    upper = {k: v for k, v in ex["g_grads"].items() if k.startswith(("main.4", "main.6"))}
+    _check_grads(tr.g_grads.clone(), tr.gs, upper, tol=1e-3)       # layers above the last BatchNorm: well conditioned
     views = dict(zip(tr.gs.params.names, tr.gs.params.views_like(tr.g_grads)))
     gnorm = float(torch.cat([v.reshape(-1) for v in ex["g_grads"].values()]).norm())
     for name in ("main.0.bias", "main.3.bias"):
@@ -183,7 +192,10 @@ def test_train_step_matches_reference_golden():
             # gradient is within rounding of zero may land 2 lr away; everything else must agree to a fraction of lr
             off = np.abs(got - ref) > 0.1 * 2e-4
             degenerate = tag == "g" and name in ("main.0.bias", "main.3.bias")     # true gradient is zero (BN)
-            assert off.mean() <= (1.0 if degenerate else 0.02), (tag, name, off.mean())
+            # generator tensors below the last BatchNorm: ill-conditioned gradients (see the gradient test), and
+            # at B=64 a tenth of their elements sits within rounding of a zero gradient
+            lower = tag == "g" and name.split(".")[1] in ("0", "1", "3")
+            assert off.mean() <= (1.0 if degenerate else 0.10 if lower else 0.02), (tag, name, off.mean())
             assert np.max(np.abs(got - ref)) <= 2.05 * 2e-4, (tag, name)
 
 
@@ -226,35 +238,40 @@ def test_data_parallel_phases_equal_full_batch():
     g_sd, d_sd, f_sd = _weights()
     spec, praw, pnorm, mnorm = fixtures.make_batch(n, seed=55)
     full, Gf, Df, lf = _native_step(g_sd, d_sd, f_sd, (spec, praw, pnorm, None, mnorm), 2e-4, 2e-4, n)
-    ranks = []
+    ranks, keep = [], []
     for r in range(2):
         G, D, F = _models(g_sd, d_sd, f_sd)
         tr = NativeTrainer(G, D, F, torch.device(DEV), max_batch=n // 2)
         sl = slice(r * n // 2, (r + 1) * n // 2)
         tr.step_count += 1
-        a = tr._args(spec[sl].to(DEV).contiguous(), praw[sl].to(DEV).contiguous(), mnorm[sl].to(DEV).contiguous(),
-                     2e-4, 2e-4)
+        shard = (spec[sl].to(DEV).contiguous(), praw[sl].to(DEV).contiguous(), mnorm[sl].to(DEV).contiguous())
+        keep.append(shard)                                # the argument block holds raw pointers
+        a = tr._args(*shard, 2e-4, 2e-4)
         a.global_batch = n
         center = spec[:512].mean(dim=0).to(DEV)          # what NativeTrainer all-reduces once (trainer.py)
         tr.engine.set_spectrum_center(center)
         ranks.append((tr, a, G, D))
 
-    def allreduce(get):
-        bufs = [get(tr) for tr, _, _, _ in ranks]
-        total = bufs[0] + bufs[1]
-        for b in bufs:
-            b.copy_(total)
+    from pigan_b200.trainer import dp_phase_plan, run_dp_step
 
-    h1, h2 = 512, 256
-    sched = {0: [lambda t: t.engine.bn_sums()[:2 * h1]], 1: [lambda t: t.engine.bn_sums()[2 * h1:]],
-             2: [lambda t: t.d_grads], 3: [lambda t: t.engine.bn_bwd_sums()[:2 * h2]],
-             4: [lambda t: t.engine.bn_bwd_sums()[2 * h2:]],
-             5: [lambda t: t.g_grads, lambda t: t.engine.loss_sums()[:8]], 6: []}
-    for ph in range(7):
+    def run_phase(ph):
         for tr, a, _, _ in ranks:
             tr.engine.train_step_phase(a, ph)
-        for get in sched[ph]:
-            allreduce(get)
+
+    class AllRanks:                       # get_buffer returns the same-named buffer of every rank
+        def __init__(self, bufs):
+            self.bufs = bufs
+
+        def __getitem__(self, sl):
+            return AllRanks([b[sl] for b in self.bufs])
+
+    def all_reduce(x):                    # in-process stand-in for dist.all_reduce(sum)
+        total = x.bufs[0] + x.bufs[1]
+        for b in x.bufs:
+            b.copy_(total)
+
+    run_dp_step(run_phase, lambda name: AllRanks([tr._buffer(name) for tr, _, _, _ in ranks]), all_reduce,
+                dp_phase_plan(512, 256))
     torch.cuda.synchronize()
     for tr, a, G, D in ranks:
         assert rel(tr.losses, lf) < 2e-4
