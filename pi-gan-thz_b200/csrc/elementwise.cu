@@ -269,34 +269,78 @@ __global__ void copy_pad_f32_kernel(const float* __restrict__ src, int n, float*
   if (idx < n_pad) dst[idx] = idx < n ? src[idx] : 0.f;
 }
 
+// ---- 4-columns-per-thread layout of the batch-coupled streaming kernels --------------------------------------
+// A thread owns 4 consecutive columns (8-byte fp16 loads) of every row it visits and keeps kU rows in flight;
+// per-column constants are folded algebraically so a kernel needs <= 64 registers and 4+ blocks fit per SM —
+// these kernels are latency-bound, measured 12-24 % active warps and 5-38 % DRAM throughput at 124-187 registers.
+constexpr int kU = 4;
+struct ColMap4 {
+  int cpr, rpb, ch, rg;
+  __device__ ColMap4(int C) {
+    cpr = C >> 2;
+    rpb = kThreads / cpr;
+    ch = threadIdx.x % cpr;
+    rg = threadIdx.x / cpr;
+  }
+};
+__device__ __forceinline__ void ld_h4(const __half* p, float* v) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st_h4(__half* p, const float* v) {
+  uint2 u;
+  __half2 h;
+  h = __floats2half2_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2half2_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void ld_f4(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+// block partial of 4 column sums -> this block's scratch row (see block_colsum_partial)
+__device__ __forceinline__ void block_colsum_partial4(const float* acc4, float* part, const ColMap4& m, float* sm) {
+  *reinterpret_cast<float4*>(sm + (m.rg * m.cpr + m.ch) * 4) = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
+  __syncthreads();
+  if (m.rg == 0) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int gq = 0; gq < m.rpb; ++gq) {
+      const float4 x = *reinterpret_cast<const float4*>(sm + (gq * m.cpr + m.ch) * 4);
+      t.x += x.x; t.y += x.y; t.z += x.z; t.w += x.w;
+    }
+    *reinterpret_cast<float4*>(part + m.ch * 4) = t;
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------ BatchNorm
-__global__ void __launch_bounds__(kThreads) colstats_kernel(const __half* __restrict__ h, long long rows, int C,
-                                                            float* __restrict__ part) {
-  __shared__ float sm[kThreads * 8];
-  const ColMap m(C);
-  float s[8], q[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+__global__ void __launch_bounds__(kThreads, 4) colstats_kernel(const __half* __restrict__ h, long long rows, int C,
+                                                               float* __restrict__ part) {
+  __shared__ float sm[kThreads * 4];
+  const ColMap4 m(C);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   const long long stride = (long long)gridDim.x * m.rpb;
-  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
-    float v[kUnroll][8];
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kU * stride) {
+    float v[kU][4];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {  // independent loads in flight before any use
+    for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
-      if (r < rows) ld_h8(h + r * C + m.ch * 8, v[u]);
-      else zero8(v[u]);
+      if (r < rows) ld_h4(h + r * C + m.ch * 4, v[u]);
+      else v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < kU; ++u)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         s[i] += v[u][i];
         q[i] = fmaf(v[u][i], v[u][i], q[i]);
       }
   }
   part += (size_t)blockIdx.x * 2 * C;
-  block_colsum_partial(s, part, m, sm);
-  block_colsum_partial(q, part + C, m, sm);
+  block_colsum_partial4(s, part, m, sm);
+  block_colsum_partial4(q, part + C, m, sm);
 }
 
 __global__ void bn_finalize_kernel(BnFinalizeArgs a) {
@@ -354,193 +398,108 @@ __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(const __half* _
   }
 }
 
-// warp per row
-__global__ void __launch_bounds__(kThreads) g_head_fwd_kernel(
+// ------------------------------------------------------------------------------------------ generator head
+// p = tanh(relu(bn2(h2)) W3^T + b3) (generator.py:22-25): warp per row pair, lane owns 8 columns of each 256-column
+// slab, W3 staged in shared memory; also denormalises (data_loader.py:238-252) and builds the fake-row tail of the
+// spectrum operand.
+__global__ void __launch_bounds__(kThreads, 3) g_head_fwd_kernel(
     const __half* __restrict__ h2, const float* __restrict__ scale, const float* __restrict__ bias,
     const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ p_out,
     float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
     int C, int Kp, int S) {
+  extern __shared__ float w3s[];  // [4][C]
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) w3s[i] = w3[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  // per-lane constants of the first 256-column slab stay in registers across rows
-  float sc0[8], bi0[8], wa0[8], wb0[8], wc0[8], wd0[8];
-  {
-    const int c = lane * 8;
-    ld_f8(scale + c, sc0);
-    ld_f8(bias + c, bi0);
-    ld_f8(w3 + c, wa0);
-    ld_f8(w3 + C + c, wb0);
-    ld_f8(w3 + 2 * C + c, wc0);
-    ld_f8(w3 + 3 * C + c, wd0);
-  }
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    {
-      float v[8];
-      ld_h8(h2 + row * C + lane * 8, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = fmaxf(fmaf(sc0[i], v[i], bi0[i]), 0.f);
-        d0 = fmaf(a, wa0[i], d0);
-        d1 = fmaf(a, wb0[i], d1);
-        d2 = fmaf(a, wc0[i], d2);
-        d3 = fmaf(a, wd0[i], d3);
-      }
-    }
-    for (int c = 256 + lane * 8; c < C; c += 256) {
-      float v[8], sc[8], bi[8], wa[8], wb[8], wc[8], wd[8];
-      ld_h8(h2 + row * C + c, v);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float b30 = __ldg(b3 + 0), b31 = __ldg(b3 + 1), b32 = __ldg(b3 + 2), b33 = __ldg(b3 + 3);
+  for (long long rp = w0; rp * 2 < rows; rp += nwarps) {
+    const long long ra = rp * 2, rb = rp * 2 + 1;
+    const bool hasb = rb < rows;
+    float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int c = lane * 8; c < C; c += 256) {
+      float va[8], vb[8], sc[8], bi[8];
+      ld_h8(h2 + ra * C + c, va);
+      if (hasb) ld_h8(h2 + rb * C + c, vb);
+      else zero8(vb);
       ld_f8(scale + c, sc);
       ld_f8(bias + c, bi);
-      ld_f8(w3 + c, wa);
-      ld_f8(w3 + C + c, wb);
-      ld_f8(w3 + 2 * C + c, wc);
-      ld_f8(w3 + 3 * C + c, wd);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float a = fmaxf(fmaf(sc[i], v[i], bi[i]), 0.f);
-        d0 = fmaf(a, wa[i], d0);
-        d1 = fmaf(a, wb[i], d1);
-        d2 = fmaf(a, wc[i], d2);
-        d3 = fmaf(a, wd[i], d3);
+        const float aa = fmaxf(fmaf(sc[i], va[i], bi[i]), 0.f);
+        const float ab = fmaxf(fmaf(sc[i], vb[i], bi[i]), 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float w = w3s[j * C + c + i];
+          d[0][j] = fmaf(aa, w, d[0][j]);
+          d[1][j] = fmaf(ab, w, d[1][j]);
+        }
       }
     }
-    d0 = warp_sum_f(d0); d1 = warp_sum_f(d1); d2 = warp_sum_f(d2); d3 = warp_sum_f(d3);
-    float p[4] = {tanhf(d0 + __ldg(b3 + 0)), tanhf(d1 + __ldg(b3 + 1)), tanhf(d2 + __ldg(b3 + 2)),
-                  tanhf(d3 + __ldg(b3 + 3))};
-    float pd[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pd[e] = (p[e] + 1.0f) / 2.0f * 0.6f + 2.2f;  // data_loader.py:238-252
-    if (lane == 0) {
-      *reinterpret_cast<float4*>(p_out + row * 4) = make_float4(p[0], p[1], p[2], p[3]);
-      if (pden_out) *reinterpret_cast<float4*>(pden_out + row * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
-    }
-    if (tail_fake != nullptr && lane < 8) {
-      const int t0 = Kp - 64;  // first spectrum-operand column held by the tail
-      float v[8];
-      ld_h8(xc + row * Kp + t0 + lane * 8, v);
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = t0 + lane * 8 + i - S;
-        if (e >= 0 && e < 4) v[i] = pd[e] - kParamCenter;
+      for (int j = 0; j < 4; ++j) d[t][j] = warp_sum_f(d[t][j]);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const long long row = t == 0 ? ra : rb;
+      if (t == 1 && !hasb) break;
+      float p[4] = {tanhf(d[t][0] + b30), tanhf(d[t][1] + b31), tanhf(d[t][2] + b32), tanhf(d[t][3] + b33)};
+      float pd[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pd[e] = (p[e] + 1.0f) / 2.0f * 0.6f + 2.2f;  // data_loader.py:238-252
+      if (lane == 0) {
+        *reinterpret_cast<float4*>(p_out + row * 4) = make_float4(p[0], p[1], p[2], p[3]);
+        if (pden_out) *reinterpret_cast<float4*>(pden_out + row * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
       }
-      st_h8(tail_fake + row * 64 + lane * 8, v);
+      if (tail_fake != nullptr && lane < 8) {
+        const int t0 = Kp - 64;  // first spectrum-operand column held by the tail
+        float v[8];
+        ld_h8(xc + row * Kp + t0 + lane * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = t0 + lane * 8 + i - S;
+          if (e >= 0 && e < 4) v[i] = pd[e] - kParamCenter;
+        }
+        st_h8(tail_fake + row * 64 + lane * 8, v);
+      }
     }
   }
 }
 
-// Generator head backward (tanh, Linear(256,4), ReLU) fused with the BatchNorm-2 backward.  Two passes over h2
-// instead of storing the pre-projection gradient dy in fp16: BatchNorm's backward removes the batch-mean and
-// x-hat components of dy, which here carry most of its norm (the adversarial gradient pushes every sample the
-// same way), so rounding dy before the projection would be amplified in what survives it.
-//   APPLY = false: column sums of dy and dy*xhat, dW3, db3, range-loss sum
-//   APPLY = true : dh = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) -> fp16, db2, dgamma, dbeta
-template <bool APPLY>
-__global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
-  __shared__ float sm[kThreads * 8];
-  const ColMap m(a.C);
-  float sc[8], bi[8], mu[8], rs[8], w[4][8];
-  ld_f8(a.scale + m.ch * 8, sc);
-  ld_f8(a.bias + m.ch * 8, bi);
-  ld_f8(a.mean + m.ch * 8, mu);
-  ld_f8(a.rstd + m.ch * 8, rs);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) ld_f8(a.w3 + j * a.C + m.ch * 8, w[j]);
-  float dw[4][8], sdy[8], sdyx[8];  // APPLY: sdy accumulates dh (-> db2), sdyx/dw unused
-  float gr[8], m1[8], m2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sdy[i] = sdyx[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) dw[j][i] = 0.f;
-  }
-  if (APPLY) {
-    ld_f8(a.gamma + m.ch * 8, gr);
-    ld_f8(a.sum_dy + m.ch * 8, m1);
-    ld_f8(a.sum_dyx + m.ch * 8, m2);
-    if (blockIdx.x == 0 && m.rg == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (a.dgamma) a.dgamma[m.ch * 8 + i] += m2[i] * a.inv_gs;
-        if (a.dbeta) a.dbeta[m.ch * 8 + i] += m1[i] * a.inv_gs;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      gr[i] *= rs[i];
-      m1[i] = (float)((double)m1[i] * a.inv_n);
-      m2[i] = (float)((double)m2[i] * a.inv_n);
-    }
-  }
+// Generator head backward, fused with the BatchNorm-2 backward, in three kernels that never store the
+// pre-projection gradient dy = relu'(.) * (dpre W3):
+//   g_head_dpre   dpre[r, 0:4] = dL/d(pre-tanh) from the adversarial, LC and range terms; db3, range-loss sum
+//   g_head_bwd<0> batch moments S0[j,c] = sum_r m dpre_j, S1[j,c] = sum_r m h dpre_j (m = ReLU mask, h = stored
+//                 pre-BN value); g_head_moments_reduce turns them into sum dy, sum dy*xhat and dW3
+//   g_head_bwd<1> dh = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) as A*dy - B*h + C0 -> fp16, db2
+// Recomputing dy costs 4 FMAs per element; storing it in fp16 before BatchNorm's projection would amplify its
+// rounding (the adversarial gradient pushes every sample the same way, so most of dy is projected out).
+__global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
+  __shared__ float sm[32];
   float db[4] = {0.f, 0.f, 0.f, 0.f};
   float range_acc = 0.f;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long stride = (long long)gridDim.x * m.rpb;
-  constexpr int U = 2;
-  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += U * stride) {
-    float h[U][8];
-    float4 p4[U], d4[U], l4[U];
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.rows;
+       r += (long long)gridDim.x * blockDim.x) {
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.p) + r);
+    const float4 d4 = a.dpden ? __ldg(reinterpret_cast<const float4*>(a.dpden) + r) : z4;
+    const float4 l4 = a.dp_lc ? __ldg(reinterpret_cast<const float4*>(a.dp_lc) + r) : z4;
+    const float p[4] = {p4.x, p4.y, p4.z, p4.w};
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+    float dpre[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * stride;
-      if (r < a.rows) {
-        ld_h8(a.h2 + r * a.C + m.ch * 8, h[u]);
-        p4[u] = __ldg(reinterpret_cast<const float4*>(a.p) + r);
-        d4[u] = a.dpden ? __ldg(reinterpret_cast<const float4*>(a.dpden) + r) : z4;
-        l4[u] = a.dp_lc ? __ldg(reinterpret_cast<const float4*>(a.dp_lc) + r) : z4;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float lo = fmaxf(-p[j], 0.f), hi = fmaxf(p[j] - 1.f, 0.f);        // loss.py:121-123
+      const float dp = (0.5f * 0.6f) * dd[j] + ll[j] + (2.f * hi - 2.f * lo) * a.range_mult;
+      dpre[j] = dp * (1.f - p[j] * p[j]);                                      // tanh backward
+      db[j] += dpre[j];
+      range_acc += lo * lo + hi * hi;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long r = r0 + u * stride;
-      if (r >= a.rows) break;
-      const float p[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w};
-      const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
-      const float ll[4] = {l4[u].x, l4[u].y, l4[u].z, l4[u].w};
-      float dpre[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float lo = fmaxf(-p[j], 0.f), hi = fmaxf(p[j] - 1.f, 0.f);        // loss.py:121-123
-        const float dp = (0.5f * 0.6f) * dd[j] + ll[j] + (2.f * hi - 2.f * lo) * a.range_mult;
-        dpre[j] = dp * (1.f - p[j] * p[j]);                                      // tanh backward
-        if (!APPLY && m.ch == 0) {
-          db[j] += dpre[j];
-          range_acc += lo * lo + hi * hi;
-        }
-      }
-      float out[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float act = fmaxf(fmaf(sc[i], h[u][i], bi[i]), 0.f);
-        float da = dpre[0] * w[0][i];
-        da = fmaf(dpre[1], w[1][i], da);
-        da = fmaf(dpre[2], w[2][i], da);
-        da = fmaf(dpre[3], w[3][i], da);
-        const float g = act > 0.f ? da : 0.f;
-        const float xh = (h[u][i] - mu[i]) * rs[i];
-        if (APPLY) {
-          const float dh = gr[i] * (g - m1[i] - xh * m2[i]);
-          out[i] = dh;
-          sdy[i] += dh;
-        } else {
-          sdy[i] += g;
-          sdyx[i] = fmaf(g, xh, sdyx[i]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dw[j][i] = fmaf(dpre[j], act, dw[j][i]);
-        }
-      }
-      if (APPLY) st_h8(a.dy2 + r * a.C + m.ch * 8, out);
-    }
+    *reinterpret_cast<float4*>(a.dpre + r * 4) = make_float4(dpre[0], dpre[1], dpre[2], dpre[3]);
   }
-  if (APPLY) {
-    block_colsum_partial(sdy, a.part + (size_t)blockIdx.x * a.C, m, sm);
-    return;
-  }
-  float* part = a.part + (size_t)blockIdx.x * 6 * a.C;
-  block_colsum_partial(sdy, part, m, sm);
-  block_colsum_partial(sdyx, part + a.C, m, sm);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) block_colsum_partial(dw[j], part + (2 + j) * a.C, m, sm);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float t = block_sum(db[j], sm);
@@ -550,147 +509,303 @@ __global__ void __launch_bounds__(kThreads) g_head_bwd_kernel(GHeadBwdArgs a) {
   if (threadIdx.x == 0 && a.range_sum) atomicAdd(a.range_sum, (double)t);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_bwd_stats_kernel(
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHeadBwdArgs a) {
+  __shared__ float sm[kThreads * 4];
+  const ColMap4 m(a.C);
+  const int c0 = m.ch * 4;
+  float sc[4], bi[4];
+  ld_f4(a.scale + c0, sc);
+  ld_f4(a.bias + c0, bi);
+  const long long stride = (long long)gridDim.x * m.rpb;
+  constexpr int U = 2;
+  if (!APPLY) {
+    float s0[4][4], s1[4][4];  // [j][column]
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s0[j][i] = s1[j][i] = 0.f;
+    for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += U * stride) {
+      float h[U][4];
+      float4 dq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < a.rows) {
+          ld_h4(a.h2 + r * a.C + c0, h[u]);
+          dq[u] = __ldg(reinterpret_cast<const float4*>(a.dpre) + r);
+        } else {
+          h[u][0] = h[u][1] = h[u][2] = h[u][3] = 0.f;
+          dq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float dp[4] = {dq[u].x, dq[u].y, dq[u].z, dq[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float mf = fmaf(sc[i], h[u][i], bi[i]) > 0.f ? 1.f : 0.f;
+          const float mh = mf * h[u][i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s0[j][i] = fmaf(mf, dp[j], s0[j][i]);
+            s1[j][i] = fmaf(mh, dp[j], s1[j][i]);
+          }
+        }
+      }
+    }
+    float* part = a.part + (size_t)blockIdx.x * 8 * a.C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      block_colsum_partial4(s0[j], part + j * a.C, m, sm);
+      block_colsum_partial4(s1[j], part + (4 + j) * a.C, m, sm);
+    }
+  } else {
+    float w[4][4], A[4], Bc[4], C0[4], sdh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ld_f4(a.w3 + j * a.C + c0, w[j]);
+    {
+      float gm[4], rs[4], mu[4], m1[4], m2[4];
+      ld_f4(a.gamma + c0, gm);
+      ld_f4(a.rstd + c0, rs);
+      ld_f4(a.mean + c0, mu);
+      ld_f4(a.sum_dy + c0, m1);
+      ld_f4(a.sum_dyx + c0, m2);
+      if (blockIdx.x == 0 && m.rg == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (a.dgamma) a.dgamma[c0 + i] += m2[i] * a.inv_gs;
+          if (a.dbeta) a.dbeta[c0 + i] += m1[i] * a.inv_gs;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mean_dy = (float)((double)m1[i] * a.inv_n);
+        const float mean_dyx = (float)((double)m2[i] * a.inv_n);
+        A[i] = gm[i] * rs[i];
+        Bc[i] = A[i] * mean_dyx * rs[i];
+        C0[i] = A[i] * (mean_dyx * rs[i] * mu[i] - mean_dy);
+        sdh[i] = 0.f;
+      }
+    }
+    for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += U * stride) {
+      float h[U][4];
+      float4 dq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < a.rows) {
+          ld_h4(a.h2 + r * a.C + c0, h[u]);
+          dq[u] = __ldg(reinterpret_cast<const float4*>(a.dpre) + r);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        if (r >= a.rows) break;
+        float out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float dy = dq[u].x * w[0][i];
+          dy = fmaf(dq[u].y, w[1][i], dy);
+          dy = fmaf(dq[u].z, w[2][i], dy);
+          dy = fmaf(dq[u].w, w[3][i], dy);
+          dy = fmaf(sc[i], h[u][i], bi[i]) > 0.f ? dy : 0.f;
+          const float dh = fmaf(A[i], dy, fmaf(-Bc[i], h[u][i], C0[i]));
+          out[i] = dh;
+          sdh[i] += dh;
+        }
+        st_h4(a.dy2 + r * a.C + c0, out);
+      }
+    }
+    block_colsum_partial4(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
+  }
+}
+
+// sums the moment partials over blocks and finishes sum dy, sum dy*xhat and dW3 (one block per 32 columns)
+__global__ void __launch_bounds__(1024) g_head_moments_reduce_kernel(GHeadBwdArgs a, int nblocks) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float tot[8];
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    float s = 0.f;
+    if (c < a.C)
+      for (int b = ty; b < nblocks; b += 32) s += a.part[(size_t)b * 8 * a.C + k * a.C + c];
+    sm[ty][tx] = s;
+    __syncthreads();
+    float t = 0.f;
+    if (ty == 0) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) t += sm[q][tx];
+    }
+    tot[k] = t;
+    __syncthreads();
+  }
+  if (ty == 0 && c < a.C) {
+    const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
+    float sdy = 0.f, sdyh = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float w = a.w3[j * a.C + c];
+      sdy = fmaf(w, tot[j], sdy);
+      sdyh = fmaf(w, tot[4 + j], sdyh);
+      a.dw3[j * a.C + c] += a.inv_gs * (sc * tot[4 + j] + bi * tot[j]);   // sum dpre_j * relu(sc*h+bi)
+    }
+    a.sum_dy[c] += sdy;
+    a.sum_dyx[c] += rs * (sdyh - mu * sdy);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
     const __half* __restrict__ da, const __half* __restrict__ h, const float* __restrict__ scale,
     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ part, long long rows, int C) {
-  __shared__ float sm[kThreads * 8];
-  const ColMap m(C);
-  float sc[8], bi[8], mu[8], rs[8], s1[8], s2[8];
-  ld_f8(scale + m.ch * 8, sc);
-  ld_f8(bias + m.ch * 8, bi);
-  ld_f8(mean + m.ch * 8, mu);
-  ld_f8(rstd + m.ch * 8, rs);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  __shared__ float sm[kThreads * 4];
+  const ColMap4 m(C);
+  const int c0 = m.ch * 4;
+  float sc[4], bi[4], mu[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  ld_f4(scale + c0, sc);
+  ld_f4(bias + c0, bi);
+  ld_f4(mean + c0, mu);
   const long long stride = (long long)gridDim.x * m.rpb;
-  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
-    float g[kUnroll][8], x[kUnroll][8];
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kU * stride) {
+    float g[kU][4], x[kU][4];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r < rows) {
-        ld_h8(da + r * C + m.ch * 8, g[u]);
-        ld_h8(h + r * C + m.ch * 8, x[u]);
+        ld_h4(da + r * C + c0, g[u]);
+        ld_h4(h + r * C + c0, x[u]);
       } else {
-        zero8(g[u]);
-        zero8(x[u]);
+        g[u][0] = g[u][1] = g[u][2] = g[u][3] = 0.f;
+        x[u][0] = x[u][1] = x[u][2] = x[u][3] = 0.f;
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    for (int u = 0; u < kU; ++u)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float dy = fmaf(sc[i], x[u][i], bi[i]) > 0.f ? g[u][i] : 0.f;
         s1[i] += dy;
-        s2[i] = fmaf(dy, (x[u][i] - mu[i]) * rs[i], s2[i]);
+        s2[i] = fmaf(dy, x[u][i] - mu[i], s2[i]);   // rstd applied once at the end
       }
   }
+  float rs[4];
+  ld_f4(rstd + c0, rs);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s2[i] *= rs[i];
   part += (size_t)blockIdx.x * 2 * C;
-  block_colsum_partial(s1, part, m, sm);
-  block_colsum_partial(s2, part + C, m, sm);
+  block_colsum_partial4(s1, part, m, sm);
+  block_colsum_partial4(s2, part + C, m, sm);
 }
 
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(BnBwdArgs a) {
-  __shared__ float sm[kThreads * 8];
-  const ColMap m(a.C);
-  float sc[8], bi[8], mu[8], rs[8], gr[8], m1[8], m2[8], sdh[8];
-  ld_f8(a.scale + m.ch * 8, sc);
-  ld_f8(a.bias + m.ch * 8, bi);
-  ld_f8(a.mean + m.ch * 8, mu);
-  ld_f8(a.rstd + m.ch * 8, rs);
-  ld_f8(a.gamma + m.ch * 8, gr);
-  ld_f8(a.sum_dy + m.ch * 8, m1);
-  ld_f8(a.sum_dyx + m.ch * 8, m2);
-  if (blockIdx.x == 0 && m.rg == 0) {
+// dh = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)), dy = da * ReLU mask, written as A*dy - B*h + C0
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) {
+  __shared__ float sm[kThreads * 4];
+  const ColMap4 m(a.C);
+  const int c0 = m.ch * 4;
+  float sc[4], bi[4], A[4], Bc[4], C0[4], sdh[4];
+  ld_f4(a.scale + c0, sc);
+  ld_f4(a.bias + c0, bi);
+  {
+    float gm[4], rs[4], mu[4], m1[4], m2[4];
+    ld_f4(a.gamma + c0, gm);
+    ld_f4(a.rstd + c0, rs);
+    ld_f4(a.mean + c0, mu);
+    ld_f4(a.sum_dy + c0, m1);
+    ld_f4(a.sum_dyx + c0, m2);
+    if (blockIdx.x == 0 && m.rg == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (a.dgamma) a.dgamma[m.ch * 8 + i] += m2[i] * a.inv_gs;
-      if (a.dbeta) a.dbeta[m.ch * 8 + i] += m1[i] * a.inv_gs;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    gr[i] *= rs[i];
-    m1[i] = (float)((double)m1[i] * a.inv_n);
-    m2[i] = (float)((double)m2[i] * a.inv_n);
-    sdh[i] = 0.f;
-  }
-  const long long stride = (long long)gridDim.x * m.rpb;
-  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += kUnroll * stride) {
-    float g[kUnroll][8], x[kUnroll][8];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const long long r = r0 + u * stride;
-      if (r < a.rows) {
-        ld_h8(a.dy + r * a.C + m.ch * 8, g[u]);
-        ld_h8(a.h + r * a.C + m.ch * 8, x[u]);
+      for (int i = 0; i < 4; ++i) {
+        if (a.dgamma) a.dgamma[c0 + i] += m2[i] * a.inv_gs;
+        if (a.dbeta) a.dbeta[c0 + i] += m1[i] * a.inv_gs;
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int i = 0; i < 4; ++i) {
+      const float mean_dy = (float)((double)m1[i] * a.inv_n);
+      const float mean_dyx = (float)((double)m2[i] * a.inv_n);
+      A[i] = gm[i] * rs[i];
+      Bc[i] = A[i] * mean_dyx * rs[i];
+      C0[i] = A[i] * (mean_dyx * rs[i] * mu[i] - mean_dy);
+      sdh[i] = 0.f;
+    }
+  }
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += kU * stride) {
+    float g[kU][4], x[kU][4];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < a.rows) {
+        ld_h4(a.dy + r * a.C + c0, g[u]);
+        ld_h4(a.h + r * a.C + c0, x[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r >= a.rows) break;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         float dy = g[u][i];
         if (a.relu_mask) dy = fmaf(sc[i], x[u][i], bi[i]) > 0.f ? dy : 0.f;
-        const float xh = (x[u][i] - mu[i]) * rs[i];
-        const float dh = gr[i] * (dy - m1[i] - xh * m2[i]);
+        const float dh = fmaf(A[i], dy, fmaf(-Bc[i], x[u][i], C0[i]));
         g[u][i] = dh;
         sdh[i] += dh;
       }
-      st_h8(a.dh + r * a.C + m.ch * 8, g[u]);
+      st_h4(a.dh + r * a.C + c0, g[u]);
     }
   }
-  if (a.dbias) block_colsum_partial(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
+  if (a.dbias) block_colsum_partial4(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
 }
 
 // ------------------------------------------------------------------------------------------ discriminator
-__global__ void __launch_bounds__(kThreads) d_l2_bwd_kernel(const __half* __restrict__ z2,
-                                                            const float* __restrict__ dlogit,
-                                                            const float* __restrict__ w3, __half* __restrict__ dh2,
-                                                            float* __restrict__ dw3, float* __restrict__ db2,
-                                                            float* __restrict__ db3, long long rows, int C,
-                                                            float inv_gs, float* __restrict__ part) {
-  __shared__ float sm[kThreads * 8];
-  const ColMap m(C);
-  float w[8], sw[8], sb[8];
-  ld_f8(w3 + m.ch * 8, w);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sw[i] = sb[i] = 0.f;
+__global__ void __launch_bounds__(kThreads, 4) d_l2_bwd_kernel(const __half* __restrict__ z2,
+                                                               const float* __restrict__ dlogit,
+                                                               const float* __restrict__ w3, __half* __restrict__ dh2,
+                                                               float* __restrict__ dw3, float* __restrict__ db2,
+                                                               float* __restrict__ db3, long long rows, int C,
+                                                               float inv_gs, float* __restrict__ part) {
+  __shared__ float sm[kThreads * 4];
+  const ColMap4 m(C);
+  const int c0 = m.ch * 4;
+  float w[4], sw[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+  ld_f4(w3 + c0, w);
   float s3 = 0.f;
   const long long stride = (long long)gridDim.x * m.rpb;
-  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kUnroll * stride) {
-    float z[kUnroll][8], dl[kUnroll];
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kU * stride) {
+    float z[kU][4], dl[kU];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r < rows) {
         dl[u] = __ldg(dlogit + r);
-        ld_h8(z2 + r * C + m.ch * 8, z[u]);
+        ld_h4(z2 + r * C + c0, z[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r >= rows) break;
-      float o[8];
+      float o[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float dh = dl[u] * w[i] * (z[u][i] > 0.f ? 1.f : kSlope);
         o[i] = dh;
         sw[i] = fmaf(dl[u], z[u][i], sw[i]);
         sb[i] += dh;
       }
-      st_h8(dh2 + r * C + m.ch * 8, o);
+      st_h4(dh2 + r * C + c0, o);
       if (m.ch == 0) s3 += dl[u];
     }
   }
   if (dw3 != nullptr) {
     part += (size_t)blockIdx.x * 2 * C;
-    block_colsum_partial(sw, part, m, sm);
-    block_colsum_partial(sb, part + C, m, sm);
+    block_colsum_partial4(sw, part, m, sm);
+    block_colsum_partial4(sb, part + C, m, sm);
     const float t = block_sum(s3, sm);
     if (threadIdx.x == 0) atomicAdd(db3, t * inv_gs);
   }
@@ -887,8 +1002,8 @@ void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStr
   note_launch(), copy_pad_f32_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
 }
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st) {
-  const int rpb = kThreads / (C / 8);
-  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  const int rpb = kThreads / (C / 4);
+  const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
   note_launch(), colstats_kernel<<<grid, kThreads, 0, st>>>(h, rows, C, part);
   ReduceArgs r{part, grid, 2 * C, 2, {{sum, C, 1.f}, {sumsq, C, 1.f}}};
   launch_reduce_partials(r, st);
@@ -908,36 +1023,35 @@ void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
-  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(h2, scale, bias, w3, b3, p_out, pden_out, xc,
-                                                                     tail_fake, rows, C, Kp, S);
+  // a warp handles two rows per trip
+  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, 8 * 2 * 2), kThreads, 4 * C * sizeof(float), st>>>(
+      h2, scale, bias, w3, b3, p_out, pden_out, xc, tail_fake, rows, C, Kp, S);
 }
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
-  const int rpb = kThreads / (a.C / 8);
-  const int grid = grid_for_rows(a.rows, rpb * 8, kPartBlocks);
+  const int rpb = kThreads / (a.C / 4);
+  const int grid = grid_for_rows(a.rows, rpb * 2 * 4, kPartBlocks);
   if (apply) {
     note_launch(), g_head_bwd_kernel<true><<<grid, kThreads, 0, st>>>(a);
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
     launch_reduce_partials(r, st);
   } else {
+    note_launch(), g_head_dpre_kernel<<<grid_for_rows(a.rows, kThreads, 148 * 2), kThreads, 0, st>>>(a);
     note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
-    ReduceArgs r{a.part, grid, 6 * a.C, 6,
-                 {{a.sum_dy, a.C, 1.f}, {a.sum_dyx, a.C, 1.f}, {a.dw3, a.C, a.inv_gs}, {a.dw3 + a.C, a.C, a.inv_gs},
-                  {a.dw3 + 2 * a.C, a.C, a.inv_gs}, {a.dw3 + 3 * a.C, a.C, a.inv_gs}}};
-    launch_reduce_partials(r, st);
+    note_launch(), g_head_moments_reduce_kernel<<<(a.C + 31) / 32, 1024, 0, st>>>(a, grid);
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
                          float* part, cudaStream_t st) {
-  const int rpb = kThreads / (C / 8);
-  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  const int rpb = kThreads / (C / 4);
+  const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
   note_launch(), bn_bwd_stats_kernel<<<grid, kThreads, 0, st>>>(da, h, scale, bias, mean, rstd, part, rows, C);
   ReduceArgs r{part, grid, 2 * C, 2, {{sum_dy, C, 1.f}, {sum_dyx, C, 1.f}}};
   launch_reduce_partials(r, st);
 }
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
-  const int rpb = kThreads / (a.C / 8);
-  const int grid = grid_for_rows(a.rows, rpb * 8, kPartBlocks);
+  const int rpb = kThreads / (a.C / 4);
+  const int grid = grid_for_rows(a.rows, rpb * kU * 2, kPartBlocks);
   note_launch(), bn_bwd_apply_kernel<<<grid, kThreads, 0, st>>>(a);
   if (a.dbias) {
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
@@ -946,8 +1060,8 @@ void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
 }
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
                      float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st) {
-  const int rpb = kThreads / (C / 8);
-  const int grid = grid_for_rows(rows, rpb * 8, kPartBlocks);
+  const int rpb = kThreads / (C / 4);
+  const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
   note_launch(), d_l2_bwd_kernel<<<grid, kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
   if (dw3 != nullptr) {
     ReduceArgs r{part, grid, 2 * C, 2, {{dw3, C, inv_gs}, {db2, C, inv_gs}}};

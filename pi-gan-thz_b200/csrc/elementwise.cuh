@@ -15,7 +15,7 @@ constexpr float kParamCenter = 2.5f;
 // stores its partial column sums to one row of a scratch matrix, reduce_partials_kernel adds the rows in a fixed
 // order.  The engine provides kPartBlocks * kPartCols floats of scratch.
 constexpr int kPartBlocks = 148 * 4;
-constexpr int kPartCols = 6 * 512;
+constexpr int kPartCols = 8 * 512;
 struct ReduceSeg {
   float* dst;   // dst[c] += mult * column sum (nullptr: skip)
   int ncols;
@@ -112,7 +112,8 @@ struct GHeadBwdArgs {
   float* dgamma;          // [C] += sum_dyx / GS
   float* dbeta;           // [C] += sum_dy / GS
   double inv_n;           // 1 / global batch
-  float* part;            // partial-sum scratch (kPartBlocks x 6C floats)
+  float* part;            // partial-sum scratch (kPartBlocks x 8C floats)
+  float* dpre;            // [B,4] scratch: dL/d(pre-tanh), written by the statistics pass
 };
 // apply = false: statistics pass (sum_dy, sum_dyx, dw3, db3, range_sum); apply = true: writes dy2 (see kernel)
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st);

@@ -102,6 +102,7 @@ struct PiganEngine {
   __half *g_w1h, *g_w2h, *g_w2th, *d_w1h, *d_w2h, *d_w2th, *f_wh[6];
   // fp32 scratch
   float *partials;                     // [kPartBlocks x kPartCols] two-stage batch reductions
+  float *dpre;                         // [B,4] generator head backward
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
   float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
   float *mean1, *rstd1, *scale1, *bias1, *mean2, *rstd2, *scale2, *bias2;
@@ -144,6 +145,7 @@ struct PiganEngine {
       in = out;
     }
     partials = c.take<float>((size_t)kPartBlocks * kPartCols);
+    dpre = c.take<float>(B * 4);
     p = c.take<float>(B * 4);
     pden = c.take<float>(B * 4);
     dpden = c.take<float>(B * 4);
@@ -424,7 +426,7 @@ GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
   hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = e->sums + kSumRange;
   hb.inv_gs = inv_gs; hb.rows = a.batch; hb.C = G.H2;
   hb.gamma = gp + G.bn2_w; hb.dbias = a.g_grads + G.b2; hb.dgamma = a.g_grads + G.bn2_w;
-  hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch; hb.part = e->partials;
+  hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch; hb.part = e->partials; hb.dpre = e->dpre;
   return hb;
 }
 
