@@ -13,6 +13,8 @@ struct EpiDebug {
     int ldc;
   };
   static constexpr int SMEM_BYTES = 0;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {
     float acc;
   };

@@ -22,6 +22,8 @@ using CfgS = GemmCfg<256, 1, 3, false>;   // store epilogues (2 x 32 KB staging)
 using CfgP = GemmCfg<256, 1, 4, false>;   // no staging
 using CfgO = GemmCfg<144, 2, 2, false>;   // forward-model output layer (64 KB target tile in the epilogue)
 using CfgW = GemmCfg<256, 1, 4, true>;    // weight gradients
+using CfgL1 = GemmCfg<256, 1, 3, false>;  // Linear+LayerNorm, 256 columns per CTA
+using CfgL2 = GemmCfg<256, 2, 3, false>;  // Linear+LayerNorm, 512 columns per CTA (all of TMEM)
 
 // loss_sums indices (fp64)
 enum { kSumD = 0, kSumAdv = 1, kSumRec = 2, kSumMet = 3, kSumMaxwell = 4, kSumLc1 = 5, kSumLc2 = 6, kSumRange = 7,
@@ -224,6 +226,33 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
   return run_tn<CfgS, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
 }
 
+// out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
+int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, const float* gamma,
+              const float* beta, __half* out, cudaStream_t st) {
+  if (n == 256) {
+    using Epi = EpiLnStore<CfgL1, 1>;
+    typename Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
+    return run_tn<CfgL1, Epi>(ep, a, rows, k, k, w, n, k, st);
+  }
+  if (n == 512) {
+    using Epi = EpiLnStore<CfgL2, 1>;
+    typename Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
+    return run_tn<CfgL2, Epi>(ep, a, rows, k, k, w, n, k, st);
+  }
+  if (n == 1024) {
+    using Epi = EpiLnStore<CfgL2, 2>;
+    typename Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
+    return run_tn<CfgL2, Epi>(ep, a, rows, k, k, w, n, k, st);
+  }
+  return fail(PIGAN_ERR_UNSUPPORTED, "LayerNorm width %d", n);
+}
+
 // dw[m_out, ld] += (1/gs) * a[kd, m_out]^T b[.., n]
 int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t b_rows, int n, float* dw, int ld,
                 int n_valid, float inv_gs, int bias_col, float* db, int64_t wrap_rows, const __half* b_tail,
@@ -381,11 +410,8 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
-    PIGAN_TRY((linear_store<true, false, true>(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], acts[i],
-                                               e->f_rowstats, st)));
-    PM("f_ln_apply");
-    launch_ln_lrelu_apply(acts[i], e->f_rowstats, ceil_div(L.H[i], 256), fp + L.ln_w[i], fp + L.ln_b[i], n, L.H[i],
-                          st);
+    PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], fp + L.ln_w[i], fp + L.ln_b[i],
+                        acts[i], st));
   }
   using Epi = EpiFwdOut<CfgO>;
   Epi::Params ep;

@@ -102,6 +102,8 @@ struct EpiStore {
     int n_tiles;
   };
   static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {
     Stager stg;
   };
@@ -153,6 +155,138 @@ struct EpiStore {
 };
 
 // =====================================================================================================
+// Linear + LayerNorm + LeakyReLU in one epilogue (forward_model.py:35-53): out = fp16(lrelu(LN(acc + bias))).
+// A thread owns one row (its TMEM lane); the whole row's accumulators stay resident in tensor memory while the
+// epilogue walks them twice — pass 1: sum / sum of squares, pass 2: normalise, activate, store — so the
+// pre-normalisation values never leave the SM.  The two epilogue groups split the CTA's columns; for the
+// 1024-wide layer two CTAs of a cluster split the row (512 accumulator columns = all of TMEM each) and the four
+// row partials meet through distributed shared memory + one cluster-scope mbarrier per unit.
+// =====================================================================================================
+template <class Cfg, int CLUSTER_>
+struct EpiLnStore {
+  static_assert(Cfg::BLOCK_N == 256, "EpiLnStore tile shape");
+  static constexpr bool SPLIT = true;
+  static constexpr int CLUSTER = CLUSTER_;
+  static constexpr int NCTA = Cfg::ACC_COLS;  // accumulator columns of one CTA (256 or 512)
+  static constexpr int NG = NCTA / 2;         // columns one epilogue group handles
+  static_assert(NG % 64 == 0, "group columns must be whole TMA-store sub-tiles");
+  struct Params {
+    CUtensorMap out;
+    const float* bias;   // [N]
+    const float* gamma;  // [N]
+    const float* beta;   // [N]
+    int n_total;         // LayerNorm width N = NCTA * CLUSTER
+  };
+  // per group: [0,32K) store staging | [32K,+3K) bias,gamma,beta of its columns | [35K,+4K) row-partial slots
+  // (buffer = group index: two buffers alternate between units) ; 40 KB in all
+  static constexpr int kConstOff = kEpiStagingBytes;
+  static constexpr int kSlotOff = kConstOff + 3 * 256 * 4;
+  static constexpr int SMEM_BYTES = 40960;
+  struct State {
+    Stager stg;
+    uint32_t xphase;
+    uint32_t it;
+    uint32_t rank;
+  };
+  __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    st.stg.init();
+    st.xphase = 0;
+    st.it = 0;
+    st.rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
+    const int col0 = (int)st.rank * NCTA + cx.group * NG;
+    for (int i = cx.tid; i < NG; i += 128) {
+      const int c = col0 + i;
+      const bool ok = c < p.n_total;
+      sts_f32(cx.smem + kConstOff + (uint32_t)i * 4u, ok ? __ldg(p.bias + c) : 0.f);
+      sts_f32(cx.smem + kConstOff + (uint32_t)(256 + i) * 4u, ok ? __ldg(p.gamma + c) : 0.f);
+      sts_f32(cx.smem + kConstOff + (uint32_t)(512 + i) * 4u, ok ? __ldg(p.beta + c) : 0.f);
+    }
+    epi_bar_sync(cx, 0);
+  }
+  __device__ static void lds32(uint32_t addr, float* out) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float4 t;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr + 16u * k) : "memory");
+      out[4 * k + 0] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
+    }
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const uint32_t tcol0 = tacc + (uint32_t)(cx.group * NG);
+    const uint32_t cb = cx.smem + kConstOff;
+    // ---- pass 1: row partials over this group's columns
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NG; c += 32) {
+      float v[32], b[32];
+      tmem_ld32(tcol0 + c, v);
+      lds32(cb + (uint32_t)c * 4u, b);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = v[i] + b[i];
+        s1 += x;
+        s2 = fmaf(x, x, s2);
+      }
+    }
+    // ---- exchange: 2 * CLUSTER partials per row
+    const uint32_t slots = cx.smem0 + (st.it & 1u) * (uint32_t)SMEM_BYTES + kSlotOff;
+    const uint32_t mine = slots + ((st.rank * 2u + (uint32_t)cx.group) * 128u + (uint32_t)r) * 8u;
+    if constexpr (CLUSTER == 1) {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mine), "f"(s1), "f"(s2) : "memory");
+      mbar_arrive(cx.xbar);
+      mbar_wait(cx.xbar, st.xphase);
+    } else {
+#pragma unroll
+      for (uint32_t c = 0; c < (uint32_t)CLUSTER; ++c) {
+        st_cluster_f32x2(mapa_shared(mine, c), s1, s2);
+        mbar_arrive_cluster(mapa_shared(cx.xbar, c));
+      }
+      mbar_wait_cluster(cx.xbar, st.xphase);
+    }
+    st.xphase ^= 1u;
+    ++st.it;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * CLUSTER; ++k) {
+      float a, b;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                   : "=f"(a), "=f"(b) : "r"(slots + (uint32_t)(k * 128 + r) * 8u) : "memory");
+      t1 += a;
+      t2 += b;
+    }
+    const float inv_n = 1.0f / (float)p.n_total;
+    const float mean = t1 * inv_n;
+    const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    // ---- pass 2: normalise, LeakyReLU, fp16, TMA store
+    const int col0 = (int)st.rank * NCTA + cx.group * NG;
+#pragma unroll 1
+    for (int sub = 0; sub < NG / 64; ++sub) {
+      const uint32_t buf = st.stg.acquire(cx);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = sub * 64 + h * 32;
+        float v[32], b[32], gm[32], bt[32];
+        tmem_ld32(tcol0 + c, v);
+        lds32(cb + (uint32_t)c * 4u, b);
+        lds32(cb + (uint32_t)(256 + c) * 4u, gm);
+        lds32(cb + (uint32_t)(512 + c) * 4u, bt);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lrelu(fmaf((v[i] + b[i] - mean) * rstd, gm[i], bt[i]));
+        Stager::put32(buf, r, h, v);
+      }
+      st.stg.commit(cx, buf, &p.out, col0 + sub * 64, w.m_tile * kBlockM);
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+};
+
+// =====================================================================================================
 // Discriminator layers 2+3 + BCE (discriminator.py:24-27, loss.py:17, train_pigan.py:127-137,152-154):
 // z2 = LeakyReLU(acc + b2) is stored (fp16) for the backward pass; logit = z2.w3 + b3; p = sigmoid(logit);
 // BCELoss against a per-row label (label_a for rows < rows_a, label_b after) summed into loss_sum; the
@@ -178,6 +312,8 @@ struct EpiDiscL2 {
     int store_z2;
   };
   static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {
     Stager stg;
     float loss;
@@ -248,6 +384,8 @@ struct EpiLeakyMaskStore {
     int ldz;
   };
   static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {
     Stager stg;
   };
@@ -294,6 +432,8 @@ struct EpiDiscParamGrad {
     float* dparams;    // [M,4] += (scaled by GS)
   };
   static constexpr int SMEM_BYTES = 0;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {};
   __device__ static void init(const Params&, State&, const GemmShape&, const EpiCtx&) {}
   __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
@@ -341,6 +481,8 @@ struct EpiDiscParamGrad {
 template <class Cfg>
 struct EpiFwdOut {
   static_assert(Cfg::BLOCK_N == 144 && Cfg::ACC_TILES == 2 && Cfg::ACC_BUFS == 1, "EpiFwdOut tile shape");
+  static constexpr bool SPLIT = true;   // group g handles output columns [144 g, 144 g + 144)
+  static constexpr int CLUSTER = 1;
   struct Params {
     const float* bias;            // [288] zero-padded
     int S, Mt;
@@ -361,30 +503,33 @@ struct EpiFwdOut {
     float* row_err;               // [M] mean_j (x - recon)^2 or null
     int f1_idx, f2_idx;
   };
-  // [0, 64 KB): target tile, 4 swizzled [128 x 64] fp16 boxes (TMA), or the per-warp [32][33] fp32 transposition
-  // buffers of the out_full path; [64 KB, +8): mbarrier of the target loads
+  // group 0's region: [0, 64 KB) target tile, 4 swizzled [128 x 64] fp16 boxes (TMA); [64 KB, +8) its mbarrier;
+  // [+1 KB, +2 KB) group 1's per-row partial errors (two buffers).  Every group's region also serves as its
+  // per-warp [32][17] fp32 transposition buffers on the out_full path (no target tile in that mode).
   static constexpr int kTileBytes = 4 * kStageBytes;
-  static constexpr int SMEM_BYTES = kTileBytes + 1024;
+  static constexpr int kPartOff = kTileBytes + 1024;
+  static constexpr int SMEM_BYTES = kTileBytes + 3072;
   struct State {
     float s_rec, s_met, s_mx, s_lc1, s_lc2;
-    uint32_t tphase;
+    uint32_t tphase, it;
   };
   __device__ static void issue_target(const Params& p, const EpiCtx& cx, int m_tile) {
-    const uint32_t bar = cx.smem + kTileBytes;
+    const uint32_t bar = cx.smem0 + kTileBytes;
     mbar_arrive_expect_tx(bar, kTileBytes);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) tma_load_2d(cx.smem + b * kStageBytes, &p.tgt, bar, b * 64, m_tile * kBlockM);
+    for (int b = 0; b < 4; ++b) tma_load_2d(cx.smem0 + b * kStageBytes, &p.tgt, bar, b * 64, m_tile * kBlockM);
   }
+  __device__ static void sync_groups() { asm volatile("bar.sync 5, 256;" ::: "memory"); }
   __device__ static void init(const Params& p, State& st, const GemmShape& g, const EpiCtx& cx) {
     st.s_rec = st.s_met = st.s_mx = st.s_lc1 = st.s_lc2 = 0.f;
     st.tphase = 0;
-    if (cx.group != 0 || p.target_mode != 2) return;  // ACC_BUFS == 1: only group 0 ever sees a unit
-    if (cx.tid == 0) {
-      mbar_init(cx.smem + kTileBytes, 1);
+    st.it = 0;
+    if (p.target_mode == 2 && cx.group == 0 && cx.tid == 0) {
+      mbar_init(cx.smem0 + kTileBytes, 1);
       fence_barrier_init();
       if ((int)blockIdx.x < g.num_m_tiles) issue_target(p, cx, blockIdx.x);
     }
-    epi_bar_sync(cx, 0);
+    sync_groups();
   }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
@@ -393,50 +538,70 @@ struct EpiFwdOut {
     const int row = row0 + cx.lane;
     const bool valid = row < g.M;
     const int OUT = p.S + p.Mt;
-    const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 33u * 4u);  // this warp's transposition buffer
+    const int jbase = cx.group * 144;
+    const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 17u * 4u);  // this warp's transposition buffer
     float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
     float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
     const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
+    if (cx.group == 1) {
+      // the second differences at columns 144 and 145 reach back into group 0's last two columns
+      float v[16], b[16];
+      tmem_ld16(tacc + 128, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + 128) + k);
+        b[4 * k] = t.x; b[4 * k + 1] = t.y; b[4 * k + 2] = t.z; b[4 * k + 3] = t.w;
+      }
+      tmem_ld_wait();
+      prev2 = v[14] + b[14];
+      prev1 = v[15] + b[15];
+    }
     if (p.target_mode == 2) {
-      mbar_wait(cx.smem + kTileBytes, st.tphase);
+      mbar_wait(cx.smem0 + kTileBytes, st.tphase);
       st.tphase ^= 1u;
     }
 #pragma unroll 1
-    for (int j0 = 0; j0 < 288; j0 += 32) {
-      float v[32];
-      tmem_ld32(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
-      float t[32];
+    for (int k16 = 0; k16 < 9; ++k16) {
+      const int j0 = jbase + 16 * k16;
+      float v[16];
+      tmem_ld16(tacc + j0, v);  // the two 144-column accumulators are adjacent in TMEM
+      float t[16], b[16];
       const bool has_t = p.target_mode != 0 && j0 < p.S;
       if (has_t) {
-        if (p.target_mode == 1) {
-          load_cols32(p.target_row + j0, t);
-        } else {
-          float c[32];
-          load_cols32(p.center + j0, c);
-          const uint32_t box = cx.smem + (uint32_t)(j0 >> 6) * kStageBytes + (uint32_t)rt * 128u;
-          const int h4 = ((j0 >> 5) & 1) * 4;  // first 16-byte chunk of this 32-column half
+        const float* src = (p.target_mode == 1 ? p.target_row : p.center) + j0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+        for (int k = 0; k < 4; ++k) {
+          const float4 q4 = __ldg(reinterpret_cast<const float4*>(src) + k);
+          t[4 * k] = q4.x; t[4 * k + 1] = q4.y; t[4 * k + 2] = q4.z; t[4 * k + 3] = q4.w;
+        }
+        if (p.target_mode == 2) {
+          const uint32_t box = cx.smem0 + (uint32_t)(j0 >> 6) * kStageBytes + (uint32_t)rt * 128u;
+          const int c8 = (j0 & 63) >> 3;  // first 16-byte chunk of these 16 columns inside the 64-column box
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
             uint32_t u0, u1, u2, u3;
-            const uint32_t addr = box + (uint32_t)(((h4 + i) ^ (rt & 7)) << 4);
+            const uint32_t addr = box + (uint32_t)(((c8 + i) ^ (rt & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(addr) : "memory");
             const uint32_t uu[4] = {u0, u1, u2, u3};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uu[k]));
-              t[8 * i + 2 * k] = f.x + c[8 * i + 2 * k];
-              t[8 * i + 2 * k + 1] = f.y + c[8 * i + 2 * k + 1];
+              t[8 * i + 2 * k] += f.x;
+              t[8 * i + 2 * k + 1] += f.y;
             }
           }
         }
       }
-      float b[32];
-      load_cols32(p.bias + j0, b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.bias + j0) + k);
+        b[4 * k] = q4.x; b[4 * k + 1] = q4.y; b[4 * k + 2] = q4.z; b[4 * k + 3] = q4.w;
+      }
       tmem_ld_wait();
       if (j0 >= OUT) continue;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int j = j0 + i;
         const float o = v[i] + b[i];
         v[i] = o;
@@ -462,32 +627,39 @@ struct EpiFwdOut {
         }
       }
       if (p.out_full) {
-        // lane = row while writing to shared memory, lane = column while storing: coalesced global writes
+        // lane = row while writing to shared memory; 2 rows x 16 columns per store instruction
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sts_f32(tb + (uint32_t)(cx.lane * 33 + i) * 4u, v[i]);
+        for (int i = 0; i < 16; ++i) sts_f32(tb + (uint32_t)(cx.lane * 17 + i) * 4u, v[i]);
         __syncwarp();
-        const int col = j0 + cx.lane;
+        const int col = j0 + (cx.lane & 15);
         if (col < OUT) {
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int r = row0 + i;
-            if (r < g.M) p.out_full[(size_t)r * OUT + col] = lds_f32(tb + (uint32_t)(i * 33 + cx.lane) * 4u);
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int rr = 2 * i + (cx.lane >> 4);
+            if (row0 + rr < g.M)
+              p.out_full[(size_t)(row0 + rr) * OUT + col] = lds_f32(tb + (uint32_t)(rr * 17 + (cx.lane & 15)) * 4u);
           }
         }
         __syncwarp();
       }
     }
-    if (p.target_mode == 2) {
-      // everyone is done with the tile: fetch the next one while the MMAs of the next unit run
-      epi_bar_sync(cx, 0);
-      const int next = w.m_tile + (int)gridDim.x;
-      if (cx.tid == 0 && next < g.num_m_tiles) issue_target(p, cx, next);
+    // group 1 hands its part of the row's squared error to group 0 (two buffers alternate between units)
+    const uint32_t part = cx.smem0 + kPartOff + (st.it & 1u) * 512u + (uint32_t)rt * 4u;
+    ++st.it;
+    if (cx.group == 1) sts_f32(part, rec);
+    sync_groups();  // also: everyone is done with the target tile
+    if (p.target_mode == 2 && cx.group == 0 && cx.tid == 0) {
+      const int next = w.m_tile + (int)gridDim.x;   // fetched while the MMAs of the next unit run
+      if (next < g.num_m_tiles) issue_target(p, cx, next);
     }
     if (!valid) return;
     st.s_rec += rec;
     st.s_met += met;
     st.s_mx += mx;
-    if (p.row_err) p.row_err[row] = rec / (float)p.S;
+    if (cx.group == 0) {
+      if (p.row_err) p.row_err[row] = (rec + lds_f32(part)) / (float)p.S;
+      return;
+    }
     if (p.p_norm) {
       const float4 pn = __ldg(reinterpret_cast<const float4*>(p.p_norm) + row);
       const float e1 = f1 - (0.4f * pn.x + 0.6f * pn.z);
@@ -529,6 +701,8 @@ struct EpiWeightGrad {
     float* db;       // [M]
   };
   static constexpr int SMEM_BYTES = 0;
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
   struct State {};
   __device__ static void init(const Params&, State&, const GemmShape&, const EpiCtx&) {}
   __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,

@@ -24,8 +24,29 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   int ctas = sm_count();
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-  const int grid = units < ctas ? units : ctas;
-  note_launch(), kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
+  int grid = units < ctas ? units : ctas;
+  if constexpr (Epi::CLUSTER > 1) {
+    // clusters of CLUSTER CTAs share an m-tile (n_group = cluster rank): the grid must be a multiple of it
+    if (g.num_n_groups != Epi::CLUSTER || g.k_splits != 1)
+      return fail(PIGAN_ERR_INVALID, "cluster epilogue needs num_n_groups == cluster size");
+    grid -= grid % Epi::CLUSTER;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Epi::CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    note_launch();
+    PIGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx ? *tx : tb, g, ep));
+  } else {
+    note_launch(), kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
+  }
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

@@ -83,6 +83,8 @@ struct EpiCtx {
   int q;          // TMEM lane quarter of this warp (row in tile = q*32 + lane)
   int lane;
   int group;      // epilogue group 0/1
+  uint32_t smem0; // scratch region of group 0 (data shared by both groups of a SPLIT epilogue lives there)
+  uint32_t xbar;  // mbarrier expecting 256 * CLUSTER arrivals per phase (SPLIT epilogues)
 };
 __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
   asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
@@ -96,6 +98,12 @@ __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // 
 //        tmem_acc = TMEM address of this unit's first accumulator column, lane field already set
 //        to this warp's 32-lane quarter; row handled by the thread = m_tile*128 + q*32 + lane.
 //   finish(const Params&, State&, const GemmShape&, const EpiCtx&)  // after the loop
+//   static constexpr bool SPLIT    // true: BOTH groups process every unit and split its columns between them
+//                                  // (whole-row epilogues: LayerNorm, the forward-model output layer); false:
+//                                  // group e owns accumulator buffer e and handles every second unit
+//   static constexpr int CLUSTER   // CTAs per cluster (1 or 2).  2: the kernel is launched in clusters of two
+//                                  // CTAs that work on the same m-tile with n_group = cluster rank and may
+//                                  // exchange per-row partials through distributed shared memory
 template <class Cfg, class Epi, int AB_FMT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -112,6 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  const uint32_t xbar = bar_base + 8u * (2 * Cfg::STAGES + 5);  // SPLIT epilogues: per-unit row-partial exchange
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -128,8 +137,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 128);
     }
+    if (Epi::SPLIT) mbar_init(xbar, 256 * Epi::CLUSTER);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -139,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (Epi::CLUSTER > 1) cluster_sync_all();  // the peer's barriers exist before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
@@ -226,6 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     EpiCtx cx;
     cx.group = (warp - 2) >> 2;
     cx.smem = epi_smem + cx.group * Epi::SMEM_BYTES;
+    cx.smem0 = epi_smem;
+    cx.xbar = xbar;
     cx.tid = threadIdx.x - 64 - 128 * cx.group;
     cx.q = warp & 3;  // TMEM lane quarter this warp may access
     cx.lane = lane;
@@ -234,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       const int buf = it % Cfg::ACC_BUFS;
-      if ((Cfg::ACC_BUFS == 2 ? buf : 0) != cx.group) continue;  // group e owns accumulator buffer e
+      if (!Epi::SPLIT && (Cfg::ACC_BUFS == 2 ? buf : 0) != cx.group) continue;  // group e owns buffer e
       const UnitInfo w = decode_unit(g, u);
       const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
       mbar_wait(tfull_bar(buf), use & 1u);
@@ -249,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (Epi::CLUSTER > 1) cluster_sync_all();  // nobody leaves while the peer may still write to it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();

@@ -188,6 +188,9 @@ def test_train_step_matches_reference_golden():
                 continue
             ref = g[f"a_final_{tag}_{name}"]
             got = t.reshape(-1)[fixtures.sample_indices(t.numel())].double().cpu().numpy()
+            if "running" in name:                       # BatchNorm buffers: plain values, batch statistics of 64 rows
+                assert rel(got, ref) < 2e-3, (tag, name)
+                continue
             # Adam's first step moves every weight by ~lr * sign(grad) whatever |grad| is, so an element whose
             # gradient is within rounding of zero may land 2 lr away; everything else must agree to a fraction of lr
             off = np.abs(got - ref) > 0.1 * 2e-4
