@@ -399,70 +399,98 @@ __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(const __half* _
 }
 
 // ------------------------------------------------------------------------------------------ generator head
-// p = tanh(relu(bn2(h2)) W3^T + b3) (generator.py:22-25): warp per row pair, lane owns 8 columns of each 256-column
-// slab, W3 staged in shared memory; also denormalises (data_loader.py:238-252) and builds the fake-row tail of the
-// spectrum operand.
-__global__ void __launch_bounds__(kThreads, 3) g_head_fwd_kernel(
+// p = tanh(relu(bn2(h2)) W3^T + b3) (generator.py:22-25), denormalisation (data_loader.py:238-252) and the fake-row
+// tail of the spectrum operand.  A block stages 128 rows of h2 in shared memory with coalesced 16-byte loads, then
+// each thread owns one row (no cross-lane reductions, tanh once per row); C must be 256.
+constexpr int kHeadRows = 128;
+constexpr int kHeadPitch = 256 * 2 + 16;  // bytes per staged row: +16 keeps the per-row reads conflict-free
+__global__ void __launch_bounds__(kHeadRows) g_head_fwd_kernel(
     const __half* __restrict__ h2, const float* __restrict__ scale, const float* __restrict__ bias,
     const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ p_out,
     float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
     int C, int Kp, int S) {
-  extern __shared__ float w3s[];  // [4][C]
-  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) w3s[i] = w3[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* cst = reinterpret_cast<float*>(smraw);                 // scale[256] bias[256] w3[4][256]
+  float* pds = cst + 6 * 256;                                    // [128][4] denormalised outputs
+  unsigned char* tile = smraw + (6 * 256 + kHeadRows * 4) * 4;   // [128][kHeadPitch]
+  for (int i = threadIdx.x; i < 256; i += kHeadRows) {
+    cst[i] = scale[i];
+    cst[256 + i] = bias[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cst[512 + j * 256 + i] = w3[j * C + i];
+  }
   const float b30 = __ldg(b3 + 0), b31 = __ldg(b3 + 1), b32 = __ldg(b3 + 2), b33 = __ldg(b3 + 3);
-  for (long long rp = w0; rp * 2 < rows; rp += nwarps) {
-    const long long ra = rp * 2, rb = rp * 2 + 1;
-    const bool hasb = rb < rows;
-    float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int c = lane * 8; c < C; c += 256) {
-      float va[8], vb[8], sc[8], bi[8];
-      ld_h8(h2 + ra * C + c, va);
-      if (hasb) ld_h8(h2 + rb * C + c, vb);
-      else zero8(vb);
-      ld_f8(scale + c, sc);
-      ld_f8(bias + c, bi);
+  for (long long base = (long long)blockIdx.x * kHeadRows; base < rows; base += (long long)gridDim.x * kHeadRows) {
+    __syncthreads();  // constants staged / previous tile fully consumed
+    // ---- stage: 128 rows x 32 chunks of 16 bytes, a warp per row and trip
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int idx = i * kHeadRows + threadIdx.x;
+      const int r = idx >> 5, ch = idx & 31;
+      const long long row = base + r < rows ? base + r : rows - 1;
+      const uint4 v = *reinterpret_cast<const uint4*>(h2 + row * C + ch * 8);
+      *reinterpret_cast<uint4*>(tile + r * kHeadPitch + ch * 16) = v;
+    }
+    __syncthreads();
+    // ---- one row per thread
+    const long long row = base + threadIdx.x;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    const unsigned char* mine = tile + threadIdx.x * kHeadPitch;
+#pragma unroll 4
+    for (int ch = 0; ch < 32; ++ch) {
+      const uint4 u = *reinterpret_cast<const uint4*>(mine + ch * 16);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float aa = fmaxf(fmaf(sc[i], va[i], bi[i]), 0.f);
-        const float ab = fmaxf(fmaf(sc[i], vb[i], bi[i]), 0.f);
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float w = w3s[j * C + c + i];
-          d[0][j] = fmaf(aa, w, d[0][j]);
-          d[1][j] = fmaf(ab, w, d[1][j]);
-        }
+      for (int q = 0; q < 2; ++q) {
+        const int c = ch * 8 + q * 4;
+        const float4 sc = *reinterpret_cast<const float4*>(cst + c);
+        const float4 bi = *reinterpret_cast<const float4*>(cst + 256 + c);
+        const float4 wa = *reinterpret_cast<const float4*>(cst + 512 + c);
+        const float4 wb = *reinterpret_cast<const float4*>(cst + 768 + c);
+        const float4 wc = *reinterpret_cast<const float4*>(cst + 1024 + c);
+        const float4 wd = *reinterpret_cast<const float4*>(cst + 1280 + c);
+        const float a0 = fmaxf(fmaf(sc.x, v[4 * q + 0], bi.x), 0.f), a1 = fmaxf(fmaf(sc.y, v[4 * q + 1], bi.y), 0.f);
+        const float a2 = fmaxf(fmaf(sc.z, v[4 * q + 2], bi.z), 0.f), a3 = fmaxf(fmaf(sc.w, v[4 * q + 3], bi.w), 0.f);
+        d0 = fmaf(a0, wa.x, d0); d0 = fmaf(a1, wa.y, d0); d0 = fmaf(a2, wa.z, d0); d0 = fmaf(a3, wa.w, d0);
+        d1 = fmaf(a0, wb.x, d1); d1 = fmaf(a1, wb.y, d1); d1 = fmaf(a2, wb.z, d1); d1 = fmaf(a3, wb.w, d1);
+        d2 = fmaf(a0, wc.x, d2); d2 = fmaf(a1, wc.y, d2); d2 = fmaf(a2, wc.z, d2); d2 = fmaf(a3, wc.w, d2);
+        d3 = fmaf(a0, wd.x, d3); d3 = fmaf(a1, wd.y, d3); d3 = fmaf(a2, wd.z, d3); d3 = fmaf(a3, wd.w, d3);
       }
     }
+    const float p[4] = {tanhf(d0 + b30), tanhf(d1 + b31), tanhf(d2 + b32), tanhf(d3 + b33)};
+    float pd[4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+    for (int e = 0; e < 4; ++e) pd[e] = (p[e] + 1.0f) / 2.0f * 0.6f + 2.2f;  // data_loader.py:238-252
+    if (row < rows) {
+      *reinterpret_cast<float4*>(p_out + row * 4) = make_float4(p[0], p[1], p[2], p[3]);
+      if (pden_out) *reinterpret_cast<float4*>(pden_out + row * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+    }
+    if (tail_fake != nullptr) {
+      *reinterpret_cast<float4*>(pds + threadIdx.x * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+      __syncthreads();
+      // copy the last 64 operand columns of every row (8 chunks of 16 bytes), parameter columns replaced
+      const int t0 = Kp - 64;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) d[t][j] = warp_sum_f(d[t][j]);
+      for (int i = 0; i < 8; ++i) {
+        const int idx = i * kHeadRows + threadIdx.x;
+        const int r = idx >> 3, ch = idx & 7;
+        if (base + r < rows) {
+          float v[8];
+          ld_h8(xc + (base + r) * Kp + t0 + ch * 8, v);
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const long long row = t == 0 ? ra : rb;
-      if (t == 1 && !hasb) break;
-      float p[4] = {tanhf(d[t][0] + b30), tanhf(d[t][1] + b31), tanhf(d[t][2] + b32), tanhf(d[t][3] + b33)};
-      float pd[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) pd[e] = (p[e] + 1.0f) / 2.0f * 0.6f + 2.2f;  // data_loader.py:238-252
-      if (lane == 0) {
-        *reinterpret_cast<float4*>(p_out + row * 4) = make_float4(p[0], p[1], p[2], p[3]);
-        if (pden_out) *reinterpret_cast<float4*>(pden_out + row * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
-      }
-      if (tail_fake != nullptr && lane < 8) {
-        const int t0 = Kp - 64;  // first spectrum-operand column held by the tail
-        float v[8];
-        ld_h8(xc + row * Kp + t0 + lane * 8, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int e = t0 + lane * 8 + i - S;
-          if (e >= 0 && e < 4) v[i] = pd[e] - kParamCenter;
+          for (int k = 0; k < 8; ++k) {
+            const int e = t0 + ch * 8 + k - S;
+            if (e >= 0 && e < 4) v[k] = pds[r * 4 + e] - kParamCenter;
+          }
+          st_h8(tail_fake + (base + r) * 64 + ch * 8, v);
         }
-        st_h8(tail_fake + row * 64 + lane * 8, v);
       }
     }
   }
@@ -622,40 +650,41 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHe
   }
 }
 
-// sums the moment partials over blocks and finishes sum dy, sum dy*xhat and dW3 (one block per 32 columns)
-__global__ void __launch_bounds__(1024) g_head_moments_reduce_kernel(GHeadBwdArgs a, int nblocks) {
+// sums the moment partials over blocks (grid: C/32 x 8 arrays) into tot[8][C] ...
+__global__ void __launch_bounds__(1024) g_head_moments_sum_kernel(const float* __restrict__ part, int nblocks, int C,
+                                                                  float* __restrict__ tot) {
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  float tot[8];
-#pragma unroll 1
-  for (int k = 0; k < 8; ++k) {
-    float s = 0.f;
-    if (c < a.C)
-      for (int b = ty; b < nblocks; b += 32) s += a.part[(size_t)b * 8 * a.C + k * a.C + c];
-    sm[ty][tx] = s;
-    __syncthreads();
+  const int k = blockIdx.y;
+  float s = 0.f;
+  if (c < C)
+    for (int b = ty; b < nblocks; b += 32) s += part[(size_t)b * 8 * C + k * C + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
     float t = 0.f;
-    if (ty == 0) {
 #pragma unroll
-      for (int q = 0; q < 32; ++q) t += sm[q][tx];
-    }
-    tot[k] = t;
-    __syncthreads();
+    for (int q = 0; q < 32; ++q) t += sm[q][tx];
+    tot[k * C + c] = t;
   }
-  if (ty == 0 && c < a.C) {
-    const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
-    float sdy = 0.f, sdyh = 0.f;
+}
+// ... and finishes sum dy, sum dy*xhat and dW3 from them
+__global__ void g_head_moments_finish_kernel(GHeadBwdArgs a, const float* __restrict__ tot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
+  float sdy = 0.f, sdyh = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float w = a.w3[j * a.C + c];
-      sdy = fmaf(w, tot[j], sdy);
-      sdyh = fmaf(w, tot[4 + j], sdyh);
-      a.dw3[j * a.C + c] += a.inv_gs * (sc * tot[4 + j] + bi * tot[j]);   // sum dpre_j * relu(sc*h+bi)
-    }
-    a.sum_dy[c] += sdy;
-    a.sum_dyx[c] += rs * (sdyh - mu * sdy);
+  for (int j = 0; j < 4; ++j) {
+    const float w = a.w3[j * a.C + c];
+    const float t0 = tot[j * a.C + c], t1 = tot[(4 + j) * a.C + c];
+    sdy = fmaf(w, t0, sdy);
+    sdyh = fmaf(w, t1, sdyh);
+    a.dw3[j * a.C + c] += a.inv_gs * (sc * t1 + bi * t0);   // sum dpre_j * relu(sc*h+bi)
   }
+  a.sum_dy[c] += sdy;
+  a.sum_dyx[c] += rs * (sdyh - mu * sdy);
 }
 
 __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
@@ -674,14 +703,12 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
     float g[kU][4], x[kU][4];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const long long r = r0 + u * stride;
-      if (r < rows) {
-        ld_h4(da + r * C + c0, g[u]);
-        ld_h4(h + r * C + c0, x[u]);
-      } else {
-        g[u][0] = g[u][1] = g[u][2] = g[u][3] = 0.f;
-        x[u][0] = x[u][1] = x[u][2] = x[u][3] = 0.f;
-      }
+      long long r = r0 + u * stride;
+      const bool ok = r < rows;
+      r = ok ? r : rows - 1;
+      ld_h4(da + r * C + c0, g[u]);
+      ld_h4(h + r * C + c0, x[u]);
+      if (!ok) g[u][0] = g[u][1] = g[u][2] = g[u][3] = 0.f;   // dy = 0: contributes nothing
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u)
@@ -737,12 +764,11 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) 
   for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < a.rows; r0 += kU * stride) {
     float g[kU][4], x[kU][4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const long long r = r0 + u * stride;
-      if (r < a.rows) {
-        ld_h4(a.dy + r * a.C + c0, g[u]);
-        ld_h4(a.h + r * a.C + c0, x[u]);
-      }
+    for (int u = 0; u < kU; ++u) {  // clamped index: all loads issue back to back, no branches
+      long long r = r0 + u * stride;
+      r = r < a.rows ? r : a.rows - 1;
+      ld_h4(a.dy + r * a.C + c0, g[u]);
+      ld_h4(a.h + r * a.C + c0, x[u]);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -812,7 +838,8 @@ __global__ void __launch_bounds__(kThreads, 4) d_l2_bwd_kernel(const __half* __r
 }
 
 // ------------------------------------------------------------------------------------------ forward model
-// first layer (K = 4, forward_model.py:30-33): warp per row, lane owns 8 of the 256 columns
+// first layer (K = 4, forward_model.py:30-33): a warp handles 4 rows per trip (independent reduction chains), a
+// lane owns 8 of the 256 columns
 __global__ void __launch_bounds__(kThreads) f_l1_kernel(const float* __restrict__ p, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ lnw,
                                                         const float* __restrict__ lnb, __half* __restrict__ out,
@@ -825,32 +852,58 @@ __global__ void __launch_bounds__(kThreads) f_l1_kernel(const float* __restrict_
   ld_f8(b1 + lane * 8, b);
   ld_f8(lnw + lane * 8, gm);
   ld_f8(lnb + lane * 8, bt);
+  constexpr int R = 4;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
-    float h[8];
-    float s = 0.f;
+  const float inv_c = 1.0f / (float)C;
+  for (long long g0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; g0 < rows;
+       g0 += wstride * R) {
+    float4 q[R];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = b[i];
-      t = fmaf(q.x, wr[i].x, t);
-      t = fmaf(q.y, wr[i].y, t);
-      t = fmaf(q.z, wr[i].z, t);
-      t = fmaf(q.w, wr[i].w, t);
-      h[i] = t;
-      s += t;
+    for (int u = 0; u < R; ++u) {
+      const long long row = g0 + u < rows ? g0 + u : rows - 1;
+      q[u] = __ldg(reinterpret_cast<const float4*>(p) + row);
     }
-    const float mean = warp_sum_f(s) / (float)C;
-    float v = 0.f;
+    float h[R][8], s[R], v[R];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float d = h[i] - mean;
-      v = fmaf(d, d, v);
+    for (int u = 0; u < R; ++u) {
+      s[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float t = b[i];
+        t = fmaf(q[u].x, wr[i].x, t);
+        t = fmaf(q[u].y, wr[i].y, t);
+        t = fmaf(q[u].z, wr[i].z, t);
+        t = fmaf(q[u].w, wr[i].w, t);
+        h[u][i] = t;
+        s[u] += t;
+      }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum_f(v) / (float)C + kLnEps);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = lrelu_f(fmaf((h[i] - mean) * rstd, gm[i], bt[i]));
-    st_h8(out + row * C + lane * 8, h);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      s[u] *= inv_c;  // mean
+      v[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = h[u][i] - s[u];
+        v[u] = fmaf(d, d, v[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      if (g0 + u >= rows) break;
+      const float rstd = 1.0f / sqrtf(v[u] * inv_c + kLnEps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[u][i] = lrelu_f(fmaf((h[u][i] - s[u]) * rstd, gm[i], bt[i]));
+      st_h8(out + (g0 + u) * C + lane * 8, h[u]);
+    }
   }
 }
 
@@ -1023,8 +1076,13 @@ void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
-  // a warp handles two rows per trip
-  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, 8 * 2 * 2), kThreads, 4 * C * sizeof(float), st>>>(
+  const size_t smem = (6 * 256 + kHeadRows * 4) * 4 + (size_t)kHeadRows * kHeadPitch;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(g_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, kHeadRows, 148 * 3), kHeadRows, smem, st>>>(
       h2, scale, bias, w3, b3, p_out, pden_out, xc, tail_fake, rows, C, Kp, S);
 }
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
@@ -1037,7 +1095,9 @@ void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
   } else {
     note_launch(), g_head_dpre_kernel<<<grid_for_rows(a.rows, kThreads, 148 * 2), kThreads, 0, st>>>(a);
     note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
-    note_launch(), g_head_moments_reduce_kernel<<<(a.C + 31) / 32, 1024, 0, st>>>(a, grid);
+    float* tot = a.part + (size_t)kPartBlocks * 8 * a.C;   // after the partial rows
+    note_launch(), g_head_moments_sum_kernel<<<dim3((a.C + 31) / 32, 8), 1024, 0, st>>>(a.part, grid, a.C, tot);
+    note_launch(), g_head_moments_finish_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(a, tot);
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
@@ -1070,7 +1130,7 @@ void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __h
 }
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,
                  int64_t rows, int C, cudaStream_t st) {
-  note_launch(), f_l1_kernel<<<grid_for_rows(rows, 8 * 4), kThreads, 0, st>>>(p, w1, b1, lnw, lnb, out, rows, C);
+  note_launch(), f_l1_kernel<<<grid_for_rows(rows, 8 * 4 * 2, 148 * 4), kThreads, 0, st>>>(p, w1, b1, lnw, lnb, out, rows, C);
 }
 void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const float* gamma, const float* beta,
                            int64_t rows, int N, cudaStream_t st) {
