@@ -965,6 +965,31 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
   }
 }
 
+// dw[m, n] += scale * sum_s part[unit(s, tile(m,n))][m % 128][n % 256]; the bias column goes to db[m]
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ part, int tiles_m, int tiles_n,
+                                                        int splits, float* __restrict__ dw, int ld, int m_valid,
+                                                        int n_valid, float scale, int bias_col,
+                                                        float* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= tiles_n * 256 || m >= m_valid) return;
+  const bool is_w = n < n_valid, is_b = n == bias_col;
+  if (!is_w && !is_b) return;
+  const int tiles = tiles_m * tiles_n;
+  const size_t off = ((size_t)((m >> 7) * tiles_n + (n >> 8)) * 128 + (m & 127)) * 256 + (n & 255);
+  const size_t stride = (size_t)tiles * 128 * 256;
+  float t = 0.f;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float a0 = part[off + (size_t)s * stride], a1 = part[off + (size_t)(s + 1) * stride];
+    const float a2 = part[off + (size_t)(s + 2) * stride], a3 = part[off + (size_t)(s + 3) * stride];
+    t += (a0 + a1) + (a2 + a3);
+  }
+  for (; s < splits; ++s) t += part[off + (size_t)s * stride];
+  if (is_w) dw[(size_t)m * ld + n] += scale * t;
+  else db[m] += scale * t;
+}
+
 __global__ void dw_fixup_kernel(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = S + P;
@@ -1147,6 +1172,11 @@ void launch_clip_adam(const AdamArgs& a, cudaStream_t st) {
   int grid = (int)((a.n + kThreads - 1) / kThreads);
   if (grid > 148 * 8) grid = 148 * 8;
   note_launch(), clip_adam_kernel<<<grid, kThreads, 0, st>>>(a);
+}
+void launch_dw_reduce(const float* part, int tiles_m, int tiles_n, int splits, float* dw, int ld, int m_valid,
+                      int n_valid, float scale, int bias_col, float* db, cudaStream_t st) {
+  note_launch(), dw_reduce_kernel<<<dim3(tiles_n, m_valid), 256, 0, st>>>(part, tiles_m, tiles_n, splits, dw, ld, m_valid,
+                                                                    n_valid, scale, bias_col, db);
 }
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,
                      cudaStream_t st) {

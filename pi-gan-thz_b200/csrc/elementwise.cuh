@@ -171,6 +171,9 @@ struct AdamArgs {
   float max_norm;
 };
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st);
+// second stage of the split-K weight-gradient GEMM (EpiWeightGradPartial): fixed-order sum of the k-split slabs
+void launch_dw_reduce(const float* part, int tiles_m, int tiles_n, int splits, float* dw, int ld, int m_valid,
+                      int n_valid, float scale, int bias_col, float* db, cudaStream_t st);
 // rank-1 fix-ups of first-layer weight gradients: dw[i*ld + j] += db[i] * cvec[j] (j < S);
 // dw[i*ld + S + e] += 2.5 * db[i] (e < P)
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,

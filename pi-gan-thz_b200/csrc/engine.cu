@@ -17,6 +17,7 @@ namespace pigan {
 
 namespace {
 
+constexpr int kDwPartSlabs = 160;  // >= SM count: one slab per (output tile, k-split) unit
 constexpr int kKp = 256;  // spectrum operand width (S + P + 2 spare columns <= 256)
 using CfgS = GemmCfg<256, 1, 3, false>;   // store epilogues (2 x 32 KB staging)
 using CfgP = GemmCfg<256, 1, 4, false>;   // no staging
@@ -103,6 +104,8 @@ struct PiganEngine {
   // fp16 weights
   __half *g_w1h, *g_w2h, *g_w2th, *d_w1h, *d_w2h, *d_w2th, *f_wh[6];
   // fp32 scratch
+  uint32_t *d_mask1;                   // [2B][H1/32] sign bits of the discriminator's first activation
+  float *dw_part;                      // [kDwPartSlabs][128][256] split-K weight-gradient slabs
   float *partials;                     // [kPartBlocks x kPartCols] two-stage batch reductions
   float *dpre;                         // [B,4] generator head backward
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
@@ -146,6 +149,8 @@ struct PiganEngine {
       f_wh[i] = c.take<__half>((size_t)out * in);
       in = out;
     }
+    d_mask1 = c.take<uint32_t>((size_t)2 * B * (D1 / 32));
+    dw_part = c.take<float>((size_t)kDwPartSlabs * kBlockM * 256);
     partials = c.take<float>((size_t)kPartBlocks * kPartCols);
     dpre = c.take<float>(B * 4);
     p = c.take<float>(B * 4);
@@ -214,15 +219,17 @@ int out_map(CUtensorMap* m, __half* ptr, int64_t rows, int cols, int ld) {
 }
 
 // out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
-template <bool BIAS, bool LRELU, bool RS>
+template <bool BIAS, bool LRELU, bool RS, bool MASKOUT = false>
 int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
-                 float* rowstats, cudaStream_t st, const __half* a_tail = nullptr) {
-  using Epi = EpiStore<CfgS, BIAS, LRELU, RS>;
+                 float* rowstats, cudaStream_t st, const __half* a_tail = nullptr, uint32_t* mask = nullptr) {
+  using Epi = EpiStore<CfgS, BIAS, LRELU, RS, MASKOUT>;
   typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
   ep.bias = bias;
   ep.rowstats = rowstats;
   ep.n_tiles = ceil_div(n, 256);
+  ep.mask = mask;
+  ep.mask_words = n / 32;
   return run_tn<CfgS, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
 }
 
@@ -256,19 +263,25 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
 // dw[m_out, ld] += (1/gs) * a[kd, m_out]^T b[.., n]
 int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t b_rows, int n, float* dw, int ld,
                 int n_valid, float inv_gs, int bias_col, float* db, int64_t wrap_rows, const __half* b_tail,
-                int64_t tail_from_row, cudaStream_t st) {
+                int64_t tail_from_row, float* part, cudaStream_t st) {
   CUtensorMap ta, tb, tx;
   PIGAN_TRY(make_nt_maps(&ta, &tb, a, (int)kd, m_out, m_out, b, (int)b_rows, n, n));
-  const int tiles = ceil_div(m_out, kBlockM) * ceil_div(n, 256);
+  const int tiles_m = ceil_div(m_out, kBlockM), tiles_n = ceil_div(n, 256);
+  const int tiles = tiles_m * tiles_n;
   int splits = sm_count() / (tiles > 0 ? tiles : 1);
   if (splits < 1) splits = 1;
   GemmShape g = make_shape<CfgW>(m_out, n, (int)kd, splits, (int)wrap_rows);
+  if (tiles * g.k_splits > kDwPartSlabs) return fail(PIGAN_ERR_UNSUPPORTED, "weight-gradient scratch too small");
   if (b_tail) {
     PIGAN_TRY(make_tmap_f16_2d(&tx, b_tail, 64, (uint64_t)(kd - tail_from_row), 64, 64, kBlockK));
     g.b_tail_from_kb = (int)(tail_from_row / kBlockK);
   }
-  EpiWeightGrad<CfgW>::Params ep{dw, ld, n_valid, inv_gs, bias_col, db};
-  return launch_gemm<CfgW, EpiWeightGrad<CfgW>>(ta, tb, g, ep, st, 0, b_tail ? &tx : nullptr);
+  using Epi = EpiWeightGradPartial<CfgW>;
+  Epi::Params ep;
+  PIGAN_TRY(make_tmap_f32_2d(&ep.part, part, 256, (uint64_t)tiles * g.k_splits * kBlockM, 256, kBlockM));
+  PIGAN_TRY((launch_gemm<CfgW, Epi>(ta, tb, g, ep, st, 0, b_tail ? &tx : nullptr)));
+  launch_dw_reduce(part, tiles_m, tiles_n, g.k_splits, dw, ld, m_out, n_valid, inv_gs, bias_col, db, st);
+  return PIGAN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ generator
@@ -352,8 +365,9 @@ void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offs
 // z1 rows [row0, row0+n) = LeakyReLU([xc | tail] . w1h^T)   (bias and parameter columns inside the MMA)
 int d_layer1(PiganEngine* e, int64_t n, int64_t row0, bool fake, cudaStream_t st) {
   PM("d_l1_gemm");
-  return linear_store<false, true, false>(e->xc, n, kKp, e->d_w1h, e->dl.H1, nullptr, e->d_z1 + row0 * e->dl.H1,
-                                          nullptr, st, fake ? e->tail_f : nullptr);
+  return linear_store<false, true, false, true>(e->xc, n, kKp, e->d_w1h, e->dl.H1, nullptr,
+                                                e->d_z1 + row0 * e->dl.H1, nullptr, st, fake ? e->tail_f : nullptr,
+                                                e->d_mask1 + row0 * (e->dl.H1 / 32));
 }
 
 struct DL2Opts {
@@ -508,16 +522,16 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
         using Epi = EpiLeakyMaskStore<CfgS>;
         Epi::Params ep;
         PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
-        ep.z = e->d_z1;
-        ep.ldz = D.H1;
+        ep.mask = e->d_mask1;
+        ep.mask_words = D.H1 / 32;
         PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
       PM("d_dw2_gemm");
       PIGAN_TRY(weight_grad(e->d_dh2, BP + B, D.H2, e->d_z1, BP + B, D.H1, a.d_grads + D.w2, D.H1, D.H1, inv_gs, -1,
-                            nullptr, 0, nullptr, 0, st));
+                            nullptr, 0, nullptr, 0, e->dw_part, st));
       PM("d_dw1_gemm");
       PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
-                            a.d_grads + D.b1, BP, e->tail_f, BP, st));
+                            a.d_grads + D.b1, BP, e->tail_f, BP, e->dw_part, st));
       PM("small");
       launch_dw_fixup(a.d_grads + D.w1, D.IN, D.S, D.P, a.d_grads + D.b1, e->cvec, D.H1, st);
       break;
@@ -538,7 +552,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       {
         PM("d_paramgrad_gemm");
         using Epi = EpiDiscParamGrad<CfgP>;
-        Epi::Params ep{e->d_z1, D.H1, e->d_wp, e->dpden};
+        Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
         PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
       FOutOpts fo{2, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
@@ -553,7 +567,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       launch_g_head_bwd(head_bwd_args(e, a), true, st);
       PM("g_dw2_gemm");
       PIGAN_TRY(weight_grad(e->g_dy2, B, G.H2, e->g_a1, B, G.H1, a.g_grads + G.w2, G.H1, G.H1, inv_gs, -1, nullptr, 0,
-                            nullptr, 0, st));
+                            nullptr, 0, e->dw_part, st));
       PM("g_da1_gemm");
       PIGAN_TRY((linear_store<false, false, false>(e->g_dy2, B, G.H2, e->g_w2th, G.H1, nullptr, e->g_da1, nullptr, st)));
       PM("g_bn_bwd_stats");
@@ -572,7 +586,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       launch_bn_bwd_apply(bb, st);
       PM("g_dw1_gemm");
       PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, kKp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
-                            a.g_grads + G.b1, 0, nullptr, 0, st));
+                            a.g_grads + G.b1, 0, nullptr, 0, e->dw_part, st));
       PM("small");
       launch_dw_fixup(a.g_grads + G.w1, G.S, G.S, 0, a.g_grads + G.b1, e->cvec, G.H1, st);
       break;

@@ -92,7 +92,7 @@ struct Stager {
 // stored value over this tile's columns — the LayerNorm partials the consumer merges
 // (forward_model.py:31-53).  `bias` must be zero-padded to a multiple of BLOCK_N.
 // =====================================================================================================
-template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS>
+template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false>
 struct EpiStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "EpiStore tile shape");
   struct Params {
@@ -100,6 +100,9 @@ struct EpiStore {
     const float* bias;
     float* rowstats;  // [M][n_tiles][2]
     int n_tiles;
+    uint32_t* mask;   // MASKOUT: [M][N/32] sign bits of the stored value (bit i of word c: column 32c+i > 0) —
+                      // all the LeakyReLU backward needs, at 1/16 of the activation's bytes
+    int mask_words;   // words per row (N / 32)
   };
   static constexpr int SMEM_BYTES = kEpiStagingBytes;
   static constexpr bool SPLIT = false;
@@ -113,7 +116,8 @@ struct EpiStore {
     const int r = cx.q * 32 + cx.lane;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
+    uint32_t mw[Cfg::BLOCK_N / 32];
+#pragma unroll
     for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
       const uint32_t buf = st.stg.acquire(cx);
 #pragma unroll
@@ -141,9 +145,23 @@ struct EpiStore {
             s2 = fmaf(v[i], v[i], s2);
           }
         }
+        if constexpr (MASKOUT) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+          mw[sub * 2 + h] = bits;
+        }
         Stager::put32(buf, r, h, v);
       }
       st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
+    }
+    if constexpr (MASKOUT) {
+      const int row = w.m_tile * kBlockM + r;
+      if (row < g.M) {
+        uint4* dst = reinterpret_cast<uint4*>(p.mask + (size_t)row * p.mask_words + n0 / 32);
+#pragma unroll
+        for (int k = 0; k < Cfg::BLOCK_N / 128; ++k) dst[k] = make_uint4(mw[4 * k], mw[4 * k + 1], mw[4 * k + 2], mw[4 * k + 3]);
+      }
     }
     if constexpr (ROWSTATS) {
       const int row = w.m_tile * kBlockM + r;
@@ -380,8 +398,8 @@ struct EpiLeakyMaskStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "tile shape");
   struct Params {
     CUtensorMap out;
-    const __half* z;  // [M, ldz] saved activations
-    int ldz;
+    const uint32_t* mask;  // [M][mask_words] sign bits of the saved activations (EpiStore MASKOUT)
+    int mask_words;
   };
   static constexpr int SMEM_BYTES = kEpiStagingBytes;
   static constexpr bool SPLIT = false;
@@ -396,19 +414,27 @@ struct EpiLeakyMaskStore {
     const int row = w.m_tile * kBlockM + r;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     const bool valid = row < g.M;
-    const __half* zrow = p.z + (size_t)(valid ? row : 0) * p.ldz + n0;
-#pragma unroll 1
+    uint32_t mw[Cfg::BLOCK_N / 32];
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32);
+#pragma unroll
+      for (int k = 0; k < Cfg::BLOCK_N / 128; ++k) {
+        const uint4 t = __ldg(src + k);
+        mw[4 * k] = t.x; mw[4 * k + 1] = t.y; mw[4 * k + 2] = t.z; mw[4 * k + 3] = t.w;
+      }
+    }
+#pragma unroll
     for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
       const uint32_t buf = st.stg.acquire(cx);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = sub * 64 + h * 32;
-        float v[32], z[32];
+        float v[32];
         tmem_ld32(tacc + c, v);
-        load_f16x32(zrow + c, z);
         tmem_ld_wait();
+        const uint32_t bits = mw[sub * 2 + h];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= lrelu_slope_from_out(z[i]);
+        for (int i = 0; i < 32; ++i) v[i] *= ((bits >> i) & 1u) ? 1.f : kLeaky;
         Stager::put32(buf, r, h, v);
       }
       st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
@@ -426,8 +452,8 @@ template <class Cfg>
 struct EpiDiscParamGrad {
   static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N % 32 == 0, "tile shape");
   struct Params {
-    const __half* z;   // [M, ldz]
-    int ldz;
+    const uint32_t* mask;  // [M][mask_words] sign bits of z1 (EpiStore MASKOUT)
+    int mask_words;
     const float* wp;   // [Npad][4]
     float* dparams;    // [M,4] += (scaled by GS)
   };
@@ -441,18 +467,18 @@ struct EpiDiscParamGrad {
     const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     const bool valid = row < g.M;
-    const __half* zrow = p.z + (size_t)(valid ? row : 0) * p.ldz + n0;
+    const uint32_t* mrow = p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
     for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
-      float v[32], z[32];
+      float v[32];
       tmem_ld32(tacc + c, v);
-      load_f16x32(zrow + c, z);
+      const uint32_t bits = __ldg(mrow + c / 32);
       tmem_ld_wait();
       const float4* wq = reinterpret_cast<const float4*>(p.wp) + n0 + c;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float gz = v[i] * lrelu_slope_from_out(z[i]);
+        const float gz = v[i] * (((bits >> i) & 1u) ? 1.f : kLeaky);
         const float4 w4 = __ldg(wq + i);
         a0 = fmaf(gz, w4.x, a0);
         a1 = fmaf(gz, w4.y, a1);
@@ -682,6 +708,53 @@ struct EpiFwdOut {
       if (cx.lane == 0 && t != 0.f && p.sums) atomicAdd(p.sums + k, (double)t);
     }
   }
+};
+
+// =====================================================================================================
+// Split-K weight gradients (autograd dW = dY^T X of every nn.Linear), atomic-free: every unit (output tile x
+// k-split) stores its fp32 accumulator tile to its own [128 x 256] slab of a scratch buffer with TMA stores;
+// dw_reduce_kernel (elementwise.cu) adds the slabs of a tile in a fixed order, un-scales by 1/GS, clips to the
+// real [out,in] extent and routes the bias column.  (The first version used fp32 atomics: 37 splits x 512 KB of
+// same-address reductions cost ~23 of a 60 us kernel and made the gradients run-to-run non-deterministic.)
+// =====================================================================================================
+template <class Cfg>
+struct EpiWeightGradPartial {
+  static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N == 256, "tile shape");
+  static constexpr bool SPLIT = true;   // group g drains columns [128 g, 128 g + 128)
+  static constexpr int CLUSTER = 1;
+  struct Params {
+    CUtensorMap part;  // fp32 [units * 128, 256], box [128 x 32]
+  };
+  static constexpr int SMEM_BYTES = kStageBytes;  // one [128 x 32] fp32 box: the 4-stage operand ring needs the rest
+  struct State {};
+  __device__ static void init(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int u = w.split * (g.num_m_tiles * g.num_n_groups) + w.m_tile * g.num_n_groups + w.n_group;
+#pragma unroll 1
+    for (int c = cx.group * 128; c < cx.group * 128 + 128; c += 32) {
+      float v[32];
+      tmem_ld32(tacc + c, v);
+      if (cx.tid == 0) tma_store_wait_read<0>();  // the previous box has left shared memory
+      epi_bar_sync(cx, 0);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t addr = cx.smem + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      epi_bar_sync(cx, 1);
+      if (cx.tid == 0) {
+        tma_store_2d(&p.part, cx.smem, c, u * kBlockM);
+        tma_store_commit();
+      }
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
 };
 
 // =====================================================================================================

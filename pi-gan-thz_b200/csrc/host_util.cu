@@ -70,6 +70,23 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return PIGAN_OK;
 }
 
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                     uint32_t box_outer) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return fail(PIGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_elems * 4) % 16 != 0 || box_outer > 256)
+    return fail(PIGAN_ERR_INVALID, "fp32 TMA operand must be 16-byte aligned with a 16-byte multiple pitch");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PIGAN_ERR_CUDA, "cuTensorMapEncodeTiled(fp32) failed (CUresult %d)", (int)r);
+  return PIGAN_OK;
+}
+
 }  // namespace pigan
 
 extern "C" int pigan_abi_version(void) { return PIGAN_ABI_VERSION; }

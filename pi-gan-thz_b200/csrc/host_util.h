@@ -44,6 +44,10 @@ int sm_count();  // multiprocessors of the current device (cached per device)
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
 
+// Row-major 2-D fp32 tensor, box = [box_outer, 32 floats] (128 B rows), 128B swizzle: TMA-store target of fp32 tiles.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                     uint32_t box_outer);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
