@@ -307,7 +307,7 @@ def run_native(args):
     score_info = {"metric": "inverse-design candidates/s", "value": cand_s, "unit": "candidates/s",
                   "candidates": n_cand, "k": 1024, "ms": ms3, "best_recon_error": float(res["recon_error"][0]),
                   "tensor_frac": cand_s * FLOP_PER_CANDIDATE / 1e12 / (peaks["tflops"] * world),
-                  "noise": "torch.randn per chunk (explicit noise tensor, SURVEY H7)"}
+                  "noise": "in-kernel Philox4x32-10 keyed by (seed, global candidate index)"}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None

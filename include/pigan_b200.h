@@ -180,6 +180,22 @@ int pigan_score_candidates(PiganEngine* engine, const float* g_params, const flo
                            const float* spectra, const float* target, const float* noise, float sigma, int64_t n,
                            float* out_params_norm, int32_t* out_violations, float* out_recon_error,
                            float* out_consistency, void* stream);
+/* Inverse-design search (BASELINE config 4): scores `count` candidates cand_i = target + sigma * z_i, i = first_candidate
+ * ... first_candidate + count - 1, through G(eval) -> F(eval) -> mean((target - recon)^2) and keeps the k best.
+ * z_i is drawn in-kernel (Philox4x32-10 keyed by `seed`, counter = (i, column block)), so candidate i gets the same
+ * noise whatever the chunking, sharding or number of ranks — a rank passes its own [first_candidate, +count) range
+ * and the k-sized results of all ranks are merged with pigan_topk_smallest after one all-gather.
+ *   out_scores [k] ascending (+inf where fewer than k candidates exist), out_indices [k] global candidate ids
+ *   (-1 for empty slots), out_params_norm [k,4] generator outputs of the winners.
+ *   noise_dump: NULL, or [count, S] fp32 receiving z (tests replay it through pigan_score_candidates).
+ * workspace: pigan_search_workspace_bytes(engine, k) bytes of device memory, 256-byte aligned; k <= 4096. */
+size_t pigan_search_workspace_bytes(const PiganEngine* engine, int32_t k);
+int pigan_inverse_design_search(PiganEngine* engine, const float* g_params, const float* g_bn_buffers,
+                                const float* target, float sigma, uint64_t seed, int64_t first_candidate,
+                                int64_t count, int32_t k, float* out_scores, int64_t* out_indices,
+                                float* out_params_norm, float* noise_dump, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* k smallest of scores[n] (k <= 4096, n < 2^32), ascending, ties by position; NaN sorts last.
  * out_indices[i] = in_indices[pos] when in_indices is given (merging gathered shard results), else
  * index_base + pos.  workspace: pigan_topk_workspace_bytes(n, k) bytes of device memory, 16-byte aligned. */

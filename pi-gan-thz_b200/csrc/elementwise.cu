@@ -203,6 +203,100 @@ __global__ void cast_center_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// Philox4x32-10 (Salmon et al., SC'11) keyed by the search seed, counter = (global candidate index, column block):
+// the noise of candidate i does not depend on how candidates are cut into chunks, shards or ranks.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// 4 uniform words -> 4 standard normals (Box-Muller)
+__device__ __forceinline__ void normal4(uint4 u, float* z) {
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)u.x + 0.5f) * k, u1 = (float)u.y * k;
+  const float u2 = ((float)u.z + 0.5f) * k, u3 = (float)u.w * k;
+  const float r0 = sqrtf(-2.f * __logf(u0)), r1 = sqrtf(-2.f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+// xc[r, j] = fp16((target[j] + sigma * z(first + r, j)) - cvec[j]) (unified_evaluator.py:453-455 with in-kernel noise);
+// noise_out (optional, [rows, S] fp32) receives z itself — tests replay it through the explicit-noise path
+__global__ void cast_center_philox_kernel(const float* __restrict__ target, float sigma, unsigned long long seed,
+                                          long long first, const float* __restrict__ cvec, __half* __restrict__ xc,
+                                          float* __restrict__ noise_out, long long rows, int S, int Kp) {
+  const int cpr = Kp >> 3;
+  const long long total = rows * cpr;
+  const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / cpr;
+    const int j0 = (int)(idx % cpr) * 8;
+    const unsigned long long gi = (unsigned long long)(first + row);
+    float z[8], v[8];
+    normal4(philox4x32_10(make_uint4((unsigned int)gi, (unsigned int)(gi >> 32), (unsigned int)(j0 >> 2), 0u), key), z);
+    normal4(philox4x32_10(make_uint4((unsigned int)gi, (unsigned int)(gi >> 32), (unsigned int)(j0 >> 2) + 1u, 0u), key),
+            z + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + i;
+      float t = 0.f;
+      if (j < S) {
+        t = (target[j] + sigma * z[i]) - cvec[j];
+        if (noise_out) noise_out[row * S + j] = z[i];
+      } else if (j >= S + 4 && j < S + 6) {
+        t = 1.f;
+      }
+      v[i] = t;
+    }
+    st_h8(xc + row * Kp + j0, v);
+  }
+}
+
+// ---- running top-k of the inverse-design search (engine.cu: pigan_inverse_design_search)
+__global__ void search_init_kernel(float* __restrict__ scores, long long* __restrict__ iota, long long* __restrict__ best_idx,
+                                   float* __restrict__ params, long long total, int k) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    iota[i] = i;
+    if (i < k) {
+      scores[i] = __int_as_float(0x7f800000);
+      best_idx[i] = -1;
+      params[4 * i] = params[4 * i + 1] = params[4 * i + 2] = params[4 * i + 3] = 0.f;
+    }
+  }
+}
+__global__ void fill_inf_kernel(float* __restrict__ s, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s[i] = __int_as_float(0x7f800000);
+}
+// winners (positions in [0, k + cap)) -> temporaries
+__global__ void search_gather_kernel(const long long* __restrict__ pos, const float* __restrict__ params,
+                                     const long long* __restrict__ best_idx, long long group_base, int k,
+                                     long long* __restrict__ tmp_idx, float* __restrict__ tmp_params) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const long long q = pos[i];
+  tmp_idx[i] = q < k ? best_idx[q] : group_base + (q - k);
+  *reinterpret_cast<float4*>(tmp_params + 4 * i) = *reinterpret_cast<const float4*>(params + 4 * q);
+}
+__global__ void search_commit_kernel(const float* __restrict__ sel_scores, const long long* __restrict__ tmp_idx,
+                                     const float* __restrict__ tmp_params, int k, float* __restrict__ scores,
+                                     long long* __restrict__ best_idx, float* __restrict__ params) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  scores[i] = sel_scores[i];
+  best_idx[i] = tmp_idx[i];
+  *reinterpret_cast<float4*>(params + 4 * i) = *reinterpret_cast<const float4*>(tmp_params + 4 * i);
+}
+
 // ------------------------------------------------------------------------------------------ weight packing
 __global__ void pack_first_layer_kernel(const float* __restrict__ w, int ld_src, int S, int P, int wp_cols,
                                         int bias_cols, const float* __restrict__ b, const float* __restrict__ cvec,
@@ -1056,6 +1150,34 @@ void launch_cast_center_noise(const float* target, const float* noise, float sig
   note_launch(), cast_center_kernel<true><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp,
                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(target) & 7) == 0 &&
                                                                              (reinterpret_cast<uintptr_t>(noise) & 7) == 0) ? 1 : 0);
+}
+void launch_cast_center_philox(const float* target, float sigma, uint64_t seed, int64_t first, const float* cvec,
+                               __half* xc, float* noise_out, int64_t rows, int S, int Kp, cudaStream_t st) {
+  const int64_t total = rows * (Kp / 8);
+  const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
+  note_launch(), cast_center_philox_kernel<<<grid > 0 ? grid : 1, kThreads, 0, st>>>(
+      target, sigma, (unsigned long long)seed, (long long)first, cvec, xc, noise_out, rows, S, Kp);
+}
+void launch_search_init(float* scores, int64_t* iota, int64_t* best_idx, float* params, int64_t total, int k,
+                        cudaStream_t st) {
+  note_launch(), search_init_kernel<<<148 * 4, 256, 0, st>>>(scores, reinterpret_cast<long long*>(iota),
+                                                       reinterpret_cast<long long*>(best_idx), params, total, k);
+}
+void launch_fill_inf(float* s, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  note_launch(), fill_inf_kernel<<<148 * 2, 256, 0, st>>>(s, n);
+}
+void launch_search_gather(const int64_t* pos, const float* params, const int64_t* best_idx, int64_t group_base, int k,
+                          int64_t* tmp_idx, float* tmp_params, cudaStream_t st) {
+  note_launch(), search_gather_kernel<<<(k + 255) / 256, 256, 0, st>>>(
+      reinterpret_cast<const long long*>(pos), params, reinterpret_cast<const long long*>(best_idx), group_base, k,
+      reinterpret_cast<long long*>(tmp_idx), tmp_params);
+}
+void launch_search_commit(const float* sel_scores, const int64_t* tmp_idx, const float* tmp_params, int k,
+                          float* scores, int64_t* best_idx, float* params, cudaStream_t st) {
+  note_launch(), search_commit_kernel<<<(k + 255) / 256, 256, 0, st>>>(sel_scores, reinterpret_cast<const long long*>(tmp_idx),
+                                                                tmp_params, k, scores,
+                                                                reinterpret_cast<long long*>(best_idx), params);
 }
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st) {

@@ -40,6 +40,18 @@ void launch_cast_center(const float* x, const float* cvec, const float* params, 
 void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
                               float* x_out, int64_t rows, int S, int P, int Kp, cudaStream_t st);
 
+// candidates with in-kernel Philox4x32-10 noise: z(first + r, j) depends only on (seed, global candidate index, j)
+void launch_cast_center_philox(const float* target, float sigma, uint64_t seed, int64_t first, const float* cvec,
+                               __half* xc, float* noise_out, int64_t rows, int S, int Kp, cudaStream_t st);
+// running top-k of the inverse-design search
+void launch_search_init(float* scores, int64_t* iota, int64_t* best_idx, float* params, int64_t total, int k,
+                        cudaStream_t st);
+void launch_fill_inf(float* s, int64_t n, cudaStream_t st);
+void launch_search_gather(const int64_t* pos, const float* params, const int64_t* best_idx, int64_t group_base, int k,
+                          int64_t* tmp_idx, float* tmp_params, cudaStream_t st);
+void launch_search_commit(const float* sel_scores, const int64_t* tmp_idx, const float* tmp_params, int k,
+                          float* scores, int64_t* best_idx, float* params, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------ weight packing
 // First layers (G: main.0, D: main.0): out[i, 0:S] = W[i, 0:S]; out[i, S:S+P] = W[i, S:S+P] (wp_cols = P) or 0;
 // out[i, S+P] = hi(b_eff), out[i, S+P+1] = lo(b_eff) with

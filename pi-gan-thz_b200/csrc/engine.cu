@@ -226,6 +226,7 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
   typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
   ep.bias = bias;
+  ep.scale = nullptr;
   ep.rowstats = rowstats;
   ep.n_tiles = ceil_div(n, 256);
   ep.mask = mask;
@@ -359,6 +360,39 @@ void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offs
   a.num_updates = num_updates;
   PM("small");
   launch_bn_finalize(a, st);
+}
+
+// Generator in eval mode from the prepared operand e->xc: BatchNorm-1 (running statistics) + ReLU are folded
+// into layer 1's epilogue, BatchNorm-2 + ReLU into the head kernel.  `packed`: weights / affines already set up.
+int g_eval_setup(PiganEngine* e, const float* gp, const float* bn, cudaStream_t st) {
+  const GenLayout& G = e->gl;
+  PIGAN_TRY(pack_generator(e, gp, false, st));
+  PM("small");
+  launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
+  launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+  return PIGAN_OK;
+}
+int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cudaStream_t st) {
+  const GenLayout& G = e->gl;
+  {
+    PM("g_l1_gemm");
+    using Epi = EpiStore<CfgS, false, false, false, false, true>;
+    Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, e->g_a1, n, G.H1, G.H1));
+    ep.bias = e->bias1;
+    ep.scale = e->scale1;
+    ep.rowstats = nullptr;
+    ep.n_tiles = 0;
+    ep.mask = nullptr;
+    ep.mask_words = 0;
+    PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st)));
+  }
+  PM("g_l2_gemm");
+  PIGAN_TRY((linear_store<false, false, false>(e->g_a1, n, G.H1, e->g_w2h, G.H2, nullptr, e->g_h2, nullptr, st)));
+  PM("g_head_fwd");
+  launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, p_out, nullptr, e->xc, nullptr, n, G.H2, kKp,
+                    G.S, st);
+  return PIGAN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ discriminator
@@ -705,26 +739,21 @@ extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GenLayout& G = e->gl;
   PIGAN_TRY(prep_spectrum(e, x, nullptr, n, st));
+  if (!training) {
+    PIGAN_TRY(g_eval_setup(e, gp, bn, st));
+    PIGAN_TRY(g_eval_forward(e, gp, n, out, st));
+    PM(nullptr);
+    PIGAN_CUDA_OK(cudaGetLastError());
+    return PIGAN_OK;
+  }
   PIGAN_TRY(pack_generator(e, gp, false, st));
   PIGAN_TRY(g_layer1(e, n, st));
-  if (training) {
-    PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
-    g_bn_stats(e, 1, n, st);
-    g_bn_finalize(e, 1, gp, e->g_beff, bn, nbt, (double)n, 1, st);
-  } else {
-    PM("small");
-    PM("small");
-  launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
-  }
+  PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+  g_bn_stats(e, 1, n, st);
+  g_bn_finalize(e, 1, gp, e->g_beff, bn, nbt, (double)n, 1, st);
   PIGAN_TRY(g_layer2(e, gp, n, st));
-  if (training) {
-    g_bn_stats(e, 2, n, st);
-    g_bn_finalize(e, 2, gp, gp + G.b2, bn, nbt, (double)n, 1, st);
-  } else {
-    PM("small");
-    PM("small");
-  launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
-  }
+  g_bn_stats(e, 2, n, st);
+  g_bn_finalize(e, 2, gp, gp + G.b2, bn, nbt, (double)n, 1, st);
   PM("g_head_fwd");
   launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, out, nullptr, e->xc, nullptr, n, G.H2, kKp,
                     G.S, st);
@@ -839,17 +868,9 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
     launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);
     launch_cast_center_noise(target, noise, sigma, e->cvec, e->xc, nullptr, n, G.S, G.P, kKp, st);
   }
-  PIGAN_TRY(pack_generator(e, gp, false, st));
-  PIGAN_TRY(g_layer1(e, n, st));
-  PM("small");
-  launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
-  PIGAN_TRY(g_layer2(e, gp, n, st));
-  PM("small");
-  launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+  PIGAN_TRY(g_eval_setup(e, gp, bn, st));
   float* p = out_p ? out_p : e->p;
-  PM("g_head_fwd");
-  launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, p, nullptr, e->xc, nullptr, n, G.H2, kKp,
-                    G.S, st);
+  PIGAN_TRY(g_eval_forward(e, gp, n, p, st));
   float* err = out_err ? out_err : e->row_err;
   // per-candidate error against its own spectrum (given spectra) or against the design target (cvec = target)
   FOutOpts fo{spectra ? 2 : 1, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
@@ -857,6 +878,90 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
   PM("small");
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
   PM(nullptr);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ inverse-design search
+namespace {
+constexpr int kSearchGroup = 16;  // chunks scored between two top-k merges
+struct SearchWs {
+  float* scores;      // [k + cap]   [0,k) best so far, [k, ...) this group's reconstruction errors
+  float* params;      // [(k + cap) * 4]
+  int64_t* iota;      // [k + cap]
+  int64_t* best_idx;  // [k]
+  float* sel_scores;  // [k]
+  int64_t* sel_pos;   // [k]
+  int64_t* tmp_idx;   // [k]
+  float* tmp_params;  // [4k]
+  void* topk_ws;
+  size_t topk_bytes;
+  size_t carve(void* base, int64_t cap, int k) {
+    Carver c(base);
+    scores = c.take<float>(k + cap);
+    params = c.take<float>((size_t)(k + cap) * 4);
+    iota = c.take<int64_t>(k + cap);
+    best_idx = c.take<int64_t>(k);
+    sel_scores = c.take<float>(k);
+    sel_pos = c.take<int64_t>(k);
+    tmp_idx = c.take<int64_t>(k);
+    tmp_params = c.take<float>((size_t)k * 4);
+    topk_bytes = pigan_topk_workspace_bytes(k + cap, k);
+    topk_ws = c.take<uint8_t>(topk_bytes);
+    return (c.off + 255) & ~size_t(255);
+  }
+};
+}  // namespace
+
+extern "C" size_t pigan_search_workspace_bytes(const PiganEngine* e, int32_t k) {
+  if (!e || k < 1 || k > 4096) return 0;
+  SearchWs w;
+  return w.carve(nullptr, (int64_t)kSearchGroup * e->max_batch, k);
+}
+
+extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, const float* bn, const float* target,
+                                           float sigma, uint64_t seed, int64_t first_candidate, int64_t count,
+                                           int32_t k, float* out_scores, int64_t* out_indices, float* out_params,
+                                           float* noise_dump, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  PIGAN_CHECK_ARG(e && gp && bn && target && out_scores && out_indices && out_params && workspace);
+  PIGAN_CHECK_ARG(k >= 1 && k <= 4096 && count >= 0 && first_candidate >= 0);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
+  if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GenLayout& G = e->gl;
+  const int64_t chunk = e->max_batch;
+  const int64_t cap = (int64_t)kSearchGroup * chunk;
+  SearchWs w;
+  const size_t need = w.carve(workspace, cap, k);
+  if (workspace_bytes < need) return fail(PIGAN_ERR_WORKSPACE, "search workspace too small: %zu < %zu", workspace_bytes, need);
+  launch_search_init(w.scores, w.iota, w.best_idx, w.params, k + cap, k, st);
+  // weights and the target do not change during a search: pack / fold once
+  launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);   // centre on the design target
+  PIGAN_TRY(g_eval_setup(e, gp, bn, st));
+  for (int64_t g0 = 0; g0 < count; g0 += cap) {
+    const int64_t in_group = count - g0 < cap ? count - g0 : cap;
+    for (int64_t off = 0; off < in_group; off += chunk) {
+      const int64_t n = in_group - off < chunk ? in_group - off : chunk;
+      PM("prep_cast");
+      launch_cast_center_philox(target, sigma, seed, first_candidate + g0 + off, e->cvec, e->xc,
+                                noise_dump ? noise_dump + (size_t)(g0 + off) * G.S : nullptr, n, G.S, kKp, st);
+      float* p = w.params + (size_t)(k + off) * 4;
+      PIGAN_TRY(g_eval_forward(e, gp, n, p, st));
+      FOutOpts fo{1, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, w.scores + k + off, 0, 1};
+      PIGAN_TRY(f_forward(e, p, n, fo, st));
+    }
+    PM("topk");
+    launch_fill_inf(w.scores + k + in_group, cap - in_group, st);
+    PIGAN_TRY(pigan_topk_smallest(w.scores, w.iota, k + cap, k, 0, w.sel_scores, w.sel_pos, w.topk_ws, w.topk_bytes,
+                                  stream));
+    launch_search_gather(w.sel_pos, w.params, w.best_idx, first_candidate + g0, k, w.tmp_idx, w.tmp_params, st);
+    launch_search_commit(w.sel_scores, w.tmp_idx, w.tmp_params, k, w.scores, w.best_idx, w.params, st);
+  }
+  PM(nullptr);
+  PIGAN_CUDA_OK(cudaMemcpyAsync(out_scores, w.scores, (size_t)k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PIGAN_CUDA_OK(cudaMemcpyAsync(out_indices, w.best_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  PIGAN_CUDA_OK(cudaMemcpyAsync(out_params, w.params, (size_t)k * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

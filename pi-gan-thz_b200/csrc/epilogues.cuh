@@ -92,12 +92,14 @@ struct Stager {
 // stored value over this tile's columns — the LayerNorm partials the consumer merges
 // (forward_model.py:31-53).  `bias` must be zero-padded to a multiple of BLOCK_N.
 // =====================================================================================================
-template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false>
+template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false>
 struct EpiStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "EpiStore tile shape");
   struct Params {
     CUtensorMap out;
     const float* bias;
+    const float* scale;  // AFFINE_RELU: out = relu(scale[c] * acc + bias[c]) — eval-mode BatchNorm + ReLU folded
+                         // into the producing layer (generator.py:19-20 with running statistics)
     float* rowstats;  // [M][n_tiles][2]
     int n_tiles;
     uint32_t* mask;   // MASKOUT: [M][N/32] sign bits of the stored value (bit i of word c: column 32c+i > 0) —
@@ -125,7 +127,14 @@ struct EpiStore {
         const int c = sub * 64 + h * 32;
         float v[32];
         tmem_ld32(tacc + c, v);
-        if constexpr (BIAS) {
+        if constexpr (AFFINE_RELU) {
+          float b[32], sc[32];
+          load_cols32(p.bias + n0 + c, b);
+          load_cols32(p.scale + n0 + c, sc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(sc[i], v[i], b[i]), 0.f);
+        } else if constexpr (BIAS) {
           float b[32];
           load_cols32(p.bias + n0 + c, b);
           tmem_ld_wait();

@@ -45,6 +45,7 @@ class Engine:
         self.handle = handle
         self._f_params = None
         self._topk_ws = None
+        self._search_ws = None
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -155,6 +156,30 @@ class Engine:
                                          native.ptr(nz), float(sigma), n, native.ptr(out_p), viol.data_ptr(),
                                          err.data_ptr(), cons.data_ptr(), native.current_stream()))
         return {"params_norm": out_p, "violations": viol, "recon_error": err, "consistency": cons}
+
+
+def _search(self, g_flat, bn, target, sigma, seed, first, count, k, dump_noise=False):
+    """pigan_inverse_design_search on this engine: (scores [k], indices [k], params_norm [k,4][, noise])."""
+    dev = self.device
+    nbytes = lib.pigan_search_workspace_bytes(self.handle, k)
+    if nbytes == 0:
+        raise native.PiganError(-1, f"k={k} out of range (1..4096)")
+    if self._search_ws is None or self._search_ws.numel() < nbytes:
+        self._search_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out_s = torch.empty(k, device=dev, dtype=torch.float32)
+    out_i = torch.empty(k, device=dev, dtype=torch.int64)
+    out_p = torch.empty(k, 4, device=dev, dtype=torch.float32)
+    noise = torch.empty(count, self.dims.spectrum_dim, device=dev, dtype=torch.float32) if dump_noise else None
+    tg = _f32c(target).reshape(-1)
+    check(lib.pigan_inverse_design_search(self.handle, g_flat.data_ptr(), bn.data_ptr(), tg.data_ptr(), float(sigma),
+                                          int(seed), int(first), int(count), int(k), out_s.data_ptr(),
+                                          out_i.data_ptr(), out_p.data_ptr(), native.ptr(noise),
+                                          self._search_ws.data_ptr(), self._search_ws.numel(),
+                                          native.current_stream()))
+    return (out_s, out_i, out_p, noise) if dump_noise else (out_s, out_i, out_p)
+
+
+Engine.search = _search
 
 
 def topk_smallest(scores: torch.Tensor, k: int, index_base: int = 0, in_indices: Optional[torch.Tensor] = None):

@@ -6,6 +6,11 @@ evaluator's per-sample reconstruction error ``mean((target - F(G(cand_i)).spectr
 are cut into fixed-size chunks; chunk ``j`` always draws its noise from ``seed + j``, and ranks own contiguous
 chunk ranges, so the ranking does not depend on the number of GPUs.  Every rank keeps a running top-k; the only
 collective is one final all-gather of k (score, global index, 4 params) rows per rank followed by a local merge.
+
+Two noise sources: ``noise="philox"`` (default) draws the noise inside the kernel from Philox4x32-10 keyed by the
+seed and counted by the GLOBAL candidate index — one C call per rank (pigan_inverse_design_search), ranks own
+contiguous index ranges, and candidate i gets the same noise at any world size.  ``noise="torch"`` feeds explicit
+``torch.randn`` tensors chunk by chunk (the parity path).
 """
 from __future__ import annotations
 
@@ -22,6 +27,11 @@ def shard_chunks(num_chunks: int, rank: int, world: int) -> Tuple[int, int]:
     base, extra = divmod(num_chunks, world)
     begin = rank * base + min(rank, extra)
     return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous candidate range [begin, end) of ``rank`` (same rule as shard_chunks)."""
+    return shard_chunks(n, rank, world)
 
 
 def merge_topk(scores: torch.Tensor, indices: torch.Tensor, params: torch.Tensor, k: int,
@@ -52,13 +62,23 @@ class InverseDesigner:
         self.world = dist.get_world_size(process_group) if on else 1
 
     def search(self, target: torch.Tensor, num_candidates: int, k: int = 1024, sigma: float = 0.01,
-               seed: int = 0) -> Dict[str, torch.Tensor]:
+               seed: int = 0, noise: str = "philox") -> Dict[str, torch.Tensor]:
         """Scores ``num_candidates`` noisy candidates around ``target`` [S] and returns the k best over all ranks
         (identical on every rank): ``recon_error`` [k] ascending, ``index`` [k] global candidate ids,
         ``params_norm`` [k,4].  ``scored`` is the number of candidates this rank processed."""
         dev = self.engine.device
         target = target.to(dev, torch.float32).reshape(-1).contiguous()
         S = target.numel()
+        if noise == "philox":
+            lo, hi = shard_range(num_candidates, self.rank, self.world)
+            best_s, best_i, best_p = self.engine.search(self.g_flat, self.g_bn, target, sigma, seed, lo, hi - lo, k)
+            keep = torch.isfinite(best_s)
+            best_s, best_i, best_p = best_s[keep], best_i[keep], best_p[keep]
+            if self.world > 1:
+                best_s, best_i, best_p = self._gather_merge(best_s, best_i, best_p, k)
+            return {"recon_error": best_s, "index": best_i, "params_norm": best_p, "scored": hi - lo}
+        if noise != "torch":
+            raise ValueError("noise must be 'philox' or 'torch'")
         num_chunks = (num_candidates + self.chunk - 1) // self.chunk
         c0, c1 = shard_chunks(num_chunks, self.rank, self.world)
         best_s = torch.empty(0, device=dev, dtype=torch.float32)

@@ -392,7 +392,7 @@ def test_inverse_design_search_is_chunk_and_shard_invariant():
     st = flat.net_state(G, "generator")
     target = fixtures.make_batch(1, seed=1)[0][0]
     des = scoring.InverseDesigner(eng, st.params.tensor(), st.bn.tensor(), chunk=4096)
-    full = des.search(target, 10 * 4096 - 100, k=256, seed=3)
+    full = des.search(target, 10 * 4096 - 100, k=256, seed=3, noise="torch")
     assert full["scored"] == 10 * 4096 - 100
     assert torch.all(full["recon_error"][1:] >= full["recon_error"][:-1])
     # emulate 3 ranks: each scores its own chunk range, then the gathered rows are merged
@@ -411,7 +411,56 @@ def _search_range(des, target, c0, c1, total, k, seed):
     saved = scoring.shard_chunks
     scoring.shard_chunks = lambda num_chunks, rank, world: (c0, c1)
     try:
-        out = des.search(target, total, k=k, seed=seed)
+        out = des.search(target, total, k=k, seed=seed, noise="torch")
     finally:
         scoring.shard_chunks = saved
     return out["recon_error"], out["index"], out["params_norm"]
+
+
+# ------------------------------------------------------------------------------------------ in-kernel noise search
+def _search_setup(max_batch):
+    from pigan_b200 import flat
+    from pigan_b200.engine import Engine
+    g_sd, d_sd, f_sd = _weights()
+    G, D, F = _models(g_sd, d_sd, f_sd)
+    G.eval()
+    eng = Engine(max_batch, torch.device(DEV))
+    eng.load_forward_model(flat.net_state(F, "forward_model").params.tensor())
+    st = flat.net_state(G, "generator")
+    return eng, st, (G, D, F)
+
+
+def test_philox_search_matches_brute_force_and_is_shard_invariant():
+    """pigan_inverse_design_search: (1) the noise it draws, replayed through the explicit-noise scoring call, gives
+    bit-identical errors, so its top-k equals the brute-force ranking; (2) splitting the candidate range over
+    'ranks' and merging their top-k reproduces the single-range result bit for bit; (3) the noise is N(0,1)."""
+    from oracle import fixtures
+    from pigan_b200 import scoring
+    eng, st, keep = _search_setup(2048)
+    target = fixtures.make_batch(1, seed=1)[0][0].to(DEV)
+    n, k = 2048 * 16 * 2 + 777, 100           # more than two top-k merge groups, ragged tail
+    s, i, p, z = eng.search(st.params.tensor(), st.bn.tensor(), target, 0.01, 1234, 0, n, k, dump_noise=True)
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.var()) - 1.0) < 5e-3
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05                 # Gaussian kurtosis
+    assert abs(float((z[:-1] * z[1:]).mean())) < 5e-3               # neighbouring candidates uncorrelated
+    errs = []
+    for c0 in range(0, n, 2048):
+        out = eng.score_candidates(st.params.tensor(), st.bn.tensor(), target=target, noise=z[c0:c0 + 2048].contiguous(),
+                                   sigma=0.01)
+        errs.append(out["recon_error"])
+    err = torch.cat(errs)
+    order = torch.argsort(err.double(), stable=True)[:k]
+    assert torch.equal(i, order) and torch.equal(s, err[order])
+    # shards: three contiguous ranges with their own first_candidate
+    parts = []
+    for r in range(3):
+        lo, hi = scoring.shard_range(n, r, 3)
+        parts.append(eng.search(st.params.tensor(), st.bn.tensor(), target, 0.01, 1234, lo, hi - lo, k))
+    ms, mi, mp = scoring.merge_topk(torch.cat([q[0] for q in parts]), torch.cat([q[1] for q in parts]),
+                                    torch.cat([q[2] for q in parts]), k)
+    assert torch.equal(mi, i) and torch.equal(ms, s) and torch.equal(mp, p)
+    # a different seed gives a different ranking; fewer candidates than k leaves empty slots
+    s2, i2, _ = eng.search(st.params.tensor(), st.bn.tensor(), target, 0.01, 99, 0, n, k)
+    assert not torch.equal(i2, i)
+    s3, i3, _ = eng.search(st.params.tensor(), st.bn.tensor(), target, 0.01, 1234, 0, 10, k)
+    assert int(torch.isfinite(s3).sum()) == 10 and int((i3 >= 0).sum()) == 10
