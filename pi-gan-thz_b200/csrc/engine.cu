@@ -237,26 +237,30 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, const float* gamma,
               const float* beta, __half* out, cudaStream_t st) {
+  CUtensorMap ta, tb;
+  PIGAN_TRY(make_tn_maps<CfgL1>(&ta, &tb, a, (int)rows, k, k, w, n, k));
+  GemmShape g = make_shape<CfgL1>((int)rows, n, k);
   if (n == 256) {
-    using Epi = EpiLnStore<CfgL1, 1>;
+    using Epi = EpiLnStore<CfgL1, 1, false>;
     typename Epi::Params ep;
     PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
     ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return run_tn<CfgL1, Epi>(ep, a, rows, k, k, w, n, k, st);
+    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
   }
+  g.pair_mode = 1;
   if (n == 512) {
-    using Epi = EpiLnStore<CfgL2, 1>;
+    using Epi = EpiLnStore<CfgL1, 1, true>;
     typename Epi::Params ep;
     PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
     ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return run_tn<CfgL2, Epi>(ep, a, rows, k, k, w, n, k, st);
+    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
   }
   if (n == 1024) {
-    using Epi = EpiLnStore<CfgL2, 2>;
+    using Epi = EpiLnStore<CfgL1, 2, true>;
     typename Epi::Params ep;
     PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
     ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return run_tn<CfgL2, Epi>(ep, a, rows, k, k, w, n, k, st);
+    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
   }
   return fail(PIGAN_ERR_UNSUPPORTED, "LayerNorm width %d", n);
 }

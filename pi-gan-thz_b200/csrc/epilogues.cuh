@@ -189,13 +189,17 @@ struct EpiStore {
 // 1024-wide layer two CTAs of a cluster split the row (512 accumulator columns = all of TMEM each) and the four
 // row partials meet through distributed shared memory + one cluster-scope mbarrier per unit.
 // =====================================================================================================
-template <class Cfg, int CLUSTER_>
+//   PAIR = false (N = 256): the two groups split the single 256-column accumulator of every unit.
+//   PAIR = true  (N = 512, 1024): a CTA handles the two 256-column n-groups of an m-tile back to back (GemmShape
+//   pair_mode), one per accumulator buffer and epilogue group, so group 0's first pass overlaps the MMAs of the
+//   second n-group and the second passes overlap the MMAs of the next m-tile.
+template <class Cfg, int CLUSTER_, bool PAIR>
 struct EpiLnStore {
-  static_assert(Cfg::BLOCK_N == 256, "EpiLnStore tile shape");
-  static constexpr bool SPLIT = true;
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1, "EpiLnStore tile shape");
+  static constexpr bool SPLIT = !PAIR;
   static constexpr int CLUSTER = CLUSTER_;
-  static constexpr int NCTA = Cfg::ACC_COLS;  // accumulator columns of one CTA (256 or 512)
-  static constexpr int NG = NCTA / 2;         // columns one epilogue group handles
+  static constexpr int NCTA = PAIR ? 512 : 256;  // columns of the row one CTA handles
+  static constexpr int NG = NCTA / 2;            // columns one epilogue group handles
   static_assert(NG % 64 == 0, "group columns must be whole TMA-store sub-tiles");
   struct Params {
     CUtensorMap out;
@@ -242,7 +246,7 @@ struct EpiLnStore {
   __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
                               const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const uint32_t tcol0 = tacc + (uint32_t)(cx.group * NG);
+    const uint32_t tcol0 = PAIR ? tacc : tacc + (uint32_t)(cx.group * NG);
     const uint32_t cb = cx.smem + kConstOff;
     // ---- pass 1: row partials over this group's columns
     float s1 = 0.f, s2 = 0.f;
@@ -635,30 +639,47 @@ struct EpiFwdOut {
       }
       tmem_ld_wait();
       if (j0 >= OUT) continue;
+      if (j0 >= 2 && j0 + 16 <= p.S) {
+        // interior spectrum chunk (all but the first and the last two of the 18): branch-free
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int j = j0 + i;
-        const float o = v[i] + b[i];
-        v[i] = o;
-        if (j < p.S) {
+        for (int i = 0; i < 16; ++i) {
+          const float o = v[i] + b[i];
+          v[i] = o;
           if (has_t) {
             const float d = o - t[i];
             rec = fmaf(d, d, rec);
           }
-          if (j >= 2) {
-            const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
-            mx = fmaf(d2, d2, mx);
-          }
+          const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
+          mx = fmaf(d2, d2, mx);
           prev2 = prev1;
           prev1 = o;
-        } else if (j < OUT) {
-          const int k = j - p.S;
-          if (ms) {
-            const float d = o - __ldg(ms + k);
-            met = fmaf(d, d, met);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int j = j0 + i;
+          const float o = v[i] + b[i];
+          v[i] = o;
+          if (j < p.S) {
+            if (has_t) {
+              const float d = o - t[i];
+              rec = fmaf(d, d, rec);
+            }
+            if (j >= 2) {
+              const float d2 = (o - prev1) - (prev1 - prev2);
+              mx = fmaf(d2, d2, mx);
+            }
+            prev2 = prev1;
+            prev1 = o;
+          } else if (j < OUT) {
+            const int k = j - p.S;
+            if (ms) {
+              const float d = o - __ldg(ms + k);
+              met = fmaf(d, d, met);
+            }
+            if (k == p.f1_idx) f1 = o;
+            if (k == p.f2_idx) f2 = o;
           }
-          if (k == p.f1_idx) f1 = o;
-          if (k == p.f2_idx) f2 = o;
         }
       }
       if (p.out_full) {

@@ -19,16 +19,19 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
                                        Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES));
     attr_done = true;
   }
-  const int units = g.num_m_tiles * g.num_n_groups * g.k_splits;
+  // CTAs that can have work: one per unit, or one per (m-tile, cluster rank) in pair mode
+  const int units = g.pair_mode ? g.num_m_tiles * Epi::CLUSTER : g.num_m_tiles * g.num_n_groups * g.k_splits;
   if (units <= 0) return PIGAN_OK;
+  if (g.pair_mode && (g.k_splits != 1 || g.num_n_groups != 2 * Epi::CLUSTER || Cfg::ACC_BUFS != 2))
+    return fail(PIGAN_ERR_INVALID, "pair mode needs num_n_groups == 2 * cluster size and two accumulator buffers");
   int ctas = sm_count();
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   int grid = units < ctas ? units : ctas;
   if constexpr (Epi::CLUSTER > 1) {
     // clusters of CLUSTER CTAs share an m-tile (n_group = cluster rank): the grid must be a multiple of it
-    if (g.num_n_groups != Epi::CLUSTER || g.k_splits != 1)
-      return fail(PIGAN_ERR_INVALID, "cluster epilogue needs num_n_groups == cluster size");
+    if (g.k_splits != 1 || g.num_n_groups != (g.pair_mode ? 2 : 1) * Epi::CLUSTER)
+      return fail(PIGAN_ERR_INVALID, "cluster epilogue needs num_n_groups == cluster size (x2 in pair mode)");
     grid -= grid % Epi::CLUSTER;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -79,6 +82,7 @@ GemmShape make_shape(int m, int n, int k, int k_splits = 1, int b_wrap_rows = 0)
   g.b_wrap_k_blocks = b_wrap_rows / kBlockK;
   g.a_tail = 0;
   g.b_tail_from_kb = -1;
+  g.pair_mode = 0;
   return g;
 }
 

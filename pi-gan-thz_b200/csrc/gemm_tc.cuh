@@ -38,6 +38,9 @@ struct GemmShape {
   int b_wrap_k_blocks;  // NT mode: B operand row block index is taken modulo this (0 = off)
   int a_tail;           // TN mode: last k-block of A is read from tmap_x at column 0
   int b_tail_from_kb;   // NT mode: k-blocks >= this read the last B box of the last n-tile from tmap_x (<0 off)
+  int pair_mode;        // a CTA handles the two n-groups of an m-tile back to back (whole-row epilogues that split
+                        // the row between the two epilogue groups / accumulator buffers); k_splits must be 1 and
+                        // num_n_groups == 2 * cluster size
 };
 
 struct UnitInfo {
@@ -54,6 +57,25 @@ __device__ __forceinline__ UnitInfo decode_unit(const GemmShape& g, int u) {
   w.kb_begin = (int)(((long long)w.split * g.num_k_blocks) / g.k_splits);
   w.kb_end = (int)(((long long)(w.split + 1) * g.num_k_blocks) / g.k_splits);
   return w;
+}
+
+// it-th unit of this CTA (false: no more).  Every role of the kernel walks the same sequence.
+template <int CLUSTER>
+__device__ __forceinline__ bool get_unit(const GemmShape& g, int it, UnitInfo& w) {
+  if (g.pair_mode) {
+    const int m_tile = (int)blockIdx.x / CLUSTER + (it >> 1) * ((int)gridDim.x / CLUSTER);
+    if (m_tile >= g.num_m_tiles) return false;
+    w.m_tile = m_tile;
+    w.n_group = 2 * ((int)blockIdx.x % CLUSTER) + (it & 1);
+    w.split = 0;
+    w.kb_begin = 0;
+    w.kb_end = g.num_k_blocks;
+    return true;
+  }
+  const int u = (int)blockIdx.x + it * (int)gridDim.x;
+  if (u >= g.num_m_tiles * g.num_n_groups * g.k_splits) return false;
+  w = decode_unit(g, u);
+  return true;
 }
 
 template <int BLOCK_N_, int ACC_TILES_, int STAGES_, bool MN_MAJOR_>
@@ -126,7 +148,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_units = g.num_m_tiles * g.num_n_groups * g.k_splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -139,7 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 128);
     }
-    if (Epi::SPLIT) mbar_init(xbar, 256 * Epi::CLUSTER);
+    mbar_init(xbar, 256 * Epi::CLUSTER);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -157,8 +178,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const UnitInfo w = decode_unit(g, u);
+      UnitInfo w;
+      for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
         for (int t = 0; t < Cfg::ACC_TILES; ++t) {
           const int nt = w.n_group * Cfg::ACC_TILES + t;
           const int n0 = nt * Cfg::BLOCK_N;
@@ -204,9 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t kstep = Cfg::MN_MAJOR ? 2048u : 32u;  // bytes per UMMA_K step
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
-        const UnitInfo w = decode_unit(g, u);
+      UnitInfo w;
+      for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
         const int buf = it % Cfg::ACC_BUFS;
         const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
@@ -244,11 +264,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     cx.lane = lane;
     typename Epi::State st;
     Epi::init(ep, st, g, cx);
-    int it = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+    UnitInfo w;
+    for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
       const int buf = it % Cfg::ACC_BUFS;
       if (!Epi::SPLIT && (Cfg::ACC_BUFS == 2 ? buf : 0) != cx.group) continue;  // group e owns buffer e
-      const UnitInfo w = decode_unit(g, u);
       const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
