@@ -217,6 +217,9 @@ int pigan_topk_smallest(const float* scores, const int64_t* in_indices, int64_t 
  *            b_wrap_rows; b_tail [Kd - tail_from_row, 64] optionally replaces B's last 64 columns for
  *            reduction rows >= tail_from_row; column bias_col of the product accumulates into db[M]
  * ---------------------------------------------------------------------------------------------- */
+/* device buffer [64][5] int64 receiving clock64 stamps of the LayerNorm epilogue (CTA 0): unit start, after pass 1,
+ * after the partial exchange, after pass 2; NULL switches the trace off (tools/ln_trace.py) */
+int pigan_debug_set_ln_trace(void* device_buffer);
 int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32_t m, int32_t n, int32_t k,
                         int32_t variant, void* stream);
 int pigan_debug_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out_f16,

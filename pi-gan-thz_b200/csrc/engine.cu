@@ -235,33 +235,28 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 }
 
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
+long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
+template <int CLUSTER>
+int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
+                const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
+  using Epi = EpiLnStore<CfgL1, CLUSTER>;
+  typename Epi::Params ep;
+  PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+  ep.bias = bias;
+  ep.gamma = gamma;
+  ep.beta = beta;
+  ep.n_total = n;
+  ep.trace = g_ln_trace ? g_ln_trace + (n == 1024 ? 1 : n == 256 ? 3 : (k == 256 ? 0 : 2)) * 320 : nullptr;
+  return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
+}
 int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, const float* gamma,
               const float* beta, __half* out, cudaStream_t st) {
   CUtensorMap ta, tb;
   PIGAN_TRY(make_tn_maps<CfgL1>(&ta, &tb, a, (int)rows, k, k, w, n, k));
-  GemmShape g = make_shape<CfgL1>((int)rows, n, k);
-  if (n == 256) {
-    using Epi = EpiLnStore<CfgL1, 1, false>;
-    typename Epi::Params ep;
-    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
-  }
-  g.pair_mode = 1;
-  if (n == 512) {
-    using Epi = EpiLnStore<CfgL1, 1, true>;
-    typename Epi::Params ep;
-    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
-  }
-  if (n == 1024) {
-    using Epi = EpiLnStore<CfgL1, 2, true>;
-    typename Epi::Params ep;
-    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
-    return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
-  }
+  const GemmShape g = make_shape<CfgL1>((int)rows, n, k);
+  if (n == 256) return linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  if (n == 512) return linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  if (n == 1024) return linear_ln_c<4>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
   return fail(PIGAN_ERR_UNSUPPORTED, "LayerNorm width %d", n);
 }
 
@@ -967,5 +962,10 @@ extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, cons
   PIGAN_CUDA_OK(cudaMemcpyAsync(out_indices, w.best_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   PIGAN_CUDA_OK(cudaMemcpyAsync(out_params, w.params, (size_t)k * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_debug_set_ln_trace(void* device_buffer) {
+  pigan::g_ln_trace = static_cast<long long*>(device_buffer);
   return PIGAN_OK;
 }

@@ -183,33 +183,33 @@ struct EpiStore {
 
 // =====================================================================================================
 // Linear + LayerNorm + LeakyReLU in one epilogue (forward_model.py:35-53): out = fp16(lrelu(LN(acc + bias))).
-// A thread owns one row (its TMEM lane); the whole row's accumulators stay resident in tensor memory while the
-// epilogue walks them twice — pass 1: sum / sum of squares, pass 2: normalise, activate, store — so the
-// pre-normalisation values never leave the SM.  The two epilogue groups split the CTA's columns; for the
-// 1024-wide layer two CTAs of a cluster split the row (512 accumulator columns = all of TMEM each) and the four
-// row partials meet through distributed shared memory + one cluster-scope mbarrier per unit.
+// A thread owns one row (its TMEM lane) and walks the tile's 256 accumulator columns twice while they stay in
+// tensor memory — pass 1: sum / sum of squares, pass 2: normalise, activate, store — so the pre-normalisation
+// values never leave the SM.  A row wider than 256 is split over a cluster of N/256 CTAs (2 for 512, 4 for 1024):
+// CTA rank r owns columns [256 r, 256 r + 256) of the same 128 rows, the row partials meet through distributed
+// shared memory and one cluster-scope mbarrier per unit.  With 256 columns per CTA tensor memory holds two
+// accumulator buffers, so the MMAs of the next row tile overlap both passes — which matters because draining
+// TMEM is slow: measured 64 B/clk per SM (tools/micro/ldtm_bench.cu), i.e. 2048 cycles per pass over a 128 x 256
+// fp32 tile against 4096 MMA cycles at K = 512.
 // =====================================================================================================
-//   PAIR = false (N = 256): the two groups split the single 256-column accumulator of every unit.
-//   PAIR = true  (N = 512, 1024): a CTA handles the two 256-column n-groups of an m-tile back to back (GemmShape
-//   pair_mode), one per accumulator buffer and epilogue group, so group 0's first pass overlaps the MMAs of the
-//   second n-group and the second passes overlap the MMAs of the next m-tile.
-template <class Cfg, int CLUSTER_, bool PAIR>
+template <class Cfg, int CLUSTER_>
 struct EpiLnStore {
-  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1, "EpiLnStore tile shape");
-  static constexpr bool SPLIT = !PAIR;
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiLnStore tile shape");
+  static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = CLUSTER_;
-  static constexpr int NCTA = PAIR ? 512 : 256;  // columns of the row one CTA handles
-  static constexpr int NG = NCTA / 2;            // columns one epilogue group handles
-  static_assert(NG % 64 == 0, "group columns must be whole TMA-store sub-tiles");
+  static constexpr int NG = 256;  // columns of the row this CTA (and the group that owns the unit) handles
   struct Params {
     CUtensorMap out;
     const float* bias;   // [N]
     const float* gamma;  // [N]
     const float* beta;   // [N]
-    int n_total;         // LayerNorm width N = NCTA * CLUSTER
+    int n_total;         // LayerNorm width N = 256 * CLUSTER
+    long long* trace;    // optional [units][5] clock64 stamps of CTA 0 / thread 0 of a group (tools/ln_trace.py)
   };
-  // per group: [0,32K) store staging | [32K,+3K) bias,gamma,beta of its columns | [35K,+4K) row-partial slots
-  // (buffer = group index: two buffers alternate between units) ; 40 KB in all
+  // per group: [0,32K) store staging | [32K,+3K) bias,gamma,beta of this CTA's columns | [35K,+4K) row-partial
+  // slots [CLUSTER][128] float2 written by the cluster's CTAs.  The slots are single-buffered: a peer can only
+  // write the partials of this group's NEXT unit after a whole pass 2 + pass 1 (thousands of cycles), while they
+  // are read in the three instructions that follow the barrier.
   static constexpr int kConstOff = kEpiStagingBytes;
   static constexpr int kSlotOff = kConstOff + 3 * 256 * 4;
   static constexpr int SMEM_BYTES = 40960;
@@ -224,7 +224,7 @@ struct EpiLnStore {
     st.xphase = 0;
     st.it = 0;
     st.rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-    const int col0 = (int)st.rank * NCTA + cx.group * NG;
+    const int col0 = (int)st.rank * NG;
     for (int i = cx.tid; i < NG; i += 128) {
       const int c = col0 + i;
       const bool ok = c < p.n_total;
@@ -246,55 +246,61 @@ struct EpiLnStore {
   __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
                               const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const uint32_t tcol0 = PAIR ? tacc : tacc + (uint32_t)(cx.group * NG);
     const uint32_t cb = cx.smem + kConstOff;
-    // ---- pass 1: row partials over this group's columns
-    float s1 = 0.f, s2 = 0.f;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && cx.tid == 0 && st.it < 32;
+    long long* trow = tr ? p.trace + (st.it * 2 + cx.group) * 5 : nullptr;
+    if (tr) trow[0] = clock64();
+    // ---- pass 1: row partials over this CTA's columns
+    float s1, s2;
+    {
+      float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c = 0; c < NG; c += 32) {
-      float v[32], b[32];
-      tmem_ld32(tcol0 + c, v);
-      lds32(cb + (uint32_t)c * 4u, b);
-      tmem_ld_wait();
+      for (int c = 0; c < NG; c += 32) {
+        float v[32], b[32];
+        tmem_ld32(tacc + c, v);
+        lds32(cb + (uint32_t)c * 4u, b);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = v[i] + b[i];
-        s1 += x;
-        s2 = fmaf(x, x, s2);
+        for (int i = 0; i < 32; ++i) {
+          const float x = v[i] + b[i];
+          a1[i & 3] += x;
+          a2[i & 3] = fmaf(x, x, a2[i & 3]);
+        }
       }
+      s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+      s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
     }
-    // ---- exchange: 2 * CLUSTER partials per row
-    const uint32_t slots = cx.smem0 + (st.it & 1u) * (uint32_t)SMEM_BYTES + kSlotOff;
-    const uint32_t mine = slots + ((st.rank * 2u + (uint32_t)cx.group) * 128u + (uint32_t)r) * 8u;
-    if constexpr (CLUSTER == 1) {
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mine), "f"(s1), "f"(s2) : "memory");
-      mbar_arrive(cx.xbar);
-      mbar_wait(cx.xbar, st.xphase);
-    } else {
+    if (tr) trow[1] = clock64();
+    // ---- exchange the row partials inside the cluster
+    if constexpr (CLUSTER > 1) {
+      const uint32_t slots = cx.smem + kSlotOff;
+      const uint32_t mine = slots + (st.rank * 128u + (uint32_t)r) * 8u;
 #pragma unroll
       for (uint32_t c = 0; c < (uint32_t)CLUSTER; ++c) {
         st_cluster_f32x2(mapa_shared(mine, c), s1, s2);
         mbar_arrive_cluster(mapa_shared(cx.xbar, c));
       }
       mbar_wait_cluster(cx.xbar, st.xphase);
-    }
-    st.xphase ^= 1u;
-    ++st.it;
-    float t1 = 0.f, t2 = 0.f;
+      st.xphase ^= 1u;
+      s1 = 0.f;
+      s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 2 * CLUSTER; ++k) {
-      float a, b;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
-                   : "=f"(a), "=f"(b) : "r"(slots + (uint32_t)(k * 128 + r) * 8u) : "memory");
-      t1 += a;
-      t2 += b;
+      for (int k = 0; k < CLUSTER; ++k) {
+        float a, b;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(a), "=f"(b) : "r"(slots + (uint32_t)(k * 128 + r) * 8u) : "memory");
+        s1 += a;
+        s2 += b;
+      }
     }
+    ++st.it;
+    if (tr) trow[2] = clock64();
     const float inv_n = 1.0f / (float)p.n_total;
-    const float mean = t1 * inv_n;
-    const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     // ---- pass 2: normalise, LeakyReLU, fp16, TMA store
-    const int col0 = (int)st.rank * NCTA + cx.group * NG;
+    const int col0 = (int)st.rank * NG;
 #pragma unroll 1
     for (int sub = 0; sub < NG / 64; ++sub) {
       const uint32_t buf = st.stg.acquire(cx);
@@ -302,7 +308,7 @@ struct EpiLnStore {
       for (int h = 0; h < 2; ++h) {
         const int c = sub * 64 + h * 32;
         float v[32], b[32], gm[32], bt[32];
-        tmem_ld32(tcol0 + c, v);
+        tmem_ld32(tacc + c, v);
         lds32(cb + (uint32_t)c * 4u, b);
         lds32(cb + (uint32_t)(256 + c) * 4u, gm);
         lds32(cb + (uint32_t)(512 + c) * 4u, bt);
@@ -313,6 +319,7 @@ struct EpiLnStore {
       }
       st.stg.commit(cx, buf, &p.out, col0 + sub * 64, w.m_tile * kBlockM);
     }
+    if (tr) trow[3] = clock64();
   }
   __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
 };
@@ -358,7 +365,7 @@ struct EpiDiscL2 {
     const int r = cx.q * 32 + cx.lane;
     const int row = w.m_tile * kBlockM + r;
     const bool valid = row < g.M && !(row >= p.row_gap_begin && row < p.row_gap_end);
-    float logit = 0.f;
+    float lg[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (a single one is latency-bound)
 #pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       uint32_t buf = 0;
@@ -374,12 +381,13 @@ struct EpiDiscL2 {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           v[i] = lrelu(v[i] + b[i]);
-          logit = fmaf(v[i], w3[i], logit);
+          lg[i & 3] = fmaf(v[i], w3[i], lg[i & 3]);
         }
         if (p.store_z2) Stager::put32(buf, r, h, v);
       }
       if (p.store_z2) st.stg.commit(cx, buf, &p.z2, sub * 64, w.m_tile * kBlockM);
     }
+    float logit = (lg[0] + lg[1]) + (lg[2] + lg[3]);
     if (valid) {
       logit += __ldg(p.b3);
       const float prob = 1.f / (1.f + expf(-logit));
@@ -581,6 +589,7 @@ struct EpiFwdOut {
     const uint32_t tb = cx.smem + (uint32_t)(cx.tid >> 5) * (32u * 17u * 4u);  // this warp's transposition buffer
     float prev1 = 0.f, prev2 = 0.f;  // recon[j-1], recon[j-2]
     float rec = 0.f, met = 0.f, mx = 0.f, f1 = 0.f, f2 = 0.f;
+    float rec4[4] = {0.f, 0.f, 0.f, 0.f}, mx4[4] = {0.f, 0.f, 0.f, 0.f};  // independent accumulation chains
     const float* ms = p.target_metrics ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
     if (cx.group == 1) {
       // the second differences at columns 144 and 145 reach back into group 0's last two columns
@@ -647,10 +656,10 @@ struct EpiFwdOut {
           v[i] = o;
           if (has_t) {
             const float d = o - t[i];
-            rec = fmaf(d, d, rec);
+            rec4[i & 3] = fmaf(d, d, rec4[i & 3]);
           }
           const float d2 = (o - prev1) - (prev1 - prev2);  // loss.py:51-53 difference of differences
-          mx = fmaf(d2, d2, mx);
+          mx4[i & 3] = fmaf(d2, d2, mx4[i & 3]);
           prev2 = prev1;
           prev1 = o;
         }
@@ -699,6 +708,8 @@ struct EpiFwdOut {
         __syncwarp();
       }
     }
+    rec += (rec4[0] + rec4[1]) + (rec4[2] + rec4[3]);
+    mx += (mx4[0] + mx4[1]) + (mx4[2] + mx4[3]);
     // group 1 hands its part of the row's squared error to group 0 (two buffers alternate between units)
     const uint32_t part = cx.smem0 + kPartOff + (st.it & 1u) * 512u + (uint32_t)rt * 4u;
     ++st.it;

@@ -32,7 +32,6 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
     // clusters of CLUSTER CTAs share an m-tile (n_group = cluster rank): the grid must be a multiple of it
     if (g.k_splits != 1 || g.num_n_groups != (g.pair_mode ? 2 : 1) * Epi::CLUSTER)
       return fail(PIGAN_ERR_INVALID, "cluster epilogue needs num_n_groups == cluster size (x2 in pair mode)");
-    grid -= grid % Epi::CLUSTER;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -45,6 +44,17 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // clusters must be co-resident inside a GPC: on B200 only 33 clusters of 4 (132 of 148 SMs) fit at once
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(ctas - ctas % Epi::CLUSTER);
+      int n = 0;
+      PIGAN_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      max_clusters = n > 0 ? n : 1;
+    }
+    if (grid > max_clusters * Epi::CLUSTER) grid = max_clusters * Epi::CLUSTER;
+    grid -= grid % Epi::CLUSTER;
+    cfg.gridDim = dim3(grid);
     note_launch();
     PIGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx ? *tx : tb, g, ep));
   } else {

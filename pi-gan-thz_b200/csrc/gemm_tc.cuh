@@ -106,7 +106,7 @@ struct EpiCtx {
   int lane;
   int group;      // epilogue group 0/1
   uint32_t smem0; // scratch region of group 0 (data shared by both groups of a SPLIT epilogue lives there)
-  uint32_t xbar;  // mbarrier expecting 256 * CLUSTER arrivals per phase (SPLIT epilogues)
+  uint32_t xbar;  // this group's cluster-exchange mbarrier: 128 * CLUSTER arrivals per phase
 };
 __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
   asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
@@ -160,7 +160,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 128);
     }
-    mbar_init(xbar, 256 * Epi::CLUSTER);
+    mbar_init(xbar, 128 * Epi::CLUSTER);      // one per epilogue group: 128 threads of every CTA of the cluster
+    mbar_init(xbar + 8u, 128 * Epi::CLUSTER);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -258,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     cx.group = (warp - 2) >> 2;
     cx.smem = epi_smem + cx.group * Epi::SMEM_BYTES;
     cx.smem0 = epi_smem;
-    cx.xbar = xbar;
+    cx.xbar = xbar + 8u * (uint32_t)cx.group;
     cx.tid = threadIdx.x - 64 - 128 * cx.group;
     cx.q = warp & 3;  // TMEM lane quarter this warp may access
     cx.lane = lane;
