@@ -96,6 +96,8 @@ struct PiganEngine {
   size_t ws_bytes;
   bool f_loaded = false;
   const float* f_params = nullptr;
+  std::vector<float> f_host;      // host copy of the frozen forward-model parameters (LayerNorm constants travel
+                                  // to the kernels as by-value arguments)
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
 
   // fp16 activations
@@ -236,15 +238,16 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
+// bias / gamma / beta are HOST pointers here: they travel to the kernel by value (constant bank)
 template <int CLUSTER>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
                 const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
   using Epi = EpiLnStore<CfgL1, CLUSTER>;
-  typename Epi::Params ep;
+  static typename Epi::Params ep;   // 12.5 KB: keep it off the stack
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-  ep.bias = bias;
-  ep.gamma = gamma;
-  ep.beta = beta;
+  memcpy(ep.consts, bias, n * sizeof(float));
+  memcpy(ep.consts + 1024, gamma, n * sizeof(float));
+  memcpy(ep.consts + 2048, beta, n * sizeof(float));
   ep.n_total = n;
   ep.trace = g_ln_trace ? g_ln_trace + (n == 1024 ? 1 : n == 256 ? 3 : (k == 256 ? 0 : 2)) * 320 : nullptr;
   return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
@@ -457,7 +460,8 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
-    PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], fp + L.ln_w[i], fp + L.ln_b[i],
+    const float* hp = e->f_host.data();
+    PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], hp + L.b[i], hp + L.ln_w[i], hp + L.ln_b[i],
                         acts[i], st));
   }
   using Epi = EpiFwdOut<CfgO>;
@@ -720,6 +724,10 @@ extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, 
   }
   launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
   PIGAN_CUDA_OK(cudaGetLastError());
+  // one-time setup: the only synchronising call of the ABI
+  e->f_host.resize((size_t)L.total);
+  PIGAN_CUDA_OK(cudaMemcpyAsync(e->f_host.data(), fp, (size_t)L.total * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PIGAN_CUDA_OK(cudaStreamSynchronize(st));
   e->f_params = fp;
   e->f_loaded = true;
   return PIGAN_OK;

@@ -196,17 +196,20 @@ template <class Cfg, int CLUSTER_>
 struct EpiLnStore {
   static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiLnStore tile shape");
   static constexpr bool SPLIT = false;
+  static constexpr bool EARLY_RELEASE = true;  // unit() arrives on cx.tempty itself, right after its only TMEM pass
   static constexpr int CLUSTER = CLUSTER_;
   static constexpr int NG = 256;  // columns of the row this CTA (and the group that owns the unit) handles
   struct Params {
     CUtensorMap out;
-    const float* bias;   // [N]
-    const float* gamma;  // [N]
-    const float* beta;   // [N]
     int n_total;         // LayerNorm width N = 256 * CLUSTER
     long long* trace;    // optional [units][5] clock64 stamps of CTA 0 / thread 0 of a group (tools/ln_trace.py)
+    // bias | gamma | beta of the layer, 1024 entries each, passed BY VALUE: kernel parameters live in the constant
+    // bank, whose broadcast reads do not touch shared memory — the operand ring (TMA writes + UMMA reads, ~190 B/clk
+    // at full MMA rate against 128 B/clk of shared-memory bandwidth) leaves no room for per-column constant loads;
+    // with them in shared memory pass 2 took 6-7k cycles per tile even when it read no tensor memory at all.
+    float consts[3 * 1024];
   };
-  // per group: [0,32K) store staging | [32K,+3K) bias,gamma,beta of this CTA's columns | [35K,+4K) row-partial
+  // per group: [0,32K) store staging | [35K,+4K) row-partial
   // slots [CLUSTER][128] float2 written by the cluster's CTAs.  The slots are single-buffered: a peer can only
   // write the partials of this group's NEXT unit after a whole pass 2 + pass 1 (thousands of cycles), while they
   // are read in the three instructions that follow the barrier.
@@ -224,14 +227,6 @@ struct EpiLnStore {
     st.xphase = 0;
     st.it = 0;
     st.rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-    const int col0 = (int)st.rank * NG;
-    for (int i = cx.tid; i < NG; i += 128) {
-      const int c = col0 + i;
-      const bool ok = c < p.n_total;
-      sts_f32(cx.smem + kConstOff + (uint32_t)i * 4u, ok ? __ldg(p.bias + c) : 0.f);
-      sts_f32(cx.smem + kConstOff + (uint32_t)(256 + i) * 4u, ok ? __ldg(p.gamma + c) : 0.f);
-      sts_f32(cx.smem + kConstOff + (uint32_t)(512 + i) * 4u, ok ? __ldg(p.beta + c) : 0.f);
-    }
     epi_bar_sync(cx, 0);
   }
   __device__ static void lds32(uint32_t addr, float* out) {
@@ -243,33 +238,51 @@ struct EpiLnStore {
       out[4 * k + 0] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
     }
   }
+  // 16 consecutive per-column constants from the kernel-parameter (constant) bank
+  __device__ static void ldc16(const float* src, float* out) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(src + 4 * k);
+      out[4 * k + 0] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
+    }
+  }
   __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
                               const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const uint32_t cb = cx.smem + kConstOff;
+    const float* cbias = p.consts + st.rank * NG;
+    const float* cgamma = p.consts + 1024 + st.rank * NG;
+    const float* cbeta = p.consts + 2048 + st.rank * NG;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && cx.tid == 0 && st.it < 32;
     long long* trow = tr ? p.trace + (st.it * 2 + cx.group) * 5 : nullptr;
     if (tr) trow[0] = clock64();
-    // ---- pass 1: row partials over this CTA's columns
+    // ---- pass 1 (the only read of tensor memory): bias, row partials, and the row itself packed to fp16 in
+    // registers.  Everything is unrolled so the stash is addressed statically.
+    uint32_t stash[NG / 2];
     float s1, s2;
     {
       float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int c = 0; c < NG; c += 32) {
-        float v[32], b[32];
-        tmem_ld32(tacc + c, v);
-        lds32(cb + (uint32_t)c * 4u, b);
+#pragma unroll
+      for (int c = 0; c < NG; c += 16) {
+        float v[16], b[16];
+        tmem_ld16(tacc + c, v);
+        ldc16(cbias + c, b);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float x = v[i] + b[i];
+          v[i] = x;
           a1[i & 3] += x;
           a2[i & 3] = fmaf(x, x, a2[i & 3]);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) stash[c / 2 + i] = pack_half2(v[2 * i], v[2 * i + 1]);
       }
       s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
     }
+    // the accumulator is free: the MMAs of the unit after next may start
+    tc_fence_before();
+    mbar_arrive(cx.tempty);
     if (tr) trow[1] = clock64();
     // ---- exchange the row partials inside the cluster
     if constexpr (CLUSTER > 1) {
@@ -299,23 +312,33 @@ struct EpiLnStore {
     const float mean = s1 * inv_n;
     const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    // ---- pass 2: normalise, LeakyReLU, fp16, TMA store
+    // ---- pass 2, from the register stash: normalise, LeakyReLU, fp16, TMA store
     const int col0 = (int)st.rank * NG;
-#pragma unroll 1
+#pragma unroll
     for (int sub = 0; sub < NG / 64; ++sub) {
       const uint32_t buf = st.stg.acquire(cx);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = sub * 64 + h * 32;
-        float v[32], b[32], gm[32], bt[32];
-        tmem_ld32(tacc + c, v);
-        lds32(cb + (uint32_t)c * 4u, b);
-        lds32(cb + (uint32_t)(256 + c) * 4u, gm);
-        lds32(cb + (uint32_t)(512 + c) * 4u, bt);
-        tmem_ld_wait();
+      for (int q16 = 0; q16 < 4; ++q16) {
+        const int c = sub * 64 + q16 * 16;
+        float gm[16], bt[16], v[16];
+        ldc16(cgamma + c, gm);
+        ldc16(cbeta + c, bt);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lrelu(fmaf((v[i] + b[i] - mean) * rstd, gm[i], bt[i]));
-        Stager::put32(buf, r, h, v);
+        for (int i = 0; i < 8; ++i) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&stash[c / 2 + i]));
+          v[2 * i] = lrelu(fmaf((f.x - mean) * rstd, gm[2 * i], bt[2 * i]));
+          v[2 * i + 1] = lrelu(fmaf((f.y - mean) * rstd, gm[2 * i + 1], bt[2 * i + 1]));
+        }
+        // 16 values -> two 16-byte chunks of this row in the swizzled [128 x 64] fp16 staging tile
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int j = q16 * 2 + i;
+          const uint32_t addr = buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_half2(v[8 * i + 0], v[8 * i + 1])), "r"(pack_half2(v[8 * i + 2], v[8 * i + 3])),
+                       "r"(pack_half2(v[8 * i + 4], v[8 * i + 5])), "r"(pack_half2(v[8 * i + 6], v[8 * i + 7]))
+                       : "memory");
+        }
       }
       st.stg.commit(cx, buf, &p.out, col0 + sub * 64, w.m_tile * kBlockM);
     }

@@ -106,8 +106,14 @@ struct EpiCtx {
   int lane;
   int group;      // epilogue group 0/1
   uint32_t smem0; // scratch region of group 0 (data shared by both groups of a SPLIT epilogue lives there)
+  uint32_t tempty; // "accumulator drained" mbarrier of the unit being processed (EARLY_RELEASE epilogues arrive on it)
   uint32_t xbar;  // this group's cluster-exchange mbarrier: 128 * CLUSTER arrivals per phase
 };
+// Epilogues that define `static constexpr bool EARLY_RELEASE = true` release the accumulator buffer themselves.
+template <class E, class = void>
+struct epi_early_release { static constexpr bool value = false; };
+template <class E>
+struct epi_early_release<E, decltype((void)E::EARLY_RELEASE)> { static constexpr bool value = E::EARLY_RELEASE; };
 __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
   asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
 }
@@ -273,9 +279,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(cx.q * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS);
+      cx.tempty = tempty_bar(buf);
       Epi::unit(ep, st, g, w, tacc, cx);
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
+      if constexpr (!epi_early_release<Epi>::value) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(buf));
+      }
     }
     Epi::finish(ep, st, g, cx);
   }
