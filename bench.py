@@ -231,7 +231,7 @@ def run_native(args):
     roof = None
     if dom_cnt:
         ach = dom_flop_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiStore> (forward-surrogate hidden layers)",
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiLnStore> (forward-surrogate hidden layers: Linear+LayerNorm+LeakyReLU)",
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
                 "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
@@ -309,6 +309,37 @@ def run_native(args):
                   "tensor_frac": cand_s * FLOP_PER_CANDIDATE / 1e12 / (peaks["tflops"] * world),
                   "noise": "in-kernel Philox4x32-10 keyed by (seed, global candidate index)"}
 
+    # ---- physics metrics (BASELINE config 3): one warp per spectrum, HBM-bound
+    from pigan_b200 import native
+    n_phys = args.physics_spectra
+    phys_info = None
+    if n_phys > 0:
+        reps = max(1, n_phys // B)
+        spec_big = sets[0][0].repeat(reps, 1)[:n_phys].contiguous() if reps > 1 else sets[0][0][:n_phys]
+        n_phys = spec_big.shape[0]
+        freq = synthetic.frequencies(250, device=dev)
+        o_idx = torch.empty(n_phys, device=dev, dtype=torch.int32)
+        o_met = torch.empty(n_phys, 4, device=dev, dtype=torch.float32)
+
+        def phys():
+            native.check(native.lib.pigan_physics_metrics(spec_big.data_ptr(), n_phys, 250, freq.data_ptr(), None, 0.0,
+                                                          o_idx.data_ptr(), o_met.data_ptr(), native.current_stream()))
+        for _ in range(3):
+            phys()
+        barrier()
+        e0.record()
+        for _ in range(5):
+            phys()
+        e1.record()
+        barrier()
+        ms4 = e0.elapsed_time(e1) / 5
+        gbs = n_phys * 1016 / (ms4 * 1e-3) / 1e9
+        phys_info = {"metric": "physics-metric spectra/s", "value": n_phys / (ms4 * 1e-3), "unit": "spectra/s",
+                     "spectra": n_phys, "ms": ms4,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
+        del spec_big, o_idx, o_met
+
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -335,6 +366,7 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "scoring": score_info,
+            "physics": phys_info,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }
         print(json.dumps(out), flush=True)
@@ -350,6 +382,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--candidates", type=int, default=1 << 23, help="candidates per GPU for the scoring line")
+    ap.add_argument("--physics-spectra", type=int, default=1 << 22, help="spectra for the physics-kernel line (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

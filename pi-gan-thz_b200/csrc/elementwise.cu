@@ -358,6 +358,77 @@ __global__ void extract_wp_kernel(const float* __restrict__ w, int ld_src, int S
   wp[idx] = (i < rows && e < P) ? w[(size_t)i * ld_src + S + e] : 0.f;
 }
 
+// One launch per network and step for all operand copies of its weights (first layer packed with the effective
+// bias, second layer cast, its transpose for dX, the parameter columns for the G-step gradient): block ranges
+// [0,nA) first layer (8 rows per block), [nA,nA+nB) cast, then 32x32 transpose tiles, then the parameter columns.
+struct PackNetArgs {
+  // first layer
+  const float* w1; int ld1, S, P, wp_cols, bias_cols; const float* b1; const float* cvec; __half* w1h; int Kp;
+  float* b_eff; int H1;
+  // second layer [H2, H1]
+  const float* w2; int H2; __half* w2h; __half* w2th;  // w2th may be null
+  float* wp;                                           // [H1][4] or null
+  int nA, nB, nC;
+};
+__global__ void __launch_bounds__(256) pack_net_kernel(PackNetArgs a) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.x;
+  if (b < a.nA) {
+    const int lane = threadIdx.x & 31;
+    const int i = b * 8 + (threadIdx.x >> 5);
+    if (i >= a.H1) return;
+    const float* wr = a.w1 + (size_t)i * a.ld1;
+    float dot = 0.f;
+    for (int j = lane; j < a.S; j += 32) dot = fmaf(a.cvec[j], wr[j], dot);
+    if (a.wp_cols)
+      for (int e = lane; e < a.P; e += 32) dot = fmaf(kParamCenter, wr[a.S + e], dot);
+    dot = warp_sum_f(dot);
+    const float be = a.b1[i] + dot;
+    const __half hi = __float2half_rn(be);
+    const __half lo = __float2half_rn(be - __half2float(hi));
+    if (lane == 0 && a.b_eff) a.b_eff[i] = be;
+    for (int j = lane; j < a.Kp; j += 32) {
+      __half o = __float2half_rn(0.f);
+      if (j < a.S) o = __float2half_rn(wr[j]);
+      else if (j < a.S + a.P) o = a.wp_cols ? __float2half_rn(wr[j]) : o;
+      else if (j == a.S + a.P) o = a.bias_cols ? hi : o;
+      else if (j == a.S + a.P + 1) o = a.bias_cols ? lo : o;
+      a.w1h[(size_t)i * a.Kp + j] = o;
+    }
+    return;
+  }
+  b -= a.nA;
+  if (b < a.nB) {
+    const int total = a.H2 * a.H1;
+    for (int idx = (b * 256 + threadIdx.x) * 4; idx < total; idx += a.nB * 256 * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(a.w2 + idx);
+      __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(a.w2h + idx) = u;
+    }
+    return;
+  }
+  b -= a.nB;
+  if (b < a.nC) {
+    // w2 [H2 rows, H1 cols] -> w2th [H1, H2]
+    const int tiles_x = a.H1 / 32;
+    const int bx = (b % tiles_x) * 32, by = (b / tiles_x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) tile[k][tx] = a.w2[(size_t)(by + k) * a.H1 + bx + tx];
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) a.w2th[(size_t)(bx + k) * a.H2 + by + tx] = __float2half_rn(tile[tx][k]);
+    return;
+  }
+  b -= a.nC;
+  const int idx = b * 256 + threadIdx.x;
+  if (a.wp != nullptr && idx < a.H1 * 4) {
+    const int i = idx >> 2, e = idx & 3;
+    a.wp[idx] = e < a.P ? a.w1[(size_t)i * a.ld1 + a.S + e] : 0.f;
+  }
+}
+
 __global__ void copy_pad_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_pad) dst[idx] = idx < n ? src[idx] : 0.f;
@@ -1178,6 +1249,19 @@ void launch_search_commit(const float* sel_scores, const int64_t* tmp_idx, const
   note_launch(), search_commit_kernel<<<(k + 255) / 256, 256, 0, st>>>(sel_scores, reinterpret_cast<const long long*>(tmp_idx),
                                                                 tmp_params, k, scores,
                                                                 reinterpret_cast<long long*>(best_idx), params);
+}
+void launch_pack_net(const float* w1, int ld1, int S, int P, int wp_cols, int bias_cols, const float* b1,
+                     const float* cvec, __half* w1h, int Kp, float* b_eff, int H1, const float* w2, int H2,
+                     __half* w2h, __half* w2th, float* wp, cudaStream_t st) {
+  PackNetArgs a;
+  a.w1 = w1; a.ld1 = ld1; a.S = S; a.P = P; a.wp_cols = wp_cols; a.bias_cols = bias_cols; a.b1 = b1; a.cvec = cvec;
+  a.w1h = w1h; a.Kp = Kp; a.b_eff = b_eff; a.H1 = H1; a.w2 = w2; a.H2 = H2; a.w2h = w2h; a.w2th = w2th; a.wp = wp;
+  a.nA = (H1 + 7) / 8;
+  a.nB = (H2 * H1 / 4 + 255) / 256;
+  if (a.nB > 128) a.nB = 128;
+  a.nC = w2th ? (H1 / 32) * (H2 / 32) : 0;
+  const int nD = wp ? (H1 * 4 + 255) / 256 : 0;
+  note_launch(), pack_net_kernel<<<a.nA + a.nB + a.nC + nD, 256, 0, st>>>(a);
 }
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st) {

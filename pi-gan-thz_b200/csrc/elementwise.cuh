@@ -60,6 +60,10 @@ void launch_search_commit(const float* sel_scores, const int64_t* tmp_idx, const
 // its fp16 rounding is relative to the batch spread, not to the constant offset; b_eff is applied in fp32).
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st);
+// all operand copies of one network's weights in a single launch (H1, H2 multiples of 32; w2 is [H2, H1] dense)
+void launch_pack_net(const float* w1, int ld1, int S, int P, int wp_cols, int bias_cols, const float* b1,
+                     const float* cvec, __half* w1h, int Kp, float* b_eff, int H1, const float* w2, int H2,
+                     __half* w2h, __half* w2th, float* wp, cudaStream_t st);
 void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st);
 void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst,
                            cudaStream_t st);

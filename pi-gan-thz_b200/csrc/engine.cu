@@ -113,6 +113,8 @@ struct PiganEngine {
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
   float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
   float *mean1, *rstd1, *scale1, *bias1, *mean2, *rstd2, *scale2, *bias2;
+  float *zero_blk;                     // sums | bn_sums | bn_bwd_sums, cleared with one memset per step
+  size_t zero_bytes;
   float *f_bias_out;                   // [288] zero padded
   double* sums;
 
@@ -167,12 +169,15 @@ struct PiganEngine {
     g_beff = c.take<float>(H1);
     d_beff = c.take<float>(D1);
     d_wp = c.take<float>((size_t)D1 * 4);
-    bn_sums = c.take<float>(2 * H1 + 2 * H2);
-    bn_bwd_sums = c.take<float>(2 * H1 + 2 * H2);
+    // one zero-filled block per step: loss sums (16 doubles) | BatchNorm forward sums | backward sums
+    zero_blk = c.take<float>(32 + 2 * (2 * H1 + 2 * H2));
+    zero_bytes = (32 + 2 * (2 * H1 + 2 * H2)) * sizeof(float);
+    sums = reinterpret_cast<double*>(zero_blk);
+    bn_sums = zero_blk ? zero_blk + 32 : nullptr;
+    bn_bwd_sums = zero_blk ? zero_blk + 32 + 2 * H1 + 2 * H2 : nullptr;
     mean1 = c.take<float>(H1); rstd1 = c.take<float>(H1); scale1 = c.take<float>(H1); bias1 = c.take<float>(H1);
     mean2 = c.take<float>(H2); rstd2 = c.take<float>(H2); scale2 = c.take<float>(H2); bias2 = c.take<float>(H2);
     f_bias_out = c.take<float>(288);
-    sums = c.take<double>(kNumSums);
     return (c.off + 255) & ~size_t(255);
   }
 };
@@ -301,9 +306,8 @@ int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n
 int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStream_t st) {
   const GenLayout& L = e->gl;
   PM("pack_weights");
-  launch_pack_first_layer(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, kKp, e->g_beff, L.H1, st);
-  launch_cast_pad(gp + L.w2, L.H1, L.H1, e->g_w2h, L.H1, L.H2, st);
-  if (need_backward) launch_transpose_cast(gp + L.w2, L.H2, L.H1, L.H1, e->g_w2th, L.H2, st);
+  launch_pack_net(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, kKp, e->g_beff, L.H1, gp + L.w2, L.H2,
+                  e->g_w2h, need_backward ? e->g_w2th : nullptr, nullptr, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -311,12 +315,8 @@ int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStre
 int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cudaStream_t st) {
   const DiscLayout& L = e->dl;
   PM("pack_weights");
-  launch_pack_first_layer(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, kKp, e->d_beff, L.H1, st);
-  launch_cast_pad(dp + L.w2, L.H1, L.H1, e->d_w2h, L.H1, L.H2, st);
-  if (need_backward) {
-    launch_transpose_cast(dp + L.w2, L.H2, L.H1, L.H1, e->d_w2th, L.H2, st);
-    launch_extract_wp(dp + L.w1, L.IN, L.S, L.P, e->d_wp, L.H1, L.H1, st);
-  }
+  launch_pack_net(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, kKp, e->d_beff, L.H1, dp + L.w2, L.H2,
+                  e->d_w2h, need_backward ? e->d_w2th : nullptr, need_backward ? e->d_wp : nullptr, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -522,9 +522,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PM("memset");
       PIGAN_CUDA_OK(cudaMemsetAsync(a.g_grads, 0, G.total * sizeof(float), st));
       PIGAN_CUDA_OK(cudaMemsetAsync(a.d_grads, 0, D.total * sizeof(float), st));
-      PIGAN_CUDA_OK(cudaMemsetAsync(e->sums, 0, kNumSums * sizeof(double), st));
-      PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
-      PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_bwd_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+      PIGAN_CUDA_OK(cudaMemsetAsync(e->zero_blk, 0, e->zero_bytes, st));
       PIGAN_CUDA_OK(cudaMemsetAsync(e->dpden, 0, (size_t)B * 4 * sizeof(float), st));
       PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
       PIGAN_TRY(pack_generator(e, gp, true, st));
