@@ -34,6 +34,9 @@ import torch
 FLOP_PER_TRAIN_SAMPLE = 7_465_984
 FLOP_PER_CANDIDATE = 3_275_776
 METRIC = "PI-GAN train samples/s"
+# DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/, round 1): the four
+# Linear+LayerNorm launches of the forward surrogate read+write 46.9 + 147.4 + 171.5 + 72.7 MB
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 109.6e6
 
 
 def read_peaks():
@@ -233,7 +236,8 @@ def run_native(args):
         ach = dom_flop_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiLnStore> (forward-surrogate hidden layers: Linear+LayerNorm+LeakyReLU)",
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_gemm_kernels_ncu_full.csv "
+                "(ncu --set full, dram__bytes_read+write, mean of the 4 EpiLnStore launches)", "peak_source": peaks["source"] + " bf16 sustained",
                 "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
     step_tflops = FLOP_PER_TRAIN_SAMPLE * B * K / (ms * 1e-3) / 1e12
 

@@ -1,0 +1,26 @@
+"""Two warm-up steps + ONE train step + one 65 536-candidate scoring call + the physics kernel (ncu target)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "pi-gan-thz_b200"))
+import torch
+from core.models.generator import Generator
+from core.models.discriminator import Discriminator
+from core.models.forward_model import ForwardModel
+from pigan_b200 import synthetic, flat, native
+from pigan_b200.trainer import NativeTrainer
+B = 65536
+dev = torch.device("cuda")
+torch.manual_seed(42)
+G = Generator(250, 4); D = Discriminator(250, 4); F = ForwardModel(4, 250, 8); F.eval()
+tr = NativeTrainer(G, D, F, dev, max_batch=B)
+sp, pr, pn, mn = synthetic.make_batch(B, 250, seed=1, device=dev)
+for _ in range(3): tr.step(sp, pr, mn, 2e-4, 2e-4)
+torch.cuda.synchronize()
+G.eval()
+st = flat.net_state(G, "generator")
+s, i, p = tr.engine.search(st.params.tensor(), st.bn.tensor(), sp[0], 0.01, 7, 0, B, 256)
+freq = synthetic.frequencies(250, device=dev)
+idx = torch.empty(B, device=dev, dtype=torch.int32); out = torch.empty(B, 4, device=dev)
+native.check(native.lib.pigan_physics_metrics(sp.data_ptr(), B, 250, freq.data_ptr(), None, 0.0, idx.data_ptr(), out.data_ptr(), native.current_stream()))
+torch.cuda.synchronize()
+print("ok", float(s[0]))
