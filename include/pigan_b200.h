@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 1
+#define PIGAN_ABI_VERSION 2
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -100,6 +100,12 @@ int pigan_engine_load_forward_model(PiganEngine* engine, const float* f_params, 
  * set; NULL restores the default. */
 int pigan_engine_set_spectrum_center(PiganEngine* engine, const float* center);
 
+/* Builds the fp16 operand of the first layers from fp32 data (device pointers): out[r, 0:S] = spectrum[r] - center,
+ * out[r, S:S+P] = params_denorm[r] - 2.5 (0 when params_denorm is NULL), out[r, S+P : S+P+2] = 1, rest 0; 256
+ * columns per row.  Rows are independent: call it once for a whole dataset and slice batches out of the result. */
+int pigan_prepare_spectrum_operand(const float* spectrum, const float* params_denorm, const float* center, int64_t n,
+                                   int32_t spectrum_dim, int32_t param_dim, void* out_operand, void* stream);
+
 /* Generator.forward (core/models/generator.py:28-33).  training != 0: BatchNorm uses batch statistics
  * and updates bn_buffers / num_batches_tracked (one update); training == 0: running statistics.
  *   spectrum [n,S] fp32  ->  out_params_norm [n,P] fp32 in (-1,1) */
@@ -154,6 +160,11 @@ typedef struct PiganTrainArgs {
   int32_t f1_idx, f2_idx; /* dataset.metric_name_to_idx['f1'/'f2'] */
   /* outputs */
   float* losses; /* [9] device: d, g, adv, recon_spec, recon_metrics, maxwell, lc, param_range, bnn_kl */
+  /* optional, instead of spectrum + params_denorm: the fp16 first-layer operand [B,256] built once per dataset by
+   * pigan_prepare_spectrum_operand (the analogue of MetamaterialDataset's one-time normalisation,
+   * data_loader.py:185-219) and the row [S] it was centred on.  Halves the bytes a step needs from the host. */
+  const void* spectrum_operand;
+  const float* spectrum_center;
 } PiganTrainArgs;
 
 int pigan_train_step(PiganEngine* engine, const PiganTrainArgs* args, void* stream);

@@ -101,6 +101,7 @@ struct PiganEngine {
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
 
   // fp16 activations
+  __half *xc_own;   // workspace copy of the spectrum operand; `xc` below points at it or at a caller-prepared operand
   __half *xc, *tail_f, *g_h1, *g_a1, *g_h2, *d_z1, *d_z2, *d_dh2, *d_dh1, *f_a1, *f_a2, *f_a3, *f_a4, *f_a5,
       *g_dy2, *g_da1;
   // fp16 weights
@@ -124,7 +125,8 @@ struct PiganEngine {
     Carver c(ws);
     const int64_t B = bp;
     const int H1 = gl.H1, H2 = gl.H2, D1 = dl.H1, D2 = dl.H2;
-    xc = c.take<__half>(B * kKp);
+    xc_own = c.take<__half>(B * kKp);
+    xc = xc_own;
     tail_f = c.take<__half>(B * 64);
     g_h1 = c.take<__half>(B * H1);
     g_a1 = c.take<__half>(B * H1);
@@ -296,6 +298,7 @@ int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t
 // spectrum prep: centring vector, fp16 operand with [params | 1 1] in the spare columns
 int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n, cudaStream_t st) {
   PM("prep_cast");
+  e->xc = e->xc_own;
   if (e->center != nullptr) launch_copy_pad_f32(e->center, e->gl.S, e->cvec, kKp, st);
   else launch_center_vec(x, n, e->gl.S, (int)(n < 512 ? n : 512), e->cvec, kKp, st);
   launch_cast_center(x, e->cvec, params, e->xc, n, e->gl.S, e->gl.P, kKp, st);
@@ -524,7 +527,15 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_CUDA_OK(cudaMemsetAsync(a.d_grads, 0, D.total * sizeof(float), st));
       PIGAN_CUDA_OK(cudaMemsetAsync(e->zero_blk, 0, e->zero_bytes, st));
       PIGAN_CUDA_OK(cudaMemsetAsync(e->dpden, 0, (size_t)B * 4 * sizeof(float), st));
-      PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
+      if (a.spectrum_operand != nullptr) {
+        // the caller prepared the fp16 operand (pigan_prepare_spectrum_operand, e.g. once per dataset) and names the
+        // row it centred on: nothing to cast, half the bytes to move
+        PM("prep_cast");
+        e->xc = const_cast<__half*>(static_cast<const __half*>(a.spectrum_operand));
+        launch_copy_pad_f32(a.spectrum_center, G.S, e->cvec, kKp, st);
+      } else {
+        PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
+      }
       PIGAN_TRY(pack_generator(e, gp, true, st));
       PIGAN_TRY(g_layer1(e, B, st));
       g_bn_stats(e, 1, B, st);
@@ -651,7 +662,10 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
 int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
   PIGAN_CHECK_ARG(e != nullptr && a != nullptr);
   PIGAN_CHECK_ARG(a->batch >= 2 && a->batch <= e->max_batch && a->global_batch >= a->batch);
-  PIGAN_CHECK_ARG(a->spectrum && a->params_denorm && a->metrics_norm);
+  PIGAN_CHECK_ARG(a->metrics_norm != nullptr);
+  PIGAN_CHECK_ARG(a->spectrum_operand ? (a->spectrum_center != nullptr &&
+                                         (reinterpret_cast<uintptr_t>(a->spectrum_operand) & 15u) == 0)
+                                      : (a->spectrum != nullptr && a->params_denorm != nullptr));
   PIGAN_CHECK_ARG(a->g_params && a->g_grads && a->g_exp_avg && a->g_exp_avg_sq);
   PIGAN_CHECK_ARG(a->d_params && a->d_grads && a->d_exp_avg && a->d_exp_avg_sq);
   PIGAN_CHECK_ARG(a->step >= 1);
@@ -728,6 +742,20 @@ extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, 
   PIGAN_CUDA_OK(cudaStreamSynchronize(st));
   e->f_params = fp;
   e->f_loaded = true;
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_prepare_spectrum_operand(const float* spectrum, const float* params_denorm, const float* center,
+                                              int64_t n, int32_t spectrum_dim, int32_t param_dim, void* out_operand,
+                                              void* stream) {
+  PIGAN_CHECK_ARG(spectrum && center && out_operand && n >= 1);
+  PIGAN_CHECK_ARG(spectrum_dim >= 1 && param_dim >= 0 && spectrum_dim + param_dim + 2 <= kKp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(center) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out_operand) & 15u) == 0);
+  // the kernel reads center[j] for j < S only, so the row needs no padding
+  launch_cast_center(spectrum, center, params_denorm, static_cast<__half*>(out_operand), n, spectrum_dim, param_dim, kKp,
+                     st);
+  PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
 
@@ -871,6 +899,7 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
     // centre on the design target: the candidates differ from it by sigma * noise only
     PM("prep_cast");
     launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);
+    e->xc = e->xc_own;
     launch_cast_center_noise(target, noise, sigma, e->cvec, e->xc, nullptr, n, G.S, G.P, kKp, st);
   }
   PIGAN_TRY(g_eval_setup(e, gp, bn, st));
@@ -940,6 +969,7 @@ extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, cons
   SearchWs w;
   const size_t need = w.carve(workspace, cap, k);
   if (workspace_bytes < need) return fail(PIGAN_ERR_WORKSPACE, "search workspace too small: %zu < %zu", workspace_bytes, need);
+  e->xc = e->xc_own;
   launch_search_init(w.scores, w.iota, w.best_idx, w.params, k + cap, k, st);
   // weights and the target do not change during a search: pack / fold once
   launch_copy_pad_f32(target, G.S, e->cvec, kKp, st);   // centre on the design target

@@ -62,6 +62,7 @@ class PiganTrainArgs(C.Structure):
         ("lambda_maxwell", _f32), ("lambda_lc", _f32), ("lambda_param_range", _f32), ("lambda_bnn_kl", _f32),
         ("f1_idx", _i32), ("f2_idx", _i32),
         ("losses", _vp),
+        ("spectrum_operand", _vp), ("spectrum_center", _vp),
     ]
 
 
@@ -82,6 +83,7 @@ SIGNATURES = {
     "pigan_engine_destroy": (_i32, [_vp]),
     "pigan_engine_load_forward_model": (_i32, [_vp, _vp, _vp]),
     "pigan_engine_set_spectrum_center": (_i32, [_vp, _vp]),
+    "pigan_prepare_spectrum_operand": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "pigan_generator_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pigan_discriminator_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "pigan_forward_model_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),

@@ -80,11 +80,13 @@ class NativeTrainer:
             p.grad = gview
 
     # ------------------------------------------------------------------
-    def _args(self, spectrum, params_denorm, metrics_norm, lr_g, lr_d):
+    def _args(self, spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand=None, center=None):
         gp, dp = self.gs.params.tensor(), self.ds.params.tensor()
-        B = spectrum.shape[0]
+        B = metrics_norm.shape[0]
         return self.engine.make_train_args(
-            spectrum=spectrum.data_ptr(), params_denorm=params_denorm.data_ptr(), metrics_norm=metrics_norm.data_ptr(),
+            spectrum=native.ptr(spectrum), params_denorm=native.ptr(params_denorm),
+            metrics_norm=metrics_norm.data_ptr(), spectrum_operand=native.ptr(operand),
+            spectrum_center=native.ptr(center),
             batch=B, global_batch=B * self.world,
             g_params=gp.data_ptr(), g_grads=self.g_grads.data_ptr(), g_exp_avg=self.g_m.data_ptr(),
             g_exp_avg_sq=self.g_v.data_ptr(), g_bn_buffers=self.gs.bn.tensor().data_ptr(),
@@ -94,18 +96,45 @@ class NativeTrainer:
             lr_g=float(lr_g), lr_d=float(lr_d), step=self.step_count,
             f1_idx=self.f1_idx, f2_idx=self.f2_idx, losses=self.losses.data_ptr(), **self.lam)
 
+    @staticmethod
+    def prepare_operand(spectrum: torch.Tensor, params_denorm: torch.Tensor, center: torch.Tensor) -> torch.Tensor:
+        """fp16 first-layer operand [N,256] of a whole dataset (device tensors in, device tensor out): spectrum -
+        center | params - 2.5 | 1 1 | 0.  Done once, like the reference's dataset normalisation
+        (data_loader.py:185-219); batches are row slices of the result and cost half the bytes of the fp32 spectra."""
+        for x in (spectrum, params_denorm, center):
+            if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+                raise RuntimeError("prepare_operand needs contiguous fp32 CUDA tensors")
+        out = torch.empty(spectrum.shape[0], 256, device=spectrum.device, dtype=torch.float16)
+        native.check(native.lib.pigan_prepare_spectrum_operand(
+            spectrum.data_ptr(), params_denorm.data_ptr(), center.data_ptr(), spectrum.shape[0], spectrum.shape[1],
+            params_denorm.shape[1], out.data_ptr(), native.current_stream()))
+        return out
+
+    def step_prepared(self, operand: torch.Tensor, center: torch.Tensor, metrics_norm: torch.Tensor, lr_g: float,
+                      lr_d: float) -> torch.Tensor:
+        """step() on a batch whose operand rows were prepared by prepare_operand (same ``center`` for every batch
+        and, under data parallelism, every rank)."""
+        if (not operand.is_cuda or operand.dtype != torch.float16 or not operand.is_contiguous()
+                or operand.shape[1] != 256):
+            raise RuntimeError("step_prepared: operand must be a contiguous fp16 CUDA tensor [B,256]")
+        return self._run(None, None, metrics_norm, lr_g, lr_d, operand=operand, center=center)
+
     def step(self, spectrum, params_denorm, metrics_norm, lr_g: float, lr_d: float) -> torch.Tensor:
         """One D-step + G-step on device-resident fp32 tensors.  Returns the [9] device tensor of losses
         (loss_history order); no host synchronisation happens here."""
-        for t, name in ((spectrum, "spectrum"), (params_denorm, "params_denorm"), (metrics_norm, "metrics_norm")):
-            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+        return self._run(spectrum, params_denorm, metrics_norm, lr_g, lr_d)
+
+    def _run(self, spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand=None, center=None) -> torch.Tensor:
+        for t, name in ((spectrum, "spectrum"), (params_denorm, "params_denorm"), (metrics_norm, "metrics_norm"),
+                        (center, "center")):
+            if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
                 raise RuntimeError(f"NativeTrainer.step: {name} must be a contiguous fp32 CUDA tensor")
         self.step_count += 1
-        args = self._args(spectrum, params_denorm, metrics_norm, lr_g, lr_d)
+        args = self._args(spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand, center)
         if self.world == 1:
             self.engine.train_step(args)
             return self.losses
-        if self._center is None:
+        if operand is None and self._center is None:
             # one centring row on all ranks (the exchanged BatchNorm sums are sums of centred pre-activations)
             c = spectrum[:512].mean(dim=0)
             dist.all_reduce(c, group=self.pg)

@@ -464,3 +464,31 @@ def test_philox_search_matches_brute_force_and_is_shard_invariant():
     assert not torch.equal(i2, i)
     s3, i3, _ = eng.search(st.params.tensor(), st.bn.tensor(), target, 0.01, 1234, 0, 10, k)
     assert int(torch.isfinite(s3).sum()) == 10 and int((i3 >= 0).sum()) == 10
+
+
+def test_step_prepared_equals_step():
+    """The fp16 operand prepared once per dataset (pigan_prepare_spectrum_operand) must give the same step as the
+    fp32 inputs centred on the same row."""
+    from oracle import fixtures
+    from pigan_b200.trainer import NativeTrainer
+    n = 4096
+    g_sd, d_sd, f_sd = _weights()
+    spec, praw, pnorm, mnorm = fixtures.make_batch(n, seed=91)
+    spec_d, praw_d, mn_d = spec.to(DEV), praw.to(DEV), mnorm.to(DEV)
+    center = spec_d[:512].mean(dim=0).contiguous()
+    outs = []
+    for prepared in (False, True):
+        G, D, F = _models(g_sd, d_sd, f_sd)
+        tr = NativeTrainer(G, D, F, torch.device(DEV), max_batch=n)
+        if prepared:
+            op = NativeTrainer.prepare_operand(spec_d, praw_d, center)
+            assert op.shape == (n, 256) and op.dtype == torch.float16
+            assert torch.equal(op[:, 254:256], torch.ones(n, 2, device=DEV, dtype=torch.float16))
+            ls = tr.step_prepared(op, center, mn_d, 2e-4, 2e-4).cpu()
+        else:
+            tr.engine.set_spectrum_center(center)
+            ls = tr.step(spec_d, praw_d, mn_d, 2e-4, 2e-4).cpu()
+        outs.append((ls, tr.gs.params.tensor().clone(), tr.ds.params.tensor().clone(), tr.gs.bn.tensor().clone()))
+    assert rel(outs[1][0], outs[0][0]) < 1e-6
+    for k in (1, 2, 3):
+        assert torch.equal(outs[1][k], outs[0][k])
