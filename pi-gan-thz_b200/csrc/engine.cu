@@ -246,10 +246,10 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
 // bias / gamma / beta are HOST pointers here: they travel to the kernel by value (constant bank)
-template <int CLUSTER>
+template <int CLUSTER, bool PAIR = false>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
                 const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
-  using Epi = EpiLnStore<CfgL1, CLUSTER>;
+  using Epi = EpiLnStore<CfgL1, CLUSTER, PAIR>;
   static typename Epi::Params ep;   // 12.5 KB: keep it off the stack
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
   memcpy(ep.consts, bias, n * sizeof(float));
@@ -266,7 +266,11 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
   const GemmShape g = make_shape<CfgL1>((int)rows, n, k);
   if (n == 256) return linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
   if (n == 512) return linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
-  if (n == 1024) return linear_ln_c<4>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  if (n == 1024) {   // clusters of 2, each CTA walks two n-groups per row tile (clusters of 4 fit only 132 SMs)
+    GemmShape gp = g;
+    gp.pair_mode = 1;
+    return linear_ln_c<2, true>(ta, tb, gp, rows, k, n, bias, gamma, beta, out, st);
+  }
   return fail(PIGAN_ERR_UNSUPPORTED, "LayerNorm width %d", n);
 }
 

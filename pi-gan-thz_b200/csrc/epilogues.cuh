@@ -192,10 +192,16 @@ struct EpiStore {
 // TMEM is slow: measured 64 B/clk per SM (tools/micro/ldtm_bench.cu), i.e. 2048 cycles per pass over a 128 x 256
 // fp32 tile against 4096 MMA cycles at K = 512.
 // =====================================================================================================
-template <class Cfg, int CLUSTER_>
+//   PAIR = false: CTA rank r owns n-group r (N = 256 * CLUSTER); its two epilogue groups alternate row tiles.
+//   PAIR = true : a CTA walks both n-groups 2r, 2r+1 of a row tile back to back (GemmShape::pair_mode, N = 512 *
+//                 CLUSTER): group e owns n-group 2r+e / accumulator buffer e, all 2 * CLUSTER groups exchange their
+//                 partials every row tile.  Used for N = 1024, where clusters of 4 would only cover 132 of 148 SMs.
+template <class Cfg, int CLUSTER_, bool PAIR = false>
 struct EpiLnStore {
   static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiLnStore tile shape");
   static constexpr bool SPLIT = false;
+  static constexpr int XBAR_COUNT = (PAIR ? 256 : 128) * CLUSTER_;
+  static constexpr int PARTS = (PAIR ? 2 : 1) * CLUSTER_;   // row partials per row
   static constexpr bool EARLY_RELEASE = true;  // unit() arrives on cx.tempty itself, right after its only TMEM pass
   static constexpr int CLUSTER = CLUSTER_;
   static constexpr int NG = 256;  // columns of the row this CTA (and the group that owns the unit) handles
@@ -209,12 +215,10 @@ struct EpiLnStore {
     // with them in shared memory pass 2 took 6-7k cycles per tile even when it read no tensor memory at all.
     float consts[3 * 1024];
   };
-  // per group: [0,32K) store staging | [35K,+4K) row-partial
-  // slots [CLUSTER][128] float2 written by the cluster's CTAs.  The slots are single-buffered: a peer can only
-  // write the partials of this group's NEXT unit after a whole pass 2 + pass 1 (thousands of cycles), while they
-  // are read in the three instructions that follow the barrier.
-  static constexpr int kConstOff = kEpiStagingBytes;
-  static constexpr int kSlotOff = kConstOff + 3 * 256 * 4;
+  // per group: [0,32K) store staging | [32K,+8K) row-partial slots written by the groups / CTAs that share the row
+  static constexpr int kSlotOff = kEpiStagingBytes;   // two buffers of [PARTS][128] float2, alternating per unit
+  static constexpr int kSlotBytes = 4096;
+  static_assert(PARTS * 128 * 8 <= kSlotBytes, "slot buffer");
   static constexpr int SMEM_BYTES = 40960;
   struct State {
     Stager stg;
@@ -249,9 +253,10 @@ struct EpiLnStore {
   __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
                               const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const float* cbias = p.consts + st.rank * NG;
-    const float* cgamma = p.consts + 1024 + st.rank * NG;
-    const float* cbeta = p.consts + 2048 + st.rank * NG;
+    const uint32_t part = PAIR ? st.rank * 2u + (uint32_t)cx.group : st.rank;   // which n-group of the row
+    const float* cbias = p.consts + part * NG;
+    const float* cgamma = p.consts + 1024 + part * NG;
+    const float* cbeta = p.consts + 2048 + part * NG;
     const bool tr = p.trace != nullptr && blockIdx.x == 0 && cx.tid == 0 && st.it < 32;
     long long* trow = tr ? p.trace + (st.it * 2 + cx.group) * 5 : nullptr;
     if (tr) trow[0] = clock64();
@@ -285,20 +290,22 @@ struct EpiLnStore {
     mbar_arrive(cx.tempty);
     if (tr) trow[1] = clock64();
     // ---- exchange the row partials inside the cluster
-    if constexpr (CLUSTER > 1) {
-      const uint32_t slots = cx.smem + kSlotOff;
-      const uint32_t mine = slots + (st.rank * 128u + (uint32_t)r) * 8u;
+    if constexpr (PARTS > 1) {
+      // PAIR: both groups meet on group 0's barrier and slots; otherwise every group has its own
+      const uint32_t slots = (PAIR ? cx.smem0 : cx.smem) + kSlotOff + (st.it & 1u) * kSlotBytes;
+      const uint32_t xb = PAIR ? cx.xbar - 8u * (uint32_t)cx.group : cx.xbar;
+      const uint32_t mine = slots + (part * 128u + (uint32_t)r) * 8u;
 #pragma unroll
       for (uint32_t c = 0; c < (uint32_t)CLUSTER; ++c) {
         st_cluster_f32x2(mapa_shared(mine, c), s1, s2);
-        mbar_arrive_cluster(mapa_shared(cx.xbar, c));
+        mbar_arrive_cluster(mapa_shared(xb, c));
       }
-      mbar_wait_cluster(cx.xbar, st.xphase);
+      mbar_wait_cluster(xb, st.xphase);
       st.xphase ^= 1u;
       s1 = 0.f;
       s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < CLUSTER; ++k) {
+      for (int k = 0; k < PARTS; ++k) {
         float a, b;
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                      : "=f"(a), "=f"(b) : "r"(slots + (uint32_t)(k * 128 + r) * 8u) : "memory");
@@ -313,7 +320,7 @@ struct EpiLnStore {
     const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     // ---- pass 2, from the register stash: normalise, LeakyReLU, fp16, TMA store
-    const int col0 = (int)st.rank * NG;
+    const int col0 = (int)part * NG;
 #pragma unroll
     for (int sub = 0; sub < NG / 64; ++sub) {
       const uint32_t buf = st.stg.acquire(cx);

@@ -114,6 +114,11 @@ template <class E, class = void>
 struct epi_early_release { static constexpr bool value = false; };
 template <class E>
 struct epi_early_release<E, decltype((void)E::EARLY_RELEASE)> { static constexpr bool value = E::EARLY_RELEASE; };
+// arrivals per phase on the cluster-exchange barriers: Epi::XBAR_COUNT when defined, else 128 per CTA of the cluster
+template <class E, class = void>
+struct epi_xbar_count { static constexpr int value = 128 * E::CLUSTER; };
+template <class E>
+struct epi_xbar_count<E, decltype((void)E::XBAR_COUNT)> { static constexpr int value = E::XBAR_COUNT; };
 __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
   asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
 }
@@ -166,8 +171,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 128);
     }
-    mbar_init(xbar, 128 * Epi::CLUSTER);      // one per epilogue group: 128 threads of every CTA of the cluster
-    mbar_init(xbar + 8u, 128 * Epi::CLUSTER);
+    mbar_init(xbar, epi_xbar_count<Epi>::value);   // one per epilogue group (see EpiLnStore)
+    mbar_init(xbar + 8u, epi_xbar_count<Epi>::value);
     fence_barrier_init();
   }
   if (warp == 1) {
