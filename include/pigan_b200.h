@@ -174,6 +174,33 @@ float* pigan_engine_bn_sums(PiganEngine* engine);      /* [2*h1 + 2*h2]  sum, su
 float* pigan_engine_bn_bwd_sums(PiganEngine* engine);  /* [2*h2 + 2*h1]  sum dy, sum dy*xhat */
 double* pigan_engine_loss_sums(PiganEngine* engine);   /* [16] fp64 */
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel exchange over NVLink peer memory (csrc/dp.cu).  The reference is single-process; under data
+ * parallelism the step exchanges BatchNorm sums, loss numerators and gradients between the phases of
+ * pigan_train_step_phase.  Every rank allocates one exchange region (pigan_dp_alloc: a cudaMalloc of its own so
+ * that it can be exported), publishes its cudaIpc handle to the others (any host channel), opens theirs and
+ * creates a context from the table of mapped regions (own region at index `rank`).
+ *   pigan_dp_allreduce_small  in-place sum over ranks of a buffer of <= 16 KB (fp32 or fp64), one CTA, one launch
+ *   pigan_dp_allreduce_grads  dst = sum over ranks of gradient slot (net, epoch & 1); the gradients of a step are
+ *                             written straight into that slot (PiganTrainArgs.g_grads / d_grads point into it)
+ * `channel` identifies the exchange point inside a step (0..15, the same on every rank), `epoch` >= 1 grows by one
+ * per step.  Ranks sum in rank order, so all replicas get bit-identical results.  Waits are bounded (5 s -> trap).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PiganDp PiganDp;
+size_t pigan_dp_region_bytes(int64_t max_grad_floats);
+size_t pigan_dp_grad_slot_offset(int64_t max_grad_floats, int32_t net /*0 G, 1 D*/, int32_t parity);
+int pigan_dp_alloc(size_t bytes, void** out);
+int pigan_dp_free(void* region);
+int pigan_dp_ipc_export(void* region, void* handle64);
+int pigan_dp_ipc_open(const void* handle64, void** out_mapped);
+int pigan_dp_ipc_close(void* mapped);
+int pigan_dp_create(PiganDp** out, int32_t world, int32_t rank, void* const* region_of_rank, int64_t max_grad_floats);
+int pigan_dp_destroy(PiganDp* dp);
+int pigan_dp_allreduce_small(PiganDp* dp, void* buf, int32_t n, int32_t is_double, int32_t channel, uint32_t epoch,
+                             void* stream);
+int pigan_dp_allreduce_grads(PiganDp* dp, int32_t net, float* dst, int64_t n, int32_t channel, uint32_t epoch,
+                             double* sumsq, void* stream);
+
 /* Optional instrumentation (replaces the reference's time.time() ETA bookkeeping, train_pigan.py:113,218, as
  * the only timing hook): between _begin and _end every engine call records CUDA events on the caller's stream
  * at the boundaries of its kernel sections.  sections_csv = NULL or "" records all sections, else only the

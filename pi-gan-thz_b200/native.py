@@ -71,6 +71,17 @@ SIGNATURES = {
     "pigan_abi_version": (_i32, []),
     "pigan_last_error": (C.c_char_p, []),
     "pigan_launch_count": (_i64, []),
+    "pigan_dp_region_bytes": (C.c_size_t, [_i64]),
+    "pigan_dp_grad_slot_offset": (C.c_size_t, [_i64, _i32, _i32]),
+    "pigan_dp_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
+    "pigan_dp_free": (_i32, [_vp]),
+    "pigan_dp_ipc_export": (_i32, [_vp, _vp]),
+    "pigan_dp_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "pigan_dp_ipc_close": (_i32, [_vp]),
+    "pigan_dp_create": (_i32, [C.POINTER(_vp), _i32, _i32, C.POINTER(_vp), _i64]),
+    "pigan_dp_destroy": (_i32, [_vp]),
+    "pigan_dp_allreduce_small": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_uint32, _vp]),
+    "pigan_dp_allreduce_grads": (_i32, [_vp, _i32, _vp, _i64, _i32, C.c_uint32, _vp, _vp]),
     "pigan_engine_profile_begin": (_i32, [_vp, C.c_char_p]),
     "pigan_engine_profile_end": (_i32, [_vp, C.c_char_p, C.c_size_t]),
     "pigan_default_dims": (None, [C.POINTER(PiganDims)]),

@@ -12,6 +12,7 @@ from typing import Dict, Optional
 import torch
 import torch.distributed as dist
 
+from . import dp as _dp
 from . import engine as _engine
 from . import flat as _flat
 from . import native
@@ -73,6 +74,13 @@ class NativeTrainer:
                        lambda_bnn_kl=cfg.LAMBDA_BNN_KL)
         self.lam = lam
         self.f1_idx, self.f2_idx = int(f1_idx), int(f2_idx)
+        # data parallel: gradients are produced straight into an NVLink-mapped exchange region and summed by the
+        # library's one-shot kernels (dp.py); NCCL all-reduce is the fallback when peers cannot be mapped
+        self.xchg = _dp.DpExchange.create(max(gp.numel(), dp.numel()), self.device, process_group) \
+            if self.world > 1 else None
+        if self.xchg is not None:
+            self._slots = {(net, par): self.xchg.grad_slot(net, par, n)
+                           for net, n in ((0, gp.numel()), (1, dp.numel())) for par in (0, 1)}
         # expose gradients on the parameters the way autograd would (views of the flat buffers)
         for p, gview in zip(self.gs.params._tensors(), self.gs.params.views_like(self.g_grads)):
             p.grad = gview
@@ -143,10 +151,37 @@ class NativeTrainer:
         # data-parallel schedule: the engine's phases with NCCL all-reduces of the batch-coupled sums between
         # them (BatchNorm forward/backward statistics, gradients, loss sums) — include/pigan_b200.h
         e = self.engine
+        if self.xchg is not None:
+            self._step_peer(args)
+            return self.losses
         run_dp_step(lambda ph: e.train_step_phase(args, ph), self._buffer,
                     lambda t: dist.all_reduce(t, group=self.pg),
                     dp_phase_plan(e.dims.g_hidden[0], e.dims.g_hidden[1]))
         return self.losses
+
+    def _step_peer(self, args) -> None:
+        """The data-parallel schedule (dp_phase_plan) with peer-memory all-reduces: this step's gradients accumulate
+        in exchange slot (net, step parity); phases that consume reduced gradients get the local reduced buffer."""
+        e, x, ep = self.engine, self.xchg, self.step_count
+        par = ep & 1
+        args.g_grads = self._slots[(0, par)].data_ptr()
+        args.d_grads = self._slots[(1, par)].data_ptr()
+        channel = 0
+        for phase, reductions in dp_phase_plan(e.dims.g_hidden[0], e.dims.g_hidden[1]):
+            if phase == 3:
+                args.d_grads = self.d_grads.data_ptr()     # Adam(D) reads the reduced gradients
+            if phase == 6:
+                args.g_grads = self.g_grads.data_ptr()
+            e.train_step_phase(args, phase)
+            for name, sl in reductions:
+                if name == "d_grads":
+                    x.allreduce_grads(1, self.d_grads, channel, ep)
+                elif name == "g_grads":
+                    x.allreduce_grads(0, self.g_grads, channel, ep)
+                else:
+                    buf = self._buffer(name)
+                    x.allreduce_small(buf if sl is None else buf[sl], channel, ep)
+                channel += 1
 
     def _buffer(self, name: str) -> torch.Tensor:
         """Device buffers the data-parallel schedule reduces (dp_phase_plan)."""
