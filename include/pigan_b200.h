@@ -262,6 +262,9 @@ int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32_t m, int32
                         int32_t variant, void* stream);
 int pigan_debug_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out_f16,
                        float* rowstats, int32_t m, int32_t n, int32_t k, int32_t leaky, void* stream);
+/* same as pigan_debug_linear through the two-CTA (cta_group::2) kernel */
+int pigan_debug_linear2(const void* a, const void* a_tail, const void* b, const float* bias, void* out_f16,
+                        float* rowstats, int32_t m, int32_t n, int32_t k, int32_t leaky, void* stream);
 int pigan_debug_gemm_nt(const void* a, const void* b, const void* b_tail, float* c, int32_t kd, int32_t m,
                         int32_t n, int32_t k_splits, int32_t b_wrap_rows, int32_t tail_from_row,
                         int32_t n_valid, int32_t bias_col, float* db, void* stream);

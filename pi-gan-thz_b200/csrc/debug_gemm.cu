@@ -2,6 +2,7 @@
 // layers use) and with the production store / weight-gradient epilogues, so tests/ can compare them with a
 // plain fp32 matmul of the same fp16 operands.
 #include "epilogues.cuh"
+#include "gemm2_tc.cuh"
 
 namespace pigan {
 
@@ -76,6 +77,30 @@ static int run_linear(const void* a, const void* a_tail, const void* b, const fl
   return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
 }
 
+template <bool BIAS, bool LRELU, bool RS>
+static int run_linear2(const void* a, const void* a_tail, const void* b, const float* bias, void* out,
+                       float* rowstats, int m, int n, int k, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<5>;
+  using Epi = EpiStore<Cfg, BIAS, LRELU, RS>;
+  CUtensorMap ta, tb, tx;
+  PIGAN_TRY(make_tmap_f16_2d(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)k, kBlockK, kBlockM));
+  PIGAN_TRY(make_tmap_f16_2d(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k, kBlockK, Cfg::BLOCK_N / 2));
+  GemmShape g = make_shape<Cfg>(m, n, k);
+  if (a_tail) {
+    PIGAN_TRY(make_tmap_f16_2d(&tx, a_tail, 64, (uint64_t)m, 64, kBlockK, kBlockM));
+    g.a_tail = 1;
+  }
+  typename Epi::Params ep;
+  PIGAN_TRY(make_tmap_f16_2d(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n, 64, kBlockM));
+  ep.bias = bias;
+  ep.scale = nullptr;
+  ep.rowstats = rowstats;
+  ep.n_tiles = g.num_n_groups;
+  ep.mask = nullptr;
+  ep.mask_words = 0;
+  return launch_gemm2<Cfg, Epi>(ta, tb, g, ep, st, a_tail ? &tx : nullptr);
+}
+
 }  // namespace pigan
 
 using namespace pigan;
@@ -108,6 +133,20 @@ extern "C" int pigan_debug_linear(const void* a, const void* a_tail, const void*
   if (bias) return run_linear<true, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
   if (leaky) return run_linear<false, true, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
   return run_linear<false, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+}
+
+extern "C" int pigan_debug_linear2(const void* a, const void* a_tail, const void* b, const float* bias,
+                                  void* out_f16, float* rowstats, int32_t m, int32_t n, int32_t k,
+                                  int32_t leaky, void* stream) {
+  PIGAN_CHECK_ARG(a && b && out_f16 && m > 0 && n > 0 && k > 0 && k % 8 == 0 && n % 8 == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool rs = rowstats != nullptr;
+  if (bias && leaky && rs) return run_linear2<true, true, true>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias && leaky) return run_linear2<true, true, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias && rs) return run_linear2<true, false, true>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (bias) return run_linear2<true, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  if (leaky) return run_linear2<false, true, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
+  return run_linear2<false, false, false>(a, a_tail, b, bias, out_f16, rowstats, m, n, k, st);
 }
 
 extern "C" int pigan_debug_gemm_nt(const void* a, const void* b, const void* b_tail, float* c, int32_t kd,

@@ -135,3 +135,24 @@ def test_linear_epilogue(m, n, k, bias, leaky, rs, tail):
         v = v.view(m, nt, 256)
         assert _rel(rowst[..., 0], v.sum(2)) < 1e-4
         assert _rel(rowst[..., 1], (v * v).sum(2)) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (1000, 512, 256), (4096 + 128, 256, 512), (8192, 1024, 512)])
+def test_two_cta_linear_matches_one_cta(m, n, k):
+    """cta_group::2 kernel (csrc/gemm2_tc.cuh): a CTA pair shares the B tile; same epilogue, same numbers."""
+    native = _native()
+    torch.manual_seed(5 + m + n + k)
+    a = (torch.randn(m, k, device="cuda") * 0.5).half()
+    b = (torch.randn(n, k, device="cuda") * 0.1).half()
+    bias = torch.randn((n + 255) // 256 * 256, device="cuda")
+    outs = []
+    for fn in (native.lib.pigan_debug_linear, native.lib.pigan_debug_linear2):
+        out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.float16)
+        native.check(fn(a.data_ptr(), None, b.data_ptr(), bias.data_ptr(), out.data_ptr(), None, m, n, k, 1,
+                        native.current_stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = torch.nn.functional.leaky_relu(a.float() @ b.float().t() + bias[:n], 0.2)
+    assert torch.isfinite(outs[1].float()).all()
+    assert _rel(outs[1].float(), ref) < 6e-4
+    assert torch.equal(outs[0], outs[1])      # same accumulation order per output element

@@ -1,0 +1,27 @@
+"""Small train step + scoring + search + physics for compute-sanitizer runs."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "pi-gan-thz_b200"))
+import torch
+from core.models.generator import Generator
+from core.models.discriminator import Discriminator
+from core.models.forward_model import ForwardModel
+from pigan_b200 import synthetic, flat, native
+from pigan_b200.trainer import NativeTrainer
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+dev = torch.device("cuda")
+torch.manual_seed(1)
+G = Generator(250, 4); D = Discriminator(250, 4); F = ForwardModel(4, 250, 8); F.eval()
+tr = NativeTrainer(G, D, F, dev, max_batch=B)
+sp, pr, pn, mn = synthetic.make_batch(B, 250, seed=1, device=dev)
+for _ in range(2): tr.step(sp, pr, mn, 2e-4, 2e-4)
+G.eval(); st = flat.net_state(G, "generator")
+tr.engine.score_candidates(st.params.tensor(), st.bn.tensor(), spectra=sp)
+tr.engine.search(st.params.tensor(), st.bn.tensor(), sp[0], 0.01, 3, 0, 3 * B + 17, 64)
+with torch.no_grad():
+    F(pn); D(sp, pr); G(sp)
+freq = synthetic.frequencies(250, device=dev)
+idx = torch.empty(B, device=dev, dtype=torch.int32); out = torch.empty(B, 4, device=dev)
+native.check(native.lib.pigan_physics_metrics(sp.data_ptr(), B, 250, freq.data_ptr(), None, 0.0, idx.data_ptr(), out.data_ptr(), native.current_stream()))
+torch.cuda.synchronize()
+print("small_step ok", tr.losses.tolist()[:2])
