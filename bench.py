@@ -241,6 +241,39 @@ def run_native(args):
                 "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
     step_tflops = FLOP_PER_TRAIN_SAMPLE * B * K / (ms * 1e-3) / 1e12
 
+    # ---- the same step at a batch that tiles the 148 SMs without a partial wave (592 row tiles = 4 per SM instead of
+    # 512 = 3.46): informational, shows how much of the gap to the roofline is wave quantisation at B = 65536
+    quant = None
+    if world == 1 and not args.no_quant_probe:
+        Bq = 148 * 128 * 4
+        del tr
+        torch.cuda.empty_cache()
+        torch.manual_seed(42)
+        Gq, Dq, Fq = Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)
+        Fq.eval()
+        trq = NativeTrainer(Gq, Dq, Fq, dev, max_batch=Bq)
+        qs = [synthetic.make_batch(Bq, 250, seed=77 + i, device=dev) for i in range(3)]
+        for i in range(3):
+            trq.step(qs[i % 3][0], qs[i % 3][1], qs[i % 3][3], lr, lr)
+        barrier()
+        e0.record()
+        for i in range(K):
+            trq.step(qs[i % 3][0], qs[i % 3][1], qs[i % 3][3], lr, lr)
+        e1.record()
+        barrier()
+        msq = e0.elapsed_time(e1) / K
+        quant = {"batch": Bq, "ms_per_step": msq, "value": Bq / (msq * 1e-3), "unit": "samples/s",
+                 "frac_of_step_roofline": FLOP_PER_TRAIN_SAMPLE * Bq / (msq * 1e-3) / 1e12 / peaks["tflops"]}
+        del trq, qs, Gq, Dq, Fq
+        torch.cuda.empty_cache()
+        torch.manual_seed(42)
+        G, D, F = Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)
+        F.eval()
+        tr = NativeTrainer(G, D, F, dev, max_batch=B)
+        for i in range(3):
+            tr.step(*sets[i % NSETS], lr, lr)
+        barrier()
+
     # ---- timed region 2: end to end from pinned HOST buffers through the public API.  Two variants:
     #   e2e      NativeTrainer.step_prepared: the dataset keeps the fp16 first-layer operand that
     #            NativeTrainer.prepare_operand built once (the analogue of the reference's one-time dataset
@@ -392,6 +425,7 @@ def run_native(args):
             "clocks": clk,
             "scoring": score_info,
             "physics": phys_info,
+            "wave_quantisation_probe": quant,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }
         print(json.dumps(out), flush=True)
@@ -409,6 +443,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=1 << 23, help="candidates per GPU for the scoring line")
     ap.add_argument("--physics-spectra", type=int, default=1 << 22, help="spectra for the physics-kernel line (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-quant-probe", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

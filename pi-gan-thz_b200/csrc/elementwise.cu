@@ -429,6 +429,58 @@ __global__ void __launch_bounds__(256) pack_net_kernel(PackNetArgs a) {
   }
 }
 
+// Constant image of the fused generator-head + surrogate-layer-1 epilogue (layout: EpiHeadF1, epilogues.cuh).
+// One block of 256 threads, thread c = column c of both the generator's second layer and the surrogate's first.
+__global__ void head_consts_kernel(const float* __restrict__ scale2, const float* __restrict__ bias2,
+                                   const float* __restrict__ w3, const float* __restrict__ b3,
+                                   const float* __restrict__ fw1, const float* __restrict__ fb1,
+                                   const float* __restrict__ flnw, const float* __restrict__ flnb,
+                                   float* __restrict__ out) {
+  __shared__ double red[256];
+  __shared__ double mean[5];
+  const int c = threadIdx.x;
+  // head part, column pairs
+  {
+    float* o = out + (c >> 1) * 12;
+    o[(c & 1) * 2 + 0] = scale2[c];
+    o[(c & 1) * 2 + 1] = bias2[c];
+    for (int j = 0; j < 4; ++j) o[4 + (c & 1) * 4 + j] = w3[j * 256 + c];
+  }
+  if (c < 4) out[1536 + c] = b3[c];
+  for (int i = 1570 + c; i < 2048; i += 256) out[i] = 0.f;
+  // centred surrogate layer: u_c = (bias_c, w_c[0..3]) minus its mean over the columns
+  double u[5] = {(double)fb1[c], (double)fw1[c * 4 + 0], (double)fw1[c * 4 + 1], (double)fw1[c * 4 + 2],
+                 (double)fw1[c * 4 + 3]};
+  for (int j = 0; j < 5; ++j) {
+    red[c] = u[j];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (c < s) red[c] += red[c + s];
+      __syncthreads();
+    }
+    if (c == 0) mean[j] = red[0] / 256.0;
+    __syncthreads();
+  }
+  for (int j = 0; j < 5; ++j) u[j] -= mean[j];
+  double* q = reinterpret_cast<double*>(out + 1540);   // 8-byte aligned: 1540 * 4 = 6160
+  int k = 0;
+  for (int i = 0; i < 5; ++i)
+    for (int j = i; j < 5; ++j, ++k) {
+      red[c] = u[i] * u[j];
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) {
+        if (c < s) red[c] += red[c + s];
+        __syncthreads();
+      }
+      if (c == 0) q[k] = red[0] / 256.0;
+      __syncthreads();
+    }
+  const float gam = flnw[c];
+  for (int j = 0; j < 4; ++j) out[2048 + c * 4 + j] = gam * (float)u[1 + j];
+  out[3072 + c * 2 + 0] = gam * (float)u[0];
+  out[3072 + c * 2 + 1] = flnb[c];
+}
+
 __global__ void copy_pad_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_pad) dst[idx] = idx < n ? src[idx] : 0.f;
@@ -1262,6 +1314,10 @@ void launch_pack_net(const float* w1, int ld1, int S, int P, int wp_cols, int bi
   a.nC = w2th ? (H1 / 32) * (H2 / 32) : 0;
   const int nD = wp ? (H1 * 4 + 255) / 256 : 0;
   note_launch(), pack_net_kernel<<<a.nA + a.nB + a.nC + nD, 256, 0, st>>>(a);
+}
+void launch_head_consts(const float* scale2, const float* bias2, const float* w3, const float* b3, const float* fw1,
+                        const float* fb1, const float* flnw, const float* flnb, float* out, cudaStream_t st) {
+  note_launch(), head_consts_kernel<<<1, 256, 0, st>>>(scale2, bias2, w3, b3, fw1, fb1, flnw, flnb, out);
 }
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st) {

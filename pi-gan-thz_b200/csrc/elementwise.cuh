@@ -64,6 +64,9 @@ void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_co
 void launch_pack_net(const float* w1, int ld1, int S, int P, int wp_cols, int bias_cols, const float* b1,
                      const float* cvec, __half* w1h, int Kp, float* b_eff, int H1, const float* w2, int H2,
                      __half* w2h, __half* w2th, float* wp, cudaStream_t st);
+// constant image of EpiHeadF1 (epilogues.cuh: kHeadImgFloats = 3584 floats); widths fixed at 256 / 4
+void launch_head_consts(const float* scale2, const float* bias2, const float* w3, const float* b3, const float* fw1,
+                        const float* fb1, const float* flnw, const float* flnb, float* out, cudaStream_t st);
 void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st);
 void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst,
                            cudaStream_t st);

@@ -114,6 +114,7 @@ struct PiganEngine {
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
   float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
   float *mean1, *rstd1, *scale1, *bias1, *mean2, *rstd2, *scale2, *bias2;
+  float *head_img;                     // [kHeadImgFloats] constants of EpiHeadF1
   float *zero_blk;                     // sums | bn_sums | bn_bwd_sums, cleared with one memset per step
   size_t zero_bytes;
   float *f_bias_out;                   // [288] zero padded
@@ -180,6 +181,7 @@ struct PiganEngine {
     mean1 = c.take<float>(H1); rstd1 = c.take<float>(H1); scale1 = c.take<float>(H1); bias1 = c.take<float>(H1);
     mean2 = c.take<float>(H2); rstd2 = c.take<float>(H2); scale2 = c.take<float>(H2); bias2 = c.take<float>(H2);
     f_bias_out = c.take<float>(288);
+    head_img = c.take<float>(kHeadImgFloats);
     return (c.off + 255) & ~size_t(255);
   }
 };
@@ -371,6 +373,10 @@ void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offs
   launch_bn_finalize(a, st);
 }
 
+// the fused generator-head + surrogate-layer-1 epilogue (EpiHeadF1) is written for the reference widths
+bool fused_head(const PiganEngine* e) {
+  return e->f_loaded && e->gl.H2 == 256 && e->gl.P == 4 && e->fl.H[0] == 256;
+}
 // Generator in eval mode from the prepared operand e->xc: BatchNorm-1 (running statistics) + ReLU are folded
 // into layer 1's epilogue, BatchNorm-2 + ReLU into the head kernel.  `packed`: weights / affines already set up.
 int g_eval_setup(PiganEngine* e, const float* gp, const float* bn, cudaStream_t st) {
@@ -379,9 +385,17 @@ int g_eval_setup(PiganEngine* e, const float* gp, const float* bn, cudaStream_t 
   PM("small");
   launch_bn_eval_affine(bn + G.rm1, bn + G.rv1, gp + G.bn1_w, gp + G.bn1_b, e->g_beff, e->scale1, e->bias1, G.H1, st);
   launch_bn_eval_affine(bn + G.rm2, bn + G.rv2, gp + G.bn2_w, gp + G.bn2_b, gp + G.b2, e->scale2, e->bias2, G.H2, st);
+  if (fused_head(e)) {
+    // constants of the fused head + surrogate-layer-1 epilogue (EpiHeadF1)
+    const FwdLayout& L = e->fl;
+    const float* fp = e->f_params;
+    launch_head_consts(e->scale2, e->bias2, gp + G.w3, gp + G.b3, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0],
+                       fp + L.ln_b[0], e->head_img, st);
+  }
   return PIGAN_OK;
 }
-int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cudaStream_t st) {
+// with_f1: also emit the surrogate's first activation (e->f_a1) from the fused epilogue (needs the surrogate loaded)
+int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cudaStream_t st, bool with_f1 = false) {
   const GenLayout& G = e->gl;
   {
     PM("g_l1_gemm");
@@ -395,6 +409,15 @@ int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cud
     ep.mask = nullptr;
     ep.mask_words = 0;
     PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st)));
+  }
+  if (with_f1 && fused_head(e)) {
+    PM("g_l2_head_f1_gemm");
+    using Epi = EpiHeadF1<CfgS>;
+    Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, e->f_a1, n, e->fl.H[0], e->fl.H[0]));
+    ep.p_out = p_out;
+    ep.img = e->head_img;
+    return run_tn<CfgS, Epi>(ep, e->g_a1, n, G.H1, G.H1, e->g_w2h, G.H2, G.H1, st);
   }
   PM("g_l2_gemm");
   PIGAN_TRY((linear_store<false, false, false>(e->g_a1, n, G.H1, e->g_w2h, G.H2, nullptr, e->g_h2, nullptr, st)));
@@ -458,12 +481,13 @@ struct FOutOpts {
   float* row_err;
   int f1_idx, f2_idx;
 };
-int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o, cudaStream_t st) {
+int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o, cudaStream_t st,
+              bool have_a1 = false) {
   if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
   const FwdLayout& L = e->fl;
   const float* fp = e->f_params;
   PM("f_l1");
-  launch_f_l1(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_a1, n, L.H[0], st);
+  if (!have_a1) launch_f_l1(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_a1, n, L.H[0], st);
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
@@ -908,11 +932,11 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
   }
   PIGAN_TRY(g_eval_setup(e, gp, bn, st));
   float* p = out_p ? out_p : e->p;
-  PIGAN_TRY(g_eval_forward(e, gp, n, p, st));
+  PIGAN_TRY(g_eval_forward(e, gp, n, p, st, true));
   float* err = out_err ? out_err : e->row_err;
   // per-candidate error against its own spectrum (given spectra) or against the design target (cvec = target)
   FOutOpts fo{spectra ? 2 : 1, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, err, 0, 1};
-  PIGAN_TRY(f_forward(e, p, n, fo, st));
+  PIGAN_TRY(f_forward(e, p, n, fo, st, fused_head(e)));
   PM("small");
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
   PM(nullptr);
@@ -986,9 +1010,9 @@ extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, cons
       launch_cast_center_philox(target, sigma, seed, first_candidate + g0 + off, e->cvec, e->xc,
                                 noise_dump ? noise_dump + (size_t)(g0 + off) * G.S : nullptr, n, G.S, kKp, st);
       float* p = w.params + (size_t)(k + off) * 4;
-      PIGAN_TRY(g_eval_forward(e, gp, n, p, st));
+      PIGAN_TRY(g_eval_forward(e, gp, n, p, st, true));
       FOutOpts fo{1, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, w.scores + k + off, 0, 1};
-      PIGAN_TRY(f_forward(e, p, n, fo, st));
+      PIGAN_TRY(f_forward(e, p, n, fo, st, fused_head(e)));
     }
     PM("topk");
     launch_fill_inf(w.scores + k + in_group, cap - in_group, st);

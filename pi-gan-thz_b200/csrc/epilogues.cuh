@@ -548,6 +548,131 @@ struct EpiDiscParamGrad {
 };
 
 // =====================================================================================================
+// Scoring path, generator layer 2 onwards in ONE epilogue (eval mode: BatchNorm uses running statistics, so rows
+// never interact): ReLU(BN2(acc)) -> Linear(256,4) + tanh = the 4 predicted parameters (generator.py:22-25), then the
+// forward surrogate's first layer Linear(4,256) + LayerNorm + LeakyReLU (forward_model.py:30-33) straight into the
+// fp16 operand of its second layer.  The pre-BatchNorm activations, the generator output round trip and two
+// streaming kernels disappear.  The accumulator is read once and released before the surrogate part starts.
+//
+// The surrogate's first layer is affine in the 4 parameters, so its LayerNorm statistics are closed-form:
+//   h_c - mean = bc_c + wc_c . p   (bc, wc = bias / weight columns centred over c),   var = u^T Q u,  u = (1, p),
+//   Q = 1/256 sum_c (bc_c, wc_c)(bc_c, wc_c)^T  (5 x 5, evaluated in fp64 per row: 15 FMAs).
+// Per-column constants (14 KB image built by head_consts_kernel, elementwise.cu) are staged once per CTA in shared
+// memory and read as warp-broadcast 16-byte loads:
+//   floats [0,1536)    per column pair t: s_2t b_2t s_2t+1 b_2t+1 | w3[0..3][2t] | w3[0..3][2t+1]   (BN2 folded, head)
+//   floats [1536,1540) b3 ; [1540,1570) Q as 15 doubles (upper triangle, row-major)
+//   floats [2048,3072) gamma_c * wc_c[0..3] ; [3072,3584) (gamma_c * bc_c, beta_c)
+// =====================================================================================================
+constexpr int kHeadImgFloats = 3584;
+
+template <class Cfg>
+struct EpiHeadF1 {
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiHeadF1 tile shape");
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
+  static constexpr bool EARLY_RELEASE = true;
+  struct Params {
+    CUtensorMap out;    // surrogate layer-1 activations [M,256] fp16
+    float* p_out;       // [M,4] predicted parameters (tanh output)
+    const float* img;   // kHeadImgFloats constants, layout above
+  };
+  // per group: [0,32K) store staging | [32K,40K) one half of the constant image (group 0: floats [0,2048),
+  // group 1: floats [2048,3584)); both groups read both halves.
+  static constexpr int SMEM_BYTES = 40960;
+  struct State {
+    Stager stg;
+  };
+  __device__ static uint32_t part_a(const EpiCtx& cx) { return cx.smem0 + kEpiStagingBytes; }
+  __device__ static uint32_t part_b(const EpiCtx& cx) { return cx.smem0 + SMEM_BYTES + kEpiStagingBytes; }
+  __device__ static float4 lds4(uint32_t addr) {
+    float4 t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
+    return t;
+  }
+  __device__ static double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+  }
+  __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    st.stg.init();
+    const int base = cx.group == 0 ? 0 : 2048, n4 = cx.group == 0 ? 512 : 384;
+    const uint32_t dst = cx.group == 0 ? part_a(cx) : part_b(cx);
+    const float4* src = reinterpret_cast<const float4*>(p.img + base);
+    for (int i = cx.tid; i < n4; i += 128) {
+      const float4 t = __ldg(src + i);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "f"(t.x), "f"(t.y), "f"(t.z),
+                   "f"(t.w) : "memory");
+    }
+    asm volatile("bar.sync 5, 256;" ::: "memory");
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int row = w.m_tile * kBlockM + r;
+    const uint32_t pa = part_a(cx), pb = part_b(cx);
+    // ---- generator head: the only pass over tensor memory
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < 256; c += 16) {
+      float v[16];
+      tmem_ld16(tacc + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t ad = pa + (uint32_t)(c / 2 + t) * 48u;
+        const float4 sb = lds4(ad), w0 = lds4(ad + 16), w1 = lds4(ad + 32);
+        const float a0 = fmaxf(fmaf(sb.x, v[2 * t], sb.y), 0.f);
+        const float a1 = fmaxf(fmaf(sb.z, v[2 * t + 1], sb.w), 0.f);
+        d0 = fmaf(a0, w0.x, d0); d1 = fmaf(a0, w0.y, d1); d2 = fmaf(a0, w0.z, d2); d3 = fmaf(a0, w0.w, d3);
+        d0 = fmaf(a1, w1.x, d0); d1 = fmaf(a1, w1.y, d1); d2 = fmaf(a1, w1.z, d2); d3 = fmaf(a1, w1.w, d3);
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(cx.tempty);   // accumulator drained: the MMAs of the unit after next may start
+    const float4 b3 = lds4(pa + 1536 * 4);
+    const float p0 = tanhf(d0 + b3.x), p1 = tanhf(d1 + b3.y), p2 = tanhf(d2 + b3.z), p3 = tanhf(d3 + b3.w);
+    if (row < g.M) *reinterpret_cast<float4*>(p.p_out + (size_t)row * 4) = make_float4(p0, p1, p2, p3);
+    // ---- surrogate layer 1: closed-form LayerNorm statistics, then one pass over the 256 columns
+    float rs;
+    {
+      const double u[5] = {1.0, (double)p0, (double)p1, (double)p2, (double)p3};
+      const uint32_t qa = pa + 1540 * 4;
+      double var = 0.0;
+      int k = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = i; j < 5; ++j, ++k) acc = fma(lds_f64(qa + 8u * k) * (j == i ? 1.0 : 2.0), u[j], acc);
+        var = fma(acc, u[i], var);
+      }
+      rs = 1.0f / sqrtf(fmaxf((float)var, 0.f) + 1e-5f);
+    }
+    const float q0 = p0 * rs, q1 = p1 * rs, q2 = p2 * rs, q3 = p3 * rs;
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+      const uint32_t buf = st.stg.acquire(cx);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int c = sub * 64 + hh * 32 + i;
+          const float4 gb = lds4(pb + 4096u + (uint32_t)c * 8u);   // (g*bc, beta) of columns c, c+1
+          const float4 g0 = lds4(pb + (uint32_t)c * 16u), g1 = lds4(pb + (uint32_t)c * 16u + 16u);
+          v[i] = lrelu(fmaf(g0.w, q3, fmaf(g0.z, q2, fmaf(g0.y, q1, fmaf(g0.x, q0, fmaf(gb.x, rs, gb.y))))));
+          v[i + 1] = lrelu(fmaf(g1.w, q3, fmaf(g1.z, q2, fmaf(g1.y, q1, fmaf(g1.x, q0, fmaf(gb.z, rs, gb.w))))));
+        }
+        Stager::put32(buf, r, hh, v);
+      }
+      st.stg.commit(cx, buf, &p.out, sub * 64, w.m_tile * kBlockM);
+    }
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+};
+
+// =====================================================================================================
 // Forward-model output layer fused with everything the step derives from it without ever writing the
 // [B,258] output (forward_model.py:56,74-75; train_pigan.py:159-170; loss.py:51-56,82-101;
 // unified_evaluator.py:387): reconstruction MSE vs the real spectrum, metric MSE, mean squared second

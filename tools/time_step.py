@@ -31,3 +31,7 @@ for _ in range(n): tr.engine.score_candidates(st.params.tensor(), st.bn.tensor()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print(f"score B={B}: {ms:.3f} ms -> {B / ms * 1e3:.3e} cand/s")
+tr.engine.profile_begin()
+for _ in range(n): tr.engine.score_candidates(st.params.tensor(), st.bn.tensor(), spectra=sp, want_params=False)
+for k, (c, t) in tr.engine.profile_end().items():
+    print(f"  {k:24s} {c:5d} {t / n * 1e3:8.1f} us/call")
