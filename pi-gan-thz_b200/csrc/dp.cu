@@ -78,6 +78,7 @@ __device__ __forceinline__ void wait_peer(const PeerTable& t, int channel, int s
 template <typename T>
 __global__ void __launch_bounds__(1024) allreduce_small_kernel(PeerTable t, T* __restrict__ buf, int n, int channel,
                                                                uint32_t epoch, size_t slot_off) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent (launch_k)
   T* mine = reinterpret_cast<T*>(t.base[t.rank] + slot_off);
   for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = buf[i];
   __syncthreads();
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) allreduce_grads_kernel(PeerTable t, size_
                                                               long long n, int channel, uint32_t epoch,
                                                               double* __restrict__ sumsq) {
   __shared__ float red[8];
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent (launch_k)
   if (blockIdx.x == 0 && threadIdx.x == 0) publish(t, channel, epoch);   // earlier kernels of the stream are done
   if (threadIdx.x < t.world) wait_peer(t, channel, threadIdx.x, epoch);
   __syncthreads();
@@ -203,11 +205,10 @@ extern "C" int pigan_dp_allreduce_small(PiganDp* d, void* buf, int32_t n, int32_
   PIGAN_CHECK_ARG((size_t)n * (is_double ? 8 : 4) <= (size_t)kSmallSlotBytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t slot = kFlagBytes + ((size_t)channel * 2 + (epoch & 1u)) * kSmallSlotBytes;
-  note_launch();
   if (is_double)
-    allreduce_small_kernel<double><<<1, 1024, 0, st>>>(d->t, static_cast<double*>(buf), n, channel, epoch, slot);
+    launch_k(allreduce_small_kernel<double>, 1, 1024, 0, st, d->t, static_cast<double*>(buf), n, channel, epoch, slot);
   else
-    allreduce_small_kernel<float><<<1, 1024, 0, st>>>(d->t, static_cast<float*>(buf), n, channel, epoch, slot);
+    launch_k(allreduce_small_kernel<float>, 1, 1024, 0, st, d->t, static_cast<float*>(buf), n, channel, epoch, slot);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -223,7 +224,7 @@ extern "C" int pigan_dp_allreduce_grads(PiganDp* d, int32_t net, float* dst, int
   int grid = (int)((n / 4 + 255) / 256);
   if (grid > sm_count()) grid = sm_count();
   if (grid < 1) grid = 1;
-  note_launch(), allreduce_grads_kernel<<<grid, 256, 0, st>>>(d->t, off, dst, (long long)n, channel, epoch, sumsq);
+  launch_k(allreduce_grads_kernel, grid, 256, 0, st, d->t, off, dst, (long long)n, channel, epoch, sumsq);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

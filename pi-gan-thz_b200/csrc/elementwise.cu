@@ -7,6 +7,10 @@
 namespace pigan {
 
 namespace {
+// first statement of every kernel here: wait for the kernel this one was launched behind (host_util.h: launch_k)
+// (An explicit early griddepcontrol.launch_dependents was measured and is slower: parked blocks of the successor
+// take slots from this kernel's later waves; the implicit trigger at block exit is what is used.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 constexpr int kThreads = 256;
 constexpr float kBnEps = 1e-5f;
@@ -104,6 +108,7 @@ inline int grid_for_rows(int64_t rows, int rows_per_block, int max_blocks = 148 
 
 // dst[c] += mult * sum_b part[b * ld + off + c] for up to 8 column segments (one block per 32 columns)
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(ReduceArgs a) {
+  pdl_wait();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -127,12 +132,13 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(ReduceArgs a) {
   }
 }
 void launch_reduce_partials(const ReduceArgs& a, cudaStream_t st) {
-  note_launch(), reduce_partials_kernel<<<(a.ld + 31) / 32, 1024, 0, st>>>(a);
+  launch_k(reduce_partials_kernel, (a.ld + 31) / 32, 1024, 0, st, a);
 }
 
 // ------------------------------------------------------------------------------------------ spectrum prep
 __global__ void center_vec_kernel(const float* __restrict__ x, int S, int rows_used, float* __restrict__ cvec,
                                   int Kp) {
+  pdl_wait();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 32
   const int col = blockIdx.x * 32 + tx;
@@ -153,6 +159,7 @@ template <bool NOISE>
 __global__ void cast_center_kernel(const float* __restrict__ x, const float* __restrict__ noise, float sigma,
                                    const float* __restrict__ cvec, const float* __restrict__ params,
                                    __half* __restrict__ xc, long long rows, int S, int P, int Kp, int vec2) {
+  pdl_wait();
   const int cpr = Kp >> 3;
   const long long total = rows * cpr;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -232,6 +239,7 @@ __device__ __forceinline__ void normal4(uint4 u, float* z) {
 __global__ void cast_center_philox_kernel(const float* __restrict__ target, float sigma, unsigned long long seed,
                                           long long first, const float* __restrict__ cvec, __half* __restrict__ xc,
                                           float* __restrict__ noise_out, long long rows, int S, int Kp) {
+  pdl_wait();
   const int cpr = Kp >> 3;
   const long long total = rows * cpr;
   const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
@@ -263,6 +271,7 @@ __global__ void cast_center_philox_kernel(const float* __restrict__ target, floa
 // ---- running top-k of the inverse-design search (engine.cu: pigan_inverse_design_search)
 __global__ void search_init_kernel(float* __restrict__ scores, long long* __restrict__ iota, long long* __restrict__ best_idx,
                                    float* __restrict__ params, long long total, int k) {
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     iota[i] = i;
@@ -274,6 +283,7 @@ __global__ void search_init_kernel(float* __restrict__ scores, long long* __rest
   }
 }
 __global__ void fill_inf_kernel(float* __restrict__ s, long long n) {
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s[i] = __int_as_float(0x7f800000);
 }
@@ -281,6 +291,7 @@ __global__ void fill_inf_kernel(float* __restrict__ s, long long n) {
 __global__ void search_gather_kernel(const long long* __restrict__ pos, const float* __restrict__ params,
                                      const long long* __restrict__ best_idx, long long group_base, int k,
                                      long long* __restrict__ tmp_idx, float* __restrict__ tmp_params) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k) return;
   const long long q = pos[i];
@@ -290,6 +301,7 @@ __global__ void search_gather_kernel(const long long* __restrict__ pos, const fl
 __global__ void search_commit_kernel(const float* __restrict__ sel_scores, const long long* __restrict__ tmp_idx,
                                      const float* __restrict__ tmp_params, int k, float* __restrict__ scores,
                                      long long* __restrict__ best_idx, float* __restrict__ params) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k) return;
   scores[i] = sel_scores[i];
@@ -301,6 +313,7 @@ __global__ void search_commit_kernel(const float* __restrict__ sel_scores, const
 __global__ void pack_first_layer_kernel(const float* __restrict__ w, int ld_src, int S, int P, int wp_cols,
                                         int bias_cols, const float* __restrict__ b, const float* __restrict__ cvec,
                                         __half* __restrict__ out, int Kp, float* __restrict__ b_eff_out, int rows) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= rows) return;
@@ -326,6 +339,7 @@ __global__ void pack_first_layer_kernel(const float* __restrict__ w, int ld_src,
 
 __global__ void cast_pad_kernel(const float* __restrict__ src, int ld_src, int ncols, __half* __restrict__ dst,
                                 int ld_dst, int rows) {
+  pdl_wait();
   const long long total = (long long)rows * ld_dst;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -336,6 +350,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int ld_src, int n
 
 __global__ void transpose_cast_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
                                       __half* __restrict__ dst, int ld_dst) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -352,6 +367,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, int rows, i
 
 __global__ void extract_wp_kernel(const float* __restrict__ w, int ld_src, int S, int P, float* __restrict__ wp,
                                   int rows, int rows_pad) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_pad * 4) return;
   const int i = idx >> 2, e = idx & 3;
@@ -371,6 +387,7 @@ struct PackNetArgs {
   int nA, nB, nC;
 };
 __global__ void __launch_bounds__(256) pack_net_kernel(PackNetArgs a) {
+  pdl_wait();
   __shared__ float tile[32][33];
   int b = blockIdx.x;
   if (b < a.nA) {
@@ -436,6 +453,7 @@ __global__ void head_consts_kernel(const float* __restrict__ scale2, const float
                                    const float* __restrict__ fw1, const float* __restrict__ fb1,
                                    const float* __restrict__ flnw, const float* __restrict__ flnb,
                                    float* __restrict__ out) {
+  pdl_wait();
   __shared__ double red[256];
   __shared__ double mean[5];
   const int c = threadIdx.x;
@@ -482,6 +500,7 @@ __global__ void head_consts_kernel(const float* __restrict__ scale2, const float
 }
 
 __global__ void copy_pad_f32_kernel(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_pad) dst[idx] = idx < n ? src[idx] : 0.f;
 }
@@ -535,6 +554,7 @@ __device__ __forceinline__ void block_colsum_partial4(const float* acc4, float* 
 // ------------------------------------------------------------------------------------------ BatchNorm
 __global__ void __launch_bounds__(kThreads, 4) colstats_kernel(const __half* __restrict__ h, long long rows, int C,
                                                                float* __restrict__ part) {
+  pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(C);
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -561,6 +581,7 @@ __global__ void __launch_bounds__(kThreads, 4) colstats_kernel(const __half* __r
 }
 
 __global__ void bn_finalize_kernel(BnFinalizeArgs a) {
+  pdl_wait();
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.C; c += gridDim.x * blockDim.x) {
     const double ms = (double)a.sum[c] / a.n;
     double var = (double)a.sumsq[c] / a.n - ms * ms;
@@ -591,6 +612,7 @@ __global__ void bn_finalize_kernel(BnFinalizeArgs a) {
 
 __global__ void bn_eval_affine_kernel(const float* rm, const float* rv, const float* gamma, const float* beta,
                                       const float* offset, float* scale, float* bias, int C) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] / sqrtf(rv[c] + kBnEps);
@@ -602,6 +624,7 @@ __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(const __half* _
                                                                  const float* __restrict__ scale,
                                                                  const float* __restrict__ bias,
                                                                  __half* __restrict__ out, long long rows, int C) {
+  pdl_wait();
   const ColMap m(C);
   float sc[8], bi[8];
   ld_f8(scale + m.ch * 8, sc);
@@ -626,6 +649,7 @@ __global__ void __launch_bounds__(kHeadRows) g_head_fwd_kernel(
     const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ p_out,
     float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
     int C, int Kp, int S) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smraw[];
   float* cst = reinterpret_cast<float*>(smraw);                 // scale[256] bias[256] w3[4][256]
   float* pds = cst + 6 * 256;                                    // [128][4] denormalised outputs
@@ -722,6 +746,7 @@ __global__ void __launch_bounds__(kHeadRows) g_head_fwd_kernel(
 // Recomputing dy costs 4 FMAs per element; storing it in fp16 before BatchNorm's projection would amplify its
 // rounding (the adversarial gradient pushes every sample the same way, so most of dy is projected out).
 __global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
+  pdl_wait();
   __shared__ float sm[32];
   float db[4] = {0.f, 0.f, 0.f, 0.f};
   float range_acc = 0.f;
@@ -756,6 +781,7 @@ __global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
 
 template <bool APPLY>
 __global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHeadBwdArgs a) {
+  pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(a.C);
   const int c0 = m.ch * 4;
@@ -870,6 +896,7 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHe
 // sums the moment partials over blocks (grid: C/32 x 8 arrays) into tot[8][C] ...
 __global__ void __launch_bounds__(1024) g_head_moments_sum_kernel(const float* __restrict__ part, int nblocks, int C,
                                                                   float* __restrict__ tot) {
+  pdl_wait();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -888,6 +915,7 @@ __global__ void __launch_bounds__(1024) g_head_moments_sum_kernel(const float* _
 }
 // ... and finishes sum dy, sum dy*xhat and dW3 from them
 __global__ void g_head_moments_finish_kernel(GHeadBwdArgs a, const float* __restrict__ tot) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
@@ -908,6 +936,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
     const __half* __restrict__ da, const __half* __restrict__ h, const float* __restrict__ scale,
     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ rstd,
     float* __restrict__ part, long long rows, int C) {
+  pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(C);
   const int c0 = m.ch * 4;
@@ -947,6 +976,7 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
 
 // dh = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)), dy = da * ReLU mask, written as A*dy - B*h + C0
 __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) {
+  pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(a.C);
   const int c0 = m.ch * 4;
@@ -1012,6 +1042,7 @@ __global__ void __launch_bounds__(kThreads, 4) d_l2_bwd_kernel(const __half* __r
                                                                float* __restrict__ dw3, float* __restrict__ db2,
                                                                float* __restrict__ db3, long long rows, int C,
                                                                float inv_gs, float* __restrict__ part) {
+  pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(C);
   const int c0 = m.ch * 4;
@@ -1061,6 +1092,7 @@ __global__ void __launch_bounds__(kThreads) f_l1_kernel(const float* __restrict_
                                                         const float* __restrict__ b1, const float* __restrict__ lnw,
                                                         const float* __restrict__ lnb, __half* __restrict__ out,
                                                         long long rows, int C) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   float4 wr[8];
   float b[8], gm[8], bt[8];
@@ -1129,6 +1161,7 @@ __global__ void __launch_bounds__(kThreads) ln_lrelu_apply_kernel(__half* __rest
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, long long rows,
                                                                   int N) {
+  pdl_wait();
   const ColMap m(N);
   float gm[8], bt[8];
   ld_f8(gamma + m.ch * 8, gm);
@@ -1154,6 +1187,7 @@ __global__ void __launch_bounds__(kThreads) ln_lrelu_apply_kernel(__half* __rest
 
 // ------------------------------------------------------------------------------------------ optimiser
 __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
+  pdl_wait();
   __shared__ float sm[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1163,6 +1197,7 @@ __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
+  pdl_wait();
   // torch.nn.utils.clip_grad_norm_(max_norm) then optim.Adam.step() (train_pigan.py:142-143,186-187)
   const float total = (float)sqrt(*a.total_sq);
   float coef = a.max_norm / (total + 1e-6f);
@@ -1187,6 +1222,7 @@ __global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict_
                                                         int splits, float* __restrict__ dw, int ld, int m_valid,
                                                         int n_valid, float scale, int bias_col,
                                                         float* __restrict__ db) {
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (n >= tiles_n * 256 || m >= m_valid) return;
@@ -1208,6 +1244,7 @@ __global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict_
 }
 
 __global__ void dw_fixup_kernel(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = S + P;
   if (idx >= rows * per) return;
@@ -1216,6 +1253,7 @@ __global__ void dw_fixup_kernel(float* dw, int ld, int S, int P, const float* db
 }
 
 __global__ void loss_finalize_kernel(LossFinalizeArgs a) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double* s = a.sums;
   const float d_loss = (float)s[0];
@@ -1241,6 +1279,7 @@ __global__ void loss_finalize_kernel(LossFinalizeArgs a) {
 
 __global__ void score_finish_kernel(const float* __restrict__ p, const float* __restrict__ err, long long rows,
                                     int P, int* __restrict__ viol, float* __restrict__ cons) {
+  pdl_wait();
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   int v = 0;
@@ -1257,20 +1296,20 @@ __global__ void score_finish_kernel(const float* __restrict__ p, const float* __
 // =========================================================================================== launchers
 void launch_center_vec(const float* x, int64_t rows, int S, int rows_used, float* cvec, int Kp, cudaStream_t st) {
   if (rows_used > rows) rows_used = (int)rows;
-  note_launch(), center_vec_kernel<<<(Kp + 31) / 32, 1024, 0, st>>>(x, S, rows_used, cvec, Kp);
+  launch_k(center_vec_kernel, (Kp + 31) / 32, 1024, 0, st, x, S, rows_used, cvec, Kp);
 }
 void launch_cast_center(const float* x, const float* cvec, const float* params, __half* xc, int64_t rows, int S,
                         int P, int Kp, cudaStream_t st) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
-  note_launch(), cast_center_kernel<false><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(x, nullptr, 0.f, cvec, params, xc, rows, S, P, Kp,
+  launch_k(cast_center_kernel<false>, grid > 0 ? grid : 1, kThreads, 0, st, x, nullptr, 0.f, cvec, params, xc, rows, S, P, Kp,
                                                                              (S % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) ? 1 : 0);
 }
 void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
                               float*, int64_t rows, int S, int P, int Kp, cudaStream_t st) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
-  note_launch(), cast_center_kernel<true><<<grid > 0 ? grid : 1, kThreads, 0, st>>>(target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp,
+  launch_k(cast_center_kernel<true>, grid > 0 ? grid : 1, kThreads, 0, st, target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp,
                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(target) & 7) == 0 &&
                                                                              (reinterpret_cast<uintptr_t>(noise) & 7) == 0) ? 1 : 0);
 }
@@ -1278,27 +1317,27 @@ void launch_cast_center_philox(const float* target, float sigma, uint64_t seed, 
                                __half* xc, float* noise_out, int64_t rows, int S, int Kp, cudaStream_t st) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
-  note_launch(), cast_center_philox_kernel<<<grid > 0 ? grid : 1, kThreads, 0, st>>>(
+  launch_k(cast_center_philox_kernel, grid > 0 ? grid : 1, kThreads, 0, st, 
       target, sigma, (unsigned long long)seed, (long long)first, cvec, xc, noise_out, rows, S, Kp);
 }
 void launch_search_init(float* scores, int64_t* iota, int64_t* best_idx, float* params, int64_t total, int k,
                         cudaStream_t st) {
-  note_launch(), search_init_kernel<<<148 * 4, 256, 0, st>>>(scores, reinterpret_cast<long long*>(iota),
+  launch_k(search_init_kernel, 148 * 4, 256, 0, st, scores, reinterpret_cast<long long*>(iota),
                                                        reinterpret_cast<long long*>(best_idx), params, total, k);
 }
 void launch_fill_inf(float* s, int64_t n, cudaStream_t st) {
   if (n <= 0) return;
-  note_launch(), fill_inf_kernel<<<148 * 2, 256, 0, st>>>(s, n);
+  launch_k(fill_inf_kernel, 148 * 2, 256, 0, st, s, n);
 }
 void launch_search_gather(const int64_t* pos, const float* params, const int64_t* best_idx, int64_t group_base, int k,
                           int64_t* tmp_idx, float* tmp_params, cudaStream_t st) {
-  note_launch(), search_gather_kernel<<<(k + 255) / 256, 256, 0, st>>>(
+  launch_k(search_gather_kernel, (k + 255) / 256, 256, 0, st, 
       reinterpret_cast<const long long*>(pos), params, reinterpret_cast<const long long*>(best_idx), group_base, k,
       reinterpret_cast<long long*>(tmp_idx), tmp_params);
 }
 void launch_search_commit(const float* sel_scores, const int64_t* tmp_idx, const float* tmp_params, int k,
                           float* scores, int64_t* best_idx, float* params, cudaStream_t st) {
-  note_launch(), search_commit_kernel<<<(k + 255) / 256, 256, 0, st>>>(sel_scores, reinterpret_cast<const long long*>(tmp_idx),
+  launch_k(search_commit_kernel, (k + 255) / 256, 256, 0, st, sel_scores, reinterpret_cast<const long long*>(tmp_idx),
                                                                 tmp_params, k, scores,
                                                                 reinterpret_cast<long long*>(best_idx), params);
 }
@@ -1313,52 +1352,52 @@ void launch_pack_net(const float* w1, int ld1, int S, int P, int wp_cols, int bi
   if (a.nB > 128) a.nB = 128;
   a.nC = w2th ? (H1 / 32) * (H2 / 32) : 0;
   const int nD = wp ? (H1 * 4 + 255) / 256 : 0;
-  note_launch(), pack_net_kernel<<<a.nA + a.nB + a.nC + nD, 256, 0, st>>>(a);
+  launch_k(pack_net_kernel, a.nA + a.nB + a.nC + nD, 256, 0, st, a);
 }
 void launch_head_consts(const float* scale2, const float* bias2, const float* w3, const float* b3, const float* fw1,
                         const float* fb1, const float* flnw, const float* flnb, float* out, cudaStream_t st) {
-  note_launch(), head_consts_kernel<<<1, 256, 0, st>>>(scale2, bias2, w3, b3, fw1, fb1, flnw, flnb, out);
+  launch_k(head_consts_kernel, 1, 256, 0, st, scale2, bias2, w3, b3, fw1, fb1, flnw, flnb, out);
 }
 void launch_pack_first_layer(const float* w, int ld_src, int S, int P, int wp_cols, int bias_cols, const float* b,
                              const float* cvec, __half* out, int Kp, float* b_eff_out, int rows, cudaStream_t st) {
-  note_launch(), pack_first_layer_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, ld_src, S, P, wp_cols, bias_cols, b, cvec, out, Kp,
+  launch_k(pack_first_layer_kernel, (rows + 7) / 8, 256, 0, st, w, ld_src, S, P, wp_cols, bias_cols, b, cvec, out, Kp,
                                                           b_eff_out, rows);
 }
 void launch_cast_pad(const float* src, int ld_src, int ncols, __half* dst, int ld_dst, int rows, cudaStream_t st) {
   const long long total = (long long)rows * ld_dst;
   int grid = (int)((total + kThreads - 1) / kThreads);
   if (grid > 148 * 8) grid = 148 * 8;
-  note_launch(), cast_pad_kernel<<<grid, kThreads, 0, st>>>(src, ld_src, ncols, dst, ld_dst, rows);
+  launch_k(cast_pad_kernel, grid, kThreads, 0, st, src, ld_src, ncols, dst, ld_dst, rows);
 }
 void launch_transpose_cast(const float* src, int rows, int cols, int ld_src, __half* dst, int ld_dst,
                            cudaStream_t st) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  note_launch(), transpose_cast_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst);
+  launch_k(transpose_cast_kernel, grid, 256, 0, st, src, rows, cols, ld_src, dst, ld_dst);
 }
 void launch_extract_wp(const float* w, int ld_src, int S, int P, float* wp, int rows, int rows_pad, cudaStream_t st) {
-  note_launch(), extract_wp_kernel<<<(rows_pad * 4 + 255) / 256, 256, 0, st>>>(w, ld_src, S, P, wp, rows, rows_pad);
+  launch_k(extract_wp_kernel, (rows_pad * 4 + 255) / 256, 256, 0, st, w, ld_src, S, P, wp, rows, rows_pad);
 }
 void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStream_t st) {
-  note_launch(), copy_pad_f32_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(src, n, dst, n_pad);
+  launch_k(copy_pad_f32_kernel, (n_pad + 255) / 256, 256, 0, st, src, n, dst, n_pad);
 }
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
-  note_launch(), colstats_kernel<<<grid, kThreads, 0, st>>>(h, rows, C, part);
+  launch_k(colstats_kernel, grid, kThreads, 0, st, h, rows, C, part);
   ReduceArgs r{part, grid, 2 * C, 2, {{sum, C, 1.f}, {sumsq, C, 1.f}}};
   launch_reduce_partials(r, st);
 }
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
-  note_launch(), bn_finalize_kernel<<<(a.C + 255) / 256, 256, 0, st>>>(a);
+  launch_k(bn_finalize_kernel, (a.C + 255) / 256, 256, 0, st, a);
 }
 void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta,
                            const float* offset, float* scale, float* bias, int C, cudaStream_t st) {
-  note_launch(), bn_eval_affine_kernel<<<(C + 255) / 256, 256, 0, st>>>(rm, rv, gamma, beta, offset, scale, bias, C);
+  launch_k(bn_eval_affine_kernel, (C + 255) / 256, 256, 0, st, rm, rv, gamma, beta, offset, scale, bias, C);
 }
 void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias, __half* a, int64_t rows, int C,
                           cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  note_launch(), bn_relu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, scale, bias, a, rows, C);
+  launch_k(bn_relu_apply_kernel, grid_for_rows(rows, rpb * 4), kThreads, 0, st, h, scale, bias, a, rows, C);
 }
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
@@ -1369,22 +1408,22 @@ void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, 
     cudaFuncSetAttribute(g_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  note_launch(), g_head_fwd_kernel<<<grid_for_rows(rows, kHeadRows, 148 * 3), kHeadRows, smem, st>>>(
+  launch_k(g_head_fwd_kernel, grid_for_rows(rows, kHeadRows, 148 * 3), kHeadRows, smem, st, 
       h2, scale, bias, w3, b3, p_out, pden_out, xc, tail_fake, rows, C, Kp, S);
 }
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 4);
   const int grid = grid_for_rows(a.rows, rpb * 2 * 4, kPartBlocks);
   if (apply) {
-    note_launch(), g_head_bwd_kernel<true><<<grid, kThreads, 0, st>>>(a);
+    launch_k(g_head_bwd_kernel<true>, grid, kThreads, 0, st, a);
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
     launch_reduce_partials(r, st);
   } else {
-    note_launch(), g_head_dpre_kernel<<<grid_for_rows(a.rows, kThreads, 148 * 2), kThreads, 0, st>>>(a);
-    note_launch(), g_head_bwd_kernel<false><<<grid, kThreads, 0, st>>>(a);
+    launch_k(g_head_dpre_kernel, grid_for_rows(a.rows, kThreads, 148 * 2), kThreads, 0, st, a);
+    launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, a);
     float* tot = a.part + (size_t)kPartBlocks * 8 * a.C;   // after the partial rows
-    note_launch(), g_head_moments_sum_kernel<<<dim3((a.C + 31) / 32, 8), 1024, 0, st>>>(a.part, grid, a.C, tot);
-    note_launch(), g_head_moments_finish_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(a, tot);
+    launch_k(g_head_moments_sum_kernel, dim3((a.C + 31) / 32, 8), 1024, 0, st, a.part, grid, a.C, tot);
+    launch_k(g_head_moments_finish_kernel, (a.C + 127) / 128, 128, 0, st, a, tot);
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
@@ -1392,14 +1431,14 @@ void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, 
                          float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
-  note_launch(), bn_bwd_stats_kernel<<<grid, kThreads, 0, st>>>(da, h, scale, bias, mean, rstd, part, rows, C);
+  launch_k(bn_bwd_stats_kernel, grid, kThreads, 0, st, da, h, scale, bias, mean, rstd, part, rows, C);
   ReduceArgs r{part, grid, 2 * C, 2, {{sum_dy, C, 1.f}, {sum_dyx, C, 1.f}}};
   launch_reduce_partials(r, st);
 }
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 4);
   const int grid = grid_for_rows(a.rows, rpb * kU * 2, kPartBlocks);
-  note_launch(), bn_bwd_apply_kernel<<<grid, kThreads, 0, st>>>(a);
+  launch_k(bn_bwd_apply_kernel, grid, kThreads, 0, st, a);
   if (a.dbias) {
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
     launch_reduce_partials(r, st);
@@ -1409,7 +1448,7 @@ void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __h
                      float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
-  note_launch(), d_l2_bwd_kernel<<<grid, kThreads, 0, st>>>(z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
+  launch_k(d_l2_bwd_kernel, grid, kThreads, 0, st, z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
   if (dw3 != nullptr) {
     ReduceArgs r{part, grid, 2 * C, 2, {{dw3, C, inv_gs}, {db2, C, inv_gs}}};
     launch_reduce_partials(r, st);
@@ -1417,38 +1456,38 @@ void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __h
 }
 void launch_f_l1(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb, __half* out,
                  int64_t rows, int C, cudaStream_t st) {
-  note_launch(), f_l1_kernel<<<grid_for_rows(rows, 8 * 4 * 2, 148 * 4), kThreads, 0, st>>>(p, w1, b1, lnw, lnb, out, rows, C);
+  launch_k(f_l1_kernel, grid_for_rows(rows, 8 * 4 * 2, 148 * 4), kThreads, 0, st, p, w1, b1, lnw, lnb, out, rows, C);
 }
 void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const float* gamma, const float* beta,
                            int64_t rows, int N, cudaStream_t st) {
   const int rpb = kThreads / (N / 8);
-  note_launch(), ln_lrelu_apply_kernel<<<grid_for_rows(rows, rpb * 4), kThreads, 0, st>>>(h, rowstats, n_tiles, gamma, beta, rows, N);
+  launch_k(ln_lrelu_apply_kernel, grid_for_rows(rows, rpb * 4), kThreads, 0, st, h, rowstats, n_tiles, gamma, beta, rows, N);
 }
 void launch_sumsq(const float* g, int64_t n, double* out, cudaStream_t st) {
   int grid = (int)((n + kThreads * 4 - 1) / (kThreads * 4));
   if (grid > 148 * 2) grid = 148 * 2;
   if (grid < 1) grid = 1;
-  note_launch(), sumsq_kernel<<<grid, kThreads, 0, st>>>(g, n, out);
+  launch_k(sumsq_kernel, grid, kThreads, 0, st, g, n, out);
 }
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st) {
   int grid = (int)((a.n + kThreads - 1) / kThreads);
   if (grid > 148 * 8) grid = 148 * 8;
-  note_launch(), clip_adam_kernel<<<grid, kThreads, 0, st>>>(a);
+  launch_k(clip_adam_kernel, grid, kThreads, 0, st, a);
 }
 void launch_dw_reduce(const float* part, int tiles_m, int tiles_n, int splits, float* dw, int ld, int m_valid,
                       int n_valid, float scale, int bias_col, float* db, cudaStream_t st) {
-  note_launch(), dw_reduce_kernel<<<dim3(tiles_n, m_valid), 256, 0, st>>>(part, tiles_m, tiles_n, splits, dw, ld, m_valid,
+  launch_k(dw_reduce_kernel, dim3(tiles_n, m_valid), 256, 0, st, part, tiles_m, tiles_n, splits, dw, ld, m_valid,
                                                                     n_valid, scale, bias_col, db);
 }
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,
                      cudaStream_t st) {
   const int total = rows * (S + P);
-  note_launch(), dw_fixup_kernel<<<(total + 255) / 256, 256, 0, st>>>(dw, ld, S, P, db, cvec, rows);
+  launch_k(dw_fixup_kernel, (total + 255) / 256, 256, 0, st, dw, ld, S, P, db, cvec, rows);
 }
-void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { note_launch(), loss_finalize_kernel<<<1, 32, 0, st>>>(a); }
+void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { launch_k(loss_finalize_kernel, 1, 32, 0, st, a); }
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st) {
-  note_launch(), score_finish_kernel<<<(int)((rows + 255) / 256), 256, 0, st>>>(p, err, rows, P, violations, consistency);
+  launch_k(score_finish_kernel, (int)((rows + 255) / 256), 256, 0, st, p, err, rows, P, violations, consistency);
 }
 
 }  // namespace pigan

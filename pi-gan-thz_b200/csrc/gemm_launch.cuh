@@ -28,22 +28,24 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   int grid = units < ctas ? units : ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if constexpr (Epi::CLUSTER > 1) {
     // clusters of CLUSTER CTAs share an m-tile (n_group = cluster rank): the grid must be a multiple of it
     if (g.k_splits != 1 || g.num_n_groups != (g.pair_mode ? 2 : 1) * Epi::CLUSTER)
       return fail(PIGAN_ERR_INVALID, "cluster epilogue needs num_n_groups == cluster size (x2 in pair mode)");
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = Epi::CLUSTER;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = Epi::CLUSTER;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     // clusters must be co-resident inside a GPC: on B200 only 33 clusters of 4 (132 of 148 SMs) fit at once
     static int max_clusters = 0;
     if (max_clusters == 0) {
@@ -55,11 +57,18 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
     if (grid > max_clusters * Epi::CLUSTER) grid = max_clusters * Epi::CLUSTER;
     grid -= grid % Epi::CLUSTER;
     cfg.gridDim = dim3(grid);
-    note_launch();
-    PIGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx ? *tx : tb, g, ep));
-  } else {
-    note_launch(), kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES, st>>>(ta, tb, tx ? *tx : tb, g, ep);
   }
+  if (pdl_enabled()) {
+    // programmatic dependent launch: this kernel's CTAs may start (barrier init, tensor-memory allocation) while
+    // the previous kernel on the stream drains; the kernel executes griddepcontrol.wait before it touches memory
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  note_launch();
+  PIGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx ? *tx : tb, g, ep));
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

@@ -184,6 +184,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   if constexpr (Epi::CLUSTER > 1) cluster_sync_all();  // the peer's barriers exist before anyone arrives on them
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // launched as a programmatic dependent (gemm_launch.cuh): everything above overlapped the previous kernel's tail;
+  // from here on its results are read and its inputs overwritten.  No-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================================================================== TMA producer

@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include <cstdlib>
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
@@ -25,6 +26,13 @@ static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("PIGAN_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
 int sm_count() {
   static int cached_dev = -1;
   static int cached = 0;

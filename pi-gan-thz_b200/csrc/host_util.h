@@ -37,6 +37,7 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 void note_launch();          // every kernel launch of the library passes through here (pigan_launch_count)
+bool pdl_enabled();         // programmatic dependent launch between consecutive kernels (PIGAN_PDL=0 disables)
 int sm_count();  // multiprocessors of the current device (cached per device)
 
 // Row-major 2-D fp16 tensor [outer, inner] with row pitch ld_elems; box = [box_outer, box_inner],
@@ -47,6 +48,24 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 // Row-major 2-D fp32 tensor, box = [box_outer, 32 floats] (128 B rows), 128B swizzle: TMA-store target of fp32 tiles.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_outer);
+
+// Launches `kern` as a programmatic dependent of the previous kernel on the stream (when enabled): its blocks may be
+// scheduled while that kernel drains.  Every kernel launched this way starts with griddepcontrol.wait (pdl_wait()).
+template <class... Exp, class... Act>
+inline void launch_k(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  note_launch();
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Act&&>(args)...);   // errors surface at the caller's cudaGetLastError
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
