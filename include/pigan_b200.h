@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 2
+#define PIGAN_ABI_VERSION 3
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -233,6 +233,51 @@ int pigan_inverse_design_search(PiganEngine* engine, const float* g_params, cons
                                 int64_t count, int32_t k, float* out_scores, int64_t* out_indices,
                                 float* out_params_norm, float* noise_dump, void* workspace, size_t workspace_bytes,
                                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Forward-surrogate training step — replaces the loop body of pretrain_forward_model,
+ * /root/reference/core/train/pretrain_fwd_model.py:68-92: F in train mode (forward_model.py:28-57, Dropout 0.2),
+ * loss = MSE(spectrum) + MSE(metrics) (:80-84), backward, clip_grad_norm_(1.0) (:90), Adam(lr) (:43, :91).
+ * Dropout keep-masks are counter based (Philox4x32-10 keyed by dropout_seed, counter = (first_row + row,
+ * layer * 4096 + column / 8, step); a column is dropped when its 16 random bits < round(p * 65536)), so the
+ * same (seed, step, global row) gives the same mask for any sharding; torch's own RNG stream is not reproduced.
+ * Parameters / Adam state: flat fp32 buffers in state_dict order (model.0.weight, model.0.bias, model.1.weight,
+ * ... model.20.bias), 1 385 730 floats for the reference widths.
+ *   losses [3] (device): total, spectrum, metrics — means over global_batch rows.
+ *   loss_sums: NULL, or [2] device floats that receive this rank's sums of squares in phase 0 (all-reduce them,
+ *              and f_grads, between the phases when training data-parallel).
+ *   mask_dump: NULL, or [sum_i H_i][...] bytes laid out layer after layer, layer i as [batch, H_i] keep flags (tests).
+ * The step reuses the engine's surrogate activations and packed weights: afterwards the frozen surrogate is
+ * unloaded, call pigan_engine_load_forward_model again before pigan_train_step / scoring.
+ * workspace: pigan_fwd_train_workspace_bytes(engine) bytes of device memory, 256-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PiganFwdTrainArgs {
+  const float* params_norm;   /* [batch, param_dim]    inputs of F (data_loader.py:185-196 normalisation) */
+  const float* spectrum;      /* [batch, spectrum_dim] regression target 1 */
+  const float* metrics_norm;  /* [batch, metrics_dim]  regression target 2 */
+  int64_t batch;              /* local rows */
+  int64_t global_batch;       /* rows over all ranks (loss means and gradient scale) */
+  int64_t first_row;          /* global index of local row 0 (Dropout counter) */
+  float* f_params;
+  float* f_grads;             /* out: unclipped after phase 0, clipped after phase 1 (as torch leaves .grad) */
+  float* f_exp_avg;
+  float* f_exp_avg_sq;
+  float lr;
+  int64_t step;               /* Adam t, 1-based; also the Dropout counter word */
+  float beta1, beta2, eps;    /* torch defaults 0.9, 0.999, 1e-8 (pretrain_fwd_model.py:43) */
+  float max_norm;             /* 1.0 (pretrain_fwd_model.py:90) */
+  float dropout_p;            /* 0.2 (forward_model.py:33); 0 disables Dropout */
+  uint64_t dropout_seed;
+  float* losses;
+  float* loss_sums;
+  uint8_t* mask_dump;
+} PiganFwdTrainArgs;
+size_t pigan_fwd_train_workspace_bytes(const PiganEngine* engine);
+int pigan_fwd_train_step(PiganEngine* engine, const PiganFwdTrainArgs* args, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* phase 0: forward + loss + backward (local gradients, already divided by global_batch); phase 1: clip + Adam */
+int pigan_fwd_train_step_phase(PiganEngine* engine, const PiganFwdTrainArgs* args, int32_t phase, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* k smallest of scores[n] (k <= 4096, n < 2^32), ascending, ties by position; NaN sorts last.
  * out_indices[i] = in_indices[pos] when in_indices is given (merging gathered shard results), else

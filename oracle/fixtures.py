@@ -89,3 +89,13 @@ def sample_indices(numel: int, count: int = 2048) -> torch.Tensor:
     if numel <= count:
         return torch.arange(numel)
     return torch.linspace(0, numel - 1, count).long()
+
+
+F_HIDDEN = (256, 512, 1024, 512, 256)
+
+
+def make_dropout_masks(n: int, seed: int, p: float = 0.2):
+    """Keep-masks (float 0/1) for the five Dropout layers of the forward model, numpy PCG64 — the explicit stand-in
+    for torch's RNG stream when the reference's pretraining step is pinned (tools/make_golden.py: fwd_pretrain)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return [torch.from_numpy((rng.random((n, h)) >= p).astype(np.float32)) for h in F_HIDDEN]

@@ -1291,6 +1291,289 @@ __global__ void score_finish_kernel(const float* __restrict__ p, const float* __
   if (cons) cons[r] = 1.0f / (1.0f + err[r]);
 }
 
+
+// ------------------------------------------------------------------------------------------ surrogate training
+// Training-mode forward model (pretrain_fwd_model.py:68-92, forward_model.py:28-52): Linear -> LayerNorm ->
+// LeakyReLU -> Dropout(0.2).  The keep-mask is counter based: Philox4x32-10 keyed by the caller's seed, counter =
+// (global row, layer * 4096 + column / 8, step): 8 columns per call, 16 bits each, dropped when bits < p * 65536.
+// It depends only on (seed, step, global row, layer, column), so the backward pass regenerates it and the result
+// does not depend on how rows are sharded over GPUs.
+__device__ __forceinline__ unsigned int drop_keep8(const DropoutArgs& d, long long grow, int layer, int col8) {
+  const uint4 u = philox4x32_10(make_uint4((unsigned int)grow, (unsigned int)(grow >> 32),
+                                           (unsigned int)(layer * 4096 + col8), d.step),
+                                make_uint2((unsigned int)d.seed, (unsigned int)(d.seed >> 32)));
+  const unsigned int w[4] = {u.x, u.y, u.z, u.w};
+  unsigned int keep = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) keep |= (((w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu) >= d.thresh16 ? 1u : 0u) << i;
+  return keep;
+}
+
+// layer 1 (K = 4): a warp per row, a lane owns 8 of the 256 columns.  Writes xhat (normalised, pre-affine), the
+// post-dropout activation, 1/std per row and (tests) the keep-mask as bytes.
+__global__ void __launch_bounds__(kThreads) f_l1_train_kernel(const float* __restrict__ p, const float* __restrict__ w1,
+                                                              const float* __restrict__ b1,
+                                                              const float* __restrict__ lnw,
+                                                              const float* __restrict__ lnb, __half* __restrict__ xhat,
+                                                              __half* __restrict__ act, float* __restrict__ rstd_out,
+                                                              unsigned char* __restrict__ mask_out, long long rows,
+                                                              DropoutArgs dr) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  float4 wr[8];
+  float b[8], gm[8], bt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wr[i] = __ldg(reinterpret_cast<const float4*>(w1) + lane * 8 + i);
+  ld_f8(b1 + lane * 8, b);
+  ld_f8(lnw + lane * 8, gm);
+  ld_f8(lnb + lane * 8, bt);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
+    float h[8], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = fmaf(q.w, wr[i].w, fmaf(q.z, wr[i].z, fmaf(q.y, wr[i].y, fmaf(q.x, wr[i].x, b[i]))));
+      s += h[i];
+    }
+    const float mean = warp_sum_f(s) * (1.0f / 256.0f);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] -= mean;
+      v = fmaf(h[i], h[i], v);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(v) * (1.0f / 256.0f) + kLnEps);
+    const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, lane);
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] *= rstd;
+      a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[i], gm[i], bt[i])) * dr.keep_scale : 0.f;
+    }
+    st_h8(xhat + row * 256 + lane * 8, h);
+    st_h8(act + row * 256 + lane * 8, a);
+    if (lane == 0) rstd_out[row] = rstd;
+    if (mask_out) {
+      unsigned long long m = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
+      *reinterpret_cast<unsigned long long*>(mask_out + row * 256 + lane * 8) = m;
+    }
+  }
+}
+
+// layers 2..5: h (fp16 Linear output incl. bias, in `xhat`) + fp32 row partials from the GEMM epilogue -> xhat in
+// place, activation, 1/std.  A warp per row, NCH = N / 256 chunks of 8 columns per lane.
+template <int NCH>
+__global__ void __launch_bounds__(kThreads) ln_train_kernel(__half* __restrict__ xhat, const float* __restrict__ rowstats,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __half* __restrict__ act,
+                                                            float* __restrict__ rstd_out,
+                                                            unsigned char* __restrict__ mask_out, long long rows,
+                                                            int layer, DropoutArgs dr) {
+  pdl_wait();
+  constexpr int N = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(rowstats) + row * NCH + t);
+      s1 += st.x;
+      s2 += st.y;
+    }
+    const float mean = s1 * (1.0f / N);
+    const float rstd = 1.0f / sqrtf(fmaxf(s2 * (1.0f / N) - mean * mean, 0.f) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float h[8], gm[8], bt[8], a[8];
+      ld_h8(xhat + row * N + c0, h);
+      ld_f8(gamma + c0, gm);
+      ld_f8(beta + c0, bt);
+      const unsigned int keep = drop_keep8(dr, dr.first_row + row, layer, c0 >> 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[i] = (h[i] - mean) * rstd;
+        a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[i], gm[i], bt[i])) * dr.keep_scale : 0.f;
+      }
+      st_h8(xhat + row * N + c0, h);
+      st_h8(act + row * N + c0, a);
+      if (mask_out) {
+        unsigned long long m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
+        *reinterpret_cast<unsigned long long*>(mask_out + row * N + c0) = m;
+      }
+    }
+    if (lane == 0) rstd_out[row] = rstd;
+  }
+}
+
+// Output layer loss: out [rows, S + Mt] fp32 against the spectrum / normalised metrics (MSELoss means,
+// pretrain_fwd_model.py:80-84).  dout (fp16, ld columns, zero padded) = d(loss_spec + loss_metrics)/d(out) * GS
+// (GS = global batch: every gradient of the step carries that scale until dw_reduce / the partial reductions remove
+// it, which keeps the fp16 operands in range).  Per block: column sums of dout (bias gradient) and the two sums
+// of squares go to part[block][0 .. S+Mt) and part[block][ld_part - 2 .. ld_part).
+__global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __restrict__ out,
+                                                              const float* __restrict__ spectrum,
+                                                              const float* __restrict__ metrics,
+                                                              __half* __restrict__ dout, int ld, long long rows, int S,
+                                                              int Mt, float* __restrict__ part, int ld_part) {
+  pdl_wait();
+  __shared__ float sm[8][328];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OUT = S + Mt;
+  const float gs_spec = 2.0f / (float)S, gs_met = 2.0f / (float)Mt;
+  constexpr int J = 10;   // column slots per lane: covers ld <= 320
+  float colsum[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) colsum[j] = 0.f;
+  float sq_spec = 0.f, sq_met = 0.f;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = j * 32 + lane;
+      if (c >= ld) continue;
+      float g = 0.f;
+      if (c < OUT) {
+        const float t = c < S ? __ldg(spectrum + row * S + c) : __ldg(metrics + row * Mt + (c - S));
+        const float d = out[row * OUT + c] - t;
+        if (c < S) sq_spec = fmaf(d, d, sq_spec);
+        else sq_met = fmaf(d, d, sq_met);
+        g = d * (c < S ? gs_spec : gs_met);
+      }
+      dout[row * ld + c] = __float2half_rn(g);
+      colsum[j] += g;
+    }
+  }
+  sq_spec = warp_sum_f(sq_spec);
+  sq_met = warp_sum_f(sq_met);
+#pragma unroll
+  for (int j = 0; j < J; ++j) sm[warp][j * 32 + lane] = colsum[j];
+  if (lane == 0) {
+    sm[warp][320] = sq_spec;
+    sm[warp][321] = sq_met;
+  }
+  __syncthreads();
+  float* prow = part + (size_t)blockIdx.x * ld_part;
+  for (int c = threadIdx.x; c < ld_part; c += blockDim.x) {
+    const int src = c >= ld_part - 2 ? 320 + (c - (ld_part - 2)) : c;
+    float t = 0.f;
+    if (src < 322 && (c < OUT || c >= ld_part - 2))
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) t += sm[wq][src];
+    prow[c] = t;
+  }
+}
+
+// Backward through Dropout, LeakyReLU and LayerNorm of one surrogate layer, a warp per row:
+//   dact = da * keep / (1 - p);  dy = dact * (y > 0 ? 1 : 0.2), y = gamma * xhat + beta;  dxh = dy * gamma
+//   dh = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat))                      (written over da)
+// and per-column sums over the rows for dbeta (dy), dgamma (dy * xhat), dbias (dh) -- FIRST: also dW1 (dh * p_j) --
+// as per-block partials part[block][k * N + c], k = 0..2 (3..6), finished by reduce_partials_kernel.
+template <int NCH, bool FIRST>
+__global__ void __launch_bounds__(kThreads) ln_bwd_kernel(__half* __restrict__ da, const __half* __restrict__ xhat,
+                                                          const float* __restrict__ rstd_in,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ p_in, long long rows, int layer,
+                                                          DropoutArgs dr, float* __restrict__ part) {
+  pdl_wait();
+  constexpr int N = NCH * 256;
+  constexpr int NQ = FIRST ? 7 : 3;
+  __shared__ float sm[NQ * N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[NCH][NQ][8];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) zero8(acc[j][k]);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
+    float dxh[NCH][8], xh[NCH][8];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float g[8], gm[8], bt[8];
+      ld_h8(da + row * N + c0, g);
+      ld_h8(xhat + row * N + c0, xh[j]);
+      ld_f8(gamma + c0, gm);
+      ld_f8(beta + c0, bt);
+      const unsigned int keep = drop_keep8(dr, dr.first_row + row, layer, c0 >> 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(xh[j][i], gm[i], bt[i]);
+        const float dy = (keep >> i) & 1u ? g[i] * dr.keep_scale * (y > 0.f ? 1.f : kSlope) : 0.f;
+        acc[j][0][i] += dy;
+        acc[j][1][i] = fmaf(dy, xh[j][i], acc[j][1][i]);
+        const float t = dy * gm[i];
+        dxh[j][i] = t;
+        m1 += t;
+        m2 = fmaf(t, xh[j][i], m2);
+      }
+    }
+    m1 = warp_sum_f(m1) * (1.0f / N);
+    m2 = warp_sum_f(m2) * (1.0f / N);
+    const float rstd = __ldg(rstd_in + row);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (FIRST) q = __ldg(reinterpret_cast<const float4*>(p_in) + row);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float dh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dh[i] = rstd * (dxh[j][i] - m1 - xh[j][i] * m2);
+        acc[j][2][i] += dh[i];
+        if constexpr (FIRST) {
+          acc[j][3][i] = fmaf(dh[i], q.x, acc[j][3][i]);
+          acc[j][4][i] = fmaf(dh[i], q.y, acc[j][4][i]);
+          acc[j][5][i] = fmaf(dh[i], q.z, acc[j][5][i]);
+          acc[j][6][i] = fmaf(dh[i], q.w, acc[j][6][i]);
+        }
+      }
+      if constexpr (!FIRST) st_h8(da + row * N + j * 256 + lane * 8, dh);
+    }
+  }
+  // block combine in a fixed warp order (deterministic), then this block's row of the partial scratch
+  for (int i = threadIdx.x; i < NQ * N; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (int wq = 0; wq < 8; ++wq) {
+    if (warp == wq) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm[k * N + j * 256 + lane * 8 + i] += acc[j][k][i];
+    }
+    __syncthreads();
+  }
+  float* prow = part + (size_t)blockIdx.x * (NQ * N);
+  for (int i = threadIdx.x; i < NQ * N; i += blockDim.x) prow[i] = sm[i];
+}
+
+// dW1 arrives from the partial reduction as [4][256] (k-major); the state_dict layout is [256][4]
+__global__ void f_dw1_transpose_kernel(const float* __restrict__ src, float* __restrict__ dw1) {
+  pdl_wait();
+  const int c = threadIdx.x;   // 256 threads
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dw1[c * 4 + j] = src[j * 256 + c];
+}
+
+__global__ void f_train_losses_kernel(const float* __restrict__ sums, double n_spec, double n_met, float* out) {
+  pdl_wait();
+  if (threadIdx.x != 0) return;
+  const float ls = (float)((double)sums[0] / n_spec), lm = (float)((double)sums[1] / n_met);
+  out[0] = ls + lm;
+  out[1] = ls;
+  out[2] = lm;
+}
+
 }  // namespace
 
 // =========================================================================================== launchers
@@ -1488,6 +1771,62 @@ void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { launch_k
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st) {
   launch_k(score_finish_kernel, (int)((rows + 255) / 256), 256, 0, st, p, err, rows, P, violations, consistency);
+}
+
+
+void launch_f_l1_train(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
+                       __half* xhat, __half* act, float* rstd, unsigned char* mask, int64_t rows,
+                       const DropoutArgs& dr, cudaStream_t st) {
+  launch_k(f_l1_train_kernel, grid_for_rows(rows, 8 * 8, 148 * 4), kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd,
+           mask, (long long)rows, dr);
+}
+void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, const float* beta, __half* act,
+                     float* rstd, unsigned char* mask, int64_t rows, int N, int layer, const DropoutArgs& dr,
+                     cudaStream_t st) {
+  const int grid = grid_for_rows(rows, 8 * 4, 148 * 4);
+  if (N == 256) launch_k(ln_train_kernel<1>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
+  else if (N == 512) launch_k(ln_train_kernel<2>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
+  else launch_k(ln_train_kernel<4>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
+}
+void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
+                       int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
+                       cudaStream_t st) {
+  const int OUT = S + Mt, ld_part = (OUT + 2 + 7) / 8 * 8;
+  const int grid = grid_for_rows(rows, 8 * 8, kPartBlocks);
+  launch_k(f_out_loss_kernel, grid, kThreads, 0, st, out, spectrum, metrics, dout, ld, (long long)rows, S, Mt, part,
+           ld_part);
+  ReduceArgs r;
+  r.part = part; r.nblocks = grid; r.ld = ld_part; r.nseg = 3;
+  r.seg[0] = {db_out, OUT, inv_gs};
+  r.seg[1] = {nullptr, ld_part - 2 - OUT, 0.f};
+  r.seg[2] = {loss_sums, 2, 1.f};
+  launch_reduce_partials(r, st);
+}
+void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const float* gamma, const float* beta,
+                   const float* p_in, int64_t rows, int N, int layer, const DropoutArgs& dr, float* part,
+                   float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs, cudaStream_t st) {
+  // partial rows are NQ * N floats wide: keep nblocks * NQ * N inside the scratch (kPartBlocks * kPartCols floats)
+  const int nq = p_in ? 7 : 3;
+  int cap = (int)(((size_t)kPartBlocks * kPartCols) / ((size_t)nq * N));
+  if (cap > 148 * 2) cap = 148 * 2;
+  const int grid = grid_for_rows(rows, 8 * 4, cap);
+  if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
+  else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
+  else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
+  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
+  ReduceArgs r;
+  r.part = part; r.nblocks = grid; r.ld = nq * N; r.nseg = p_in ? 4 : 3;
+  r.seg[0] = {dbeta, N, inv_gs};
+  r.seg[1] = {dgamma, N, inv_gs};
+  r.seg[2] = {dbias, N, inv_gs};
+  if (p_in) r.seg[3] = {dw1_kmajor, 4 * N, inv_gs};
+  launch_reduce_partials(r, st);
+}
+void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st) {
+  launch_k(f_dw1_transpose_kernel, 1, 256, 0, st, src, dw1);
+}
+void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st) {
+  launch_k(f_train_losses_kernel, 1, 32, 0, st, sums, n_spec, n_met, out);
 }
 
 }  // namespace pigan

@@ -279,9 +279,9 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
 // dw[m_out, ld] += (1/gs) * a[kd, m_out]^T b[.., n]
 int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t b_rows, int n, float* dw, int ld,
                 int n_valid, float inv_gs, int bias_col, float* db, int64_t wrap_rows, const __half* b_tail,
-                int64_t tail_from_row, float* part, cudaStream_t st) {
+                int64_t tail_from_row, float* part, cudaStream_t st, int lda = 0) {
   CUtensorMap ta, tb, tx;
-  PIGAN_TRY(make_nt_maps(&ta, &tb, a, (int)kd, m_out, m_out, b, (int)b_rows, n, n));
+  PIGAN_TRY(make_nt_maps(&ta, &tb, a, (int)kd, m_out, lda > 0 ? lda : m_out, b, (int)b_rows, n, n));
   const int tiles_m = ceil_div(m_out, kBlockM), tiles_n = ceil_div(n, 256);
   const int tiles = tiles_m * tiles_n;
   int splits = sm_count() / (tiles > 0 ? tiles : 1);
@@ -481,6 +481,7 @@ struct FOutOpts {
   float* row_err;
   int f1_idx, f2_idx;
 };
+int f_out_layer(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st);
 int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o, cudaStream_t st,
               bool have_a1 = false) {
   if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
@@ -495,6 +496,11 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
     PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], hp + L.b[i], hp + L.ln_w[i], hp + L.ln_b[i],
                         acts[i], st));
   }
+  return f_out_layer(e, e->f_a5, n, o, st);
+}
+// Output layer (forward_model.py:55) with the fused loss / error epilogue; weights from e->f_wh[5], e->f_bias_out
+int f_out_layer(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
   using Epi = EpiFwdOut<CfgO>;
   Epi::Params ep;
   ep.bias = e->f_bias_out;
@@ -514,7 +520,7 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   ep.f1_idx = o.f1_idx;
   ep.f2_idx = o.f2_idx;
   PM("f_out_gemm");
-  PIGAN_TRY((run_tn<CfgO, Epi>(ep, e->f_a5, n, L.H[4], L.H[4], e->f_wh[5], L.OUT, L.H[4], st)));
+  PIGAN_TRY((run_tn<CfgO, Epi>(ep, a5, n, L.H[4], L.H[4], e->f_wh[5], L.OUT, L.H[4], st)));
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -941,6 +947,186 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
   PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ surrogate training
+// One optimiser step of pretrain_forward_model (core/train/pretrain_fwd_model.py:68-92): F in train
+// mode (Dropout 0.2, counter based), MSE(spectrum) + MSE(metrics), backward through all six layers, clip 1.0, Adam.
+//   phase 0: zero grads, pack weights, forward, loss, backward -> f_grads (local rows, already divided by the
+//            global batch) and loss_sums (local sums of squares)          [data parallel: all-reduce both here]
+//   phase 1: clip_grad_norm_ + Adam + the three reported losses
+// Activations a_i reuse the engine's f_a1..f_a5 and packed-weight buffers, so the frozen-surrogate state of the
+// engine is invalidated: call pigan_engine_load_forward_model again before PI-GAN steps or scoring.
+namespace {
+constexpr int kDoutLd = 320;   // output-layer gradient operand: S + Mt = 258 columns padded to a multiple of 64
+struct FTrainWs {
+  __half* xhat[5];
+  float* rstd[5];
+  float* out32;
+  __half* dout;
+  __half* dbuf[2];
+  __half* wth[6];     // transposed fp16 weights: [in_i, out_i] (layer 5: [256, kDoutLd])
+  float* dw1_tmp;     // [4][256]
+  double* sumsq;
+  float* loss_sums;   // [2] (used when the caller passes none)
+  uint8_t* zero_from; // dw1_tmp .. loss_sums are cleared every step
+  size_t zero_bytes;
+  size_t carve(void* base, const FwdLayout& L, int64_t B) {
+    Carver c(base);
+    const int64_t Bp = round_up(B, 128);
+    int wmax = 0;
+    for (int i = 0; i < 5; ++i) {
+      xhat[i] = c.take<__half>((size_t)Bp * L.H[i]);
+      rstd[i] = c.take<float>(Bp);
+      wmax = L.H[i] > wmax ? L.H[i] : wmax;
+    }
+    out32 = c.take<float>((size_t)Bp * L.OUT);
+    dout = c.take<__half>((size_t)Bp * kDoutLd);
+    dbuf[0] = c.take<__half>((size_t)Bp * wmax);
+    dbuf[1] = c.take<__half>((size_t)Bp * wmax);
+    wth[0] = nullptr;
+    for (int i = 1; i < 5; ++i) wth[i] = c.take<__half>((size_t)L.H[i - 1] * L.H[i]);
+    wth[5] = c.take<__half>((size_t)L.H[4] * kDoutLd);
+    dw1_tmp = c.take<float>(4 * L.H[0]);
+    zero_from = reinterpret_cast<uint8_t*>(dw1_tmp);
+    sumsq = c.take<double>(1);
+    loss_sums = c.take<float>(2);
+    zero_bytes = base ? (size_t)(reinterpret_cast<uint8_t*>(loss_sums + 2) - zero_from) : 0;
+    return (c.off + 255) & ~size_t(255);
+  }
+};
+
+int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrainWs& w, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
+  const int64_t n = a.batch;
+  float* fp = a.f_params;
+  float* gr = a.f_grads;
+  float* loss_sums = a.loss_sums ? a.loss_sums : w.loss_sums;
+  const float inv_gs = (float)(1.0 / (double)a.global_batch);
+  if (phase == 1) {
+    PM("clip_adam");
+    launch_sumsq(gr, L.total, w.sumsq, st);
+    AdamArgs ad{fp, gr, a.f_exp_avg, a.f_exp_avg_sq, L.total, a.lr, a.beta1, a.beta2, a.eps,
+                1.0 - pow((double)a.beta1, (double)a.step), 1.0 - pow((double)a.beta2, (double)a.step), w.sumsq,
+                a.max_norm};
+    launch_clip_adam(ad, st);
+    launch_f_train_losses(loss_sums, (double)a.global_batch * L.S, (double)a.global_batch * L.Mt, a.losses, st);
+    PM(nullptr);
+    PIGAN_CUDA_OK(cudaGetLastError());
+    return PIGAN_OK;
+  }
+  DropoutArgs dr;
+  dr.seed = a.dropout_seed;
+  dr.first_row = a.first_row;
+  dr.step = (unsigned int)a.step;
+  dr.thresh16 = (unsigned int)lround((double)a.dropout_p * 65536.0);
+  dr.keep_scale = 1.0f / (1.0f - a.dropout_p);
+  e->f_loaded = false;   // the packed weights below replace the frozen surrogate's
+  PM("memset");
+  PIGAN_CUDA_OK(cudaMemsetAsync(gr, 0, (size_t)L.total * sizeof(float), st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(w.zero_from, 0, w.zero_bytes, st));
+  if (a.loss_sums) PIGAN_CUDA_OK(cudaMemsetAsync(a.loss_sums, 0, 2 * sizeof(float), st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(w.wth[5], 0, (size_t)L.H[4] * kDoutLd * sizeof(__half), st));
+  PM("pack_weights");
+  for (int i = 1; i < 6; ++i) {
+    const int in = L.H[i - 1], out = i < 5 ? L.H[i] : L.OUT;
+    launch_cast_pad(fp + L.w[i], in, in, e->f_wh[i], in, out, st);
+    launch_transpose_cast(fp + L.w[i], out, in, in, w.wth[i], i < 5 ? out : kDoutLd, st);
+  }
+  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
+  // ---- forward (train mode)
+  __half* act[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
+  size_t moff[5];
+  int hsum = 0;
+  for (int i = 0; i < 5; ++i) {
+    moff[i] = (size_t)hsum * (size_t)n;
+    hsum += L.H[i];
+  }
+  auto mask = [&](int i) { return a.mask_dump ? a.mask_dump + moff[i] : nullptr; };
+  PM("f_l1");
+  launch_f_l1_train(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
+                    w.rstd[0], mask(0), n, dr, st);
+  for (int i = 1; i < 5; ++i) {
+    PM("f_hidden_gemm");
+    PIGAN_TRY((linear_store<true, false, true>(act[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], w.xhat[i],
+                                               e->f_rowstats, st)));
+    PM("f_ln_dropout");
+    launch_ln_train(w.xhat[i], e->f_rowstats, fp + L.ln_w[i], fp + L.ln_b[i], act[i], w.rstd[i], mask(i), n, L.H[i], i,
+                    dr, st);
+  }
+  PM("f_out_gemm");
+  FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, w.out32, nullptr, 0, 1};
+  PIGAN_TRY(f_out_layer(e, act[4], n, fo, st));
+  PM("f_out_loss");
+  launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
+                    loss_sums, inv_gs, st);
+  // ---- backward
+  PM("f_wgrad_gemm");
+  PIGAN_TRY(weight_grad(w.dout, n, L.OUT, act[4], n, L.H[4], gr + L.w[5], L.H[4], L.H[4], inv_gs, -1, nullptr, 0,
+                        nullptr, 0, e->dw_part, st, kDoutLd));
+  PM("f_dgrad_gemm");
+  __half* d = w.dbuf[0];
+  __half* d2 = w.dbuf[1];
+  PIGAN_TRY((linear_store<false, false, false>(w.dout, n, kDoutLd, w.wth[5], L.H[4], nullptr, d, nullptr, st)));
+  for (int i = 4; i >= 0; --i) {
+    PM("f_ln_bwd");
+    launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], i == 0 ? a.params_norm : nullptr, n, L.H[i],
+                  i, dr, e->partials, gr + L.ln_w[i], gr + L.ln_b[i], gr + L.b[i], w.dw1_tmp, inv_gs, st);
+    if (i == 0) {
+      launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
+      break;
+    }
+    PM("f_wgrad_gemm");
+    PIGAN_TRY(weight_grad(d, n, L.H[i], act[i - 1], n, L.H[i - 1], gr + L.w[i], L.H[i - 1], L.H[i - 1], inv_gs, -1,
+                          nullptr, 0, nullptr, 0, e->dw_part, st));
+    PM("f_dgrad_gemm");
+    PIGAN_TRY((linear_store<false, false, false>(d, n, L.H[i], w.wth[i], L.H[i - 1], nullptr, d2, nullptr, st)));
+    __half* t = d;
+    d = d2;
+    d2 = t;
+  }
+  PM(nullptr);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+int check_fwd_train_args(const PiganEngine* e, const PiganFwdTrainArgs* a, const void* ws, size_t ws_bytes) {
+  PIGAN_CHECK_ARG(e != nullptr && a != nullptr && ws != nullptr);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0);
+  PIGAN_CHECK_ARG(a->batch >= 1 && a->batch <= e->max_batch && a->global_batch >= a->batch && a->first_row >= 0);
+  PIGAN_CHECK_ARG(a->params_norm && a->spectrum && a->metrics_norm && a->losses);
+  PIGAN_CHECK_ARG(a->f_params && a->f_grads && a->f_exp_avg && a->f_exp_avg_sq);
+  PIGAN_CHECK_ARG(a->step >= 1 && a->dropout_p >= 0.f && a->dropout_p < 1.f);
+  PIGAN_CHECK_ARG(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->max_norm > 0.f);
+  FTrainWs w;
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  if (ws_bytes < need) return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", ws_bytes, need);
+  return PIGAN_OK;
+}
+}  // namespace
+
+extern "C" size_t pigan_fwd_train_workspace_bytes(const PiganEngine* e) {
+  if (!e) return 0;
+  FTrainWs w;
+  return w.carve(nullptr, e->fl, e->max_batch);
+}
+
+extern "C" int pigan_fwd_train_step_phase(PiganEngine* e, const PiganFwdTrainArgs* a, int32_t phase, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  PIGAN_TRY(check_fwd_train_args(e, a, workspace, workspace_bytes));
+  if (phase < 0 || phase > 1) return fail(PIGAN_ERR_INVALID, "surrogate-training phase %d out of range", phase);
+  FTrainWs w;
+  w.carve(workspace, e->fl, e->max_batch);
+  return fwd_train_phase(e, *a, phase, w, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pigan_fwd_train_step(PiganEngine* e, const PiganFwdTrainArgs* a, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  PIGAN_TRY(check_fwd_train_args(e, a, workspace, workspace_bytes));
+  FTrainWs w;
+  w.carve(workspace, e->fl, e->max_batch);
+  for (int ph = 0; ph <= 1; ++ph) PIGAN_TRY(fwd_train_phase(e, *a, ph, w, static_cast<cudaStream_t>(stream)));
   return PIGAN_OK;
 }
 

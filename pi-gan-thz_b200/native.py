@@ -50,6 +50,19 @@ class PiganDims(C.Structure):
     ]
 
 
+class PiganFwdTrainArgs(C.Structure):
+    """include/pigan_b200.h: struct PiganFwdTrainArgs (surrogate training step)."""
+    _fields_ = [
+        ("params_norm", C.c_void_p), ("spectrum", C.c_void_p), ("metrics_norm", C.c_void_p),
+        ("batch", C.c_int64), ("global_batch", C.c_int64), ("first_row", C.c_int64),
+        ("f_params", C.c_void_p), ("f_grads", C.c_void_p), ("f_exp_avg", C.c_void_p), ("f_exp_avg_sq", C.c_void_p),
+        ("lr", C.c_float), ("step", C.c_int64),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("max_norm", C.c_float),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("losses", C.c_void_p), ("loss_sums", C.c_void_p), ("mask_dump", C.c_void_p),
+    ]
+
+
 class PiganTrainArgs(C.Structure):
     _fields_ = [
         ("spectrum", _vp), ("params_denorm", _vp), ("metrics_norm", _vp),
@@ -107,6 +120,9 @@ SIGNATURES = {
     "pigan_search_workspace_bytes": (C.c_size_t, [_vp, _i32]),
     "pigan_inverse_design_search": (_i32, [_vp, _vp, _vp, _vp, _f32, C.c_uint64, _i64, _i64, _i32, _vp, _vp, _vp, _vp,
                                            _vp, C.c_size_t, _vp]),
+    "pigan_fwd_train_workspace_bytes": (C.c_size_t, [_vp]),
+    "pigan_fwd_train_step": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _vp, C.c_size_t, _vp]),
+    "pigan_fwd_train_step_phase": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _i32, _vp, C.c_size_t, _vp]),
     "pigan_topk_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "pigan_topk_smallest": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),

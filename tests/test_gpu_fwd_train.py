@@ -1,0 +1,198 @@
+"""Parity of the surrogate-training step (pigan_fwd_train_step) with the CPU oracle
+(oracle/models.py: pretrain_step, itself pinned to the reference's pretrain_forward_model by
+tests/test_oracle_golden.py::test_pretrain_step_matches_reference_loop).
+
+Dropout: the kernels draw counter-based keep-masks and dump them (mask_dump); the oracle replays exactly those, so
+the comparison is deterministic.  Tolerances as in test_gpu_engine.py: fp16 operands / fp32 accumulation, losses
+1e-3.  Gradients are compared norm-wise; their error is per-sample fp16 rounding noise of the six GEMM layers each
+way, so it averages out with the batch (measured, whole gradient: 5.4e-3 at B=64, 1.9e-3 at 1024, 9.4e-4 at 4096 —
+tools/fwd_train_diag.py) and grows from the output layer (3e-4) down to the first one: the bound depends on B.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pi-gan-thz_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+DEV = "cuda"
+HID = (256, 512, 1024, 512, 256)
+TOL_LOSS = 1e-3
+TOL_GRAD = {64: 8e-3, 130: 6e-3, 1024: 3e-3}   # whole gradient, by batch size; single tensors 6x
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _setup(B, seed=11, dropout_p=0.2, max_batch=None):
+    from core.models.forward_model import ForwardModel
+    from oracle import fixtures
+    from pigan_b200.fwd_trainer import ForwardTrainer
+    _, _, f_sd = fixtures.make_weights(42)
+    F = ForwardModel(4, 250, 8)
+    F.load_state_dict(f_sd)
+    tr = ForwardTrainer(F, DEV, max_batch=max_batch or B, dropout_p=dropout_p, seed=1234)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=seed)
+    return tr, F, f_sd, (pnorm, spec, mnorm)
+
+
+def _masks(dump, B):
+    out, off = [], 0
+    for h in HID:
+        out.append(dump[off:off + B * h].view(B, h).float().cpu())
+        off += B * h
+    return out
+
+
+def _names():
+    from oracle import models as O
+    return [f"model.{i}.{s}" for i in sorted(O.F_LINEAR + O.F_NORM) for s in ("weight", "bias")]
+
+
+@pytest.mark.parametrize("B", [64, 130, 1024])
+def test_step_matches_oracle(B):
+    """Losses, unclipped gradients (phase 0) and the Adam update (phase 1) of one step, incl. a ragged batch."""
+    import ctypes as C
+    from oracle import models as O
+    from pigan_b200 import native
+    tr, F, f_sd, (pn, spec, mn) = _setup(B)
+    dump = torch.zeros(sum(HID) * B, dtype=torch.uint8, device=DEV)
+    png, sg, mng = pn.to(DEV), spec.to(DEV), mn.to(DEV)
+    # phase 0 by hand to look at the raw gradients, then the public step on a twin for the update
+    a = native.PiganFwdTrainArgs()
+    a.params_norm, a.spectrum, a.metrics_norm = png.data_ptr(), sg.data_ptr(), mng.data_ptr()
+    a.batch = a.global_batch = B
+    a.first_row = 0
+    a.f_params = tr.fs.params.tensor().data_ptr()
+    a.f_grads, a.f_exp_avg, a.f_exp_avg_sq = tr.grads.data_ptr(), tr.m.data_ptr(), tr.v.data_ptr()
+    a.lr, a.step, a.beta1, a.beta2, a.eps, a.max_norm = 1e-3, 1, 0.9, 0.999, 1e-8, 1.0
+    a.dropout_p, a.dropout_seed = 0.2, 1234
+    a.losses, a.loss_sums, a.mask_dump = tr.losses.data_ptr(), tr.loss_sums.data_ptr(), dump.data_ptr()
+    ws, nb, st = tr.workspace.data_ptr(), tr.workspace.numel(), native.current_stream()
+    native.check(native.lib.pigan_fwd_train_step_phase(tr.engine.handle, C.byref(a), 0, ws, nb, st))
+    raw = tr.grads.clone()
+    native.check(native.lib.pigan_fwd_train_step_phase(tr.engine.handle, C.byref(a), 1, ws, nb, st))
+    torch.cuda.synchronize()
+    masks = _masks(dump, B)
+    keep = float(torch.cat([m.reshape(-1) for m in masks]).mean())
+    assert abs(keep - 0.8) < 0.01, keep
+    ref_sd = copy.deepcopy(f_sd)
+    opt = O.Adam(_names(), betas=(0.9, 0.999))
+    ref, ref_grads = O.pretrain_step(ref_sd, opt, pn, spec, mn, 1e-3, masks)
+    got = tr.losses.cpu().tolist()
+    for i, k in enumerate(("loss", "loss_spec", "loss_metrics")):
+        assert abs(got[i] - ref[k]) <= TOL_LOSS * abs(ref[k]), (k, got[i], ref[k])
+    views = dict(zip(_names(), tr.fs.params.views_like(raw)))
+    flat_ref = torch.cat([ref_grads[n].reshape(-1) for n in _names()])
+    tol = TOL_GRAD[B]
+    assert rel(raw, flat_ref) < tol, rel(raw, flat_ref)
+    for n in _names():
+        r = rel(views[n], ref_grads[n])
+        assert r < 6 * tol, (n, r)
+    # clipped gradients left behind like torch's .grad after clip_grad_norm_
+    coef = min(1.0, 1.0 / (float(flat_ref.norm()) + 1e-6))
+    assert rel(tr.grads, flat_ref * coef) < tol
+    # first Adam step moves every weight by ~lr * sign(g): compare in units of lr, ignoring near-zero gradients
+    newp = dict(zip(_names(), tr.fs.params._tensors()))
+    for n in _names():
+        d = (newp[n].detach().cpu() - ref_sd[n]).abs() / 1e-3
+        gmag = ref_grads[n].abs() * coef
+        solid = gmag > 50 * 1e-8 / 3e-3    # |g| well above eps: the update is lr * sign(g) on both sides
+        assert float(d[solid].max()) < 0.05 if solid.any() else True, (n, float(d[solid].max()))
+        assert float((d > 0.05).float().mean()) < 0.02, (n, float((d > 0.05).float().mean()))
+
+
+def test_masks_are_counter_based_and_shard_invariant():
+    """Same (seed, step, global row) -> same mask whatever the batch split; a new step draws a new mask."""
+    B = 256
+    tr, F, f_sd, (pn, spec, mn) = _setup(B)
+    png, sg, mng = pn.to(DEV), spec.to(DEV), mn.to(DEV)
+
+    def run(rows, first_row, step):
+        from core.models.forward_model import ForwardModel
+        from pigan_b200.fwd_trainer import ForwardTrainer
+        F2 = ForwardModel(4, 250, 8)
+        F2.load_state_dict(f_sd)
+        t2 = ForwardTrainer(F2, DEV, max_batch=B, seed=77, engine=tr.engine)
+        t2.step_count = step - 1
+        n = rows.stop - rows.start
+        dump = torch.zeros(sum(HID) * n, dtype=torch.uint8, device=DEV)
+        t2.step(png[rows].contiguous(), sg[rows].contiguous(), mng[rows].contiguous(), 1e-3, first_row=first_row,
+                mask_dump=dump)
+        torch.cuda.synchronize()
+        return _masks(dump, n)
+
+    full = run(slice(0, B), 0, 1)
+    lo, hi = run(slice(0, 100), 0, 1), run(slice(100, B), 100, 1)
+    for m, a, b in zip(full, lo, hi):
+        assert torch.equal(m, torch.cat([a, b]))
+    again, nxt = run(slice(0, B), 0, 1), run(slice(0, B), 0, 2)
+    assert all(torch.equal(a, b) for a, b in zip(full, again))
+    assert not torch.equal(full[2], nxt[2])
+
+
+def test_training_loop_tracks_oracle_and_learns():
+    """Three steps against the oracle trajectory (replayed masks), then the loss keeps falling on a fixed batch."""
+    from oracle import models as O
+    B = 512
+    tr, F, f_sd, (pn, spec, mn) = _setup(B)
+    png, sg, mng = pn.to(DEV), spec.to(DEV), mn.to(DEV)
+    ref_sd = copy.deepcopy(f_sd)
+    opt = O.Adam(_names(), betas=(0.9, 0.999))
+    for step in range(3):
+        dump = torch.zeros(sum(HID) * B, dtype=torch.uint8, device=DEV)
+        got = tr.step(png, sg, mng, 1e-3, mask_dump=dump).cpu().tolist()
+        ref, _ = O.pretrain_step(ref_sd, opt, pn, spec, mn, 1e-3, _masks(dump, B))
+        assert abs(got[0] - ref["loss"]) <= 5e-3 * abs(ref["loss"]), (step, got[0], ref["loss"])
+    first = got[0]
+    for _ in range(60):
+        last = float(tr.step(png, sg, mng, 1e-3)[0])
+    assert last < 0.7 * first, (first, last)
+    # the module sees the trained weights (state_dict is what pretrain_forward_model saves)
+    sd = F.state_dict()
+    assert set(sd.keys()) == set(f_sd.keys())
+    assert not torch.equal(sd["model.20.weight"].cpu(), f_sd["model.20.weight"])
+
+
+def test_frozen_surrogate_must_be_reloaded_after_training():
+    from pigan_b200 import native
+    B = 64
+    tr, F, f_sd, (pn, spec, mn) = _setup(B)
+    tr.step(pn.to(DEV), spec.to(DEV), mn.to(DEV), 1e-3)
+    with pytest.raises(native.PiganError):
+        tr.engine.forward_model_forward(pn.to(DEV))
+    tr.engine.load_forward_model(tr.fs.params.tensor())
+    out = tr.engine.forward_model_forward(pn.to(DEV))
+    assert torch.isfinite(out).all()
+
+
+def test_dropin_pretrain_forward_model(tmp_path):
+    """The drop-in core.train.pretrain_fwd_model keeps the reference's signature, files and return value."""
+    import config.config as cfg
+    from core.models.forward_model import ForwardModel
+    from core.train.pretrain_fwd_model import pretrain_forward_model
+    from oracle import fixtures
+    cfg.SAVED_MODELS_DIR = str(tmp_path / "saved")
+    data = []
+    for i in range(3):
+        spec, praw, pnorm, mnorm = fixtures.make_batch(64, seed=400 + i)
+        data.append((spec, praw, pnorm, torch.zeros(64, 8), mnorm))
+    F = ForwardModel(4, 250, 8)
+    hist = pretrain_forward_model(F, data, torch.device(DEV), num_epochs=4, lr=1e-3, log_interval=2)
+    assert len(hist) == 4 and hist[-1] < hist[0]
+    sd = torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "forward_model_pretrained.pth"), map_location="cpu")
+    G = ForwardModel(4, 250, 8)
+    G.load_state_dict(sd)
+    lh = torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "fwd_pretrain_loss_history.pt"))
+    assert lh["train_losses"] == hist

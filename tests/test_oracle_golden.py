@@ -146,6 +146,44 @@ def test_train_loop_matches_reference_three_epochs():
            g["b_final_g_main.1.running_mean"], rtol=1e-3, atol=1e-4)
 
 
+def test_pretrain_step_matches_reference_loop():
+    """The oracle's surrogate-training step vs pretrain_forward_model itself (2 epochs x 2 batches, Dropout fed
+    from the same explicit masks): epoch losses, first-step raw gradients, final weights."""
+    torch.set_num_threads(1)
+    g = _load("fwd_pretrain.npz")
+    _, _, f_sd = fixtures.make_weights(42)
+    names = [f"model.{i}.{s}" for i in sorted(O.F_LINEAR + O.F_NORM) for s in ("weight", "bias")]
+    opt = O.Adam(names, betas=(0.9, 0.999))
+    B, n_batches, epochs, lr0 = 64, 2, 2, 1e-3
+    data = []
+    for i in range(n_batches):
+        spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=300 + i)
+        data.append((pnorm, spec, mnorm))
+    hist, step, first = [], 0, None
+    for epoch in range(epochs):
+        lr = O.lr_generator(epoch, epochs, lr0)      # same cosine schedule (eta_min = 0.01 lr0)
+        tot = 0.0
+        for pn, spec, mn in data:
+            losses, unclipped = O.pretrain_step(f_sd, opt, pn, spec, mn, lr,
+                                                fixtures.make_dropout_masks(B, seed=1000 + step))
+            first = unclipped if first is None else first
+            tot += losses["loss"]
+            step += 1
+        hist.append(tot / n_batches)
+    _close(hist, g["epoch_losses"], rtol=2e-5, atol=1e-7)
+    for name, gr in first.items():
+        ref = g[f"grad_{name}"]
+        got = gr.reshape(-1)[fixtures.sample_indices(gr.numel())].numpy()
+        scale = float(g[f"gradnorm_{name}"]) / np.sqrt(gr.numel()) + 1e-12
+        assert np.max(np.abs(got - ref)) <= 2e-4 * scale + 1e-9, name
+        _close(gr.norm().item(), g[f"gradnorm_{name}"], rtol=1e-4, atol=1e-9)
+    for name, t in f_sd.items():
+        ref = g[f"final_{name}"]
+        got = t.reshape(-1)[fixtures.sample_indices(t.numel())].double().numpy()
+        # four Adam steps of ~lr each: compare in units of lr
+        assert np.max(np.abs(got - ref)) <= 0.05 * lr0 + 1e-6 * np.max(np.abs(ref)), name
+
+
 def test_lr_schedules_match_torch():
     import torch.optim as optim
     from torch.optim.lr_scheduler import CosineAnnealingLR, StepLR

@@ -10,6 +10,8 @@ outputs are stored.  What is pinned:
                    denormalize_params, the six loss functions
   train_step.npz   core.train.train_pigan.train_pigan itself: 1 epoch x 1 batch (per-step losses, raw gradients
                    captured with hooks) and 3 epochs x 2 batches (schedulers, Adam t>1, BN momentum), sampled
+  fwd_pretrain.npz core.train.pretrain_fwd_model.pretrain_forward_model itself: 2 epochs x 2 batches with Dropout
+                   fed from explicit masks (epoch losses, first-step raw gradients, final weights, sampled)
   scoring.npz      the evaluator loop (unified_evaluator.py:369-392) through UnifiedEvaluator itself with the
                    plotting modules stubbed out
 """
@@ -180,7 +182,60 @@ def scoring():
     print("scoring:", {k: float(v) for k, v in agg.items()})
 
 
+def fwd_pretrain():
+    """The reference's own pretrain_forward_model (pretrain_fwd_model.py:24-158) with torch.nn.functional.dropout
+    replaced by explicit keep-masks (oracle/fixtures.make_dropout_masks) so the run is reproducible elsewhere."""
+    import torch.nn.functional as TF
+    from core.train import pretrain_fwd_model as ref_pre
+    res = {}
+    tmp = tempfile.mkdtemp()
+    cfg.SAVED_MODELS_DIR = os.path.join(tmp, "saved")
+    B, n_batches, epochs, lr = 64, 2, 2, 1e-3
+    data = []
+    for i in range(n_batches):
+        spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=300 + i)
+        data.append((spec, praw, pnorm, torch.zeros(B, 8), mnorm))
+    state = {"call": 0}
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        assert training and abs(p - 0.2) < 1e-12
+        step, layer = divmod(state["call"], 5)
+        state["call"] += 1
+        m = fixtures.make_dropout_masks(B, seed=1000 + step)[layer]
+        assert m.shape == x.shape
+        return x * m / (1.0 - p)
+
+    _, _, F = ref_models()
+    first = {}
+    for name, prm in F.named_parameters():
+        def hook(gr, name=name):
+            if name not in first:
+                first[name] = gr.detach().clone()
+            return None
+        prm.register_hook(hook)
+    real = TF.dropout
+    TF.dropout = fake_dropout
+    try:
+        hist = ref_pre.pretrain_forward_model(F, data, torch.device("cpu"), num_epochs=epochs, lr=lr, log_interval=10)
+    finally:
+        TF.dropout = real
+    assert state["call"] == 5 * n_batches * epochs
+    res["epoch_losses"] = np.array(hist, dtype=np.float64)
+    for name, gr in first.items():
+        res[f"grad_{name}"] = gr.reshape(-1)[fixtures.sample_indices(gr.numel())].numpy()
+        res[f"gradnorm_{name}"] = np.array(gr.norm().item())
+    for name, t in F.state_dict().items():
+        tt = t.reshape(-1).double()
+        res[f"final_{name}"] = tt[fixtures.sample_indices(tt.numel())].numpy()
+    np.savez(os.path.join(OUT, "fwd_pretrain.npz"), **res)
+    print("fwd_pretrain: epoch losses", hist)
+
+
 if __name__ == "__main__":
-    physics(); forward(); train_step(); scoring()
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()[name]()
+    else:
+        physics(); forward(); train_step(); scoring(); fwd_pretrain()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
