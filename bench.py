@@ -33,6 +33,7 @@ import torch
 # algorithmic work per unit: minimal necessary FLOPs
 FLOP_PER_TRAIN_SAMPLE = 7_465_984
 FLOP_PER_CANDIDATE = 3_275_776
+FLOP_PER_PRETRAIN_SAMPLE = 2 * 4_132_352   # F fwd + bwd (dW + dX), MACs x 2
 METRIC = "PI-GAN train samples/s"
 # DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/, round 1): the four
 # Linear+LayerNorm launches of the forward surrogate read+write 46.9 + 147.4 + 171.5 + 72.7 MB
@@ -104,6 +105,29 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
+def cpu_pretrain_baseline(batch: int, budget_s: float, threads: int):
+    """BASELINE config 1: the reference's forward-surrogate training loop body (pretrain_fwd_model.py:68-92) as the
+    oracle port (oracle/models.py: pretrain_step) on the host cores, at the reference's batch size."""
+    from oracle import fixtures
+    from oracle import models as O
+    torch.set_num_threads(threads)
+    _, _, f_sd = fixtures.make_weights(42)
+    names = [f"model.{i}.{s}" for i in sorted(O.F_LINEAR + O.F_NORM) for s in ("weight", "bias")]
+    opt = O.Adam(names, betas=(0.9, 0.999))
+    spec, praw, pnorm, mnorm = fixtures.make_batch(batch, seed=12)
+    masks = fixtures.make_dropout_masks(batch, seed=5)
+    O.pretrain_step(f_sd, opt, pnorm, spec, mnorm, 1e-3, masks)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.pretrain_step(f_sd, opt, pnorm, spec, mnorm, 1e-3, masks)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 2000:
+            break
+    return batch * n / el, n, el
+
+
 def cpu_train_baseline(batch: int, budget_s: float, threads: int):
     """The oracle port of the reference train step (oracle/models.py, pinned to the reference by tests/golden)
     on the host cores: returns (samples/s, steps timed)."""
@@ -397,6 +421,32 @@ def run_native(args):
                                   "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
         del spec_big, o_idx, o_met
 
+    # ---- forward-surrogate training step (BASELINE config 1 moved to the GPU): replicas + gradient
+    # all-reduce under data parallelism.  Runs last: it replaces the engine's frozen-surrogate state.
+    from pigan_b200.fwd_trainer import ForwardTrainer
+    Ft = ForwardModel(4, 250, 8)
+    Ft.load_state_dict({k: v.detach().clone() for k, v in F.state_dict().items()})
+    ftr = ForwardTrainer(Ft, dev, max_batch=B, engine=tr.engine)
+    pnorm_sets = [((s_[1] - 2.5) / 0.3).contiguous() for s_ in sets]   # data_loader.py:185-196 normalisation
+    for i in range(3):
+        ftr.step(pnorm_sets[i % NSETS], sets[i % NSETS][0], sets[i % NSETS][2], 1e-3)
+    barrier()
+    e0.record()
+    for i in range(K):
+        ftr.step(pnorm_sets[i % NSETS], sets[i % NSETS][0], sets[i % NSETS][2], 1e-3)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms5 = float(t.item()) / K
+    f_tflops = B * FLOP_PER_PRETRAIN_SAMPLE / (ms5 * 1e-3) / 1e12
+    fwd_info = {"metric": "forward-surrogate train samples/s", "value": B * world / (ms5 * 1e-3), "unit": "samples/s",
+                "batch_per_gpu": B, "ms_per_step": ms5, "dropout": "counter-based Philox, p=0.2",
+                "tensor_frac": f_tflops / peaks["tflops"], "flop_per_sample": FLOP_PER_PRETRAIN_SAMPLE,
+                "loss_last_step": float(ftr.losses[0])}
+    del pnorm_sets, ftr
+
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -404,6 +454,10 @@ def run_native(args):
         v, n, el = cpu_train_baseline(4096, 12.0, cores)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": f"{n} steps of batch 4096 in {el:.1f} s (oracle/models.py train_step, fp32, torch CPU)"}
+        v, n, el = cpu_pretrain_baseline(64, 6.0, cores)
+        fwd_info["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} steps of batch 64 (cfg.BATCH_SIZE, BASELINE config 1) in {el:.1f} s "
+                                              f"(oracle/models.py pretrain_step, fp32, torch CPU)"}
 
     if rank == 0:
         out = {
@@ -425,6 +479,7 @@ def run_native(args):
             "clocks": clk,
             "scoring": score_info,
             "physics": phys_info,
+            "surrogate_training": fwd_info,
             "wave_quantisation_probe": quant,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }
