@@ -1,4 +1,7 @@
-"""Summarise an ncu launch list (gpu__time_duration.sum CSV) : one train step of tools/time_step.py."""
+"""Summarise an ncu launch list (gpu__time_duration.sum CSV): the launches between two occurrences of a marker
+kernel.  usage: launch_summary.py FILE [WHICH [MARKER]] — MARKER 'center_vec' (default) opens a PI-GAN train step;
+'end:NAME' takes the launches after occurrence WHICH of NAME up to and including occurrence WHICH+1 (e.g.
+end:f_train_losses = one surrogate-training step of tools/one_step.py)."""
 import csv, re, sys
 path = sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/launches.csv'
 which = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -12,8 +15,13 @@ for r in data:
     v = float(r[vi].replace(',', '')); u = r[ui]
     v = v / 1000 if u == 'ns' else (v * 1000 if u == 'ms' else v)
     seq.append((r[ki], v))
-idx = [i for i, (k, _) in enumerate(seq) if 'center_vec' in k]
-s, e = idx[which], idx[which + 1]
+marker = sys.argv[3] if len(sys.argv) > 3 else 'center_vec'
+if marker.startswith('end:'):
+    idx = [i for i, (k, _) in enumerate(seq) if marker[4:] in k]
+    s, e = idx[which] + 1, idx[which + 1] + 1
+else:
+    idx = [i for i, (k, _) in enumerate(seq) if marker in k]
+    s, e = idx[which], idx[which + 1] if which + 1 < len(idx) else len(seq)
 tot = 0
 for k, v in seq[s:e]:
     name = re.sub(r'pigan::(<unnamed>::)?', '', k)

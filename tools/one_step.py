@@ -1,4 +1,5 @@
-"""Two warm-up steps + ONE train step + one 65 536-candidate scoring call + the physics kernel (ncu target)."""
+"""Three train steps + one 65 536-candidate search call + the physics kernel + two surrogate-training steps
+(ncu target; tools/launch_summary.py cuts the list into steps)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "pi-gan-thz_b200"))
@@ -23,4 +24,9 @@ freq = synthetic.frequencies(250, device=dev)
 idx = torch.empty(B, device=dev, dtype=torch.int32); out = torch.empty(B, 4, device=dev)
 native.check(native.lib.pigan_physics_metrics(sp.data_ptr(), B, 250, freq.data_ptr(), None, 0.0, idx.data_ptr(), out.data_ptr(), native.current_stream()))
 torch.cuda.synchronize()
-print("ok", float(s[0]))
+from pigan_b200.fwd_trainer import ForwardTrainer
+Ft = ForwardModel(4, 250, 8)
+ftr = ForwardTrainer(Ft, dev, max_batch=B, engine=tr.engine)
+for _ in range(2): ftr.step(pn, sp, mn, 1e-3)
+torch.cuda.synchronize()
+print("ok", float(s[0]), ftr.losses.tolist())
