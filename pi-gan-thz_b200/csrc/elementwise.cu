@@ -640,97 +640,92 @@ __global__ void __launch_bounds__(kThreads) bn_relu_apply_kernel(const __half* _
 
 // ------------------------------------------------------------------------------------------ generator head
 // p = tanh(relu(bn2(h2)) W3^T + b3) (generator.py:22-25), denormalisation (data_loader.py:238-252) and the fake-row
-// tail of the spectrum operand.  A block stages 128 rows of h2 in shared memory with coalesced 16-byte loads, then
-// each thread owns one row (no cross-lane reductions, tanh once per row); C must be 256.
-constexpr int kHeadRows = 128;
-constexpr int kHeadPitch = 256 * 2 + 16;  // bytes per staged row: +16 keeps the per-row reads conflict-free
-__global__ void __launch_bounds__(kHeadRows) g_head_fwd_kernel(
+// tail of the spectrum operand.  A warp takes 8 rows per trip with coalesced 16-byte loads; a lane owns 8 of the 256
+// columns (its BatchNorm affine and W3 slices stay in registers) and forms the 8 x 4 partial dot products, which a
+// 31-shuffle transposing reduction turns into one finished output per lane (lane L: row L/4, parameter L%4), so tanh
+// runs once per output and the [rows,4] stores are coalesced.  C must be 256.
+constexpr int kHeadRows = 8;   // rows per warp and trip
+// v[0..31] per lane -> returns sum over the lanes of v[lane]
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+__global__ void __launch_bounds__(kThreads, 2) g_head_fwd_kernel(
     const __half* __restrict__ h2, const float* __restrict__ scale, const float* __restrict__ bias,
     const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ p_out,
     float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
     int C, int Kp, int S) {
   pdl_wait();
-  extern __shared__ __align__(16) unsigned char smraw[];
-  float* cst = reinterpret_cast<float*>(smraw);                 // scale[256] bias[256] w3[4][256]
-  float* pds = cst + 6 * 256;                                    // [128][4] denormalised outputs
-  unsigned char* tile = smraw + (6 * 256 + kHeadRows * 4) * 4;   // [128][kHeadPitch]
-  for (int i = threadIdx.x; i < 256; i += kHeadRows) {
-    cst[i] = scale[i];
-    cst[256 + i] = bias[i];
+  const int lane = threadIdx.x & 31;
+  float sc[8], bi[8], w[4][8];
+  ld_f8(scale + lane * 8, sc);
+  ld_f8(bias + lane * 8, bi);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cst[512 + j * 256 + i] = w3[j * C + i];
-  }
-  const float b30 = __ldg(b3 + 0), b31 = __ldg(b3 + 1), b32 = __ldg(b3 + 2), b33 = __ldg(b3 + 3);
-  for (long long base = (long long)blockIdx.x * kHeadRows; base < rows; base += (long long)gridDim.x * kHeadRows) {
-    __syncthreads();  // constants staged / previous tile fully consumed
-    // ---- stage: 128 rows x 32 chunks of 16 bytes, a warp per row and trip
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const int idx = i * kHeadRows + threadIdx.x;
-      const int r = idx >> 5, ch = idx & 31;
-      const long long row = base + r < rows ? base + r : rows - 1;
-      const uint4 v = *reinterpret_cast<const uint4*>(h2 + row * C + ch * 8);
-      *reinterpret_cast<uint4*>(tile + r * kHeadPitch + ch * 16) = v;
+  for (int e = 0; e < 4; ++e) ld_f8(w3 + e * C + lane * 8, w[e]);
+  const float b3l = __ldg(b3 + (lane & 3));
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * kHeadRows;
+  for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kHeadRows; r0 < rows;
+       r0 += wstride) {
+    uint4 u[kHeadRows];
+#pragma unroll
+    for (int q = 0; q < kHeadRows; ++q) {
+      const long long row = r0 + q < rows ? r0 + q : rows - 1;
+      u[q] = *reinterpret_cast<const uint4*>(h2 + row * C + lane * 8);
     }
-    __syncthreads();
-    // ---- one row per thread
-    const long long row = base + threadIdx.x;
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    const unsigned char* mine = tile + threadIdx.x * kHeadPitch;
-#pragma unroll 4
-    for (int ch = 0; ch < 32; ++ch) {
-      const uint4 u = *reinterpret_cast<const uint4*>(mine + ch * 16);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      float v[8];
+    float part[32];
+#pragma unroll
+    for (int q = 0; q < kHeadRows; ++q) {
+      const uint32_t hw[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+      float a[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-        v[2 * j] = f.x;
-        v[2 * j + 1] = f.y;
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+        a[2 * j] = fmaxf(fmaf(sc[2 * j], f.x, bi[2 * j]), 0.f);
+        a[2 * j + 1] = fmaxf(fmaf(sc[2 * j + 1], f.y, bi[2 * j + 1]), 0.f);
       }
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = ch * 8 + q * 4;
-        const float4 sc = *reinterpret_cast<const float4*>(cst + c);
-        const float4 bi = *reinterpret_cast<const float4*>(cst + 256 + c);
-        const float4 wa = *reinterpret_cast<const float4*>(cst + 512 + c);
-        const float4 wb = *reinterpret_cast<const float4*>(cst + 768 + c);
-        const float4 wc = *reinterpret_cast<const float4*>(cst + 1024 + c);
-        const float4 wd = *reinterpret_cast<const float4*>(cst + 1280 + c);
-        const float a0 = fmaxf(fmaf(sc.x, v[4 * q + 0], bi.x), 0.f), a1 = fmaxf(fmaf(sc.y, v[4 * q + 1], bi.y), 0.f);
-        const float a2 = fmaxf(fmaf(sc.z, v[4 * q + 2], bi.z), 0.f), a3 = fmaxf(fmaf(sc.w, v[4 * q + 3], bi.w), 0.f);
-        d0 = fmaf(a0, wa.x, d0); d0 = fmaf(a1, wa.y, d0); d0 = fmaf(a2, wa.z, d0); d0 = fmaf(a3, wa.w, d0);
-        d1 = fmaf(a0, wb.x, d1); d1 = fmaf(a1, wb.y, d1); d1 = fmaf(a2, wb.z, d1); d1 = fmaf(a3, wb.w, d1);
-        d2 = fmaf(a0, wc.x, d2); d2 = fmaf(a1, wc.y, d2); d2 = fmaf(a2, wc.z, d2); d2 = fmaf(a3, wc.w, d2);
-        d3 = fmaf(a0, wd.x, d3); d3 = fmaf(a1, wd.y, d3); d3 = fmaf(a2, wd.z, d3); d3 = fmaf(a3, wd.w, d3);
+      for (int e = 0; e < 4; ++e) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d = fmaf(a[i], w[e][i], d);
+        part[q * 4 + e] = d;
       }
     }
-    const float p[4] = {tanhf(d0 + b30), tanhf(d1 + b31), tanhf(d2 + b32), tanhf(d3 + b33)};
-    float pd[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) pd[e] = (p[e] + 1.0f) / 2.0f * 0.6f + 2.2f;  // data_loader.py:238-252
+    const float pv = tanhf(warp_transpose_sum32(part) + b3l);       // lane L: row r0 + L/4, parameter L%4
+    const float pd = (pv + 1.0f) / 2.0f * 0.6f + 2.2f;               // data_loader.py:238-252
+    const long long row = r0 + (lane >> 2);
     if (row < rows) {
-      *reinterpret_cast<float4*>(p_out + row * 4) = make_float4(p[0], p[1], p[2], p[3]);
-      if (pden_out) *reinterpret_cast<float4*>(pden_out + row * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+      p_out[r0 * 4 + lane] = pv;
+      if (pden_out) pden_out[r0 * 4 + lane] = pd;
     }
     if (tail_fake != nullptr) {
-      *reinterpret_cast<float4*>(pds + threadIdx.x * 4) = make_float4(pd[0], pd[1], pd[2], pd[3]);
-      __syncthreads();
-      // copy the last 64 operand columns of every row (8 chunks of 16 bytes), parameter columns replaced
+      // last 64 operand columns of the 8 rows (8 chunks of 16 bytes each), parameter columns replaced
       const int t0 = Kp - 64;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = i * kHeadRows + threadIdx.x;
-        const int r = idx >> 3, ch = idx & 7;
-        if (base + r < rows) {
+      for (int j = 0; j < 2; ++j) {
+        const int t = j * 32 + lane, r = t >> 3, ch = t & 7;
+        float pr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pr[e] = __shfl_sync(0xffffffffu, pd, r * 4 + e);
+        if (r0 + r < rows) {
           float v[8];
-          ld_h8(xc + (base + r) * Kp + t0 + ch * 8, v);
+          ld_h8(xc + (r0 + r) * Kp + t0 + ch * 8, v);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int e = t0 + ch * 8 + k - S;
-            if (e >= 0 && e < 4) v[k] = pds[r * 4 + e] - kParamCenter;
+            if (e >= 0 && e < 4) v[k] = pr[e] - kParamCenter;
           }
-          st_h8(tail_fake + (base + r) * 64 + ch * 8, v);
+          st_h8(tail_fake + (r0 + r) * 64 + ch * 8, v);
         }
       }
     }
@@ -780,7 +775,7 @@ __global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
 }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHeadBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a) {
   pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(a.C);
@@ -789,7 +784,7 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 3 : 3) g_head_bwd_kernel(GHe
   ld_f4(a.scale + c0, sc);
   ld_f4(a.bias + c0, bi);
   const long long stride = (long long)gridDim.x * m.rpb;
-  constexpr int U = 2;
+  constexpr int U = APPLY ? 4 : 6;   // rows in flight per thread: these kernels are bound by memory-level parallelism
   if (!APPLY) {
     float s0[4][4], s1[4][4];  // [j][column]
 #pragma unroll
@@ -1685,18 +1680,12 @@ void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
-  const size_t smem = (6 * 256 + kHeadRows * 4) * 4 + (size_t)kHeadRows * kHeadPitch;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(g_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  launch_k(g_head_fwd_kernel, grid_for_rows(rows, kHeadRows, 148 * 3), kHeadRows, smem, st, 
-      h2, scale, bias, w3, b3, p_out, pden_out, xc, tail_fake, rows, C, Kp, S);
+  launch_k(g_head_fwd_kernel, grid_for_rows(rows, 8 * kHeadRows * 2, 148 * 2), kThreads, 0, st, h2, scale, bias, w3, b3,
+           p_out, pden_out, xc, tail_fake, (long long)rows, C, Kp, S);
 }
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
   const int rpb = kThreads / (a.C / 4);
-  const int grid = grid_for_rows(a.rows, rpb * 2 * 4, kPartBlocks);
+  const int grid = grid_for_rows(a.rows, rpb * (apply ? 4 : 6) * 2, kPartBlocks);
   if (apply) {
     launch_k(g_head_bwd_kernel<true>, grid, kThreads, 0, st, a);
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};

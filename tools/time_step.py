@@ -22,6 +22,11 @@ for _ in range(n): tr.step(sp, pr, mn, 2e-4, 2e-4)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print(f"train step B={B}: {ms:.3f} ms  -> {B / ms * 1e3:.3e} samples/s ; losses {tr.losses.tolist()[:3]}")
+if len(sys.argv) > 2:
+    tr.engine.profile_begin()
+    for _ in range(n): tr.step(sp, pr, mn, 2e-4, 2e-4)
+    for k, (c, t) in tr.engine.profile_end().items():
+        print(f"  {k:24s} {c:5d} {t / n * 1e3:8.1f} us/step")
 G.eval()
 st = flat.net_state(G, "generator")
 for _ in range(3): tr.engine.score_candidates(st.params.tensor(), st.bn.tensor(), spectra=sp, want_params=False)
