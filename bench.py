@@ -421,6 +421,28 @@ def run_native(args):
                                   "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
         del spec_big, o_idx, o_met
 
+    # ---- evaluator reductions: calculate_metrics over [n, 250] result arrays, HBM-bound
+    from pigan_b200 import evalstats
+    n_ev = 1 << 20
+    yt = sets[0][0].repeat(n_ev // B + 1, 1)[:n_ev].contiguous()
+    yp = yt + 0.25
+    rm = evalstats.RegressionMetrics(250, dev)
+    for _ in range(2):
+        rm.update(yt, yp)
+    barrier()
+    e0.record()
+    for _ in range(5):
+        rm.update(yt, yp)
+    e1.record()
+    barrier()
+    ms6 = e0.elapsed_time(e1) / 5
+    ev_gbs = 2 * n_ev * 250 * 4 / (ms6 * 1e-3) / 1e9
+    eval_info = {"metric": "evaluator regression-metric rows/s", "value": n_ev / (ms6 * 1e-3), "unit": "rows/s",
+                 "rows": n_ev, "cols": 250, "ms": ms6, "mse": rm.compute()["mse"],
+                 "roofline": {"bound": "hbm", "achieved": ev_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": ev_gbs / peaks["hbm_gbs"], "bytes_per_row": 2000}}
+    del yt, yp, rm
+
     # ---- forward-surrogate training step (BASELINE config 1 moved to the GPU): replicas + gradient
     # all-reduce under data parallelism.  Runs last: it replaces the engine's frozen-surrogate state.
     from pigan_b200.fwd_trainer import ForwardTrainer
@@ -480,6 +502,7 @@ def run_native(args):
             "scoring": score_info,
             "physics": phys_info,
             "surrogate_training": fwd_info,
+            "evaluator_reductions": eval_info,
             "wave_quantisation_probe": quant,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }

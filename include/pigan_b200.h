@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 3
+#define PIGAN_ABI_VERSION 4
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -278,6 +278,30 @@ int pigan_fwd_train_step(PiganEngine* engine, const PiganFwdTrainArgs* args, voi
 /* phase 0: forward + loss + backward (local gradients, already divided by global_batch); phase 1: clip + Adam */
 int pigan_fwd_train_step_phase(PiganEngine* engine, const PiganFwdTrainArgs* args, int32_t phase, void* workspace,
                                size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Evaluator reductions on the device.
+ * Regression metrics of UnifiedEvaluator.calculate_metrics, /root/reference/core/evaluate/unified_evaluator.py:
+ * 138-184 (sklearn mean_squared_error / mean_absolute_error / r2_score with uniform column average, mean of the
+ * per-column scipy pearsonr, MAPE with the reference's +1e-8 in float32):
+ *   pigan_regression_sums      y_true, y_pred [n, cols] fp32 row-major -> sums[cols][8] fp64 (sum y, p, y^2, p^2,
+ *                              y p, |y-p|, (y-p)^2, |(y-p)/(y+1e-8)|); accumulate != 0 adds to what sums holds
+ *                              (batches / all-reduce over ranks happen on the sums)
+ *   pigan_regression_finalize  sums + total row count -> out[6] fp64 = mse, mae, rmse, r2, pearson_r, mape
+ * Summary of the structural-prediction loop (:393-405):
+ *   pigan_score_summary_sums      violations int32[n], recon_error, consistency fp32[n] (any may be NULL) ->
+ *                                 sums[6] fp64 (count(v>0), sum v, sum e, sum e^2, sum c, sum c^2)
+ *   pigan_score_summary_finalize  -> out[6] = param_range_violation_rate, avg_param_violations,
+ *                                 reconstruction_error_mean, _std (population, np.std), consistency_score_mean, _std
+ * workspace: pigan_eval_workspace_bytes(cols) bytes of device memory, 16-byte aligned (cols = 1 for the summary).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pigan_eval_workspace_bytes(int32_t cols);
+int pigan_regression_sums(const float* y_true, const float* y_pred, int64_t n, int32_t cols, double* sums,
+                          int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+int pigan_regression_finalize(const double* sums, int64_t n_total, int32_t cols, double* out6, void* stream);
+int pigan_score_summary_sums(const int32_t* violations, const float* recon_error, const float* consistency, int64_t n,
+                             double* sums, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+int pigan_score_summary_finalize(const double* sums, int64_t n_total, double* out6, void* stream);
 
 /* k smallest of scores[n] (k <= 4096, n < 2^32), ascending, ties by position; NaN sorts last.
  * out_indices[i] = in_indices[pos] when in_indices is given (merging gathered shard results), else

@@ -99,3 +99,21 @@ def make_dropout_masks(n: int, seed: int, p: float = 0.2):
     for torch's RNG stream when the reference's pretraining step is pinned (tools/make_golden.py: fwd_pretrain)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     return [torch.from_numpy((rng.random((n, h)) >= p).astype(np.float32)) for h in F_HIDDEN]
+
+
+def evaluator_cases():
+    """Seeded (y_true, y_pred) pairs and score arrays of tests/golden/evaluator_metrics.npz (same construction as
+    tools/make_golden.py: evaluator_cases / evaluator_metrics)."""
+    cases = {}
+    spec, praw, pnorm, mnorm = make_batch(300, seed=500)
+    rng = np.random.Generator(np.random.PCG64(501))
+    cases["spectra"] = (spec.numpy(), (spec + 0.3 * torch.from_numpy(rng.standard_normal(spec.shape).astype(np.float32))).numpy())
+    cases["params"] = (praw.numpy(), (praw + 0.05 * torch.from_numpy(rng.standard_normal(praw.shape).astype(np.float32))).numpy())
+    cases["metrics"] = (mnorm.numpy(), (0.8 * mnorm + 0.1).numpy())
+    y = rng.standard_normal(257).astype(np.float32)
+    cases["vector"] = (y, (y + 0.1 * rng.standard_normal(257)).astype(np.float32))
+    rng = np.random.Generator(np.random.PCG64(502))
+    viol = rng.integers(0, 3, size=1000) * (rng.random(1000) < 0.3)
+    err = rng.random(1000).astype(np.float32) * 5
+    cons = (1.0 / (1.0 + err)).astype(np.float32)
+    return cases, (viol.astype(np.int32), err, cons)

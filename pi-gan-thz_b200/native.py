@@ -123,6 +123,11 @@ SIGNATURES = {
     "pigan_fwd_train_workspace_bytes": (C.c_size_t, [_vp]),
     "pigan_fwd_train_step": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_step_phase": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _i32, _vp, C.c_size_t, _vp]),
+    "pigan_eval_workspace_bytes": (C.c_size_t, [_i32]),
+    "pigan_regression_sums": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, C.c_size_t, _vp]),
+    "pigan_regression_finalize": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "pigan_score_summary_sums": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, C.c_size_t, _vp]),
+    "pigan_score_summary_finalize": (_i32, [_vp, _i64, _vp, _vp]),
     "pigan_topk_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "pigan_topk_smallest": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),

@@ -184,6 +184,25 @@ def test_pretrain_step_matches_reference_loop():
         assert np.max(np.abs(got - ref)) <= 0.05 * lr0 + 1e-6 * np.max(np.abs(ref)), name
 
 
+def test_evaluator_reductions_match_reference():
+    """oracle/evalstats.py vs UnifiedEvaluator.calculate_metrics (sklearn + scipy) and numpy's mean/std."""
+    from oracle import evalstats as ES
+    g = _load("evaluator_metrics.npz")
+    cases, (viol, err, cons) = fixtures.evaluator_cases()
+    for name, (y, p) in cases.items():
+        m = ES.regression_metrics(y, p)
+        for k, v in m.items():
+            _close(v, g[f"{name}_{k}"], rtol=2e-5, atol=1e-7)
+    s = ES.score_summary(viol, err, cons)
+    for k, v in s.items():
+        if k != "num_samples":
+            _close(v, g["summ_" + k], rtol=1e-5, atol=1e-8)
+    # constant columns: r2 by sklearn's force_finite rule, Pearson undefined
+    y = np.ones((10, 2), dtype=np.float32)
+    assert ES.regression_metrics(y, y)["r2"] == 1.0 and np.isnan(ES.regression_metrics(y, y)["pearson_r"])
+    assert ES.regression_metrics(y, y + 1)["r2"] == 0.0
+
+
 def test_lr_schedules_match_torch():
     import torch.optim as optim
     from torch.optim.lr_scheduler import CosineAnnealingLR, StepLR

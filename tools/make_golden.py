@@ -12,6 +12,7 @@ outputs are stored.  What is pinned:
                    captured with hooks) and 3 epochs x 2 batches (schedulers, Adam t>1, BN momentum), sampled
   fwd_pretrain.npz core.train.pretrain_fwd_model.pretrain_forward_model itself: 2 epochs x 2 batches with Dropout
                    fed from explicit masks (epoch losses, first-step raw gradients, final weights, sampled)
+  evaluator_metrics.npz  UnifiedEvaluator.calculate_metrics (sklearn/scipy) on seeded arrays + the numpy summary
   scoring.npz      the evaluator loop (unified_evaluator.py:369-392) through UnifiedEvaluator itself with the
                    plotting modules stubbed out
 """
@@ -231,11 +232,47 @@ def fwd_pretrain():
     print("fwd_pretrain: epoch losses", hist)
 
 
+def evaluator_cases():
+    """Seeded inputs of the evaluator-reduction golden (rebuilt identically by the tests)."""
+    cases = {}
+    spec, praw, pnorm, mnorm = fixtures.make_batch(300, seed=500)
+    rng = np.random.Generator(np.random.PCG64(501))
+    cases["spectra"] = (spec.numpy(), (spec + 0.3 * torch.from_numpy(rng.standard_normal(spec.shape).astype(np.float32))).numpy())
+    cases["params"] = (praw.numpy(), (praw + 0.05 * torch.from_numpy(rng.standard_normal(praw.shape).astype(np.float32))).numpy())
+    cases["metrics"] = (mnorm.numpy(), (0.8 * mnorm + 0.1).numpy())
+    y = rng.standard_normal(257).astype(np.float32)
+    cases["vector"] = (y, (y + 0.1 * rng.standard_normal(257)).astype(np.float32))
+    return cases
+
+
+def evaluator_metrics():
+    """UnifiedEvaluator.calculate_metrics itself (sklearn + scipy; unified_evaluator.py:138-184) and the numpy
+    summary of the structural-prediction loop (:393-405) on seeded arrays."""
+    from core.evaluate.unified_evaluator import UnifiedEvaluator
+    res = {}
+    for name, (y, p) in evaluator_cases().items():
+        m = UnifiedEvaluator.calculate_metrics(None, y, p)
+        for k, v in m.items():
+            res[f"{name}_{k}"] = np.array(float(v))
+    rng = np.random.Generator(np.random.PCG64(502))
+    viol = rng.integers(0, 3, size=1000) * (rng.random(1000) < 0.3)
+    err = rng.random(1000).astype(np.float32) * 5
+    cons = (1.0 / (1.0 + err)).astype(np.float32)
+    res["summ_param_range_violation_rate"] = np.array(np.mean(viol > 0))
+    res["summ_avg_param_violations"] = np.array(np.mean(viol))
+    res["summ_reconstruction_error_mean"] = np.array(float(np.mean(err)))
+    res["summ_reconstruction_error_std"] = np.array(float(np.std(err)))
+    res["summ_consistency_score_mean"] = np.array(float(np.mean(cons)))
+    res["summ_consistency_score_std"] = np.array(float(np.std(cons)))
+    np.savez(os.path.join(OUT, "evaluator_metrics.npz"), **res)
+    print("evaluator_metrics:", {k: float(v) for k, v in res.items() if k.startswith("spectra")})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain()
+        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
