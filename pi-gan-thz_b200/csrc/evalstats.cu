@@ -31,14 +31,28 @@ __global__ void __launch_bounds__(256) regression_partials_kernel(const float* _
 #pragma unroll
   for (int q = 0; q < kQ; ++q) s[q] = 0.0;
   if (c < C) {
-    for (long long r = (long long)blockIdx.x * 8 + ry; r < n; r += (long long)gridDim.x * 8) {
-      const float yf = __ldg(y + r * C + c), pf = __ldg(p + r * C + c);
-      const float df = yf - pf;
-      const float ape = fabsf(df / (yf + 1e-8f));   // float32 arithmetic as in numpy (unified_evaluator.py:182)
-      const double yd = yf, pd = pf, d = (double)yf - (double)pf;
-      s[0] += yd; s[1] += pd;
-      s[2] = fma(yd, yd, s[2]); s[3] = fma(pd, pd, s[3]); s[4] = fma(yd, pd, s[4]);
-      s[5] += fabs(d); s[6] = fma(d, d, s[6]); s[7] += (double)ape;
+    // 8 rows in flight per thread: the kernel is bound by memory-level parallelism, not by the fp64 adds
+    constexpr int U = 8;
+    const long long stride = (long long)gridDim.x * 8;
+    for (long long r0 = (long long)blockIdx.x * 8 + ry; r0 < n; r0 += U * stride) {
+      float yv[U], pv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + u * stride;
+        yv[u] = r < n ? __ldg(y + r * C + c) : 0.f;
+        pv[u] = r < n ? __ldg(p + r * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r0 + u * stride >= n) break;
+        const float yf = yv[u], pf = pv[u];
+        const float df = yf - pf;
+        const float ape = fabsf(df / (yf + 1e-8f));   // float32 arithmetic as in numpy (unified_evaluator.py:182)
+        const double yd = yf, pd = pf, d = (double)yf - (double)pf;
+        s[0] += yd; s[1] += pd;
+        s[2] = fma(yd, yd, s[2]); s[3] = fma(pd, pd, s[3]); s[4] = fma(yd, pd, s[4]);
+        s[5] += fabs(d); s[6] = fma(d, d, s[6]); s[7] += (double)ape;
+      }
     }
   }
 #pragma unroll
@@ -169,7 +183,7 @@ extern "C" int pigan_regression_sums(const float* y_true, const float* y_pred, i
   if (sm_count() <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* part = static_cast<double*>(workspace);
-  const int gx = row_blocks(n, 8 * 16);
+  const int gx = row_blocks(n, 8 * 8 * 4);
   launch_k(regression_partials_kernel, dim3(gx, (cols + 31) / 32), 256, 0, st, y_true, y_pred, (long long)n, (int)cols,
            part);
   const int width = cols * kQ;
