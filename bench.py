@@ -421,6 +421,63 @@ def run_native(args):
                                   "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
         del spec_big, o_idx, o_met
 
+    # ---- on-device data pipeline: synthetic-spectrum generator, shuffled batch gather, and the
+    # train step fed from a resident dataset (gather of the fp16 operand + metrics rows, then step_prepared)
+    from pigan_b200 import device_data
+    n_gen = 1 << 20
+    for _ in range(2):
+        gspec, gpar = device_data.generate_spectra(n_gen, dev, seed=1)
+    barrier()
+    e0.record()
+    for i in range(5):
+        gspec, gpar = device_data.generate_spectra(n_gen, dev, seed=2 + i)
+    e1.record()
+    barrier()
+    ms7 = e0.elapsed_time(e1) / 5
+    del gspec, gpar
+    n_res = 4 * B
+    res_op = torch.cat([NativeTrainer.prepare_operand(s_[0], s_[1], center) for s_ in sets])
+    res_mn = torch.cat([s_[2] for s_ in sets])
+    gperm = torch.Generator(device=dev)
+    gperm.manual_seed(5)
+    perm = torch.randperm(n_res, generator=gperm, device=dev)
+    ob, mb = torch.empty(B, 256, device=dev, dtype=torch.float16), torch.empty(B, 8, device=dev)
+    for i in range(3):
+        idx = perm[(i % 4) * B:(i % 4 + 1) * B]
+        device_data.gather_rows(res_op, idx, ob); device_data.gather_rows(res_mn, idx, mb)
+        tr.step_prepared(ob, center, mb, lr, lr)
+    barrier()
+    e0.record()
+    for i in range(K):
+        idx = perm[(i % 4) * B:(i % 4 + 1) * B]
+        device_data.gather_rows(res_op, idx, ob); device_data.gather_rows(res_mn, idx, mb)
+        tr.step_prepared(ob, center, mb, lr, lr)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms8 = float(t.item()) / K
+    e0.record()
+    for i in range(20):
+        device_data.gather_rows(res_op, perm[(i % 4) * B:(i % 4 + 1) * B], ob)
+    e1.record()
+    barrier()
+    ms9 = e0.elapsed_time(e1) / 20
+    gen_gbs = n_gen * 1016 / (ms7 * 1e-3) / 1e9
+    gat_gbs = 2 * B * 512 / (ms9 * 1e-3) / 1e9
+    pipe_info = {"generator": {"value": n_gen / (ms7 * 1e-3), "unit": "spectra/s", "rows": n_gen, "ms": ms7,
+                               "roofline": {"bound": "hbm", "achieved": gen_gbs, "peak": peaks["hbm_gbs"],
+                                            "unit": "GB/s", "frac": gen_gbs / peaks["hbm_gbs"],
+                                            "bytes_per_spectrum": 1016}},
+                 "gather": {"rows": B, "row_bytes": 512, "ms": ms9,
+                            "roofline": {"bound": "hbm", "achieved": gat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                         "frac": gat_gbs / peaks["hbm_gbs"]}},
+                 "loader_fed_train": {"value": B * world / (ms8 * 1e-3), "unit": "samples/s", "ms_per_step": ms8,
+                                      "api": "gather_rows(resident fp16 operand + metrics, shuffled index) + "
+                                             "NativeTrainer.step_prepared", "resident_rows": n_res}}
+    del res_op, res_mn, ob, mb
+
     # ---- evaluator reductions: calculate_metrics over [n, 250] result arrays, HBM-bound
     from pigan_b200 import evalstats
     n_ev = 1 << 20
@@ -503,6 +560,7 @@ def run_native(args):
             "physics": phys_info,
             "surrogate_training": fwd_info,
             "evaluator_reductions": eval_info,
+            "data_pipeline": pipe_info,
             "wave_quantisation_probe": quant,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 4
+#define PIGAN_ABI_VERSION 5
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -302,6 +302,31 @@ int pigan_regression_finalize(const double* sums, int64_t n_total, int32_t cols,
 int pigan_score_summary_sums(const int32_t* violations, const float* recon_error, const float* consistency, int64_t n,
                              double* sums, int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 int pigan_score_summary_finalize(const double* sums, int64_t n_total, double* out6, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-device data pipeline: the dataset lives in HBM; batches are row gathers, synthetic
+ * spectra are generated where they are consumed.  Replaces DataLoader(shuffle=True, num_workers=4) + per-batch
+ * H2D of /root/reference/core/train/train_pigan.py:114-121, 351-357.
+ *   pigan_gather_rows       dst[i, :] = src[index[i], :] for i < count; rows are row_bytes wide (any array:
+ *                           fp16 operand rows of 512 B, spectra of 1000 B, metrics of 32 B ...), index int64 on the
+ *                           device.  Indices outside [0, n_rows) write zeros and set *out_of_range (device int32,
+ *                           optional) instead of reading out of bounds.
+ *   pigan_generate_spectra  the spectrum part of generate_single_terahertz_spectrum_and_params,
+ *                           /root/reference/core/utils/data_loader.py:62-80, for n rows: two Gaussian dips whose
+ *                           centre / depth / width depend on (r1, r2, w, g), tanh baseline, optional linear offset,
+ *                           noise_level * z, min(., 0).  params_denorm [n,4] given, or NULL: drawn U(2.2, 2.8)
+ *                           here and written to params_out [n,4].  z is counter based (Philox4x32-10 keyed by seed;
+ *                           counter = (first_index + row, (col % 32) * 64 + (col / 32) / 4, 1), Box-Muller word
+ *                           (col / 32) % 4), so row i of the dataset is the same for any batching or sharding;
+ *                           numpy's RNG stream is not reproduced.  noise_dump: NULL or [n, S] receiving z (tests).
+ *                           The peak search of :83-110 (scipy.find_peaks) is not part of this call; per-spectrum
+ *                           metrics come from pigan_physics_metrics.
+ * ---------------------------------------------------------------------------------------------- */
+int pigan_gather_rows(const void* src, int64_t n_rows, int32_t row_bytes, const int64_t* index, int64_t count,
+                      void* dst, int32_t* out_of_range, void* stream);
+int pigan_generate_spectra(const float* params_denorm, float* params_out, const float* frequency, int64_t n,
+                           int32_t spectrum_dim, float noise_level, uint64_t seed, int64_t first_index,
+                           int32_t apply_offset, float* out_spectrum, float* noise_dump, void* stream);
 
 /* k smallest of scores[n] (k <= 4096, n < 2^32), ascending, ties by position; NaN sorts last.
  * out_indices[i] = in_indices[pos] when in_indices is given (merging gathered shard results), else

@@ -1,0 +1,146 @@
+"""On-device data pipeline.  The reference feeds the step from ``DataLoader(dataset, shuffle=True,
+num_workers=4, pin_memory=True)`` and one H2D copy per tensor and batch (core/train/train_pigan.py:114-121,
+351-357) — about 1e5 samples/s, three orders of magnitude below the step.  Here the dataset is resident in HBM and a
+batch is a row gather (``pigan_gather_rows``) by a device permutation; synthetic datasets are generated on the device
+(``pigan_generate_spectra``, the formula of data_loader.py:62-80).
+
+``DeviceLoader`` yields the reference's 5-tuple ``(spectrum, params_denorm, params_norm, metrics_denorm,
+metrics_norm)`` as device tensors, so ``train_pigan(dataloader=DeviceLoader(...), ...)`` and
+``pretrain_forward_model`` run unchanged.  Under data parallelism every rank draws the same permutation (same seed
+and epoch) and takes its contiguous slice of every global batch.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import torch
+
+from . import native
+from .native import check, lib
+
+
+def _dev(x: torch.Tensor, device) -> torch.Tensor:
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = src[index[i]] for a contiguous 2-D (or 1-D) CUDA tensor of any dtype; index int64 on the device."""
+    if not src.is_cuda or not src.is_contiguous():
+        raise RuntimeError("gather_rows needs a contiguous CUDA tensor — the B200 path has no CPU fallback")
+    if index.dtype != torch.int64 or not index.is_cuda or not index.is_contiguous():
+        raise RuntimeError("gather_rows: index must be a contiguous int64 CUDA tensor")
+    n = src.shape[0]
+    row_bytes = src[0].numel() * src.element_size() if n else 0
+    if out is None:
+        out = torch.empty((index.numel(),) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+    if index.numel() and n:
+        check(lib.pigan_gather_rows(src.data_ptr(), n, row_bytes, index.data_ptr(), index.numel(), out.data_ptr(),
+                                    None, native.current_stream()))
+    return out
+
+
+def generate_spectra(n: int, device, seed: int = 0, first_index: int = 0, noise_level: float = 0.1,
+                     params_denorm: Optional[torch.Tensor] = None, frequency: Optional[torch.Tensor] = None,
+                     apply_offset: bool = True, noise_dump: Optional[torch.Tensor] = None
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(spectrum [n,S], params_denorm [n,4]) from the reference's generator formula (data_loader.py:62-80)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("generate_spectra needs a CUDA device — the B200 path has no CPU fallback")
+    if frequency is None:
+        frequency = torch.linspace(0.5, 3.0, 250, dtype=torch.float32, device=device)
+    frequency = _dev(frequency, device)
+    S = frequency.numel()
+    out = torch.empty(n, S, device=device, dtype=torch.float32)
+    if params_denorm is None:
+        p_in, p_out = None, torch.empty(n, 4, device=device, dtype=torch.float32)
+    else:
+        p_in = p_out = _dev(params_denorm, device)
+    check(lib.pigan_generate_spectra(native.ptr(p_in), None if p_in is not None else p_out.data_ptr(),
+                                     frequency.data_ptr(), n, S, float(noise_level), int(seed), int(first_index),
+                                     int(apply_offset), out.data_ptr(), native.ptr(noise_dump),
+                                     native.current_stream()))
+    return out, p_out
+
+
+def rank_slice(count: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of a global batch of ``count`` rows that ``rank`` takes: near-equal contiguous slices, the last
+    ranks may get fewer (or no) rows of a ragged final batch."""
+    per = (count + world - 1) // world
+    return min(rank * per, count), min((rank + 1) * per, count)
+
+
+class DeviceDataset:
+    """The tensors of a MetamaterialDataset (data_loader.py:124-147, 185-219) resident on the GPU."""
+
+    def __init__(self, spectra, params_denorm, params_norm, metrics_denorm, metrics_norm, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceDataset needs a CUDA device — the B200 path has no CPU fallback")
+        self.spectra = _dev(spectra, self.device)
+        self.params_denorm = _dev(params_denorm, self.device)
+        self.params_norm = _dev(params_norm, self.device)
+        self.metrics_denorm = _dev(metrics_denorm, self.device)
+        self.metrics_norm = _dev(metrics_norm, self.device)
+        n = self.spectra.shape[0]
+        for t in (self.params_denorm, self.params_norm, self.metrics_denorm, self.metrics_norm):
+            if t.shape[0] != n:
+                raise ValueError("all dataset tensors need the same number of rows")
+
+    def __len__(self) -> int:
+        return self.spectra.shape[0]
+
+    @classmethod
+    def from_dataset(cls, ds, device) -> "DeviceDataset":
+        """From the reference-compatible MetamaterialDataset (attributes of data_loader.py:139-147)."""
+        t = torch.as_tensor
+        return cls(t(ds.spectra), t(ds.parameters), t(ds.normalized_parameters), t(ds.metrics),
+                   t(ds.normalized_metrics), device)
+
+    @classmethod
+    def synthetic(cls, n: int, device, seed: int = 42, noise_level: float = 0.1, metrics_dim: int = 8
+                  ) -> "DeviceDataset":
+        """n synthetic rows generated on the device; metrics are uniform placeholders in (0,1) as in bench.py."""
+        spec, p = generate_spectra(n, device, seed=seed, noise_level=noise_level)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        mn = torch.rand(n, metrics_dim, generator=g, device=device, dtype=torch.float32)
+        return cls(spec, p, (p - 2.2) / 0.6 * 2.0 - 1.0, mn, mn, device)
+
+
+class DeviceLoader:
+    """Iterable over shuffled batches of a DeviceDataset; ``len()`` and ``batch_size`` as a DataLoader has them."""
+
+    def __init__(self, dataset: DeviceDataset, batch_size: int, shuffle: bool = True, drop_last: bool = False,
+                 seed: int = 0, rank: int = 0, world: int = 1):
+        if batch_size < 1 or not (0 <= rank < world):
+            raise ValueError("batch_size >= 1 and 0 <= rank < world required")
+        self.ds, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.seed, self.rank, self.world, self.epoch = int(seed), int(rank), int(world), 0
+
+    def __len__(self) -> int:
+        gb = self.batch_size * self.world
+        n = len(self.ds)
+        return n // gb if self.drop_last else (n + gb - 1) // gb
+
+    def batch_indices(self, epoch: int) -> Iterator[torch.Tensor]:
+        """This rank's index vector of every global batch of ``epoch`` (device int64)."""
+        n, dev = len(self.ds), self.ds.device
+        if self.shuffle:
+            g = torch.Generator(device=dev)
+            g.manual_seed(self.seed * 1_000_003 + epoch)
+            perm = torch.randperm(n, generator=g, device=dev)
+        else:
+            perm = torch.arange(n, device=dev)
+        gb = self.batch_size * self.world
+        for b in range(len(self)):
+            chunk = perm[b * gb:(b + 1) * gb]
+            lo, hi = rank_slice(chunk.numel(), self.rank, self.world)
+            yield chunk[lo:hi].contiguous()
+
+    def __iter__(self):
+        ds = self.ds
+        for idx in self.batch_indices(self.epoch):
+            yield tuple(gather_rows(t, idx) for t in (ds.spectra, ds.params_denorm, ds.params_norm, ds.metrics_denorm,
+                                                      ds.metrics_norm))
+        self.epoch += 1

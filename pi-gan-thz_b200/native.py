@@ -128,6 +128,8 @@ SIGNATURES = {
     "pigan_regression_finalize": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "pigan_score_summary_sums": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, C.c_size_t, _vp]),
     "pigan_score_summary_finalize": (_i32, [_vp, _i64, _vp, _vp]),
+    "pigan_gather_rows": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp]),
+    "pigan_generate_spectra": (_i32, [_vp, _vp, _vp, _i64, _i32, _f32, C.c_uint64, _i64, _i32, _vp, _vp, _vp]),
     "pigan_topk_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "pigan_topk_smallest": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),

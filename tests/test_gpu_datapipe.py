@@ -1,0 +1,150 @@
+"""On-device data pipeline (pigan_gather_rows, pigan_generate_spectra).
+Gather: bit-exact against torch indexing.  Generator: fp32 against the reference's own function
+(tests/golden/datagen.npz, produced by generate_single_terahertz_spectrum_and_params) and the float64 oracle —
+absolute 2e-5 on values of magnitude <= 14 (fp32 exp / tanh)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pi-gan-thz_b200")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+TOL_ABS = 2e-5
+
+
+@pytest.mark.parametrize("shape,dtype", [((1000, 256), torch.float16), ((777, 250), torch.float32),
+                                          ((513, 8), torch.float32), ((64, 4), torch.float32),
+                                          ((100, 3), torch.float16), ((50, 7), torch.uint8), ((33,), torch.float32)])
+def test_gather_rows_is_bit_exact(shape, dtype):
+    from pigan_b200 import device_data as DD
+    g = torch.Generator(device=DEV).manual_seed(1)
+    src = (torch.rand(shape, device=DEV, generator=g) * 200).to(dtype)
+    for count in (0, 1, 31, shape[0], 3 * shape[0] + 5):
+        idx = torch.randint(0, shape[0], (count,), device=DEV, generator=g)
+        out = DD.gather_rows(src, idx)
+        assert out.shape[0] == count and torch.equal(out, src[idx])
+
+
+def test_gather_rows_flags_bad_indices_instead_of_reading_out_of_bounds():
+    from pigan_b200 import native
+    src = torch.arange(40, device=DEV, dtype=torch.float32).view(10, 4)
+    idx = torch.tensor([0, 9, 10, -1, 3], device=DEV)
+    out = torch.full((5, 4), 7.0, device=DEV)
+    bad = torch.zeros(1, device=DEV, dtype=torch.int32)
+    native.check(native.lib.pigan_gather_rows(src.data_ptr(), 10, 16, idx.data_ptr(), 5, out.data_ptr(), bad.data_ptr(),
+                                              native.current_stream()))
+    assert int(bad) == 1
+    assert torch.equal(out[[0, 1, 4]], src[[0, 9, 3]]) and float(out[2:4].abs().sum()) == 0.0
+
+
+def test_generator_matches_reference_function():
+    from oracle import datagen as DG
+    from pigan_b200 import device_data as DD
+    g = np.load(os.path.join(GOLD, "datagen.npz"))
+    params = torch.from_numpy(g["params"]).float().to(DEV)
+    freq64 = np.linspace(0.5, 3.0, 250)
+    freq = torch.from_numpy(freq64).float().to(DEV)
+    n = params.shape[0]
+    clean, p_back = DD.generate_spectra(n, DEV, noise_level=0.0, params_denorm=params, frequency=freq)
+    assert torch.equal(p_back, params)
+    assert np.max(np.abs(clean.cpu().numpy() - g["clean"])) < TOL_ABS
+    nooff, _ = DD.generate_spectra(n, DEV, noise_level=0.0, params_denorm=params, frequency=freq, apply_offset=False)
+    assert np.max(np.abs(nooff.cpu().numpy() - g["clean_nooffset"])) < TOL_ABS
+    # with noise: replay the kernel's own z through the oracle (numpy's RNG stream is not reproduced)
+    dump = torch.empty(n, 250, device=DEV)
+    noisy, _ = DD.generate_spectra(n, DEV, seed=5, noise_level=0.1, params_denorm=params, frequency=freq,
+                                   noise_dump=dump)
+    ref = DG.generate_spectra(freq64, params.cpu().numpy().astype(np.float64), noise=dump.cpu().numpy(),
+                              noise_level=0.1)
+    assert np.max(np.abs(noisy.cpu().numpy() - ref)) < TOL_ABS
+    assert float(noisy.max()) <= 0.0
+
+
+def test_generator_noise_and_parameters_are_counter_based():
+    from pigan_b200 import device_data as DD
+    n = 4096
+    dump = torch.empty(n, 250, device=DEV)
+    spec, p = DD.generate_spectra(n, DEV, seed=9, noise_level=0.1, noise_dump=dump)
+    # statistics of the draws
+    assert abs(float(dump.mean())) < 5e-3 and abs(float(dump.std()) - 1.0) < 5e-3
+    assert float(p.min()) >= 2.2 and float(p.max()) <= 2.8 and abs(float(p.mean()) - 2.5) < 5e-3
+    # any batching / sharding of the same global rows gives the same data
+    a, pa = DD.generate_spectra(1000, DEV, seed=9, first_index=0, noise_level=0.1)
+    b, pb = DD.generate_spectra(n - 1000, DEV, seed=9, first_index=1000, noise_level=0.1)
+    assert torch.equal(torch.cat([a, b]), spec) and torch.equal(torch.cat([pa, pb]), p)
+    c, _ = DD.generate_spectra(n, DEV, seed=10, noise_level=0.1)
+    assert not torch.equal(c, spec)
+    # peak indices of generated rows are what the physics kernel reports for them (bit-exact argmin)
+    from pigan_b200 import native, synthetic
+    idx = torch.empty(n, device=DEV, dtype=torch.int32)
+    out = torch.empty(n, 4, device=DEV)
+    freq = synthetic.frequencies(250, device=DEV)
+    native.check(native.lib.pigan_physics_metrics(spec.data_ptr(), n, 250, freq.data_ptr(), None, 0.0, idx.data_ptr(),
+                                                  out.data_ptr(), native.current_stream()))
+    assert torch.equal(idx.long(), spec.argmin(dim=1))
+
+
+def test_device_loader_epochs_cover_the_dataset_and_shard_across_ranks():
+    from pigan_b200 import device_data as DD
+    ds = DD.DeviceDataset.synthetic(1000, DEV, seed=3)
+    assert len(ds) == 1000
+    ld = DD.DeviceLoader(ds, batch_size=96, shuffle=True, seed=1)
+    assert len(ld) == 11 and ld.batch_size == 96
+    rows = []
+    for spec, pden, pnorm, mden, mnorm in ld:
+        assert spec.is_cuda and spec.shape[1] == 250 and pden.shape[1] == 4 and mnorm.shape[1] == 8
+        assert torch.allclose(pnorm, (pden - 2.2) / 0.6 * 2 - 1)
+        rows.append(spec)
+    got = torch.cat(rows)
+    assert got.shape[0] == 1000
+    # every dataset row exactly once (rows are distinct: noisy spectra)
+    key = lambda t: sorted(map(float, t.double().sum(dim=1).cpu()))
+    assert key(got) == key(ds.spectra)
+    # next epoch: another order; same epoch + seed on another loader object: same order
+    first2 = next(iter(ld))[0]
+    assert not torch.equal(first2, rows[0])
+    again = next(iter(DD.DeviceLoader(ds, batch_size=96, shuffle=True, seed=1)))[0]
+    assert torch.equal(again, rows[0])
+    # two ranks split every global batch; together they see what one rank with the global batch sees
+    one = list(DD.DeviceLoader(ds, 64, seed=4).batch_indices(0))
+    r0 = list(DD.DeviceLoader(ds, 32, seed=4, rank=0, world=2).batch_indices(0))
+    r1 = list(DD.DeviceLoader(ds, 32, seed=4, rank=1, world=2).batch_indices(0))
+    assert len(one) == len(r0) == len(r1)
+    for a, b, c in zip(one, r0, r1):
+        assert torch.equal(a, torch.cat([b, c]))
+    assert len(DD.DeviceLoader(ds, 96, drop_last=True)) == 10
+
+
+def test_reference_trainers_run_from_the_device_loader(tmp_path):
+    """train_pigan and pretrain_forward_model (drop-in modules) take the DeviceLoader where the reference takes a
+    DataLoader; nothing crosses PCIe per batch."""
+    import config.config as cfg
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from core.train.pretrain_fwd_model import pretrain_forward_model
+    from core.train.train_pigan import train_pigan
+    from pigan_b200 import device_data as DD
+    cfg.SAVED_MODELS_DIR = str(tmp_path / "saved")
+    cfg.CHECKPOINT_DIR = str(tmp_path / "ckpt")
+    ds = DD.DeviceDataset.synthetic(512, DEV, seed=8)
+    F = ForwardModel(4, 250, 8)
+    hist = pretrain_forward_model(F, DD.DeviceLoader(ds, 128, seed=2), torch.device(DEV), num_epochs=3, lr=1e-3)
+    assert len(hist) == 3 and hist[-1] < hist[0]
+
+    class Meta:   # what train_pigan reads from the dataset object (train_pigan.py:132,162,165-166)
+        param_ranges = {k: (2.2, 2.8) for k in ("r1", "r2", "w", "g")}
+        frequencies = np.linspace(0.5, 3.0, 250)
+        metric_name_to_idx = {"f1": 0, "f2": 1}
+    F.eval()
+    lh = train_pigan(DD.DeviceLoader(ds, 128, seed=3), torch.device(DEV), Generator(250, 4), Discriminator(250, 4), F,
+                     Meta(), num_epochs=2, log_interval=10)
+    assert len(lh["g_losses"]) == 2 and all(np.isfinite(v) for v in lh["g_losses"] + lh["d_losses"])

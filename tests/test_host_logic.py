@@ -135,3 +135,16 @@ def test_dataset_normalisation_and_denormalisation(tmp_path):
     with pytest.raises(FileNotFoundError):
         dl.MetamaterialDataset(str(tmp_path / "missing.csv"))
     assert dl.MetamaterialDataset("", load_data=False).metric_name_to_idx["f2"] == 1
+
+
+def test_rank_slice_partitions_every_global_batch():
+    """device_data.rank_slice: contiguous, disjoint, exhaustive for any (count, world), also ragged last batches."""
+    from pigan_b200.device_data import rank_slice
+    for count in (0, 1, 5, 64, 65, 1000):
+        for world in (1, 2, 3, 8):
+            covered = []
+            for r in range(world):
+                lo, hi = rank_slice(count, r, world)
+                assert 0 <= lo <= hi <= count
+                covered += list(range(lo, hi))
+            assert covered == list(range(count))

@@ -203,6 +203,17 @@ def test_evaluator_reductions_match_reference():
     assert ES.regression_metrics(y, y + 1)["r2"] == 0.0
 
 
+def test_synthetic_spectra_match_reference_generator():
+    """oracle/datagen.py vs generate_single_terahertz_spectrum_and_params (data_loader.py:62-80), incl. noise."""
+    from oracle import datagen as DG
+    g = _load("datagen.npz")
+    freq = np.linspace(0.5, 3.0, 250)
+    _close(DG.generate_spectra(freq, g["params"]), g["clean"], rtol=1e-12, atol=1e-12)
+    _close(DG.generate_spectra(freq, g["params"], apply_offset=False), g["clean_nooffset"], rtol=1e-12, atol=1e-12)
+    _close(DG.generate_spectra(freq, g["params"], noise=g["noise_unit"], noise_level=0.1), g["noisy"], rtol=1e-12,
+           atol=1e-12)
+
+
 def test_lr_schedules_match_torch():
     import torch.optim as optim
     from torch.optim.lr_scheduler import CosineAnnealingLR, StepLR

@@ -13,6 +13,7 @@ outputs are stored.  What is pinned:
   fwd_pretrain.npz core.train.pretrain_fwd_model.pretrain_forward_model itself: 2 epochs x 2 batches with Dropout
                    fed from explicit masks (epoch losses, first-step raw gradients, final weights, sampled)
   evaluator_metrics.npz  UnifiedEvaluator.calculate_metrics (sklearn/scipy) on seeded arrays + the numpy summary
+  datagen.npz      generate_single_terahertz_spectrum_and_params: noise-free rows, rows with (stored) numpy noise
   scoring.npz      the evaluator loop (unified_evaluator.py:369-392) through UnifiedEvaluator itself with the
                    plotting modules stubbed out
 """
@@ -232,6 +233,32 @@ def fwd_pretrain():
     print("fwd_pretrain: epoch losses", hist)
 
 
+def datagen():
+    """generate_single_terahertz_spectrum_and_params itself (data_loader.py:62-111): noise-free rows for seeded
+    parameters, and rows with numpy noise (the noise is recovered as output - noise-free output where unclamped,
+    so it is stored explicitly by re-drawing it from the same seed)."""
+    res = {}
+    freq = np.linspace(0.5, 3.0, 250)
+    rng = np.random.Generator(np.random.PCG64(600))
+    params = 2.2 + 0.6 * rng.random((24, 4))
+    params[0] = 2.5                      # |.| kinks of the width terms
+    params[1] = (2.2, 2.8, 2.2, 2.8)
+    clean, clean_nooff, noisy, noise = [], [], [], []
+    for i, (r1, r2, w, g) in enumerate(params):
+        clean.append(ref_dl.generate_single_terahertz_spectrum_and_params(freq, r1, r2, w, g, noise_level=0.0)[0])
+        clean_nooff.append(ref_dl.generate_single_terahertz_spectrum_and_params(freq, r1, r2, w, g, apply_offset=False,
+                                                                                 noise_level=0.0)[0])
+        np.random.seed(700 + i)
+        noisy.append(ref_dl.generate_single_terahertz_spectrum_and_params(freq, r1, r2, w, g, noise_level=0.1)[0])
+        np.random.seed(700 + i)
+        noise.append(np.random.normal(0, 0.1, 250) / 0.1)
+    res["params"] = params
+    res["clean"] = np.array(clean); res["clean_nooffset"] = np.array(clean_nooff)
+    res["noisy"] = np.array(noisy); res["noise_unit"] = np.array(noise)
+    np.savez(os.path.join(OUT, "datagen.npz"), **res)
+    print("datagen:", res["clean"].shape, float(res["clean"].min()))
+
+
 def evaluator_cases():
     """Seeded inputs of the evaluator-reduction golden (rebuilt identically by the tests)."""
     cases = {}
@@ -273,6 +300,6 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics()
+        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
