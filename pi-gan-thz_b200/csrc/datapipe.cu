@@ -59,6 +59,7 @@ __device__ __forceinline__ void normal4(uint4 u, float* z) {   // Box-Muller, as
 // Noise z(row, col): Philox4x32-10 keyed by seed, counter = (global row, (col % 32) * 64 + (col / 32) / 4, 1),
 // word (col / 32) % 4 of the Box-Muller quadruple.  Structure parameters, when drawn here: counter
 // (global row, 0, 2), word e -> 2.2 + 0.6 * (u + 0.5) / 2^32.
+template <int NQ>   // NQ = ceil(S / 128): a lane owns up to 4 * NQ columns
 __global__ void __launch_bounds__(256) generate_spectra_kernel(const float* __restrict__ params_in,
                                                                float* __restrict__ params_out,
                                                                const float* __restrict__ freq, long long n, int S,
@@ -69,6 +70,16 @@ __global__ void __launch_bounds__(256) generate_spectra_kernel(const float* __re
   const int lane = threadIdx.x & 31;
   const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  // the baseline terms depend on the column only: once per lane for its (up to 16) columns
+  constexpr int kMaxCols = 4 * NQ;
+  float fq[kMaxCols], base[kMaxCols];
+#pragma unroll
+  for (int k = 0; k < kMaxCols; ++k) {
+    const int col = k * 32 + lane;
+    fq[k] = col < S ? __ldg(freq + col) : 0.f;
+    base[k] = -0.5f * (tanhf((fq[k] - 1.5f) * 2.0f) + 1.0f);                // data_loader.py:74
+    if (apply_offset) base[k] += -0.5f + 0.5f * (fq[k] / 3.0f);             // :75-77
+  }
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += wstride) {
     const long long gi = first + row;
     float4 pr;
@@ -89,7 +100,9 @@ __global__ void __launch_bounds__(256) generate_spectra_kernel(const float* __re
     const float m2 = -11.763f + r1 * 1.0f - w * 0.8f;           // :70
     const float w2 = 0.15f + fabsf(r2 * 0.03f);                 // :71
     const float i1 = 1.0f / (2.0f * w1 * w1), i2 = 1.0f / (2.0f * w2 * w2);
-    for (int q = 0; q * 128 < S; ++q) {
+#pragma unroll
+    for (int q = 0; q < kMaxCols / 4; ++q) {
+      if (q * 128 >= S) break;
       float z[4] = {0.f, 0.f, 0.f, 0.f};
       if (noise_level != 0.f || noise_out)
         normal4(philox4x32_10(make_uint4((unsigned int)gi, (unsigned int)(gi >> 32), (unsigned int)(lane * 64 + q), 1u),
@@ -98,13 +111,12 @@ __global__ void __launch_bounds__(256) generate_spectra_kernel(const float* __re
       for (int i = 0; i < 4; ++i) {
         const int col = (q * 4 + i) * 32 + lane;
         if (col >= S) break;
-        const float f = __ldg(freq + col);
-        float t = m1 * expf(-((f - c1) * (f - c1)) * i1);                 // :67
-        t += m2 * expf(-((f - c2) * (f - c2)) * i2);                      // :72-73
-        t += -0.5f * (tanhf((f - 1.5f) * 2.0f) + 1.0f);                     // :74
-        if (apply_offset) t += -0.5f + 0.5f * (f / 3.0f);                   // :75-77
-        t += noise_level * z[i];                                          // :78-79
-        out[row * S + col] = fminf(t, 0.f);                                  // :80
+        const float f = fq[q * 4 + i];
+        float t = m1 * expf(-((f - c1) * (f - c1)) * i1);                   // :67
+        t += m2 * expf(-((f - c2) * (f - c2)) * i2);                        // :72-73
+        t += base[q * 4 + i];                                               // :74-77
+        t += noise_level * z[i];                                            // :78-79
+        out[row * S + col] = fminf(t, 0.f);                                 // :80
         if (noise_out) noise_out[row * S + col] = z[i];
       }
     }
@@ -147,15 +159,20 @@ extern "C" int pigan_gather_rows(const void* src, int64_t n_rows, int32_t row_by
 extern "C" int pigan_generate_spectra(const float* params_denorm, float* params_out, const float* frequency, int64_t n,
                                       int32_t spectrum_dim, float noise_level, uint64_t seed, int64_t first_index,
                                       int32_t apply_offset, float* out_spectrum, float* noise_dump, void* stream) {
-  PIGAN_CHECK_ARG(frequency && out_spectrum && n >= 1 && spectrum_dim >= 1 && first_index >= 0);
+  PIGAN_CHECK_ARG(frequency && out_spectrum && n >= 1 && spectrum_dim >= 1 && spectrum_dim <= 512 && first_index >= 0);
   PIGAN_CHECK_ARG(params_denorm == nullptr || (reinterpret_cast<uintptr_t>(params_denorm) & 15u) == 0);
   PIGAN_CHECK_ARG(params_out == nullptr || (reinterpret_cast<uintptr_t>(params_out) & 15u) == 0);
   if (sm_count() <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device: the B200 path has no CPU fallback");
   long long blocks = (n + 8 * 4 - 1) / (8 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(generate_spectra_kernel, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), params_denorm, params_out,
-           frequency, (long long)n, (int)spectrum_dim, noise_level, (unsigned long long)seed, (long long)first_index,
-           (int)apply_offset, out_spectrum, noise_dump);
+  auto go = [&](auto kern) {
+    launch_k(kern, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), params_denorm, params_out, frequency,
+             (long long)n, (int)spectrum_dim, noise_level, (unsigned long long)seed, (long long)first_index,
+             (int)apply_offset, out_spectrum, noise_dump);
+  };
+  if (spectrum_dim <= 128) go(generate_spectra_kernel<1>);
+  else if (spectrum_dim <= 256) go(generate_spectra_kernel<2>);
+  else go(generate_spectra_kernel<4>);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

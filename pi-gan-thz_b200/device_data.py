@@ -41,9 +41,11 @@ def gather_rows(src: torch.Tensor, index: torch.Tensor, out: Optional[torch.Tens
 
 def generate_spectra(n: int, device, seed: int = 0, first_index: int = 0, noise_level: float = 0.1,
                      params_denorm: Optional[torch.Tensor] = None, frequency: Optional[torch.Tensor] = None,
-                     apply_offset: bool = True, noise_dump: Optional[torch.Tensor] = None
+                     apply_offset: bool = True, noise_dump: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None, params_out: Optional[torch.Tensor] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(spectrum [n,S], params_denorm [n,4]) from the reference's generator formula (data_loader.py:62-80)."""
+    """(spectrum [n,S], params_denorm [n,4]) from the reference's generator formula (data_loader.py:62-80).
+    ``out`` / ``params_out``: preallocated fp32 CUDA buffers to fill (streaming generation without allocations)."""
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("generate_spectra needs a CUDA device — the B200 path has no CPU fallback")
@@ -51,9 +53,15 @@ def generate_spectra(n: int, device, seed: int = 0, first_index: int = 0, noise_
         frequency = torch.linspace(0.5, 3.0, 250, dtype=torch.float32, device=device)
     frequency = _dev(frequency, device)
     S = frequency.numel()
-    out = torch.empty(n, S, device=device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(n, S, device=device, dtype=torch.float32)
+    elif out.shape != (n, S) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous fp32 CUDA tensor [{n}, {S}]")
     if params_denorm is None:
-        p_in, p_out = None, torch.empty(n, 4, device=device, dtype=torch.float32)
+        p_in = None
+        p_out = params_out if params_out is not None else torch.empty(n, 4, device=device, dtype=torch.float32)
+        if p_out.shape != (n, 4) or p_out.dtype != torch.float32 or not p_out.is_cuda or not p_out.is_contiguous():
+            raise ValueError(f"params_out must be a contiguous fp32 CUDA tensor [{n}, 4]")
     else:
         p_in = p_out = _dev(params_denorm, device)
     check(lib.pigan_generate_spectra(native.ptr(p_in), None if p_in is not None else p_out.data_ptr(),
