@@ -185,6 +185,25 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this rank to the CPU cores next to its GPU (NVML's affinity mask) BEFORE it allocates pinned host
+    buffers, so the e2e leg's H2D traffic of the 8 ranks does not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 # ---------------------------------------------------------------------------------------------- native arm
 def run_native(args):
     import torch.distributed as dist
@@ -202,7 +221,9 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = 0
     if world > 1:
+        numa_cpus = bind_to_gpu_numa_node(local)   # N=1 keeps all cores (the CPU baseline runs on them)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, max(3, args.warmup)
@@ -549,6 +570,7 @@ def run_native(args):
             "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate, 7 losses, clip+Adam), "
                                    f"batch {B} per GPU, S=250, reference widths",
                        "global_batch": B * world, "parallelism": f"dp{world}",
+                       "rank_cpu_affinity": f"{numa_cpus} GPU-local cores per rank (NVML)" if numa_cpus else "default",
                        "l2": f"{NSETS} distinct input batches rotated ({NSETS * h2d_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roof,
             "step_roofline": {"bound": "tensor", "achieved": step_tflops, "peak": peaks["tflops"],

@@ -1311,7 +1311,8 @@ __global__ void __launch_bounds__(kThreads) f_l1_train_kernel(const float* __res
                                                               const float* __restrict__ lnw,
                                                               const float* __restrict__ lnb, __half* __restrict__ xhat,
                                                               __half* __restrict__ act, float* __restrict__ rstd_out,
-                                                              unsigned char* __restrict__ mask_out, long long rows,
+                                                              unsigned char* __restrict__ mask_out,
+                                                              unsigned char* __restrict__ keepbits, long long rows,
                                                               DropoutArgs dr) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -1348,6 +1349,7 @@ __global__ void __launch_bounds__(kThreads) f_l1_train_kernel(const float* __res
     }
     st_h8(xhat + row * 256 + lane * 8, h);
     st_h8(act + row * 256 + lane * 8, a);
+    keepbits[row * 32 + lane] = (unsigned char)keep;   // 1 bit per element: the backward pass reads it back
     if (lane == 0) rstd_out[row] = rstd;
     if (mask_out) {
       unsigned long long m = 0;
@@ -1365,7 +1367,8 @@ __global__ void __launch_bounds__(kThreads) ln_train_kernel(__half* __restrict__
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __half* __restrict__ act,
                                                             float* __restrict__ rstd_out,
-                                                            unsigned char* __restrict__ mask_out, long long rows,
+                                                            unsigned char* __restrict__ mask_out,
+                                                            unsigned char* __restrict__ keepbits, long long rows,
                                                             int layer, DropoutArgs dr) {
   pdl_wait();
   constexpr int N = NCH * 256;
@@ -1396,6 +1399,7 @@ __global__ void __launch_bounds__(kThreads) ln_train_kernel(__half* __restrict__
       }
       st_h8(xhat + row * N + c0, h);
       st_h8(act + row * N + c0, a);
+      keepbits[row * (N / 8) + (c0 >> 3)] = (unsigned char)keep;
       if (mask_out) {
         unsigned long long m = 0;
 #pragma unroll
@@ -1465,86 +1469,149 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __res
   }
 }
 
-// Backward through Dropout, LeakyReLU and LayerNorm of one surrogate layer, a warp per row:
+// Backward through Dropout, LeakyReLU and LayerNorm of one surrogate layer:
 //   dact = da * keep / (1 - p);  dy = dact * (y > 0 ? 1 : 0.2), y = gamma * xhat + beta;  dxh = dy * gamma
 //   dh = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat))                      (written over da)
+// (keep = the forward pass's mask, 1 bit per element in keepbits: reading 320 B per row is cheaper than a second
+// Philox evaluation, which was 38 % of this kernel's instructions)
 // and per-column sums over the rows for dbeta (dy), dgamma (dy * xhat), dbias (dh) -- FIRST: also dW1 (dh * p_j) --
 // as per-block partials part[block][k * N + c], k = 0..2 (3..6), finished by reduce_partials_kernel.
+// Layout: a thread owns 8 consecutive columns for the whole kernel (its 24 / 56 column accumulators stay in
+// registers) and R = 4 rows per trip; WPR = N / 256 warps share a row and meet through shared memory for the two row
+// means, so a block of 8 warps works on 8 / WPR row groups x 4 rows at a time.  (The first version gave a warp the
+// whole row: 96 accumulators per lane at N = 1024, 254 registers, 8 warps per SM, 2.7x the HBM time.)
 template <int NCH, bool FIRST>
-__global__ void __launch_bounds__(kThreads) ln_bwd_kernel(__half* __restrict__ da, const __half* __restrict__ xhat,
-                                                          const float* __restrict__ rstd_in,
-                                                          const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta,
-                                                          const float* __restrict__ p_in, long long rows, int layer,
-                                                          DropoutArgs dr, float* __restrict__ part) {
+__global__ void __launch_bounds__(kThreads, FIRST ? 1 : 2) ln_bwd_kernel(__half* __restrict__ da, const __half* __restrict__ xhat,
+                                                             const float* __restrict__ rstd_in,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ p_in,
+                                                             const unsigned char* __restrict__ keepbits,
+                                                             long long rows, float keep_scale,
+                                                             float* __restrict__ part) {
   pdl_wait();
   constexpr int N = NCH * 256;
   constexpr int NQ = FIRST ? 7 : 3;
+  constexpr int WPR = NCH;          // warps per row
+  constexpr int RG = 8 / WPR;       // row groups per block
+  constexpr int R = 4;              // rows per group and trip
   __shared__ float sm[NQ * N];
+  __shared__ float xch[2][RG][R][WPR][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float acc[NCH][NQ][8];
+  const int wr = warp % WPR, grp = warp / WPR;
+  const int c0 = wr * 256 + lane * 8;
+  float gm[8], bt[8], acc[NQ][8];
+  ld_f8(gamma + c0, gm);
+  ld_f8(beta + c0, bt);
 #pragma unroll
-  for (int j = 0; j < NCH; ++j)
+  for (int k = 0; k < NQ; ++k) zero8(acc[k]);
+  const long long rows_per_trip = (long long)gridDim.x * RG * R;
+  const long long trips = (rows + rows_per_trip - 1) / rows_per_trip;
+  auto unpack = [](const uint4& u, float* v) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) zero8(acc[j][k]);
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
-    float dxh[NCH][8], xh[NCH][8];
-    float m1 = 0.f, m2 = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  };
+  for (long long t = 0; t < trips; ++t) {
+    const long long rbase = t * rows_per_trip + ((long long)blockIdx.x * RG + grp) * R;
+    // the rows stay packed (fp16) in registers between the two phases; dy is recomputed in phase 2
+    uint4 graw[R], xraw[R];
+    unsigned int keep[R];
+    float m1[R], m2[R];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int c0 = j * 256 + lane * 8;
-      float g[8], gm[8], bt[8];
-      ld_h8(da + row * N + c0, g);
-      ld_h8(xhat + row * N + c0, xh[j]);
-      ld_f8(gamma + c0, gm);
-      ld_f8(beta + c0, bt);
-      const unsigned int keep = drop_keep8(dr, dr.first_row + row, layer, c0 >> 3);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float y = fmaf(xh[j][i], gm[i], bt[i]);
-        const float dy = (keep >> i) & 1u ? g[i] * dr.keep_scale * (y > 0.f ? 1.f : kSlope) : 0.f;
-        acc[j][0][i] += dy;
-        acc[j][1][i] = fmaf(dy, xh[j][i], acc[j][1][i]);
-        const float t = dy * gm[i];
-        dxh[j][i] = t;
-        m1 += t;
-        m2 = fmaf(t, xh[j][i], m2);
+    for (int u = 0; u < R; ++u) {
+      const long long row = rbase + u;
+      if (row < rows) {
+        graw[u] = *reinterpret_cast<const uint4*>(da + row * N + c0);
+        xraw[u] = *reinterpret_cast<const uint4*>(xhat + row * N + c0);
+      } else {
+        graw[u] = make_uint4(0u, 0u, 0u, 0u);
+        xraw[u] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
-    m1 = warp_sum_f(m1) * (1.0f / N);
-    m2 = warp_sum_f(m2) * (1.0f / N);
-    const float rstd = __ldg(rstd_in + row);
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (FIRST) q = __ldg(reinterpret_cast<const float4*>(p_in) + row);
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      float dh[8];
+    for (int u = 0; u < R; ++u) {
+      const long long row = rbase + u;
+      keep[u] = row < rows ? (unsigned int)__ldg(keepbits + row * (N / 8) + (c0 >> 3)) : 0u;
+      float g[8], xh[8];
+      unpack(graw[u], g);
+      unpack(xraw[u], xh);
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        dh[i] = rstd * (dxh[j][i] - m1 - xh[j][i] * m2);
-        acc[j][2][i] += dh[i];
-        if constexpr (FIRST) {
-          acc[j][3][i] = fmaf(dh[i], q.x, acc[j][3][i]);
-          acc[j][4][i] = fmaf(dh[i], q.y, acc[j][4][i]);
-          acc[j][5][i] = fmaf(dh[i], q.z, acc[j][5][i]);
-          acc[j][6][i] = fmaf(dh[i], q.w, acc[j][6][i]);
+        const float y = fmaf(xh[i], gm[i], bt[i]);
+        const float dy = (keep[u] >> i) & 1u ? g[i] * keep_scale * (y > 0.f ? 1.f : kSlope) : 0.f;
+        acc[0][i] += dy;
+        acc[1][i] = fmaf(dy, xh[i], acc[1][i]);
+        const float dx = dy * gm[i];
+        a1 += dx;
+        a2 = fmaf(dx, xh[i], a2);
+      }
+      m1[u] = warp_sum_f(a1);
+      m2[u] = warp_sum_f(a2);
+    }
+    if constexpr (WPR > 1) {
+      const int par = (int)(t & 1);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          xch[par][grp][u][wr][0] = m1[u];
+          xch[par][grp][u][wr][1] = m2[u];
         }
       }
-      if constexpr (!FIRST) st_h8(da + row * N + j * 256 + lane * 8, dh);
+      __syncthreads();   // uniform trip count: every warp of the block gets here
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+          s1 += xch[par][grp][u][w][0];
+          s2 += xch[par][grp][u][w][1];
+        }
+        m1[u] = s1;
+        m2[u] = s2;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const long long row = rbase + u;
+      if (row >= rows) continue;
+      const float rstd = __ldg(rstd_in + row);
+      const float mu1 = m1[u] * (1.0f / N), mu2 = m2[u] * (1.0f / N);
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (FIRST) q = __ldg(reinterpret_cast<const float4*>(p_in) + row);
+      float g[8], xh[8], dh[8];
+      unpack(graw[u], g);
+      unpack(xraw[u], xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(xh[i], gm[i], bt[i]);
+        const float dy = (keep[u] >> i) & 1u ? g[i] * keep_scale * (y > 0.f ? 1.f : kSlope) : 0.f;
+        dh[i] = rstd * (dy * gm[i] - mu1 - xh[i] * mu2);
+        acc[2][i] += dh[i];
+        if constexpr (FIRST) {
+          acc[3][i] = fmaf(dh[i], q.x, acc[3][i]);
+          acc[4][i] = fmaf(dh[i], q.y, acc[4][i]);
+          acc[5][i] = fmaf(dh[i], q.z, acc[5][i]);
+          acc[6][i] = fmaf(dh[i], q.w, acc[6][i]);
+        }
+      }
+      if constexpr (!FIRST) st_h8(da + row * N + c0, dh);
     }
   }
-  // block combine in a fixed warp order (deterministic), then this block's row of the partial scratch
+  // block combine over the row groups in a fixed order (deterministic), then this block's row of the partial scratch
   for (int i = threadIdx.x; i < NQ * N; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  for (int wq = 0; wq < 8; ++wq) {
-    if (warp == wq) {
+  for (int gq = 0; gq < RG; ++gq) {
+    if (grp == gq) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j)
+      for (int k = 0; k < NQ; ++k)
 #pragma unroll
-        for (int k = 0; k < NQ; ++k)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sm[k * N + j * 256 + lane * 8 + i] += acc[j][k][i];
+        for (int i = 0; i < 8; ++i) sm[k * N + c0 + i] += acc[k][i];
     }
     __syncthreads();
   }
@@ -1764,18 +1831,18 @@ void launch_score_finish(const float* p, const float* err, int64_t rows, int P, 
 
 
 void launch_f_l1_train(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
-                       __half* xhat, __half* act, float* rstd, unsigned char* mask, int64_t rows,
-                       const DropoutArgs& dr, cudaStream_t st) {
+                       __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
+                       int64_t rows, const DropoutArgs& dr, cudaStream_t st) {
   launch_k(f_l1_train_kernel, grid_for_rows(rows, 8 * 8, 148 * 4), kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd,
-           mask, (long long)rows, dr);
+           mask, keepbits, (long long)rows, dr);
 }
 void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, const float* beta, __half* act,
-                     float* rstd, unsigned char* mask, int64_t rows, int N, int layer, const DropoutArgs& dr,
-                     cudaStream_t st) {
+                     float* rstd, unsigned char* mask, unsigned char* keepbits, int64_t rows, int N, int layer,
+                     const DropoutArgs& dr, cudaStream_t st) {
   const int grid = grid_for_rows(rows, 8 * 4, 148 * 4);
-  if (N == 256) launch_k(ln_train_kernel<1>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
-  else if (N == 512) launch_k(ln_train_kernel<2>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
-  else launch_k(ln_train_kernel<4>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, (long long)rows, layer, dr);
+  if (N == 256) launch_k(ln_train_kernel<1>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
+  else if (N == 512) launch_k(ln_train_kernel<2>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
+  else launch_k(ln_train_kernel<4>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
 }
 void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
@@ -1792,17 +1859,18 @@ void launch_f_out_loss(const float* out, const float* spectrum, const float* met
   launch_reduce_partials(r, st);
 }
 void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const float* gamma, const float* beta,
-                   const float* p_in, int64_t rows, int N, int layer, const DropoutArgs& dr, float* part,
-                   float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs, cudaStream_t st) {
+                   const float* p_in, const unsigned char* keepbits, int64_t rows, int N, float keep_scale,
+                   float* part, float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs,
+                   cudaStream_t st) {
   // partial rows are NQ * N floats wide: keep nblocks * NQ * N inside the scratch (kPartBlocks * kPartCols floats)
   const int nq = p_in ? 7 : 3;
   int cap = (int)(((size_t)kPartBlocks * kPartCols) / ((size_t)nq * N));
   if (cap > 148 * 2) cap = 148 * 2;
-  const int grid = grid_for_rows(rows, 8 * 4, cap);
-  if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
-  else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
-  else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
-  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, (long long)rows, layer, dr, part);
+  const int grid = grid_for_rows(rows, (8 / (N / 256)) * 4 * 4, cap);
+  if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
+  else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
+  else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
+  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
   ReduceArgs r;
   r.part = part; r.nblocks = grid; r.ld = nq * N; r.nseg = p_in ? 4 : 3;
   r.seg[0] = {dbeta, N, inv_gs};

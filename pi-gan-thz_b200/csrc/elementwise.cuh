@@ -223,19 +223,21 @@ struct DropoutArgs {
   float keep_scale;         // 1 / (1 - p)
 };
 void launch_f_l1_train(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
-                       __half* xhat, __half* act, float* rstd, unsigned char* mask, int64_t rows,
-                       const DropoutArgs& dr, cudaStream_t st);
+                       __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
+                       int64_t rows, const DropoutArgs& dr, cudaStream_t st);
 void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, const float* beta, __half* act,
-                     float* rstd, unsigned char* mask, int64_t rows, int N, int layer, const DropoutArgs& dr,
-                     cudaStream_t st);
+                     float* rstd, unsigned char* mask, unsigned char* keepbits, int64_t rows, int N, int layer,
+                     const DropoutArgs& dr, cudaStream_t st);
 // loss + output-layer gradient; db_out[S+Mt] += inv_gs * column sums of dout, loss_sums[2] += sums of squares
 void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
                        cudaStream_t st);
+// keepbits: [rows, N / 8] bytes written by the forward kernels (bit i = column 8 k + i kept).
 // da -> dh in place (not for the first layer, p_in != null, whose dW1 comes out k-major [4][N] instead)
 void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const float* gamma, const float* beta,
-                   const float* p_in, int64_t rows, int N, int layer, const DropoutArgs& dr, float* part,
-                   float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs, cudaStream_t st);
+                   const float* p_in, const unsigned char* keepbits, int64_t rows, int N, float keep_scale,
+                   float* part, float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs,
+                   cudaStream_t st);
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st);
 void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 

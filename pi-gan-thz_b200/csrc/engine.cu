@@ -963,6 +963,7 @@ constexpr int kDoutLd = 320;   // output-layer gradient operand: S + Mt = 258 co
 struct FTrainWs {
   __half* xhat[5];
   float* rstd[5];
+  uint8_t* keepbits[5];   // Dropout keep-masks of the forward pass, 1 bit per element
   float* out32;
   __half* dout;
   __half* dbuf[2];
@@ -979,6 +980,7 @@ struct FTrainWs {
     for (int i = 0; i < 5; ++i) {
       xhat[i] = c.take<__half>((size_t)Bp * L.H[i]);
       rstd[i] = c.take<float>(Bp);
+      keepbits[i] = c.take<uint8_t>((size_t)Bp * (L.H[i] / 8));
       wmax = L.H[i] > wmax ? L.H[i] : wmax;
     }
     out32 = c.take<float>((size_t)Bp * L.OUT);
@@ -1046,14 +1048,14 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   auto mask = [&](int i) { return a.mask_dump ? a.mask_dump + moff[i] : nullptr; };
   PM("f_l1");
   launch_f_l1_train(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
-                    w.rstd[0], mask(0), n, dr, st);
+                    w.rstd[0], mask(0), w.keepbits[0], n, dr, st);
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
     PIGAN_TRY((linear_store<true, false, true>(act[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], w.xhat[i],
                                                e->f_rowstats, st)));
     PM("f_ln_dropout");
-    launch_ln_train(w.xhat[i], e->f_rowstats, fp + L.ln_w[i], fp + L.ln_b[i], act[i], w.rstd[i], mask(i), n, L.H[i], i,
-                    dr, st);
+    launch_ln_train(w.xhat[i], e->f_rowstats, fp + L.ln_w[i], fp + L.ln_b[i], act[i], w.rstd[i], mask(i), w.keepbits[i],
+                    n, L.H[i], i, dr, st);
   }
   PM("f_out_gemm");
   FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, w.out32, nullptr, 0, 1};
@@ -1071,8 +1073,9 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   PIGAN_TRY((linear_store<false, false, false>(w.dout, n, kDoutLd, w.wth[5], L.H[4], nullptr, d, nullptr, st)));
   for (int i = 4; i >= 0; --i) {
     PM("f_ln_bwd");
-    launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], i == 0 ? a.params_norm : nullptr, n, L.H[i],
-                  i, dr, e->partials, gr + L.ln_w[i], gr + L.ln_b[i], gr + L.b[i], w.dw1_tmp, inv_gs, st);
+    launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], i == 0 ? a.params_norm : nullptr,
+                  w.keepbits[i], n, L.H[i], dr.keep_scale, e->partials, gr + L.ln_w[i], gr + L.ln_b[i], gr + L.b[i],
+                  w.dw1_tmp, inv_gs, st);
     if (i == 0) {
       launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
       break;

@@ -9,7 +9,10 @@ want = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "duration_us"), ("
         ("dram__bytes_write.sum", "dram_write_MB"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"), ("launch__registers_per_thread", "regs"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"), ("launch__grid_size", "grid")]
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"), ("launch__grid_size", "grid"),
+        ("sm__inst_executed.sum", "warp_insts"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+        ("sm__inst_executed_pipe_alu.sum", "alu_insts"), ("sm__inst_executed_pipe_fma.sum", "fma_insts"),
+        ("smsp__inst_executed_pipe_xu.sum", "xu_insts")]
 idx = [(hdr.index(k) if k in hdr else -1, n) for k, n in want]
 units = rows[1]
 w = csv.writer(sys.stdout)
