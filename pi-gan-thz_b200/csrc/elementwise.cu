@@ -1323,39 +1323,61 @@ __global__ void __launch_bounds__(kThreads) f_l1_train_kernel(const float* __res
   ld_f8(b1 + lane * 8, b);
   ld_f8(lnw + lane * 8, gm);
   ld_f8(lnb + lane * 8, bt);
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
-    float h[8], s = 0.f;
+  constexpr int R = 4;   // rows per warp and trip: four independent reduction chains in flight
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * R;
+  for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; r0 < rows; r0 += wstride) {
+    float h[R][8], s[R], v[R];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] = fmaf(q.w, wr[i].w, fmaf(q.z, wr[i].z, fmaf(q.y, wr[i].y, fmaf(q.x, wr[i].x, b[i]))));
-      s += h[i];
+    for (int u = 0; u < R; ++u) {
+      const long long row = r0 + u < rows ? r0 + u : rows - 1;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
+      s[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[u][i] = fmaf(q.w, wr[i].w, fmaf(q.z, wr[i].z, fmaf(q.y, wr[i].y, fmaf(q.x, wr[i].x, b[i]))));
+        s[u] += h[u][i];
+      }
     }
-    const float mean = warp_sum_f(s) * (1.0f / 256.0f);
-    float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] -= mean;
-      v = fmaf(h[i], h[i], v);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < R; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const float mean = s[u] * (1.0f / 256.0f);
+      v[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[u][i] -= mean;
+        v[u] = fmaf(h[u][i], h[u][i], v[u]);
+      }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum_f(v) * (1.0f / 256.0f) + kLnEps);
-    const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, lane);
-    float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      h[i] *= rstd;
-      a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[i], gm[i], bt[i])) * dr.keep_scale : 0.f;
-    }
-    st_h8(xhat + row * 256 + lane * 8, h);
-    st_h8(act + row * 256 + lane * 8, a);
-    keepbits[row * 32 + lane] = (unsigned char)keep;   // 1 bit per element: the backward pass reads it back
-    if (lane == 0) rstd_out[row] = rstd;
-    if (mask_out) {
-      unsigned long long m = 0;
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
-      *reinterpret_cast<unsigned long long*>(mask_out + row * 256 + lane * 8) = m;
+      for (int u = 0; u < R; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const long long row = r0 + u;
+      if (row >= rows) break;
+      const float rstd = 1.0f / sqrtf(v[u] * (1.0f / 256.0f) + kLnEps);
+      const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, lane);
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[u][i] *= rstd;
+        a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[u][i], gm[i], bt[i])) * dr.keep_scale : 0.f;
+      }
+      st_h8(xhat + row * 256 + lane * 8, h[u]);
+      st_h8(act + row * 256 + lane * 8, a);
+      keepbits[row * 32 + lane] = (unsigned char)keep;   // 1 bit per element: the backward pass reads it back
+      if (lane == 0) rstd_out[row] = rstd;
+      if (mask_out) {
+        unsigned long long m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
+        *reinterpret_cast<unsigned long long*>(mask_out + row * 256 + lane * 8) = m;
+      }
     }
   }
 }
@@ -1422,37 +1444,61 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __res
                                                               __half* __restrict__ dout, int ld, long long rows, int S,
                                                               int Mt, float* __restrict__ part, int ld_part) {
   pdl_wait();
+  // a lane owns the column pairs (2 lane + 64 j, +1), j < 5: 8-byte loads, 4-byte stores; S, Mt and ld are even,
+  // so a pair never straddles the spectrum / metrics / padding boundaries.  Two rows per warp and trip.
   __shared__ float sm[8][328];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OUT = S + Mt;
   const float gs_spec = 2.0f / (float)S, gs_met = 2.0f / (float)Mt;
-  constexpr int J = 10;   // column slots per lane: covers ld <= 320
-  float colsum[J];
+  constexpr int J = 5;    // covers ld <= 320
+  constexpr int R = 2;
+  float colsum[J][2];
 #pragma unroll
-  for (int j = 0; j < J; ++j) colsum[j] = 0.f;
+  for (int j = 0; j < J; ++j) colsum[j][0] = colsum[j][1] = 0.f;
   float sq_spec = 0.f, sq_met = 0.f;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * R;
+  for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * R; r0 < rows; r0 += wstride) {
+    float2 o[R][J], t[R][J];
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int c = j * 32 + lane;
-      if (c >= ld) continue;
-      float g = 0.f;
-      if (c < OUT) {
-        const float t = c < S ? __ldg(spectrum + row * S + c) : __ldg(metrics + row * Mt + (c - S));
-        const float d = out[row * OUT + c] - t;
-        if (c < S) sq_spec = fmaf(d, d, sq_spec);
-        else sq_met = fmaf(d, d, sq_met);
-        g = d * (c < S ? gs_spec : gs_met);
+    for (int u = 0; u < R; ++u) {
+      const long long row = r0 + u < rows ? r0 + u : rows - 1;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = j * 64 + 2 * lane;
+        o[u][j] = t[u][j] = make_float2(0.f, 0.f);
+        if (c < OUT) {
+          o[u][j] = *reinterpret_cast<const float2*>(out + row * OUT + c);
+          t[u][j] = c < S ? __ldg(reinterpret_cast<const float2*>(spectrum + row * S + c))
+                          : __ldg(reinterpret_cast<const float2*>(metrics + row * Mt + (c - S)));
+        }
       }
-      dout[row * ld + c] = __float2half_rn(g);
-      colsum[j] += g;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      if (r0 + u >= rows) break;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int c = j * 64 + 2 * lane;
+        if (c >= ld) continue;
+        const float d0 = o[u][j].x - t[u][j].x, d1 = o[u][j].y - t[u][j].y;   // zero in the padding columns
+        const float sq = fmaf(d0, d0, d1 * d1);
+        if (c < S) sq_spec += sq;
+        else sq_met += sq;
+        const float gsc = c < S ? gs_spec : gs_met;
+        const float g0 = d0 * gsc, g1 = d1 * gsc;
+        *reinterpret_cast<__half2*>(dout + (r0 + u) * ld + c) = __floats2half2_rn(g0, g1);
+        colsum[j][0] += g0;
+        colsum[j][1] += g1;
+      }
     }
   }
   sq_spec = warp_sum_f(sq_spec);
   sq_met = warp_sum_f(sq_met);
 #pragma unroll
-  for (int j = 0; j < J; ++j) sm[warp][j * 32 + lane] = colsum[j];
+  for (int j = 0; j < J; ++j) {
+    sm[warp][j * 64 + 2 * lane] = colsum[j][0];
+    sm[warp][j * 64 + 2 * lane + 1] = colsum[j][1];
+  }
   if (lane == 0) {
     sm[warp][320] = sq_spec;
     sm[warp][321] = sq_met;
@@ -1461,11 +1507,11 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __res
   float* prow = part + (size_t)blockIdx.x * ld_part;
   for (int c = threadIdx.x; c < ld_part; c += blockDim.x) {
     const int src = c >= ld_part - 2 ? 320 + (c - (ld_part - 2)) : c;
-    float t = 0.f;
+    float tt = 0.f;
     if (src < 322 && (c < OUT || c >= ld_part - 2))
 #pragma unroll
-      for (int wq = 0; wq < 8; ++wq) t += sm[wq][src];
-    prow[c] = t;
+      for (int wq = 0; wq < 8; ++wq) tt += sm[wq][src];
+    prow[c] = tt;
   }
 }
 
@@ -1481,7 +1527,7 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __res
 // means, so a block of 8 warps works on 8 / WPR row groups x 4 rows at a time.  (The first version gave a warp the
 // whole row: 96 accumulators per lane at N = 1024, 254 registers, 8 warps per SM, 2.7x the HBM time.)
 template <int NCH, bool FIRST>
-__global__ void __launch_bounds__(kThreads, FIRST ? 1 : 2) ln_bwd_kernel(__half* __restrict__ da, const __half* __restrict__ xhat,
+__global__ void __launch_bounds__(kThreads, 2) ln_bwd_kernel(__half* __restrict__ da, const __half* __restrict__ xhat,
                                                              const float* __restrict__ rstd_in,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta,
@@ -1494,7 +1540,7 @@ __global__ void __launch_bounds__(kThreads, FIRST ? 1 : 2) ln_bwd_kernel(__half*
   constexpr int NQ = FIRST ? 7 : 3;
   constexpr int WPR = NCH;          // warps per row
   constexpr int RG = 8 / WPR;       // row groups per block
-  constexpr int R = 4;              // rows per group and trip
+  constexpr int R = FIRST ? 2 : 4;  // rows per group and trip (the first layer carries 56 column accumulators)
   __shared__ float sm[NQ * N];
   __shared__ float xch[2][RG][R][WPR][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1833,7 +1879,7 @@ void launch_score_finish(const float* p, const float* err, int64_t rows, int P, 
 void launch_f_l1_train(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
                        __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
                        int64_t rows, const DropoutArgs& dr, cudaStream_t st) {
-  launch_k(f_l1_train_kernel, grid_for_rows(rows, 8 * 8, 148 * 4), kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd,
+  launch_k(f_l1_train_kernel, grid_for_rows(rows, 8 * 4 * 2, 148 * 4), kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd,
            mask, keepbits, (long long)rows, dr);
 }
 void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, const float* beta, __half* act,
@@ -1848,7 +1894,7 @@ void launch_f_out_loss(const float* out, const float* spectrum, const float* met
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
                        cudaStream_t st) {
   const int OUT = S + Mt, ld_part = (OUT + 2 + 7) / 8 * 8;
-  const int grid = grid_for_rows(rows, 8 * 8, kPartBlocks);
+  const int grid = grid_for_rows(rows, 8 * 2 * 4, kPartBlocks);
   launch_k(f_out_loss_kernel, grid, kThreads, 0, st, out, spectrum, metrics, dout, ld, (long long)rows, S, Mt, part,
            ld_part);
   ReduceArgs r;
@@ -1866,7 +1912,7 @@ void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const floa
   const int nq = p_in ? 7 : 3;
   int cap = (int)(((size_t)kPartBlocks * kPartCols) / ((size_t)nq * N));
   if (cap > 148 * 2) cap = 148 * 2;
-  const int grid = grid_for_rows(rows, (8 / (N / 256)) * 4 * 4, cap);
+  const int grid = grid_for_rows(rows, (8 / (N / 256)) * (p_in ? 2 : 4) * 4, cap);
   if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
   else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
   else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
