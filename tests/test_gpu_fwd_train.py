@@ -196,3 +196,17 @@ def test_dropin_pretrain_forward_model(tmp_path):
     G.load_state_dict(sd)
     lh = torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "fwd_pretrain_loss_history.pt"))
     assert lh["train_losses"] == hist
+
+
+@pytest.mark.parametrize("B", [1, 3, 127])
+def test_tiny_batches_match_oracle_losses(B):
+    """Edge sizes (a single row, fewer rows than a warp trip, one short of a row tile): losses against the oracle."""
+    from oracle import models as O
+    tr, F, f_sd, (pn, spec, mn) = _setup(B, max_batch=128)
+    dump = torch.zeros(sum(HID) * B, dtype=torch.uint8, device=DEV)
+    got = tr.step(pn.to(DEV), spec.to(DEV), mn.to(DEV), 1e-3, mask_dump=dump).cpu().tolist()
+    ref, _ = O.pretrain_step(copy.deepcopy(f_sd), O.Adam(_names(), betas=(0.9, 0.999)), pn, spec, mn, 1e-3,
+                             _masks(dump, B))
+    for i, k in enumerate(("loss", "loss_spec", "loss_metrics")):
+        assert abs(got[i] - ref[k]) <= 2e-3 * abs(ref[k]), (k, got[i], ref[k])
+    assert all(torch.isfinite(p).all() for p in F.parameters())
