@@ -1031,50 +1031,61 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------ discriminator
-__global__ void __launch_bounds__(kThreads, 4) d_l2_bwd_kernel(const __half* __restrict__ z2,
+__global__ void __launch_bounds__(kThreads, 3) d_l2_bwd_kernel(const __half* __restrict__ z2,
                                                                const float* __restrict__ dlogit,
                                                                const float* __restrict__ w3, __half* __restrict__ dh2,
                                                                float* __restrict__ dw3, float* __restrict__ db2,
                                                                float* __restrict__ db3, long long rows, int C,
                                                                float inv_gs, float* __restrict__ part) {
   pdl_wait();
-  __shared__ float sm[kThreads * 4];
-  const ColMap4 m(C);
-  const int c0 = m.ch * 4;
-  float w[4], sw[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
-  ld_f4(w3 + c0, w);
+  // 8 columns per thread (16-byte loads and stores), 4 rows in flight: bound by memory-level parallelism
+  __shared__ float sm[kThreads * 8];
+  const ColMap m(C);
+  const int c0 = m.ch * 8;
+  float w[8], sw[8], sb[8];
+  ld_f8(w3 + c0, w);
+  zero8(sw);
+  zero8(sb);
   float s3 = 0.f;
   const long long stride = (long long)gridDim.x * m.rpb;
   for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += kU * stride) {
-    float z[kU][4], dl[kU];
+    uint4 zraw[kU];   // rows stay packed until they are used
+    float dl[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r < rows) {
         dl[u] = __ldg(dlogit + r);
-        ld_h4(z2 + r * C + c0, z[u]);
+        zraw[u] = *reinterpret_cast<const uint4*>(z2 + r * C + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const long long r = r0 + u * stride;
       if (r >= rows) break;
-      float o[4];
+      float o[8], z[8];
+      const uint32_t zw[4] = {zraw[u].x, zraw[u].y, zraw[u].z, zraw[u].w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float dh = dl[u] * w[i] * (z[u][i] > 0.f ? 1.f : kSlope);
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&zw[j]));
+        z[2 * j] = f.x;
+        z[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dh = dl[u] * w[i] * (z[i] > 0.f ? 1.f : kSlope);
         o[i] = dh;
-        sw[i] = fmaf(dl[u], z[u][i], sw[i]);
+        sw[i] = fmaf(dl[u], z[i], sw[i]);
         sb[i] += dh;
       }
-      st_h4(dh2 + r * C + c0, o);
+      st_h8(dh2 + r * C + c0, o);
       if (m.ch == 0) s3 += dl[u];
     }
   }
   if (dw3 != nullptr) {
     part += (size_t)blockIdx.x * 2 * C;
-    block_colsum_partial4(sw, part, m, sm);
-    block_colsum_partial4(sb, part + C, m, sm);
+    block_colsum_partial(sw, part, m, sm);
+    block_colsum_partial(sb, part + C, m, sm);
     const float t = block_sum(s3, sm);
     if (threadIdx.x == 0) atomicAdd(db3, t * inv_gs);
   }
@@ -1831,7 +1842,7 @@ void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
 }
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
                      float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st) {
-  const int rpb = kThreads / (C / 4);
+  const int rpb = kThreads / (C / 8);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
   launch_k(d_l2_bwd_kernel, grid, kThreads, 0, st, z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
   if (dw3 != nullptr) {

@@ -1,0 +1,40 @@
+"""Physics metrics of spectra on the device (csrc/physics.cu through ``pigan_physics_metrics``): the quantities the
+north star's PINN loss is built from — resonance peak, FWHM-based Q, FoM, sensitivity S
+(``calculate_peak_parameters``, core/utils/data_loader.py:13-58, and its callers :96,105) — plus the peak shift
+between two spectra.  The reference defines no peak shift; it is taken as in SURVEY 8(f) N2:
+``peak_shift = f_res(reconstructed) - f_res(target)`` with f_res at each row's argmin."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import native, synthetic
+
+
+def peak_metrics(spectra: torch.Tensor, frequency: Optional[torch.Tensor] = None,
+                 peak_idx: Optional[torch.Tensor] = None, baseline_transmission: float = 0.0
+                 ) -> Dict[str, torch.Tensor]:
+    """spectra [n,S] fp32 CUDA -> {'peak_idx' int32 [n], 'f_res', 'Q', 'FoM', 'S' fp32 [n]} (NaN where the reference
+    returns NaN).  ``peak_idx=None``: argmin of every row, first occurrence."""
+    if not spectra.is_cuda:
+        raise RuntimeError("peak_metrics needs CUDA tensors — the B200 path has no CPU fallback")
+    spec = spectra.float().contiguous()
+    n, s = spec.shape
+    freq = synthetic.frequencies(s, device=spec.device) if frequency is None \
+        else torch.as_tensor(frequency).to(spec.device, torch.float64).contiguous()
+    pk = None if peak_idx is None else peak_idx.to(spec.device, torch.int32).contiguous()
+    idx = torch.empty(n, device=spec.device, dtype=torch.int32)
+    out = torch.empty(n, 4, device=spec.device, dtype=torch.float32)
+    native.check(native.lib.pigan_physics_metrics(spec.data_ptr(), n, s, freq.data_ptr(), native.ptr(pk),
+                                                  float(baseline_transmission), idx.data_ptr(), out.data_ptr(),
+                                                  native.current_stream()))
+    return {"peak_idx": idx, "f_res": out[:, 0], "Q": out[:, 1], "FoM": out[:, 2], "S": out[:, 3]}
+
+
+def peak_shift(reconstructed: torch.Tensor, target: torch.Tensor, frequency: Optional[torch.Tensor] = None
+               ) -> Dict[str, torch.Tensor]:
+    """Per row: resonance frequency of ``reconstructed`` minus that of ``target`` (THz), with both peak indices."""
+    a, b = peak_metrics(reconstructed, frequency), peak_metrics(target, frequency)
+    return {"peak_shift": a["f_res"] - b["f_res"], "peak_idx_reconstructed": a["peak_idx"],
+            "peak_idx_target": b["peak_idx"]}

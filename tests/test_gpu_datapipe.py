@@ -148,3 +148,21 @@ def test_reference_trainers_run_from_the_device_loader(tmp_path):
     lh = train_pigan(DD.DeviceLoader(ds, 128, seed=3), torch.device(DEV), Generator(250, 4), Discriminator(250, 4), F,
                      Meta(), num_epochs=2, log_interval=10)
     assert len(lh["g_losses"]) == 2 and all(np.isfinite(v) for v in lh["g_losses"] + lh["d_losses"])
+
+
+def test_peak_shift_is_the_difference_of_argmin_frequencies():
+    """physics.peak_shift (SURVEY 8(f) N2's definition): indices bit-exact against numpy argmin, shift 1e-6."""
+    from pigan_b200 import device_data as DD
+    from pigan_b200 import physics
+    a, _ = DD.generate_spectra(2048, DEV, seed=21, noise_level=0.1)
+    b, _ = DD.generate_spectra(2048, DEV, seed=22, noise_level=0.1)
+    r = physics.peak_shift(a, b)
+    freq = np.linspace(0.5, 3.0, 250)
+    ia, ib = a.cpu().numpy().argmin(axis=1), b.cpu().numpy().argmin(axis=1)
+    assert np.array_equal(r["peak_idx_reconstructed"].cpu().numpy(), ia)
+    assert np.array_equal(r["peak_idx_target"].cpu().numpy(), ib)
+    np.testing.assert_allclose(r["peak_shift"].cpu().numpy(), freq[ia] - freq[ib], atol=1e-6)
+    assert float(physics.peak_shift(a, a)["peak_shift"].abs().max()) == 0.0
+    m = physics.peak_metrics(a)
+    ok = ~torch.isnan(m["Q"])
+    assert ok.float().mean() > 0.9 and torch.allclose(m["S"][ok], m["f_res"][ok] * m["Q"][ok], rtol=1e-5)
