@@ -99,6 +99,13 @@ struct PiganEngine {
   std::vector<float> f_host;      // host copy of the frozen forward-model parameters (LayerNorm constants travel
                                   // to the kernels as by-value arguments)
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
+  // The frozen surrogate's forward pass of the G-step depends only on the generator output, not on the D-step: it
+  // runs on a second, high-priority stream from the moment that output exists (phase 2) and is joined before the
+  // generator-head backward (phase 3).  Its CTAs fill the SMs that the D-step's kernels leave idle in their last,
+  // partial wave (512 row tiles on 148 SMs = 3.46 waves).  PIGAN_OVERLAP=0 keeps everything on the caller's stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
 
   // fp16 activations
   __half *xc_own;   // workspace copy of the spectrum operand; `xc` below points at it or at a caller-prepared operand
@@ -544,6 +551,37 @@ GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
   return hb;
 }
 
+bool overlap_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("PIGAN_OVERLAP");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+// surrogate forward of the G-step + its fused losses (train_pigan.py:156-172)
+int g_step_surrogate(PiganEngine* e, const PiganTrainArgs& a, cudaStream_t st) {
+  FOutOpts fo{2, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr, a.f1_idx, a.f2_idx};
+  return f_forward(e, e->p, a.batch, fo, st);
+}
+// phase 2, once e->p exists: start the surrogate chain on the side stream
+int fork_surrogate(PiganEngine* e, const PiganTrainArgs& a, cudaStream_t st) {
+  e->side_pending = false;
+  if (!overlap_enabled() || e->prof.on) return PIGAN_OK;   // profiling keeps one stream so sections stay meaningful
+  if (e->side == nullptr) {
+    int lo = 0, hi = 0;
+    PIGAN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PIGAN_CUDA_OK(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, hi));   // measured: priority is neutral
+    PIGAN_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    PIGAN_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  PIGAN_CUDA_OK(cudaEventRecord(e->ev_fork, st));
+  PIGAN_CUDA_OK(cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  PIGAN_TRY(g_step_surrogate(e, a, e->side));
+  PIGAN_CUDA_OK(cudaEventRecord(e->ev_join, e->side));
+  e->side_pending = true;
+  return PIGAN_OK;
+}
+
 int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t st) {
   const GenLayout& G = e->gl;
   const DiscLayout& D = e->dl;
@@ -588,6 +626,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PM("g_head_fwd");
       launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, e->p, e->pden, e->xc, e->tail_f, B, G.H2,
                         kKp, G.S, st);
+      PIGAN_TRY(fork_surrogate(e, a, st));
       // ---- D-step (train_pigan.py:123-143)
       PIGAN_TRY(pack_discriminator(e, dp, true, st));
       PIGAN_TRY(d_layer1(e, B, 0, false, st));
@@ -635,9 +674,12 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
         Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
         PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
-      FOutOpts fo{2, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr,
-                  a.f1_idx, a.f2_idx};
-      PIGAN_TRY(f_forward(e, e->p, B, fo, st));
+      if (e->side_pending) {
+        PIGAN_CUDA_OK(cudaStreamWaitEvent(st, e->ev_join, 0));   // the surrogate chain started in phase 2
+        e->side_pending = false;
+      } else {
+        PIGAN_TRY(g_step_surrogate(e, a, st));
+      }
       PM("g_head_bwd");
       launch_g_head_bwd(head_bwd_args(e, a), false, st);
       break;
@@ -752,8 +794,12 @@ extern "C" int pigan_engine_create(PiganEngine** out, const PiganDims* dims, int
 }
 
 extern "C" int pigan_engine_destroy(PiganEngine* e) {
-  if (e)
+  if (e) {
     for (cudaEvent_t ev : e->prof.pool) cudaEventDestroy(ev);
+    if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+  }
   delete e;
   return PIGAN_OK;
 }

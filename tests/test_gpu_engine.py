@@ -515,8 +515,9 @@ def test_train_step_ragged_batches(n):
 
 def test_dependent_launches_do_not_change_results():
     """Every kernel of the step is launched as a programmatic dependent of its predecessor (PIGAN_PDL, default on)
-    and waits (griddepcontrol.wait) before touching memory; the reductions are fixed-order.  So three train steps
-    and a surrogate-training step must be bit-identical with the overlap switched off."""
+    and waits (griddepcontrol.wait) before touching memory, the frozen surrogate's forward chain of the G-step runs
+    on a second stream beside the D-step (PIGAN_OVERLAP, default on), and the reductions are fixed-order.  So three
+    train steps and a surrogate-training step must be bit-identical with both overlaps switched off."""
     import subprocess
     code = r'''
 import os, sys, torch
@@ -530,20 +531,21 @@ from pigan_b200.fwd_trainer import ForwardTrainer
 g_sd, d_sd, f_sd = fixtures.make_weights(42)
 G, D, F = Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)
 G.load_state_dict(g_sd); D.load_state_dict(d_sd); F.load_state_dict(f_sd); F.eval()
-tr = NativeTrainer(G, D, F, "cuda", max_batch=2048)
-spec, praw, pnorm, mnorm = (t.cuda() for t in fixtures.make_batch(2048, seed=3))
+tr = NativeTrainer(G, D, F, "cuda", max_batch=16384)
+spec, praw, pnorm, mnorm = (t.cuda() for t in fixtures.make_batch(16384, seed=3))
 out = []
 for _ in range(3):
     out += tr.step(spec, praw, mnorm, 2e-4, 2e-4).cpu().tolist()
 F2 = ForwardModel(4, 250, 8); F2.load_state_dict(f_sd)
-ft = ForwardTrainer(F2, "cuda", max_batch=2048, seed=5)
+ft = ForwardTrainer(F2, "cuda", max_batch=16384, seed=5)
 out += ft.step(pnorm, spec, mnorm, 1e-3).cpu().tolist()
 out.append(float(tr.gs.params.tensor().double().sum())); out.append(float(ft.fs.params.tensor().double().sum()))
 print("RESULT", " ".join(repr(x) for x in out))
 ''' % (ROOT, PKG)
     res = {}
     for flag in ("1", "0"):
-        env = dict(os.environ, PIGAN_PDL=flag)
+        # "0" also keeps the surrogate chain of the G-step on the caller's stream (no second stream)
+        env = dict(os.environ, PIGAN_PDL=flag, PIGAN_OVERLAP=flag)
         p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert p.returncode == 0, p.stderr[-2000:]
         res[flag] = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0]
