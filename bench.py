@@ -389,8 +389,10 @@ def run_native(args):
     # ---- inverse-design scoring (BASELINE config 4): candidates/s, sharded by candidate, final top-k gather
     G.eval()
     gs = flat.net_state(G, "generator")
-    chunk = min(B, 1 << 16)
-    designer = scoring.InverseDesigner(tr.engine, gs.params.tensor(), gs.bn.tensor(), chunk=chunk)
+    chunk = scoring.full_wave_chunk(dev)      # 148 SMs x 128 rows x 4 waves = 75 776: no partial wave per GEMM
+    seng = E.Engine(chunk, dev)
+    seng.load_forward_model(tr.fs.params.tensor())
+    designer = scoring.InverseDesigner(seng, gs.params.tensor(), gs.bn.tensor(), chunk=chunk)
     target = sets[0][0][0].clone()
     n_cand = args.candidates * world
     designer.search(target, 4 * chunk * world, k=1024)
@@ -409,7 +411,9 @@ def run_native(args):
     score_info = {"metric": "inverse-design candidates/s", "value": cand_s, "unit": "candidates/s",
                   "candidates": n_cand, "k": 1024, "ms": ms3, "best_recon_error": float(res["recon_error"][0]),
                   "tensor_frac": cand_s * FLOP_PER_CANDIDATE / 1e12 / (peaks["tflops"] * world),
+                  "chunk": chunk,
                   "noise": "in-kernel Philox4x32-10 keyed by (seed, global candidate index)"}
+    del designer, seng
 
     # ---- physics metrics (BASELINE config 3): one warp per spectrum, HBM-bound
     from pigan_b200 import native

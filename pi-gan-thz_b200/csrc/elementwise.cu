@@ -765,13 +765,15 @@ __global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
     }
     *reinterpret_cast<float4*>(a.dpre + r * 4) = make_float4(dpre[0], dpre[1], dpre[2], dpre[3]);
   }
+  // per-block partials (db3[0..3], range sum) -> a.dpre_part[block][8]; g_head_moments_finish_kernel adds them in
+  // block order (float atomics here made the bias gradient, hence the whole run, irreproducible in the last bit)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float t = block_sum(db[j], sm);
-    if (threadIdx.x == 0) atomicAdd(a.db3 + j, t * a.inv_gs);
+    if (threadIdx.x == 0) a.dpre_part[blockIdx.x * 8 + j] = t;
   }
   const float t = block_sum(range_acc, sm);
-  if (threadIdx.x == 0 && a.range_sum) atomicAdd(a.range_sum, (double)t);
+  if (threadIdx.x == 0) a.dpre_part[blockIdx.x * 8 + 4] = t;
 }
 
 template <bool APPLY>
@@ -909,9 +911,24 @@ __global__ void __launch_bounds__(1024) g_head_moments_sum_kernel(const float* _
   }
 }
 // ... and finishes sum dy, sum dy*xhat and dW3 from them
-__global__ void g_head_moments_finish_kernel(GHeadBwdArgs a, const float* __restrict__ tot) {
+__global__ void g_head_moments_finish_kernel(GHeadBwdArgs a, const float* __restrict__ tot, int dpre_blocks) {
   pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {   // db3 and the range-loss sum from g_head_dpre_kernel's partials, fixed order
+    __shared__ double dsm[16][8];
+    const int q = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 128 threads: 16 groups x 8 quantities (5 used)
+    double t = 0.0;
+    if (q < 5)
+      for (int b = grp; b < dpre_blocks; b += 16) t += (double)a.dpre_part[b * 8 + q];
+    dsm[grp][q] = t;
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      double tt = 0.0;
+      for (int k = 0; k < 16; ++k) tt += dsm[k][threadIdx.x];
+      if (threadIdx.x < 4) a.db3[threadIdx.x] += (float)tt * a.inv_gs;
+      else if (a.range_sum) *a.range_sum += tt;
+    }
+  }
   if (c >= a.C) return;
   const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
   float sdy = 0.f, sdyh = 0.f;
@@ -1083,11 +1100,11 @@ __global__ void __launch_bounds__(kThreads, 3) d_l2_bwd_kernel(const __half* __r
     }
   }
   if (dw3 != nullptr) {
-    part += (size_t)blockIdx.x * 2 * C;
+    part += (size_t)blockIdx.x * (2 * C + 8);
     block_colsum_partial(sw, part, m, sm);
     block_colsum_partial(sb, part + C, m, sm);
     const float t = block_sum(s3, sm);
-    if (threadIdx.x == 0) atomicAdd(db3, t * inv_gs);
+    if (threadIdx.x == 0) part[2 * C] = t;   // db3: column 2C of the partial row (no float atomics)
   }
 }
 
@@ -1192,20 +1209,46 @@ __global__ void __launch_bounds__(kThreads) ln_lrelu_apply_kernel(__half* __rest
 }
 
 // ------------------------------------------------------------------------------------------ optimiser
-__global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
+// squared gradient norm, stage 1: one fp64 partial per block (no atomics: clip_adam_kernel adds the partials in a
+// fixed order, so the clip coefficient - and with it every weight - is run-to-run reproducible)
+__global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, long long n,
+                                                         double* __restrict__ parts) {
   pdl_wait();
-  __shared__ float sm[32];
-  float s = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    s = fmaf(g[i], g[i], s);
-  const float t = block_sum(s, sm);
-  if (threadIdx.x == 0) atomicAdd(out, (double)t);
+  __shared__ double smd[8];
+  double s = 0.0;
+  float f = 0.f;
+  int cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    f = fmaf(g[i], g[i], f);
+    if (++cnt == 64) {   // bounded fp32 runs, fp64 across them
+      s += (double)f;
+      f = 0.f;
+      cnt = 0;
+    }
+  }
+  s += (double)f;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) smd[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += smd[k];
+    parts[blockIdx.x] = t;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
   pdl_wait();
   // torch.nn.utils.clip_grad_norm_(max_norm) then optim.Adam.step() (train_pigan.py:142-143,186-187)
-  const float total = (float)sqrt(*a.total_sq);
+  __shared__ double tot_sm;
+  if (threadIdx.x < 32) {   // every block adds the partials of sumsq_kernel in the same order
+    double t = 0.0;
+    for (int k = threadIdx.x; k < a.n_parts; k += 32) t += a.sq_parts[k];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) tot_sm = t;
+  }
+  __syncthreads();
+  const float total = (float)sqrt(tot_sm);
   float coef = a.max_norm / (total + 1e-6f);
   coef = coef > 1.f ? 1.f : coef;
   const float step = (float)((double)a.lr / a.bias_c1);
@@ -1815,11 +1858,14 @@ void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
     ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
     launch_reduce_partials(r, st);
   } else {
-    launch_k(g_head_dpre_kernel, grid_for_rows(a.rows, kThreads, 148 * 2), kThreads, 0, st, a);
-    launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, a);
+    GHeadBwdArgs b = a;
     float* tot = a.part + (size_t)kPartBlocks * 8 * a.C;   // after the partial rows
+    b.dpre_part = tot + 8 * a.C;                            // [dpre blocks][8] after the moment totals
+    const int dpre_blocks = grid_for_rows(a.rows, kThreads, 148 * 2);
+    launch_k(g_head_dpre_kernel, dpre_blocks, kThreads, 0, st, b);
+    launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, b);
     launch_k(g_head_moments_sum_kernel, dim3((a.C + 31) / 32, 8), 1024, 0, st, a.part, grid, a.C, tot);
-    launch_k(g_head_moments_finish_kernel, (a.C + 127) / 128, 128, 0, st, a, tot);
+    launch_k(g_head_moments_finish_kernel, (a.C + 127) / 128, 128, 0, st, b, tot, dpre_blocks);
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
@@ -1846,7 +1892,7 @@ void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __h
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
   launch_k(d_l2_bwd_kernel, grid, kThreads, 0, st, z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
   if (dw3 != nullptr) {
-    ReduceArgs r{part, grid, 2 * C, 2, {{dw3, C, inv_gs}, {db2, C, inv_gs}}};
+    ReduceArgs r{part, grid, 2 * C + 8, 3, {{dw3, C, inv_gs}, {db2, C, inv_gs}, {db3, 1, inv_gs}}};
     launch_reduce_partials(r, st);
   }
 }
@@ -1859,11 +1905,12 @@ void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const 
   const int rpb = kThreads / (N / 8);
   launch_k(ln_lrelu_apply_kernel, grid_for_rows(rows, rpb * 4), kThreads, 0, st, h, rowstats, n_tiles, gamma, beta, rows, N);
 }
-void launch_sumsq(const float* g, int64_t n, double* out, cudaStream_t st) {
+int launch_sumsq(const float* g, int64_t n, double* parts, cudaStream_t st) {
   int grid = (int)((n + kThreads * 4 - 1) / (kThreads * 4));
   if (grid > 148 * 2) grid = 148 * 2;
   if (grid < 1) grid = 1;
-  launch_k(sumsq_kernel, grid, kThreads, 0, st, g, n, out);
+  launch_k(sumsq_kernel, grid, kThreads, 0, st, g, (long long)n, parts);
+  return grid;
 }
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st) {
   int grid = (int)((a.n + kThreads - 1) / kThreads);

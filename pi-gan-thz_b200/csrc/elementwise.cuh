@@ -122,6 +122,7 @@ struct GHeadBwdArgs {
   float* sum_dy;          // [C] += (scaled)
   float* sum_dyx;         // [C] +=
   double* range_sum;      // += sum of clamp terms
+  float* dpre_part;       // scratch [blocks][8] of g_head_dpre_kernel (set by launch_g_head_bwd)
   float inv_gs;
   int64_t rows;
   int C;
@@ -177,7 +178,8 @@ void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const 
                            int64_t rows, int N, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ optimiser
-void launch_sumsq(const float* g, int64_t n, double* out, cudaStream_t st);
+// stage 1 of the squared gradient norm: returns the number of fp64 block partials written to parts (<= 296)
+int launch_sumsq(const float* g, int64_t n, double* parts, cudaStream_t st);
 struct AdamArgs {
   float* p;
   float* g;
@@ -186,7 +188,8 @@ struct AdamArgs {
   int64_t n;
   float lr, beta1, beta2, eps;
   double bias_c1, bias_c2;  // 1 - beta^t
-  const double* total_sq;   // squared global grad norm
+  const double* sq_parts;   // block partials of the squared global grad norm (launch_sumsq)
+  int n_parts;
   float max_norm;
 };
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st);

@@ -548,6 +548,7 @@ GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
   hb.inv_gs = inv_gs; hb.rows = a.batch; hb.C = G.H2;
   hb.gamma = gp + G.bn2_w; hb.dbias = a.g_grads + G.b2; hb.dgamma = a.g_grads + G.bn2_w;
   hb.dbeta = a.g_grads + G.bn2_b; hb.inv_n = 1.0 / (double)a.global_batch; hb.part = e->partials; hb.dpre = e->dpre;
+  hb.dpre_part = nullptr;   // placed inside the partial scratch by launch_g_head_bwd
   return hb;
 }
 
@@ -657,9 +658,10 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
     }
     case 3: {
       PM("clip_adam");
-      launch_sumsq(a.d_grads, D.total, e->sums + kSumGradD, st);
+      double* sq = reinterpret_cast<double*>(e->partials);   // free here: block partials of the gradient norm
+      const int nsq = launch_sumsq(a.d_grads, D.total, sq, st);
       AdamArgs ad{dp, a.d_grads, a.d_exp_avg, a.d_exp_avg_sq, D.total, a.lr_d, 0.5f, 0.999f, 1e-8f,
-                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradD, 1.0f};
+                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), sq, nsq, 1.0f};
       launch_clip_adam(ad, st);
       // ---- G-step (train_pigan.py:145-187) against the updated discriminator
       PIGAN_TRY(pack_discriminator(e, dp, true, st));
@@ -715,9 +717,10 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
     }
     case 6: {
       PM("clip_adam");
-      launch_sumsq(a.g_grads, G.total, e->sums + kSumGradG, st);
+      double* sq = reinterpret_cast<double*>(e->partials);
+      const int nsq = launch_sumsq(a.g_grads, G.total, sq, st);
       AdamArgs ad{gp, a.g_grads, a.g_exp_avg, a.g_exp_avg_sq, G.total, a.lr_g, 0.5f, 0.999f, 1e-8f,
-                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), e->sums + kSumGradG, 1.0f};
+                  1.0 - pow(0.5, (double)a.step), 1.0 - pow(0.999, (double)a.step), sq, nsq, 1.0f};
       launch_clip_adam(ad, st);
       if (a.losses) {
         LossFinalizeArgs lf{e->sums, a.losses, NG, G.S, e->fl.Mt, G.P, a.lambda_recon, a.lambda_physics_spectrum,
@@ -1054,9 +1057,10 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   const float inv_gs = (float)(1.0 / (double)a.global_batch);
   if (phase == 1) {
     PM("clip_adam");
-    launch_sumsq(gr, L.total, w.sumsq, st);
+    double* sq = reinterpret_cast<double*>(e->partials);
+    const int nsq = launch_sumsq(gr, L.total, sq, st);
     AdamArgs ad{fp, gr, a.f_exp_avg, a.f_exp_avg_sq, L.total, a.lr, a.beta1, a.beta2, a.eps,
-                1.0 - pow((double)a.beta1, (double)a.step), 1.0 - pow((double)a.beta2, (double)a.step), w.sumsq,
+                1.0 - pow((double)a.beta1, (double)a.step), 1.0 - pow((double)a.beta2, (double)a.step), sq, nsq,
                 a.max_norm};
     launch_clip_adam(ad, st);
     launch_f_train_losses(loss_sums, (double)a.global_batch * L.S, (double)a.global_batch * L.Mt, a.losses, st);

@@ -47,6 +47,14 @@ def merge_topk(scores: torch.Tensor, indices: torch.Tensor, params: torch.Tensor
     return vals, indices[pos], params[pos]
 
 
+def full_wave_chunk(device=None, waves: int = 4) -> int:
+    """Candidates per chunk that tile the GPU without a partial wave: one 128-row tile per SM and wave (148 SMs ->
+    75 776 for 4 waves).  A 65 536-candidate chunk is 3.46 waves, i.e. ~8 % of every GEMM's time runs on 68 of 148
+    SMs; results do not depend on the chunk size (the noise is keyed by the global candidate index)."""
+    sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    return int(sms) * 128 * int(waves)
+
+
 class InverseDesigner:
     def __init__(self, engine: _engine.Engine, g_flat: torch.Tensor, g_bn: torch.Tensor, chunk: Optional[int] = None,
                  process_group=None):
