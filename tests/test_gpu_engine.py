@@ -550,3 +550,31 @@ print("RESULT", " ".join(repr(x) for x in out))
         assert p.returncode == 0, p.stderr[-2000:]
         res[flag] = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0]
     assert res["1"] == res["0"]
+
+
+def test_training_is_bit_reproducible():
+    """Two runs of the same job give identical weights: no atomics on the gradient path (fixed-order partial
+    reductions for bias / norm gradients, BatchNorm statistics, split-K weight gradients and the clip norm)."""
+    from oracle import fixtures
+    from pigan_b200.fwd_trainer import ForwardTrainer
+    from pigan_b200.trainer import NativeTrainer
+    g_sd, d_sd, f_sd = _weights()
+    B = 16384
+    spec, praw, pnorm, mnorm = (t.to(DEV) for t in fixtures.make_batch(B, seed=17))
+
+    def run():
+        G, D, F = _models(g_sd, d_sd, f_sd)
+        tr = NativeTrainer(G, D, F, DEV, max_batch=B)
+        for _ in range(6):
+            tr.step(spec, praw, mnorm, 2e-4, 2e-4)
+        F2 = _models(g_sd, d_sd, f_sd)[2]
+        ft = ForwardTrainer(F2, DEV, max_batch=B, seed=3)
+        for _ in range(3):
+            ft.step(pnorm, spec, mnorm, 1e-3)
+        torch.cuda.synchronize()
+        return (tr.gs.params.tensor().clone(), tr.ds.params.tensor().clone(), tr.gs.bn.tensor().clone(),
+                ft.fs.params.tensor().clone())   # (reported loss scalars go through fp64 atomics: not compared)
+
+    a, b = run(), run()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
