@@ -53,6 +53,33 @@ def test_fails_loudly_without_a_gpu():
     assert rc != 0
 
 
+def test_new_entry_points_validate_arguments_and_refuse_to_run_without_a_gpu():
+    """Data pipeline, evaluator reductions, surrogate training: bad arguments -> PIGAN_ERR_INVALID with a message;
+    on a box without CUDA the kernels are not launched (error, not a CPU computation)."""
+    import torch
+    from pigan_b200 import native
+    lib = native.lib
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.addressof(buf)
+    assert lib.pigan_eval_workspace_bytes(250) >= 148 * 4 * 250 * 8 * 8 and lib.pigan_eval_workspace_bytes(0) == 0
+    assert lib.pigan_regression_sums(None, p, 4, 4, p, 0, p, 1 << 20, None) != 0 and native.last_error()
+    assert lib.pigan_regression_sums(p, p, 0, 4, p, 0, p, 1 << 20, None) != 0
+    assert lib.pigan_regression_sums(p, p, 4, 4, p, 0, p, 16, None) != 0          # workspace too small
+    assert lib.pigan_regression_finalize(None, 4, 4, p, None) != 0
+    assert lib.pigan_score_summary_finalize(p, 0, p, None) != 0
+    assert lib.pigan_gather_rows(None, 4, 16, p, 1, p, None, None) != 0
+    assert lib.pigan_gather_rows(p, 4, 0, p, 1, p, None, None) != 0
+    assert lib.pigan_generate_spectra(None, p, None, 4, 250, 0.1, 1, 0, 1, p, None, None) != 0
+    assert lib.pigan_generate_spectra(None, p, p, 4, 4096, 0.1, 1, 0, 1, p, None, None) != 0    # S > 512
+    assert lib.pigan_fwd_train_workspace_bytes(None) == 0
+    assert lib.pigan_fwd_train_step(None, None, p, 1 << 20, None) != 0
+    if not torch.cuda.is_available():
+        assert lib.pigan_regression_sums(p, p, 4, 4, p, 0, p, 1 << 26, None) != 0
+        assert lib.pigan_gather_rows(p, 4, 16, p, 1, p, None, None) != 0
+        assert lib.pigan_generate_spectra(None, p, p, 4, 250, 0.1, 1, 0, 1, p, None, None) != 0
+        assert "no CUDA device" in native.last_error()
+
+
 def test_sass_contains_blackwell_instructions():
     """The shipped .so really is tcgen05 + TMA code (B200_PROFILING.md 'what proves a Blackwell-native kernel')."""
     import shutil
