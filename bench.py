@@ -332,14 +332,16 @@ def run_native(args):
     main = torch.cuda.current_stream()
 
     def run_e2e(host_sets, step_fn, n_steps):
-        """double-buffered H2D on a copy stream, one step per batch, D2H of the 9 losses every step"""
-        dbuf = [tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_sets[0]) for _ in range(2)]
+        """H2D on a copy stream into a ring of NBUF device buffers (prefetch depth NBUF - 1), one step per batch,
+        D2H of the 9 losses every step"""
+        NBUF = 3
+        dbuf = [tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in host_sets[0]) for _ in range(NBUF)]
         loss_host = torch.empty(n_steps, 9, dtype=torch.float32).pin_memory()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(NBUF)]
+        freed = [torch.cuda.Event() for _ in range(NBUF)]
 
         def h2d(i):
-            slot = i % 2
+            slot = i % NBUF
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[slot])
                 for d, h in zip(dbuf[slot], host_sets[i % NSETS]):
@@ -347,13 +349,14 @@ def run_native(args):
                 ready[slot].record(copy_stream)
 
         def loop(n):
-            for s_ in range(2):
+            for s_ in range(NBUF):
                 freed[s_].record(main)
-            h2d(0)
+            for j in range(min(NBUF - 1, n)):
+                h2d(j)
             for i in range(n):
-                if i + 1 < n:
-                    h2d(i + 1)
-                slot = i % 2
+                if i + NBUF - 1 < n:
+                    h2d(i + NBUF - 1)
+                slot = i % NBUF
                 main.wait_event(ready[slot])
                 ls = step_fn(dbuf[slot])
                 freed[slot].record(main)
