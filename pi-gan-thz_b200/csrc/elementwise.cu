@@ -1209,6 +1209,21 @@ __global__ void __launch_bounds__(kThreads) ln_lrelu_apply_kernel(__half* __rest
 }
 
 // ------------------------------------------------------------------------------------------ optimiser
+// clears up to 4 fp32 buffers in one launch: replaces a row of cudaMemsetAsync calls, each of which is a separate
+// stream operation that also breaks the chain of programmatic dependent launches
+__global__ void __launch_bounds__(kThreads) zero_buffers_kernel(ZeroArgs a) {
+  pdl_wait();
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4* p = reinterpret_cast<uint4*>(a.ptr[k]);
+    const long long n16 = a.nfloat[k] >> 2;
+    for (long long i = tid; i < n16; i += nth) p[i] = z;
+    if (tid < (a.nfloat[k] & 3)) a.ptr[k][(n16 << 2) + tid] = 0.f;
+  }
+}
+
 // squared gradient norm, stage 1: one fp64 partial per block (no atomics: clip_adam_kernel adds the partials in a
 // fixed order, so the clip coefficient - and with it every weight - is run-to-run reproducible)
 __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ g, long long n,
@@ -1904,6 +1919,19 @@ void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const 
                            int64_t rows, int N, cudaStream_t st) {
   const int rpb = kThreads / (N / 8);
   launch_k(ln_lrelu_apply_kernel, grid_for_rows(rows, rpb * 4), kThreads, 0, st, h, rowstats, n_tiles, gamma, beta, rows, N);
+}
+void launch_zero_buffers(float* const* ptrs, const int64_t* nfloat, int count, cudaStream_t st) {
+  ZeroArgs a;
+  long long most = 0;
+  for (int k = 0; k < 4; ++k) {
+    a.ptr[k] = k < count ? ptrs[k] : nullptr;
+    a.nfloat[k] = k < count ? (long long)nfloat[k] : 0;
+    most = a.nfloat[k] > most ? a.nfloat[k] : most;
+  }
+  int grid = (int)((most / 4 + kThreads - 1) / kThreads);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid < 1) grid = 1;
+  launch_k(zero_buffers_kernel, grid, kThreads, 0, st, a);
 }
 int launch_sumsq(const float* g, int64_t n, double* parts, cudaStream_t st) {
   int grid = (int)((n + kThreads * 4 - 1) / (kThreads * 4));

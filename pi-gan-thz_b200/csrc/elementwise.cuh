@@ -178,6 +178,12 @@ void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const 
                            int64_t rows, int N, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------ optimiser
+struct ZeroArgs {
+  float* ptr[4];
+  long long nfloat[4];
+};
+// zero up to 4 fp32 buffers (16-byte aligned) in one kernel
+void launch_zero_buffers(float* const* ptrs, const int64_t* nfloat, int count, cudaStream_t st);
 // stage 1 of the squared gradient norm: returns the number of fp64 block partials written to parts (<= 296)
 int launch_sumsq(const float* g, int64_t n, double* parts, cudaStream_t st);
 struct AdamArgs {
