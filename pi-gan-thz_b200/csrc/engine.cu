@@ -1083,10 +1083,19 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   dr.keep_scale = 1.0f / (1.0f - a.dropout_p);
   e->f_loaded = false;   // the packed weights below replace the frozen surrogate's
   PM("memset");
-  PIGAN_CUDA_OK(cudaMemsetAsync(gr, 0, (size_t)L.total * sizeof(float), st));
-  PIGAN_CUDA_OK(cudaMemsetAsync(w.zero_from, 0, w.zero_bytes, st));
-  if (a.loss_sums) PIGAN_CUDA_OK(cudaMemsetAsync(a.loss_sums, 0, 2 * sizeof(float), st));
-  PIGAN_CUDA_OK(cudaMemsetAsync(w.wth[5], 0, (size_t)L.H[4] * kDoutLd * sizeof(__half), st));
+  if (((reinterpret_cast<uintptr_t>(gr) | reinterpret_cast<uintptr_t>(a.loss_sums)) & 15u) == 0 &&
+      w.zero_bytes % sizeof(float) == 0) {
+    // one kernel instead of four memset stream operations
+    float* ptrs[4] = {gr, reinterpret_cast<float*>(w.zero_from), reinterpret_cast<float*>(w.wth[5]), a.loss_sums};
+    const int64_t nf[4] = {L.total, (int64_t)(w.zero_bytes / sizeof(float)), (int64_t)L.H[4] * kDoutLd / 2,
+                           a.loss_sums ? 2 : 0};
+    launch_zero_buffers(ptrs, nf, 4, st);
+  } else {
+    PIGAN_CUDA_OK(cudaMemsetAsync(gr, 0, (size_t)L.total * sizeof(float), st));
+    PIGAN_CUDA_OK(cudaMemsetAsync(w.zero_from, 0, w.zero_bytes, st));
+    if (a.loss_sums) PIGAN_CUDA_OK(cudaMemsetAsync(a.loss_sums, 0, 2 * sizeof(float), st));
+    PIGAN_CUDA_OK(cudaMemsetAsync(w.wth[5], 0, (size_t)L.H[4] * kDoutLd * sizeof(__half), st));
+  }
   PM("pack_weights");
   for (int i = 1; i < 6; ++i) {
     const int in = L.H[i - 1], out = i < 5 ? L.H[i] : L.OUT;
