@@ -117,3 +117,19 @@ def evaluator_cases():
     err = rng.random(1000).astype(np.float32) * 5
     cons = (1.0 / (1.0 + err)).astype(np.float32)
     return cases, (viol.astype(np.int32), err, cons)
+
+
+def dataset_csv_columns():
+    """Columns of the 32-row synthetic CSV behind tests/golden/dataset.npz (same construction in
+    tools/make_golden.py: dataset and tests/test_host_logic.py)."""
+    spec, praw, pnorm, _ = make_batch(32, seed=3)
+    freqs = np.linspace(0.5, 3.0, 250)
+    cols = {f"Freq_{f:.2f}": spec[:, i].numpy() for i, f in enumerate(freqs)}
+    for i, n in enumerate(["r1", "r2", "w", "g"]):
+        cols[n] = praw[:, i].numpy()
+    rng = np.random.default_rng(0)
+    metrics = rng.uniform(0.5, 9.0, size=(32, 8))
+    metrics[3, 2] = np.nan
+    for i, n in enumerate(["f1", "f2", "Q1", "FoM1", "S1", "Q2", "FoM2", "S2"]):
+        cols[n] = metrics[:, i]
+    return cols

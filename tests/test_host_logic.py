@@ -137,6 +137,32 @@ def test_dataset_normalisation_and_denormalisation(tmp_path):
     assert dl.MetamaterialDataset("", load_data=False).metric_name_to_idx["f2"] == 1
 
 
+def test_dataset_is_bit_compatible_with_the_reference_class(tmp_path):
+    """Drop-in MetamaterialDataset / helpers vs the reference's own class on the same CSV (tests/golden/dataset.npz,
+    tools/make_golden.py: dataset): the tensors that feed the step must be identical, NaN pattern included."""
+    import pandas as pd
+    from core.utils import data_loader as dl
+    from oracle import fixtures
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dataset.npz"))
+    path = tmp_path / "data.csv"
+    pd.DataFrame(fixtures.dataset_csv_columns()).to_csv(path, index=False)
+    ds = dl.MetamaterialDataset(str(path), num_points_per_sample=250)
+    assert len(ds) == int(g["len"])
+    np.testing.assert_array_equal(np.asarray(ds.frequencies), g["frequencies"])
+    for name in ("spectra", "parameters", "metrics", "normalized_parameters", "normalized_metrics"):
+        np.testing.assert_array_equal(np.asarray(getattr(ds, name)), g[name], err_msg=name)
+    for k, (lo, hi) in ds.metric_ranges.items():
+        np.testing.assert_array_equal(np.array([lo, hi], dtype=np.float64), g[f"range_{k}"], err_msg=k)
+    for i, t in enumerate(ds[5]):
+        np.testing.assert_array_equal(t.numpy(), g[f"item5_{i}"])
+        assert t.dtype == torch.float32
+    np.testing.assert_array_equal(
+        dl.denormalize_params(torch.as_tensor(ds.normalized_parameters), ds.param_ranges).numpy(), g["denorm_params"])
+    np.testing.assert_array_equal(
+        dl.denormalize_metrics(torch.as_tensor(ds.normalized_metrics), ds.metric_ranges).numpy(), g["denorm_metrics"])
+    np.testing.assert_array_equal(dl.normalize_spectrum(torch.as_tensor(ds.spectra)).numpy(), g["norm_spectrum"])
+
+
 def test_rank_slice_partitions_every_global_batch():
     """device_data.rank_slice: contiguous, disjoint, exhaustive for any (count, world), also ragged last batches."""
     from pigan_b200.device_data import rank_slice

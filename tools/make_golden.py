@@ -14,6 +14,7 @@ outputs are stored.  What is pinned:
                    fed from explicit masks (epoch losses, first-step raw gradients, final weights, sampled)
   evaluator_metrics.npz  UnifiedEvaluator.calculate_metrics (sklearn/scipy) on seeded arrays + the numpy summary
   datagen.npz      generate_single_terahertz_spectrum_and_params: noise-free rows, rows with (stored) numpy noise
+  dataset.npz      MetamaterialDataset on a 32-row synthetic CSV: tensors, item tuple, (de)normalisation helpers
   scoring.npz      the evaluator loop (unified_evaluator.py:369-392) through UnifiedEvaluator itself with the
                    plotting modules stubbed out
 """
@@ -259,6 +260,31 @@ def datagen():
     print("datagen:", res["clean"].shape, float(res["clean"].min()))
 
 
+def dataset():
+    """The reference's MetamaterialDataset (data_loader.py:115-234) on a 32-row synthetic CSV, its item tuple and
+    the normalisation helpers (:238-330)."""
+    import pandas as pd
+    res = {}
+    tmp = tempfile.mkdtemp()
+    path = os.path.join(tmp, "data.csv")
+    pd.DataFrame(fixtures.dataset_csv_columns()).to_csv(path, index=False)
+    ds = ref_dl.MetamaterialDataset(path, num_points_per_sample=250)
+    for name in ("spectra", "parameters", "metrics", "normalized_parameters", "normalized_metrics"):
+        res[name] = np.asarray(getattr(ds, name))
+    res["frequencies"] = np.asarray(ds.frequencies)
+    for k, (lo, hi) in ds.metric_ranges.items():
+        res[f"range_{k}"] = np.array([lo, hi], dtype=np.float64)
+    item = ds[5]
+    for i, t in enumerate(item):
+        res[f"item5_{i}"] = t.numpy()
+    res["denorm_params"] = ref_dl.denormalize_params(torch.as_tensor(ds.normalized_parameters), ds.param_ranges).numpy()
+    res["denorm_metrics"] = ref_dl.denormalize_metrics(torch.as_tensor(ds.normalized_metrics), ds.metric_ranges).numpy()
+    res["norm_spectrum"] = ref_dl.normalize_spectrum(torch.as_tensor(ds.spectra)).numpy()
+    res["len"] = np.array(len(ds))
+    np.savez(os.path.join(OUT, "dataset.npz"), **res)
+    print("dataset:", {k: v.shape for k, v in res.items() if v.ndim == 2})
+
+
 def evaluator_cases():
     """Seeded inputs of the evaluator-reduction golden (rebuilt identically by the tests)."""
     cases = {}
@@ -300,6 +326,6 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen()
+        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
