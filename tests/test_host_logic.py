@@ -89,6 +89,21 @@ def test_config_surface():
     assert cfg.FORWARD_MODEL_OUTPUT_METRICS_DIM == 8 and cfg.SAVE_MODEL_INTERVAL == 50
 
 
+def test_config_constants_equal_the_reference_module():
+    """Every scalar constant of the reference's config/config.py (dumped to tests/golden/config.json in the build
+    container) exists in the drop-in module with the same value."""
+    import json
+    import config.config as cfg
+    ref = json.load(open(os.path.join(GOLD, "config.json")))
+    assert len(ref) >= 30
+    for name, value in ref.items():
+        assert hasattr(cfg, name), name
+        assert getattr(cfg, name) == value, (name, getattr(cfg, name), value)
+    for name in ("CHECKPOINT_DIR", "SAVED_MODELS_DIR", "DATA_DIR", "LOG_DIR", "PLOTS_DIR", "FULL_DATA_PATH", "PROJECT_ROOT"):
+        assert isinstance(getattr(cfg, name), str)
+    assert callable(cfg.create_directories)
+
+
 def test_loss_helpers_match_reference_golden():
     from core.utils import loss as L
     from oracle import fixtures

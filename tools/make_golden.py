@@ -285,6 +285,16 @@ def dataset():
     print("dataset:", {k: v.shape for k, v in res.items() if v.ndim == 2})
 
 
+def config_constants():
+    """Scalar constants of the reference's config/config.py (paths and the device string excluded)."""
+    import json
+    ref = {n: getattr(cfg, n) for n in dir(cfg)
+           if n.isupper() and isinstance(getattr(cfg, n), (int, float, str))
+           and not n.endswith(("_DIR", "_PATH", "ROOT")) and n != "DEVICE"}
+    json.dump(ref, open(os.path.join(OUT, "config.json"), "w"), indent=1, sort_keys=True)
+    print("config:", len(ref), "constants")
+
+
 def evaluator_cases():
     """Seeded inputs of the evaluator-reduction golden (rebuilt identically by the tests)."""
     cases = {}
@@ -326,6 +336,6 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset()
+        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset(); config_constants()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
