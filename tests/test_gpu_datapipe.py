@@ -166,3 +166,66 @@ def test_peak_shift_is_the_difference_of_argmin_frequencies():
     m = physics.peak_metrics(a)
     ok = ~torch.isnan(m["Q"])
     assert ok.float().mean() > 0.9 and torch.allclose(m["S"][ok], m["f_res"][ok] * m["Q"][ok], rtol=1e-5)
+
+
+def test_checkpoint_files_have_the_reference_layout(tmp_path):
+    """Files and their structure as written by the reference's train_pigan (train_pigan.py:284-309; golden
+    tests/golden/checkpoint_structure.json from a reference run with SAVE_MODEL_INTERVAL = 1): same file names,
+    checkpoint keys, state_dict keys / shapes / dtypes, Adam state entries and param-group hyper-parameters."""
+    import json
+    import config.config as cfg
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from core.train.train_pigan import train_pigan
+    from oracle import fixtures
+    gold = json.load(open(os.path.join(GOLD, "checkpoint_structure.json")))
+    cfg.SAVED_MODELS_DIR, cfg.CHECKPOINT_DIR = str(tmp_path / "saved"), str(tmp_path / "ckpt")
+    old = cfg.SAVE_MODEL_INTERVAL
+    cfg.SAVE_MODEL_INTERVAL = 1
+
+    class Meta:
+        param_ranges = {k: (2.2, 2.8) for k in ("r1", "r2", "w", "g")}
+        frequencies = np.linspace(0.5, 3.0, 250)
+        metric_name_to_idx = {"f1": 0, "f2": 1}
+    try:
+        spec, praw, pnorm, mnorm = fixtures.make_batch(64, seed=100)
+        F = ForwardModel(4, 250, 8)
+        F.eval()
+        train_pigan([(spec, praw, pnorm, torch.zeros(64, 8), mnorm)], torch.device(DEV), Generator(250, 4),
+                    Discriminator(250, 4), F, Meta(), num_epochs=1, log_interval=10)
+    finally:
+        cfg.SAVE_MODEL_INTERVAL = old
+    assert sorted(os.listdir(cfg.CHECKPOINT_DIR)) == gold["checkpoint_files"]
+    assert sorted(os.listdir(cfg.SAVED_MODELS_DIR)) == gold["saved_files"]
+
+    def structure(obj):
+        if isinstance(obj, dict):
+            return {str(k): structure(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return [structure(v) for v in obj]
+        if isinstance(obj, torch.Tensor):
+            return {"tensor": list(obj.shape), "dtype": str(obj.dtype)}
+        if isinstance(obj, (bool, int, float)) or obj is None:
+            return {"scalar": type(obj).__name__}
+        return {"other": type(obj).__name__}
+
+    ck = torch.load(os.path.join(cfg.CHECKPOINT_DIR, "pigan_epoch_1.pth"), map_location="cpu", weights_only=False)
+    got = structure(ck)
+    assert set(got) == set(gold["checkpoint"])
+    for key in ("generator_state_dict", "discriminator_state_dict", "forward_model_state_dict"):
+        assert got[key] == gold["checkpoint"][key], key
+    for key in ("optimizer_g_state_dict", "optimizer_d_state_dict"):
+        assert got[key]["state"] == gold["checkpoint"][key]["state"], key          # per-parameter step / exp_avg / exp_avg_sq
+        assert set(got[key]["param_groups"][0]) == set(gold["checkpoint"][key]["param_groups"][0]), key
+    pg = ck["optimizer_g_state_dict"]["param_groups"][0]
+    for k, v in gold["param_group_g"].items():
+        if k == "lr":
+            assert abs(pg[k] - v) <= 1e-12, (k, pg[k], v)       # CosineAnnealingLR after one epoch of one
+        else:
+            assert (list(pg[k]) if isinstance(pg[k], (list, tuple)) else pg[k]) == v, (k, pg[k], v)
+    hist = torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "pigan_loss_history.pt"), weights_only=False)
+    assert structure(hist) == gold["loss_history"]
+    # and the reference's modules can load what was written
+    assert set(torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "generator_final.pth"), map_location="cpu").keys()) == \
+        set(gold["checkpoint"]["generator_state_dict"])

@@ -295,6 +295,49 @@ def config_constants():
     print("config:", len(ref), "constants")
 
 
+def _structure(obj):
+    """JSON-able description of a checkpoint object: dict keys, tensor shapes / dtypes, scalar types."""
+    if isinstance(obj, dict):
+        return {str(k): _structure(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_structure(v) for v in obj]
+    if isinstance(obj, torch.Tensor):
+        return {"tensor": list(obj.shape), "dtype": str(obj.dtype)}
+    if isinstance(obj, bool) or obj is None:
+        return {"scalar": type(obj).__name__}
+    if isinstance(obj, (int, float)):
+        return {"scalar": type(obj).__name__}
+    return {"other": type(obj).__name__}
+
+
+def checkpoint_structure():
+    """Files train_pigan writes (train_pigan.py:284-309) and the layout of their contents: one epoch with
+    SAVE_MODEL_INTERVAL = 1."""
+    import json
+    tmp = tempfile.mkdtemp()
+    cfg.CHECKPOINT_DIR = os.path.join(tmp, "ckpt")
+    cfg.SAVED_MODELS_DIR = os.path.join(tmp, "saved")
+    old = cfg.SAVE_MODEL_INTERVAL
+    cfg.SAVE_MODEL_INTERVAL = 1
+    try:
+        ds = ref_dl.MetamaterialDataset("", load_data=False)
+        G, D, F = ref_models()
+        spec, praw, pnorm, mnorm = fixtures.make_batch(64, seed=100)
+        ref_train.train_pigan([(spec, praw, pnorm, torch.zeros(64, 8), mnorm)], torch.device("cpu"), G, D, F, ds,
+                              num_epochs=1, log_interval=10)
+    finally:
+        cfg.SAVE_MODEL_INTERVAL = old
+    res = {"checkpoint_files": sorted(os.listdir(cfg.CHECKPOINT_DIR)), "saved_files": sorted(os.listdir(cfg.SAVED_MODELS_DIR))}
+    ck = torch.load(os.path.join(cfg.CHECKPOINT_DIR, "pigan_epoch_1.pth"), weights_only=False)
+    res["checkpoint"] = _structure(ck)
+    res["loss_history"] = _structure(torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "pigan_loss_history.pt"),
+                                                weights_only=False))
+    res["param_group_g"] = {k: v for k, v in ck["optimizer_g_state_dict"]["param_groups"][0].items()
+                            if isinstance(v, (int, float, bool, type(None))) or k in ("betas", "params")}
+    json.dump(res, open(os.path.join(OUT, "checkpoint_structure.json"), "w"), indent=1, sort_keys=True, default=list)
+    print("checkpoint_structure:", res["checkpoint_files"], res["saved_files"], list(ck.keys()))
+
+
 def evaluator_cases():
     """Seeded inputs of the evaluator-reduction golden (rebuilt identically by the tests)."""
     cases = {}
@@ -336,6 +379,6 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset(); config_constants()
+        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset(); config_constants(); checkpoint_structure()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
