@@ -178,6 +178,20 @@ def test_dataset_is_bit_compatible_with_the_reference_class(tmp_path):
     np.testing.assert_array_equal(dl.normalize_spectrum(torch.as_tensor(ds.spectra)).numpy(), g["norm_spectrum"])
 
 
+def test_pretrain_lr_schedule_matches_torch_cosine_annealing():
+    """Drop-in pretrain_forward_model applies CosineAnnealingLR(T_max=num_epochs, eta_min=0.01 lr) in closed form
+    (pretrain_fwd_model.py:46,135): same per-epoch learning rates as torch's scheduler."""
+    import torch.optim as optim
+    from torch.optim.lr_scheduler import CosineAnnealingLR
+    from core.train.pretrain_fwd_model import cosine_lr
+    for T in (1, 3, 10, 500):
+        opt = optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+        sch = CosineAnnealingLR(opt, T_max=T, eta_min=1e-5)
+        for e in range(min(T, 15)):
+            assert abs(opt.param_groups[0]["lr"] - cosine_lr(e, T, 1e-3)) <= 1e-12, (T, e)
+            opt.step(); sch.step()
+
+
 def test_rank_slice_partitions_every_global_batch():
     """device_data.rank_slice: contiguous, disjoint, exhaustive for any (count, world), also ragged last batches."""
     from pigan_b200.device_data import rank_slice
