@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 5
+#define PIGAN_ABI_VERSION 6
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -77,6 +77,19 @@ int64_t pigan_generator_bn_buffer_count(const PiganDims* dims);
 int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s, const double* frequency,
                           const int32_t* peak_idx, float baseline_transmission, int32_t* out_idx,
                           float* out_metrics, void* stream);
+
+/* Differentiable physics metrics (the reference has no such term, F3): the vector-Jacobian product of
+ * the four metrics above with respect to the spectrum, for loss terms on Q / FoM / S of a predicted spectrum.  The
+ * branch decisions of calculate_peak_parameters (peak index, the two half-depth crossing pairs) are held fixed, as
+ * autograd does on a differentiable restatement: Q depends on t[idx] (through the half-depth level), and on the two
+ * samples of each crossing pair (through the linear interpolation, data_loader.py:24,36); FoM = Q / |t_min| adds its
+ * own t[idx] term; f_res = frequency[idx] has zero gradient.
+ *   grad_metrics [n, 4] fp32  dL/d(f_res, Q, FoM, S) (16-byte aligned)
+ *   grad_spectra [n, s] fp32  out: dL/d(spectra) — at most five non-zeros per row, all zero where Q is NaN
+ *   out_idx, out_metrics      optional forward outputs as in pigan_physics_metrics                               */
+int pigan_physics_metrics_backward(const float* spectra, int64_t n, int32_t s, const double* frequency,
+                                   const int32_t* peak_idx, float baseline_transmission, const float* grad_metrics,
+                                   float* grad_spectra, int32_t* out_idx, float* out_metrics, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Engine: owns nothing but a view of the caller's workspace (activations, fp16 operand copies of the

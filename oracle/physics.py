@@ -91,3 +91,53 @@ def physics_batch(spectra: np.ndarray, frequency: np.ndarray, peak_idx=None, bas
                                        None if pk is None else pk.ctypes.data, float(baseline),
                                        idx.ctypes.data, out.ctypes.data)
     return idx, out
+
+
+def peak_parameters_vjp(frequency, transmission_db, peak_idx, grad, baseline_transmission=0):
+    """Differentiable restatement of ``peak_parameters`` (+ sensitivity) in torch float64: the branch decisions are
+    taken exactly as above (same loops, same comparisons), the arithmetic of :16, :24, :36, :49-54 and :96 is
+    replayed on a leaf tensor and autograd returns d(sum_k grad[k] * metric_k)/d(transmission_db).  Returns
+    (metrics float64 [4] = f_res, Q, FoM, S with NaN where undefined, gradient float64 [len])."""
+    import torch
+    f = np.asarray(frequency, dtype=np.float64)
+    tn = np.asarray(transmission_db, dtype=np.float64)
+    t = torch.tensor(tn, dtype=torch.float64, requires_grad=True)
+    f_res = float(f[peak_idx])
+    t_min = t[peak_idx]
+    half = t_min + (baseline_transmission - t_min) / 2                       # :16
+    hv = float(half.detach())
+    f_lower = f_upper = None
+    for i in range(peak_idx - 1, -1, -1):                                    # :20
+        if (tn[i] >= hv and tn[i + 1] < hv) or (tn[i] < hv and tn[i + 1] >= hv):
+            if (tn[i + 1] - tn[i]) != 0:
+                f_lower = f[i] + (half - t[i]) * (f[i + 1] - f[i]) / (t[i + 1] - t[i])
+            else:
+                f_lower = torch.tensor(f[i], dtype=torch.float64)
+            break
+    for i in range(peak_idx + 1, len(f) - 1):                                # :32
+        if (tn[i] <= hv and tn[i + 1] > hv) or (tn[i] > hv and tn[i + 1] <= hv):
+            if (tn[i + 1] - tn[i]) != 0:
+                f_upper = f[i] + (half - t[i]) * (f[i + 1] - f[i]) / (t[i + 1] - t[i])
+            else:
+                f_upper = torch.tensor(f[i], dtype=torch.float64)
+            break
+    nan = float("nan")
+    q = fom = s = None
+    if f_lower is not None and f_upper is not None and float(f_upper.detach()) > float(f_lower.detach()):   # :47
+        delta_f = f_upper - f_lower
+        if float(delta_f.detach()) > 1e-9:
+            q = f_res / delta_f
+        if abs(float(t_min.detach())) > 1e-6 and q is not None:              # :53
+            fom = q / torch.abs(t_min)
+    if q is not None:
+        s = (f_res / 1.0) * (q / 100.0) * 100                                # :96
+    loss = torch.zeros((), dtype=torch.float64)
+    for gk, mk in zip(grad[1:], (q, fom, s)):
+        if mk is not None:
+            loss = loss + float(gk) * mk
+    g = np.zeros_like(tn)
+    if loss.requires_grad:
+        loss.backward()
+        g = t.grad.numpy().copy()
+    vals = [f_res] + [float(m.detach()) if m is not None else nan for m in (q, fom, s)]
+    return np.array(vals, dtype=np.float64), g

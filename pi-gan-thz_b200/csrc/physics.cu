@@ -138,11 +138,17 @@ __device__ __forceinline__ void row_scan(const float (&v)[VPL], int s, int lane,
 
 // A warp takes 32 consecutive rows: the warp-wide scan row by row (results parked in lane r for row r), then the
 // scalar fp64 interpolation of all 32 rows in parallel, one lane per row — the serial tail costs one pass per 32 rows.
-template <int VPL>
+//
+// BWD: also the vector-Jacobian product of (f_res, Q, FoM, S) with respect to the spectrum samples:
+// with the branch decisions (peak index, the two crossing pairs) held fixed, the outputs depend on at most five
+// samples of a row — t[idx] through the half-depth level and |t_min|, and the two samples of each crossing pair
+// through the linear interpolation.  The warp clears the row of grad_spectra while it scans it, the lane that owns the
+// row adds the five entries after the interpolation.  Rows whose Q is undefined get a zero gradient.
+template <int VPL, bool BWD>
 __global__ void __launch_bounds__(256) physics_metrics_kernel(
     const float* __restrict__ spectra, long long n, int s, const double* __restrict__ freq,
     const int* __restrict__ peak_idx, float baseline, int* __restrict__ out_idx,
-    float* __restrict__ out_metrics) {
+    float* __restrict__ out_metrics, const float* __restrict__ grad_metrics, float* __restrict__ grad_spectra) {
   const int lane = threadIdx.x & 31;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -173,11 +179,20 @@ __global__ void __launch_bounds__(256) physics_metrics_kernel(
           vn[j] = (j * 32 + 32 <= s || i < s) ? __ldg(t + i) : kInf;
         }
       }
+      if constexpr (BWD) {
+        float* gr = grad_spectra + (base + r) * (long long)s;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int i = j * 32 + lane;
+          if (i < s) gr[i] = 0.f;
+        }
+      }
       int idx, lo, up;
       float tmin;
       row_scan<VPL>(v, s, lane, peak_idx, base + r, baseline, idx, lo, up, tmin);
       if (lane == r) { my_idx = idx; my_lo = lo; my_up = up; my_tmin = tmin; }
     }
+    if constexpr (BWD) __syncwarp();   // the rows are cleared before their owners add to them
     if (lane < rows_here) {
       const long long row = base + lane;
       const float* t = spectra + row * (long long)s;
@@ -206,10 +221,46 @@ __global__ void __launch_bounds__(256) physics_metrics_kernel(
           if (!isnan(tm) && fabs(tm) > 1e-6) FoM = isnan(Q) ? kNaN : Q / fabs(tm);
         }
         if (!isnan(Q)) S = (f_res / 1.0) * (Q / 100.0) * 100.0;
+        if constexpr (BWD) {
+          if (!isnan(Q)) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(grad_metrics) + row);   // d/d(f_res, Q, FoM, S)
+            const double tm = (double)t_min, delta_f = f_upper - f_lower;
+            const bool fom_ok = !isnan(FoM);
+            // Q = f_res / (f_upper - f_lower), FoM = Q / |t_min|, S = f_res * Q; f_res = frequency[idx] is constant
+            const double gq = (double)gm.y + (fom_ok ? (double)gm.z / fabs(tm) : 0.0) + (double)gm.w * f_res;
+            const double g_fup = -gq * f_res / (delta_f * delta_f), g_flo = -g_fup;
+            double g_h = 0.0;
+            float* gr = grad_spectra + row * (long long)s;
+            {
+              const double ti = (double)__ldg(t + lo), tj = (double)__ldg(t + lo + 1), dt = tj - ti;
+              if (dt != 0.0) {   // f_lower = f_i + (h - t_i) w / (t_j - t_i)
+                const double w = freq[lo + 1] - freq[lo];
+                g_h += g_flo * w / dt;
+                gr[lo] += (float)(g_flo * w * (h - tj) / (dt * dt));
+                gr[lo + 1] += (float)(-g_flo * w * (h - ti) / (dt * dt));
+              }
+            }
+            {
+              const double ti = (double)__ldg(t + up), tj = (double)__ldg(t + up + 1), dt = tj - ti;
+              if (dt != 0.0) {
+                const double w = freq[up + 1] - freq[up];
+                g_h += g_fup * w / dt;
+                gr[up] += (float)(g_fup * w * (h - tj) / (dt * dt));
+                gr[up + 1] += (float)(-g_fup * w * (h - ti) / (dt * dt));
+              }
+            }
+            // h = t_min + (baseline - t_min) / 2; FoM's own dependence on |t_min|
+            double g_tmin = 0.5 * g_h;
+            if (fom_ok) g_tmin += (double)gm.z * (-Q * (tm > 0.0 ? 1.0 : -1.0) / (tm * tm));
+            gr[idx] += (float)g_tmin;
+          }
+        }
       }
       if (out_idx != nullptr) out_idx[row] = idx;   // 32 consecutive rows per warp: coalesced
-      float4 o = make_float4((float)f_res, (float)Q, (float)FoM, (float)S);
-      *reinterpret_cast<float4*>(out_metrics + row * 4) = o;
+      if (!BWD || out_metrics != nullptr) {
+        float4 o = make_float4((float)f_res, (float)Q, (float)FoM, (float)S);
+        *reinterpret_cast<float4*>(out_metrics + row * 4) = o;
+      }
     }
   }
 }
@@ -233,13 +284,41 @@ extern "C" int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s,
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   const int vpl = (s + 31) / 32;
 #define PIGAN_LAUNCH_PHYS(V)                                                                        \
-  note_launch(), physics_metrics_kernel<V><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx,    \
-                                                  baseline_transmission, out_idx, out_metrics)
+  note_launch(), physics_metrics_kernel<V, false><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx, \
+                                                  baseline_transmission, out_idx, out_metrics, nullptr, nullptr)
   if (vpl <= 8) PIGAN_LAUNCH_PHYS(8);
   else if (vpl <= 16) PIGAN_LAUNCH_PHYS(16);
   else if (vpl <= 32) PIGAN_LAUNCH_PHYS(32);
   else PIGAN_LAUNCH_PHYS(64);
 #undef PIGAN_LAUNCH_PHYS
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_physics_metrics_backward(const float* spectra, int64_t n, int32_t s, const double* frequency,
+                                              const int32_t* peak_idx, float baseline_transmission,
+                                              const float* grad_metrics, float* grad_spectra, int32_t* out_idx,
+                                              float* out_metrics, void* stream) {
+  PIGAN_CHECK_ARG(n >= 0);
+  PIGAN_CHECK_ARG(s >= 2 && s <= 2048);
+  if (n == 0) return PIGAN_OK;
+  PIGAN_CHECK_ARG(spectra != nullptr && frequency != nullptr && grad_metrics != nullptr && grad_spectra != nullptr);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(grad_metrics) & 15u) == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sm_count() <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
+  const int64_t blocks_needed = ceil_div64(ceil_div64(n, 32), 8);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  const int vpl = (s + 31) / 32;
+#define PIGAN_LAUNCH_PHYS_BWD(V)                                                                                       \
+  note_launch(), physics_metrics_kernel<V, true><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx,  \
+                                                  baseline_transmission, out_idx, out_metrics, grad_metrics,         \
+                                                  grad_spectra)
+  if (vpl <= 8) PIGAN_LAUNCH_PHYS_BWD(8);
+  else if (vpl <= 16) PIGAN_LAUNCH_PHYS_BWD(16);
+  else if (vpl <= 32) PIGAN_LAUNCH_PHYS_BWD(32);
+  else PIGAN_LAUNCH_PHYS_BWD(64);
+#undef PIGAN_LAUNCH_PHYS_BWD
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

@@ -38,3 +38,47 @@ def peak_shift(reconstructed: torch.Tensor, target: torch.Tensor, frequency: Opt
     a, b = peak_metrics(reconstructed, frequency), peak_metrics(target, frequency)
     return {"peak_shift": a["f_res"] - b["f_res"], "peak_idx_reconstructed": a["peak_idx"],
             "peak_idx_target": b["peak_idx"]}
+
+
+def peak_metrics_vjp(spectra: torch.Tensor, grad_metrics: torch.Tensor, frequency: Optional[torch.Tensor] = None,
+                     peak_idx: Optional[torch.Tensor] = None, baseline_transmission: float = 0.0) -> torch.Tensor:
+    """dL/d(spectra) [n,S] from dL/d(f_res, Q, FoM, S) [n,4] (``pigan_physics_metrics_backward``): at most five
+    non-zeros per row, zero where Q is undefined."""
+    if not spectra.is_cuda:
+        raise RuntimeError("peak_metrics_vjp needs CUDA tensors — the B200 path has no CPU fallback")
+    spec = spectra.detach().float().contiguous()
+    n, s = spec.shape
+    gm = grad_metrics.detach().to(spec.device, torch.float32).contiguous()
+    if gm.shape != (n, 4):
+        raise ValueError(f"grad_metrics must be [{n}, 4]")
+    freq = synthetic.frequencies(s, device=spec.device) if frequency is None \
+        else torch.as_tensor(frequency).to(spec.device, torch.float64).contiguous()
+    pk = None if peak_idx is None else peak_idx.to(spec.device, torch.int32).contiguous()
+    out = torch.empty_like(spec)
+    native.check(native.lib.pigan_physics_metrics_backward(spec.data_ptr(), n, s, freq.data_ptr(), native.ptr(pk),
+                                                           float(baseline_transmission), gm.data_ptr(), out.data_ptr(),
+                                                           None, None, native.current_stream()))
+    return out
+
+
+class _PeakMetrics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spectra, frequency, baseline):
+        m = peak_metrics(spectra, frequency, None, baseline)
+        ctx.save_for_backward(spectra)
+        ctx.frequency, ctx.baseline, ctx.peak_idx = frequency, baseline, m["peak_idx"]
+        return torch.stack([m["f_res"], m["Q"], m["FoM"], m["S"]], dim=1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (spectra,) = ctx.saved_tensors
+        # NaN outputs (no half-depth crossing) carry no gradient; incoming NaNs must not poison the rows that have one
+        g = torch.nan_to_num(grad_out, nan=0.0)
+        return peak_metrics_vjp(spectra, g, ctx.frequency, ctx.peak_idx, ctx.baseline), None, None
+
+
+def differentiable_peak_metrics(spectra: torch.Tensor, frequency: Optional[torch.Tensor] = None,
+                                baseline_transmission: float = 0.0) -> torch.Tensor:
+    """[n,4] = (f_res, Q, FoM, S) of every spectrum with a backward pass into the spectra, e.g. a physics-metric loss
+    ``((m - m_target)[ok] ** 2).mean()`` on a surrogate's predicted spectra (rows where Q is NaN: mask them out)."""
+    return _PeakMetrics.apply(spectra, frequency, float(baseline_transmission))

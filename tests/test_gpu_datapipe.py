@@ -229,3 +229,59 @@ def test_checkpoint_files_have_the_reference_layout(tmp_path):
     # and the reference's modules can load what was written
     assert set(torch.load(os.path.join(cfg.SAVED_MODELS_DIR, "generator_final.pth"), map_location="cpu").keys()) == \
         set(gold["checkpoint"]["generator_state_dict"])
+
+
+def test_differentiable_physics_metrics_match_the_autograd_oracle():
+    """pigan_physics_metrics_backward against oracle/physics.py: peak_parameters_vjp (torch float64
+    autograd on the reference's arithmetic with its branch decisions): fp32 outputs of fp64 math, 1e-5 relative."""
+    from oracle import fixtures
+    from oracle import physics as P
+    from pigan_b200 import physics
+    spec, *_ = fixtures.make_batch(256, seed=31)
+    freq = np.linspace(0.5, 3.0, 250)
+    rng = np.random.Generator(np.random.PCG64(7))
+    gm = rng.standard_normal((256, 4)).astype(np.float32)
+    got = physics.peak_metrics_vjp(spec.to(DEV), torch.from_numpy(gm).to(DEV)).cpu().numpy()
+    nan_rows = 0
+    for r in range(256):
+        idx = int(np.argmin(spec[r].numpy()))
+        vals, g = P.peak_parameters_vjp(freq, spec[r].numpy().astype(np.float64), idx, gm[r].astype(np.float64))
+        if np.isnan(vals[1]):
+            nan_rows += 1
+            assert not got[r].any()
+            continue
+        assert np.count_nonzero(got[r]) <= 5 and set(np.nonzero(got[r])[0]) <= set(np.nonzero(g)[0])
+        scale = np.abs(g).max()
+        assert np.max(np.abs(got[r] - g)) <= 1e-5 * scale + 1e-12, (r, np.max(np.abs(got[r] - g)), scale)
+    assert nan_rows < 64
+    # autograd Function: a metric loss on spectra reaches the spectra
+    x = spec[:64].to(DEV).clone().requires_grad_(True)
+    m = physics.differentiable_peak_metrics(x)
+    ok = ~torch.isnan(m[:, 1])
+    loss = ((m[ok, 1] - 5.0) ** 2).mean() + 0.1 * m[ok, 2].sum()
+    loss.backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+    assert float(x.grad[~ok].abs().sum()) == 0.0
+    # descent direction: a small step along -grad lowers the loss
+    with torch.no_grad():
+        m2 = physics.differentiable_peak_metrics(x - 1e-3 * x.grad / x.grad.abs().max())
+        loss2 = ((m2[ok, 1] - 5.0) ** 2).mean() + 0.1 * m2[ok, 2].sum()
+    assert float(loss2) < float(loss.detach())
+
+
+def test_physics_backward_full_size_properties():
+    """4 M spectra: at most five non-zeros per row, zero rows exactly where Q is undefined, forward outputs equal
+    the forward kernel's."""
+    from pigan_b200 import device_data as DD
+    from pigan_b200 import native, physics
+    n = 1 << 22
+    spec, _ = DD.generate_spectra(n, DEV, seed=4, noise_level=0.1)
+    gm = torch.ones(n, 4, device=DEV)
+    g = physics.peak_metrics_vjp(spec, gm)
+    m = physics.peak_metrics(spec)
+    nnz = (g != 0).sum(dim=1)
+    assert int(nnz.max()) <= 5
+    undefined = torch.isnan(m["Q"])
+    assert int(nnz[undefined].max()) == 0 if undefined.any() else True
+    assert float((nnz[~undefined] > 0).float().mean()) > 0.999
+    assert torch.isfinite(g).all()

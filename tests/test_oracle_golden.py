@@ -266,3 +266,35 @@ def test_bf16_autocast_reference_is_looser():
 
     assert rel(e16["d_grads"]["main.2.weight"].float(), e32["d_grads"]["main.2.weight"]) > 2e-3
     assert rel(e16["g_grads"]["main.3.weight"].float(), e32["g_grads"]["main.3.weight"]) > 2e-3
+
+
+def test_differentiable_physics_restatement_is_consistent():
+    """oracle/physics.py: peak_parameters_vjp — its forward values equal peak_parameters (pinned to the reference
+    above) and its gradient equals central finite differences of that function on the touched samples."""
+    spec, *_ = fixtures.make_batch(48, seed=5)
+    freq = np.linspace(0.5, 3.0, 250)
+    w = [0.3, 1.0, -2.0, 0.5]
+    seen = 0
+    for r in range(48):
+        row = spec[r].numpy().astype(np.float64)
+        idx = int(np.argmin(spec[r].numpy()))
+        f, q, fom = P.peak_parameters(freq, row, idx)
+        vals, g = P.peak_parameters_vjp(freq, row, idx, w)
+        _close(vals, [f, q, fom, P.sensitivity(f, q)], rtol=1e-12, atol=0)
+        if np.isnan(q):
+            assert not g.any()
+            continue
+        nz = np.nonzero(g)[0]
+        assert 1 <= len(nz) <= 5
+        seen += 1
+
+        def loss(x):
+            f2, q2, fom2 = P.peak_parameters(freq, x, idx)
+            return w[1] * q2 + w[2] * fom2 + w[3] * P.sensitivity(f2, q2)
+        for k in nz:
+            rp, rm = row.copy(), row.copy()
+            rp[k] += 1e-6
+            rm[k] -= 1e-6
+            fd = (loss(rp) - loss(rm)) / 2e-6
+            assert abs(fd - g[k]) <= 1e-4 * max(1.0, abs(g[k])), (r, k, fd, g[k])
+    assert seen >= 40
