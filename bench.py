@@ -447,7 +447,28 @@ def run_native(args):
                      "spectra": n_phys, "ms": ms4,
                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
-        del spec_big, o_idx, o_met
+        # backward of the same kernel: vector-Jacobian product into the spectra
+        g_met = torch.ones(n_phys, 4, device=dev)
+        g_spec = torch.empty_like(spec_big)
+
+        def phys_bwd():
+            native.check(native.lib.pigan_physics_metrics_backward(spec_big.data_ptr(), n_phys, 250, freq.data_ptr(), None,
+                                                                   0.0, g_met.data_ptr(), g_spec.data_ptr(), None, None,
+                                                                   native.current_stream()))
+        for _ in range(2):
+            phys_bwd()
+        barrier()
+        e0.record()
+        for _ in range(5):
+            phys_bwd()
+        e1.record()
+        barrier()
+        ms4b = e0.elapsed_time(e1) / 5
+        gbs_b = n_phys * 2016 / (ms4b * 1e-3) / 1e9
+        phys_info["backward"] = {"value": n_phys / (ms4b * 1e-3), "unit": "spectra/s", "ms": ms4b,
+                                 "roofline": {"bound": "hbm", "achieved": gbs_b, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                              "frac": gbs_b / peaks["hbm_gbs"], "bytes_per_spectrum": 2016}}
+        del spec_big, o_idx, o_met, g_met, g_spec
 
     # ---- on-device data pipeline: synthetic-spectrum generator, shuffled batch gather, and the
     # train step fed from a resident dataset (gather of the fp16 operand + metrics rows, then step_prepared)
