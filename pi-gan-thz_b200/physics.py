@@ -82,3 +82,30 @@ def differentiable_peak_metrics(spectra: torch.Tensor, frequency: Optional[torch
     """[n,4] = (f_res, Q, FoM, S) of every spectrum with a backward pass into the spectra, e.g. a physics-metric loss
     ``((m - m_target)[ok] ** 2).mean()`` on a surrogate's predicted spectra (rows where Q is NaN: mask them out)."""
     return _PeakMetrics.apply(spectra, frequency, float(baseline_transmission))
+
+
+METRIC_NAMES = ("f1", "f2", "Q1", "FoM1", "S1", "Q2", "FoM2", "S2")   # data_loader.py:131
+
+
+def two_peak_metrics(spectra: torch.Tensor, frequency: Optional[torch.Tensor] = None, split_thz: float = 1.5
+                     ) -> Dict[str, torch.Tensor]:
+    """The dataset's eight metric columns (f1, f2, Q1, FoM1, S1, Q2, FoM2, S2) from the spectra themselves: the band
+    below ``split_thz`` holds the first dip of the reference's generator (centre ~0.87 THz, data_loader.py:64), the
+    band above it the second (~2.1 THz, :69).  Each band's resonance index is the argmin inside the band (first
+    occurrence); Q / FoM / S come from ``calculate_peak_parameters`` at that index over the WHOLE spectrum, as the
+    reference evaluates it (:95, :104).  Returns the [n,8] tensor ``metrics`` in the reference's column order plus
+    ``peak_idx`` [n,2].  (SURVEY 8(f) N2's two-peak variant; the reference picks its peaks with scipy.find_peaks.)"""
+    if not spectra.is_cuda:
+        raise RuntimeError("two_peak_metrics needs CUDA tensors — the B200 path has no CPU fallback")
+    spec = spectra.float().contiguous()
+    s = spec.shape[1]
+    freq = synthetic.frequencies(s, device=spec.device) if frequency is None \
+        else torch.as_tensor(frequency).to(spec.device, torch.float64).contiguous()
+    k = int((freq < split_thz).sum().item())
+    if k < 1 or k >= s:
+        raise ValueError("split_thz must fall inside the frequency grid")
+    i1 = spec[:, :k].argmin(dim=1)
+    i2 = spec[:, k:].argmin(dim=1) + k
+    m1, m2 = peak_metrics(spec, freq, i1), peak_metrics(spec, freq, i2)
+    cols = [m1["f_res"], m2["f_res"], m1["Q"], m1["FoM"], m1["S"], m2["Q"], m2["FoM"], m2["S"]]
+    return {"metrics": torch.stack(cols, dim=1), "peak_idx": torch.stack([i1, i2], dim=1).to(torch.int32)}

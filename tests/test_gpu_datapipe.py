@@ -285,3 +285,27 @@ def test_physics_backward_full_size_properties():
     assert int(nnz[undefined].max()) == 0 if undefined.any() else True
     assert float((nnz[~undefined] > 0).float().mean()) > 0.999
     assert torch.isfinite(g).all()
+
+
+def test_two_peak_metrics_match_the_oracle_at_band_minima():
+    """physics.two_peak_metrics: band argmins bit-exact against numpy, the eight metric columns against
+    oracle/physics.py (calculate_peak_parameters at those indices), 1e-5."""
+    from oracle import fixtures
+    from oracle import physics as P
+    from pigan_b200 import physics
+    spec, *_ = fixtures.make_batch(300, seed=41)
+    freq = np.linspace(0.5, 3.0, 250)
+    k = int((freq < 1.5).sum())
+    r = physics.two_peak_metrics(spec.to(DEV))
+    i1, i2 = spec[:, :k].numpy().argmin(axis=1), spec[:, k:].numpy().argmin(axis=1) + k
+    assert np.array_equal(r["peak_idx"].cpu().numpy(), np.stack([i1, i2], axis=1))
+    _, a = P.physics_batch(spec.numpy(), freq, i1.astype(np.int32))
+    _, b = P.physics_batch(spec.numpy(), freq, i2.astype(np.int32))
+    ref = np.stack([a[:, 0], b[:, 0], a[:, 1], a[:, 2], a[:, 3], b[:, 1], b[:, 2], b[:, 3]], axis=1)
+    got = r["metrics"].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    np.testing.assert_allclose(got[ok], ref[ok], rtol=1e-5)
+    assert physics.METRIC_NAMES == ("f1", "f2", "Q1", "FoM1", "S1", "Q2", "FoM2", "S2")
+    # the two dips sit where the generator put them
+    assert abs(float(np.nanmean(got[:, 0])) - 0.87) < 0.05 and abs(float(np.nanmean(got[:, 1])) - 2.11) < 0.06
