@@ -106,14 +106,40 @@ class DeviceDataset:
                    t(ds.normalized_metrics), device)
 
     @classmethod
-    def synthetic(cls, n: int, device, seed: int = 42, noise_level: float = 0.1, metrics_dim: int = 8
+    def synthetic(cls, n: int, device, seed: int = 42, noise_level: float = 0.1, metrics: str = "physics"
                   ) -> "DeviceDataset":
-        """n synthetic rows generated on the device; metrics are uniform placeholders in (0,1) as in bench.py."""
+        """n synthetic rows generated on the device (spectra from ``pigan_generate_spectra``).
+        ``metrics="physics"``: the eight metric columns come from the spectra themselves (``physics.two_peak_metrics``,
+        i.e. the physics kernel at the two band minima) and are normalised as the dataset does it — min/max over the
+        non-NaN entries of each column, NaN -> 0.5 (data_loader.py:198-219); ``metric_ranges`` holds the ranges.
+        ``metrics="uniform"``: placeholders in (0,1) (what bench.py's shape-only batches use)."""
+        from . import physics
         spec, p = generate_spectra(n, device, seed=seed, noise_level=noise_level)
-        g = torch.Generator(device=device)
-        g.manual_seed(seed)
-        mn = torch.rand(n, metrics_dim, generator=g, device=device, dtype=torch.float32)
-        return cls(spec, p, (p - 2.2) / 0.6 * 2.0 - 1.0, mn, mn, device)
+        ranges = {}
+        if metrics == "uniform":
+            g = torch.Generator(device=device)
+            g.manual_seed(seed)
+            md = mn = torch.rand(n, 8, generator=g, device=device, dtype=torch.float32)
+        elif metrics == "physics":
+            md = physics.two_peak_metrics(spec)["metrics"]
+            mn = md.clone()
+            for i, name in enumerate(physics.METRIC_NAMES):
+                col = md[:, i]
+                ok = col[~torch.isnan(col)]
+                lo, hi = (float(ok.min()), float(ok.max())) if ok.numel() > 0 else (0.0, 1.0)
+                ranges[name] = (lo, hi)
+                mn[:, i] = (col - lo) / (hi - lo) if hi - lo > 1e-6 else 0.5
+            mn[torch.isnan(mn)] = 0.5
+        else:
+            raise ValueError("metrics must be 'physics' or 'uniform'")
+        ds = cls(spec, p, (p - 2.2) / 0.6 * 2.0 - 1.0, md, mn, device)
+        ds.metric_ranges = ranges
+        ds.metric_name_to_idx = {name: i for i, name in enumerate(physics.METRIC_NAMES)}
+        ds.param_ranges = {k: (2.2, 2.8) for k in ("r1", "r2", "w", "g")}
+        ds.frequencies = torch.linspace(0.5, 3.0, spec.shape[1], dtype=torch.float64).numpy()
+        # with these attributes the object can stand in for the ``dataset`` argument of train_pigan
+        # (train_pigan.py:132,162,165-166 read param_ranges, frequencies, metric_name_to_idx)
+        return ds
 
 
 class DeviceLoader:

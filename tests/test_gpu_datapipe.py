@@ -146,7 +146,8 @@ def test_reference_trainers_run_from_the_device_loader(tmp_path):
         metric_name_to_idx = {"f1": 0, "f2": 1}
     F.eval()
     lh = train_pigan(DD.DeviceLoader(ds, 128, seed=3), torch.device(DEV), Generator(250, 4), Discriminator(250, 4), F,
-                     Meta(), num_epochs=2, log_interval=10)
+                     ds, num_epochs=2, log_interval=10)     # the synthetic dataset carries what train_pigan reads
+    assert Meta.metric_name_to_idx == {k: ds.metric_name_to_idx[k] for k in ("f1", "f2")}
     assert len(lh["g_losses"]) == 2 and all(np.isfinite(v) for v in lh["g_losses"] + lh["d_losses"])
 
 
@@ -309,3 +310,25 @@ def test_two_peak_metrics_match_the_oracle_at_band_minima():
     assert physics.METRIC_NAMES == ("f1", "f2", "Q1", "FoM1", "S1", "Q2", "FoM2", "S2")
     # the two dips sit where the generator put them
     assert abs(float(np.nanmean(got[:, 0])) - 0.87) < 0.05 and abs(float(np.nanmean(got[:, 1])) - 2.11) < 0.06
+
+
+def test_synthetic_dataset_carries_physics_metrics_normalised_like_the_reference():
+    """DeviceDataset.synthetic: metric columns from the physics kernel at the two band minima, normalised with the
+    dataset's rule (min/max over non-NaN, NaN -> 0.5, data_loader.py:198-219)."""
+    from pigan_b200 import device_data as DD
+    from pigan_b200 import physics
+    ds = DD.DeviceDataset.synthetic(4096, DEV, seed=11)
+    md, mn = ds.metrics_denorm, ds.metrics_norm
+    assert md.shape == (4096, 8) and mn.shape == (4096, 8)
+    assert float(mn.min()) >= 0.0 and float(mn.max()) <= 1.0 and not torch.isnan(mn).any()
+    again = physics.two_peak_metrics(ds.spectra)["metrics"]
+    assert torch.equal(torch.nan_to_num(md, nan=-1.0), torch.nan_to_num(again, nan=-1.0))
+    for i, name in enumerate(physics.METRIC_NAMES):
+        col = md[:, i]
+        ok = ~torch.isnan(col)
+        lo, hi = ds.metric_ranges[name]
+        assert lo == float(col[ok].min()) and hi == float(col[ok].max())
+        torch.testing.assert_close(mn[ok, i], (col[ok] - lo) / (hi - lo), rtol=0, atol=1e-6)
+        assert bool((mn[~ok, i] == 0.5).all())
+    assert ds.metric_name_to_idx["f2"] == 1 and abs(float(md[:, 0].nanmean()) - 0.87) < 0.05
+    assert DD.DeviceDataset.synthetic(64, DEV, seed=1, metrics="uniform").metrics_norm.shape == (64, 8)
