@@ -3,6 +3,10 @@
 ``peak_parameters`` restates calculate_peak_parameters (reference core/utils/data_loader.py:13-58) as
 scalar Python/NumPy float64 for small cases; ``physics_batch`` calls the C restatement (oracle/physics.c)
 for millions of spectra.  ``sensitivity`` is the S its callers derive (data_loader.py:96,105).
+``peak_parameters_vjp`` is the differentiable restatement used to check ``pigan_physics_metrics_backward``: the
+reference has no gradient of these metrics, so that function is pinned to ``peak_parameters`` itself —
+same forward values, gradient equal to its central finite differences (tests/test_oracle_golden.py).
+Pinned against the reference by tests/golden/physics.npz; only tests/, smoke() and bench.py's CPU legs use it.
 """
 from __future__ import annotations
 
