@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 6
+#define PIGAN_ABI_VERSION 7
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -286,6 +286,17 @@ typedef struct PiganFwdTrainArgs {
   uint8_t* mask_dump;
 } PiganFwdTrainArgs;
 size_t pigan_fwd_train_workspace_bytes(const PiganEngine* engine);
+/* Gradient of the surrogate's regression loss with respect to its INPUT, weights frozen (the
+ * physics-loss gradient of UnifiedTrainer.train_pigan_step, /root/reference/core/train/unified_trainer.py:240-256,
+ * 325).  F runs in eval mode (Dropout = identity) on params_norm [n, param_dim];
+ *   L = w_spectrum * MSE(F(p).spectrum, spectrum) + w_metrics * MSE(F(p).metrics, metrics_norm)   (means over n rows)
+ *   out_dp [n, param_dim] = dL/d(params_norm) (16-byte aligned); out_losses [2] (device) = the two unweighted MSEs.
+ * f_params: flat parameters as for pigan_engine_load_forward_model (passing the loaded buffer keeps it loaded).
+ * workspace: pigan_fwd_train_workspace_bytes(engine). */
+int pigan_forward_model_input_grad(PiganEngine* engine, const float* f_params, const float* params_norm,
+                                   const float* spectrum, const float* metrics_norm, int64_t n, float w_spectrum,
+                                   float w_metrics, float* out_dp, float* out_losses, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 int pigan_fwd_train_step(PiganEngine* engine, const PiganFwdTrainArgs* args, void* workspace, size_t workspace_bytes,
                          void* stream);
 /* phase 0: forward + loss + backward (local gradients, already divided by global_batch); phase 1: clip + Adam */

@@ -1511,14 +1511,15 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_kernel(const float* __res
                                                               const float* __restrict__ spectrum,
                                                               const float* __restrict__ metrics,
                                                               __half* __restrict__ dout, int ld, long long rows, int S,
-                                                              int Mt, float* __restrict__ part, int ld_part) {
+                                                              int Mt, float* __restrict__ part, int ld_part,
+                                                              float w_spec, float w_met) {
   pdl_wait();
   // a lane owns the column pairs (2 lane + 64 j, +1), j < 5: 8-byte loads, 4-byte stores; S, Mt and ld are even,
   // so a pair never straddles the spectrum / metrics / padding boundaries.  Two rows per warp and trip.
   __shared__ float sm[8][328];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int OUT = S + Mt;
-  const float gs_spec = 2.0f / (float)S, gs_met = 2.0f / (float)Mt;
+  const float gs_spec = w_spec * 2.0f / (float)S, gs_met = w_met * 2.0f / (float)Mt;   // loss weights (1, 1 in training)
   constexpr int J = 5;    // covers ld <= 320
   constexpr int R = 2;
   float colsum[J][2];
@@ -1603,7 +1604,7 @@ __global__ void __launch_bounds__(kThreads, 2) ln_bwd_kernel(__half* __restrict_
                                                              const float* __restrict__ p_in,
                                                              const unsigned char* __restrict__ keepbits,
                                                              long long rows, float keep_scale,
-                                                             float* __restrict__ part) {
+                                                             float* __restrict__ part, int store_dh) {
   pdl_wait();
   constexpr int N = NCH * 256;
   constexpr int NQ = FIRST ? 7 : 3;
@@ -1715,7 +1716,7 @@ __global__ void __launch_bounds__(kThreads, 2) ln_bwd_kernel(__half* __restrict_
           acc[6][i] = fmaf(dh[i], q.w, acc[6][i]);
         }
       }
-      if constexpr (!FIRST) st_h8(da + row * N + c0, dh);
+      if (!FIRST || store_dh) st_h8(da + row * N + c0, dh);   // the first layer keeps dh only for the input gradient
     }
   }
   // block combine over the row groups in a fixed order (deterministic), then this block's row of the partial scratch
@@ -1734,6 +1735,31 @@ __global__ void __launch_bounds__(kThreads, 2) ln_bwd_kernel(__half* __restrict_
   for (int i = threadIdx.x; i < NQ * N; i += blockDim.x) prow[i] = sm[i];
 }
 
+// input gradient of the surrogate: dp[r, j] = scale * sum_c dh1[r, c] * W1[c, j]  (W1 [256, 4]); a warp per row
+__global__ void __launch_bounds__(kThreads) f_dp_kernel(const __half* __restrict__ dh1, const float* __restrict__ w1,
+                                                        float* __restrict__ dp, long long rows, float scale) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  float4 wr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wr[i] = __ldg(reinterpret_cast<const float4*>(w1) + lane * 8 + i);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    float d[8];
+    ld_h8(dh1 + row * 256 + lane * 8, d);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0 = fmaf(d[i], wr[i].x, a0);
+      a1 = fmaf(d[i], wr[i].y, a1);
+      a2 = fmaf(d[i], wr[i].z, a2);
+      a3 = fmaf(d[i], wr[i].w, a3);
+    }
+    a0 = warp_sum_f(a0); a1 = warp_sum_f(a1); a2 = warp_sum_f(a2); a3 = warp_sum_f(a3);
+    if (lane == 0) *reinterpret_cast<float4*>(dp + row * 4) = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
+  }
+}
+
 // dW1 arrives from the partial reduction as [4][256] (k-major); the state_dict layout is [256][4]
 __global__ void f_dw1_transpose_kernel(const float* __restrict__ src, float* __restrict__ dw1) {
   pdl_wait();
@@ -1742,6 +1768,12 @@ __global__ void f_dw1_transpose_kernel(const float* __restrict__ src, float* __r
   for (int j = 0; j < 4; ++j) dw1[c * 4 + j] = src[j * 256 + c];
 }
 
+__global__ void f_input_grad_losses_kernel(const float* __restrict__ sums, double n_spec, double n_met, float* out) {
+  pdl_wait();
+  if (threadIdx.x != 0) return;
+  out[0] = (float)((double)sums[0] / n_spec);
+  out[1] = (float)((double)sums[1] / n_met);
+}
 __global__ void f_train_losses_kernel(const float* __restrict__ sums, double n_spec, double n_met, float* out) {
   pdl_wait();
   if (threadIdx.x != 0) return;
@@ -1978,11 +2010,11 @@ void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, co
 }
 void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
-                       cudaStream_t st) {
+                       cudaStream_t st, float w_spec, float w_met) {
   const int OUT = S + Mt, ld_part = (OUT + 2 + 7) / 8 * 8;
   const int grid = grid_for_rows(rows, 8 * 2 * 4, kPartBlocks);
   launch_k(f_out_loss_kernel, grid, kThreads, 0, st, out, spectrum, metrics, dout, ld, (long long)rows, S, Mt, part,
-           ld_part);
+           ld_part, w_spec, w_met);
   ReduceArgs r;
   r.part = part; r.nblocks = grid; r.ld = ld_part; r.nseg = 3;
   r.seg[0] = {db_out, OUT, inv_gs};
@@ -1993,16 +2025,16 @@ void launch_f_out_loss(const float* out, const float* spectrum, const float* met
 void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const float* gamma, const float* beta,
                    const float* p_in, const unsigned char* keepbits, int64_t rows, int N, float keep_scale,
                    float* part, float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs,
-                   cudaStream_t st) {
+                   cudaStream_t st, int store_dh) {
   // partial rows are NQ * N floats wide: keep nblocks * NQ * N inside the scratch (kPartBlocks * kPartCols floats)
   const int nq = p_in ? 7 : 3;
   int cap = (int)(((size_t)kPartBlocks * kPartCols) / ((size_t)nq * N));
   if (cap > 148 * 2) cap = 148 * 2;
   const int grid = grid_for_rows(rows, (8 / (N / 256)) * (p_in ? 2 : 4) * 4, cap);
-  if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
-  else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
-  else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
-  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part);
+  if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
+  else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
+  else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
+  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
   ReduceArgs r;
   r.part = part; r.nblocks = grid; r.ld = nq * N; r.nseg = p_in ? 4 : 3;
   r.seg[0] = {dbeta, N, inv_gs};
@@ -2011,8 +2043,14 @@ void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const floa
   if (p_in) r.seg[3] = {dw1_kmajor, 4 * N, inv_gs};
   launch_reduce_partials(r, st);
 }
+void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, float scale, cudaStream_t st) {
+  launch_k(f_dp_kernel, grid_for_rows(rows, 8 * 4, 148 * 4), kThreads, 0, st, dh1, w1, dp, (long long)rows, scale);
+}
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st) {
   launch_k(f_dw1_transpose_kernel, 1, 256, 0, st, src, dw1);
+}
+void launch_f_input_grad_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st) {
+  launch_k(f_input_grad_losses_kernel, 1, 32, 0, st, sums, n_spec, n_met, out);
 }
 void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st) {
   launch_k(f_train_losses_kernel, 1, 32, 0, st, sums, n_spec, n_met, out);

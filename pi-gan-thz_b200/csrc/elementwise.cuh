@@ -240,14 +240,17 @@ void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, co
 // loss + output-layer gradient; db_out[S+Mt] += inv_gs * column sums of dout, loss_sums[2] += sums of squares
 void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
-                       cudaStream_t st);
+                       cudaStream_t st, float w_spec = 1.f, float w_met = 1.f);
 // keepbits: [rows, N / 8] bytes written by the forward kernels (bit i = column 8 k + i kept).
 // da -> dh in place (not for the first layer, p_in != null, whose dW1 comes out k-major [4][N] instead)
 void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const float* gamma, const float* beta,
                    const float* p_in, const unsigned char* keepbits, int64_t rows, int N, float keep_scale,
                    float* part, float* dgamma, float* dbeta, float* dbias, float* dw1_kmajor, float inv_gs,
-                   cudaStream_t st);
+                   cudaStream_t st, int store_dh = 0);
+// dp[r, 0:4] = scale * dh1[r, :] . W1   (input gradient of the first layer; dh1 kept by launch_ln_bwd(store_dh = 1))
+void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, float scale, cudaStream_t st);
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st);
+void launch_f_input_grad_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 
 }  // namespace pigan

@@ -1024,6 +1024,7 @@ struct FTrainWs {
   __half* dout;
   __half* dbuf[2];
   __half* wth[6];     // transposed fp16 weights: [in_i, out_i] (layer 5: [256, kDoutLd])
+  float* grads_scratch;   // [L.total] parameter-gradient sink of pigan_forward_model_input_grad (weights frozen)
   float* dw1_tmp;     // [4][256]
   double* sumsq;
   float* loss_sums;   // [2] (used when the caller passes none)
@@ -1046,6 +1047,7 @@ struct FTrainWs {
     wth[0] = nullptr;
     for (int i = 1; i < 5; ++i) wth[i] = c.take<__half>((size_t)L.H[i - 1] * L.H[i]);
     wth[5] = c.take<__half>((size_t)L.H[4] * kDoutLd);
+    grads_scratch = c.take<float>((size_t)L.total);
     dw1_tmp = c.take<float>(4 * L.H[0]);
     zero_from = reinterpret_cast<uint8_t*>(dw1_tmp);
     sumsq = c.take<double>(1);
@@ -1055,11 +1057,19 @@ struct FTrainWs {
   }
 };
 
-int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrainWs& w, cudaStream_t st) {
+// input_grad: weights frozen (A19) — no weight-gradient GEMMs, the small parameter gradients go to a scratch buffer,
+// the first layer keeps dh and the gradient with respect to params_norm is written to dp_out
+struct FwdRunOpts {
+  bool input_grad = false;
+  float w_spec = 1.f, w_met = 1.f;
+  float* dp_out = nullptr;
+};
+int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrainWs& w, cudaStream_t st,
+                    const FwdRunOpts& opt = FwdRunOpts()) {
   const FwdLayout& L = e->fl;
   const int64_t n = a.batch;
   float* fp = a.f_params;
-  float* gr = a.f_grads;
+  float* gr = opt.input_grad ? w.grads_scratch : a.f_grads;
   float* loss_sums = a.loss_sums ? a.loss_sums : w.loss_sums;
   const float inv_gs = (float)(1.0 / (double)a.global_batch);
   if (phase == 1) {
@@ -1081,7 +1091,7 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   dr.step = (unsigned int)a.step;
   dr.thresh16 = (unsigned int)lround((double)a.dropout_p * 65536.0);
   dr.keep_scale = 1.0f / (1.0f - a.dropout_p);
-  e->f_loaded = false;   // the packed weights below replace the frozen surrogate's
+  if (fp != e->f_params) e->f_loaded = false;   // the packed weights below replace the frozen surrogate's
   PM("memset");
   if (((reinterpret_cast<uintptr_t>(gr) | reinterpret_cast<uintptr_t>(a.loss_sums)) & 15u) == 0 &&
       w.zero_bytes % sizeof(float) == 0) {
@@ -1128,11 +1138,12 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   PIGAN_TRY(f_out_layer(e, act[4], n, fo, st));
   PM("f_out_loss");
   launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
-                    loss_sums, inv_gs, st);
+                    loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
   // ---- backward
   PM("f_wgrad_gemm");
-  PIGAN_TRY(weight_grad(w.dout, n, L.OUT, act[4], n, L.H[4], gr + L.w[5], L.H[4], L.H[4], inv_gs, -1, nullptr, 0,
-                        nullptr, 0, e->dw_part, st, kDoutLd));
+  if (!opt.input_grad)
+    PIGAN_TRY(weight_grad(w.dout, n, L.OUT, act[4], n, L.H[4], gr + L.w[5], L.H[4], L.H[4], inv_gs, -1, nullptr, 0,
+                          nullptr, 0, e->dw_part, st, kDoutLd));
   PM("f_dgrad_gemm");
   __half* d = w.dbuf[0];
   __half* d2 = w.dbuf[1];
@@ -1141,14 +1152,16 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
     PM("f_ln_bwd");
     launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], i == 0 ? a.params_norm : nullptr,
                   w.keepbits[i], n, L.H[i], dr.keep_scale, e->partials, gr + L.ln_w[i], gr + L.ln_b[i], gr + L.b[i],
-                  w.dw1_tmp, inv_gs, st);
+                  w.dw1_tmp, inv_gs, st, (i == 0 && opt.input_grad) ? 1 : 0);
     if (i == 0) {
-      launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
+      if (opt.input_grad) launch_f_dp(d, fp + L.w[0], opt.dp_out, n, inv_gs, st);
+      else launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
       break;
     }
     PM("f_wgrad_gemm");
-    PIGAN_TRY(weight_grad(d, n, L.H[i], act[i - 1], n, L.H[i - 1], gr + L.w[i], L.H[i - 1], L.H[i - 1], inv_gs, -1,
-                          nullptr, 0, nullptr, 0, e->dw_part, st));
+    if (!opt.input_grad)
+      PIGAN_TRY(weight_grad(d, n, L.H[i], act[i - 1], n, L.H[i - 1], gr + L.w[i], L.H[i - 1], L.H[i - 1], inv_gs, -1,
+                            nullptr, 0, nullptr, 0, e->dw_part, st));
     PM("f_dgrad_gemm");
     PIGAN_TRY((linear_store<false, false, false>(d, n, L.H[i], w.wth[i], L.H[i - 1], nullptr, d2, nullptr, st)));
     __half* t = d;
@@ -1174,6 +1187,39 @@ int check_fwd_train_args(const PiganEngine* e, const PiganFwdTrainArgs* a, const
   return PIGAN_OK;
 }
 }  // namespace
+
+extern "C" int pigan_forward_model_input_grad(PiganEngine* e, const float* f_params, const float* params_norm,
+                                              const float* spectrum, const float* metrics_norm, int64_t n,
+                                              float w_spectrum, float w_metrics, float* out_dp, float* out_losses,
+                                              void* workspace, size_t workspace_bytes, void* stream) {
+  PIGAN_CHECK_ARG(e && f_params && params_norm && spectrum && metrics_norm && out_dp && out_losses && workspace);
+  PIGAN_CHECK_ARG(n >= 1 && n <= e->max_batch && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dp) & 15u) == 0);
+  FTrainWs w;
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  if (workspace_bytes < need)
+    return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", workspace_bytes, need);
+  w.carve(workspace, e->fl, e->max_batch);
+  PiganFwdTrainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params_norm = params_norm; a.spectrum = spectrum; a.metrics_norm = metrics_norm;
+  a.batch = a.global_batch = n;
+  a.f_params = const_cast<float*>(f_params);   // read only on this path
+  a.step = 1;
+  a.dropout_p = 0.f;                           // eval mode: Dropout is the identity
+  a.losses = out_losses;
+  FwdRunOpts opt;
+  opt.input_grad = true;
+  opt.w_spec = w_spectrum;
+  opt.w_met = w_metrics;
+  opt.dp_out = out_dp;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PIGAN_TRY(fwd_train_phase(e, a, 0, w, st, opt));
+  // out_losses[0..1] = unweighted MSE(spectrum), MSE(metrics) of this batch
+  launch_f_input_grad_losses(w.loss_sums, (double)n * e->fl.S, (double)n * e->fl.Mt, out_losses, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
 
 extern "C" size_t pigan_fwd_train_workspace_bytes(const PiganEngine* e) {
   if (!e) return 0;

@@ -93,6 +93,25 @@ class Engine:
                                               native.current_stream()))
         return out
 
+    def forward_model_input_grad(self, f_flat, params_norm, spectrum, metrics_norm, w_spectrum: float = 1.0,
+                                 w_metrics: float = 0.0):
+        """(dL/d params_norm [n,4], losses [2]) for L = w_spectrum * MSE(F(p).spectrum, spectrum) + w_metrics *
+        MSE(F(p).metrics, metrics_norm) with the surrogate's weights frozen and Dropout off — the physics-loss gradient
+        of the reference's UnifiedTrainer (unified_trainer.py:240-256, 325)."""
+        _require_cuda(params_norm, "params_norm")
+        p, sp, mn = _f32c(params_norm), _f32c(spectrum), _f32c(metrics_norm)
+        n = p.shape[0]
+        if getattr(self, "_ftrain_ws", None) is None:
+            self._ftrain_ws = torch.empty(lib.pigan_fwd_train_workspace_bytes(self.handle), dtype=torch.uint8,
+                                          device=self.device)
+        dp = torch.empty(n, self.dims.param_dim, device=p.device, dtype=torch.float32)
+        losses = torch.empty(2, device=p.device, dtype=torch.float32)
+        check(lib.pigan_forward_model_input_grad(self.handle, f_flat.data_ptr(), p.data_ptr(), sp.data_ptr(),
+                                                 mn.data_ptr(), n, float(w_spectrum), float(w_metrics), dp.data_ptr(),
+                                                 losses.data_ptr(), self._ftrain_ws.data_ptr(),
+                                                 self._ftrain_ws.numel(), native.current_stream()))
+        return dp, losses
+
     # ------------------------------------------------------------------ training
     def make_train_args(self, **kw) -> PiganTrainArgs:
         a = PiganTrainArgs()

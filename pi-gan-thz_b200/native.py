@@ -121,6 +121,7 @@ SIGNATURES = {
     "pigan_inverse_design_search": (_i32, [_vp, _vp, _vp, _vp, _f32, C.c_uint64, _i64, _i64, _i32, _vp, _vp, _vp, _vp,
                                            _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_workspace_bytes": (C.c_size_t, [_vp]),
+    "pigan_forward_model_input_grad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_step": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_step_phase": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _i32, _vp, C.c_size_t, _vp]),
     "pigan_eval_workspace_bytes": (C.c_size_t, [_i32]),

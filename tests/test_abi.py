@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_layout_counts():
     from pigan_b200 import native
-    assert native.lib.pigan_abi_version() == 6
+    assert native.lib.pigan_abi_version() == 7
     d = native.default_dims()
     assert (d.spectrum_dim, d.param_dim, d.metrics_dim) == (250, 4, 8)
     # parameter counts of the reference modules

@@ -298,3 +298,30 @@ def test_differentiable_physics_restatement_is_consistent():
             fd = (loss(rp) - loss(rm)) / 2e-6
             assert abs(fd - g[k]) <= 1e-4 * max(1.0, abs(g[k])), (r, k, fd, g[k])
     assert seen >= 40
+
+
+def test_bf16_autocast_input_gradient_yardstick():
+    """Yard-stick for tests/test_gpu_fwd_train.py::test_input_gradient_with_frozen_weights_matches_autograd: the
+    reference's forward model under torch.autocast(bfloat16) moves d MSE(F(p).spectrum, s)/dp by more than 5e-2
+    against fp32 (8.8e-2 measured), fp32 itself is within 1e-5 of fp64 — the per-row input gradient is
+    ill-conditioned with respect to rounding of the activations, not a kernel property."""
+    _, _, f_sd = fixtures.make_weights(42)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(256, seed=23)
+
+    def grad(sd, p0, target, autocast):
+        p = p0.clone().requires_grad_(True)
+        if autocast:
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                ps, _ = O.forward_model_forward(sd, p, 250, training=False)
+                loss = O.mse(ps.float(), target)
+        else:
+            ps, _ = O.forward_model_forward(sd, p, 250, training=False)
+            loss = O.mse(ps, target)
+        loss.backward()
+        return p.grad
+
+    g32 = grad(f_sd, pnorm, spec, False)
+    g16 = grad(f_sd, pnorm, spec, True)
+    g64 = grad({k: v.double() for k, v in f_sd.items()}, pnorm.double(), spec.double(), False)
+    assert float((g16 - g32).norm() / g32.norm()) > 5e-2
+    assert float((g32.double() - g64).norm() / g64.norm()) < 1e-5
