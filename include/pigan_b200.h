@@ -378,6 +378,8 @@ int pigan_topk_smallest(const float* scores, const int64_t* in_indices, int64_t 
 int pigan_debug_set_ln_trace(void* device_buffer);
 int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32_t m, int32_t n, int32_t k,
                         int32_t variant, void* stream);
+/* on != 0: pigan_debug_linear uses the streamed-operand kernel even where production keeps the weights resident */
+int pigan_debug_force_streamed(int32_t on);
 int pigan_debug_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out_f16,
                        float* rowstats, int32_t m, int32_t n, int32_t k, int32_t leaky, void* stream);
 /* same as pigan_debug_linear through the two-CTA (cta_group::2) kernel */

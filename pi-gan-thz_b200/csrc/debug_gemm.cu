@@ -57,10 +57,9 @@ static int run_tn(const void* a, const void* b, float* c, int m, int n, int k, c
   return launch_gemm<Cfg, EpiDebug<Cfg, MODE>>(ta, tb, g, ep, st);
 }
 
-template <bool BIAS, bool LRELU, bool RS>
-static int run_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out,
-                      float* rowstats, int m, int n, int k, cudaStream_t st) {
-  using Cfg = GemmCfg<256, 1, 3, false>;
+template <bool BIAS, bool LRELU, bool RS, class Cfg>
+static int run_linear_cfg(const void* a, const void* a_tail, const void* b, const float* bias, void* out,
+                          float* rowstats, int m, int n, int k, cudaStream_t st) {
   using Epi = EpiStore<Cfg, BIAS, LRELU, RS>;
   CUtensorMap ta, tb, tx;
   PIGAN_TRY(make_tn_maps<Cfg>(&ta, &tb, a, m, k, k, b, n, k));
@@ -70,11 +69,24 @@ static int run_linear(const void* a, const void* a_tail, const void* b, const fl
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  PIGAN_TRY(make_tmap_f16_2d(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n, 64, kBlockM));
+  PIGAN_TRY(make_tmap_f16_store(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
   ep.bias = bias;
+  ep.scale = nullptr;
   ep.rowstats = rowstats;
   ep.n_tiles = g.num_n_groups;
+  ep.mask = nullptr;
+  ep.mask_words = 0;
   return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
+}
+// K <= 256: the production path keeps the weights resident in shared memory (engine.cu: CfgSR); g_force_streamed
+// selects the streamed-operand kernel for the same shape (tools/gemm_perf.py compares the two)
+static bool g_force_streamed = false;
+template <bool BIAS, bool LRELU, bool RS>
+static int run_linear(const void* a, const void* a_tail, const void* b, const float* bias, void* out,
+                      float* rowstats, int m, int n, int k, cudaStream_t st) {
+  if (k <= 256 && !g_force_streamed)
+    return run_linear_cfg<BIAS, LRELU, RS, GemmCfg<256, 1, 4, false, 4>>(a, a_tail, b, bias, out, rowstats, m, n, k, st);
+  return run_linear_cfg<BIAS, LRELU, RS, GemmCfg<256, 1, 4, false>>(a, a_tail, b, bias, out, rowstats, m, n, k, st);
 }
 
 template <bool BIAS, bool LRELU, bool RS>
@@ -91,7 +103,7 @@ static int run_linear2(const void* a, const void* a_tail, const void* b, const f
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  PIGAN_TRY(make_tmap_f16_2d(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n, 64, kBlockM));
+  PIGAN_TRY(make_tmap_f16_store(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
   ep.bias = bias;
   ep.scale = nullptr;
   ep.rowstats = rowstats;
@@ -119,6 +131,11 @@ extern "C" int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32
     case 12: return run_tn<GemmCfg<256, 1, 3, false>, 1>(a, b, c, m, n, k, st);
     default: return fail(PIGAN_ERR_INVALID, "unknown gemm variant %d", variant);
   }
+}
+
+extern "C" int pigan_debug_force_streamed(int32_t on) {
+  g_force_streamed = on != 0;
+  return PIGAN_OK;
 }
 
 extern "C" int pigan_debug_linear(const void* a, const void* a_tail, const void* b, const float* bias,

@@ -19,12 +19,15 @@ namespace {
 
 constexpr int kDwPartSlabs = 160;  // >= SM count: one slab per (output tile, k-split) unit
 constexpr int kKp = 256;  // spectrum operand width (S + P + 2 spare columns <= 256)
-using CfgS = GemmCfg<256, 1, 3, false>;   // store epilogues (2 x 32 KB staging)
-using CfgP = GemmCfg<256, 1, 4, false>;   // no staging
-using CfgO = GemmCfg<144, 2, 2, false>;   // forward-model output layer (64 KB target tile in the epilogue)
-using CfgW = GemmCfg<256, 1, 4, true>;    // weight gradients
-using CfgL1 = GemmCfg<256, 1, 3, false>;  // Linear+LayerNorm, 256 columns per CTA
-using CfgL2 = GemmCfg<256, 2, 3, false>;  // Linear+LayerNorm, 512 columns per CTA (all of TMEM)
+using CfgS = GemmCfg<256, 1, 4, false>;      // store epilogues, both operands streamed (K > 256)
+using CfgSR = GemmCfg<256, 1, 4, false, 4>;  // store epilogues, K <= 256: the n-group's weights stay in shared memory
+using CfgP = GemmCfg<256, 1, 4, false>;      // no staging
+using CfgPR = GemmCfg<256, 1, 6, false, 4>;  // no staging, resident weights
+using CfgO = GemmCfg<144, 2, 2, false>;      // forward-model output layer (64 KB target tile in the epilogue)
+using CfgW = GemmCfg<256, 1, 4, true>;       // weight gradients
+using CfgL1 = GemmCfg<256, 1, 3, false>;     // Linear+LayerNorm, 256 columns per CTA
+using CfgL1R = GemmCfg<256, 1, 3, false, 4>; // Linear+LayerNorm, K <= 256, resident weights
+using CfgH = GemmCfg<256, 1, 3, false>;      // scoring: generator layer 2 + head + surrogate layer 1 (24 KB epilogue scratch)
 
 // loss_sums indices (fp64)
 enum { kSumD = 0, kSumAdv = 1, kSumRec = 2, kSumMet = 3, kSumMaxwell = 4, kSumLc1 = 5, kSumLc2 = 6, kSumRange = 7,
@@ -233,13 +236,25 @@ int run_tn(typename Epi::Params& ep, const __half* a, int64_t m, int k, int lda,
 }
 
 int out_map(CUtensorMap* m, __half* ptr, int64_t rows, int cols, int ld) {
-  return make_tmap_f16_2d(m, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld, 64, kBlockM);
+  return make_tmap_f16_store(m, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
 }
 
 // out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
 template <bool BIAS, bool LRELU, bool RS, bool MASKOUT = false>
 int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
                  float* rowstats, cudaStream_t st, const __half* a_tail = nullptr, uint32_t* mask = nullptr) {
+  if (k <= CfgSR::B_RES_KB * kBlockK) {
+    using Epi = EpiStore<CfgSR, BIAS, LRELU, RS, MASKOUT>;
+    typename Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+    ep.bias = bias;
+    ep.scale = nullptr;
+    ep.rowstats = rowstats;
+    ep.n_tiles = ceil_div(n, 256);
+    ep.mask = mask;
+    ep.mask_words = n / 32;
+    return run_tn<CfgSR, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
+  }
   using Epi = EpiStore<CfgS, BIAS, LRELU, RS, MASKOUT>;
   typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
@@ -255,26 +270,30 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
 // bias / gamma / beta are HOST pointers here: they travel to the kernel by value (constant bank)
-template <int CLUSTER, bool PAIR = false>
+template <int CLUSTER, bool PAIR = false, class Cfg = CfgL1>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
                 const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
-  using Epi = EpiLnStore<CfgL1, CLUSTER, PAIR>;
-  static typename Epi::Params ep;   // 12.5 KB: keep it off the stack
+  using Epi = EpiLnStore<Cfg, CLUSTER, PAIR>;
+  static thread_local typename Epi::Params ep;   // 12.5 KB: keep it off the stack (per thread: engines may be driven
+                                                 // from several host threads)
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
   memcpy(ep.consts, bias, n * sizeof(float));
   memcpy(ep.consts + 1024, gamma, n * sizeof(float));
   memcpy(ep.consts + 2048, beta, n * sizeof(float));
   ep.n_total = n;
   ep.trace = g_ln_trace ? g_ln_trace + (n == 1024 ? 1 : n == 256 ? 3 : (k == 256 ? 0 : 2)) * 320 : nullptr;
-  return launch_gemm<CfgL1, Epi>(ta, tb, g, ep, st);
+  return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st);
 }
 int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, const float* gamma,
               const float* beta, __half* out, cudaStream_t st) {
   CUtensorMap ta, tb;
   PIGAN_TRY(make_tn_maps<CfgL1>(&ta, &tb, a, (int)rows, k, k, w, n, k));
   const GemmShape g = make_shape<CfgL1>((int)rows, n, k);
-  if (n == 256) return linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
-  if (n == 512) return linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  const bool res = k <= CfgL1R::B_RES_KB * kBlockK;   // K <= 256: weights resident in shared memory
+  if (n == 256) return res ? linear_ln_c<1, false, CfgL1R>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st)
+                           : linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  if (n == 512) return res ? linear_ln_c<2, false, CfgL1R>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st)
+                           : linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
   if (n == 1024) {   // clusters of 2, each CTA walks two n-groups per row tile (clusters of 4 fit only 132 SMs)
     GemmShape gp = g;
     gp.pair_mode = 1;
@@ -406,7 +425,7 @@ int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cud
   const GenLayout& G = e->gl;
   {
     PM("g_l1_gemm");
-    using Epi = EpiStore<CfgS, false, false, false, false, true>;
+    using Epi = EpiStore<CfgSR, false, false, false, false, true>;
     Epi::Params ep;
     PIGAN_TRY(out_map(&ep.out, e->g_a1, n, G.H1, G.H1));
     ep.bias = e->bias1;
@@ -415,16 +434,16 @@ int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cud
     ep.n_tiles = 0;
     ep.mask = nullptr;
     ep.mask_words = 0;
-    PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st)));
+    PIGAN_TRY((run_tn<CfgSR, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st)));
   }
   if (with_f1 && fused_head(e)) {
     PM("g_l2_head_f1_gemm");
-    using Epi = EpiHeadF1<CfgS>;
+    using Epi = EpiHeadF1<CfgH>;
     Epi::Params ep;
     PIGAN_TRY(out_map(&ep.out, e->f_a1, n, e->fl.H[0], e->fl.H[0]));
     ep.p_out = p_out;
     ep.img = e->head_img;
-    return run_tn<CfgS, Epi>(ep, e->g_a1, n, G.H1, G.H1, e->g_w2h, G.H2, G.H1, st);
+    return run_tn<CfgH, Epi>(ep, e->g_a1, n, G.H1, G.H1, e->g_w2h, G.H2, G.H1, st);
   }
   PM("g_l2_gemm");
   PIGAN_TRY((linear_store<false, false, false>(e->g_a1, n, G.H1, e->g_w2h, G.H2, nullptr, e->g_h2, nullptr, st)));
@@ -646,12 +665,12 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
                       BP + B, D.H2, inv_gs, e->partials, st);
       {
         PM("d_dh1_gemm");
-        using Epi = EpiLeakyMaskStore<CfgS>;
+        using Epi = EpiLeakyMaskStore<CfgSR>;
         Epi::Params ep;
         PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
         ep.mask = e->d_mask1;
         ep.mask_words = D.H1 / 32;
-        PIGAN_TRY((run_tn<CfgS, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+        PIGAN_TRY((run_tn<CfgSR, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
       PM("d_dw2_gemm");
       PIGAN_TRY(weight_grad(e->d_dh2, BP + B, D.H2, e->d_z1, BP + B, D.H1, a.d_grads + D.w2, D.H1, D.H1, inv_gs, -1,
@@ -679,9 +698,9 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, e->partials, st);
       {
         PM("d_paramgrad_gemm");
-        using Epi = EpiDiscParamGrad<CfgP>;
+        using Epi = EpiDiscParamGrad<CfgPR>;
         Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
-        PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+        PIGAN_TRY((run_tn<CfgPR, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
       if (e->side_pending) {
         PIGAN_CUDA_OK(cudaStreamWaitEvent(st, e->ev_join, 0));   // the surrogate chain started in phase 2

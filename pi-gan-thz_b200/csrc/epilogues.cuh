@@ -1,6 +1,6 @@
 // Fused epilogues of the tcgen05 GEMM.  One thread owns one output row of the 128-row tile and walks
-// its accumulator columns out of TMEM in chunks of 32; fp16 outputs are staged through 128B-swizzled
-// shared memory and written with TMA stores (coalesced, clipped at the tensor bounds).
+// its accumulator columns out of TMEM in blocks of 32 (the next block's load in flight); fp16 outputs are staged
+// per warp through swizzled shared memory and written with TMA stores (coalesced, clipped at the tensor bounds).
 //
 // Measured on B200 these K<=1024 layers are bound by epilogue issue slots, not by the tensor pipe, so
 // the epilogues are kept to a few instructions per element: per-column constants are fetched with
@@ -15,8 +15,7 @@
 
 namespace pigan {
 
-constexpr int kStageBytes = 16384;  // one [128 x 64] fp16 sub-tile
-constexpr int kEpiStagingBytes = 2 * kStageBytes;
+constexpr int kStageBytes = 16384;  // one [128 x 64] fp16 sub-tile (TMA-loaded target tiles of EpiFwdOut, fp32 dW boxes)
 constexpr float kLeaky = 0.2f;
 
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, kLeaky * x); }  // valid for slope < 1
@@ -50,41 +49,99 @@ __device__ __forceinline__ void load_cols32(const float* __restrict__ base, floa
   }
 }
 
-// Double-buffered staging of [128 x 64] fp16 sub-tiles for TMA stores (one instance per epilogue group).
-struct Stager {
+// Per-warp staging of fp16 output blocks for TMA stores.  A warp owns 32 rows of the tile (its TMEM lane quarter);
+// it packs 32 columns of them into a [32 x 32] fp16 block (64-byte rows, 64B-swizzled: conflict-free 16-byte stores
+// with a row per thread) and lane 0 issues the TMA store.  Two blocks per warp alternate, so the store of one block
+// overlaps the arithmetic of the next; nothing is shared between warps - no named barriers on the store path.
+// (Round 1 staged [128 x 64] blocks per epilogue GROUP behind two bar.sync each and waited for the TMA unit to have
+// read a block before its buffer was reused; profiles/r02_ln_trace_before.txt shows 1900 cycles per block of that.)
+// Per group: 4 warps x 2 blocks x 2 KB = 16 KB.
+constexpr int kWarpBlockBytes = 2048;
+constexpr int kEpiStagingBytes = 4 * 2 * kWarpBlockBytes;
+
+struct WarpStager {
   uint32_t cnt;
-  __device__ __forceinline__ void init() { cnt = 0; }
-  __device__ __forceinline__ uint32_t acquire(const EpiCtx& cx) {
-    if (cx.tid == 0) tma_store_wait_read<1>();  // the store that used this buffer two commits ago is done
-    epi_bar_sync(cx, 0);
-    return cx.smem + (cnt & 1u) * kStageBytes;
+  uint32_t base;   // this warp's two blocks
+  __device__ __forceinline__ void init(const EpiCtx& cx) {
+    cnt = 0;
+    base = cx.smem + (uint32_t)(cx.tid >> 5) * (2u * kWarpBlockBytes);
   }
-  // 32 values of this thread's row -> columns [32h, 32h+32) of the sub-tile (128B-swizzled rows)
-  __device__ __forceinline__ static void put32(uint32_t buf, int r, int h, const float* v) {
+  __device__ __forceinline__ uint32_t acquire(const EpiCtx& cx) {
+    if (cx.lane == 0) tma_store_wait_read<1>();  // the store that used this block two commits ago has read it
+    __syncwarp();
+    return base + (cnt & 1u) * kWarpBlockBytes;
+  }
+  // 32 values of this thread's row (lane = row within the warp's 32 rows)
+  __device__ __forceinline__ static void put32(uint32_t buf, int lane, const float* v) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = h * 4 + i;
-      const uint32_t addr = buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t addr = buf + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                   "r"(pack_half2(v[8 * i + 0], v[8 * i + 1])), "r"(pack_half2(v[8 * i + 2], v[8 * i + 3])),
-                   "r"(pack_half2(v[8 * i + 4], v[8 * i + 5])), "r"(pack_half2(v[8 * i + 6], v[8 * i + 7]))
+                   "r"(pack_half2(v[8 * j + 0], v[8 * j + 1])), "r"(pack_half2(v[8 * j + 2], v[8 * j + 3])),
+                   "r"(pack_half2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_half2(v[8 * j + 6], v[8 * j + 7]))
                    : "memory");
     }
   }
-  __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const CUtensorMap* m, int col0,
-                                         int row0) {
+  // already packed: 16 words = 32 halves
+  __device__ __forceinline__ static void put32_packed(uint32_t buf, int lane, const uint32_t* h) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t addr = buf + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h[4 * j]), "r"(h[4 * j + 1]),
+                   "r"(h[4 * j + 2]), "r"(h[4 * j + 3])
+                   : "memory");
+    }
+  }
+  // col0: first of the 32 columns; row0: first row of the 128-row tile
+  __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const CUtensorMap* m, int col0, int row0) {
     fence_proxy_async_smem();
-    epi_bar_sync(cx, 1);
-    if (cx.tid == 0) {
-      tma_store_2d(m, buf, col0, row0);
+    __syncwarp();
+    if (cx.lane == 0) {
+      tma_store_2d(m, buf, col0, row0 + cx.q * 32);
       tma_store_commit();
     }
     ++cnt;
   }
   __device__ __forceinline__ static void drain(const EpiCtx& cx) {
-    if (cx.tid == 0) tma_store_wait<0>();
+    if (cx.lane == 0) tma_store_wait<0>();
   }
 };
+
+// Walks NCOLS accumulator columns of this thread's row: one tcgen05.ld.x64 (64 columns, 8 KB per warp) at a time,
+// f(c, v) is called for each 32-column block.  Loads of several warps of an SM sub-partition overlap each other and
+// the other warps' arithmetic: 8 epilogue warps drain and pack a 128 x 256 tile in ~1100 cycles this way against 2650
+// with .x32 loads that are waited for one by one (tools/micro/ldtm_bench2.cu, profiles/r02_ldtm_bench2.txt).  Keeping a
+// second register set in flight inside one warp was tried: ptxas places both 32-register destinations on the same
+// range and spills the live set (840 bytes of spill stores per thread).
+// GROUP = columns per trip of the (not unrolled) loop: 64, or 128 when f collects something per 128 columns in
+// registers (mask words); the loop is deliberately NOT unrolled across trips - ptxas would hoist the next trip's
+// load above this trip's arithmetic and run out of registers.
+template <int NCOLS, int GROUP = 64, class F>
+__device__ __forceinline__ void drain_blocks32(uint32_t tacc, F&& f) {
+  static_assert(NCOLS % GROUP == 0 && GROUP % 64 == 0, "pairs of 32-column blocks");
+#pragma unroll 1
+  for (int c0 = 0; c0 < NCOLS; c0 += GROUP) {
+#pragma unroll
+    for (int c = 0; c < GROUP; c += 64) {
+      float v[64];
+      tmem_ld64(tacc + c0 + c, v);
+      tmem_ld_wait();
+      f(c0 + c, c / 32, v);
+      f(c0 + c + 32, c / 32 + 1, v + 32);
+    }
+  }
+}
+// .x32 loads, fully unrolled (callers that keep per-column state in registers: the LayerNorm stash)
+template <int NCOLS, class F>
+__device__ __forceinline__ void drain_blocks32_unrolled(uint32_t tacc, F&& f) {
+#pragma unroll
+  for (int c = 0; c < NCOLS; c += 32) {
+    float v[32];
+    tmem_ld32(tacc + c, v);
+    tmem_ld_wait();
+    f(c, v);
+  }
+}
 
 // =====================================================================================================
 // out = fp16(act(acc + bias)).  Linear layers of G (generator.py:18,21), F (forward_model.py:30-56) and
@@ -94,7 +151,7 @@ struct Stager {
 // =====================================================================================================
 template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false>
 struct EpiStore {
-  static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "EpiStore tile shape");
+  static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1 && (!MASKOUT || Cfg::BLOCK_N % 128 == 0), "EpiStore tile shape");
   struct Params {
     CUtensorMap out;
     const float* bias;
@@ -110,75 +167,59 @@ struct EpiStore {
   static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = 1;
   struct State {
-    Stager stg;
+    WarpStager stg;
   };
-  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) { st.stg.init(); }
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx& cx) { st.stg.init(cx); }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     float s1 = 0.f, s2 = 0.f;
-    uint32_t mw[Cfg::BLOCK_N / 32];
+    uint32_t mw[4];
+    const int row = w.m_tile * kBlockM + r;
+    drain_blocks32<Cfg::BLOCK_N, MASKOUT ? 128 : 64>(tacc, [&](int c, int k, float* v) {
+      if constexpr (AFFINE_RELU) {
+        float b[32], sc[32];
+        load_cols32(p.bias + n0 + c, b);
+        load_cols32(p.scale + n0 + c, sc);
 #pragma unroll
-    for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(sc[i], v[i], b[i]), 0.f);
+      } else if constexpr (BIAS) {
+        float b[32];
+        load_cols32(p.bias + n0 + c, b);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += b[i];
+      }
+      if constexpr (LRELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+      }
+      if constexpr (ROWSTATS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s1 += v[i];
+          s2 = fmaf(v[i], v[i], s2);
+        }
+      }
+      if constexpr (MASKOUT) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+        mw[k] = bits;
+        if (k == 3 && row < g.M)   // 128 columns done: one 16-byte store
+          *reinterpret_cast<uint4*>(p.mask + (size_t)row * p.mask_words + (n0 + c - 96) / 32) =
+              make_uint4(mw[0], mw[1], mw[2], mw[3]);
+      }
       const uint32_t buf = st.stg.acquire(cx);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = sub * 64 + h * 32;
-        float v[32];
-        tmem_ld32(tacc + c, v);
-        if constexpr (AFFINE_RELU) {
-          float b[32], sc[32];
-          load_cols32(p.bias + n0 + c, b);
-          load_cols32(p.scale + n0 + c, sc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(sc[i], v[i], b[i]), 0.f);
-        } else if constexpr (BIAS) {
-          float b[32];
-          load_cols32(p.bias + n0 + c, b);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += b[i];
-        } else {
-          tmem_ld_wait();
-        }
-        if constexpr (LRELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
-        }
-        if constexpr (ROWSTATS) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            s1 += v[i];
-            s2 = fmaf(v[i], v[i], s2);
-          }
-        }
-        if constexpr (MASKOUT) {
-          uint32_t bits = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-          mw[sub * 2 + h] = bits;
-        }
-        Stager::put32(buf, r, h, v);
-      }
-      st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
-    }
-    if constexpr (MASKOUT) {
-      const int row = w.m_tile * kBlockM + r;
-      if (row < g.M) {
-        uint4* dst = reinterpret_cast<uint4*>(p.mask + (size_t)row * p.mask_words + n0 / 32);
-#pragma unroll
-        for (int k = 0; k < Cfg::BLOCK_N / 128; ++k) dst[k] = make_uint4(mw[4 * k], mw[4 * k + 1], mw[4 * k + 2], mw[4 * k + 3]);
-      }
-    }
+      WarpStager::put32(buf, cx.lane, v);
+      st.stg.commit(cx, buf, &p.out, n0 + c, w.m_tile * kBlockM);
+    });
     if constexpr (ROWSTATS) {
-      const int row = w.m_tile * kBlockM + r;
       if (row < g.M)
         *reinterpret_cast<float2*>(p.rowstats + ((size_t)row * p.n_tiles + w.n_group) * 2) = make_float2(s1, s2);
     }
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
 };
 
 // =====================================================================================================
@@ -215,32 +256,23 @@ struct EpiLnStore {
     // with them in shared memory pass 2 took 6-7k cycles per tile even when it read no tensor memory at all.
     float consts[3 * 1024];
   };
-  // per group: [0,32K) store staging | [32K,+8K) row-partial slots written by the groups / CTAs that share the row
+  // per group: [0,16K) per-warp store staging | [16K,+8K) row-partial slots written by the groups / CTAs that share the row
   static constexpr int kSlotOff = kEpiStagingBytes;   // two buffers of [PARTS][128] float2, alternating per unit
   static constexpr int kSlotBytes = 4096;
   static_assert(PARTS * 128 * 8 <= kSlotBytes, "slot buffer");
-  static constexpr int SMEM_BYTES = 40960;
+  static constexpr int SMEM_BYTES = kEpiStagingBytes + 2 * kSlotBytes;
   struct State {
-    Stager stg;
+    WarpStager stg;
     uint32_t xphase;
     uint32_t it;
     uint32_t rank;
   };
   __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
-    st.stg.init();
+    st.stg.init(cx);
     st.xphase = 0;
     st.it = 0;
     st.rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
     epi_bar_sync(cx, 0);
-  }
-  __device__ static void lds32(uint32_t addr, float* out) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float4 t;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr + 16u * k) : "memory");
-      out[4 * k + 0] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
-    }
   }
   // 16 consecutive per-column constants from the kernel-parameter (constant) bank
   __device__ static void ldc16(const float* src, float* out) {
@@ -266,22 +298,22 @@ struct EpiLnStore {
     float s1, s2;
     {
       float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+      drain_blocks32_unrolled<NG>(tacc, [&](int c, float* v) {
 #pragma unroll
-      for (int c = 0; c < NG; c += 16) {
-        float v[16], b[16];
-        tmem_ld16(tacc + c, v);
-        ldc16(cbias + c, b);
-        tmem_ld_wait();
+        for (int h = 0; h < 32; h += 16) {
+          float b[16];
+          ldc16(cbias + c + h, b);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x = v[i] + b[i];
-          v[i] = x;
-          a1[i & 3] += x;
-          a2[i & 3] = fmaf(x, x, a2[i & 3]);
+          for (int i = 0; i < 16; ++i) {
+            const float x = v[h + i] + b[i];
+            v[h + i] = x;
+            a1[i & 3] += x;
+            a2[i & 3] = fmaf(x, x, a2[i & 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stash[(c + h) / 2 + i] = pack_half2(v[h + 2 * i], v[h + 2 * i + 1]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) stash[c / 2 + i] = pack_half2(v[2 * i], v[2 * i + 1]);
-      }
+      });
       s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
     }
@@ -322,36 +354,27 @@ struct EpiLnStore {
     // ---- pass 2, from the register stash: normalise, LeakyReLU, fp16, TMA store
     const int col0 = (int)part * NG;
 #pragma unroll
-    for (int sub = 0; sub < NG / 64; ++sub) {
-      const uint32_t buf = st.stg.acquire(cx);
+    for (int c = 0; c < NG; c += 32) {
+      uint32_t hw[16];
 #pragma unroll
-      for (int q16 = 0; q16 < 4; ++q16) {
-        const int c = sub * 64 + q16 * 16;
-        float gm[16], bt[16], v[16];
-        ldc16(cgamma + c, gm);
-        ldc16(cbeta + c, bt);
+      for (int h = 0; h < 32; h += 16) {
+        float gm[16], bt[16];
+        ldc16(cgamma + c + h, gm);
+        ldc16(cbeta + c + h, bt);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&stash[c / 2 + i]));
-          v[2 * i] = lrelu(fmaf((f.x - mean) * rstd, gm[2 * i], bt[2 * i]));
-          v[2 * i + 1] = lrelu(fmaf((f.y - mean) * rstd, gm[2 * i + 1], bt[2 * i + 1]));
-        }
-        // 16 values -> two 16-byte chunks of this row in the swizzled [128 x 64] fp16 staging tile
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int j = q16 * 2 + i;
-          const uint32_t addr = buf + (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_half2(v[8 * i + 0], v[8 * i + 1])), "r"(pack_half2(v[8 * i + 2], v[8 * i + 3])),
-                       "r"(pack_half2(v[8 * i + 4], v[8 * i + 5])), "r"(pack_half2(v[8 * i + 6], v[8 * i + 7]))
-                       : "memory");
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&stash[(c + h) / 2 + i]));
+          hw[h / 2 + i] = pack_half2(lrelu(fmaf((f.x - mean) * rstd, gm[2 * i], bt[2 * i])),
+                                     lrelu(fmaf((f.y - mean) * rstd, gm[2 * i + 1], bt[2 * i + 1])));
         }
       }
-      st.stg.commit(cx, buf, &p.out, col0 + sub * 64, w.m_tile * kBlockM);
+      const uint32_t buf = st.stg.acquire(cx);
+      WarpStager::put32_packed(buf, cx.lane, hw);
+      st.stg.commit(cx, buf, &p.out, col0 + c, w.m_tile * kBlockM);
     }
     if (tr) trow[3] = clock64();
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
 };
 
 // =====================================================================================================
@@ -383,11 +406,11 @@ struct EpiDiscL2 {
   static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = 1;
   struct State {
-    Stager stg;
+    WarpStager stg;
     float loss;
   };
-  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) {
-    st.stg.init();
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx& cx) {
+    st.stg.init(cx);
     st.loss = 0.f;
   }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
@@ -396,27 +419,21 @@ struct EpiDiscL2 {
     const int row = w.m_tile * kBlockM + r;
     const bool valid = row < g.M && !(row >= p.row_gap_begin && row < p.row_gap_end);
     float lg[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (a single one is latency-bound)
-#pragma unroll 1
-    for (int sub = 0; sub < 4; ++sub) {
-      uint32_t buf = 0;
-      if (p.store_z2) buf = st.stg.acquire(cx);
+    drain_blocks32<256>(tacc, [&](int c, int, float* v) {
+      float b[32], w3[32];
+      load_cols32(p.b2 + c, b);
+      load_cols32(p.w3 + c, w3);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = sub * 64 + h * 32;
-        float v[32], b[32], w3[32];
-        tmem_ld32(tacc + c, v);
-        load_cols32(p.b2 + c, b);
-        load_cols32(p.w3 + c, w3);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = lrelu(v[i] + b[i]);
-          lg[i & 3] = fmaf(v[i], w3[i], lg[i & 3]);
-        }
-        if (p.store_z2) Stager::put32(buf, r, h, v);
+      for (int i = 0; i < 32; ++i) {
+        v[i] = lrelu(v[i] + b[i]);
+        lg[i & 3] = fmaf(v[i], w3[i], lg[i & 3]);
       }
-      if (p.store_z2) st.stg.commit(cx, buf, &p.z2, sub * 64, w.m_tile * kBlockM);
-    }
+      if (p.store_z2) {
+        const uint32_t buf = st.stg.acquire(cx);
+        WarpStager::put32(buf, cx.lane, v);
+        st.stg.commit(cx, buf, &p.z2, c, w.m_tile * kBlockM);
+      }
+    });
     float logit = (lg[0] + lg[1]) + (lg[2] + lg[3]);
     if (valid) {
       logit += __ldg(p.b3);
@@ -436,7 +453,7 @@ struct EpiDiscL2 {
   __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
     const float l = warp_sum(st.loss);
     if (cx.lane == 0 && l != 0.f && p.loss_sum) atomicAdd(p.loss_sum, (double)l);
-    Stager::drain(cx);
+    WarpStager::drain(cx);
   }
 };
 
@@ -456,42 +473,30 @@ struct EpiLeakyMaskStore {
   static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = 1;
   struct State {
-    Stager stg;
+    WarpStager stg;
   };
-  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx&) { st.stg.init(); }
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx& cx) { st.stg.init(cx); }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
     const int row = w.m_tile * kBlockM + r;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     const bool valid = row < g.M;
-    uint32_t mw[Cfg::BLOCK_N / 32];
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32);
+    // the row's sign bits for this tile (two 16-byte loads issued before the first tensor-memory load is waited for)
+    static_assert(Cfg::BLOCK_N == 256, "mask words of a 256-column tile");
+    const uint4* msrc = reinterpret_cast<const uint4*>(p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32);
+    const uint4 mA = __ldg(msrc), mB = __ldg(msrc + 1);
+    drain_blocks32<Cfg::BLOCK_N, 128>(tacc, [&](int c, int k, float* v) {
+      const uint4 m4 = (c >> 7) ? mB : mA;
+      const uint32_t bits = k == 0 ? m4.x : k == 1 ? m4.y : k == 2 ? m4.z : m4.w;
 #pragma unroll
-      for (int k = 0; k < Cfg::BLOCK_N / 128; ++k) {
-        const uint4 t = __ldg(src + k);
-        mw[4 * k] = t.x; mw[4 * k + 1] = t.y; mw[4 * k + 2] = t.z; mw[4 * k + 3] = t.w;
-      }
-    }
-#pragma unroll
-    for (int sub = 0; sub < Cfg::BLOCK_N / 64; ++sub) {
+      for (int i = 0; i < 32; ++i) v[i] *= ((bits >> i) & 1u) ? 1.f : kLeaky;
       const uint32_t buf = st.stg.acquire(cx);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = sub * 64 + h * 32;
-        float v[32];
-        tmem_ld32(tacc + c, v);
-        tmem_ld_wait();
-        const uint32_t bits = mw[sub * 2 + h];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= ((bits >> i) & 1u) ? 1.f : kLeaky;
-        Stager::put32(buf, r, h, v);
-      }
-      st.stg.commit(cx, buf, &p.out, n0 + sub * 64, w.m_tile * kBlockM);
-    }
+      WarpStager::put32(buf, cx.lane, v);
+      st.stg.commit(cx, buf, &p.out, n0 + c, w.m_tile * kBlockM);
+    });
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
 };
 
 // =====================================================================================================
@@ -501,7 +506,7 @@ struct EpiLeakyMaskStore {
 // =====================================================================================================
 template <class Cfg>
 struct EpiDiscParamGrad {
-  static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N % 32 == 0, "tile shape");
+  static_assert(Cfg::ACC_TILES == 1 && Cfg::BLOCK_N % 128 == 0, "tile shape");
   struct Params {
     const uint32_t* mask;  // [M][mask_words] sign bits of z1 (EpiStore MASKOUT)
     int mask_words;
@@ -518,14 +523,13 @@ struct EpiDiscParamGrad {
     const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     const bool valid = row < g.M;
-    const uint32_t* mrow = p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32;
+    static_assert(Cfg::BLOCK_N == 256, "mask words of a 256-column tile");
+    const uint4* msrc = reinterpret_cast<const uint4*>(p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32);
+    const uint4 mA = __ldg(msrc), mB = __ldg(msrc + 1);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
-      float v[32];
-      tmem_ld32(tacc + c, v);
-      const uint32_t bits = __ldg(mrow + c / 32);
-      tmem_ld_wait();
+    drain_blocks32<Cfg::BLOCK_N, 128>(tacc, [&](int c, int k, float* v) {
+      const uint4 m4 = (c >> 7) ? mB : mA;
+      const uint32_t bits = k == 0 ? m4.x : k == 1 ? m4.y : k == 2 ? m4.z : m4.w;
       const float4* wq = reinterpret_cast<const float4*>(p.wp) + n0 + c;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -536,7 +540,7 @@ struct EpiDiscParamGrad {
         a2 = fmaf(gz, w4.z, a2);
         a3 = fmaf(gz, w4.w, a3);
       }
-    }
+    });
     if (valid) {
       atomicAdd(p.dparams + (size_t)row * 4 + 0, a0);
       atomicAdd(p.dparams + (size_t)row * 4 + 1, a1);
@@ -576,11 +580,11 @@ struct EpiHeadF1 {
     float* p_out;       // [M,4] predicted parameters (tanh output)
     const float* img;   // kHeadImgFloats constants, layout above
   };
-  // per group: [0,32K) store staging | [32K,40K) one half of the constant image (group 0: floats [0,2048),
+  // per group: [0,16K) per-warp store staging | [16K,24K) one half of the constant image (group 0: floats [0,2048),
   // group 1: floats [2048,3584)); both groups read both halves.
-  static constexpr int SMEM_BYTES = 40960;
+  static constexpr int SMEM_BYTES = kEpiStagingBytes + 8192;
   struct State {
-    Stager stg;
+    WarpStager stg;
   };
   __device__ static uint32_t part_a(const EpiCtx& cx) { return cx.smem0 + kEpiStagingBytes; }
   __device__ static uint32_t part_b(const EpiCtx& cx) { return cx.smem0 + SMEM_BYTES + kEpiStagingBytes; }
@@ -595,7 +599,7 @@ struct EpiHeadF1 {
     return v;
   }
   __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
-    st.stg.init();
+    st.stg.init(cx);
     const int base = cx.group == 0 ? 0 : 2048, n4 = cx.group == 0 ? 512 : 384;
     const uint32_t dst = cx.group == 0 ? part_a(cx) : part_b(cx);
     const float4* src = reinterpret_cast<const float4*>(p.img + base);
@@ -613,13 +617,9 @@ struct EpiHeadF1 {
     const uint32_t pa = part_a(cx), pb = part_b(cx);
     // ---- generator head: the only pass over tensor memory
     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll 2
-    for (int c = 0; c < 256; c += 16) {
-      float v[16];
-      tmem_ld16(tacc + c, v);
-      tmem_ld_wait();
+    drain_blocks32<256>(tacc, [&](int c, int, float* v) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < 16; ++t) {
         const uint32_t ad = pa + (uint32_t)(c / 2 + t) * 48u;
         const float4 sb = lds4(ad), w0 = lds4(ad + 16), w1 = lds4(ad + 32);
         const float a0 = fmaxf(fmaf(sb.x, v[2 * t], sb.y), 0.f);
@@ -627,7 +627,7 @@ struct EpiHeadF1 {
         d0 = fmaf(a0, w0.x, d0); d1 = fmaf(a0, w0.y, d1); d2 = fmaf(a0, w0.z, d2); d3 = fmaf(a0, w0.w, d3);
         d0 = fmaf(a1, w1.x, d0); d1 = fmaf(a1, w1.y, d1); d2 = fmaf(a1, w1.z, d2); d3 = fmaf(a1, w1.w, d3);
       }
-    }
+    });
     tc_fence_before();
     mbar_arrive(cx.tempty);   // accumulator drained: the MMAs of the unit after next may start
     const float4 b3 = lds4(pa + 1536 * 4);
@@ -651,25 +651,22 @@ struct EpiHeadF1 {
     }
     const float q0 = p0 * rs, q1 = p1 * rs, q2 = p2 * rs, q3 = p3 * rs;
 #pragma unroll 1
-    for (int sub = 0; sub < 4; ++sub) {
-      const uint32_t buf = st.stg.acquire(cx);
+    for (int blk = 0; blk < 8; ++blk) {
+      float v[32];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int c = sub * 64 + hh * 32 + i;
-          const float4 gb = lds4(pb + 4096u + (uint32_t)c * 8u);   // (g*bc, beta) of columns c, c+1
-          const float4 g0 = lds4(pb + (uint32_t)c * 16u), g1 = lds4(pb + (uint32_t)c * 16u + 16u);
-          v[i] = lrelu(fmaf(g0.w, q3, fmaf(g0.z, q2, fmaf(g0.y, q1, fmaf(g0.x, q0, fmaf(gb.x, rs, gb.y))))));
-          v[i + 1] = lrelu(fmaf(g1.w, q3, fmaf(g1.z, q2, fmaf(g1.y, q1, fmaf(g1.x, q0, fmaf(gb.z, rs, gb.w))))));
-        }
-        Stager::put32(buf, r, hh, v);
+      for (int i = 0; i < 32; i += 2) {
+        const int c = blk * 32 + i;
+        const float4 gb = lds4(pb + 4096u + (uint32_t)c * 8u);   // (g*bc, beta) of columns c, c+1
+        const float4 g0 = lds4(pb + (uint32_t)c * 16u), g1 = lds4(pb + (uint32_t)c * 16u + 16u);
+        v[i] = lrelu(fmaf(g0.w, q3, fmaf(g0.z, q2, fmaf(g0.y, q1, fmaf(g0.x, q0, fmaf(gb.x, rs, gb.y))))));
+        v[i + 1] = lrelu(fmaf(g1.w, q3, fmaf(g1.z, q2, fmaf(g1.y, q1, fmaf(g1.x, q0, fmaf(gb.z, rs, gb.w))))));
       }
-      st.stg.commit(cx, buf, &p.out, sub * 64, w.m_tile * kBlockM);
+      const uint32_t buf = st.stg.acquire(cx);
+      WarpStager::put32(buf, cx.lane, v);
+      st.stg.commit(cx, buf, &p.out, blk * 32, w.m_tile * kBlockM);
     }
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
 };
 
 // =====================================================================================================
@@ -950,7 +947,9 @@ struct EpiWeightGradPartial {
       }
     }
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { Stager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) {
+    if (cx.tid == 0) tma_store_wait<0>();
+  }
 };
 
 // =====================================================================================================

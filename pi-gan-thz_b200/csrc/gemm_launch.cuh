@@ -28,6 +28,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   int grid = units < ctas ? units : ctas;
+  if constexpr (Cfg::B_RESIDENT) {
+    // a CTA keeps the weights of ONE n-group: its units must all share it (u = block + it * grid, n_group = u % groups)
+    if (g.k_splits != 1 || g.pair_mode || g.num_k_blocks > Cfg::B_RES_KB)
+      return fail(PIGAN_ERR_INVALID, "resident-B GEMM: K up to %d, no split-K / pair mode", Cfg::B_RES_KB * kBlockK);
+    if (grid > g.num_n_groups) grid -= grid % g.num_n_groups;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);

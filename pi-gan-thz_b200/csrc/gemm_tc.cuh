@@ -78,24 +78,35 @@ __device__ __forceinline__ bool get_unit(const GemmShape& g, int it, UnitInfo& w
   return true;
 }
 
-template <int BLOCK_N_, int ACC_TILES_, int STAGES_, bool MN_MAJOR_>
+// B_RES_KB > 0 ("resident B", TN mode): the CTA keeps the whole B operand of ITS n-group - B_RES_KB k-blocks, e.g.
+// 4 x 32 KB for a 256-column group of a K = 256 layer - in shared memory for the lifetime of the kernel and only
+// streams A.  Measured on B200 (profiles/r02_*): with both operands streamed a 128 x 256 x 256 unit moves 64 KB of A,
+// 128 KB of B and 64 KB of output through the L2 <-> SM fabric (~42 B/clk per SM) for 2048 MMA cycles, i.e. the
+// K = 256 layers were bound by re-reading the weights once per 128 rows; resident weights halve that traffic.
+// Needs gridDim.x % num_n_groups == 0 (a CTA then sees one n-group only) and K <= 64 * B_RES_KB.
+template <int BLOCK_N_, int ACC_TILES_, int STAGES_, bool MN_MAJOR_, int B_RES_KB_ = 0>
 struct GemmCfg {
   static constexpr int BLOCK_N = BLOCK_N_;
   static constexpr int ACC_TILES = ACC_TILES_;
   static constexpr int STAGES = STAGES_;
   static constexpr bool MN_MAJOR = MN_MAJOR_;
+  static constexpr int B_RES_KB = B_RES_KB_;
+  static constexpr bool B_RESIDENT = B_RES_KB_ > 0;
   static constexpr int ACC_COLS = BLOCK_N * ACC_TILES;
   static constexpr int ACC_BUFS = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int B_TILE_BYTES = BLOCK_N * kBlockK * 2;
   // keep every stage base 1024-B aligned (swizzle atom)
   static constexpr int B_TILE_ALLOC = (B_TILE_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = kATileBytes + B_TILE_ALLOC;
-  static constexpr int TX_BYTES = kATileBytes + B_TILE_BYTES;
-  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int RES_BYTES = B_RES_KB * B_TILE_ALLOC;
+  static constexpr int STAGE_BYTES = kATileBytes + (B_RESIDENT ? 0 : B_TILE_ALLOC);
+  static constexpr int TX_BYTES = kATileBytes + (B_RESIDENT ? 0 : B_TILE_BYTES);
+  static constexpr int PIPE_BYTES = RES_BYTES + STAGES * STAGE_BYTES + 256 /*barriers*/;
   static constexpr int SMEM_BYTES = PIPE_BYTES + 1024 /*align slack*/;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(!MN_MAJOR || BLOCK_N % 64 == 0, "NT mode loads B in 64-wide boxes");
+  static_assert(!B_RESIDENT || (!MN_MAJOR && ACC_TILES == 1), "resident B: TN mode, one accumulator tile per unit");
+  static_assert(2 * STAGES + 8 <= 32, "barrier block");
 };
 
 // What an epilogue thread knows about itself.
@@ -145,7 +156,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   static_assert(Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(Epi::SMEM_BYTES % 1024 == 0, "epilogue scratch must keep 1024-B alignment");
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // resident B k-blocks (B_RESIDENT), else empty
+  const uint32_t smem_base = res_base + Cfg::RES_BYTES;                 // operand ring
   const uint32_t epi_smem = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
   const uint32_t bar_base = epi_smem + 2 * Epi::SMEM_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -154,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
   const uint32_t xbar = bar_base + 8u * (2 * Cfg::STAGES + 5);  // SPLIT epilogues: per-unit row-partial exchange
+  const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::STAGES + 7);  // resident B has landed
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -173,6 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     mbar_init(xbar, epi_xbar_count<Epi>::value);   // one per epilogue group (see EpiLnStore)
     mbar_init(xbar + 8u, epi_xbar_count<Epi>::value);
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -194,6 +208,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       UnitInfo w;
+      if constexpr (Cfg::B_RESIDENT) {
+        // every unit of this CTA has the same n-group (host: gridDim.x % num_n_groups == 0): fetch its weights once
+        if (get_unit<Epi::CLUSTER>(g, 0, w)) {
+          mbar_arrive_expect_tx(bres_bar, (uint32_t)g.num_k_blocks * Cfg::B_TILE_BYTES);
+          for (int kb = 0; kb < g.num_k_blocks; ++kb)
+            tma_load_2d(res_base + kb * Cfg::B_TILE_ALLOC, &tmap_b, bres_bar, kb * kBlockK,
+                        w.n_group * Cfg::BLOCK_N);
+        }
+      }
       for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
         for (int t = 0; t < Cfg::ACC_TILES; ++t) {
           const int nt = w.n_group * Cfg::ACC_TILES + t;
@@ -208,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tma_load_2d(sa, &tmap_x, full_bar(stage), 0, w.m_tile * kBlockM);
               else
                 tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, w.m_tile * kBlockM);
-              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+              if constexpr (!Cfg::B_RESIDENT) tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
             } else {
               const int kb_b = g.b_wrap_k_blocks ? (kb % g.b_wrap_k_blocks) : kb;
 #pragma unroll
@@ -241,6 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       UnitInfo w;
+      if constexpr (Cfg::B_RESIDENT) {
+        if (get_unit<Epi::CLUSTER>(g, 0, w)) mbar_wait(bres_bar, 0);
+      }
       for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
         const int buf = it % Cfg::ACC_BUFS;
         const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
@@ -252,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-            const uint32_t sb = sa + kATileBytes;
+            const uint32_t sb = Cfg::B_RESIDENT ? res_base + (uint32_t)(kb * Cfg::B_TILE_ALLOC) : sa + kATileBytes;
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               const uint64_t da = umma_desc_sw128(sa + k * kstep, lbo, 1024);

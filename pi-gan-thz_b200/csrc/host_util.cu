@@ -78,6 +78,24 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return PIGAN_OK;
 }
 
+// TMA-store target of the epilogues' per-warp staging: fp16 [rows, cols], box = 32 rows x 32 columns (64-byte rows),
+// 64B swizzle (epilogues.cuh: WarpStager)
+int make_tmap_f16_store(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
+  auto fn = encode_fn();
+  if (fn == nullptr) return fail(PIGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_elems * 2) % 16 != 0)
+    return fail(PIGAN_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple pitch");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PIGAN_ERR_CUDA, "cuTensorMapEncodeTiled(store) failed (CUresult %d)", (int)r);
+  return PIGAN_OK;
+}
+
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_outer) {
   auto fn = encode_fn();

@@ -45,6 +45,9 @@ int sm_count();  // multiprocessors of the current device (cached per device)
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer,
                      uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
 
+// Row-major fp16 [rows, cols] as the TMA-store target of an epilogue warp: box = 32 rows x 32 columns, 64B swizzle.
+int make_tmap_f16_store(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems);
+
 // Row-major 2-D fp32 tensor, box = [box_outer, 32 floats] (128 B rows), 128B swizzle: TMA-store target of fp32 tiles.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_outer);

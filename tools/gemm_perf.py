@@ -31,6 +31,11 @@ for n, k, bias, leaky, rs in [(512, 256, False, False, False), (512, 256, True, 
     st = native.current_stream()
     f = lambda: native.check(native.lib.pigan_debug_linear(a.data_ptr(), None, b.data_ptr(), native.ptr(bias_t), out.data_ptr(), native.ptr(rowst), M, n, k, int(leaky), st))
     ms = timeit(f)
+    if k <= 256:   # production keeps the weights resident for K <= 256: also time the streamed-operand kernel
+        native.lib.pigan_debug_force_streamed(1)
+        ms_streamed = timeit(f)
+        native.lib.pigan_debug_force_streamed(0)
+        print(f"   streamed-operand kernel for the same shape: {ms_streamed:.4f} ms (resident: {ms:.4f} ms)", flush=True)
     ref = timeit(lambda: torch.nn.functional.linear(a, b))
     res.append(dict(kind="linear", bias=bias, leaky=leaky, rowstats=rs, M=M, N=n, K=k, ms=round(ms,4), tflops=round(2*M*n*k/ms/1e9,1), hbm_gbs=round((M*k*2+M*n*2)/ms/1e6), cublas_ms=round(ref,4), cublas_tflops=round(2*M*n*k/ref/1e9,1)))
     print(res[-1], flush=True)
