@@ -69,7 +69,7 @@ static int run_linear_cfg(const void* a, const void* a_tail, const void* b, cons
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  PIGAN_TRY(make_tmap_f16_store(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
+  ep.out = OutTile{static_cast<__half*>(out), n, m, n};
   ep.bias = bias;
   ep.scale = nullptr;
   ep.rowstats = rowstats;
@@ -103,7 +103,7 @@ static int run_linear2(const void* a, const void* a_tail, const void* b, const f
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  PIGAN_TRY(make_tmap_f16_store(&ep.out, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
+  ep.out = OutTile{static_cast<__half*>(out), n, m, n};
   ep.bias = bias;
   ep.scale = nullptr;
   ep.rowstats = rowstats;
@@ -129,6 +129,13 @@ extern "C" int pigan_debug_gemm_tn(const void* a, const void* b, float* c, int32
     case 10: return run_tn<GemmCfg<256, 1, 4, false>, 1>(a, b, c, m, n, k, st);
     case 11: return run_tn<GemmCfg<256, 1, 4, false>, 2>(a, b, c, m, n, k, st);
     case 12: return run_tn<GemmCfg<256, 1, 3, false>, 1>(a, b, c, m, n, k, st);
+    // resident-B probes (K <= 256): no-op epilogue with 3 / 4 / 6 A stages, TMEM loads only with 6
+    case 20: return run_tn<GemmCfg<256, 1, 3, false, 4>, 1>(a, b, c, m, n, k, st);
+    case 21: return run_tn<GemmCfg<256, 1, 4, false, 4>, 1>(a, b, c, m, n, k, st);
+    case 22: return run_tn<GemmCfg<256, 1, 6, false, 4>, 1>(a, b, c, m, n, k, st);
+    case 23: return run_tn<GemmCfg<256, 1, 6, false, 4>, 2>(a, b, c, m, n, k, st);
+    case 24: return run_tn<GemmCfg<256, 1, 2, false>, 1>(a, b, c, m, n, k, st);
+    case 25: return run_tn<GemmCfg<128, 1, 8, false, 4>, 1>(a, b, c, m, n, k, st);
     default: return fail(PIGAN_ERR_INVALID, "unknown gemm variant %d", variant);
   }
 }

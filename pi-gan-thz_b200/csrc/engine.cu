@@ -23,10 +23,10 @@ using CfgS = GemmCfg<256, 1, 4, false>;      // store epilogues, both operands s
 using CfgSR = GemmCfg<256, 1, 4, false, 4>;  // store epilogues, K <= 256: the n-group's weights stay in shared memory
 using CfgP = GemmCfg<256, 1, 4, false>;      // no staging
 using CfgPR = GemmCfg<256, 1, 6, false, 4>;  // no staging, resident weights
-using CfgO = GemmCfg<144, 2, 2, false>;      // forward-model output layer (64 KB target tile in the epilogue)
+using CfgO = GemmCfg<144, 2, 2, false>;      // forward-model output layer, generic epilogue (fp32 dump)
+using CfgO4 = GemmCfg<144, 2, 4, false>;     // forward-model output layer, loss / scoring epilogues
 using CfgW = GemmCfg<256, 1, 4, true>;       // weight gradients
 using CfgL1 = GemmCfg<256, 1, 3, false>;     // Linear+LayerNorm, 256 columns per CTA
-using CfgL1R = GemmCfg<256, 1, 3, false, 4>; // Linear+LayerNorm, K <= 256, resident weights
 using CfgH = GemmCfg<256, 1, 3, false>;      // scoring: generator layer 2 + head + surrogate layer 1 (24 KB epilogue scratch)
 
 // loss_sums indices (fp64)
@@ -99,8 +99,6 @@ struct PiganEngine {
   size_t ws_bytes;
   bool f_loaded = false;
   const float* f_params = nullptr;
-  std::vector<float> f_host;      // host copy of the frozen forward-model parameters (LayerNorm constants travel
-                                  // to the kernels as by-value arguments)
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
   // The frozen surrogate's forward pass of the G-step depends only on the generator output, not on the D-step: it
   // runs on a second, high-priority stream from the moment that output exists (phase 2) and is joined before the
@@ -235,8 +233,14 @@ int run_tn(typename Epi::Params& ep, const __half* a, int64_t m, int k, int lda,
   return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
 }
 
-int out_map(CUtensorMap* m, __half* ptr, int64_t rows, int cols, int ld) {
-  return make_tmap_f16_store(m, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
+int out_map(OutTile* m, __half* ptr, int64_t rows, int cols, int ld) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || ld % 8 != 0 || cols % 8 != 0)
+    return fail(PIGAN_ERR_INVALID, "epilogue output must be 16-byte aligned with columns / pitch multiples of 8");
+  m->ptr = ptr;
+  m->ld = ld;
+  m->rows = (int)rows;
+  m->cols = cols;
+  return PIGAN_OK;
 }
 
 // out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
@@ -269,17 +273,16 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
-// bias / gamma / beta are HOST pointers here: they travel to the kernel by value (constant bank)
+// bias / gamma / beta: device pointers (the layer's fp32 parameters); the epilogue stages its columns in shared memory
 template <int CLUSTER, bool PAIR = false, class Cfg = CfgL1>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
                 const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
   using Epi = EpiLnStore<Cfg, CLUSTER, PAIR>;
-  static thread_local typename Epi::Params ep;   // 12.5 KB: keep it off the stack (per thread: engines may be driven
-                                                 // from several host threads)
+  typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-  memcpy(ep.consts, bias, n * sizeof(float));
-  memcpy(ep.consts + 1024, gamma, n * sizeof(float));
-  memcpy(ep.consts + 2048, beta, n * sizeof(float));
+  ep.bias = bias;
+  ep.gamma = gamma;
+  ep.beta = beta;
   ep.n_total = n;
   ep.trace = g_ln_trace ? g_ln_trace + (n == 1024 ? 1 : n == 256 ? 3 : (k == 256 ? 0 : 2)) * 320 : nullptr;
   return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st);
@@ -289,11 +292,10 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
   CUtensorMap ta, tb;
   PIGAN_TRY(make_tn_maps<CfgL1>(&ta, &tb, a, (int)rows, k, k, w, n, k));
   const GemmShape g = make_shape<CfgL1>((int)rows, n, k);
-  const bool res = k <= CfgL1R::B_RES_KB * kBlockK;   // K <= 256: weights resident in shared memory
-  if (n == 256) return res ? linear_ln_c<1, false, CfgL1R>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st)
-                           : linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
-  if (n == 512) return res ? linear_ln_c<2, false, CfgL1R>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st)
-                           : linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  // (resident weights were measured for the K = 256 layer and make no difference here: 16 epilogue warps need the
+  // shared memory more than the operand ring does)
+  if (n == 256) return linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
+  if (n == 512) return linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
   if (n == 1024) {   // clusters of 2, each CTA walks two n-groups per row tile (clusters of 4 fit only 132 SMs)
     GemmShape gp = g;
     gp.pair_mode = 1;
@@ -518,15 +520,43 @@ int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o,
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
-    const float* hp = e->f_host.data();
-    PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], hp + L.b[i], hp + L.ln_w[i], hp + L.ln_b[i],
+    PIGAN_TRY(linear_ln(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], fp + L.ln_w[i], fp + L.ln_b[i],
                         acts[i], st));
   }
   return f_out_layer(e, e->f_a5, n, o, st);
 }
 // Output layer (forward_model.py:55) with the fused loss / error epilogue; weights from e->f_wh[5], e->f_bias_out
+template <int TMODE, bool TRAIN>
+int f_out_loss(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
+  using Epi = EpiFwdLoss<CfgO4, TMODE, TRAIN>;
+  typename Epi::Params ep;
+  ep.bias = e->f_bias_out;
+  ep.tcen = e->cvec;
+  PIGAN_TRY(make_tmap_f16_2d(&ep.tgt, e->xc, kKp, (uint64_t)n, kKp, 64, kBlockM));
+  ep.S = L.S;
+  ep.Mt = L.Mt;
+  ep.target_metrics = o.target_metrics;
+  ep.p_norm = o.p_norm;
+  ep.sums = o.sums;
+  ep.dp_lc = o.dp_lc;
+  ep.lc_grad_mult = o.lc_grad_mult;
+  ep.row_err = o.row_err;
+  ep.f1_idx = o.f1_idx;
+  ep.f2_idx = o.f2_idx;
+  PM("f_out_gemm");
+  PIGAN_TRY((run_tn<CfgO4, Epi>(ep, a5, n, L.H[4], L.H[4], e->f_wh[5], L.OUT, L.H[4], st)));
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
 int f_out_layer(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st) {
   const FwdLayout& L = e->fl;
+  // the loss / scoring modes have their own lean epilogue; the generic one keeps the fp32 dump of the output
+  if (o.out_full == nullptr && L.S <= 256 && L.OUT <= 288) {
+    if (o.sums != nullptr && o.target_mode == 2 && o.row_err == nullptr) return f_out_loss<2, true>(e, a5, n, o, st);
+    if (o.sums == nullptr && o.row_err != nullptr && o.target_mode == 2) return f_out_loss<2, false>(e, a5, n, o, st);
+    if (o.sums == nullptr && o.row_err != nullptr && o.target_mode == 1) return f_out_loss<1, false>(e, a5, n, o, st);
+  }
   using Epi = EpiFwdOut<CfgO>;
   Epi::Params ep;
   ep.bias = e->f_bias_out;
@@ -845,10 +875,6 @@ extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, 
   }
   launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
   PIGAN_CUDA_OK(cudaGetLastError());
-  // one-time setup: the only synchronising call of the ABI
-  e->f_host.resize((size_t)L.total);
-  PIGAN_CUDA_OK(cudaMemcpyAsync(e->f_host.data(), fp, (size_t)L.total * sizeof(float), cudaMemcpyDeviceToHost, st));
-  PIGAN_CUDA_OK(cudaStreamSynchronize(st));
   e->f_params = fp;
   e->f_loaded = true;
   return PIGAN_OK;

@@ -49,27 +49,44 @@ __device__ __forceinline__ void load_cols32(const float* __restrict__ base, floa
   }
 }
 
-// Per-warp staging of fp16 output blocks for TMA stores.  A warp owns 32 rows of the tile (its TMEM lane quarter);
-// it packs 32 columns of them into a [32 x 32] fp16 block (64-byte rows, 64B-swizzled: conflict-free 16-byte stores
-// with a row per thread) and lane 0 issues the TMA store.  Two blocks per warp alternate, so the store of one block
-// overlaps the arithmetic of the next; nothing is shared between warps - no named barriers on the store path.
-// (Round 1 staged [128 x 64] blocks per epilogue GROUP behind two bar.sync each and waited for the TMA unit to have
-// read a block before its buffer was reused; profiles/r02_ln_trace_before.txt shows 1900 cycles per block of that.)
-// Per group: 4 warps x 2 blocks x 2 KB = 16 KB.
-constexpr int kWarpBlockBytes = 2048;
-constexpr int kEpiStagingBytes = 4 * 2 * kWarpBlockBytes;
+// Output tensor of a store epilogue: row-major fp16 [rows, cols] with row pitch ld (elements; ld % 8 == 0, 16-byte
+// aligned base)
+struct OutTile {
+  __half* ptr;
+  int ld, rows, cols;
+};
 
-struct WarpStager {
+// Per-warp staging of fp16 output blocks.  A warp owns 32 rows of the tile (its TMEM lane quarter); it packs 32
+// columns of them into a [32 x 32] fp16 block in shared memory (64-byte rows, 16-byte chunks XOR-swizzled:
+// conflict-free stores with a row per thread), reads the block back with four lanes per row and writes it with
+// ordinary 16-byte global stores - every store instruction covers 8 rows x 64 contiguous bytes.  Nothing is shared
+// between warps: one __syncwarp per block, no named barriers, no asynchronous proxy.
+//
+// Why not TMA stores (rounds 1 and early 2): the SM's TMA unit serves requests in order, and a store queues behind
+// the operand loads the producer warp keeps in flight.  clock64 traces of the LayerNorm epilogue showed 1900 cycles
+// per [128 x 64] block with group-wide staging (profiles/r02_ln_trace_before.txt) and 3000-8600 cycles per
+// [32 x 32] block when every warp waited for its own previous store (4 epilogue groups, one staging block per warp):
+// the wait for "the TMA unit has read my staging buffer" was the whole of pass 2.  LSU stores do not share that queue.
+constexpr int kWarpBlockBytes = 2048;
+constexpr int kEpiStagingBytes = 4 * 2 * kWarpBlockBytes;   // per group of 4 warps, two blocks per warp
+
+template <int NBUF>
+struct WarpStagerT {
+  static_assert(NBUF == 1 || NBUF == 2, "blocks per warp");
   uint32_t cnt;
-  uint32_t base;   // this warp's two blocks
+  uint32_t base;   // this warp's blocks
   __device__ __forceinline__ void init(const EpiCtx& cx) {
     cnt = 0;
-    base = cx.smem + (uint32_t)(cx.tid >> 5) * (2u * kWarpBlockBytes);
+    base = cx.smem + (uint32_t)(cx.tid >> 5) * (uint32_t)(NBUF * kWarpBlockBytes);
   }
-  __device__ __forceinline__ uint32_t acquire(const EpiCtx& cx) {
-    if (cx.lane == 0) tma_store_wait_read<1>();  // the store that used this block two commits ago has read it
-    __syncwarp();
-    return base + (cnt & 1u) * kWarpBlockBytes;
+  __device__ __forceinline__ void init_at(uint32_t warp_base) {
+    cnt = 0;
+    base = warp_base;
+  }
+  __device__ __forceinline__ uint32_t acquire(const EpiCtx&) {
+    if (NBUF == 1) __syncwarp();   // the read-back of the previous block is done (two blocks: the sync of the block
+                                   // in between already separates them)
+    return base + (NBUF == 2 ? (cnt & 1u) * kWarpBlockBytes : 0u);
   }
   // 32 values of this thread's row (lane = row within the warp's 32 rows)
   __device__ __forceinline__ static void put32(uint32_t buf, int lane, const float* v) {
@@ -93,19 +110,28 @@ struct WarpStager {
     }
   }
   // col0: first of the 32 columns; row0: first row of the 128-row tile
-  __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const CUtensorMap* m, int col0, int row0) {
-    fence_proxy_async_smem();
+  __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const OutTile& o, int col0, int row0) {
     __syncwarp();
-    if (cx.lane == 0) {
-      tma_store_2d(m, buf, col0, row0 + cx.q * 32);
-      tma_store_commit();
+    const int chunk = cx.lane & 3;
+    const int col = col0 + chunk * 8;
+    const int rbase = row0 + cx.q * 32 + (cx.lane >> 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = (cx.lane >> 2) + 8 * i;   // row within the warp's 32
+      uint32_t w0, w1, w2, w3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                   : "r"(buf + (uint32_t)rl * 64u + (uint32_t)((chunk ^ ((rl >> 1) & 3)) << 4))
+                   : "memory");
+      const int row = rbase + 8 * i;
+      if (row < o.rows && col < o.cols)
+        *reinterpret_cast<uint4*>(o.ptr + (size_t)row * o.ld + col) = make_uint4(w0, w1, w2, w3);
     }
     ++cnt;
   }
-  __device__ __forceinline__ static void drain(const EpiCtx& cx) {
-    if (cx.lane == 0) tma_store_wait<0>();
-  }
+  __device__ __forceinline__ static void drain(const EpiCtx&) {}
 };
+using WarpStager = WarpStagerT<2>;
 
 // Walks NCOLS accumulator columns of this thread's row: one tcgen05.ld.x64 (64 columns, 8 KB per warp) at a time,
 // f(c, v) is called for each 32-column block.  Loads of several warps of an SM sub-partition overlap each other and
@@ -153,7 +179,7 @@ template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false,
 struct EpiStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1 && (!MASKOUT || Cfg::BLOCK_N % 128 == 0), "EpiStore tile shape");
   struct Params {
-    CUtensorMap out;
+    OutTile out;
     const float* bias;
     const float* scale;  // AFFINE_RELU: out = relu(scale[c] * acc + bias[c]) — eval-mode BatchNorm + ReLU folded
                          // into the producing layer (generator.py:19-20 with running statistics)
@@ -212,7 +238,7 @@ struct EpiStore {
       }
       const uint32_t buf = st.stg.acquire(cx);
       WarpStager::put32(buf, cx.lane, v);
-      st.stg.commit(cx, buf, &p.out, n0 + c, w.m_tile * kBlockM);
+      st.stg.commit(cx, buf, p.out, n0 + c, w.m_tile * kBlockM);
     });
     if constexpr (ROWSTATS) {
       if (row < g.M)
@@ -225,115 +251,152 @@ struct EpiStore {
 // =====================================================================================================
 // Linear + LayerNorm + LeakyReLU in one epilogue (forward_model.py:35-53): out = fp16(lrelu(LN(acc + bias))).
 // A thread owns one row (its TMEM lane) and walks the tile's 256 accumulator columns twice while they stay in
-// tensor memory — pass 1: sum / sum of squares, pass 2: normalise, activate, store — so the pre-normalisation
-// values never leave the SM.  A row wider than 256 is split over a cluster of N/256 CTAs (2 for 512, 4 for 1024):
-// CTA rank r owns columns [256 r, 256 r + 256) of the same 128 rows, the row partials meet through distributed
-// shared memory and one cluster-scope mbarrier per unit.  With 256 columns per CTA tensor memory holds two
-// accumulator buffers, so the MMAs of the next row tile overlap both passes — which matters because draining
-// TMEM is slow: measured 64 B/clk per SM (tools/micro/ldtm_bench.cu), i.e. 2048 cycles per pass over a 128 x 256
-// fp32 tile against 4096 MMA cycles at K = 512.
+// tensor memory - pass 1: sum / sum of squares, pass 2: normalise, activate, store - so the pre-normalisation
+// values never leave the SM and the normalisation works on the fp32 accumulator itself.  A row wider than 256 is
+// split over a cluster of CTAs: CTA rank r owns columns [256 r, 256 r + 256) of the same 128 rows; the row partials
+// travel through distributed shared memory as st.async stores that complete a transaction count on the receiving
+// CTA's mbarrier (no fences, no arrive instructions).  Tensor memory holds two accumulator buffers, so the MMAs of
+// the next row tile overlap both passes.
+//
+// Round 1 kept the row as packed fp16 in 128 registers between the passes ("stash") to release the accumulator early,
+// which forces both passes to be fully unrolled: 45 KB of code per kernel, and the ncu source view showed the
+// epilogue warps issuing one instruction every ~4 cycles (18 % of their stall samples "no instruction", 14 % the
+// membar of the release-arrive on the peer's barrier).  tcgen05.ld delivers ~460 B/clk per SM (profiles/
+// r02_ldtm_bench2.txt), so re-reading the accumulator is cheap; both passes are now rolled loops over 64-column
+// chunks (4 KB of code).
 // =====================================================================================================
 //   PAIR = false: CTA rank r owns n-group r (N = 256 * CLUSTER); its two epilogue groups alternate row tiles.
 //   PAIR = true : a CTA walks both n-groups 2r, 2r+1 of a row tile back to back (GemmShape::pair_mode, N = 512 *
 //                 CLUSTER): group e owns n-group 2r+e / accumulator buffer e, all 2 * CLUSTER groups exchange their
 //                 partials every row tile.  Used for N = 1024, where clusters of 4 would only cover 132 of 148 SMs.
-template <class Cfg, int CLUSTER_, bool PAIR = false>
+//   GROUPS = 4  : four epilogue groups (16 warps, four per SM sub-partition): groups g and g + 2 share the units of
+//                 accumulator buffer g & 1 and take 128 columns each.  The ncu source view of the two-group version
+//                 showed the epilogue warps stalled 77 % of the time on fixed-latency dependencies and constant
+//                 loads with only two warps per scheduler to hide them.
+template <class Cfg, int CLUSTER_, bool PAIR = false, int GROUPS_ = 4>
 struct EpiLnStore {
   static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiLnStore tile shape");
+  static_assert(GROUPS_ == 2 || GROUPS_ == 4, "epilogue groups");
   static constexpr bool SPLIT = false;
-  static constexpr int XBAR_COUNT = (PAIR ? 256 : 128) * CLUSTER_;
-  static constexpr int PARTS = (PAIR ? 2 : 1) * CLUSTER_;   // row partials per row
-  static constexpr bool EARLY_RELEASE = true;  // unit() arrives on cx.tempty itself, right after its only TMEM pass
+  static constexpr int GROUPS = GROUPS_;
+  static constexpr int HALVES = GROUPS_ / 2;                 // column slices of a unit (one per group that shares it)
+  static constexpr int PARTS = (PAIR ? 2 : 1) * CLUSTER_ * HALVES;   // row partials per row
+  // cluster: one arrive.expect_tx per phase, the partials arrive as transaction bytes; single CTA: plain arrivals of
+  // the threads that share the row
+  static constexpr int XBAR_COUNT = CLUSTER_ > 1 ? 1 : 128 * PARTS;
   static constexpr int CLUSTER = CLUSTER_;
-  static constexpr int NG = 256;  // columns of the row this CTA (and the group that owns the unit) handles
+  static constexpr int NG = 256;           // columns of the row this CTA handles per unit
+  static constexpr int NT = NG / HALVES;   // columns per thread
   struct Params {
-    CUtensorMap out;
+    OutTile out;
     int n_total;         // LayerNorm width N = 256 * CLUSTER
     long long* trace;    // optional [units][5] clock64 stamps of CTA 0 / thread 0 of a group (tools/ln_trace.py)
-    // bias | gamma | beta of the layer, 1024 entries each, passed BY VALUE: kernel parameters live in the constant
-    // bank, whose broadcast reads do not touch shared memory — the operand ring (TMA writes + UMMA reads, ~190 B/clk
-    // at full MMA rate against 128 B/clk of shared-memory bandwidth) leaves no room for per-column constant loads;
-    // with them in shared memory pass 2 took 6-7k cycles per tile even when it read no tensor memory at all.
-    float consts[3 * 1024];
+    const float* bias;   // [N] device pointers into the layer's fp32 parameters (Linear bias, LayerNorm weight / bias)
+    const float* gamma;
+    const float* beta;
   };
-  // per group: [0,16K) per-warp store staging | [16K,+8K) row-partial slots written by the groups / CTAs that share the row
-  static constexpr int kSlotOff = kEpiStagingBytes;   // two buffers of [PARTS][128] float2, alternating per unit
-  static constexpr int kSlotBytes = 4096;
+  // shared memory of all groups together: per-warp store staging (two blocks per warp with 2 groups, one with 4) |
+  // row-partial slots: [owner group 0/1][unit parity] buffers of [PARTS][128] float2
+  static constexpr int NBUF = GROUPS_ == 2 ? 2 : 1;
+  static constexpr int kStagingTotal = GROUPS_ * 4 * NBUF * kWarpBlockBytes;   // 32 KB either way
+  static constexpr int kSlotBytes = PARTS * 128 * 8 > 4096 ? 8192 : 4096;
   static_assert(PARTS * 128 * 8 <= kSlotBytes, "slot buffer");
-  static constexpr int SMEM_BYTES = kEpiStagingBytes + 2 * kSlotBytes;
+  // | bias, gamma, beta of the CTA's columns (W floats each).  Rounds 1 / early 2 read them from the kernel-parameter
+  // constant bank: three streams 4 KB apart thrash the small constant cache - pass 2 (three constants per column)
+  // took 9-32k cycles per unit against 1.7k for pass 1 (one constant per column), profiles/r02_ln_trace_*.txt.
+  static constexpr int W = PAIR ? 512 : 256;
+  static constexpr int kConstOff = kStagingTotal + 4 * kSlotBytes;
+  static constexpr int SMEM_TOTAL = kConstOff + 8192;
+  static_assert(3 * W * 4 <= 8192, "constant block");
+  static constexpr int SMEM_BYTES = SMEM_TOTAL / GROUPS_;
+  static_assert(SMEM_TOTAL % (1024 * GROUPS_) == 0, "alignment of the barrier block behind the epilogue scratch");
   struct State {
-    WarpStager stg;
-    uint32_t xphase;
+    WarpStagerT<NBUF> stg;
     uint32_t it;
     uint32_t rank;
   };
   __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
-    st.stg.init(cx);
-    st.xphase = 0;
+    st.stg.init_at(cx.smem0 + (uint32_t)((cx.group * 4 + (cx.tid >> 5)) * NBUF * kWarpBlockBytes));
     st.it = 0;
     st.rank = CLUSTER > 1 ? cluster_ctarank() : 0u;
-    epi_bar_sync(cx, 0);
+    // this CTA's columns [rank * W, rank * W + W) of the three constant rows -> shared memory
+    const int first = (int)st.rank * W;
+    for (int i = cx.group * 128 + cx.tid; i < 3 * W; i += 128 * GROUPS_) {
+      const int a = i / W, c = i - a * W;
+      const float* src = a == 0 ? p.bias : a == 1 ? p.gamma : p.beta;
+      sts_f32(cx.smem0 + kConstOff + 4u * (uint32_t)i, __ldg(src + first + c));
+    }
+    asm volatile("bar.sync 9, %0;" ::"n"(128 * GROUPS_) : "memory");   // all epilogue groups
   }
-  // 16 consecutive per-column constants from the kernel-parameter (constant) bank
-  __device__ static void ldc16(const float* src, float* out) {
+  // 16 consecutive per-column constants from shared memory (warp-uniform address: one broadcast per 16 bytes)
+  __device__ static void ldc16(uint32_t addr, float* out) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 t = *reinterpret_cast<const float4*>(src + 4 * k);
+      float4 t;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr + 16u * k));
       out[4 * k + 0] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
     }
   }
   __device__ static void unit(const Params& p, State& st, const GemmShape&, const UnitInfo& w, uint32_t tacc,
                               const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const uint32_t part = PAIR ? st.rank * 2u + (uint32_t)cx.group : st.rank;   // which n-group of the row
-    const float* cbias = p.consts + part * NG;
-    const float* cgamma = p.consts + 1024 + part * NG;
-    const float* cbeta = p.consts + 2048 + part * NG;
-    const bool tr = p.trace != nullptr && blockIdx.x == 0 && cx.tid == 0 && st.it < 32;
+    const int buf = cx.group & 1;            // accumulator buffer / (PAIR) n-group parity of this unit
+    const int half = cx.group >> 1;          // column slice within the unit
+    const uint32_t ngrp = PAIR ? st.rank * 2u + (uint32_t)buf : st.rank;   // which n-group of the row
+    const uint32_t part = ngrp * HALVES + (uint32_t)half;                  // which partial of the row
+    const int cofs = (int)ngrp * NG + half * NT;                           // first column of this thread
+    const uint32_t cbias = cx.smem0 + kConstOff + 4u * (uint32_t)((PAIR ? buf * NG : 0) + half * NT);
+    const uint32_t cgamma = cbias + 4u * W, cbeta = cbias + 8u * W;
+    const uint32_t tcol = tacc + (uint32_t)(half * NT);
+    const bool tr = p.trace != nullptr && blockIdx.x == 0 && cx.tid == 0 && cx.group < 2 && st.it < 32;
     long long* trow = tr ? p.trace + (st.it * 2 + cx.group) * 5 : nullptr;
     if (tr) trow[0] = clock64();
-    // ---- pass 1 (the only read of tensor memory): bias, row partials, and the row itself packed to fp16 in
-    // registers.  Everything is unrolled so the stash is addressed statically.
-    uint32_t stash[NG / 2];
+    // ---- pass 1: row sum and sum of squares of acc + bias
     float s1, s2;
     {
       float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-      drain_blocks32_unrolled<NG>(tacc, [&](int c, float* v) {
+#pragma unroll 1
+      for (int c = 0; c < NT; c += 32) {
+        float v[32];
+        tmem_ld32(tcol + c, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 32; h += 16) {
           float b[16];
-          ldc16(cbias + c + h, b);
+          ldc16(cbias + 4u * (uint32_t)(c + h), b);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float x = v[h + i] + b[i];
-            v[h + i] = x;
             a1[i & 3] += x;
             a2[i & 3] = fmaf(x, x, a2[i & 3]);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) stash[(c + h) / 2 + i] = pack_half2(v[h + 2 * i], v[h + 2 * i + 1]);
         }
-      });
+      }
       s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
     }
-    // the accumulator is free: the MMAs of the unit after next may start
-    tc_fence_before();
-    mbar_arrive(cx.tempty);
     if (tr) trow[1] = clock64();
-    // ---- exchange the row partials inside the cluster
+    // ---- exchange the row partials (between the groups that share the unit and inside the cluster)
     if constexpr (PARTS > 1) {
-      // PAIR: both groups meet on group 0's barrier and slots; otherwise every group has its own
-      const uint32_t slots = (PAIR ? cx.smem0 : cx.smem) + kSlotOff + (st.it & 1u) * kSlotBytes;
-      const uint32_t xb = PAIR ? cx.xbar - 8u * (uint32_t)cx.group : cx.xbar;
+      // The exchange of a unit lives in the region of ONE group: group 0 (PAIR: all groups of the CTA pair up on the
+      // row) or the group that owns the accumulator buffer.  Barriers and slots alternate between units, so a peer
+      // that is one unit ahead never touches the phase being waited for.
+      const int owner = PAIR ? 0 : buf;
+      const uint32_t par = st.it & 1u;
+      const uint32_t slots = cx.smem0 + kStagingTotal + (uint32_t)(owner * 2 + (int)par) * kSlotBytes;
+      const uint32_t xb = (PAIR ? cx.xbar - 16u * (uint32_t)buf : cx.xbar) + 8u * par;
       const uint32_t mine = slots + (part * 128u + (uint32_t)r) * 8u;
+      if constexpr (CLUSTER > 1) {
+        if (cx.tid == 0 && cx.group == owner) mbar_arrive_expect_tx(xb, PARTS * 128 * 8);
 #pragma unroll
-      for (uint32_t c = 0; c < (uint32_t)CLUSTER; ++c) {
-        st_cluster_f32x2(mapa_shared(mine, c), s1, s2);
-        mbar_arrive_cluster(mapa_shared(xb, c));
+        for (uint32_t c = 0; c < (uint32_t)CLUSTER; ++c)
+          st_async_f32x2(mapa_shared(mine, c), s1, s2, mapa_shared(xb, c));
+      } else {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(mine), "f"(s1), "f"(s2) : "memory");
+        mbar_arrive(xb);   // release (CTA scope) of the store above
       }
-      mbar_wait_cluster(xb, st.xphase);
-      st.xphase ^= 1u;
+      mbar_wait(xb, (st.it >> 1) & 1u);
       s1 = 0.f;
       s2 = 0.f;
 #pragma unroll
@@ -351,30 +414,37 @@ struct EpiLnStore {
     const float mean = s1 * inv_n;
     const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    // ---- pass 2, from the register stash: normalise, LeakyReLU, fp16, TMA store
-    const int col0 = (int)part * NG;
-#pragma unroll
-    for (int c = 0; c < NG; c += 32) {
+    const float nmr = -mean * rstd;
+    // ---- pass 2: normalise the fp32 accumulator, LeakyReLU, fp16, TMA store
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 32) {
+      float v[32];
+      tmem_ld32(tcol + c, v);
+      tmem_ld_wait();
       uint32_t hw[16];
 #pragma unroll
       for (int h = 0; h < 32; h += 16) {
-        float gm[16], bt[16];
-        ldc16(cgamma + c + h, gm);
-        ldc16(cbeta + c + h, bt);
+        float bs[16], gm[16], bt[16];
+        ldc16(cbias + 4u * (uint32_t)(c + h), bs);
+        ldc16(cgamma + 4u * (uint32_t)(c + h), gm);
+        ldc16(cbeta + 4u * (uint32_t)(c + h), bt);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&stash[(c + h) / 2 + i]));
-          hw[h / 2 + i] = pack_half2(lrelu(fmaf((f.x - mean) * rstd, gm[2 * i], bt[2 * i])),
-                                     lrelu(fmaf((f.y - mean) * rstd, gm[2 * i + 1], bt[2 * i + 1])));
+        for (int i = 0; i < 16; i += 2) {
+          // ((acc + b) - mean) * rstd = fma(acc, rstd, fma(b, rstd, -mean * rstd)); then the affine
+          const float y0 = fmaf(fmaf(v[h + i], rstd, fmaf(bs[i], rstd, nmr)), gm[i], bt[i]);
+          const float y1 = fmaf(fmaf(v[h + i + 1], rstd, fmaf(bs[i + 1], rstd, nmr)), gm[i + 1], bt[i + 1]);
+          hw[(h + i) / 2] = pack_half2(lrelu(y0), lrelu(y1));
         }
       }
-      const uint32_t buf = st.stg.acquire(cx);
-      WarpStager::put32_packed(buf, cx.lane, hw);
-      st.stg.commit(cx, buf, &p.out, col0 + c, w.m_tile * kBlockM);
+      const uint32_t sbuf = st.stg.acquire(cx);
+      WarpStagerT<NBUF>::put32_packed(sbuf, cx.lane, hw);
+      st.stg.commit(cx, sbuf, p.out, cofs + c, w.m_tile * kBlockM);
     }
     if (tr) trow[3] = clock64();
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) {
+    WarpStagerT<NBUF>::drain(cx);
+  }
 };
 
 // =====================================================================================================
@@ -388,7 +458,7 @@ template <class Cfg>
 struct EpiDiscL2 {
   static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1, "EpiDiscL2 needs the whole row in one tile");
   struct Params {
-    CUtensorMap z2;       // [rows, 256] fp16 out (may be unused: store_z2 = 0)
+    OutTile z2;           // [rows, 256] fp16 out (may be unused: store_z2 = 0)
     const float* b2;      // [256]
     const float* w3;      // [256]
     const float* b3;      // [1]
@@ -431,7 +501,7 @@ struct EpiDiscL2 {
       if (p.store_z2) {
         const uint32_t buf = st.stg.acquire(cx);
         WarpStager::put32(buf, cx.lane, v);
-        st.stg.commit(cx, buf, &p.z2, c, w.m_tile * kBlockM);
+        st.stg.commit(cx, buf, p.z2, c, w.m_tile * kBlockM);
       }
     });
     float logit = (lg[0] + lg[1]) + (lg[2] + lg[3]);
@@ -465,7 +535,7 @@ template <class Cfg>
 struct EpiLeakyMaskStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1, "tile shape");
   struct Params {
-    CUtensorMap out;
+    OutTile out;
     const uint32_t* mask;  // [M][mask_words] sign bits of the saved activations (EpiStore MASKOUT)
     int mask_words;
   };
@@ -493,7 +563,7 @@ struct EpiLeakyMaskStore {
       for (int i = 0; i < 32; ++i) v[i] *= ((bits >> i) & 1u) ? 1.f : kLeaky;
       const uint32_t buf = st.stg.acquire(cx);
       WarpStager::put32(buf, cx.lane, v);
-      st.stg.commit(cx, buf, &p.out, n0 + c, w.m_tile * kBlockM);
+      st.stg.commit(cx, buf, p.out, n0 + c, w.m_tile * kBlockM);
     });
   }
   __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
@@ -576,7 +646,7 @@ struct EpiHeadF1 {
   static constexpr int CLUSTER = 1;
   static constexpr bool EARLY_RELEASE = true;
   struct Params {
-    CUtensorMap out;    // surrogate layer-1 activations [M,256] fp16
+    OutTile out;        // surrogate layer-1 activations [M,256] fp16
     float* p_out;       // [M,4] predicted parameters (tanh output)
     const float* img;   // kHeadImgFloats constants, layout above
   };
@@ -663,7 +733,7 @@ struct EpiHeadF1 {
       }
       const uint32_t buf = st.stg.acquire(cx);
       WarpStager::put32(buf, cx.lane, v);
-      st.stg.commit(cx, buf, &p.out, blk * 32, w.m_tile * kBlockM);
+      st.stg.commit(cx, buf, p.out, blk * 32, w.m_tile * kBlockM);
     }
   }
   __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
@@ -899,6 +969,222 @@ struct EpiFwdOut {
     for (int k = 0; k < 5; ++k) {
       const float t = warp_sum(s[k]);
       if (cx.lane == 0 && t != 0.f && p.sums) atomicAdd(p.sums + k, (double)t);
+    }
+  }
+};
+
+// =====================================================================================================
+// The loss / scoring variants of the forward-model output layer (same tile shape and column split as EpiFwdOut, which
+// keeps the generic path with the fp32 dump).  Round 1 ran every mode through one epilogue with run-time switches:
+// 34 instructions per accumulator element, 7.7 % tensor-pipe activity (profiles/r02_fwd_gemms_ncu_before.csv).  Here
+// the mode is a template parameter, the per-column constants (bias, bias - target centre) are staged once per CTA in
+// shared memory, a trip handles 48 columns branch-free (one .x32 + one .x16 tensor-memory load in flight), and the
+// second differences of the maxwell term come from the neighbouring registers instead of a serial chain.
+//   TMODE 1: one target row for all rows (candidate search; tcen = the target)         d = acc + (bias - target)
+//   TMODE 2: per-row targets as the centred fp16 operand copy (TMA-staged) + centre     d = acc + (bias - centre) - x16
+//   TRAIN  : also metric MSE, LC terms and d(LC)/dp, sums for the loss scalars (train_pigan.py:159-170); else the
+//            per-row reconstruction error (unified_evaluator.py:387)
+// =====================================================================================================
+template <class Cfg, int TMODE, bool TRAIN>
+struct EpiFwdLoss {
+  static_assert(Cfg::BLOCK_N == 144 && Cfg::ACC_TILES == 2 && Cfg::ACC_BUFS == 1, "EpiFwdLoss tile shape");
+  static_assert(TMODE == 1 || TMODE == 2, "target mode");
+  static constexpr bool SPLIT = true;   // group g handles output columns [144 g, 144 g + 144)
+  static constexpr int CLUSTER = 1;
+  struct Params {
+    const float* bias;            // [288] zero-padded
+    const float* tcen;            // [256] zero-padded: the target row (TMODE 1) or the operand's centring row (TMODE 2)
+    CUtensorMap tgt;              // TMODE 2: centred fp16 operand copy [M,256], 128 x 64 boxes
+    int S, Mt;
+    const float* target_metrics;  // TRAIN: [M,Mt]
+    const float* p_norm;          // TRAIN: [M,4] generator output (LC loss)
+    double* sums;                 // TRAIN: [0]=sum (recon-x)^2 [1]=sum (pm-m)^2 [2]=sum d2^2 [3]=sum lc1 [4]=sum lc2
+    float* dp_lc;                 // TRAIN: [M,4] d(lambda_lc * LC)/dp * GS  or null
+    float lc_grad_mult;           // lambda_lc * GS / global batch
+    float* row_err;               // !TRAIN: [M] mean_j (x - recon)^2
+    int f1_idx, f2_idx;
+  };
+  // group 0's region: [0, 64 KB) target tile, 4 swizzled [128 x 64] fp16 boxes (TMA); [64 KB, +8) its mbarrier;
+  // [+1 KB, +2 KB) group 1's per-row partial errors (two buffers); [+2 KB, +4.25 KB) bias[288] | bias - tcen [288]
+  static constexpr int kTileBytes = 4 * kStageBytes;
+  static constexpr int kPartOff = kTileBytes + 1024;
+  static constexpr int kConstOff = kTileBytes + 2048;
+  static constexpr int SMEM_BYTES = kTileBytes + 5120;
+  static constexpr int SMEM_TOTAL = SMEM_BYTES;   // everything lives in group 0's region: the operand ring gets the rest
+  struct State {
+    float s_rec, s_met, s_mx, s_lc1, s_lc2;
+    uint32_t tphase, it;
+  };
+  __device__ static void issue_target(const Params& p, const EpiCtx& cx, int m_tile) {
+    const uint32_t bar = cx.smem0 + kTileBytes;
+    mbar_arrive_expect_tx(bar, kTileBytes);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) tma_load_2d(cx.smem0 + b * kStageBytes, &p.tgt, bar, b * 64, m_tile * kBlockM);
+  }
+  __device__ static void sync_groups() { asm volatile("bar.sync 5, 256;" ::: "memory"); }
+  __device__ static float4 lds4(uint32_t addr) {
+    float4 t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr));
+    return t;
+  }
+  __device__ static void init(const Params& p, State& st, const GemmShape& g, const EpiCtx& cx) {
+    st.s_rec = st.s_met = st.s_mx = st.s_lc1 = st.s_lc2 = 0.f;
+    st.tphase = 0;
+    st.it = 0;
+    if (TMODE == 2 && cx.group == 0 && cx.tid == 0) {
+      mbar_init(cx.smem0 + kTileBytes, 1);
+      fence_barrier_init();
+      if ((int)blockIdx.x < g.num_m_tiles) issue_target(p, cx, blockIdx.x);
+    }
+    // per-column constants: bias | bias - tcen (columns >= S carry no target)
+    for (int j = cx.tid + 128 * cx.group; j < 288; j += 256) {
+      const float b = __ldg(p.bias + j);
+      const float t = j < p.S ? __ldg(p.tcen + j) : 0.f;
+      sts_f32(cx.smem0 + kConstOff + 4u * j, b);
+      sts_f32(cx.smem0 + kConstOff + 4u * (288 + j), b - t);
+    }
+    sync_groups();
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int rt = cx.q * 32 + cx.lane;               // row within the tile
+    const int row = w.m_tile * kBlockM + rt;
+    const bool valid = row < g.M;
+    const int OUT = p.S + p.Mt;
+    const int jbase = cx.group * 144;
+    const uint32_t cb = cx.smem0 + kConstOff;
+    float rec4[4] = {0.f, 0.f, 0.f, 0.f}, mx4[4] = {0.f, 0.f, 0.f, 0.f};
+    float met = 0.f, f1 = 0.f, f2 = 0.f;
+    float p1 = 0.f, q = 0.f;   // o[j-1] and o[j-1] - o[j-2] entering the current trip
+    if (cx.group == 1) {
+      // the second differences at columns 144 and 145 reach back into group 0's last two columns
+      float v[16];
+      tmem_ld16(tacc + 128, v);
+      const float4 b = lds4(cb + 4u * 140);
+      tmem_ld_wait();
+      const float o142 = v[14] + b.z, o143 = v[15] + b.w;
+      p1 = o143;
+      q = o143 - o142;
+    }
+    if constexpr (TMODE == 2) {
+      mbar_wait(cx.smem0 + kTileBytes, st.tphase);
+      st.tphase ^= 1u;
+    }
+#pragma unroll 1
+    for (int trip = 0; trip < 3; ++trip) {
+      const int j0 = jbase + 48 * trip;
+      float v[48];
+      tmem_ld32(tacc + j0, v);   // the two 144-column accumulators are adjacent in tensor memory
+      tmem_ld16(tacc + j0 + 32, v + 32);
+      // target values of these 48 columns (TMODE 2): six 16-byte chunks of this row in the swizzled boxes
+      uint32_t xh[24];
+      if constexpr (TMODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int j = j0 + 8 * k < 256 ? j0 + 8 * k : 248;   // the tile has 256 columns; columns >= S are never used
+          const uint32_t addr = cx.smem0 + (uint32_t)(j >> 6) * kStageBytes + (uint32_t)rt * 128u +
+                                (uint32_t)(((((j & 63) >> 3)) ^ (rt & 7)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(xh[4 * k]), "=r"(xh[4 * k + 1]), "=r"(xh[4 * k + 2]), "=r"(xh[4 * k + 3]) : "r"(addr) : "memory");
+        }
+      }
+      tmem_ld_wait();
+      if (j0 + 48 <= p.S) {
+        // ---- all 48 columns are spectrum samples: branch-free
+#pragma unroll
+        for (int i4 = 0; i4 < 48; i4 += 4) {
+          const float4 b4 = lds4(cb + 4u * (j0 + i4)), c4 = lds4(cb + 4u * (288 + j0 + i4));
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i4 + u;
+            const float o = v[i] + bb[u];
+            float d = v[i] + cc[u];
+            if constexpr (TMODE == 2) {
+              const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&xh[i >> 1]));
+              d -= (i & 1) ? xf.y : xf.x;
+            }
+            rec4[u] = fmaf(d, d, rec4[u]);
+            const float t1 = o - p1;           // loss.py:51-53 difference of differences
+            float d2 = t1 - q;
+            if (i < 2) d2 = (j0 + i >= 2) ? d2 : 0.f;   // the first two columns of the row have no second difference
+            mx4[u] = fmaf(d2, d2, mx4[u]);
+            q = t1;
+            p1 = o;
+          }
+        }
+      } else {
+        // ---- the trip that holds the end of the spectrum, the metric columns and the padding
+        const float* ms = (TRAIN && p.target_metrics) ? p.target_metrics + (size_t)(valid ? row : 0) * p.Mt : nullptr;
+#pragma unroll
+        for (int i = 0; i < 48; ++i) {
+          const int j = j0 + i;
+          const float o = v[i] + lds_f32(cb + 4u * j);
+          if (j < p.S) {
+            float d = v[i] + lds_f32(cb + 4u * (288 + j));
+            if constexpr (TMODE == 2) {
+              const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&xh[i >> 1]));
+              d -= (i & 1) ? xf.y : xf.x;
+            }
+            rec4[i & 3] = fmaf(d, d, rec4[i & 3]);
+            const float t1 = o - p1;
+            const float d2 = t1 - q;
+            if (j >= 2) mx4[i & 3] = fmaf(d2, d2, mx4[i & 3]);
+            q = t1;
+            p1 = o;
+          } else if (TRAIN && j < OUT) {
+            const int k = j - p.S;
+            if (ms) {
+              const float d = o - __ldg(ms + k);
+              met = fmaf(d, d, met);
+            }
+            if (k == p.f1_idx) f1 = o;
+            if (k == p.f2_idx) f2 = o;
+          }
+        }
+      }
+    }
+    const float rec = (rec4[0] + rec4[1]) + (rec4[2] + rec4[3]);
+    const float mx = (mx4[0] + mx4[1]) + (mx4[2] + mx4[3]);
+    // group 1 hands its part of the row's squared error to group 0 (two buffers alternate between units)
+    const uint32_t part = cx.smem0 + kPartOff + (st.it & 1u) * 512u + (uint32_t)rt * 4u;
+    ++st.it;
+    if (!TRAIN && cx.group == 1) sts_f32(part, rec);
+    sync_groups();  // also: everyone is done with the target tile
+    if (TMODE == 2 && cx.group == 0 && cx.tid == 0) {
+      const int next = w.m_tile + (int)gridDim.x;   // fetched while the MMAs of the next unit run
+      if (next < g.num_m_tiles) issue_target(p, cx, next);
+    }
+    if (!valid) return;
+    if constexpr (!TRAIN) {
+      if (cx.group == 0) p.row_err[row] = (rec + lds_f32(part)) / (float)p.S;
+    } else {
+      st.s_rec += rec;
+      st.s_met += met;
+      st.s_mx += mx;
+      if (cx.group == 1 && p.p_norm) {
+        const float4 pn = __ldg(reinterpret_cast<const float4*>(p.p_norm) + row);
+        const float e1 = f1 - (0.4f * pn.x + 0.6f * pn.z);
+        const float e2 = f2 - (0.3f * pn.y + 0.7f * pn.w);
+        st.s_lc1 = fmaf(e1, e1, st.s_lc1);
+        st.s_lc2 = fmaf(e2, e2, st.s_lc2);
+        if (p.dp_lc) {
+          // d/dp of (f - th)^2 with f constant (no grad through F, train_pigan.py:156-157): -2 e dth/dp
+          const float m = -2.f * p.lc_grad_mult;
+          *reinterpret_cast<float4*>(p.dp_lc + (size_t)row * 4) =
+              make_float4(m * e1 * 0.4f, m * e2 * 0.3f, m * e1 * 0.6f, m * e2 * 0.7f);
+        }
+      }
+    }
+  }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    if constexpr (TRAIN) {
+      float s[5] = {st.s_rec, st.s_met, st.s_mx, st.s_lc1, st.s_lc2};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float t = warp_sum(s[k]);
+        if (cx.lane == 0 && t != 0.f && p.sums) atomicAdd(p.sums + k, (double)t);
+      }
     }
   }
 };

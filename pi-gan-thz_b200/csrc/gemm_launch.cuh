@@ -16,7 +16,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   static bool attr_done = false;
   if (!attr_done) {
     PIGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES));
+                                       Cfg::SMEM_BYTES + epi_smem_total<Epi>::value));
     attr_done = true;
   }
   // CTAs that can have work: one per unit, or one per (m-tile, cluster rank) in pair mode
@@ -36,8 +36,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES;
+  cfg.blockDim = dim3(gemm_threads<Epi>());
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES + epi_smem_total<Epi>::value;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -76,6 +76,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   note_launch();
   PIGAN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tx ? *tx : tb, g, ep));
   PIGAN_CUDA_OK(cudaGetLastError());
+  if (debug_sync_enabled()) {   // PIGAN_DEBUG_SYNC=1: name the kernel that faults (development aid; serialises everything)
+    const cudaError_t err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess)
+      return fail(PIGAN_ERR_CUDA, "%s while running %s (grid %d)", cudaGetErrorString(err), __PRETTY_FUNCTION__, grid);
+  }
   return PIGAN_OK;
 }
 

@@ -25,7 +25,7 @@ namespace pigan {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;   // 64 halves = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;
+constexpr int kGemmThreads = 320;   // 2 epilogue groups (the default); see gemm_threads<Epi>()
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 
 struct GemmShape {
@@ -106,7 +106,7 @@ struct GemmCfg {
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(!MN_MAJOR || BLOCK_N % 64 == 0, "NT mode loads B in 64-wide boxes");
   static_assert(!B_RESIDENT || (!MN_MAJOR && ACC_TILES == 1), "resident B: TN mode, one accumulator tile per unit");
-  static_assert(2 * STAGES + 8 <= 32, "barrier block");
+  static_assert(2 * STAGES + 10 <= 32, "barrier block");
 };
 
 // What an epilogue thread knows about itself.
@@ -115,10 +115,10 @@ struct EpiCtx {
   int tid;        // 0..127 within the epilogue group
   int q;          // TMEM lane quarter of this warp (row in tile = q*32 + lane)
   int lane;
-  int group;      // epilogue group 0/1
+  int group;      // epilogue group 0/1 (0..3 with Epi::GROUPS = 4: accumulator buffer = group & 1, column half = group >> 1)
   uint32_t smem0; // scratch region of group 0 (data shared by both groups of a SPLIT epilogue lives there)
   uint32_t tempty; // "accumulator drained" mbarrier of the unit being processed (EARLY_RELEASE epilogues arrive on it)
-  uint32_t xbar;  // this group's cluster-exchange mbarrier: 128 * CLUSTER arrivals per phase
+  uint32_t xbar;  // this group's two cluster-exchange mbarriers (alternating between units)
 };
 // Epilogues that define `static constexpr bool EARLY_RELEASE = true` release the accumulator buffer themselves.
 template <class E, class = void>
@@ -130,6 +130,20 @@ template <class E, class = void>
 struct epi_xbar_count { static constexpr int value = 128 * E::CLUSTER; };
 template <class E>
 struct epi_xbar_count<E, decltype((void)E::XBAR_COUNT)> { static constexpr int value = E::XBAR_COUNT; };
+// Epilogue groups of 4 warps: 2 by default (group e owns accumulator buffer e), Epi::GROUPS = 4 puts four warps on
+// every SM sub-partition - groups g and g + 2 then share the units of buffer g & 1 and split their columns
+// (EpiCtx::group >> 1 = column half).  Epilogues that are bound by instruction latency, not by issue slots, need that.
+template <class E, class = void>
+struct epi_groups { static constexpr int value = 2; };
+template <class E>
+struct epi_groups<E, decltype((void)E::GROUPS)> { static constexpr int value = E::GROUPS; };
+// shared memory of all epilogue groups together: GROUPS * Epi::SMEM_BYTES unless the epilogue names a total
+template <class E, class = void>
+struct epi_smem_total { static constexpr int value = epi_groups<E>::value * E::SMEM_BYTES; };
+template <class E>
+struct epi_smem_total<E, decltype((void)E::SMEM_TOTAL)> { static constexpr int value = E::SMEM_TOTAL; };
+template <class E>
+constexpr int gemm_threads() { return 64 + 128 * epi_groups<E>::value; }
 __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // named barrier over one group
   asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * cx.group + which) : "memory");
 }
@@ -149,24 +163,26 @@ __device__ __forceinline__ void epi_bar_sync(const EpiCtx& cx, int which) {  // 
 //                                  // CTAs that work on the same m-tile with n_group = cluster rank and may
 //                                  // exchange per-row partials through distributed shared memory
 template <class Cfg, class Epi, int AB_FMT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<Epi>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_x, const GemmShape g,
                const __grid_constant__ typename Epi::Params ep) {
-  static_assert(Cfg::SMEM_BYTES + 2 * Epi::SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(Cfg::SMEM_BYTES + epi_smem_total<Epi>::value <= 232448, "shared memory budget");
+  static_assert(epi_groups<Epi>::value == 2 || (epi_groups<Epi>::value == 4 && !Epi::SPLIT && Cfg::ACC_BUFS == 2),
+                "4 epilogue groups: two per accumulator buffer");
   static_assert(Epi::SMEM_BYTES % 1024 == 0, "epilogue scratch must keep 1024-B alignment");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t res_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // resident B k-blocks (B_RESIDENT), else empty
   const uint32_t smem_base = res_base + Cfg::RES_BYTES;                 // operand ring
   const uint32_t epi_smem = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
-  const uint32_t bar_base = epi_smem + 2 * Epi::SMEM_BYTES;
+  const uint32_t bar_base = epi_smem + epi_smem_total<Epi>::value;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  const uint32_t xbar = bar_base + 8u * (2 * Cfg::STAGES + 5);  // SPLIT epilogues: per-unit row-partial exchange
-  const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::STAGES + 7);  // resident B has landed
+  const uint32_t bres_bar = bar_base + 8u * (2 * Cfg::STAGES + 5);  // resident B has landed
+  const uint32_t xbar = bar_base + 8u * (2 * Cfg::STAGES + 6);  // cluster exchange of row partials: [group][unit parity]
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -182,10 +198,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 128);
+      mbar_init(tempty_bar(b), Epi::SPLIT ? 256 : 64 * epi_groups<Epi>::value);
     }
-    mbar_init(xbar, epi_xbar_count<Epi>::value);   // one per epilogue group (see EpiLnStore)
-    mbar_init(xbar + 8u, epi_xbar_count<Epi>::value);
+    for (int b = 0; b < 4; ++b) mbar_init(xbar + 8u * b, epi_xbar_count<Epi>::value);   // see EpiLnStore
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -299,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     cx.group = (warp - 2) >> 2;
     cx.smem = epi_smem + cx.group * Epi::SMEM_BYTES;
     cx.smem0 = epi_smem;
-    cx.xbar = xbar + 8u * (uint32_t)cx.group;
+    cx.xbar = xbar + 16u * (uint32_t)(cx.group & 1);
     cx.tid = threadIdx.x - 64 - 128 * cx.group;
     cx.q = warp & 3;  // TMEM lane quarter this warp may access
     cx.lane = lane;
@@ -308,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     UnitInfo w;
     for (int it = 0; get_unit<Epi::CLUSTER>(g, it, w); ++it) {
       const int buf = it % Cfg::ACC_BUFS;
-      if (!Epi::SPLIT && (Cfg::ACC_BUFS == 2 ? buf : 0) != cx.group) continue;  // group e owns buffer e
+      if (!Epi::SPLIT && (Cfg::ACC_BUFS == 2 ? buf : 0) != (cx.group & 1)) continue;  // groups e, e + 2 own buffer e
       const uint32_t use = (uint32_t)(it / Cfg::ACC_BUFS);
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();

@@ -33,6 +33,13 @@ bool pdl_enabled() {
   }();
   return on;
 }
+bool debug_sync_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("PIGAN_DEBUG_SYNC");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
 int sm_count() {
   static int cached_dev = -1;
   static int cached = 0;

@@ -37,6 +37,7 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 void note_launch();          // every kernel launch of the library passes through here (pigan_launch_count)
+bool debug_sync_enabled();  // PIGAN_DEBUG_SYNC=1: synchronise after every GEMM launch and name the kernel that failed
 bool pdl_enabled();         // programmatic dependent launch between consecutive kernels (PIGAN_PDL=0 disables)
 int sm_count();  // multiprocessors of the current device (cached per device)
 

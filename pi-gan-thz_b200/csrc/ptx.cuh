@@ -86,6 +86,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
 }
+// 8-byte store into (possibly another CTA's) shared memory that completes 8 transaction bytes on an mbarrier of the
+// receiving CTA: data and signal travel together, the sender needs no fence and no arrive
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_mbar) : "memory");
+}
 // arrive (release at cluster scope) on an mbarrier that may live in another CTA of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
