@@ -69,7 +69,8 @@ static int run_linear_cfg(const void* a, const void* a_tail, const void* b, cons
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  ep.out = OutTile{static_cast<__half*>(out), n, m, n};
+  ep.out.ptr = static_cast<__half*>(out); ep.out.ld = n; ep.out.rows = m; ep.out.cols = n;
+  PIGAN_TRY(make_tmap_f16_store(&ep.out.map, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
   ep.bias = bias;
   ep.scale = nullptr;
   ep.rowstats = rowstats;
@@ -103,7 +104,8 @@ static int run_linear2(const void* a, const void* a_tail, const void* b, const f
     g.a_tail = 1;
   }
   typename Epi::Params ep;
-  ep.out = OutTile{static_cast<__half*>(out), n, m, n};
+  ep.out.ptr = static_cast<__half*>(out); ep.out.ld = n; ep.out.rows = m; ep.out.cols = n;
+  PIGAN_TRY(make_tmap_f16_store(&ep.out.map, out, (uint64_t)n, (uint64_t)m, (uint64_t)n));
   ep.bias = bias;
   ep.scale = nullptr;
   ep.rowstats = rowstats;

@@ -22,7 +22,6 @@ constexpr int kKp = 256;  // spectrum operand width (S + P + 2 spare columns <= 
 using CfgS = GemmCfg<256, 1, 4, false>;      // store epilogues, both operands streamed (K > 256)
 using CfgSR = GemmCfg<256, 1, 4, false, 4>;  // store epilogues, K <= 256: the n-group's weights stay in shared memory
 using CfgP = GemmCfg<256, 1, 4, false>;      // no staging
-using CfgPR = GemmCfg<256, 1, 6, false, 4>;  // no staging, resident weights
 using CfgO = GemmCfg<144, 2, 2, false>;      // forward-model output layer, generic epilogue (fp32 dump)
 using CfgO4 = GemmCfg<144, 2, 4, false>;     // forward-model output layer, loss / scoring epilogues
 using CfgW = GemmCfg<256, 1, 4, true>;       // weight gradients
@@ -240,7 +239,7 @@ int out_map(OutTile* m, __half* ptr, int64_t rows, int cols, int ld) {
   m->ld = ld;
   m->rows = (int)rows;
   m->cols = cols;
-  return PIGAN_OK;
+  return make_tmap_f16_store(&m->map, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
 }
 
 // out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
@@ -277,6 +276,15 @@ long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
 template <int CLUSTER, bool PAIR = false, class Cfg = CfgL1>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
                 const float* bias, const float* gamma, const float* beta, __half* out, cudaStream_t st) {
+  static const bool lsu_store = [] { const char* v = getenv("PIGAN_LN_TMA"); return v && v[0] == '0'; }();
+  if (lsu_store) {   // comparison variant: read-back + global stores instead of TMA stores
+    using Epi = EpiLnStore<Cfg, CLUSTER, PAIR, 4, false>;
+    typename Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+    ep.bias = bias; ep.gamma = gamma; ep.beta = beta; ep.n_total = n;
+    ep.trace = g_ln_trace ? g_ln_trace + (n == 1024 ? 1 : n == 256 ? 3 : (k == 256 ? 0 : 2)) * 320 : nullptr;
+    return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st);
+  }
   using Epi = EpiLnStore<Cfg, CLUSTER, PAIR>;
   typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
@@ -296,7 +304,11 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
   // shared memory more than the operand ring does)
   if (n == 256) return linear_ln_c<1>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
   if (n == 512) return linear_ln_c<2>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
-  if (n == 1024) {   // clusters of 2, each CTA walks two n-groups per row tile (clusters of 4 fit only 132 SMs)
+  if (n == 1024) {
+    // clusters of 4 (132 of 148 SMs) unless PIGAN_LN_PAIR=1: clusters of 2 whose CTAs walk two n-groups per row tile
+    // (all SMs, but the row's statistics then wait for the second unit's MMAs and nothing overlaps)
+    static const bool pair = [] { const char* v = getenv("PIGAN_LN_PAIR"); return v && v[0] == '1'; }();
+    if (!pair) return linear_ln_c<4>(ta, tb, g, rows, k, n, bias, gamma, beta, out, st);
     GemmShape gp = g;
     gp.pair_mode = 1;
     return linear_ln_c<2, true>(ta, tb, gp, rows, k, n, bias, gamma, beta, out, st);
@@ -728,9 +740,11 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, e->partials, st);
       {
         PM("d_paramgrad_gemm");
-        using Epi = EpiDiscParamGrad<CfgPR>;
+        // streamed operands on purpose: the epilogue reads 16 bytes of first-layer weights per accumulator column
+        // through L1, and the resident-weight configuration leaves no shared memory for an L1 cache (66 vs 37 us)
+        using Epi = EpiDiscParamGrad<CfgP>;
         Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
-        PIGAN_TRY((run_tn<CfgPR, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+        PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
       }
       if (e->side_pending) {
         PIGAN_CUDA_OK(cudaStreamWaitEvent(st, e->ev_join, 0));   // the surrogate chain started in phase 2

@@ -52,25 +52,27 @@ __device__ __forceinline__ void load_cols32(const float* __restrict__ base, floa
 // Output tensor of a store epilogue: row-major fp16 [rows, cols] with row pitch ld (elements; ld % 8 == 0, 16-byte
 // aligned base)
 struct OutTile {
-  __half* ptr;
+  CUtensorMap map;   // box = 32 rows x 32 columns, 64B swizzle (host_util: make_tmap_f16_store): TMA-store variant
+  __half* ptr;       // LSU-store variant
   int ld, rows, cols;
 };
 
 // Per-warp staging of fp16 output blocks.  A warp owns 32 rows of the tile (its TMEM lane quarter); it packs 32
 // columns of them into a [32 x 32] fp16 block in shared memory (64-byte rows, 16-byte chunks XOR-swizzled:
-// conflict-free stores with a row per thread), reads the block back with four lanes per row and writes it with
-// ordinary 16-byte global stores - every store instruction covers 8 rows x 64 contiguous bytes.  Nothing is shared
-// between warps: one __syncwarp per block, no named barriers, no asynchronous proxy.
-//
-// Why not TMA stores (rounds 1 and early 2): the SM's TMA unit serves requests in order, and a store queues behind
-// the operand loads the producer warp keeps in flight.  clock64 traces of the LayerNorm epilogue showed 1900 cycles
-// per [128 x 64] block with group-wide staging (profiles/r02_ln_trace_before.txt) and 3000-8600 cycles per
-// [32 x 32] block when every warp waited for its own previous store (4 epilogue groups, one staging block per warp):
-// the wait for "the TMA unit has read my staging buffer" was the whole of pass 2.  LSU stores do not share that queue.
+// conflict-free stores with a row per thread) and the block leaves either as a TMA store issued by lane 0 or through
+// a read-back with four lanes per row and 16-byte global stores.  Nothing is shared between warps: one __syncwarp
+// per block, no named barriers.  (Round 1 staged [128 x 64] blocks per epilogue GROUP behind two bar.sync each.)
+// Measured (profiles/r02_time_step_*.txt): TMA stores win for every epilogue, by 3-8 % of the kernel - the read-back
+// costs shared-memory cycles the operand ring needs; the LSU variant is kept for comparison (PIGAN_LN_TMA=0).
 constexpr int kWarpBlockBytes = 2048;
 constexpr int kEpiStagingBytes = 4 * 2 * kWarpBlockBytes;   // per group of 4 warps, two blocks per warp
 
-template <int NBUF>
+// TMA = true : lane 0 issues a TMA store of the block; the buffer is reused once the TMA unit has read it (NBUF blocks
+//              alternate).  Best for epilogues with slack (plain Linear / dX stores): nothing but the pack and four
+//              16-byte shared-memory stores per block on the warp's critical path.
+// TMA = false: the warp reads the block back (four lanes per row) and writes it with 16-byte global stores.  For
+//              epilogues that must not wait for the TMA unit (see above).
+template <int NBUF, bool TMA = true>
 struct WarpStagerT {
   static_assert(NBUF == 1 || NBUF == 2, "blocks per warp");
   uint32_t cnt;
@@ -83,9 +85,14 @@ struct WarpStagerT {
     cnt = 0;
     base = warp_base;
   }
-  __device__ __forceinline__ uint32_t acquire(const EpiCtx&) {
-    if (NBUF == 1) __syncwarp();   // the read-back of the previous block is done (two blocks: the sync of the block
-                                   // in between already separates them)
+  __device__ __forceinline__ uint32_t acquire(const EpiCtx& cx) {
+    if constexpr (TMA) {
+      if (cx.lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that used this block NBUF commits ago has read it
+      __syncwarp();
+    } else {
+      if (NBUF == 1) __syncwarp();   // the read-back of the previous block is done (two blocks: the sync of the block
+                                     // in between already separates them)
+    }
     return base + (NBUF == 2 ? (cnt & 1u) * kWarpBlockBytes : 0u);
   }
   // 32 values of this thread's row (lane = row within the warp's 32 rows)
@@ -111,25 +118,38 @@ struct WarpStagerT {
   }
   // col0: first of the 32 columns; row0: first row of the 128-row tile
   __device__ __forceinline__ void commit(const EpiCtx& cx, uint32_t buf, const OutTile& o, int col0, int row0) {
-    __syncwarp();
-    const int chunk = cx.lane & 3;
-    const int col = col0 + chunk * 8;
-    const int rbase = row0 + cx.q * 32 + (cx.lane >> 2);
+    if constexpr (TMA) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (cx.lane == 0) {
+        tma_store_2d(&o.map, buf, col0, row0 + cx.q * 32);
+        tma_store_commit();
+      }
+    } else {
+      __syncwarp();
+      const int chunk = cx.lane & 3;
+      const int col = col0 + chunk * 8;
+      const int rbase = row0 + cx.q * 32 + (cx.lane >> 2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rl = (cx.lane >> 2) + 8 * i;   // row within the warp's 32
-      uint32_t w0, w1, w2, w3;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                   : "r"(buf + (uint32_t)rl * 64u + (uint32_t)((chunk ^ ((rl >> 1) & 3)) << 4))
-                   : "memory");
-      const int row = rbase + 8 * i;
-      if (row < o.rows && col < o.cols)
-        *reinterpret_cast<uint4*>(o.ptr + (size_t)row * o.ld + col) = make_uint4(w0, w1, w2, w3);
+      for (int i = 0; i < 4; ++i) {
+        const int rl = (cx.lane >> 2) + 8 * i;   // row within the warp's 32
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(buf + (uint32_t)rl * 64u + (uint32_t)((chunk ^ ((rl >> 1) & 3)) << 4))
+                     : "memory");
+        const int row = rbase + 8 * i;
+        if (row < o.rows && col < o.cols)
+          *reinterpret_cast<uint4*>(o.ptr + (size_t)row * o.ld + col) = make_uint4(w0, w1, w2, w3);
+      }
     }
     ++cnt;
   }
-  __device__ __forceinline__ static void drain(const EpiCtx&) {}
+  __device__ __forceinline__ static void drain(const EpiCtx& cx) {
+    if constexpr (TMA) {
+      if (cx.lane == 0) tma_store_wait<0>();
+    }
+  }
 };
 using WarpStager = WarpStagerT<2>;
 
@@ -262,8 +282,10 @@ struct EpiStore {
 // which forces both passes to be fully unrolled: 45 KB of code per kernel, and the ncu source view showed the
 // epilogue warps issuing one instruction every ~4 cycles (18 % of their stall samples "no instruction", 14 % the
 // membar of the release-arrive on the peer's barrier).  tcgen05.ld delivers ~460 B/clk per SM (profiles/
-// r02_ldtm_bench2.txt), so re-reading the accumulator is cheap; both passes are now rolled loops over 64-column
-// chunks (4 KB of code).
+// r02_ldtm_bench2.txt), so re-reading the accumulator is cheap; both passes are now rolled loops over 32-column
+// chunks.  What the epilogue is bound by after that (profiles/r02_ln_trace_*.txt, tools/ln_trace.py): the three
+// per-column constants of pass 2 - every constant a thread needs costs a cycle of the shared-memory / L1 data
+// pipe per warp whether it comes from shared memory, L1 or the constant bank, because a thread owns a ROW.
 // =====================================================================================================
 //   PAIR = false: CTA rank r owns n-group r (N = 256 * CLUSTER); its two epilogue groups alternate row tiles.
 //   PAIR = true : a CTA walks both n-groups 2r, 2r+1 of a row tile back to back (GemmShape::pair_mode, N = 512 *
@@ -273,7 +295,7 @@ struct EpiStore {
 //                 accumulator buffer g & 1 and take 128 columns each.  The ncu source view of the two-group version
 //                 showed the epilogue warps stalled 77 % of the time on fixed-latency dependencies and constant
 //                 loads with only two warps per scheduler to hide them.
-template <class Cfg, int CLUSTER_, bool PAIR = false, int GROUPS_ = 4>
+template <class Cfg, int CLUSTER_, bool PAIR = false, int GROUPS_ = 4, bool TMA_STORE = true>
 struct EpiLnStore {
   static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiLnStore tile shape");
   static_assert(GROUPS_ == 2 || GROUPS_ == 4, "epilogue groups");
@@ -311,7 +333,7 @@ struct EpiLnStore {
   static constexpr int SMEM_BYTES = SMEM_TOTAL / GROUPS_;
   static_assert(SMEM_TOTAL % (1024 * GROUPS_) == 0, "alignment of the barrier block behind the epilogue scratch");
   struct State {
-    WarpStagerT<NBUF> stg;
+    WarpStagerT<NBUF, TMA_STORE> stg;
     uint32_t it;
     uint32_t rank;
   };
@@ -437,13 +459,13 @@ struct EpiLnStore {
         }
       }
       const uint32_t sbuf = st.stg.acquire(cx);
-      WarpStagerT<NBUF>::put32_packed(sbuf, cx.lane, hw);
+      WarpStagerT<NBUF, TMA_STORE>::put32_packed(sbuf, cx.lane, hw);
       st.stg.commit(cx, sbuf, p.out, cofs + c, w.m_tile * kBlockM);
     }
     if (tr) trow[3] = clock64();
   }
   __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) {
-    WarpStagerT<NBUF>::drain(cx);
+    WarpStagerT<NBUF, TMA_STORE>::drain(cx);
   }
 };
 
@@ -593,13 +615,16 @@ struct EpiDiscParamGrad {
     const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
     const int n0 = w.n_group * Cfg::BLOCK_N;
     const bool valid = row < g.M;
-    static_assert(Cfg::BLOCK_N == 256, "mask words of a 256-column tile");
-    const uint4* msrc = reinterpret_cast<const uint4*>(p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32);
-    const uint4 mA = __ldg(msrc), mB = __ldg(msrc + 1);
+    // (one .x32 load per trip and the loop left rolled: the 32 uniform 16-byte weight loads per trip dominate, and
+    // larger trips only add register pressure - 37 us against 53 us with .x64 loads and 128-column trips)
+    const uint32_t* mrow = p.mask + (size_t)(valid ? row : 0) * p.mask_words + n0 / 32;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    drain_blocks32<Cfg::BLOCK_N, 128>(tacc, [&](int c, int k, float* v) {
-      const uint4 m4 = (c >> 7) ? mB : mA;
-      const uint32_t bits = k == 0 ? m4.x : k == 1 ? m4.y : k == 2 ? m4.z : m4.w;
+#pragma unroll 1
+    for (int c = 0; c < Cfg::BLOCK_N; c += 32) {
+      float v[32];
+      tmem_ld32(tacc + c, v);
+      const uint32_t bits = __ldg(mrow + c / 32);
+      tmem_ld_wait();
       const float4* wq = reinterpret_cast<const float4*>(p.wp) + n0 + c;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -610,7 +635,7 @@ struct EpiDiscParamGrad {
         a2 = fmaf(gz, w4.z, a2);
         a3 = fmaf(gz, w4.w, a3);
       }
-    });
+    }
     if (valid) {
       atomicAdd(p.dparams + (size_t)row * 4 + 0, a0);
       atomicAdd(p.dparams + (size_t)row * 4 + 1, a1);
