@@ -37,7 +37,7 @@ FLOP_PER_PRETRAIN_SAMPLE = 2 * 4_132_352   # F fwd + bwd (dW + dX),
 METRIC = "PI-GAN train samples/s"
 # DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/, round 1): the four
 # Linear+LayerNorm launches of the forward surrogate read+write 46.9 + 147.4 + 171.5 + 72.7 MB
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 109.6e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 109.6e6   # refreshed from profiles/r02_gemm_kernels_ncu_full.csv by tools/ncu_summary.py
 
 
 def read_peaks():
@@ -165,7 +165,8 @@ def run_reference(args):
     spec, praw, pnorm, mnorm = fixtures.make_batch(sample, seed=11)
     b = (spec, praw, pnorm, None, mnorm)
     steps = max(1, min(args.steps, 20))
-    for _ in range(max(1, min(args.warmup, 3))):
+    warm = max(3, args.warmup)            # same warm-up count as the native arm
+    for _ in range(warm):
         O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -174,10 +175,14 @@ def run_reference(args):
     v = sample * steps / el
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": el / steps * 1e3, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate), batch {args.batch} per GPU, "
-                               "S=250, reference widths", "sample_batch": sample},
+                               "S=250, reference widths", "sample_batch": sample,
+                   "extrapolation": f"a CPU step is timed at batch {sample} (bounded sample); samples/s is per-sample "
+                                    f"throughput and does not grow with the batch on the CPU (measured 68 vs 78 ms per "
+                                    f"4096 rows for the port and the real train_pigan), so it is compared as is with "
+                                    f"the GPU's samples/s at batch {args.batch}"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of batch {sample} (oracle/models.py train_step, fp32, torch CPU)"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -283,6 +288,9 @@ def run_native(args):
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
                 "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_gemm_kernels_ncu_full.csv "
                 "(ncu --set full, dram__bytes_read+write, mean of the 4 EpiLnStore launches)", "peak_source": peaks["source"] + " bf16 sustained",
+                "frac_of_burst_peak": ach / peaks["tflops_burst"], "peak_burst": peaks["tflops_burst"],
+                "timed_region_ms": ms, "note": "the timed region is tens of milliseconds at full clocks: between the "
+                "burst and the sustained (seconds-long, power-capped) cuBLAS figure; both fractions are given",
                 "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
     step_tflops = FLOP_PER_TRAIN_SAMPLE * B * K / (ms * 1e-3) / 1e12
 
@@ -378,15 +386,18 @@ def run_native(args):
         op = NativeTrainer.prepare_operand(sp, pr, center)
         host_prep.append((op.cpu().pin_memory(), mn.cpu().pin_memory()))
     ms2, h2d_bytes_prep = run_e2e(host_prep, lambda b: tr.step_prepared(b[0], center, b[1], lr, lr), K)
-    e2e = {"value": B * world * K / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes_prep,
-           "d2h_bytes_per_step": 36, "ms_per_step": ms2 / K,
-           "api": "NativeTrainer.step_prepared(fp16 operand prepared once per dataset, metrics_norm)"}
+    e2e_prepared = {"value": B * world * K / (ms2 * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes_prep,
+                    "d2h_bytes_per_step": 36, "ms_per_step": ms2 / K,
+                    "api": "NativeTrainer.step_prepared(fp16 operand prepared once per dataset, metrics_norm)"}
     del host_prep
     host_raw = [tuple(x.cpu().pin_memory() for x in s_) for s_ in sets]
     ms2b, h2d_bytes = run_e2e(host_raw, lambda b: tr.step(b[0], b[1], b[2], lr, lr), K)
-    e2e_fp32 = {"value": B * world * K / (ms2b * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 36, "ms_per_step": ms2b / K,
-                "api": "NativeTrainer.step(spectrum, params_denorm, metrics_norm) on fp32 host tensors"}
+    e2e = {"value": B * world * K / (ms2b * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+           "d2h_bytes_per_step": 36, "ms_per_step": ms2b / K,
+           "api": "NativeTrainer.step(spectrum, params_denorm, metrics_norm) on the fp32 host tensors the reference's "
+                  "DataLoader yields (pinned), H2D on a copy stream, 9 losses read back every step",
+           "critical_path": "h2d" if ms2b / K > 1.15 * ms / K else "step",
+           "h2d_gbs": h2d_bytes * world / (ms2b / K * 1e-3) / 1e9}
     del host_raw
 
     # ---- inverse-design scoring (BASELINE config 4): candidates/s, sharded by candidate, final top-k gather
@@ -397,7 +408,7 @@ def run_native(args):
     seng.load_forward_model(tr.fs.params.tensor())
     designer = scoring.InverseDesigner(seng, gs.params.tensor(), gs.bn.tensor(), chunk=chunk)
     target = sets[0][0][0].clone()
-    n_cand = args.candidates * world
+    n_cand = args.candidates               # TOTAL over all ranks (BASELINE config 4: 100 M, strong scaling)
     designer.search(target, 4 * chunk * world, k=1024)
     barrier()
     e0.record()
@@ -411,48 +422,98 @@ def run_native(args):
     ms3 = float(t.item())
     cand_s = n_cand / (ms3 * 1e-3)
     clk = clocks.stop()     # sampled across the three timed regions (device-resident, end-to-end, scoring)
+    score_tf = cand_s * FLOP_PER_CANDIDATE / 1e12 / world
     score_info = {"metric": "inverse-design candidates/s", "value": cand_s, "unit": "candidates/s",
-                  "candidates": n_cand, "k": 1024, "ms": ms3, "best_recon_error": float(res["recon_error"][0]),
-                  "tensor_frac": cand_s * FLOP_PER_CANDIDATE / 1e12 / (peaks["tflops"] * world),
-                  "chunk": chunk,
+                  "candidates": n_cand, "candidates_per_gpu": n_cand // world, "scaling": "strong", "n_gpus": world,
+                  "per_gpu": cand_s / world, "k": 1024, "ms": ms3,
+                  "best_recon_error": float(res["recon_error"][0]),
+                  "roofline": {"bound": "tensor", "achieved": score_tf, "peak": peaks["tflops"],
+                               "unit": "TFLOP/s per GPU", "frac": score_tf / peaks["tflops"],
+                               "frac_of_burst_peak": score_tf / peaks["tflops_burst"],
+                               "flop_per_candidate": FLOP_PER_CANDIDATE,
+                               "target_50pct": 0.5 * peaks["tflops"] * 1e12 / FLOP_PER_CANDIDATE},
+                  "tensor_frac": score_tf / peaks["tflops"],
+                  "chunk": chunk, "collective": "one all_gather of k rows per rank + local merge" if world > 1 else "none",
                   "noise": "in-kernel Philox4x32-10 keyed by (seed, global candidate index)"}
+    # model-validation loop (unified_evaluator.py:439-468): cycle error + stability + plausibility per row, one call
+    vn = min(chunk, 65536)
+    vspec = sets[0][0][:vn]
+    vnoise = torch.randn(vn, 250, device=dev)
+    for _ in range(2):
+        seng.validate(gs.params.tensor(), gs.bn.tensor(), vspec, vnoise, 0.01)
+    barrier()
+    e0.record()
+    for _ in range(5):
+        vres = seng.validate(gs.params.tensor(), gs.bn.tensor(), vspec, vnoise, 0.01)
+    e1.record()
+    barrier()
+    msv = e0.elapsed_time(e1) / 5
+    score_info["model_validation"] = {"rows_per_s": vn / (msv * 1e-3), "rows": vn, "ms": msv,
+                                      "cycle_error_mean": float(vres["cycle_error"].mean()),
+                                      "stability_mean": float(vres["stability"].mean()),
+                                      "plausibility_mean": float(vres["plausibility"].mean())}
+    del vspec, vnoise
     del designer, seng
 
-    # ---- physics metrics (BASELINE config 3): one warp per spectrum, HBM-bound
+    # ---- physics metrics (BASELINE config 3): sweep 1 M .. 64 M spectra, HBM-bound, sharded by spectrum
     from pigan_b200 import native
-    n_phys = args.physics_spectra
     phys_info = None
-    if n_phys > 0:
-        reps = max(1, n_phys // B)
-        spec_big = sets[0][0].repeat(reps, 1)[:n_phys].contiguous() if reps > 1 else sets[0][0][:n_phys]
-        n_phys = spec_big.shape[0]
+    sizes = [int(x) for x in args.physics_sweep.split(",") if x] if args.physics_sweep else []
+    if sizes:
+        from pigan_b200 import physics as phys_mod
         freq = synthetic.frequencies(250, device=dev)
-        o_idx = torch.empty(n_phys, device=dev, dtype=torch.int32)
-        o_met = torch.empty(n_phys, 4, device=dev, dtype=torch.float32)
+        sweep = []
+        lo, hi = phys_mod.shard_rows(max(sizes), rank, world)       # sharded by spectrum, no collective
+        base = sets[0][0]
+        try:
+            spec_big = base.repeat((hi - lo + B - 1) // B, 1)[: hi - lo].contiguous()
+        except torch.OutOfMemoryError:
+            spec_big = None
+            sizes = [n for n in sizes if n * 1000 < 40e9]
+            lo, hi = phys_mod.shard_rows(max(sizes), rank, world)
+            spec_big = base.repeat((hi - lo + B - 1) // B, 1)[: hi - lo].contiguous()
+        o_idx = torch.empty(hi - lo, device=dev, dtype=torch.int32)
+        o_met = torch.empty(hi - lo, 4, device=dev, dtype=torch.float32)
+        for n_total in sizes:
+            a, b_ = phys_mod.shard_rows(n_total, rank, world)
+            n_loc = b_ - a
 
-        def phys():
-            native.check(native.lib.pigan_physics_metrics(spec_big.data_ptr(), n_phys, 250, freq.data_ptr(), None, 0.0,
-                                                          o_idx.data_ptr(), o_met.data_ptr(), native.current_stream()))
-        for _ in range(3):
-            phys()
-        barrier()
-        e0.record()
-        for _ in range(5):
-            phys()
-        e1.record()
-        barrier()
-        ms4 = e0.elapsed_time(e1) / 5
-        gbs = n_phys * 1016 / (ms4 * 1e-3) / 1e9
-        phys_info = {"metric": "physics-metric spectra/s", "value": n_phys / (ms4 * 1e-3), "unit": "spectra/s",
-                     "spectra": n_phys, "ms": ms4,
-                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                  "frac": gbs / peaks["hbm_gbs"], "bytes_per_spectrum": 1016}}
-        # backward of the same kernel: vector-Jacobian product into the spectra
-        g_met = torch.ones(n_phys, 4, device=dev)
-        g_spec = torch.empty_like(spec_big)
+            def phys():
+                native.check(native.lib.pigan_physics_metrics(spec_big.data_ptr(), n_loc, 250, freq.data_ptr(), None,
+                                                              0.0, o_idx.data_ptr(), o_met.data_ptr(),
+                                                              native.current_stream()))
+            for _ in range(3):
+                phys()
+            barrier()
+            e0.record()
+            for _ in range(5):
+                phys()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms4 = float(t.item())
+            gbs = n_total * 1016 / (ms4 * 1e-3) / 1e9 / world
+            sweep.append({"spectra": n_total, "ms": ms4, "value": n_total / (ms4 * 1e-3), "unit": "spectra/s",
+                          "gbs_per_gpu": gbs, "frac": gbs / peaks["hbm_gbs"]})
+        best = max(sweep, key=lambda r: r["value"])
+        phys_info = {"metric": "physics-metric spectra/s", "value": best["value"], "unit": "spectra/s",
+                     "spectra": best["spectra"], "ms": best["ms"], "n_gpus": world, "scaling": "weak-by-size sweep, "
+                     "sharded by spectrum over the ranks, no collective",
+                     "input": f"the {B}-row synthetic batch tiled to the sweep size (distinct rows do not matter for "
+                              f"an HBM-bound row kernel; {best['spectra'] * 1000 / 1e9:.0f} GB >> 126 MB L2)",
+                     "sweep": sweep,
+                     "roofline": {"bound": "hbm", "achieved": best["gbs_per_gpu"], "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s per GPU", "frac": best["gbs_per_gpu"] / peaks["hbm_gbs"],
+                                  "bytes_per_spectrum": 1016}}
+        # backward of the same kernel: vector-Jacobian product into the spectra, at the 4 M point
+        n_b = min(hi - lo, (1 << 22) // world)
+        g_met = torch.ones(n_b, 4, device=dev)
+        g_spec = torch.empty(n_b, 250, device=dev)
 
         def phys_bwd():
-            native.check(native.lib.pigan_physics_metrics_backward(spec_big.data_ptr(), n_phys, 250, freq.data_ptr(), None,
+            native.check(native.lib.pigan_physics_metrics_backward(spec_big.data_ptr(), n_b, 250, freq.data_ptr(), None,
                                                                    0.0, g_met.data_ptr(), g_spec.data_ptr(), None, None,
                                                                    native.current_stream()))
         for _ in range(2):
@@ -464,11 +525,12 @@ def run_native(args):
         e1.record()
         barrier()
         ms4b = e0.elapsed_time(e1) / 5
-        gbs_b = n_phys * 2016 / (ms4b * 1e-3) / 1e9
-        phys_info["backward"] = {"value": n_phys / (ms4b * 1e-3), "unit": "spectra/s", "ms": ms4b,
+        gbs_b = n_b * 2016 / (ms4b * 1e-3) / 1e9
+        phys_info["backward"] = {"value": n_b / (ms4b * 1e-3), "unit": "spectra/s per GPU", "spectra": n_b, "ms": ms4b,
                                  "roofline": {"bound": "hbm", "achieved": gbs_b, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                               "frac": gbs_b / peaks["hbm_gbs"], "bytes_per_spectrum": 2016}}
         del spec_big, o_idx, o_met, g_met, g_spec
+        torch.cuda.empty_cache()
 
     # ---- on-device data pipeline: synthetic-spectrum generator, shuffled batch gather, and the
     # train step fed from a resident dataset (gather of the fp16 operand + metrics rows, then step_prepared)
@@ -598,6 +660,9 @@ def run_native(args):
             "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate, 7 losses, clip+Adam), "
                                    f"batch {B} per GPU, S=250, reference widths",
                        "global_batch": B * world, "parallelism": f"dp{world}",
+                       "exchange": ("none (one GPU)" if world == 1 else
+                                    ("peer: one-shot all-reduce kernels over cudaIpc-mapped NVLink memory (csrc/dp.cu)"
+                                     if tr.xchg is not None else "nccl all-reduce")),
                        "rank_cpu_affinity": f"{numa_cpus} GPU-local cores per rank (NVML)" if numa_cpus else "default",
                        "l2": f"{NSETS} distinct input batches rotated ({NSETS * h2d_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roof,
@@ -606,7 +671,7 @@ def run_native(args):
                               "flop_per_sample": FLOP_PER_TRAIN_SAMPLE},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "e2e_fp32_inputs": e2e_fp32,
+            "e2e_prepared_operand": e2e_prepared,
             "gpu_launches": int(launches),
             "clocks": clk,
             "scoring": score_info,
@@ -629,8 +694,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=65536)
-    ap.add_argument("--candidates", type=int, default=1 << 23, help="candidates per GPU for the scoring line")
-    ap.add_argument("--physics-spectra", type=int, default=1 << 22, help="spectra for the physics-kernel line (0: skip)")
+    ap.add_argument("--candidates", type=int, default=100_000_000,
+                    help="TOTAL candidates of the scoring line (BASELINE config 4: 100 M), split over the ranks")
+    ap.add_argument("--physics-sweep", default="1048576,4194304,16777216,67108864",
+                    help="total spectra of the physics-kernel sweep (BASELINE config 3), comma separated; '' skips")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-quant-probe", action="store_true")
     args = ap.parse_args()

@@ -139,10 +139,10 @@ int pigan_forward_model_forward(PiganEngine* engine, const float* params_norm, i
  * Adam(betas 0.5/0.999) for both networks.  Phases let the host interleave the data-parallel all-reduces:
  *   phase 0  G forward up to BatchNorm-1 statistics     -> reduce bn_sums[0 .. 2*h1)
  *   phase 1  ... up to BatchNorm-2 statistics           -> reduce bn_sums[2*h1 .. 2*h1+2*h2)
- *   phase 2  G head, D-step forward/backward            -> reduce d_grads, loss_sums
+ *   phase 2  G head, D-step forward/backward            -> reduce d_grads
  *   phase 3  D clip+Adam; G-step D/F forward, losses, head backward -> reduce bn_bwd_sums[0 .. 2*h2)
  *   phase 4  BatchNorm-2 backward, dW2, dX              -> reduce bn_bwd_sums[2*h2 .. 2*h2+2*h1)
- *   phase 5  BatchNorm-1 backward, dW1                  -> reduce g_grads, loss_sums
+ *   phase 5  BatchNorm-1 backward, dW1                  -> reduce g_grads, loss_sums[0:8] (all loss numerators)
  *   phase 6  G clip+Adam, loss finalisation
  * With one process, pigan_train_step runs phases 0..6 back to back. */
 typedef struct PiganTrainArgs {
@@ -175,7 +175,8 @@ typedef struct PiganTrainArgs {
   float* losses; /* [9] device: d, g, adv, recon_spec, recon_metrics, maxwell, lc, param_range, bnn_kl */
   /* optional, instead of spectrum + params_denorm: the fp16 first-layer operand [B,256] built once per dataset by
    * pigan_prepare_spectrum_operand (the analogue of MetamaterialDataset's one-time normalisation,
-   * data_loader.py:185-219) and the row [S] it was centred on.  Halves the bytes a step needs from the host. */
+   * data_loader.py:185-219) and the row [S] it was centred on.  Halves the bytes a step needs from the host.
+   * The batch must then be a multiple of 128 rows (PIGAN_ERR_INVALID otherwise). */
   const void* spectrum_operand;
   const float* spectrum_center;
 } PiganTrainArgs;
@@ -231,6 +232,13 @@ int pigan_score_candidates(PiganEngine* engine, const float* g_params, const flo
                            const float* spectra, const float* target, const float* noise, float sigma, int64_t n,
                            float* out_params_norm, int32_t* out_violations, float* out_recon_error,
                            float* out_consistency, void* stream);
+/* Model-validation loop body — UnifiedEvaluator.evaluate_model_validation (core/evaluate/unified_evaluator.py:439-468)
+ * for n rows in one call: out_cycle_error[r] = mean((x_r - F(G(x_r)).spectrum)^2), out_stability[r] =
+ * mean((G(x_r) - G(x_r + sigma * noise_r))^2), out_plausibility[r] = mean(sigmoid(10 G(x_r) - 5)); noise [n,S] is
+ * passed explicitly (the reference draws torch.randn_like).  out_params_norm [n,4] may be NULL. */
+int pigan_validate_model(PiganEngine* engine, const float* g_params, const float* g_bn_buffers, const float* spectra,
+                         const float* noise, float sigma, int64_t n, float* out_params_norm, float* out_cycle_error,
+                         float* out_stability, float* out_plausibility, void* stream);
 /* Inverse-design search (BASELINE config 4): scores `count` candidates cand_i = target + sigma * z_i, i = first_candidate
  * ... first_candidate + count - 1, through G(eval) -> F(eval) -> mean((target - recon)^2) and keeps the k best.
  * z_i is drawn in-kernel (Philox4x32-10 keyed by `seed`, counter = (i, column block)), so candidate i gets the same

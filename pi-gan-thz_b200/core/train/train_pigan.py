@@ -35,6 +35,11 @@ from core.utils.set_seed import set_seed
 from pigan_b200.trainer import LOSS_KEYS, NativeTrainer
 
 
+def _is_rank0() -> bool:
+    d = torch.distributed
+    return not (d.is_available() and d.is_initialized()) or d.get_rank() == 0
+
+
 def train_pigan(dataloader, device, generator, discriminator, forward_model, dataset, num_epochs: int,
                 log_interval: int = 10):
     print("\n--- starting PI-GAN training (B200-native step) ---")
@@ -99,7 +104,7 @@ def train_pigan(dataloader, device, generator, discriminator, forward_model, dat
         for k, v in zip(LOSS_KEYS, avg):
             loss_history[k].append(v)
 
-        if (epoch + 1) % cfg.SAVE_MODEL_INTERVAL == 0:
+        if (epoch + 1) % cfg.SAVE_MODEL_INTERVAL == 0 and _is_rank0():   # replicas are identical: rank 0 writes
             os.makedirs(cfg.CHECKPOINT_DIR, exist_ok=True)
             trainer.export_optimizer_state(optimizer_g, optimizer_d)
             path = os.path.join(cfg.CHECKPOINT_DIR, f"pigan_epoch_{epoch + 1}.pth")
@@ -114,11 +119,14 @@ def train_pigan(dataloader, device, generator, discriminator, forward_model, dat
             print(f"checkpoint saved to {path}")
 
     print("--- PI-GAN training finished ---")
-    os.makedirs(cfg.SAVED_MODELS_DIR, exist_ok=True)
-    torch.save(generator.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "generator_final.pth"))
-    torch.save(discriminator.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "discriminator_final.pth"))
-    torch.save(forward_model.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "forward_model_final.pth"))
-    torch.save(loss_history, os.path.join(cfg.SAVED_MODELS_DIR, "pigan_loss_history.pt"))
+    if _is_rank0():
+        os.makedirs(cfg.SAVED_MODELS_DIR, exist_ok=True)
+        torch.save(generator.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "generator_final.pth"))
+        torch.save(discriminator.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "discriminator_final.pth"))
+        torch.save(forward_model.state_dict(), os.path.join(cfg.SAVED_MODELS_DIR, "forward_model_final.pth"))
+        torch.save(loss_history, os.path.join(cfg.SAVED_MODELS_DIR, "pigan_loss_history.pt"))
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()      # nobody returns (and reads the files) before rank 0 has written them
     return loss_history
 
 

@@ -158,7 +158,9 @@ __global__ void center_vec_kernel(const float* __restrict__ x, int S, int rows_u
 template <bool NOISE>
 __global__ void cast_center_kernel(const float* __restrict__ x, const float* __restrict__ noise, float sigma,
                                    const float* __restrict__ cvec, const float* __restrict__ params,
-                                   __half* __restrict__ xc, long long rows, int S, int P, int Kp, int vec2) {
+                                   __half* __restrict__ xc, long long rows, int S, int P, int Kp, int vec2,
+                                   long long x_stride) {
+  // NOISE: row r of the operand is x[r * x_stride + j] + sigma * noise[r, j] (x_stride = 0: one target row for all)
   pdl_wait();
   const int cpr = Kp >> 3;
   const long long total = rows * cpr;
@@ -176,7 +178,7 @@ __global__ void cast_center_kernel(const float* __restrict__ x, const float* __r
 #pragma unroll
       for (int i = 0; i < 4; ++i) t[i] = __ldg(src + i);
       if (NOISE) {
-        const float2* tg = reinterpret_cast<const float2*>(x + j0);
+        const float2* tg = reinterpret_cast<const float2*>(x + row * x_stride + j0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 g = __ldg(tg + i);
@@ -196,7 +198,7 @@ __global__ void cast_center_kernel(const float* __restrict__ x, const float* __r
         const int j = j0 + i;
         float t = 0.f;
         if (j < S) {
-          if (NOISE) t = (x[j] + sigma * noise[row * S + j]) - cvec[j];
+          if (NOISE) t = (x[row * x_stride + j] + sigma * noise[row * S + j]) - cvec[j];
           else t = x[row * S + j] - cvec[j];
         } else if (j < S + P) {
           t = params ? params[row * P + (j - S)] - kParamCenter : 0.f;
@@ -1356,6 +1358,23 @@ __global__ void score_finish_kernel(const float* __restrict__ p, const float* __
 }
 
 
+// Model-validation scores (unified_evaluator.py:453-468): stability[r] = mean_j (p[r,j] - p_noisy[r,j])^2,
+// plausibility[r] = mean_j sigmoid(10 p[r,j] - 5)
+__global__ void validation_scores_kernel(const float* __restrict__ p, const float* __restrict__ pn, long long rows,
+                                         int P, float* __restrict__ stab, float* __restrict__ plaus) {
+  pdl_wait();
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < P; ++j) {
+    const float a = p[r * P + j], d = a - pn[r * P + j];
+    s = fmaf(d, d, s);
+    q += 1.0f / (1.0f + expf(-(a * 10.f - 5.f)));
+  }
+  if (stab) stab[r] = s / (float)P;
+  if (plaus) plaus[r] = q / (float)P;
+}
+
 // ------------------------------------------------------------------------------------------ surrogate training
 // Training-mode forward model (pretrain_fwd_model.py:68-92, forward_model.py:28-52): Linear -> LayerNorm ->
 // LeakyReLU -> Dropout(0.2).  The keep-mask is counter based: Philox4x32-10 keyed by the caller's seed, counter =
@@ -1795,15 +1814,17 @@ void launch_cast_center(const float* x, const float* cvec, const float* params, 
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
   launch_k(cast_center_kernel<false>, grid > 0 ? grid : 1, kThreads, 0, st, x, nullptr, 0.f, cvec, params, xc, rows, S, P, Kp,
-                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) ? 1 : 0);
+                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) ? 1 : 0,
+                                                                             0ll);
 }
 void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
-                              float*, int64_t rows, int S, int P, int Kp, cudaStream_t st) {
+                              float*, int64_t rows, int S, int P, int Kp, cudaStream_t st, int64_t target_stride) {
   const int64_t total = rows * (Kp / 8);
   const int grid = (int)((total + kThreads - 1) / kThreads < 148 * 16 ? (total + kThreads - 1) / kThreads : 148 * 16);
   launch_k(cast_center_kernel<true>, grid > 0 ? grid : 1, kThreads, 0, st, target, noise, sigma, cvec, nullptr, xc, rows, S, P, Kp,
                                                                             (S % 2 == 0 && (reinterpret_cast<uintptr_t>(target) & 7) == 0 &&
-                                                                             (reinterpret_cast<uintptr_t>(noise) & 7) == 0) ? 1 : 0);
+                                                                             (reinterpret_cast<uintptr_t>(noise) & 7) == 0) ? 1 : 0,
+                                                                            (long long)target_stride);
 }
 void launch_cast_center_philox(const float* target, float sigma, uint64_t seed, int64_t first, const float* cvec,
                                __half* xc, float* noise_out, int64_t rows, int S, int Kp, cudaStream_t st) {
@@ -1988,6 +2009,11 @@ void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const flo
   launch_k(dw_fixup_kernel, (total + 255) / 256, 256, 0, st, dw, ld, S, P, db, cvec, rows);
 }
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { launch_k(loss_finalize_kernel, 1, 32, 0, st, a); }
+void launch_validation_scores(const float* p, const float* p_noisy, int64_t rows, int P, float* stability,
+                              float* plausibility, cudaStream_t st) {
+  launch_k(validation_scores_kernel, (int)((rows + 255) / 256), 256, 0, st, p, p_noisy, (long long)rows, P, stability,
+           plausibility);
+}
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st) {
   launch_k(score_finish_kernel, (int)((rows + 255) / 256), 256, 0, st, p, err, rows, P, violations, consistency);

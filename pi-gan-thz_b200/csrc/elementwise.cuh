@@ -37,8 +37,10 @@ void launch_center_vec(const float* x, int64_t rows, int S, int rows_used, float
 void launch_cast_center(const float* x, const float* cvec, const float* params, __half* xc, int64_t rows, int S,
                         int P, int Kp, cudaStream_t st);
 // candidate spectra x = target + sigma * noise (unified_evaluator.py:453-455), centred on cvec
+// target_stride = S: per-row base spectra x[r] + sigma * noise[r] (the evaluator's stability test, :453-455)
 void launch_cast_center_noise(const float* target, const float* noise, float sigma, const float* cvec, __half* xc,
-                              float* x_out, int64_t rows, int S, int P, int Kp, cudaStream_t st);
+                              float* x_out, int64_t rows, int S, int P, int Kp, cudaStream_t st,
+                              int64_t target_stride = 0);
 
 // candidates with in-kernel Philox4x32-10 noise: z(first + r, j) depends only on (seed, global candidate index, j)
 void launch_cast_center_philox(const float* target, float sigma, uint64_t seed, int64_t first, const float* cvec,
@@ -220,6 +222,9 @@ void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st);
 // violations[r] = #{j : p[r,j] < 0 or p[r,j] > 1}; consistency[r] = 1 / (1 + err[r])  (unified_evaluator.py:380,391)
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st);
+// stability[r] = mean_j (p - p_noisy)^2, plausibility[r] = mean_j sigmoid(10 p - 5)   (unified_evaluator.py:458-468)
+void launch_validation_scores(const float* p, const float* p_noisy, int64_t rows, int P, float* stability,
+                              float* plausibility, cudaStream_t st);
 
 
 // ------------------------------------------------------------------------------------------ surrogate training

@@ -219,17 +219,23 @@ int check_dims(const PiganDims& d) {
   return PIGAN_OK;
 }
 
+// a_tail: [m, 64] replaces the last k-block of A.  a2 (k2 columns, pitch k2): A = [a | a2] along K, b has k + k2 columns.
 template <class Cfg, class Epi>
 int run_tn(typename Epi::Params& ep, const __half* a, int64_t m, int k, int lda, const __half* b, int n, int ldb,
-           cudaStream_t st, const __half* a_tail = nullptr) {
+           cudaStream_t st, const __half* a_tail = nullptr, const __half* a2 = nullptr, int k2 = 0) {
   CUtensorMap ta, tb, tx;
   PIGAN_TRY(make_tn_maps<Cfg>(&ta, &tb, a, (int)m, k, lda, b, n, ldb));
-  GemmShape g = make_shape<Cfg>((int)m, n, k);
+  GemmShape g = make_shape<Cfg>((int)m, n, k + k2);
   if (a_tail) {
     PIGAN_TRY(make_tmap_f16_2d(&tx, a_tail, 64, (uint64_t)m, 64, kBlockK, kBlockM));
     g.a_tail = 1;
+  } else if (a2) {
+    if (k % kBlockK != 0) return fail(PIGAN_ERR_INVALID, "K-concatenated operands: first part must be a multiple of 64");
+    PIGAN_TRY(make_tmap_f16_2d(&tb, b, (uint64_t)(k + k2), (uint64_t)n, (uint64_t)ldb, kBlockK, Cfg::BLOCK_N));
+    PIGAN_TRY(make_tmap_f16_2d(&tx, a2, (uint64_t)k2, (uint64_t)m, (uint64_t)k2, kBlockK, kBlockM));
+    g.a_split_kb = k / kBlockK;
   }
-  return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, a_tail ? &tx : nullptr);
+  return launch_gemm<Cfg, Epi>(ta, tb, g, ep, st, 0, (a_tail || a2) ? &tx : nullptr);
 }
 
 int out_map(OutTile* m, __half* ptr, int64_t rows, int cols, int ld) {
@@ -815,6 +821,11 @@ int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
   PIGAN_CHECK_ARG(a->spectrum_operand ? (a->spectrum_center != nullptr &&
                                          (reinterpret_cast<uintptr_t>(a->spectrum_operand) & 15u) == 0)
                                       : (a->spectrum != nullptr && a->params_denorm != nullptr));
+  // caller-prepared operand: the weight-gradient GEMM of D's first layer walks the operand in 128-row tiles (fake rows
+  // wrap onto the same tiles), so a ragged slice would be read up to 127 rows past its end
+  if (a->spectrum_operand != nullptr && a->batch % 128 != 0)
+    return fail(PIGAN_ERR_INVALID, "spectrum_operand: batch %lld must be a multiple of 128 (pass spectrum / "
+                "params_denorm for ragged batches)", (long long)a->batch);
   PIGAN_CHECK_ARG(a->g_params && a->g_grads && a->g_exp_avg && a->g_exp_avg_sq);
   PIGAN_CHECK_ARG(a->d_params && a->d_grads && a->d_exp_avg && a->d_exp_avg_sq);
   PIGAN_CHECK_ARG(a->step >= 1);
@@ -1060,6 +1071,36 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
   PIGAN_TRY(f_forward(e, p, n, fo, st, fused_head(e)));
   PM("small");
   if (out_viol || out_cons) launch_score_finish(p, err, n, G.P, out_viol, out_cons, st);
+  PM(nullptr);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// Model-validation loop body (core/evaluate/unified_evaluator.py:439-468) in one call: cycle-consistency error
+// mean((x - F(G(x)).spectrum)^2), prediction stability mean((G(x) - G(x + sigma * noise))^2) and the plausibility
+// score mean(sigmoid(10 p - 5)) per row; the noise tensor is passed explicitly.
+extern "C" int pigan_validate_model(PiganEngine* e, const float* gp, const float* bn, const float* spectra,
+                                    const float* noise, float sigma, int64_t n, float* out_p, float* out_cycle_error,
+                                    float* out_stability, float* out_plausibility, void* stream) {
+  PIGAN_CHECK_ARG(e && gp && bn && spectra && noise && n >= 1 && n <= e->max_batch);
+  PIGAN_CHECK_ARG(out_cycle_error && out_stability && out_plausibility);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GenLayout& G = e->gl;
+  PIGAN_TRY(prep_spectrum(e, spectra, nullptr, n, st));
+  PIGAN_TRY(g_eval_setup(e, gp, bn, st));
+  float* p = out_p ? out_p : e->p;
+  PIGAN_TRY(g_eval_forward(e, gp, n, p, st, true));
+  FOutOpts fo{2, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, out_cycle_error, 0, 1};
+  PIGAN_TRY(f_forward(e, p, n, fo, st, fused_head(e)));
+  // the same generator on x + sigma * noise (same centring row, same packed weights).  Measured: feeding the noise as
+  // a second operand against sigma * W1 (identical rounding of the x part in both passes) does not help - the score
+  // is a difference of two outputs ~1e-3 apart and the fp16 rounding of the stored activations of the two passes
+  // (2e-4 each) limits a row's value to ~20 %; means over rows agree to 1 % (tests/test_gpu_engine.py)
+  PM("prep_cast");
+  launch_cast_center_noise(spectra, noise, sigma, e->cvec, e->xc, nullptr, n, G.S, G.P, kKp, st, G.S);
+  PIGAN_TRY(g_eval_forward(e, gp, n, e->pden, st, false));
+  PM("small");
+  launch_validation_scores(p, e->pden, n, G.P, out_stability, out_plausibility, st);
   PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;

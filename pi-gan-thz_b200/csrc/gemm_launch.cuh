@@ -111,6 +111,7 @@ GemmShape make_shape(int m, int n, int k, int k_splits = 1, int b_wrap_rows = 0)
   g.k_splits = k_splits < 1 ? 1 : (k_splits > g.num_k_blocks ? g.num_k_blocks : k_splits);
   g.b_wrap_k_blocks = b_wrap_rows / kBlockK;
   g.a_tail = 0;
+  g.a_split_kb = -1;
   g.b_tail_from_kb = -1;
   g.pair_mode = 0;
   return g;

@@ -37,6 +37,8 @@ struct GemmShape {
   int k_splits;         // >= 1; units = m_tiles * n_groups * k_splits
   int b_wrap_k_blocks;  // NT mode: B operand row block index is taken modulo this (0 = off)
   int a_tail;           // TN mode: last k-block of A is read from tmap_x at column 0
+  int a_split_kb;       // TN mode: k-blocks >= a_split_kb of A come from tmap_x, column (kb - a_split_kb) * 64
+                        // (K-concatenation of two operands: [x | z] . [W | s W]^T); < 0: off
   int b_tail_from_kb;   // NT mode: k-blocks >= this read the last B box of the last n-tile from tmap_x (<0 off)
   int pair_mode;        // a CTA handles the two n-groups of an m-tile back to back (whole-row epilogues that split
                         // the row between the two epilogue groups / accumulator buffers); k_splits must be 1 and
@@ -244,6 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if constexpr (!Cfg::MN_MAJOR) {
               if (g.a_tail && kb == g.num_k_blocks - 1)
                 tma_load_2d(sa, &tmap_x, full_bar(stage), 0, w.m_tile * kBlockM);
+              else if (g.a_split_kb >= 0 && kb >= g.a_split_kb)
+                tma_load_2d(sa, &tmap_x, full_bar(stage), (kb - g.a_split_kb) * kBlockK, w.m_tile * kBlockM);
               else
                 tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, w.m_tile * kBlockM);
               if constexpr (!Cfg::B_RESIDENT) tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);

@@ -169,8 +169,17 @@ class DeviceLoader:
         gb = self.batch_size * self.world
         for b in range(len(self)):
             chunk = perm[b * gb:(b + 1) * gb]
-            lo, hi = rank_slice(chunk.numel(), self.rank, self.world)
-            yield chunk[lo:hi].contiguous()
+            if self.world > 1:
+                # data parallel: every rank must see the SAME number of rows (the trainers take global batch =
+                # local rows x world for BatchNorm statistics, loss means and the gradient scale, and a rank that
+                # skipped a step would leave its peers waiting in the exchange kernels): a ragged last global batch is
+                # cut to a multiple of the world size on all ranks alike, and dropped when that leaves < 2 rows each
+                per = chunk.numel() // self.world
+                if per < 2:
+                    continue
+                yield chunk[self.rank * per:(self.rank + 1) * per].contiguous()
+                continue
+            yield chunk.contiguous()
 
     def __iter__(self):
         ds = self.ds

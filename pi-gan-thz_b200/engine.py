@@ -177,6 +177,23 @@ class Engine:
         return {"params_norm": out_p, "violations": viol, "recon_error": err, "consistency": cons}
 
 
+def _validate(self, g_flat, bn, spectra, noise, sigma: float = 0.01) -> Dict[str, torch.Tensor]:
+    """Loop body of UnifiedEvaluator.evaluate_model_validation (unified_evaluator.py:439-468) for all rows at once:
+    per-row cycle-consistency error, prediction stability under ``sigma * noise`` and plausibility score."""
+    _require_cuda(spectra, "spectra")
+    n, dev = spectra.shape[0], spectra.device
+    out_p = torch.empty(n, self.dims.param_dim, device=dev, dtype=torch.float32)
+    cyc, stab, plaus = (torch.empty(n, device=dev, dtype=torch.float32) for _ in range(3))
+    sp, nz = _f32c(spectra), _f32c(noise)
+    check(lib.pigan_validate_model(self.handle, g_flat.data_ptr(), bn.data_ptr(), sp.data_ptr(), nz.data_ptr(),
+                                   float(sigma), n, out_p.data_ptr(), cyc.data_ptr(), stab.data_ptr(),
+                                   plaus.data_ptr(), native.current_stream()))
+    return {"params_norm": out_p, "cycle_error": cyc, "stability": stab, "plausibility": plaus}
+
+
+Engine.validate = _validate
+
+
 def _search(self, g_flat, bn, target, sigma, seed, first, count, k, dump_noise=False):
     """pigan_inverse_design_search on this engine: (scores [k], indices [k], params_norm [k,4][, noise])."""
     dev = self.device

@@ -59,6 +59,9 @@ class ForwardTrainer:
             if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
                 raise RuntimeError(f"ForwardTrainer.step: {name} must be a contiguous fp32 CUDA tensor")
         B = params_norm.shape[0]
+        if self.world > 1:
+            from .trainer import check_equal_batch
+            self._dp_batch = check_equal_batch(B, getattr(self, "_dp_batch", None), self.pg)
         self.step_count += 1
         a = PiganFwdTrainArgs()
         a.params_norm, a.spectrum, a.metrics_norm = params_norm.data_ptr(), spectrum.data_ptr(), metrics_norm.data_ptr()

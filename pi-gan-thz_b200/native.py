@@ -117,6 +117,7 @@ SIGNATURES = {
     "pigan_engine_bn_bwd_sums": (_vp, [_vp]),
     "pigan_engine_loss_sums": (_vp, [_vp]),
     "pigan_score_candidates": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "pigan_validate_model": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "pigan_search_workspace_bytes": (C.c_size_t, [_vp, _i32]),
     "pigan_inverse_design_search": (_i32, [_vp, _vp, _vp, _vp, _f32, C.c_uint64, _i64, _i64, _i32, _vp, _vp, _vp, _vp,
                                            _vp, C.c_size_t, _vp]),

@@ -109,3 +109,36 @@ def two_peak_metrics(spectra: torch.Tensor, frequency: Optional[torch.Tensor] = 
     m1, m2 = peak_metrics(spec, freq, i1), peak_metrics(spec, freq, i2)
     cols = [m1["f_res"], m2["f_res"], m1["Q"], m1["FoM"], m1["S"], m2["Q"], m2["FoM"], m2["S"]]
     return {"metrics": torch.stack(cols, dim=1), "peak_idx": torch.stack([i1, i2], dim=1).to(torch.int32)}
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU
+def shard_rows(n: int, rank: int, world: int):
+    """Contiguous row range [begin, end) of ``rank`` when n spectra are split over ``world`` GPUs: the first
+    ``n % world`` ranks take one row more.  The physics kernel treats every spectrum independently, so the sharded
+    result is the concatenation of the ranks' results - no collective on the data path."""
+    if not (0 <= rank < world):
+        raise ValueError("0 <= rank < world required")
+    base, extra = divmod(int(n), int(world))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def sharded_peak_summary(local: Dict[str, torch.Tensor], group=None) -> Dict[str, float]:
+    """Global summary of a sharded ``peak_metrics`` run: number of spectra, number with a defined Q, and the means of
+    f_res / Q / FoM over the defined ones.  The only collective is ONE all-reduce of seven float64 sums; the per-row
+    results stay on the rank that computed them."""
+    import torch.distributed as dist
+    q = local["Q"]
+    ok = ~torch.isnan(q)
+    sums = torch.stack([torch.tensor(float(q.numel()), device=q.device, dtype=torch.float64),
+                        ok.sum().double(),
+                        local["f_res"].double().sum(),
+                        torch.where(ok, q, torch.zeros_like(q)).double().sum(),
+                        torch.where(ok, local["FoM"], torch.zeros_like(q)).nan_to_num(0.0).double().sum(),
+                        (~torch.isnan(local["FoM"])).sum().double(),
+                        torch.where(ok, local["S"], torch.zeros_like(q)).double().sum()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, group=group)
+    n, nq, sf, sq, sfom, nfom, ss = (float(x) for x in sums.tolist())
+    return {"spectra": n, "defined_Q": nq, "f_res_mean": sf / max(n, 1.0), "Q_mean": sq / max(nq, 1.0),
+            "FoM_mean": sfom / max(nfom, 1.0), "S_mean": ss / max(nq, 1.0)}

@@ -34,6 +34,26 @@ def dp_phase_plan(h1: int, h2: int):
     ]
 
 
+def check_equal_batch(batch: int, last_checked, group=None) -> int:
+    """Data parallel: all ranks must step with the same number of rows (global batch = rows x world enters BatchNorm
+    statistics, loss means and the gradient scale; a rank that stops early leaves its peers spinning in the peer
+    exchange kernels).  Called before anything is launched whenever the local batch size changes (the ragged last
+    batch of an epoch changes it on all ranks at once); raises on EVERY rank when the sizes differ.  A loader that
+    changes the size on some ranks only is not caught here - device_data.DeviceLoader(rank, world) never does.
+    Returns the size to remember."""
+    if batch == last_checked:
+        return last_checked
+    world = dist.get_world_size(group)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(batch), group=group)
+    if len(set(sizes)) != 1:
+        raise RuntimeError(f"data-parallel step with unequal local batches {sizes}: use drop_last / "
+                           "device_data.DeviceLoader(rank, world), which cuts ragged batches on all ranks alike")
+    if batch < 2:
+        raise RuntimeError("data-parallel step needs at least 2 rows per rank")
+    return batch
+
+
 def run_dp_step(run_phase, get_buffer, all_reduce, plan) -> None:
     """One data-parallel step: engine phases in order, each followed by its all-reduces (in place, sum)."""
     for phase, reductions in plan:
@@ -137,6 +157,8 @@ class NativeTrainer:
                         (center, "center")):
             if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
                 raise RuntimeError(f"NativeTrainer.step: {name} must be a contiguous fp32 CUDA tensor")
+        if self.world > 1:
+            self._dp_batch = check_equal_batch(metrics_norm.shape[0], getattr(self, "_dp_batch", None), self.pg)
         self.step_count += 1
         args = self._args(spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand, center)
         if self.world == 1:

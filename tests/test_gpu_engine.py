@@ -393,6 +393,39 @@ def test_scoring_matches_oracle_and_is_row_independent(n):
         assert torch.equal(out2["violations"].cpu(), out["violations"].cpu()[perm])
 
 
+def test_model_validation_scores_match_reference_golden_and_oracle():
+    """pigan_validate_model against UnifiedEvaluator.evaluate_model_validation (golden, 96 rows, the reference's own
+    noise draws) and against the oracle at 5 000 rows: cycle error and plausibility within 1e-3.  The stability score is
+    the squared DIFFERENCE of two generator outputs ~1e-3 apart: the fp16 rounding of the stored activations of the
+    two passes (2e-4 each) limits a single row to ~20 %; that noise is independent of the true difference, so it adds
+    its variance to the squared difference: the mean over rows (what the evaluator reports) reads 4 % high."""
+    from oracle import fixtures
+    from oracle import models as O
+    from pigan_b200 import flat
+    from pigan_b200.engine import get_engine
+    g = np.load(os.path.join(GOLD, "validation.npz"))
+    g_sd, d_sd, f_sd = _weights()
+    G, D, F = _models(g_sd, d_sd, f_sd)
+    G.eval()
+    st = flat.net_state(G, "generator")
+    fs = flat.net_state(F, "forward_model")
+    for n, seed in ((96, 32), (5000, 33)):
+        spec, _, _, _ = fixtures.make_batch(n, seed=seed)
+        if n == 96:
+            noise = torch.from_numpy(g["noise"])
+            ref = tuple(torch.from_numpy(g[k]) for k in ("cycle_error", "stability", "plausibility"))
+        else:
+            noise = torch.randn(n, 250, generator=torch.Generator().manual_seed(5))
+            ref = O.validation_scores(g_sd, f_sd, spec, noise)
+        eng = get_engine(DEV, 8192)
+        eng.load_forward_model(fs.params.tensor())
+        out = eng.validate(st.params.tensor(), st.bn.tensor(), spec.to(DEV), noise.to(DEV), 0.01)
+        assert rel(out["cycle_error"], ref[0]) < TOL_OUT
+        assert rel(out["plausibility"], ref[2]) < TOL_OUT
+        assert rel(out["stability"], ref[1]) < 0.3, rel(out["stability"], ref[1])
+        assert abs(float(out["stability"].mean()) - float(ref[1].mean())) < 8e-2 * float(ref[1].mean())
+
+
 @pytest.mark.parametrize("n,k", [(1, 1), (1000, 7), (65536, 1024), (1 << 20, 4096), (300000, 64)])
 def test_topk_is_exact(n, k):
     from pigan_b200.engine import topk_smallest

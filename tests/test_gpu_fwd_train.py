@@ -26,7 +26,7 @@ if PKG not in sys.path:
 DEV = "cuda"
 HID = (256, 512, 1024, 512, 256)
 TOL_LOSS = 1e-3
-TOL_GRAD = {64: 8e-3, 130: 6e-3, 1024: 3e-3}   # whole gradient, by batch size; single tensors 6x
+TOL_GRAD = {64: 8e-3, 130: 6e-3, 1024: 3e-3, 65536: 1.5e-3}   # whole gradient, by batch size; single tensors 6x
 
 
 def rel(a, b):
@@ -60,7 +60,7 @@ def _names():
     return [f"model.{i}.{s}" for i in sorted(O.F_LINEAR + O.F_NORM) for s in ("weight", "bias")]
 
 
-@pytest.mark.parametrize("B", [64, 130, 1024])
+@pytest.mark.parametrize("B", [64, 130, 1024, 65536])
 def test_step_matches_oracle(B):
     """Losses, unclipped gradients (phase 0) and the Adam update (phase 1) of one step, incl. a ragged batch."""
     import ctypes as C
@@ -97,9 +97,12 @@ def test_step_matches_oracle(B):
     flat_ref = torch.cat([ref_grads[n].reshape(-1) for n in _names()])
     tol = TOL_GRAD[B]
     assert rel(raw, flat_ref) < tol, rel(raw, flat_ref)
+    worst = {}
     for n in _names():
-        r = rel(views[n], ref_grads[n])
-        assert r < 6 * tol, (n, r)
+        worst[n] = rel(views[n], ref_grads[n])
+        assert worst[n] < 6 * tol, (n, worst[n])
+    print(f"\n[surrogate step B={B}] whole gradient {rel(raw, flat_ref):.2e}; worst tensor "
+          f"{max(worst, key=worst.get)} {max(worst.values()):.2e}")
     # clipped gradients left behind like torch's .grad after clip_grad_norm_
     coef = min(1.0, 1.0 / (float(flat_ref.norm()) + 1e-6))
     assert rel(tr.grads, flat_ref * coef) < tol

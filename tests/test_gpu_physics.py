@@ -82,3 +82,21 @@ def test_physics_edge_cases():
 def test_physics_empty():
     from pigan_b200 import native
     assert native.lib.pigan_physics_metrics(None, 0, 250, None, None, 0.0, None, None, None) == 0
+
+
+def test_physics_sharded_by_spectrum_equals_unsharded():
+    """the kernel shards by spectrum with no collective - the ranks' results (physics.shard_rows ranges)
+    concatenate to the single-GPU result bit for bit, for any world size."""
+    from oracle import fixtures
+    from pigan_b200 import physics
+    n = 10007
+    spec, _, _, _ = fixtures.make_batch(n, seed=91)
+    x = spec.cuda()
+    full = physics.peak_metrics(x)
+    for world in (2, 3, 8):
+        parts = [physics.peak_metrics(x[slice(*physics.shard_rows(n, r, world))]) for r in range(world)]
+        for k in ("peak_idx", "f_res", "Q", "FoM", "S"):
+            cat = torch.cat([p[k] for p in parts])
+            assert torch.equal(torch.nan_to_num(cat.float(), nan=-7.0), torch.nan_to_num(full[k].float(), nan=-7.0)), (world, k)
+    s = physics.sharded_peak_summary(full)
+    assert s["spectra"] == n and 0 < s["defined_Q"] <= n

@@ -242,6 +242,21 @@ def test_scoring_matches_reference_evaluator():
     _close(cons.numpy().std(), g["agg_consistency_score_std"], rtol=1e-4)
 
 
+def test_validation_scores_match_reference_evaluator():
+    """oracle.validation_scores against UnifiedEvaluator.evaluate_model_validation itself (tests/golden/validation.npz,
+    noise recorded from the reference's own torch.randn_like calls)."""
+    g = _load("validation.npz")
+    g_sd, d_sd, f_sd = fixtures.make_weights(42)
+    spec, _, _, _ = fixtures.make_batch(96, seed=32)
+    cyc, stab, plaus = O.validation_scores(g_sd, f_sd, spec, torch.from_numpy(g["noise"]))
+    _close(cyc.numpy(), g["cycle_error"], rtol=2e-5)
+    _close(stab.numpy(), g["stability"], rtol=1e-4)
+    _close(plaus.numpy(), g["plausibility"], rtol=2e-5)
+    _close(cyc.mean(), g["agg_cycle_consistency_error_mean"], rtol=1e-5)
+    _close(stab.mean(), g["agg_prediction_stability_mean"], rtol=1e-4)
+    _close(plaus.numpy().std(), g["agg_physical_plausibility_std"], rtol=1e-4)
+
+
 def test_bf16_autocast_reference_is_looser():
     """Yard-stick for the GPU tolerances (tests/test_gpu_engine.py): the reference step under torch's own bf16
     autocast deviates from its fp32 self by ~1e-2 on D gradients and several 1e-2 on G gradients — the '1e-3

@@ -185,6 +185,63 @@ def scoring():
     print("scoring:", {k: float(v) for k, v in agg.items()})
 
 
+def validation():
+    """The model-validation loop (unified_evaluator.py:415-490) through UnifiedEvaluator.evaluate_model_validation
+    itself: cycle-consistency error, prediction stability under 0.01 * randn noise, plausibility score.  torch's
+    randn_like is replaced by a recorded noise source for the duration of the call (batch size 64, rows in the order
+    the reference's np.random.choice picked them), so the noise travels with the golden file."""
+    from torch.utils.data import Dataset
+    import core.evaluate.unified_evaluator as ue
+
+    G, D, F = ref_models()
+    G.eval(); F.eval()
+    n = 96
+    spec, praw, pnorm, mnorm = fixtures.make_batch(n, seed=32)
+
+    class DS(Dataset):
+        param_ranges = {k: (2.2, 2.8) for k in ("r1", "r2", "w", "g")}
+        def __len__(self): return n
+        def __getitem__(self, i): return spec[i], praw[i], pnorm[i], torch.zeros(8), mnorm[i]
+
+    ev = ue.UnifiedEvaluator.__new__(ue.UnifiedEvaluator)
+    ev.device = torch.device("cpu"); ev.generator = G; ev.forward_model = F; ev.discriminator = D; ev.dataset = DS()
+    gen = torch.Generator().manual_seed(77)
+    drawn = []
+    orig = torch.randn_like
+
+    def recorded(t, **kw):
+        z = torch.randn(t.shape, generator=gen, dtype=t.dtype)
+        drawn.append(z.clone())
+        return z
+
+    np.random.seed(1)
+    order = np.random.choice(n, n, replace=False)     # the rows evaluate_model_validation will pick
+    np.random.seed(1)
+    torch.randn_like = recorded
+    try:
+        agg = ev.evaluate_model_validation(num_samples=n)
+    finally:
+        torch.randn_like = orig
+    noise_in_order = torch.cat(drawn)                  # row j of the loop = dataset row order[j]
+    noise = torch.empty_like(noise_in_order)
+    noise[torch.as_tensor(order)] = noise_in_order
+    res = {"agg_" + k: np.array(v, dtype=np.float64) for k, v in agg.items()}
+    res["noise"] = noise.numpy()
+    with torch.no_grad():                              # per-row values of the same loop body (:446-468)
+        p = G(spec)
+        rec, _ = F(p)
+        res["cycle_error"] = torch.mean((spec - rec) ** 2, dim=1).numpy()
+        pn_ = G(spec + noise * 0.01)
+        res["stability"] = torch.mean((p - pn_) ** 2, dim=1).numpy()
+        res["plausibility"] = torch.mean(torch.sigmoid(p * 10 - 5), dim=1).numpy()
+    for k in ("cycle_error", "stability", "plausibility"):   # the per-row restatement reproduces the aggregates
+        key = {"cycle_error": "cycle_consistency_error", "stability": "prediction_stability",
+               "plausibility": "physical_plausibility"}[k]
+        assert abs(res[k].mean() - agg[key + "_mean"]) <= 1e-6 * abs(agg[key + "_mean"]) + 1e-12, (k, res[k].mean(), agg)
+    np.savez(os.path.join(OUT, "validation.npz"), **res)
+    print("validation:", {k: float(v) for k, v in agg.items()})
+
+
 def fwd_pretrain():
     """The reference's own pretrain_forward_model (pretrain_fwd_model.py:24-158) with torch.nn.functional.dropout
     replaced by explicit keep-masks (oracle/fixtures.make_dropout_masks) so the run is reproducible elsewhere."""
@@ -379,6 +436,6 @@ if __name__ == "__main__":
         for name in sys.argv[1:]:
             globals()[name]()
     else:
-        physics(); forward(); train_step(); scoring(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset(); config_constants(); checkpoint_structure()
+        physics(); forward(); train_step(); scoring(); validation(); fwd_pretrain(); evaluator_metrics(); datagen(); dataset(); config_constants(); checkpoint_structure()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
