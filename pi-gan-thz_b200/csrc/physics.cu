@@ -9,6 +9,8 @@
 // the only difference from the oracle on fp32 inputs is the final rounding of the outputs to fp32.
 // HBM-bound: s*4 bytes in, 20 bytes out per spectrum.
 #include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 
@@ -136,6 +138,79 @@ __device__ __forceinline__ void row_scan(const float (&v)[VPL], int s, int lane,
   tmin_out = t_min;
 }
 
+// The scalar part of calculate_peak_parameters for one row (data_loader.py:27-58), run by the lane that holds the
+// row's scan results: float64 interpolation of the two crossings, Q, FoM, S (and, BWD, the five gradient entries).
+template <bool BWD>
+__device__ __forceinline__ void row_finish(const float* __restrict__ t, long long row, int s,
+                                           const double* __restrict__ freq, float baseline, int idx, int lo, int up,
+                                           float t_min, int* __restrict__ out_idx, float* __restrict__ out_metrics,
+                                           const float* __restrict__ grad_metrics, float* __restrict__ grad_spectra) {
+  // t: the row's samples (global or shared memory)
+      const double h = (double)t_min + ((double)baseline - (double)t_min) / 2.0;
+      const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
+      double f_res = kNaN, Q = kNaN, FoM = kNaN, S = kNaN;
+      if (idx >= 0 && idx < s) {
+        f_res = freq[idx];
+        double f_lower = kNaN, f_upper = kNaN;
+        if (lo >= 0) {
+          const double ti = (double)t[lo], tj = (double)t[lo + 1];
+          const double fi = freq[lo], fj = freq[lo + 1];
+          f_lower = ((tj - ti) != 0.0) ? fi + (h - ti) * (fj - fi) / (tj - ti) : fi;
+        }
+        if (up != 0x7fffffff) {
+          const double ti = (double)t[up], tj = (double)t[up + 1];
+          const double fi = freq[up], fj = freq[up + 1];
+          f_upper = ((tj - ti) != 0.0) ? fi + (h - ti) * (fj - fi) / (tj - ti) : fi;
+        }
+        if (!isnan(f_lower) && !isnan(f_upper) && f_upper > f_lower) {
+          const double delta_f = f_upper - f_lower;
+          if (delta_f > 1e-9) Q = f_res / delta_f;
+          const double tm = (double)t_min;
+          if (!isnan(tm) && fabs(tm) > 1e-6) FoM = isnan(Q) ? kNaN : Q / fabs(tm);
+        }
+        if (!isnan(Q)) S = (f_res / 1.0) * (Q / 100.0) * 100.0;
+        if constexpr (BWD) {
+          if (!isnan(Q)) {
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(grad_metrics) + row);   // d/d(f_res, Q, FoM, S)
+            const double tm = (double)t_min, delta_f = f_upper - f_lower;
+            const bool fom_ok = !isnan(FoM);
+            // Q = f_res / (f_upper - f_lower), FoM = Q / |t_min|, S = f_res * Q; f_res = frequency[idx] is constant
+            const double gq = (double)gm.y + (fom_ok ? (double)gm.z / fabs(tm) : 0.0) + (double)gm.w * f_res;
+            const double g_fup = -gq * f_res / (delta_f * delta_f), g_flo = -g_fup;
+            double g_h = 0.0;
+            float* gr = grad_spectra + row * (long long)s;
+            {
+              const double ti = (double)t[lo], tj = (double)t[lo + 1], dt = tj - ti;
+              if (dt != 0.0) {   // f_lower = f_i + (h - t_i) w / (t_j - t_i)
+                const double w = freq[lo + 1] - freq[lo];
+                g_h += g_flo * w / dt;
+                gr[lo] += (float)(g_flo * w * (h - tj) / (dt * dt));
+                gr[lo + 1] += (float)(-g_flo * w * (h - ti) / (dt * dt));
+              }
+            }
+            {
+              const double ti = (double)t[up], tj = (double)t[up + 1], dt = tj - ti;
+              if (dt != 0.0) {
+                const double w = freq[up + 1] - freq[up];
+                g_h += g_fup * w / dt;
+                gr[up] += (float)(g_fup * w * (h - tj) / (dt * dt));
+                gr[up + 1] += (float)(-g_fup * w * (h - ti) / (dt * dt));
+              }
+            }
+            // h = t_min + (baseline - t_min) / 2; FoM's own dependence on |t_min|
+            double g_tmin = 0.5 * g_h;
+            if (fom_ok) g_tmin += (double)gm.z * (-Q * (tm > 0.0 ? 1.0 : -1.0) / (tm * tm));
+            gr[idx] += (float)g_tmin;
+          }
+        }
+      }
+      if (out_idx != nullptr) out_idx[row] = idx;   // 32 consecutive rows per warp: coalesced
+      if (!BWD || out_metrics != nullptr) {
+        float4 o = make_float4((float)f_res, (float)Q, (float)FoM, (float)S);
+        *reinterpret_cast<float4*>(out_metrics + row * 4) = o;
+      }
+}
+
 // A warp takes 32 consecutive rows: the warp-wide scan row by row (results parked in lane r for row r), then the
 // scalar fp64 interpolation of all 32 rows in parallel, one lane per row — the serial tail costs one pass per 32 rows.
 //
@@ -193,81 +268,202 @@ __global__ void __launch_bounds__(256) physics_metrics_kernel(
       if (lane == r) { my_idx = idx; my_lo = lo; my_up = up; my_tmin = tmin; }
     }
     if constexpr (BWD) __syncwarp();   // the rows are cleared before their owners add to them
-    if (lane < rows_here) {
-      const long long row = base + lane;
-      const float* t = spectra + row * (long long)s;
-      const int idx = my_idx, lo = my_lo, up = my_up;
-      const float t_min = my_tmin;
-      const double h = (double)t_min + ((double)baseline - (double)t_min) / 2.0;
-      const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
-      double f_res = kNaN, Q = kNaN, FoM = kNaN, S = kNaN;
-      if (idx >= 0 && idx < s) {
-        f_res = freq[idx];
-        double f_lower = kNaN, f_upper = kNaN;
-        if (lo >= 0) {
-          const double ti = (double)__ldg(t + lo), tj = (double)__ldg(t + lo + 1);
-          const double fi = freq[lo], fj = freq[lo + 1];
-          f_lower = ((tj - ti) != 0.0) ? fi + (h - ti) * (fj - fi) / (tj - ti) : fi;
-        }
-        if (up != 0x7fffffff) {
-          const double ti = (double)__ldg(t + up), tj = (double)__ldg(t + up + 1);
-          const double fi = freq[up], fj = freq[up + 1];
-          f_upper = ((tj - ti) != 0.0) ? fi + (h - ti) * (fj - fi) / (tj - ti) : fi;
-        }
-        if (!isnan(f_lower) && !isnan(f_upper) && f_upper > f_lower) {
-          const double delta_f = f_upper - f_lower;
-          if (delta_f > 1e-9) Q = f_res / delta_f;
-          const double tm = (double)t_min;
-          if (!isnan(tm) && fabs(tm) > 1e-6) FoM = isnan(Q) ? kNaN : Q / fabs(tm);
-        }
-        if (!isnan(Q)) S = (f_res / 1.0) * (Q / 100.0) * 100.0;
-        if constexpr (BWD) {
-          if (!isnan(Q)) {
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(grad_metrics) + row);   // d/d(f_res, Q, FoM, S)
-            const double tm = (double)t_min, delta_f = f_upper - f_lower;
-            const bool fom_ok = !isnan(FoM);
-            // Q = f_res / (f_upper - f_lower), FoM = Q / |t_min|, S = f_res * Q; f_res = frequency[idx] is constant
-            const double gq = (double)gm.y + (fom_ok ? (double)gm.z / fabs(tm) : 0.0) + (double)gm.w * f_res;
-            const double g_fup = -gq * f_res / (delta_f * delta_f), g_flo = -g_fup;
-            double g_h = 0.0;
-            float* gr = grad_spectra + row * (long long)s;
-            {
-              const double ti = (double)__ldg(t + lo), tj = (double)__ldg(t + lo + 1), dt = tj - ti;
-              if (dt != 0.0) {   // f_lower = f_i + (h - t_i) w / (t_j - t_i)
-                const double w = freq[lo + 1] - freq[lo];
-                g_h += g_flo * w / dt;
-                gr[lo] += (float)(g_flo * w * (h - tj) / (dt * dt));
-                gr[lo + 1] += (float)(-g_flo * w * (h - ti) / (dt * dt));
-              }
-            }
-            {
-              const double ti = (double)__ldg(t + up), tj = (double)__ldg(t + up + 1), dt = tj - ti;
-              if (dt != 0.0) {
-                const double w = freq[up + 1] - freq[up];
-                g_h += g_fup * w / dt;
-                gr[up] += (float)(g_fup * w * (h - tj) / (dt * dt));
-                gr[up + 1] += (float)(-g_fup * w * (h - ti) / (dt * dt));
-              }
-            }
-            // h = t_min + (baseline - t_min) / 2; FoM's own dependence on |t_min|
-            double g_tmin = 0.5 * g_h;
-            if (fom_ok) g_tmin += (double)gm.z * (-Q * (tm > 0.0 ? 1.0 : -1.0) / (tm * tm));
-            gr[idx] += (float)g_tmin;
-          }
-        }
-      }
-      if (out_idx != nullptr) out_idx[row] = idx;   // 32 consecutive rows per warp: coalesced
-      if (!BWD || out_metrics != nullptr) {
-        float4 o = make_float4((float)f_res, (float)Q, (float)FoM, (float)S);
-        *reinterpret_cast<float4*>(out_metrics + row * 4) = o;
+    if (lane < rows_here)
+      row_finish<BWD>(spectra + (base + lane) * (long long)s, base + lane, s, freq, baseline, my_idx, my_lo, my_up,
+                      my_tmin, out_idx, out_metrics, grad_metrics, grad_spectra);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lane-per-row variant for rows of up to 256 samples (the dataset's 250).  The 32 rows of a warp's chunk are contiguous
+// in memory (32 s floats), so lane 0 fetches the whole chunk with ONE bulk asynchronous copy (cp.async.bulk, the 1-D
+// TMA path) into the warp's private two-stage ring in shared memory and signals an mbarrier; then every LANE scans its
+// own row out of shared memory: a running (min, first index) over the row, and from the peak outwards the first
+// half-depth crossing on each side.  No shuffles, no reductions, no bit masks: ~55 warp instructions per row instead of
+// the ~350 of the warp-per-row kernel above, which profiles at 47 % of the HBM peak because it is ISSUE-bound, not
+// latency-bound (staging its rows with bulk copies, 192 KB in flight per SM, made it 10 % slower: tools/phys_bench.py).
+// Rows with a NaN, or a half-depth level that is not an fp32 number, take the reference's comparisons one by one in
+// float64 (exact path, same lane).
+constexpr int kRowsWarps = 6;     // 6 warps x 1 stage x 32 rows x 1000 B = 192 KB of shared memory per SM: a warp loads,
+constexpr int kRowsStages = 1;    // then scans; the other warps' loads and scans overlap it
+
+__device__ __forceinline__ uint32_t phys_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void phys_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void phys_bar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+// one row, one thread: peak index (given, or NumPy argmin) and the two crossing pairs (data_loader.py:27-47)
+__device__ __forceinline__ void row_scan_serial(const float* __restrict__ t, int s, const int* peak_idx, long long row,
+                                                float baseline, int& idx_out, int& lo_out, int& up_out, float& tmin_out) {
+  const float kInf = __int_as_float(0x7f800000);
+  // running (min, first index) in four independent chains (element p -> chain p & 3; strict < keeps the first
+  // occurrence inside a chain), 16 elements per trip with all loads issued up front: one lane walks its row alone,
+  // so the shared-memory latency has to be covered by instruction-level parallelism
+  float bv[4] = {kInf, kInf, kInf, kInf};
+  int bi[4] = {0, 1, 2, 3};
+  bool has_nan = false;
+  int i = 0;
+  if ((s & 1) == 0) {                   // rows start 8-byte aligned for even s: 64-bit loads
+    const float2* t2 = reinterpret_cast<const float2*>(t);
+    for (; i + 16 <= s; i += 16) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = t2[(i >> 1) + k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        has_nan |= (v[k].x != v[k].x) | (v[k].y != v[k].y);
+        const int c = (2 * k) & 3;
+        if (v[k].x < bv[c]) { bv[c] = v[k].x; bi[c] = i + 2 * k; }
+        if (v[k].y < bv[c + 1]) { bv[c + 1] = v[k].y; bi[c + 1] = i + 2 * k + 1; }
       }
     }
+  }
+  for (; i < s; ++i) {
+    const float v0 = t[i];
+    has_nan |= (v0 != v0);
+    const int c = i & 3;
+    // (dynamic chain index only in this short tail)
+    if (c == 0) { if (v0 < bv[0]) { bv[0] = v0; bi[0] = i; } }
+    else if (c == 1) { if (v0 < bv[1]) { bv[1] = v0; bi[1] = i; } }
+    else if (c == 2) { if (v0 < bv[2]) { bv[2] = v0; bi[2] = i; } }
+    else { if (v0 < bv[3]) { bv[3] = v0; bi[3] = i; } }
+  }
+  float b0 = bv[0];
+  int idx = bi[0];
+#pragma unroll
+  for (int c = 1; c < 4; ++c)
+    if (bv[c] < b0 || (bv[c] == b0 && bi[c] < idx)) { b0 = bv[c]; idx = bi[c]; }
+  if (has_nan) {                        // np.argmin: the first NaN
+    for (int k = 0; k < s; ++k)
+      if (t[k] != t[k]) { idx = k; break; }
+  }
+  if (peak_idx != nullptr) idx = peak_idx[row];
+  const bool idx_ok = idx >= 0 && idx < s;
+  const int ic = idx_ok ? idx : 0;
+  const float t_min = t[ic];
+  const double h = (double)t_min + ((double)baseline - (double)t_min) / 2.0;
+  const float hf = (float)h;
+  int lo = -1, up = 0x7fffffff;
+  if (!has_nan && (double)hf == h) {
+    for (int k = ic - 1; k >= 0; --k)
+      if ((t[k] >= hf) != (t[k + 1] >= hf)) { lo = k; break; }
+    for (int k = ic + 1; k + 1 < s; ++k)
+      if ((t[k] > hf) != (t[k + 1] > hf)) { up = k; break; }
+  } else {
+    for (int k = ic - 1; k >= 0; --k) {
+      const double a = (double)t[k], b = (double)t[k + 1];
+      if ((a >= h && b < h) || (a < h && b >= h)) { lo = k; break; }
+    }
+    for (int k = ic + 1; k + 1 < s; ++k) {
+      const double a = (double)t[k], b = (double)t[k + 1];
+      if ((a <= h && b > h) || (a > h && b <= h)) { up = k; break; }
+    }
+  }
+  idx_out = idx;
+  lo_out = lo;
+  up_out = up;
+  tmin_out = t_min;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kRowsWarps * 32, 1) physics_metrics_rows_kernel(
+    const float* __restrict__ spectra, long long n, int s, const double* __restrict__ freq,
+    const int* __restrict__ peak_idx, float baseline, int* __restrict__ out_idx,
+    float* __restrict__ out_metrics, const float* __restrict__ grad_metrics, float* __restrict__ grad_spectra) {
+  extern __shared__ __align__(128) unsigned char phys_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stage_pitch = ((uint32_t)(32 * s) * 4u + 127u) & ~127u;
+  unsigned char* my = phys_smem + (size_t)warp * kRowsStages * stage_pitch;
+  unsigned long long* bars =
+      reinterpret_cast<unsigned long long*>(phys_smem + (size_t)kRowsWarps * kRowsStages * stage_pitch) + warp * kRowsStages;
+  if (lane == 0) {
+    for (int i = 0; i < kRowsStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(phys_smem_u32(bars + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long warps_total = (long long)gridDim.x * kRowsWarps;
+  const long long warp0 = (long long)blockIdx.x * kRowsWarps + warp;
+  const long long groups = (n + 31) / 32;      // n is a multiple of 4 here: every chunk is a multiple of 16 bytes
+  auto issue = [&](long long k) {              // this warp's k-th chunk
+    const long long g = warp0 + k * warps_total;
+    if (g >= groups) return;
+    const long long r0 = g * 32;
+    const int rows = (int)(n - r0 < 32 ? n - r0 : 32);
+    const int slot = (int)(k % kRowsStages);
+    phys_bulk_load(phys_smem_u32(my + (size_t)slot * stage_pitch), spectra + r0 * (long long)s,
+                   (uint32_t)(rows * s) * 4u, phys_smem_u32(bars + slot));
+  };
+  if (lane == 0)
+    for (int k = 0; k < kRowsStages; ++k) issue(k);
+  for (long long k = 0;; ++k) {
+    const long long g = warp0 + k * warps_total;
+    if (g >= groups) break;
+    const long long r0 = g * 32;
+    const int rows = (int)(n - r0 < 32 ? n - r0 : 32);
+    const int slot = (int)(k % kRowsStages);
+    if constexpr (BWD) {
+      // clear the chunk's gradient rows (contiguous, 16-byte aligned: the host checks the base)
+      float4* gz = reinterpret_cast<float4*>(grad_spectra + r0 * (long long)s);
+      const int n4 = rows * s / 4;
+      for (int i = lane; i < n4; i += 32) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    phys_bar_wait(phys_smem_u32(bars + slot), (uint32_t)((k / kRowsStages) & 1));
+    if constexpr (BWD) __syncwarp();     // the rows are cleared before their owners add to them
+    if (lane < rows) {
+      const float* t = reinterpret_cast<const float*>(my + (size_t)slot * stage_pitch) + lane * s;
+      int idx, lo, up;
+      float tmin;
+      row_scan_serial(t, s, peak_idx, r0 + lane, baseline, idx, lo, up, tmin);
+      row_finish<BWD>(t, r0 + lane, s, freq, baseline, idx, lo, up, tmin, out_idx, out_metrics, grad_metrics,
+                      grad_spectra);
+    }
+    __syncwarp();                        // every lane has read the stage: it may be refilled
+    if (lane == 0) issue(k + kRowsStages);
   }
 }
 
 }  // namespace pigan
 
 using namespace pigan;
+
+namespace {
+bool phys_bulk_ok(const float* spectra, int s) {
+  static const bool off = [] { const char* v = getenv("PIGAN_PHYS_BULK"); return v && v[0] == '0'; }();
+  return !off && s >= 2 && s <= 256 && (reinterpret_cast<uintptr_t>(spectra) & 15u) == 0;
+}
+template <bool BWD>
+int launch_phys_bulk(const float* spectra, int64_t n, int s, const double* freq, const int* peak_idx, float baseline,
+                     int* out_idx, float* out_metrics, const float* grad_metrics, float* grad_spectra, cudaStream_t st) {
+  const uint32_t stage_pitch = ((uint32_t)(32 * s) * 4u + 127u) & ~127u;
+  const size_t smem = (size_t)kRowsWarps * kRowsStages * stage_pitch + (size_t)kRowsWarps * kRowsStages * 8;
+  auto kern = physics_metrics_rows_kernel<BWD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PIGAN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const int64_t groups = ceil_div64(n, 32);
+  const int64_t blocks_needed = ceil_div64(groups, kRowsWarps);
+  const int grid = (int)(blocks_needed < sm_count() ? blocks_needed : sm_count());
+  note_launch();
+  kern<<<grid, kRowsWarps * 32, smem, st>>>(spectra, (long long)n, s, freq, peak_idx, baseline, out_idx, out_metrics,
+                                            grad_metrics, grad_spectra);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+}  // namespace
 
 extern "C" int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s, const double* frequency,
                                      const int32_t* peak_idx, float baseline_transmission,
@@ -283,6 +479,19 @@ extern "C" int pigan_physics_metrics(const float* spectra, int64_t n, int32_t s,
   if (sm_count() <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   const int vpl = (s + 31) / 32;
+  if (phys_bulk_ok(spectra, s)) {
+    // rows of up to 256 samples: the lane-per-row kernel on the leading multiple of 4 rows (its bulk copies move
+    // multiples of 16 bytes), the warp-per-row kernel on the last 1-3
+    const int64_t nb = n - n % 4;
+    if (nb > 0) PIGAN_TRY((launch_phys_bulk<false>(spectra, nb, s, frequency, peak_idx, baseline_transmission, out_idx,
+                                                   out_metrics, nullptr, nullptr, st)));
+    if (nb == n) return PIGAN_OK;
+    spectra += nb * s;
+    if (peak_idx) peak_idx += nb;
+    if (out_idx) out_idx += nb;
+    out_metrics += nb * 4;
+    n -= nb;
+  }
 #define PIGAN_LAUNCH_PHYS(V)                                                                        \
   note_launch(), physics_metrics_kernel<V, false><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx, \
                                                   baseline_transmission, out_idx, out_metrics, nullptr, nullptr)
@@ -310,6 +519,19 @@ extern "C" int pigan_physics_metrics_backward(const float* spectra, int64_t n, i
   const int64_t cap = (int64_t)sm_count() * 8;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   const int vpl = (s + 31) / 32;
+  if (phys_bulk_ok(spectra, s) && (reinterpret_cast<uintptr_t>(grad_spectra) & 15u) == 0) {
+    const int64_t nb = n - n % 4;
+    if (nb > 0) PIGAN_TRY((launch_phys_bulk<true>(spectra, nb, s, frequency, peak_idx, baseline_transmission, out_idx,
+                                                  out_metrics, grad_metrics, grad_spectra, st)));
+    if (nb == n) return PIGAN_OK;
+    spectra += nb * s;
+    if (peak_idx) peak_idx += nb;
+    if (out_idx) out_idx += nb;
+    if (out_metrics) out_metrics += nb * 4;
+    grad_metrics += nb * 4;
+    grad_spectra += nb * s;
+    n -= nb;
+  }
 #define PIGAN_LAUNCH_PHYS_BWD(V)                                                                                       \
   note_launch(), physics_metrics_kernel<V, true><<<grid, 256, 0, st>>>(spectra, (long long)n, s, frequency, peak_idx,  \
                                                   baseline_transmission, out_idx, out_metrics, grad_metrics,         \
