@@ -17,6 +17,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpigan_b200.so")
+TEST_LIB = os.path.join(LIBDIR, "libpigan_b200_test.so")   # GEMM test hooks (include/pigan_b200_debug.h): tests/ and tools/ only
+TEST_ONLY = {"debug_gemm.cu"}                              # sources that stay out of the product library
+TEST_SHARED = {"host_util.cu"}                             # ... and what the test library needs besides them
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -75,12 +78,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             futs = [ex.submit(_compile, s, o, verbose) for s, o in jobs]
             for f in futs:
                 f.result()
-    need_link = bool(jobs) or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
-    if need_link:
-        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    def obj_of(name):
+        return os.path.join(OBJ, name[:-3] + ".o")
+    for lib, members in ((LIB, [obj_of(x) for x in srcs if x not in TEST_ONLY]),
+                         (TEST_LIB, [obj_of(x) for x in srcs if x in TEST_ONLY or x in TEST_SHARED])):
+        need_link = bool(jobs) or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in members)
+        if need_link:
+            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *members]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB
 
 

@@ -1,6 +1,7 @@
 // Test hooks: run the tcgen05 GEMM core with a trivial fp32 epilogue (every tile configuration the
 // layers use) and with the production store / weight-gradient epilogues, so tests/ can compare them with a
 // plain fp32 matmul of the same fp16 operands.
+#include "../../include/pigan_b200_debug.h"
 #include "epilogues.cuh"
 #include "gemm2_tc.cuh"
 

@@ -277,7 +277,7 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
 }
 
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
-long long* g_ln_trace = nullptr;  // debug: pigan_debug_set_ln_trace
+long long* g_ln_trace = nullptr;  // pigan_engine_trace_layernorm
 // bias / gamma / beta: device pointers (the layer's fp32 parameters); the epilogue stages its columns in shared memory
 template <int CLUSTER, bool PAIR = false, class Cfg = CfgL1>
 int linear_ln_c(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g, int64_t rows, int k, int n,
@@ -1430,7 +1430,7 @@ extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, cons
   return PIGAN_OK;
 }
 
-extern "C" int pigan_debug_set_ln_trace(void* device_buffer) {
+extern "C" int pigan_engine_trace_layernorm(void* device_buffer) {
   pigan::g_ln_trace = static_cast<long long*>(device_buffer);
   return PIGAN_OK;
 }

@@ -135,13 +135,8 @@ SIGNATURES = {
     "pigan_topk_workspace_bytes": (C.c_size_t, [_i64, _i32]),
     "pigan_topk_smallest": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "pigan_physics_metrics": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "pigan_engine_trace_layernorm": (_i32, [_vp]),
     "pigan_physics_metrics_backward": (_i32, [_vp, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
-    "pigan_debug_set_ln_trace": (_i32, [_vp]),
-    "pigan_debug_force_streamed": (_i32, [_i32]),
-    "pigan_debug_gemm_tn": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "pigan_debug_linear": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "pigan_debug_linear2": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "pigan_debug_gemm_nt": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 
 

@@ -7,8 +7,8 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "pigan_b200.h")).read()
+def _declared_symbols(header="pigan_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(pigan_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,9 +25,23 @@ def test_header_symbols_are_exported_and_bound():
         assert s in syms, f"{s} bound in native.py but not declared in the header"
 
 
+def test_test_hooks_live_in_their_own_library():
+    """include/pigan_b200_debug.h is bound by native_test.py against libpigan_b200_test.so; the product library
+    exports none of the pigan_debug_* symbols."""
+    from pigan_b200 import native, native_test
+    syms = [s for s in _declared_symbols("pigan_b200_debug.h") if s.startswith("pigan_debug_")]
+    assert len(syms) >= 4
+    product = ctypes.CDLL(native.LIB_PATH)
+    hooks = ctypes.CDLL(native_test.LIB_PATH)
+    for s in syms:
+        assert hasattr(hooks, s) and s in native_test.SIGNATURES, s
+        assert not hasattr(product, s), f"{s} leaked into the product library"
+    assert not any(s.startswith("pigan_debug_") for s in _declared_symbols())
+
+
 def test_version_and_layout_counts():
     from pigan_b200 import native
-    assert native.lib.pigan_abi_version() == 7
+    assert native.lib.pigan_abi_version() == 8
     d = native.default_dims()
     assert (d.spectrum_dim, d.param_dim, d.metrics_dim) == (250, 4, 8)
     # parameter counts of the reference modules (SURVEY Appendix B)

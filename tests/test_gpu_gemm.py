@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _native():
-    from pigan_b200 import native
+    from pigan_b200 import native_test as native
     return native
 
 

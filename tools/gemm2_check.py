@@ -3,7 +3,7 @@ import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "pi-gan-thz_b200"))
 import torch
-from pigan_b200 import native
+from pigan_b200 import native_test as native
 _out = {}
 def run(fn, a, b, bias, m, n, k, leaky, fresh=False):
     if fresh or (m, n) not in _out:

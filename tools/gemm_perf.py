@@ -2,7 +2,7 @@
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pigan_b200 import native
+from pigan_b200 import native_test as native
 
 def timeit(fn, iters=20, warm=3):
     for _ in range(warm): fn()

@@ -12,9 +12,9 @@ p = torch.rand(B, 4, device="cuda") * 2 - 1
 with torch.no_grad():
     F(p); torch.cuda.synchronize()
     tr = torch.zeros(4, 64, 5, dtype=torch.int64, device="cuda")
-    native.lib.pigan_debug_set_ln_trace(tr.data_ptr())
+    native.lib.pigan_engine_trace_layernorm(tr.data_ptr())
     F(p); torch.cuda.synchronize()
-    native.lib.pigan_debug_set_ln_trace(None)
+    native.lib.pigan_engine_trace_layernorm(None)
     li = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     t = tr[li].cpu()
     t0 = int(t[:, 0][t[:, 0] > 0].min())

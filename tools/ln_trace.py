@@ -14,10 +14,10 @@ with torch.no_grad():
     torch.cuda.synchronize()
     import ctypes
     tr = torch.zeros(4, 64, 5, dtype=torch.int64, device="cuda")
-    native.lib.pigan_debug_set_ln_trace(tr.data_ptr())
+    native.lib.pigan_engine_trace_layernorm(tr.data_ptr())
     F(p)
     torch.cuda.synchronize()
-    native.lib.pigan_debug_set_ln_trace(None)
+    native.lib.pigan_engine_trace_layernorm(None)
     for li, name in enumerate(["L2 256->512", "L3 512->1024 (cluster 2)", "L4 1024->512", "L5 512->256"]):
         t = tr[li].cpu()[0::2]        # group 0's units (group 1's are the odd rows)
         k = int((t[:, 0] > 0).sum())

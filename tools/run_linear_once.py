@@ -1,7 +1,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pigan_b200 import native
+from pigan_b200 import native_test as native
 M, n, k = 65536, 512, 256
 a = torch.randn(M, k, device="cuda").half(); b = torch.randn(n, k, device="cuda").half()
 bias = torch.randn(n, device="cuda"); out = torch.empty(M, n, device="cuda", dtype=torch.float16)
