@@ -327,6 +327,31 @@ def run_native(args):
             tr.step(*sets[i % NSETS], lr, lr)
         barrier()
 
+    # ---- the same step with the physics-metric loss term switched on (lambda = 0 is the reference):
+    # F forward with the fp32 dump, physics metrics forward + backward, surrogate VJP, then the fused phases
+    pm_info = None
+    if world == 1 and not args.no_quant_probe:
+        torch.manual_seed(42)
+        Gp, Dp, Fp = Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)
+        Fp.eval()
+        trp = NativeTrainer(Gp, Dp, Fp, dev, max_batch=B, lambda_physics_metric=1.0)
+        for i in range(3):
+            trp.step(*sets[i % NSETS], lr, lr)
+        barrier()
+        e0.record()
+        for i in range(max(3, K // 2)):
+            trp.step(*sets[i % NSETS], lr, lr)
+        e1.record()
+        barrier()
+        mspm = e0.elapsed_time(e1) / max(3, K // 2)
+        pm_info = {"ms_per_step": mspm, "extra_ms": mspm - ms / K, "value": B / (mspm * 1e-3), "unit": "samples/s",
+                   "physics_metric_loss": float(trp.last_physics_metric_loss),
+                   "what": "NativeTrainer(lambda_physics_metric=1): + F forward (fp32 dump), peak metrics fwd/bwd of "
+                           "reconstruction and target, surrogate VJP (pigan_forward_model_vjp), one stream"}
+        del trp, Gp, Dp, Fp
+        torch.cuda.empty_cache()
+        tr.engine.load_forward_model(tr.fs.params.tensor())
+
     # ---- timed region 2: end to end from pinned HOST buffers through the public API.  Two variants:
     #   e2e      NativeTrainer.step_prepared: the dataset keeps the fp16 first-layer operand that
     #            NativeTrainer.prepare_operand built once (the analogue of the reference's one-time dataset
@@ -680,6 +705,7 @@ def run_native(args):
             "evaluator_reductions": eval_info,
             "data_pipeline": pipe_info,
             "wave_quantisation_probe": quant,
+            "physics_metric_term": pm_info,
             "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]},
         }
         print(json.dumps(out), flush=True)

@@ -179,10 +179,20 @@ typedef struct PiganTrainArgs {
    * The batch must then be a multiple of 128 rows (PIGAN_ERR_INVALID otherwise). */
   const void* spectrum_operand;
   const float* spectrum_center;
+  /* optional extra gradient into the generator output (the physics-metric loss): dp_extra [B,P] =
+   * d(extra loss)/d(params_norm) of a loss that is a MEAN over the global batch, already multiplied by its weight;
+   * read by phase 3 (the generator-head backward), so it may be computed between phases 2 and 3 from
+   * pigan_engine_generator_output.  NULL (the default, = the reference's loss) adds nothing. */
+  const float* dp_extra;
+  /* bit 0: keep every kernel of the step on the caller's stream (no second stream for the surrogate chain), so the
+   * caller may use the engine (pigan_forward_model_forward, pigan_forward_model_vjp) between the phases */
+  int32_t flags;
 } PiganTrainArgs;
 
 int pigan_train_step(PiganEngine* engine, const PiganTrainArgs* args, void* stream);
 int pigan_train_step_phase(PiganEngine* engine, const PiganTrainArgs* args, int32_t phase, void* stream);
+/* [B,P] generator output params_norm of the current step (valid after phase 2) */
+float* pigan_engine_generator_output(PiganEngine* engine);
 /* Device buffers the host all-reduces between phases (fp32 unless noted); valid for the engine's lifetime. */
 float* pigan_engine_bn_sums(PiganEngine* engine);      /* [2*h1 + 2*h2]  sum, sumsq per BatchNorm */
 float* pigan_engine_bn_bwd_sums(PiganEngine* engine);  /* [2*h2 + 2*h1]  sum dy, sum dy*xhat */
@@ -294,6 +304,13 @@ typedef struct PiganFwdTrainArgs {
   uint8_t* mask_dump;
 } PiganFwdTrainArgs;
 size_t pigan_fwd_train_workspace_bytes(const PiganEngine* engine);
+/* Vector-Jacobian product of the surrogate with frozen weights (eval mode): out_dp [n,P] = J^T grad_out for
+ * grad_out [n, S+Mt] = dL/d(F(params_norm)) (spectrum columns first, then metrics), the general form of
+ * pigan_forward_model_input_grad (UnifiedTrainer semantics, core/train/unified_trainer.py:240-256,325: a loss on
+ * F(G(x)) that reaches G through F).  Same workspace and engine-state caveats as pigan_fwd_train_step. */
+int pigan_forward_model_vjp(PiganEngine* engine, const float* f_params, const float* params_norm,
+                            const float* grad_out, int64_t n, float* out_dp, void* workspace, size_t workspace_bytes,
+                            void* stream);
 /* Gradient of the surrogate's regression loss with respect to its INPUT, weights frozen (the
  * physics-loss gradient of UnifiedTrainer.train_pigan_step, /root/reference/core/train/unified_trainer.py:240-256,
  * 325).  F runs in eval mode (Dropout = identity) on params_norm [n, param_dim];

@@ -753,9 +753,11 @@ __global__ void __launch_bounds__(kThreads) g_head_dpre_kernel(GHeadBwdArgs a) {
     const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.p) + r);
     const float4 d4 = a.dpden ? __ldg(reinterpret_cast<const float4*>(a.dpden) + r) : z4;
     const float4 l4 = a.dp_lc ? __ldg(reinterpret_cast<const float4*>(a.dp_lc) + r) : z4;
+    const float4 e4 = a.dp_extra ? __ldg(reinterpret_cast<const float4*>(a.dp_extra) + r) : z4;
     const float p[4] = {p4.x, p4.y, p4.z, p4.w};
     const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+    // the caller's extra term is a true gradient; the others carry the gradient scale GS
+    const float ll[4] = {fmaf(e4.x, a.gs, l4.x), fmaf(e4.y, a.gs, l4.y), fmaf(e4.z, a.gs, l4.z), fmaf(e4.w, a.gs, l4.w)};
     float dpre[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1357,6 +1359,19 @@ __global__ void score_finish_kernel(const float* __restrict__ p, const float* __
   if (cons) cons[r] = 1.0f / (1.0f + err[r]);
 }
 
+
+// dout[r, 0:ld] = fp16(scale * g[r, 0:cols]) (zero beyond cols): an upstream gradient as the surrogate's backward
+// operand (pigan_forward_model_vjp); scale = the gradient scale GS the backward chain carries
+__global__ void f_upstream_cast_kernel(const float* __restrict__ g, int cols, __half* __restrict__ dout, int ld,
+                                       long long rows, float scale) {
+  pdl_wait();
+  const long long total = rows * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld;
+    const int c = (int)(i - r * ld);
+    dout[i] = __float2half_rn(c < cols ? scale * g[r * cols + c] : 0.f);
+  }
+}
 
 // Model-validation scores (unified_evaluator.py:453-468): stability[r] = mean_j (p[r,j] - p_noisy[r,j])^2,
 // plausibility[r] = mean_j sigmoid(10 p[r,j] - 5)
@@ -2009,6 +2024,9 @@ void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const flo
   launch_k(dw_fixup_kernel, (total + 255) / 256, 256, 0, st, dw, ld, S, P, db, cvec, rows);
 }
 void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st) { launch_k(loss_finalize_kernel, 1, 32, 0, st, a); }
+void launch_f_upstream_cast(const float* g, int cols, __half* dout, int ld, int64_t rows, float scale, cudaStream_t st) {
+  launch_k(f_upstream_cast_kernel, 148 * 8, 256, 0, st, g, cols, dout, ld, (long long)rows, scale);
+}
 void launch_validation_scores(const float* p, const float* p_noisy, int64_t rows, int P, float* stability,
                               float* plausibility, cudaStream_t st) {
   launch_k(validation_scores_kernel, (int)((rows + 255) / 256), 256, 0, st, p, p_noisy, (long long)rows, P, stability,

@@ -111,6 +111,8 @@ struct GHeadBwdArgs {
   const float* p;         // [B,4] tanh output
   const float* dpden;     // [B,4] dL/dPden * GS (may be null)
   const float* dp_lc;     // [B,4] lambda_lc * dLC/dp * GS (may be null)
+  const float* dp_extra;  // [B,4] caller's extra d(loss)/dp, unscaled (may be null)
+  float gs;               // gradient scale GS (= global batch)
   float range_mult;       // lambda_range * GS / (4 * global batch)
   const __half* h2;       // [B,C]
   const float* scale;     // BN2 affine
@@ -222,6 +224,8 @@ void launch_loss_finalize(const LossFinalizeArgs& a, cudaStream_t st);
 // violations[r] = #{j : p[r,j] < 0 or p[r,j] > 1}; consistency[r] = 1 / (1 + err[r])  (unified_evaluator.py:380,391)
 void launch_score_finish(const float* p, const float* err, int64_t rows, int P, int32_t* violations,
                          float* consistency, cudaStream_t st);
+// dout [rows, ld] fp16 = scale * g [rows, cols] (zero padded)
+void launch_f_upstream_cast(const float* g, int cols, __half* dout, int ld, int64_t rows, float scale, cudaStream_t st);
 // stability[r] = mean_j (p - p_noisy)^2, plausibility[r] = mean_j sigmoid(10 p - 5)   (unified_evaluator.py:458-468)
 void launch_validation_scores(const float* p, const float* p_noisy, int64_t rows, int P, float* stability,
                               float* plausibility, cudaStream_t st);

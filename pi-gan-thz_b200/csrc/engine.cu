@@ -608,6 +608,7 @@ GHeadBwdArgs head_bwd_args(PiganEngine* e, const PiganTrainArgs& a) {
   float* gp = a.g_params;
   GHeadBwdArgs hb;
   hb.p = e->p; hb.dpden = e->dpden; hb.dp_lc = e->dp_lc;
+  hb.dp_extra = a.dp_extra; hb.gs = (float)a.global_batch;
   hb.range_mult = a.lambda_param_range / (float)G.P;
   hb.h2 = e->g_h2; hb.scale = e->scale2; hb.bias = e->bias2; hb.mean = e->mean2; hb.rstd = e->rstd2;
   hb.w3 = gp + G.w3; hb.dy2 = e->g_dy2; hb.dw3 = a.g_grads + G.w3; hb.db3 = a.g_grads + G.b3;
@@ -634,7 +635,7 @@ int g_step_surrogate(PiganEngine* e, const PiganTrainArgs& a, cudaStream_t st) {
 // phase 2, once e->p exists: start the surrogate chain on the side stream
 int fork_surrogate(PiganEngine* e, const PiganTrainArgs& a, cudaStream_t st) {
   e->side_pending = false;
-  if (!overlap_enabled() || e->prof.on) return PIGAN_OK;   // profiling keeps one stream so sections stay meaningful
+  if (!overlap_enabled() || e->prof.on || (a.flags & 1)) return PIGAN_OK;   // profiling keeps one stream so sections stay meaningful
   if (e->side == nullptr) {
     int lo = 0, hi = 0;
     PIGAN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1041,6 +1042,7 @@ extern "C" int pigan_engine_profile_end(PiganEngine* e, char* report, size_t rep
   return PIGAN_OK;
 }
 
+extern "C" float* pigan_engine_generator_output(PiganEngine* e) { return e ? e->p : nullptr; }
 extern "C" float* pigan_engine_bn_sums(PiganEngine* e) { return e ? e->bn_sums : nullptr; }
 extern "C" float* pigan_engine_bn_bwd_sums(PiganEngine* e) { return e ? e->bn_bwd_sums : nullptr; }
 extern "C" double* pigan_engine_loss_sums(PiganEngine* e) { return e ? e->sums : nullptr; }
@@ -1163,6 +1165,7 @@ struct FwdRunOpts {
   bool input_grad = false;
   float w_spec = 1.f, w_met = 1.f;
   float* dp_out = nullptr;
+  const float* upstream = nullptr;   // input_grad: dL/d(output) [n, S+Mt] instead of the two MSE terms
 };
 int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrainWs& w, cudaStream_t st,
                     const FwdRunOpts& opt = FwdRunOpts()) {
@@ -1237,8 +1240,11 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, w.out32, nullptr, 0, 1};
   PIGAN_TRY(f_out_layer(e, act[4], n, fo, st));
   PM("f_out_loss");
-  launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
-                    loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
+  if (opt.upstream != nullptr)
+    launch_f_upstream_cast(opt.upstream, L.OUT, w.dout, kDoutLd, n, (float)a.global_batch, st);
+  else
+    launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
+                      loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
   // ---- backward
   PM("f_wgrad_gemm");
   if (!opt.input_grad)
@@ -1317,6 +1323,33 @@ extern "C" int pigan_forward_model_input_grad(PiganEngine* e, const float* f_par
   PIGAN_TRY(fwd_train_phase(e, a, 0, w, st, opt));
   // out_losses[0..1] = unweighted MSE(spectrum), MSE(metrics) of this batch
   launch_f_input_grad_losses(w.loss_sums, (double)n * e->fl.S, (double)n * e->fl.Mt, out_losses, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+extern "C" int pigan_forward_model_vjp(PiganEngine* e, const float* f_params, const float* params_norm,
+                                       const float* grad_out, int64_t n, float* out_dp, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  PIGAN_CHECK_ARG(e && f_params && params_norm && grad_out && out_dp && workspace);
+  PIGAN_CHECK_ARG(n >= 1 && n <= e->max_batch && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dp) & 15u) == 0);
+  FTrainWs w;
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  if (workspace_bytes < need)
+    return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", workspace_bytes, need);
+  w.carve(workspace, e->fl, e->max_batch);
+  PiganFwdTrainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params_norm = params_norm;
+  a.batch = a.global_batch = n;
+  a.f_params = const_cast<float*>(f_params);   // read only on this path
+  a.step = 1;
+  a.dropout_p = 0.f;                           // eval mode: Dropout is the identity
+  FwdRunOpts opt;
+  opt.input_grad = true;
+  opt.dp_out = out_dp;
+  opt.upstream = grad_out;
+  PIGAN_TRY(fwd_train_phase(e, a, 0, w, static_cast<cudaStream_t>(stream), opt));
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

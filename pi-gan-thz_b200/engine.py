@@ -112,6 +112,28 @@ class Engine:
                                                  self._ftrain_ws.numel(), native.current_stream()))
         return dp, losses
 
+    def forward_model_vjp(self, f_flat, params_norm, grad_out) -> torch.Tensor:
+        """dL/d params_norm [n,4] from dL/d F(params_norm) [n, S+Mt] (spectrum columns, then metrics), weights frozen,
+        Dropout off - how a loss on F(G(x)) reaches the generator (unified_trainer.py:240-256, 325)."""
+        _require_cuda(params_norm, "params_norm")
+        p, g = _f32c(params_norm), _f32c(grad_out)
+        n = p.shape[0]
+        if g.shape != (n, self.dims.spectrum_dim + self.dims.metrics_dim):
+            raise ValueError("grad_out must be [n, spectrum_dim + metrics_dim]")
+        if getattr(self, "_ftrain_ws", None) is None:
+            self._ftrain_ws = torch.empty(lib.pigan_fwd_train_workspace_bytes(self.handle), dtype=torch.uint8,
+                                          device=self.device)
+        dp = torch.empty(n, self.dims.param_dim, device=p.device, dtype=torch.float32)
+        check(lib.pigan_forward_model_vjp(self.handle, f_flat.data_ptr(), p.data_ptr(), g.data_ptr(), n, dp.data_ptr(),
+                                          self._ftrain_ws.data_ptr(), self._ftrain_ws.numel(),
+                                          native.current_stream()))
+        return dp
+
+    def generator_output(self, n: int) -> torch.Tensor:
+        """[n, P] view of the generator output params_norm of the current train step (valid after phase 2)."""
+        return self._wrap(lib.pigan_engine_generator_output(self.handle), n * self.dims.param_dim,
+                          torch.float32).view(n, self.dims.param_dim)
+
     # ------------------------------------------------------------------ training
     def make_train_args(self, **kw) -> PiganTrainArgs:
         a = PiganTrainArgs()

@@ -76,6 +76,7 @@ class PiganTrainArgs(C.Structure):
         ("f1_idx", _i32), ("f2_idx", _i32),
         ("losses", _vp),
         ("spectrum_operand", _vp), ("spectrum_center", _vp),
+        ("dp_extra", _vp), ("flags", _i32),
     ]
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "pigan_forward_model_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "pigan_train_step": (_i32, [_vp, C.POINTER(PiganTrainArgs), _vp]),
     "pigan_train_step_phase": (_i32, [_vp, C.POINTER(PiganTrainArgs), _i32, _vp]),
+    "pigan_engine_generator_output": (_vp, [_vp]),
     "pigan_engine_bn_sums": (_vp, [_vp]),
     "pigan_engine_bn_bwd_sums": (_vp, [_vp]),
     "pigan_engine_loss_sums": (_vp, [_vp]),
@@ -123,6 +125,7 @@ SIGNATURES = {
                                            _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_workspace_bytes": (C.c_size_t, [_vp]),
     "pigan_forward_model_input_grad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "pigan_forward_model_vjp": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_step": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _vp, C.c_size_t, _vp]),
     "pigan_fwd_train_step_phase": (_i32, [_vp, C.POINTER(PiganFwdTrainArgs), _i32, _vp, C.c_size_t, _vp]),
     "pigan_eval_workspace_bytes": (C.c_size_t, [_i32]),

@@ -65,7 +65,8 @@ def run_dp_step(run_phase, get_buffer, all_reduce, plan) -> None:
 
 class NativeTrainer:
     def __init__(self, generator, discriminator, forward_model, device, max_batch: int, cfg=None,
-                 f1_idx: int = 0, f2_idx: int = 1, process_group=None):
+                 f1_idx: int = 0, f2_idx: int = 1, process_group=None, lambda_physics_metric: float = 0.0,
+                 physics_metric_weights=(1.0, 1e-2, 1.0, 1e-2)):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("NativeTrainer needs a CUDA device — the B200 path has no CPU fallback")
@@ -94,6 +95,13 @@ class NativeTrainer:
                        lambda_bnn_kl=cfg.LAMBDA_BNN_KL)
         self.lam = lam
         self.f1_idx, self.f2_idx = int(f1_idx), int(f2_idx)
+        # SURVEY 8(f) N2 (the reference has no such term, default 0 = the reference's loss): a physics-metric loss
+        #   L_pm = mean_rows sum_k w_k (m_k(F(G(x)).spectrum) - m_k(x))^2,  m = (f_res, Q, FoM, S) at the row's minimum,
+        # over rows where both sides have a defined Q; it reaches the generator through the metrics' own backward
+        # (pigan_physics_metrics_backward) and the frozen surrogate's vector-Jacobian product (pigan_forward_model_vjp)
+        self.lambda_physics_metric = float(lambda_physics_metric)
+        self.physics_metric_weights = tuple(float(x) for x in physics_metric_weights)
+        self.last_physics_metric_loss = None
         # data parallel: gradients are produced straight into an NVLink-mapped exchange region and summed by the
         # library's one-shot kernels (dp.py); NCCL all-reduce is the fallback when peers cannot be mapped
         self.xchg = _dp.DpExchange.create(max(gp.numel(), dp.numel()), self.device, process_group) \
@@ -161,8 +169,20 @@ class NativeTrainer:
             self._dp_batch = check_equal_batch(metrics_norm.shape[0], getattr(self, "_dp_batch", None), self.pg)
         self.step_count += 1
         args = self._args(spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand, center)
+        self._pm_spectrum = spectrum
+        if self.lambda_physics_metric > 0.0:
+            if spectrum is None:
+                raise RuntimeError("the physics-metric term needs the fp32 spectra (step(), not step_prepared())")
+            args.flags = 1          # one stream: the engine is used between the phases
         if self.world == 1:
-            self.engine.train_step(args)
+            if self.lambda_physics_metric > 0.0:
+                for ph in range(7):
+                    if ph == 3:
+                        self._physics_metric_term(args)
+                    self.engine.train_step_phase(args, ph)
+                self._add_physics_metric_loss()
+            else:
+                self.engine.train_step(args)
             return self.losses
         if operand is None and self._center is None:
             # one centring row on all ranks (the exchanged BatchNorm sums are sums of centred pre-activations)
@@ -175,11 +195,52 @@ class NativeTrainer:
         e = self.engine
         if self.xchg is not None:
             self._step_peer(args)
+            self._add_physics_metric_loss()
             return self.losses
-        run_dp_step(lambda ph: e.train_step_phase(args, ph), self._buffer,
-                    lambda t: dist.all_reduce(t, group=self.pg),
+
+        def run_phase(ph):
+            if ph == 3 and self.lambda_physics_metric > 0.0:
+                self._physics_metric_term(args)
+            e.train_step_phase(args, ph)
+
+        run_dp_step(run_phase, self._buffer, lambda t: dist.all_reduce(t, group=self.pg),
                     dp_phase_plan(e.dims.g_hidden[0], e.dims.g_hidden[1]))
+        self._add_physics_metric_loss()
         return self.losses
+
+    # ------------------------------------------------------------------ physics-metric term
+    def _physics_metric_term(self, args) -> None:
+        """Between phases 2 and 3: dp_extra = lambda * dL_pm/d(params_norm) for this rank's rows."""
+        from . import physics as _physics
+        e = self.engine
+        x = self._pm_spectrum
+        n = x.shape[0]
+        S = e.dims.spectrum_dim
+        p = e.generator_output(n)
+        out = e.forward_model_forward(p)                                  # [n, S + Mt] fp32
+        rec = out[:, :S].contiguous().requires_grad_(True)
+        m_rec = _physics.differentiable_peak_metrics(rec)                 # [n, 4] with a backward into rec
+        tgt = _physics.peak_metrics(x)
+        m_tgt = torch.stack([tgt["f_res"], tgt["Q"], tgt["FoM"], tgt["S"]], dim=1)
+        ok = torch.isfinite(m_rec.detach()).all(dim=1) & torch.isfinite(m_tgt).all(dim=1)
+        w = torch.tensor(self.physics_metric_weights, device=x.device, dtype=torch.float32)
+        diff = torch.where(ok[:, None], m_rec - m_tgt, torch.zeros_like(m_rec))
+        loss = (w * diff * diff).sum() / float(n * self.world)            # mean over the GLOBAL batch
+        loss.backward()
+        g_out = torch.zeros_like(out)
+        g_out[:, :S] = rec.grad
+        dp = e.forward_model_vjp(self.fs.params.tensor(), p, g_out)
+        self._pm_dp = (self.lambda_physics_metric * dp).contiguous()       # kept alive until the step has consumed it
+        self._pm_loss = loss.detach()
+        args.dp_extra = self._pm_dp.data_ptr()
+
+    def _add_physics_metric_loss(self) -> None:
+        if self.lambda_physics_metric > 0.0:
+            pm = self._pm_loss.clone()
+            if self.world > 1:
+                dist.all_reduce(pm, group=self.pg)
+            self.last_physics_metric_loss = pm
+            self.losses[1] += self.lambda_physics_metric * pm              # g_losses: the generator's total
 
     def _step_peer(self, args) -> None:
         """The data-parallel schedule (dp_phase_plan) with peer-memory all-reduces: this step's gradients accumulate
@@ -192,6 +253,8 @@ class NativeTrainer:
         for phase, reductions in dp_phase_plan(e.dims.g_hidden[0], e.dims.g_hidden[1]):
             if phase == 3:
                 args.d_grads = self.d_grads.data_ptr()     # Adam(D) reads the reduced gradients
+                if self.lambda_physics_metric > 0.0:
+                    self._physics_metric_term(args)
             if phase == 6:
                 args.g_grads = self.g_grads.data_ptr()
             e.train_step_phase(args, phase)
