@@ -13,6 +13,27 @@ import torch.nn as nn
 from ._native import _pkg, check_input
 
 
+class _SurrogateFn(torch.autograd.Function):
+    """F(params_norm) with a backward pass into the INPUT (weights frozen): the vector-Jacobian product of the engine
+    (pigan_forward_model_vjp).  This is how the reference's variant trainers use the surrogate - a loss on F(G(x))
+    whose gradient reaches the generator through F (core/train/unified_trainer.py:240-256, 325)."""
+
+    @staticmethod
+    def forward(ctx, params_norm, engine, flat_params):
+        engine.load_forward_model(flat_params)
+        out = engine.forward_model_forward(params_norm)
+        ctx.engine, ctx.flat = engine, flat_params
+        ctx.save_for_backward(params_norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (p,) = ctx.saved_tensors
+        dp = ctx.engine.forward_model_vjp(ctx.flat, p, grad_out.contiguous())
+        ctx.engine.load_forward_model(ctx.flat)     # the VJP re-packs the weights: keep the frozen surrogate loaded
+        return dp, None, None
+
+
 class ForwardModel(nn.Module):
     def __init__(self, input_param_dim: int, output_spectrum_dim: int, output_metrics_dim: int):
         super().__init__()
@@ -28,6 +49,10 @@ class ForwardModel(nn.Module):
         self.model = nn.Sequential(*layers)
 
     def forward(self, structural_params_norm: torch.Tensor):
+        # under autograd the surrogate is differentiable with respect to its INPUT; its own parameters get no
+        # gradient here (they are frozen wherever the reference back-propagates through F) - training F itself is
+        # core.train.pretrain_fwd_model / pigan_fwd_train_step
+        self._pigan_autograd_error = False
         check_input(self, structural_params_norm, "structural_params_norm")
         if self.training:
             raise NotImplementedError("ForwardModel.forward in train() mode (active Dropout) is not on the native "
@@ -35,6 +60,9 @@ class ForwardModel(nn.Module):
         eng, flat = _pkg()
         st = flat.net_state(self, "forward_model")
         engine = eng.get_engine(structural_params_norm.device, structural_params_norm.shape[0])
-        engine.load_forward_model(st.params.tensor())
-        out = engine.forward_model_forward(structural_params_norm)
+        if torch.is_grad_enabled() and structural_params_norm.requires_grad:
+            out = _SurrogateFn.apply(structural_params_norm.float().contiguous(), engine, st.params.tensor())
+        else:
+            engine.load_forward_model(st.params.tensor())
+            out = engine.forward_model_forward(structural_params_norm)
         return out[:, :self.output_spectrum_dim], out[:, self.output_spectrum_dim:]

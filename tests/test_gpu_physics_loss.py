@@ -124,3 +124,26 @@ def test_physics_metric_term_reaches_the_generator():
         ref = g[name].grad
         assert float(ref.norm()) > 0
         assert rel(d, ref) < 3e-2, (name, rel(d, ref))
+
+
+def test_forward_model_module_is_differentiable_in_its_input():
+    """The drop-in ForwardModel under autograd: a reconstruction loss on F(p) back-propagates into p through the engine's
+    VJP, as the reference's UnifiedTrainer does (unified_trainer.py:240-256, 325); the module's weights get no gradient."""
+    from core.models.forward_model import ForwardModel
+    from oracle import fixtures
+    from oracle import models as O
+    _, _, f_sd = fixtures.make_weights(42)
+    F = ForwardModel(4, 250, 8)
+    F.load_state_dict(f_sd)
+    F = F.to(DEV).eval()
+    n = 512
+    spec, praw, pnorm, mnorm = fixtures.make_batch(n, seed=8)
+    p = pnorm.to(DEV).requires_grad_(True)
+    s, m = F(p)
+    loss = ((s - spec.to(DEV)) ** 2).mean() + 0.5 * ((m - mnorm.to(DEV)) ** 2).mean()
+    loss.backward()
+    assert all(q.grad is None for q in F.parameters())
+    pr = pnorm.clone().requires_grad_(True)
+    sr, mr = O.forward_model_forward(f_sd, pr)
+    (((sr - spec) ** 2).mean() + 0.5 * ((mr - mnorm) ** 2).mean()).backward()
+    assert rel(p.grad, pr.grad) < 5e-2, rel(p.grad, pr.grad)
