@@ -26,6 +26,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    # function-local statics of templates (launch_gemm's "attribute set" flags) must stay per library: as GNU-unique
+    # symbols they would be shared process-wide between the product and the test library, which both instantiate
+    # some of the same kernels - one library's flag would then skip the other's cudaFuncSetAttribute
+    "-Xcompiler", "-fno-gnu-unique",
     "--expt-relaxed-constexpr",
     "-I", INCLUDE,
 ]
@@ -84,7 +88,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
                          (TEST_LIB, [obj_of(x) for x in srcs if x in TEST_ONLY or x in TEST_SHARED])):
         need_link = bool(jobs) or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in members)
         if need_link:
-            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *members]
+            # -Bsymbolic: both libraries instantiate some of the same kernel templates; each must bind (and register
+            # with the CUDA runtime) its OWN host stubs, not whichever copy the dynamic loader saw first
+            cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xlinker", "-Bsymbolic",
+                   "-o", lib, *members]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
