@@ -35,9 +35,10 @@ FLOP_PER_TRAIN_SAMPLE = 7_465_984
 FLOP_PER_CANDIDATE = 3_275_776
 FLOP_PER_PRETRAIN_SAMPLE = 2 * 4_132_352   # F fwd + bwd (dW + dX), MACs x 2
 METRIC = "PI-GAN train samples/s"
-# DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/, round 1): the four
-# Linear+LayerNorm launches of the forward surrogate read+write 46.9 + 147.4 + 171.5 + 72.7 MB
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 109.6e6   # refreshed from profiles/r02_gemm_kernels_ncu_full.csv by tools/ncu_summary.py
+# DRAM traffic of the dominant kernel per launch from the committed ncu capture (profiles/r02_gemm_kernels_ncu_full.csv,
+# round 2, the kernels as they are now): the four Linear+LayerNorm launches of the forward surrogate read+write
+# 50.8 + 150.7 + 174.6 + 74.7 MB (algorithmic fp16 activation bytes: 100.7 + 201.3 + 201.3 + 100.7 MB, mean 151 - L2 absorbs part of the writes)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 112.7e6
 
 
 def read_peaks():
@@ -286,7 +287,7 @@ def run_native(args):
         ach = dom_flop_per_launch / (dom_ms / dom_cnt * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiLnStore> (forward-surrogate hidden layers: Linear+LayerNorm+LeakyReLU)",
                 "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r01_gemm_kernels_ncu_full.csv "
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": "profiles/r02_gemm_kernels_ncu_full.csv "
                 "(ncu --set full, dram__bytes_read+write, mean of the 4 EpiLnStore launches)", "peak_source": peaks["source"] + " bf16 sustained",
                 "frac_of_burst_peak": ach / peaks["tflops_burst"], "peak_burst": peaks["tflops_burst"],
                 "timed_region_ms": ms, "note": "the timed region is tens of milliseconds at full clocks: between the "
