@@ -347,6 +347,9 @@ def run_native(args):
         mspm = e0.elapsed_time(e1) / max(3, K // 2)
         pm_info = {"ms_per_step": mspm, "extra_ms": mspm - ms / K, "value": B / (mspm * 1e-3), "unit": "samples/s",
                    "physics_metric_loss": float(trp.last_physics_metric_loss),
+                   "rows_with_defined_metrics": int(trp.last_physics_metric_rows),
+                   "note": "random-initialised surrogate: its reconstructions rarely have a half-depth crossing, so few "
+                           "or no rows contribute to the loss VALUE here; the cost of the term is the same either way",
                    "what": "NativeTrainer(lambda_physics_metric=1): + F forward (fp32 dump), peak metrics fwd/bwd of "
                            "reconstruction and target, surrogate VJP (pigan_forward_model_vjp), one stream"}
         del trp, Gp, Dp, Fp

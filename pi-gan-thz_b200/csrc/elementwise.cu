@@ -582,31 +582,67 @@ __global__ void __launch_bounds__(kThreads, 4) colstats_kernel(const __half* __r
   block_colsum_partial4(q, part + C, m, sm);
 }
 
+__device__ __forceinline__ void bn_finalize_column(const BnFinalizeArgs& a, int c, float sum, float sumsq) {
+  const double ms = (double)sum / a.n;
+  double var = (double)sumsq / a.n - ms * ms;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)ms;
+  const float mean_full = (float)(ms + (a.offset ? (double)a.offset[c] : 0.0));
+  const float varf = (float)var;
+  const float rstd = 1.0f / sqrtf(varf + kBnEps);
+  const float sc = a.gamma[c] * rstd;
+  a.mean[c] = mean;
+  a.rstd[c] = rstd;
+  a.scale[c] = sc;
+  a.bias[c] = a.beta[c] - mean * sc;
+  if (a.running_mean != nullptr) {
+    const float unbiased = (float)(var * (a.n / (a.n > 1.0 ? a.n - 1.0 : 1.0)));
+    float rm = a.running_mean[c], rv = a.running_var[c];
+    for (int u = 0; u < a.num_updates; ++u) {
+      rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean_full;
+      rv = (1.f - kBnMomentum) * rv + kBnMomentum * unbiased;
+    }
+    a.running_mean[c] = rm;
+    a.running_var[c] = rv;
+  }
+}
 __global__ void bn_finalize_kernel(BnFinalizeArgs a) {
   pdl_wait();
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.C; c += gridDim.x * blockDim.x) {
-    const double ms = (double)a.sum[c] / a.n;
-    double var = (double)a.sumsq[c] / a.n - ms * ms;
-    if (var < 0.0) var = 0.0;
-    const float mean = (float)ms;
-    const float mean_full = (float)(ms + (a.offset ? (double)a.offset[c] : 0.0));
-    const float varf = (float)var;
-    const float rstd = 1.0f / sqrtf(varf + kBnEps);
-    const float sc = a.gamma[c] * rstd;
-    a.mean[c] = mean;
-    a.rstd[c] = rstd;
-    a.scale[c] = sc;
-    a.bias[c] = a.beta[c] - mean * sc;
-    if (a.running_mean != nullptr) {
-      const float unbiased = (float)(var * (a.n / (a.n > 1.0 ? a.n - 1.0 : 1.0)));
-      float rm = a.running_mean[c], rv = a.running_var[c];
-      for (int u = 0; u < a.num_updates; ++u) {
-        rm = (1.f - kBnMomentum) * rm + kBnMomentum * mean_full;
-        rv = (1.f - kBnMomentum) * rv + kBnMomentum * unbiased;
-      }
-      a.running_mean[c] = rm;
-      a.running_var[c] = rv;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.C; c += gridDim.x * blockDim.x)
+    bn_finalize_column(a, c, a.sum[c], a.sumsq[c]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_batches_tracked != nullptr)
+    *a.num_batches_tracked += a.num_updates;
+}
+// reduce_partials_kernel + bn_finalize_kernel in one launch (single-GPU step: nothing to exchange between the two):
+// part[nblocks][2 * C] = per-block [sums | sums of squares]; a.sum / a.sumsq (the step's zeroed accumulators) receive
+// the totals as before.  One block per 32 columns.
+__global__ void __launch_bounds__(1024) bn_reduce_finalize_kernel(BnFinalizeArgs a, const float* __restrict__ part,
+                                                                  int nblocks) {
+  pdl_wait();
+  __shared__ float sm[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float s = 0.f, q = 0.f;
+  if (col < a.C)
+    for (int b = ty; b < nblocks; b += 32) {
+      s += part[(size_t)b * 2 * a.C + col];
+      q += part[(size_t)b * 2 * a.C + a.C + col];
     }
+  sm[0][ty][tx] = s;
+  sm[1][ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && col < a.C) {
+    float t = 0.f, u = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      t += sm[0][k][tx];
+      u += sm[1][k][tx];
+    }
+    t += a.sum[col];      // same association as the two-kernel path: accumulator (zero) + partial total
+    u += a.sumsq[col];
+    const_cast<float*>(a.sum)[col] = t;
+    const_cast<float*>(a.sumsq)[col] = u;
+    bn_finalize_column(a, col, t, u);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_batches_tracked != nullptr)
     *a.num_batches_tracked += a.num_updates;
@@ -894,52 +930,55 @@ __global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a)
   }
 }
 
-// sums the moment partials over blocks (grid: C/32 x 8 arrays) into tot[8][C] ...
-__global__ void __launch_bounds__(1024) g_head_moments_sum_kernel(const float* __restrict__ part, int nblocks, int C,
-                                                                  float* __restrict__ tot) {
+// Sums the moment partials over blocks (part[nblocks][8][C]: four arrays of sum dpre_j * 1[relu], four of
+// sum dpre_j * relu'd xhat terms) in a fixed order and finishes sum dy, sum dy*xhat and dW3 from them; one extra block
+// adds g_head_dpre_kernel's partials (db3, range-loss sum).  One launch (was: a summing kernel and a finishing kernel):
+// a block owns 8 columns; thread = (column, array, one of 16 row groups).
+__global__ void __launch_bounds__(1024) g_head_moments_kernel(GHeadBwdArgs a, const float* __restrict__ part,
+                                                              int nblocks, int dpre_blocks) {
   pdl_wait();
-  __shared__ float sm[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int k = blockIdx.y;
-  float s = 0.f;
-  if (c < C)
-    for (int b = ty; b < nblocks; b += 32) s += part[(size_t)b * 8 * C + k * C + c];
-  sm[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && c < C) {
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 32; ++q) t += sm[q][tx];
-    tot[k * C + c] = t;
-  }
-}
-// ... and finishes sum dy, sum dy*xhat and dW3 from them
-__global__ void g_head_moments_finish_kernel(GHeadBwdArgs a, const float* __restrict__ tot, int dpre_blocks) {
-  pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0) {   // db3 and the range-loss sum from g_head_dpre_kernel's partials, fixed order
-    __shared__ double dsm[16][8];
-    const int q = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 128 threads: 16 groups x 8 quantities (5 used)
+  if (blockIdx.x == gridDim.x - 1) {   // db3 and the range-loss sum from g_head_dpre_kernel's partials, fixed order
+    __shared__ double dsm[128][8];
+    const int q = threadIdx.x & 7, grp = threadIdx.x >> 3;   // 128 groups x 8 quantities (5 used)
     double t = 0.0;
     if (q < 5)
-      for (int b = grp; b < dpre_blocks; b += 16) t += (double)a.dpre_part[b * 8 + q];
+      for (int b = grp; b < dpre_blocks; b += 128) t += (double)a.dpre_part[b * 8 + q];
     dsm[grp][q] = t;
     __syncthreads();
     if (threadIdx.x < 5) {
       double tt = 0.0;
-      for (int k = 0; k < 16; ++k) tt += dsm[k][threadIdx.x];
+      for (int k = 0; k < 128; ++k) tt += dsm[k][threadIdx.x];
       if (threadIdx.x < 4) a.db3[threadIdx.x] += (float)tt * a.inv_gs;
       else if (a.range_sum) *a.range_sum += tt;
     }
+    return;
   }
-  if (c >= a.C) return;
+  __shared__ float sm[16][64];
+  __shared__ float tot[8][8];
+  const int cl = threadIdx.x & 7, k = (threadIdx.x >> 3) & 7, rg = threadIdx.x >> 6;
+  const int c = blockIdx.x * 8 + cl;
+  float s = 0.f;
+  if (c < a.C) {
+    const float* col = part + (size_t)k * a.C + c;
+#pragma unroll 4
+    for (int b = rg; b < nblocks; b += 16) s += col[(size_t)b * 8 * a.C];
+  }
+  sm[rg][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += sm[q][threadIdx.x];
+    tot[k][cl] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 8 || c >= a.C) return;
   const float sc = a.scale[c], bi = a.bias[c], mu = a.mean[c], rs = a.rstd[c];
   float sdy = 0.f, sdyh = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float w = a.w3[j * a.C + c];
-    const float t0 = tot[j * a.C + c], t1 = tot[(4 + j) * a.C + c];
+    const float t0 = tot[j][cl], t1 = tot[4 + j][cl];
     sdy = fmaf(w, t0, sdy);
     sdyh = fmaf(w, t1, sdyh);
     a.dw3[j * a.C + c] += a.inv_gs * (sc * t1 + bi * t0);   // sum dpre_j * relu(sc*h+bi)
@@ -1908,6 +1947,7 @@ void launch_extract_wp(const float* w, int ld_src, int S, int P, float* wp, int 
 void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStream_t st) {
   launch_k(copy_pad_f32_kernel, (n_pad + 255) / 256, 256, 0, st, src, n, dst, n_pad);
 }
+void launch_reduce_columns(const ReduceArgs& a, cudaStream_t st) { launch_reduce_partials(a, st); }
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
@@ -1917,6 +1957,9 @@ void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* su
 }
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st) {
   launch_k(bn_finalize_kernel, (a.C + 255) / 256, 256, 0, st, a);
+}
+void launch_bn_reduce_finalize(const BnFinalizeArgs& a, const float* part, int nblocks, cudaStream_t st) {
+  launch_k(bn_reduce_finalize_kernel, (a.C + 31) / 32, 1024, 0, st, a, part, nblocks);
 }
 void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta,
                            const float* offset, float* scale, float* bias, int C, cudaStream_t st) {
@@ -1947,8 +1990,7 @@ void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
     const int dpre_blocks = grid_for_rows(a.rows, kThreads, 148 * 2);
     launch_k(g_head_dpre_kernel, dpre_blocks, kThreads, 0, st, b);
     launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, b);
-    launch_k(g_head_moments_sum_kernel, dim3((a.C + 31) / 32, 8), 1024, 0, st, a.part, grid, a.C, tot);
-    launch_k(g_head_moments_finish_kernel, (a.C + 127) / 128, 128, 0, st, b, tot, dpre_blocks);
+    launch_k(g_head_moments_kernel, (a.C + 7) / 8 + 1, 1024, 0, st, b, a.part, grid, dpre_blocks);
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,

@@ -79,6 +79,7 @@ void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStr
 // ------------------------------------------------------------------------------------------ BatchNorm (G)
 // sum[c] += sum_r h[r,c], sumsq[c] += sum_r h[r,c]^2
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st);
+void launch_reduce_columns(const ReduceArgs& a, cudaStream_t st);   // dst[c] += mult * sum over the partial rows
 struct BnFinalizeArgs {
   const float* sum;       // sums over the (global) batch of the stored (bias-free) pre-activation
   const float* sumsq;
@@ -97,6 +98,8 @@ struct BnFinalizeArgs {
   int num_updates;        // running-stat updates to apply (the reference runs G.forward twice per step, F8)
 };
 void launch_bn_finalize(const BnFinalizeArgs& a, cudaStream_t st);
+// reduction of [nblocks][2C] partial rows (sums | sums of squares) + finalize in one launch
+void launch_bn_reduce_finalize(const BnFinalizeArgs& a, const float* part, int nblocks, cudaStream_t st);
 // eval mode: y = gamma * (h + offset - running_mean) / sqrt(running_var + eps) + beta = scale * h + bias
 void launch_bn_eval_affine(const float* rm, const float* rv, const float* gamma, const float* beta,
                            const float* offset, float* scale, float* bias, int C, cudaStream_t st);

@@ -117,6 +117,8 @@ struct PiganEngine {
   uint32_t *d_mask1;                   // [2B][H1/32] sign bits of the discriminator's first activation
   float *dw_part;                      // [kDwPartSlabs][128][256] split-K weight-gradient slabs
   float *partials;                     // [kPartBlocks x kPartCols] two-stage batch reductions
+  int bn_pending_blocks = 0;           // > 0: partial rows of BatchNorm sums wait in `partials` for the fused reduce+finalize
+  bool whole_step = false;             // pigan_train_step (one GPU): nothing is exchanged between the phases
   float *dpre;                         // [B,4] generator head backward
   float *p, *pden, *dpden, *dp_lc, *dlogit, *prob, *row_err, *f_rowstats, *cvec, *g_beff, *d_beff, *d_wp;
   float *bn_sums, *bn_bwd_sums;        // [2*H1 + 2*H2], [2*H2 + 2*H1]
@@ -276,6 +278,37 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
   return run_tn<CfgS, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
 }
 
+// out[rows, n] = fp16(a . w^T) and, from the same epilogue, the column sums / sums of squares of the stored values
+// added into sum[n] / sumsq[n] (train-mode BatchNorm statistics of the generator's hidden layers); n = 256 or 512
+int linear_store_colstats(const __half* a, int64_t rows, int k, const __half* w, int n, __half* out, float* sum,
+                          float* sumsq, float* partials, cudaStream_t st, int* defer_blocks = nullptr) {
+  using Epi = EpiStore<CfgL1, false, false, false, false, false, true>;
+  if (n % 256 != 0) return fail(PIGAN_ERR_INVALID, "column statistics in the GEMM epilogue: n must be a multiple of 256");
+  typename Epi::Params ep;
+  PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
+  ep.bias = nullptr;
+  ep.scale = nullptr;
+  ep.rowstats = nullptr;
+  ep.n_tiles = n / 256;
+  ep.mask = nullptr;
+  ep.mask_words = 0;
+  ep.colpart = partials;
+  ep.col_groups = n / 256;
+  PIGAN_TRY((run_tn<CfgL1, Epi>(ep, a, rows, k, k, w, n, k, st)));
+  // launch_gemm's grid: min(units, SMs) rounded down to a multiple of the n-groups; 8 partial rows per CTA group
+  const int groups = n / 256;
+  const int units = ceil_div((int)rows, kBlockM) * groups;
+  int grid = units < sm_count() ? units : sm_count();
+  if (grid > groups) grid -= grid % groups;
+  if (defer_blocks) {   // the caller reduces and finalises in one launch (launch_bn_reduce_finalize)
+    *defer_blocks = grid / groups * 8;
+    return PIGAN_OK;
+  }
+  ReduceArgs r{partials, grid / groups * 8, 2 * n, 2, {{sum, n, 1.f}, {sumsq, n, 1.f}}};
+  launch_reduce_columns(r, st);
+  return PIGAN_OK;
+}
+
 // out[rows, n] = fp16(LeakyReLU(LayerNorm(a . w^T + bias)))   n = 256, 512 (one CTA per row tile) or 1024 (cluster of 2)
 long long* g_ln_trace = nullptr;  // pigan_engine_trace_layernorm
 // bias / gamma / beta: device pointers (the layer's fp32 parameters); the epilogue stages its columns in shared memory
@@ -377,19 +410,33 @@ int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cuda
 }
 
 // G layer 1 -> h1 (pre-BN product WITHOUT its constant bias: see launch_pack_first_layer)
-int g_layer1(PiganEngine* e, int64_t n, cudaStream_t st) {
+// PIGAN_GEMM_COLSTATS=0: statistics from a separate pass over the stored tensor (colstats_kernel), as in round 1
+static bool gemm_colstats(const PiganEngine* e) {
+  static const bool on = [] { const char* v = getenv("PIGAN_GEMM_COLSTATS"); return !(v && v[0] == '0'); }();
+  return on && e->gl.H1 % 256 == 0 && e->gl.H2 % 256 == 0;
+}
+// train = also produce the layer's BatchNorm batch sums (bn_sums); false: g_bn_stats is not called (eval mode)
+int g_layer1(PiganEngine* e, int64_t n, cudaStream_t st, bool train = false) {
   PM("g_l1_gemm");
+  if (train && gemm_colstats(e))
+    return linear_store_colstats(e->xc, n, kKp, e->g_w1h, e->gl.H1, e->g_h1, e->bn_sums, e->bn_sums + e->gl.H1,
+                                 e->partials, st, e->whole_step ? &e->bn_pending_blocks : nullptr);
   return linear_store<false, false, false>(e->xc, n, kKp, e->g_w1h, e->gl.H1, nullptr, e->g_h1, nullptr, st);
 }
-int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st) {
+int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st, bool train = false) {
   PM("g_bn_relu_apply");
   launch_bn_relu_apply(e->g_h1, e->scale1, e->bias1, e->g_a1, n, e->gl.H1, st);
   (void)gp;
   PM("g_l2_gemm");
+  if (train && gemm_colstats(e))
+    return linear_store_colstats(e->g_a1, n, e->gl.H1, e->g_w2h, e->gl.H2, e->g_h2, e->bn_sums + 2 * e->gl.H1,
+                                 e->bn_sums + 2 * e->gl.H1 + e->gl.H2, e->partials, st,
+                                 e->whole_step ? &e->bn_pending_blocks : nullptr);
   return linear_store<false, false, false>(e->g_a1, n, e->gl.H1, e->g_w2h, e->gl.H2, nullptr, e->g_h2, nullptr, st);
 }
 void g_bn_stats(PiganEngine* e, int which, int64_t n, cudaStream_t st) {
   const int H1 = e->gl.H1, H2 = e->gl.H2;
+  if (gemm_colstats(e)) return;   // the producing GEMM's epilogue already added them (g_layer1/2 with train = true)
   PM("g_bn_colstats");
   if (which == 1) launch_colstats(e->g_h1, n, H1, e->bn_sums, e->bn_sums + H1, e->partials, st);
   else launch_colstats(e->g_h2, n, H2, e->bn_sums + 2 * H1, e->bn_sums + 2 * H1 + H2, e->partials, st);
@@ -416,6 +463,11 @@ void g_bn_finalize(PiganEngine* e, int which, const float* gp, const float* offs
   a.n = n_global;
   a.num_updates = num_updates;
   PM("small");
+  if (e->bn_pending_blocks > 0) {
+    launch_bn_reduce_finalize(a, e->partials, e->bn_pending_blocks, st);
+    e->bn_pending_blocks = 0;
+    return;
+  }
   launch_bn_finalize(a, st);
 }
 
@@ -685,7 +737,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
         PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
       }
       PIGAN_TRY(pack_generator(e, gp, true, st));
-      PIGAN_TRY(g_layer1(e, B, st));
+      PIGAN_TRY(g_layer1(e, B, st, true));
       g_bn_stats(e, 1, B, st);
       break;
     }
@@ -693,7 +745,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       // the reference calls G.forward twice per step in train mode (train_pigan.py:131,148): same batch
       // statistics, running statistics updated twice
       g_bn_finalize(e, 1, gp, e->g_beff, a.g_bn_buffers, a.g_num_batches_tracked, NG, 2, st);
-      PIGAN_TRY(g_layer2(e, gp, B, st));
+      PIGAN_TRY(g_layer2(e, gp, B, st, true));
       g_bn_stats(e, 2, B, st);
       break;
     }
@@ -941,11 +993,11 @@ extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* b
     return PIGAN_OK;
   }
   PIGAN_TRY(pack_generator(e, gp, false, st));
-  PIGAN_TRY(g_layer1(e, n, st));
   PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+  PIGAN_TRY(g_layer1(e, n, st, true));
   g_bn_stats(e, 1, n, st);
   g_bn_finalize(e, 1, gp, e->g_beff, bn, nbt, (double)n, 1, st);
-  PIGAN_TRY(g_layer2(e, gp, n, st));
+  PIGAN_TRY(g_layer2(e, gp, n, st, true));
   g_bn_stats(e, 2, n, st);
   g_bn_finalize(e, 2, gp, gp + G.b2, bn, nbt, (double)n, 1, st);
   PM("g_head_fwd");
@@ -986,8 +1038,14 @@ extern "C" int pigan_train_step_phase(PiganEngine* e, const PiganTrainArgs* a, i
 
 extern "C" int pigan_train_step(PiganEngine* e, const PiganTrainArgs* a, void* stream) {
   PIGAN_TRY(check_train_args(e, a));
-  for (int ph = 0; ph <= 6; ++ph) PIGAN_TRY(train_phase(e, *a, ph, static_cast<cudaStream_t>(stream)));
-  return PIGAN_OK;
+  static const bool fuse = [] { const char* v = getenv("PIGAN_FUSE_BN_FINALIZE"); return !(v && v[0] == '0'); }();
+  e->whole_step = fuse;
+  e->bn_pending_blocks = 0;
+  int rc = PIGAN_OK;
+  for (int ph = 0; ph <= 6 && rc == PIGAN_OK; ++ph) rc = train_phase(e, *a, ph, static_cast<cudaStream_t>(stream));
+  e->whole_step = false;
+  e->bn_pending_blocks = 0;
+  return rc;
 }
 
 extern "C" int pigan_engine_profile_begin(PiganEngine* e, const char* sections_csv) {

@@ -195,9 +195,21 @@ __device__ __forceinline__ void drain_blocks32_unrolled(uint32_t tacc, F&& f) {
 // stored value over this tile's columns — the LayerNorm partials the consumer merges
 // (forward_model.py:31-53).  `bias` must be zero-padded to a multiple of BLOCK_N.
 // =====================================================================================================
-template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false>
+// COLSTATS (train-mode BatchNorm, generator.py:19,22): the epilogue also produces the per-column sum and sum of squares
+// of the STORED fp16 values over the rows this CTA handled - every warp reads its staged [32 x 32] block back column-
+// wise (lane = column pair, half-warp = row parity: 16 conflict-free LDS.32 per block) while the TMA store of the same
+// block is in flight, and keeps (sum, sumsq) x 2 columns per lane in its own 4 KB shared-memory slab; finish() writes
+// one partial row per warp for reduce_partials_kernel.  Replaces colstats_kernel's second pass over the tensor (67 MB
+// re-read per layer at B = 65 536).  A CTA must see ONE n-group for its whole life (FIXED_NGROUP: the launcher makes
+// the grid a multiple of the number of n-groups, so n_group = blockIdx.x % groups); partial matrix: row
+// (blockIdx.x / groups) * 8 + warp, columns [sums of N | sums of squares of N].
+template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false,
+          bool COLSTATS = false>
 struct EpiStore {
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1 && (!MASKOUT || Cfg::BLOCK_N % 128 == 0), "EpiStore tile shape");
+  static_assert(!COLSTATS || (Cfg::BLOCK_N == 256 && !BIAS && !AFFINE_RELU && !LRELU),
+                "column statistics: 256-column n-groups, rows beyond M must store zeros");
+  static constexpr bool FIXED_NGROUP = COLSTATS;
   struct Params {
     OutTile out;
     const float* bias;
@@ -208,14 +220,28 @@ struct EpiStore {
     uint32_t* mask;   // MASKOUT: [M][N/32] sign bits of the stored value (bit i of word c: column 32c+i > 0) —
                       // all the LeakyReLU backward needs, at 1/16 of the activation's bytes
     int mask_words;   // words per row (N / 32)
+    float* colpart;   // COLSTATS: [gridDim.x / col_groups * 8][2 * N] partial rows
+    int col_groups;   // n-groups of the layer (N / 256)
   };
-  static constexpr int SMEM_BYTES = kEpiStagingBytes;
+  static constexpr int kSlabBytes = 8 * 32 * 16;   // per warp: 8 column blocks x 32 lanes x float4
+  static constexpr int SMEM_BYTES = kEpiStagingBytes + (COLSTATS ? 4 * kSlabBytes : 0);
   static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = 1;
   struct State {
     WarpStager stg;
+    uint32_t slab;
+    int ng;
   };
-  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx& cx) { st.stg.init(cx); }
+  __device__ static void init(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    st.stg.init(cx);
+    if constexpr (COLSTATS) {
+      st.ng = (int)blockIdx.x % p.col_groups;
+      st.slab = cx.smem + kEpiStagingBytes + (uint32_t)(cx.tid >> 5) * kSlabBytes + (uint32_t)cx.lane * 16u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(st.slab + b * 512u), "f"(0.f) : "memory");
+    }
+  }
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
@@ -259,13 +285,57 @@ struct EpiStore {
       const uint32_t buf = st.stg.acquire(cx);
       WarpStager::put32(buf, cx.lane, v);
       st.stg.commit(cx, buf, p.out, n0 + c, w.m_tile * kBlockM);
+      if constexpr (COLSTATS) {
+        // after commit's __syncwarp the whole block is visible: this lane sums columns 2j, 2j+1 over the rows of
+        // its parity (the TMA store only reads the block, so both proceed together)
+        const int j = cx.lane & 15, par = cx.lane >> 4;
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          uint32_t hw;
+          asm volatile("ld.shared.b32 %0, [%1];"
+                       : "=r"(hw)
+                       : "r"(buf + (uint32_t)(2 * i + par) * 64u + (uint32_t)(((j >> 2) ^ (i & 3)) << 4) + (uint32_t)(j & 3) * 4u)
+                       : "memory");
+          const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+          a1 += x.x; a2 = fmaf(x.x, x.x, a2);
+          b1 += x.y; b2 = fmaf(x.y, x.y, b2);
+        }
+        const uint32_t sl = st.slab + (uint32_t)(c >> 5) * 512u;
+        float o0, o1, o2, o3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(sl) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl), "f"(o0 + a1), "f"(o1 + a2), "f"(o2 + b1), "f"(o3 + b2)
+                     : "memory");
+      }
     });
     if constexpr (ROWSTATS) {
       if (row < g.M)
         *reinterpret_cast<float2*>(p.rowstats + ((size_t)row * p.n_tiles + w.n_group) * 2) = make_float2(s1, s2);
     }
   }
-  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx& cx) { WarpStager::drain(cx); }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    if constexpr (COLSTATS) {
+      // one partial row per warp: this n-group's 256 columns of [sums | sums of squares]
+      const int N = p.col_groups * 256;
+      float* row = p.colpart + ((size_t)(blockIdx.x / p.col_groups) * 8 + (size_t)(cx.group * 4 + (cx.tid >> 5))) * (2 * N) +
+                   st.ng * 256;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        float o0, o1, o2, o3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(st.slab + b * 512u) : "memory");
+        o0 += __shfl_xor_sync(0xffffffffu, o0, 16);
+        o1 += __shfl_xor_sync(0xffffffffu, o1, 16);
+        o2 += __shfl_xor_sync(0xffffffffu, o2, 16);
+        o3 += __shfl_xor_sync(0xffffffffu, o3, 16);
+        if (cx.lane < 16) {
+          *reinterpret_cast<float2*>(row + b * 32 + 2 * cx.lane) = make_float2(o0, o2);
+          *reinterpret_cast<float2*>(row + N + b * 32 + 2 * cx.lane) = make_float2(o1, o3);
+        }
+      }
+    }
+    WarpStager::drain(cx);
+  }
 };
 
 // =====================================================================================================

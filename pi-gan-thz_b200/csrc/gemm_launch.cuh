@@ -28,6 +28,11 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& g
   if (ctas <= 0) return fail(PIGAN_ERR_CUDA, "no CUDA device");
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   int grid = units < ctas ? units : ctas;
+  if constexpr (epi_fixed_ngroup<Epi>::value) {
+    // the epilogue keeps per-column state for ONE n-group per CTA (u = block + it * grid, n_group = u % groups)
+    if (g.k_splits != 1 || g.pair_mode) return fail(PIGAN_ERR_INVALID, "fixed-n-group epilogue: no split-K / pair mode");
+    if (grid > g.num_n_groups) grid -= grid % g.num_n_groups;
+  }
   if constexpr (Cfg::B_RESIDENT) {
     // a CTA keeps the weights of ONE n-group: its units must all share it (u = block + it * grid, n_group = u % groups)
     if (g.k_splits != 1 || g.pair_mode || g.num_k_blocks > Cfg::B_RES_KB)

@@ -127,6 +127,11 @@ template <class E, class = void>
 struct epi_early_release { static constexpr bool value = false; };
 template <class E>
 struct epi_early_release<E, decltype((void)E::EARLY_RELEASE)> { static constexpr bool value = E::EARLY_RELEASE; };
+// Epilogues with `static constexpr bool FIXED_NGROUP = true` need every CTA to see one n-group only (gemm_launch.cuh)
+template <class E, class = void>
+struct epi_fixed_ngroup { static constexpr bool value = false; };
+template <class E>
+struct epi_fixed_ngroup<E, decltype((void)E::FIXED_NGROUP)> { static constexpr bool value = E::FIXED_NGROUP; };
 // arrivals per phase on the cluster-exchange barriers: Epi::XBAR_COUNT when defined, else 128 per CTA of the cluster
 template <class E, class = void>
 struct epi_xbar_count { static constexpr int value = 128 * E::CLUSTER; };

@@ -232,6 +232,7 @@ class NativeTrainer:
         dp = e.forward_model_vjp(self.fs.params.tensor(), p, g_out)
         self._pm_dp = (self.lambda_physics_metric * dp).contiguous()       # kept alive until the step has consumed it
         self._pm_loss = loss.detach()
+        self.last_physics_metric_rows = ok.sum()                           # rows where all four metrics are defined
         args.dp_extra = self._pm_dp.data_ptr()
 
     def _add_physics_metric_loss(self) -> None:
