@@ -295,6 +295,21 @@ def run_native(args):
                 "launches_timed": dom_cnt, "share_of_step": dom_ms / ms}
     step_tflops = FLOP_PER_TRAIN_SAMPLE * B * K / (ms * 1e-3) / 1e12
 
+    # ---- data parallel: what each exchange point of the step costs on this rank (kernel + wait for the slowest peer),
+    # CUDA events around the exchange kernels in a few extra, untimed steps
+    dp_exchange_us = None
+    if world > 1 and tr.xchg is not None:
+        tr.exchange_events = []
+        for i in range(5):
+            tr.step(*sets[i % NSETS], lr, lr)
+        torch.cuda.synchronize()
+        acc = {}
+        for name, a, b in tr.exchange_events:
+            acc.setdefault(name, []).append(a.elapsed_time(b) * 1e3)
+        tr.exchange_events = None
+        dp_exchange_us = {k: round(sum(v) / len(v), 1) for k, v in acc.items()}
+        barrier()
+
     # ---- the same step at a batch that tiles the 148 SMs without a partial wave (592 row tiles = 4 per SM instead of
     # 512 = 3.46): informational, shows how much of the gap to the roofline is wave quantisation at B = 65536
     quant = None
@@ -692,6 +707,7 @@ def run_native(args):
                        "exchange": ("none (one GPU)" if world == 1 else
                                     ("peer: one-shot all-reduce kernels over cudaIpc-mapped NVLink memory (csrc/dp.cu)"
                                      if tr.xchg is not None else "nccl all-reduce")),
+                       "exchange_us_rank0": dp_exchange_us,
                        "rank_cpu_affinity": f"{numa_cpus} GPU-local cores per rank (NVML)" if numa_cpus else "default",
                        "l2": f"{NSETS} distinct input batches rotated ({NSETS * h2d_bytes / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": roof,

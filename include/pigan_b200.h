@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PIGAN_ABI_VERSION 8
+#define PIGAN_ABI_VERSION 9
 
 #define PIGAN_OK 0
 #define PIGAN_ERR_INVALID (-1)     /* bad argument (null pointer, size, unsupported dimension) */
@@ -204,7 +204,7 @@ double* pigan_engine_loss_sums(PiganEngine* engine);   /* [16] fp64 */
  * pigan_train_step_phase.  Every rank allocates one exchange region (pigan_dp_alloc: a cudaMalloc of its own so
  * that it can be exported), publishes its cudaIpc handle to the others (any host channel), opens theirs and
  * creates a context from the table of mapped regions (own region at index `rank`).
- *   pigan_dp_allreduce_small  in-place sum over ranks of a buffer of <= 16 KB (fp32 or fp64), one CTA, one launch
+ *   pigan_dp_allreduce_small  in-place sum over ranks of a buffer of <= 8 KB (fp32 or fp64), one CTA, one launch
  *   pigan_dp_allreduce_grads  dst = sum over ranks of gradient slot (net, epoch & 1); the gradients of a step are
  *                             written straight into that slot (PiganTrainArgs.g_grads / d_grads point into it)
  * `channel` identifies the exchange point inside a step (0..15, the same on every rank), `epoch` >= 1 grows by one
@@ -222,6 +222,9 @@ int pigan_dp_create(PiganDp** out, int32_t world, int32_t rank, void* const* reg
 int pigan_dp_destroy(PiganDp* dp);
 int pigan_dp_allreduce_small(PiganDp* dp, void* buf, int32_t n, int32_t is_double, int32_t channel, uint32_t epoch,
                              void* stream);
+/* fp32 buffer a[0:na] and fp64 buffer b[0:nb] summed over ranks in ONE exchange (na + 2 nb <= 2048 words) */
+int pigan_dp_allreduce_small2(PiganDp* d, float* a, int32_t na, double* b, int32_t nb, int32_t channel, uint32_t epoch,
+                              void* stream);
 int pigan_dp_allreduce_grads(PiganDp* dp, int32_t net, float* dst, int64_t n, int32_t channel, uint32_t epoch,
                              double* sumsq, void* stream);
 

@@ -3,14 +3,19 @@
 // (SURVEY 2.2); under data parallelism the step needs 8 small all-reduces per iteration, all of them
 // latency-bound: 3-4 KB for the BatchNorm sums, 1 MB for each network's gradients.  Instead of a library call per
 // reduction every rank maps every other rank's exchange region (cudaIpc, NVLink P2P through NVSwitch) and
-//   small buffers: copies its values into its own slot, publishes an epoch flag to all peers, waits for theirs and
-//                  sums the slots in rank order (one CTA, one launch, result in place);
+//   small buffers: PUSHES its values into a slot of its own in every peer's region as 8-byte (word, epoch) pairs - the
+//                  pair is one store, so the epoch doubles as the "data valid" flag and no fence or separate flag is
+//                  needed (the LL idea of NCCL) - then polls its local slots until every peer's pairs carry this
+//                  epoch and sums them in rank order (one CTA, one launch, result in place).  One NVLink one-way
+//                  latency per exchange instead of fence + flag + remote read round trip (PIGAN_DP_PULL=1 keeps the
+//                  pull variant: copy into the own slot, flag, read the peers' slots);
 //   gradients    : live in the exchange region already (the weight-gradient kernels write there); each CTA waits for
 //                  the peers' flags, then sums its chunk straight out of the peers' memory into the local buffer
 //                  Adam reads, and accumulates the squared norm clip_grad_norm_ needs on the way.
 // Sums run in rank order on every rank, so the replicas stay bit-identical.  Spins are bounded: a protocol bug traps.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -22,7 +27,9 @@ namespace {
 
 constexpr int kMaxWorld = 16;
 constexpr int kChannels = 16;            // exchange points per step
-constexpr int kSmallSlotBytes = 16384;   // per channel and parity
+constexpr int kSmallWords = 2048;                           // 32-bit words per small exchange (8 KB of payload)
+constexpr int kSmallSrcBytes = kSmallWords * 8;             // one source rank's (word, epoch) pairs
+constexpr int kSmallSlotBytes = kSmallSrcBytes * kMaxWorld; // per channel and parity: [source rank][word]
 constexpr size_t kFlagBytes = 4096;      // [kChannels][kMaxWorld] uint32
 constexpr size_t kSmallBytes = (size_t)kChannels * 2 * kSmallSlotBytes;
 
@@ -72,6 +79,72 @@ __device__ __forceinline__ void wait_peer(const PeerTable& t, int channel, int s
         __trap();
       }
     }
+  }
+}
+
+__device__ __forceinline__ void st_pair_sys(uint2* p, uint32_t w, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(w), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_pair_sys(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Push variant.  Slot of (channel, parity) in every region: [source rank][word] pairs.  A slot is rewritten two
+// epochs later, which a peer can only reach after it has consumed this epoch's exchange of the other parity, i.e.
+// after this rank finished reading.  exchange_one: element i of a T buffer occupies words [w0, w0 + sizeof(T)/4).
+template <typename T>
+__device__ __forceinline__ void exchange_one(const PeerTable& t, T* __restrict__ buf, int i, int w0, int channel,
+                                             uint32_t epoch, size_t slot_off) {
+  constexpr int WORDS = sizeof(T) / 4;
+  const T mine = buf[i];
+  uint32_t w[WORDS];
+  memcpy(w, &mine, sizeof(T));
+  for (int p = 0; p < t.world; ++p) {
+    if (p == t.rank) continue;
+    uint2* dst = reinterpret_cast<uint2*>(t.base[p] + slot_off + (size_t)t.rank * kSmallSrcBytes) + w0;
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) st_pair_sys(dst + k, w[k], epoch);
+  }
+  T s = 0;
+  for (int r = 0; r < t.world; ++r) {
+    T v = mine;
+    if (r != t.rank) {
+      const uint2* src = reinterpret_cast<const uint2*>(t.base[t.rank] + slot_off + (size_t)r * kSmallSrcBytes) + w0;
+      uint32_t g[WORDS];
+#pragma unroll
+      for (int k = 0; k < WORDS; ++k) {
+        uint2 pr = ld_pair_sys(src + k);
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        while (pr.y != epoch) {
+          if ((++spins & 0xFFFu) == 0) {
+            const uint64_t now = timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 5000000000ull) {  // 5 s: a rank died or the schedule diverged
+              printf("pigan dp: rank %d waited 5 s for rank %d on channel %d epoch %u (word %d)\n", t.rank, r, channel,
+                     epoch, w0 + k);
+              __trap();
+            }
+          }
+          pr = ld_pair_sys(src + k);
+        }
+        g[k] = pr.x;
+      }
+      memcpy(&v, g, sizeof(T));
+    }
+    s += v;
+  }
+  buf[i] = s;
+}
+// a[0:na] (fp32) and b[0:nb] (fp64) in ONE exchange (either may be empty): words [0, na) | [na, na + 2 nb)
+__global__ void __launch_bounds__(1024) allreduce_small_push_kernel(PeerTable t, float* __restrict__ a, int na,
+                                                                    double* __restrict__ b, int nb, int channel,
+                                                                    uint32_t epoch, size_t slot_off) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent (launch_k)
+  for (int i = threadIdx.x; i < na + nb; i += blockDim.x) {
+    if (i < na) exchange_one<float>(t, a, i, i, channel, epoch, slot_off);
+    else exchange_one<double>(t, b, i - na, na + 2 * (i - na), channel, epoch, slot_off);
   }
 }
 
@@ -202,13 +275,37 @@ extern "C" int pigan_dp_destroy(PiganDp* d) {
 extern "C" int pigan_dp_allreduce_small(PiganDp* d, void* buf, int32_t n, int32_t is_double, int32_t channel,
                                         uint32_t epoch, void* stream) {
   PIGAN_CHECK_ARG(d && buf && n >= 1 && channel >= 0 && channel < kChannels && epoch >= 1);
-  PIGAN_CHECK_ARG((size_t)n * (is_double ? 8 : 4) <= (size_t)kSmallSlotBytes);
+  PIGAN_CHECK_ARG((size_t)n * (is_double ? 2 : 1) <= (size_t)kSmallWords);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t slot = kFlagBytes + ((size_t)channel * 2 + (epoch & 1u)) * kSmallSlotBytes;
+  static const bool pull = [] { const char* v = getenv("PIGAN_DP_PULL"); return v && v[0] == '1'; }();
+  if (!pull) {
+    if (is_double)
+      launch_k(allreduce_small_push_kernel, 1, 1024, 0, st, d->t, static_cast<float*>(nullptr), 0,
+               static_cast<double*>(buf), n, channel, epoch, slot);
+    else
+      launch_k(allreduce_small_push_kernel, 1, 1024, 0, st, d->t, static_cast<float*>(buf), n,
+               static_cast<double*>(nullptr), 0, channel, epoch, slot);
+    PIGAN_CUDA_OK(cudaGetLastError());
+    return PIGAN_OK;
+  }
   if (is_double)
     launch_k(allreduce_small_kernel<double>, 1, 1024, 0, st, d->t, static_cast<double*>(buf), n, channel, epoch, slot);
   else
     launch_k(allreduce_small_kernel<float>, 1, 1024, 0, st, d->t, static_cast<float*>(buf), n, channel, epoch, slot);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// One exchange for an fp32 buffer and an fp64 buffer together (BatchNorm backward sums + loss numerators): in-place
+// sums over ranks of a[0:na] and b[0:nb]; na + 2 nb <= 2048 words.  Push variant only.
+extern "C" int pigan_dp_allreduce_small2(PiganDp* d, float* a, int32_t na, double* b, int32_t nb, int32_t channel,
+                                         uint32_t epoch, void* stream) {
+  PIGAN_CHECK_ARG(d && na >= 0 && nb >= 0 && na + nb >= 1 && (na == 0 || a) && (nb == 0 || b));
+  PIGAN_CHECK_ARG(channel >= 0 && channel < kChannels && epoch >= 1 && (size_t)na + 2 * (size_t)nb <= (size_t)kSmallWords);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t slot = kFlagBytes + ((size_t)channel * 2 + (epoch & 1u)) * kSmallSlotBytes;
+  launch_k(allreduce_small_push_kernel, 1, 1024, 0, st, d->t, a, (int)na, b, (int)nb, channel, epoch, slot);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }

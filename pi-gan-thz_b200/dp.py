@@ -84,6 +84,12 @@ class DpExchange:
         check(lib.pigan_dp_allreduce_small(self.ctx, t.data_ptr(), t.numel(), is_double, channel, epoch,
                                            native.current_stream()))
 
+    def allreduce_small2(self, a: torch.Tensor, b: torch.Tensor, channel: int, epoch: int) -> None:
+        """fp32 tensor a and fp64 tensor b in one exchange."""
+        assert a.dtype == torch.float32 and b.dtype == torch.float64
+        check(lib.pigan_dp_allreduce_small2(self.ctx, a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), channel, epoch,
+                                            native.current_stream()))
+
     def allreduce_grads(self, net: int, dst: torch.Tensor, channel: int, epoch: int) -> None:
         check(lib.pigan_dp_allreduce_grads(self.ctx, net, dst.data_ptr(), dst.numel(), channel, epoch, None,
                                            native.current_stream()))

@@ -95,6 +95,7 @@ SIGNATURES = {
     "pigan_dp_create": (_i32, [C.POINTER(_vp), _i32, _i32, C.POINTER(_vp), _i64]),
     "pigan_dp_destroy": (_i32, [_vp]),
     "pigan_dp_allreduce_small": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_uint32, _vp]),
+    "pigan_dp_allreduce_small2": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, C.c_uint32, _vp]),
     "pigan_dp_allreduce_grads": (_i32, [_vp, _i32, _vp, _i64, _i32, C.c_uint32, _vp, _vp]),
     "pigan_engine_profile_begin": (_i32, [_vp, C.c_char_p]),
     "pigan_engine_profile_end": (_i32, [_vp, C.c_char_p, C.c_size_t]),

@@ -28,8 +28,9 @@ def dp_phase_plan(h1: int, h2: int):
         (1, [("bn_sums", slice(2 * h1, 2 * h1 + 2 * h2))]),         # BatchNorm-2
         (2, [("d_grads", None)]),                                   # discriminator gradients (before clip+Adam)
         (3, [("bn_bwd_sums", slice(0, 2 * h2))]),                   # BatchNorm-2 backward: sum dy, sum dy*xhat
-        (4, [("bn_bwd_sums", slice(2 * h2, 2 * h2 + 2 * h1))]),     # BatchNorm-1 backward
-        (5, [("g_grads", None), ("loss_sums", slice(0, 8))]),       # generator gradients, loss numerators
+        # BatchNorm-1 backward + the loss numerators (complete after phase 3: they ride along, one exchange fewer)
+        (4, [("bn_bwd_sums", slice(2 * h2, 2 * h2 + 2 * h1)), ("loss_sums", slice(0, 8))]),
+        (5, [("g_grads", None)]),                                   # generator gradients
         (6, []),                                                    # clip+Adam(G), loss finalisation
     ]
 
@@ -102,6 +103,7 @@ class NativeTrainer:
         self.lambda_physics_metric = float(lambda_physics_metric)
         self.physics_metric_weights = tuple(float(x) for x in physics_metric_weights)
         self.last_physics_metric_loss = None
+        self.exchange_events = None      # set to [] to collect (name, start, end) CUDA events of every peer exchange
         # data parallel: gradients are produced straight into an NVLink-mapped exchange region and summed by the
         # library's one-shot kernels (dp.py); NCCL all-reduce is the fallback when peers cannot be mapped
         self.xchg = _dp.DpExchange.create(max(gp.numel(), dp.numel()), self.device, process_group) \
@@ -259,14 +261,32 @@ class NativeTrainer:
             if phase == 6:
                 args.g_grads = self.g_grads.data_ptr()
             e.train_step_phase(args, phase)
-            for name, sl in reductions:
+            small = [(n, sl) for n, sl in reductions if n not in ("d_grads", "g_grads")]
+            todo = [(n, sl) for n, sl in reductions if n in ("d_grads", "g_grads")]
+            if len(small) == 2:      # an fp32 and an fp64 buffer: one exchange for both
+                todo.append(("+".join(n for n, _ in small), small))
+            else:
+                todo += small
+            for name, sl in todo:
+                ev = None
+                if self.exchange_events is not None:     # profiling aid (bench.py: dp_exchange_us)
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
                 if name == "d_grads":
                     x.allreduce_grads(1, self.d_grads, channel, ep)
                 elif name == "g_grads":
                     x.allreduce_grads(0, self.g_grads, channel, ep)
+                elif isinstance(sl, list):
+                    bufs = [self._buffer(n)[s_] for n, s_ in sl]
+                    f32 = next(b for b in bufs if b.dtype == torch.float32)
+                    f64 = next(b for b in bufs if b.dtype == torch.float64)
+                    x.allreduce_small2(f32, f64, channel, ep)
                 else:
                     buf = self._buffer(name)
                     x.allreduce_small(buf if sl is None else buf[sl], channel, ep)
+                if ev is not None:
+                    ev[1].record()
+                    self.exchange_events.append((f"after_phase_{phase}:{name}", ev[0], ev[1]))
                 channel += 1
 
     def _buffer(self, name: str) -> torch.Tensor:

@@ -41,7 +41,7 @@ def test_test_hooks_live_in_their_own_library():
 
 def test_version_and_layout_counts():
     from pigan_b200 import native
-    assert native.lib.pigan_abi_version() == 8
+    assert native.lib.pigan_abi_version() == 9
     d = native.default_dims()
     assert (d.spectrum_dim, d.param_dim, d.metrics_dim) == (250, 4, 8)
     # parameter counts of the reference modules

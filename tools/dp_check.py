@@ -41,6 +41,17 @@ for mode in ("nccl", "peer"):
     for _ in range(20): tr.step(sp, pr, mn, 2e-4, 2e-4)
     e1.record(); torch.cuda.synchronize()
     if rank == 0: print(f"{mode}: {e0.elapsed_time(e1)/20:.3f} ms/step at B={B} x {world}")
+    if mode == "peer":
+        tr.exchange_events = []
+        for _ in range(10): tr.step(sp, pr, mn, 2e-4, 2e-4)
+        torch.cuda.synchronize()
+        acc = {}
+        for name, a, b in tr.exchange_events:
+            acc.setdefault(name, []).append(a.elapsed_time(b) * 1e3)
+        tr.exchange_events = None
+        if rank == 0:
+            print("  per-exchange us on rank 0 (kernel + wait for the slowest peer):",
+                  {k: round(sum(v) / len(v), 1) for k, v in acc.items()})
 def rel(a, b): return float((a.double() - b.double()).norm() / b.double().norm())
 if rank == 0:
     print("losses rel", rel(res["peer"][0], res["nccl"][0]), "G params", rel(res["peer"][1], res["nccl"][1]),
