@@ -129,6 +129,20 @@ int pigan_generator_forward(PiganEngine* engine, const float* g_params, float* g
  * -> out_prob [n] (= [n,1]) */
 int pigan_discriminator_forward(PiganEngine* engine, const float* d_params, const float* spectrum,
                                 const float* params, int64_t n, float* out_prob, void* stream);
+/* Backward passes of the two trainable modules for callers that drive them through autograd (the drop-in modules'
+ * torch.autograd.Function wrappers) instead of the fused train step; what the reference gets from loss.backward()
+ * on Generator / Discriminator (train_pigan.py:141,185 and every variant trainer).  Both recompute the forward pass
+ * from the inputs (train-mode BatchNorm batch statistics for the generator; running buffers untouched), then run the
+ * backward kernels of pigan_train_step.  grad_scale s > 0: the fp16 gradient tensors inside hold s x the gradient -
+ * choose s so that s * max|upstream| is about 1.  Outputs are unscaled and OVERWRITTEN.
+ *   generator:      g_grads[G params] = d sum(grad_params_norm * G(spectrum)) / d(g_params);  n >= 2
+ *   discriminator:  d_grads[D params] = d sum(grad_prob * D(spectrum, params)) / d(d_params);
+ *                   grad_params [n,P] (may be NULL) = the same derivative with respect to `params`           */
+int pigan_generator_backward(PiganEngine* engine, const float* g_params, const float* spectrum, int64_t n,
+                             const float* grad_params_norm, float grad_scale, float* g_grads, void* stream);
+int pigan_discriminator_backward(PiganEngine* engine, const float* d_params, const float* spectrum,
+                                 const float* params, int64_t n, const float* grad_prob, float grad_scale,
+                                 float* d_grads, float* grad_params, void* stream);
 /* ForwardModel.forward in eval mode (core/models/forward_model.py:62-76): params_norm [n,P] ->
  * out [n, S+Mt] fp32 (columns [0,S) spectrum, [S,S+Mt) metrics, one buffer as in the reference) */
 int pigan_forward_model_forward(PiganEngine* engine, const float* params_norm, int64_t n, float* out,

@@ -8,7 +8,27 @@ columns of the spectrum operand of the first tensor-core GEMM.
 import torch
 import torch.nn as nn
 
-from ._native import _pkg, check_input
+from ._native import _pkg, check_input, module_params
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    """D(spectrum, params) with a backward pass into the module's parameters and into ``params`` (the path the
+    generator's adversarial gradient takes in D(x, denormalize(G(x))), train_pigan.py:152-154):
+    pigan_discriminator_backward recomputes the forward from the saved inputs, then runs the fused step's kernels."""
+
+    @staticmethod
+    def forward(ctx, spectrum, params_in, engine, st, *params):
+        out = engine.discriminator_forward(st.params.tensor(), spectrum, params_in)
+        ctx.engine, ctx.st = engine, st
+        ctx.save_for_backward(spectrum, params_in)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, p = ctx.saved_tensors
+        flat, gp = ctx.engine.discriminator_backward(ctx.st.params.tensor(), x, p, grad_out.contiguous(),
+                                                     want_grad_params=ctx.needs_input_grad[1])
+        return (None, gp, None, None, *ctx.st.params.views_like(flat))
 
 
 class Discriminator(nn.Module):
@@ -30,4 +50,9 @@ class Discriminator(nn.Module):
         eng, flat = _pkg()
         st = flat.net_state(self, "discriminator")
         engine = eng.get_engine(spectrum.device, spectrum.shape[0])
+        mp = module_params(st)
+        if torch.is_grad_enabled() and (params.requires_grad or any(p.requires_grad for p in mp)):
+            if spectrum.requires_grad:
+                raise NotImplementedError("gradient with respect to the discriminator's input spectrum is not provided")
+            return _DiscriminatorFn.apply(spectrum.float().contiguous(), params.float().contiguous(), engine, st, *mp)
         return engine.discriminator_forward(st.params.tensor(), spectrum, params)

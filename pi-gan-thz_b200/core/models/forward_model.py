@@ -52,7 +52,6 @@ class ForwardModel(nn.Module):
         # under autograd the surrogate is differentiable with respect to its INPUT; its own parameters get no
         # gradient here (they are frozen wherever the reference back-propagates through F) - training F itself is
         # core.train.pretrain_fwd_model / pigan_fwd_train_step
-        self._pigan_autograd_error = False
         check_input(self, structural_params_norm, "structural_params_norm")
         if self.training:
             raise NotImplementedError("ForwardModel.forward in train() mode (active Dropout) is not on the native "

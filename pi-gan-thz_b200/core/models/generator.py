@@ -9,7 +9,26 @@ init consumes torch's RNG exactly like the reference); the math runs in csrc/ vi
 import torch
 import torch.nn as nn
 
-from ._native import _pkg, check_input
+from ._native import _pkg, check_input, module_params
+
+
+class _GeneratorFn(torch.autograd.Function):
+    """G(spectrum) in train mode with a backward pass into the module's parameters (pigan_generator_backward: the
+    forward is recomputed from the saved spectrum, then the fused step's backward kernels run).  No gradient with
+    respect to the spectrum (the reference never asks for one)."""
+
+    @staticmethod
+    def forward(ctx, spectrum, engine, st, *params):
+        out = engine.generator_forward(st.params.tensor(), st.bn.tensor(), st.nbt.tensor(), spectrum, True)
+        ctx.engine, ctx.st = engine, st
+        ctx.save_for_backward(spectrum)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        flat = ctx.engine.generator_backward(ctx.st.params.tensor(), x, grad_out.contiguous())
+        return (None, None, None, *ctx.st.params.views_like(flat))
 
 
 class Generator(nn.Module):
@@ -28,4 +47,13 @@ class Generator(nn.Module):
         eng, flat = _pkg()
         st = flat.net_state(self, "generator")
         engine = eng.get_engine(spectrum.device, spectrum.shape[0])
+        params = module_params(st)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if not self.training:
+                raise NotImplementedError("Generator.forward under autograd in eval() mode (BatchNorm on running "
+                                          "statistics) is not on the native path; the reference differentiates the "
+                                          "generator in train() mode only (core/train/train_pigan.py:117)")
+            if spectrum.requires_grad:
+                raise NotImplementedError("gradient with respect to the generator's input spectrum is not provided")
+            return _GeneratorFn.apply(spectrum.float().contiguous(), engine, st, *params)
         return engine.generator_forward(st.params.tensor(), st.bn.tensor(), st.nbt.tensor(), spectrum, self.training)

@@ -106,6 +106,21 @@ inline int grid_for_rows(int64_t rows, int rows_per_block, int max_blocks = 148 
   return (int)(b < max_blocks ? b : max_blocks);
 }
 
+// p[i] (sigmoid output) -> scale * grad_out[i] * p (1 - p): the upstream gradient carried through the sigmoid
+__global__ void sigmoid_bwd_kernel(float* __restrict__ p, const float* __restrict__ g, float scale, long long n) {
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = p[i];
+    p[i] = scale * g[i] * v * (1.0f - v);
+  }
+}
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float mult, long long n) {
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = mult * src[i];
+}
+
 // dst[c] += mult * sum_b part[b * ld + off + c] for up to 8 column segments (one block per 32 columns)
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(ReduceArgs a) {
   pdl_wait();
@@ -1948,6 +1963,12 @@ void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStr
   launch_k(copy_pad_f32_kernel, (n_pad + 255) / 256, 256, 0, st, src, n, dst, n_pad);
 }
 void launch_reduce_columns(const ReduceArgs& a, cudaStream_t st) { launch_reduce_partials(a, st); }
+void launch_sigmoid_bwd(float* p_inout, const float* grad_out, float scale, int64_t n, cudaStream_t st) {
+  launch_k(sigmoid_bwd_kernel, (int)((n + 255) / 256), 256, 0, st, p_inout, grad_out, scale, (long long)n);
+}
+void launch_scale_copy(const float* src, float* dst, float mult, int64_t n, cudaStream_t st) {
+  launch_k(scale_copy_kernel, (int)((n + 255) / 256), 256, 0, st, src, dst, mult, (long long)n);
+}
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);

@@ -79,6 +79,8 @@ void launch_copy_pad_f32(const float* src, int n, float* dst, int n_pad, cudaStr
 // ------------------------------------------------------------------------------------------ BatchNorm (G)
 // sum[c] += sum_r h[r,c], sumsq[c] += sum_r h[r,c]^2
 void launch_colstats(const __half* h, int64_t rows, int C, float* sum, float* sumsq, float* part, cudaStream_t st);
+void launch_sigmoid_bwd(float* p_inout, const float* grad_out, float scale, int64_t n, cudaStream_t st);
+void launch_scale_copy(const float* src, float* dst, float mult, int64_t n, cudaStream_t st);
 void launch_reduce_columns(const ReduceArgs& a, cudaStream_t st);   // dst[c] += mult * sum over the partial rows
 struct BnFinalizeArgs {
   const float* sum;       // sums over the (global) batch of the stored (bias-free) pre-activation

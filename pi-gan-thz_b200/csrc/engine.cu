@@ -1021,6 +1021,117 @@ extern "C" int pigan_discriminator_forward(PiganEngine* e, const float* dp, cons
   return PIGAN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward passes of the two trainable modules for callers that drive them through autograd (the drop-in modules'
+// torch.autograd.Function wrappers, core/models/*.py) instead of the fused train step.  Both RECOMPUTE the forward
+// pass from the saved inputs (the engine's activation buffers are shared by every module call, so they cannot be
+// relied on between a forward and its backward), then run the same backward kernels as pigan_train_step.
+// `grad_scale` s: the fp16 gradient tensors hold s x the true gradient (the train step uses s = global batch); the
+// caller picks s so that s * max|upstream gradient| is O(1).  Outputs are unscaled.
+// ---------------------------------------------------------------------------------------------------------------
+
+// Generator (generator.py:28-33, train mode: batch statistics; the running buffers are NOT touched here):
+// g_grads[G.total] = d/d(params) of sum(grad_p * G(x)); g_grads is overwritten.
+extern "C" int pigan_generator_backward(PiganEngine* e, const float* gp, const float* x, int64_t n, const float* grad_p,
+                                        float grad_scale, float* g_grads, void* stream) {
+  PIGAN_CHECK_ARG(e && gp && x && grad_p && g_grads && n >= 2 && n <= e->max_batch && grad_scale > 0.f);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(g_grads) & 15u) == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GenLayout& G = e->gl;
+  const float inv_gs = 1.0f / grad_scale;
+  // ---- forward, activations into the engine's buffers
+  PIGAN_TRY(prep_spectrum(e, x, nullptr, n, st));
+  PIGAN_TRY(pack_generator(e, gp, true, st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(e->bn_bwd_sums, 0, (2 * G.H1 + 2 * G.H2) * sizeof(float), st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(g_grads, 0, G.total * sizeof(float), st));
+  PIGAN_TRY(g_layer1(e, n, st, true));
+  g_bn_stats(e, 1, n, st);
+  g_bn_finalize(e, 1, gp, e->g_beff, nullptr, nullptr, (double)n, 1, st);
+  PIGAN_TRY(g_layer2(e, gp, n, st, true));
+  g_bn_stats(e, 2, n, st);
+  g_bn_finalize(e, 2, gp, gp + G.b2, nullptr, nullptr, (double)n, 1, st);
+  launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, e->p, nullptr, e->xc, nullptr, n, G.H2, kKp,
+                    G.S, st);
+  // ---- backward: head + BatchNorm-2, layer 2, BatchNorm-1, layer 1 (train_phase cases 3-5 without the loss terms)
+  GHeadBwdArgs hb;
+  hb.p = e->p; hb.dpden = nullptr; hb.dp_lc = nullptr; hb.dp_extra = grad_p; hb.gs = grad_scale; hb.range_mult = 0.f;
+  hb.h2 = e->g_h2; hb.scale = e->scale2; hb.bias = e->bias2; hb.mean = e->mean2; hb.rstd = e->rstd2;
+  hb.w3 = gp + G.w3; hb.dy2 = e->g_dy2; hb.dw3 = g_grads + G.w3; hb.db3 = g_grads + G.b3;
+  hb.sum_dy = e->bn_bwd_sums; hb.sum_dyx = e->bn_bwd_sums + G.H2; hb.range_sum = nullptr;
+  hb.inv_gs = inv_gs; hb.rows = n; hb.C = G.H2;
+  hb.gamma = gp + G.bn2_w; hb.dbias = g_grads + G.b2; hb.dgamma = g_grads + G.bn2_w; hb.dbeta = g_grads + G.bn2_b;
+  hb.inv_n = 1.0 / (double)n; hb.part = e->partials; hb.dpre = e->dpre; hb.dpre_part = nullptr;
+  launch_g_head_bwd(hb, false, st);
+  launch_g_head_bwd(hb, true, st);
+  PIGAN_TRY(weight_grad(e->g_dy2, n, G.H2, e->g_a1, n, G.H1, g_grads + G.w2, G.H1, G.H1, inv_gs, -1, nullptr, 0, nullptr,
+                        0, e->dw_part, st));
+  PIGAN_TRY((linear_store<false, false, false>(e->g_dy2, n, G.H2, e->g_w2th, G.H1, nullptr, e->g_da1, nullptr, st)));
+  launch_bn_bwd_stats(e->g_da1, e->g_h1, e->scale1, e->bias1, e->mean1, e->rstd1, e->bn_bwd_sums + 2 * G.H2,
+                      e->bn_bwd_sums + 2 * G.H2 + G.H1, n, G.H1, e->partials, st);
+  BnBwdArgs bb;
+  bb.dy = e->g_da1; bb.h = e->g_h1; bb.relu_mask = 1;
+  bb.scale = e->scale1; bb.bias = e->bias1; bb.mean = e->mean1; bb.rstd = e->rstd1; bb.gamma = gp + G.bn1_w;
+  bb.sum_dy = e->bn_bwd_sums + 2 * G.H2; bb.sum_dyx = e->bn_bwd_sums + 2 * G.H2 + G.H1;
+  bb.dh = e->g_da1; bb.dbias = nullptr; bb.dgamma = g_grads + G.bn1_w; bb.dbeta = g_grads + G.bn1_b;
+  bb.inv_n = 1.0 / (double)n; bb.inv_gs = inv_gs; bb.rows = n; bb.C = G.H1; bb.part = e->partials;
+  launch_bn_bwd_apply(bb, st);
+  PIGAN_TRY(weight_grad(e->g_da1, n, G.H1, e->xc, n, kKp, g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P, g_grads + G.b1, 0,
+                        nullptr, 0, e->dw_part, st));
+  launch_dw_fixup(g_grads + G.w1, G.S, G.S, 0, g_grads + G.b1, e->cvec, G.H1, st);
+  PM(nullptr);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
+// Discriminator (discriminator.py:30-39): for out = D(x, params) [n] and an upstream gradient grad_out = dL/d(out),
+// d_grads[D.total] = dL/d(D's parameters) (overwritten) and grad_params[n,4] = dL/d(params) (may be null).
+// No gradient with respect to the spectrum x is produced (nothing in the reference asks for it).
+extern "C" int pigan_discriminator_backward(PiganEngine* e, const float* dp, const float* x, const float* params,
+                                            int64_t n, const float* grad_out, float grad_scale, float* d_grads,
+                                            float* grad_params, void* stream) {
+  PIGAN_CHECK_ARG(e && dp && x && params && grad_out && d_grads && n >= 1 && n <= e->max_batch && grad_scale > 0.f);
+  PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_grads) & 15u) == 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DiscLayout& D = e->dl;
+  const float inv_gs = 1.0f / grad_scale;
+  // ---- forward: z1 + sign mask, z2, probabilities (into the dlogit buffer)
+  PIGAN_TRY(prep_spectrum(e, x, params, n, st));
+  PIGAN_TRY(pack_discriminator(e, dp, true, st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(d_grads, 0, D.total * sizeof(float), st));
+  PIGAN_CUDA_OK(cudaMemsetAsync(e->dpden, 0, (size_t)n * 4 * sizeof(float), st));
+  PIGAN_TRY(d_layer1(e, n, 0, false, st));
+  DL2Opts o{n, n, 1.0f, 1.0f, 0, 0, (double)n, nullptr, e->dlogit, true, false};
+  PIGAN_TRY(d_layer2(e, dp, o, st));
+  // dlogit = s * grad_out * p * (1 - p)   (sigmoid backward)
+  launch_sigmoid_bwd(e->dlogit, grad_out, grad_scale, n, st);
+  // ---- backward (train_phase case 2 / 3 for one block of rows)
+  launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, d_grads + D.w3, d_grads + D.b2, d_grads + D.b3, n, D.H2,
+                  inv_gs, e->partials, st);
+  {
+    using Epi = EpiLeakyMaskStore<CfgSR>;
+    Epi::Params ep;
+    PIGAN_TRY(out_map(&ep.out, e->d_dh1, n, D.H1, D.H1));
+    ep.mask = e->d_mask1;
+    ep.mask_words = D.H1 / 32;
+    PIGAN_TRY((run_tn<CfgSR, Epi>(ep, e->d_dh2, n, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+  }
+  PIGAN_TRY(weight_grad(e->d_dh2, n, D.H2, e->d_z1, n, D.H1, d_grads + D.w2, D.H1, D.H1, inv_gs, -1, nullptr, 0, nullptr,
+                        0, e->dw_part, st));
+  PIGAN_TRY(weight_grad(e->d_dh1, n, D.H1, e->xc, n, kKp, d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN, d_grads + D.b1, 0,
+                        nullptr, 0, e->dw_part, st));
+  launch_dw_fixup(d_grads + D.w1, D.IN, D.S, D.P, d_grads + D.b1, e->cvec, D.H1, st);
+  if (grad_params != nullptr) {
+    using Epi = EpiDiscParamGrad<CfgP>;
+    Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
+    PIGAN_TRY((run_tn<CfgP, Epi>(ep, e->d_dh2, n, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+    launch_scale_copy(e->dpden, grad_params, inv_gs, n * 4, st);
+  }
+  PM(nullptr);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
+
 extern "C" int pigan_forward_model_forward(PiganEngine* e, const float* p_norm, int64_t n, float* out,
                                            void* stream) {
   PIGAN_CHECK_ARG(e && p_norm && out && n >= 1 && n <= e->max_batch);

@@ -84,6 +84,34 @@ class Engine:
                                               out.data_ptr(), native.current_stream()))
         return out
 
+    @staticmethod
+    def _grad_scale(g: torch.Tensor) -> float:
+        """s with s * max|g| = 1 (the fp16 gradient tensors of the backward kernels hold s x the gradient); one host
+        read - these entry points serve autograd callers, not the fused train step."""
+        m = float(g.abs().max())
+        return 1.0 / m if m > 0.0 and m == m and m != float("inf") else 1.0
+
+    def generator_backward(self, g_flat, spectrum, grad_params_norm) -> torch.Tensor:
+        """Flat gradient (layout of g_flat) of sum(grad_params_norm * G(spectrum)), train-mode BatchNorm."""
+        _require_cuda(spectrum, "spectrum")
+        x, g = _f32c(spectrum), _f32c(grad_params_norm)
+        out = torch.empty_like(g_flat)
+        check(lib.pigan_generator_backward(self.handle, g_flat.data_ptr(), x.data_ptr(), x.shape[0], g.data_ptr(),
+                                           self._grad_scale(g), out.data_ptr(), native.current_stream()))
+        return out
+
+    def discriminator_backward(self, d_flat, spectrum, params, grad_prob, want_grad_params: bool = True):
+        """(flat gradient of D's parameters, gradient with respect to `params` [n,4] or None) of
+        sum(grad_prob * D(spectrum, params))."""
+        _require_cuda(spectrum, "spectrum")
+        x, p, g = _f32c(spectrum), _f32c(params), _f32c(grad_prob).reshape(-1)
+        out = torch.empty_like(d_flat)
+        gp = torch.empty_like(p) if want_grad_params else None
+        check(lib.pigan_discriminator_backward(self.handle, d_flat.data_ptr(), x.data_ptr(), p.data_ptr(), x.shape[0],
+                                               g.data_ptr(), self._grad_scale(g), out.data_ptr(), native.ptr(gp),
+                                               native.current_stream()))
+        return out, gp
+
     def forward_model_forward(self, params_norm) -> torch.Tensor:
         _require_cuda(params_norm, "params_norm")
         p = _f32c(params_norm)

@@ -112,6 +112,8 @@ SIGNATURES = {
     "pigan_prepare_spectrum_operand": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "pigan_generator_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pigan_discriminator_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "pigan_generator_backward": (_i32, [_vp, _vp, _vp, _i64, _vp, _f32, _vp, _vp]),
+    "pigan_discriminator_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _f32, _vp, _vp, _vp]),
     "pigan_forward_model_forward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "pigan_train_step": (_i32, [_vp, C.POINTER(PiganTrainArgs), _vp]),
     "pigan_train_step_phase": (_i32, [_vp, C.POINTER(PiganTrainArgs), _i32, _vp]),
