@@ -70,12 +70,18 @@ def discriminator_forward(d: Dict[str, Tensor], xq: Tensor, c: Tensor, params: T
     return torch.sigmoid(z2 @ d["main.4.weight"].t() + d["main.4.bias"])
 
 
-def forward_model_forward(f: Dict[str, Tensor], p: Tensor, S: int, on: bool) -> Tuple[Tensor, Tensor]:
-    """forward_model.py:62-76 (eval): fp16 activations between the layers, fp16 weight copies from layer 2 on."""
+def forward_model_forward(f: Dict[str, Tensor], p: Tensor, S: int, on: bool, stored_pre_ln: bool = False
+                          ) -> Tuple[Tensor, Tensor]:
+    """forward_model.py:62-76 (eval): fp16 activations between the layers, fp16 weight copies from layer 2 on.
+    stored_pre_ln: the backward-capable path of the engine (pigan_fwd_train_step, pigan_forward_model_input_grad /
+    _vjp) stores the Linear output of the tensor-core layers in fp16 and normalises the stored values; the inference
+    path (EpiLnStore) normalises the fp32 accumulator."""
     h = p
     for k, (li, ni) in enumerate(zip(O.F_LINEAR[:-1], O.F_NORM)):
         w = f[f"model.{li}.weight"]
         h = h @ (w if k == 0 else q16(w, on, "weights")).t() + f[f"model.{li}.bias"]
+        if stored_pre_ln and k > 0:
+            h = q16(h, on)
         h = F.layer_norm(h, (h.shape[1],), f[f"model.{ni}.weight"], f[f"model.{ni}.bias"], O.LN_EPS)
         h = q16(F.leaky_relu(h, O.LEAKY), on)
     out = h @ q16(f["model.20.weight"], on, "weights").t() + f["model.20.bias"]
