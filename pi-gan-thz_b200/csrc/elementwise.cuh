@@ -209,8 +209,11 @@ struct AdamArgs {
 };
 void launch_clip_adam(const AdamArgs& a, cudaStream_t st);
 // second stage of the split-K weight-gradient GEMM (EpiWeightGradPartial): fixed-order sum of the k-split slabs
+// fix_cvec != nullptr: also dw[i*ld + j] += db[i] * (j < fix_S ? fix_cvec[j] : 2.5) for j < fix_S + fix_P (the rank-1
+// fix-up of a first layer whose operand is centred), db zero on entry
 void launch_dw_reduce(const float* part, int tiles_m, int tiles_n, int splits, float* dw, int ld, int m_valid,
-                      int n_valid, float scale, int bias_col, float* db, cudaStream_t st);
+                      int n_valid, float scale, int bias_col, float* db, cudaStream_t st,
+                      const float* fix_cvec = nullptr, int fix_S = 0, int fix_P = 0);
 // rank-1 fix-ups of first-layer weight gradients: dw[i*ld + j] += db[i] * cvec[j] (j < S);
 // dw[i*ld + S + e] += 2.5 * db[i] (e < P)
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,

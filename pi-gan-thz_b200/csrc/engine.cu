@@ -358,7 +358,8 @@ int linear_ln(const __half* a, int64_t rows, int k, const __half* w, int n, cons
 // dw[m_out, ld] += (1/gs) * a[kd, m_out]^T b[.., n]
 int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t b_rows, int n, float* dw, int ld,
                 int n_valid, float inv_gs, int bias_col, float* db, int64_t wrap_rows, const __half* b_tail,
-                int64_t tail_from_row, float* part, cudaStream_t st, int lda = 0) {
+                int64_t tail_from_row, float* part, cudaStream_t st, int lda = 0, const float* fix_cvec = nullptr,
+                int fix_S = 0, int fix_P = 0) {
   CUtensorMap ta, tb, tx;
   PIGAN_TRY(make_nt_maps(&ta, &tb, a, (int)kd, m_out, lda > 0 ? lda : m_out, b, (int)b_rows, n, n));
   const int tiles_m = ceil_div(m_out, kBlockM), tiles_n = ceil_div(n, 256);
@@ -375,7 +376,8 @@ int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t
   Epi::Params ep;
   PIGAN_TRY(make_tmap_f32_2d(&ep.part, part, 256, (uint64_t)tiles * g.k_splits * kBlockM, 256, kBlockM));
   PIGAN_TRY((launch_gemm<CfgW, Epi>(ta, tb, g, ep, st, 0, b_tail ? &tx : nullptr)));
-  launch_dw_reduce(part, tiles_m, tiles_n, g.k_splits, dw, ld, m_out, n_valid, inv_gs, bias_col, db, st);
+  launch_dw_reduce(part, tiles_m, tiles_n, g.k_splits, dw, ld, m_out, n_valid, inv_gs, bias_col, db, st, fix_cvec, fix_S,
+                   fix_P);
   return PIGAN_OK;
 }
 
@@ -778,9 +780,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
                             nullptr, 0, nullptr, 0, e->dw_part, st));
       PM("d_dw1_gemm");
       PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
-                            a.d_grads + D.b1, BP, e->tail_f, BP, e->dw_part, st));
-      PM("small");
-      launch_dw_fixup(a.d_grads + D.w1, D.IN, D.S, D.P, a.d_grads + D.b1, e->cvec, D.H1, st);
+                            a.d_grads + D.b1, BP, e->tail_f, BP, e->dw_part, st, 0, e->cvec, D.S, D.P));
       break;
     }
     case 3: {
@@ -839,9 +839,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       launch_bn_bwd_apply(bb, st);
       PM("g_dw1_gemm");
       PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, kKp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
-                            a.g_grads + G.b1, 0, nullptr, 0, e->dw_part, st));
-      PM("small");
-      launch_dw_fixup(a.g_grads + G.w1, G.S, G.S, 0, a.g_grads + G.b1, e->cvec, G.H1, st);
+                            a.g_grads + G.b1, 0, nullptr, 0, e->dw_part, st, 0, e->cvec, G.S, 0));
       break;
     }
     case 6: {
@@ -1077,8 +1075,7 @@ extern "C" int pigan_generator_backward(PiganEngine* e, const float* gp, const f
   bb.inv_n = 1.0 / (double)n; bb.inv_gs = inv_gs; bb.rows = n; bb.C = G.H1; bb.part = e->partials;
   launch_bn_bwd_apply(bb, st);
   PIGAN_TRY(weight_grad(e->g_da1, n, G.H1, e->xc, n, kKp, g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P, g_grads + G.b1, 0,
-                        nullptr, 0, e->dw_part, st));
-  launch_dw_fixup(g_grads + G.w1, G.S, G.S, 0, g_grads + G.b1, e->cvec, G.H1, st);
+                        nullptr, 0, e->dw_part, st, 0, e->cvec, G.S, 0));
   PM(nullptr);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
@@ -1119,8 +1116,7 @@ extern "C" int pigan_discriminator_backward(PiganEngine* e, const float* dp, con
   PIGAN_TRY(weight_grad(e->d_dh2, n, D.H2, e->d_z1, n, D.H1, d_grads + D.w2, D.H1, D.H1, inv_gs, -1, nullptr, 0, nullptr,
                         0, e->dw_part, st));
   PIGAN_TRY(weight_grad(e->d_dh1, n, D.H1, e->xc, n, kKp, d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN, d_grads + D.b1, 0,
-                        nullptr, 0, e->dw_part, st));
-  launch_dw_fixup(d_grads + D.w1, D.IN, D.S, D.P, d_grads + D.b1, e->cvec, D.H1, st);
+                        nullptr, 0, e->dw_part, st, 0, e->cvec, D.S, D.P));
   if (grad_params != nullptr) {
     using Epi = EpiDiscParamGrad<CfgP>;
     Epi::Params ep{e->d_mask1, D.H1 / 32, e->d_wp, e->dpden};
