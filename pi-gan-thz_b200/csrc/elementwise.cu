@@ -1344,19 +1344,7 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
 // dw[m, n] += db[m] * (n < fix_S ? c[n] : 2.5) for n < fix_S + fix_P, where db[m] = scale * (bias column's sum) - db
 // must be zero on entry.  Every thread of a row sums the bias column itself (a warp-uniform address: one broadcast
 // load per slab), which saves the separate fix-up launch.
-__device__ __forceinline__ float sum_slabs(const float* __restrict__ p, size_t stride, int splits) {
-  float t = 0.f;
-  int s = 0;
-  for (; s + 8 <= splits; s += 8) {
-    const float a0 = p[(size_t)s * stride], a1 = p[(size_t)(s + 1) * stride];
-    const float a2 = p[(size_t)(s + 2) * stride], a3 = p[(size_t)(s + 3) * stride];
-    const float a4 = p[(size_t)(s + 4) * stride], a5 = p[(size_t)(s + 5) * stride];
-    const float a6 = p[(size_t)(s + 6) * stride], a7 = p[(size_t)(s + 7) * stride];
-    t += ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  }
-  for (; s < splits; ++s) t += p[(size_t)s * stride];
-  return t;
-}
+template <bool FIX>
 __global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ part, int tiles_m, int tiles_n,
                                                         int splits, float* __restrict__ dw, int ld, int m_valid,
                                                         int n_valid, float scale, int bias_col,
@@ -1370,17 +1358,33 @@ __global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict_
   if (!is_w && !is_b) return;
   const int tiles = tiles_m * tiles_n;
   const size_t stride = (size_t)tiles * 128 * 256;
-  const size_t off = ((size_t)((m >> 7) * tiles_n + (n >> 8)) * 128 + (m & 127)) * 256 + (n & 255);
-  const float t = sum_slabs(part + off, stride, splits);
+  const float* p = part + ((size_t)((m >> 7) * tiles_n + (n >> 8)) * 128 + (m & 127)) * 256 + (n & 255);
+  // the row's bias column: the same address for every thread of the warp (one broadcast load per slab)
+  const int bc = FIX ? bias_col : 0;
+  const float* q = part + ((size_t)((m >> 7) * tiles_n + (bc >> 8)) * 128 + (m & 127)) * 256 + (bc & 255);
+  float t = 0.f, tb = 0.f;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    const float a0 = p[(size_t)s * stride], a1 = p[(size_t)(s + 1) * stride];
+    const float a2 = p[(size_t)(s + 2) * stride], a3 = p[(size_t)(s + 3) * stride];
+    if constexpr (FIX) {
+      const float b0 = q[(size_t)s * stride], b1 = q[(size_t)(s + 1) * stride];
+      const float b2 = q[(size_t)(s + 2) * stride], b3 = q[(size_t)(s + 3) * stride];
+      tb += (b0 + b1) + (b2 + b3);
+    }
+    t += (a0 + a1) + (a2 + a3);
+  }
+  for (; s < splits; ++s) {
+    t += p[(size_t)s * stride];
+    if constexpr (FIX) tb += q[(size_t)s * stride];
+  }
   if (!is_w) {
     db[m] += scale * t;
     return;
   }
   float v = dw[(size_t)m * ld + n] + scale * t;
-  if (fix_cvec != nullptr && n < fix_S + fix_P) {
-    const size_t boff = ((size_t)((m >> 7) * tiles_n + (bias_col >> 8)) * 128 + (m & 127)) * 256 + (bias_col & 255);
-    const float dbm = scale * sum_slabs(part + boff, stride, splits);
-    v += dbm * (n < fix_S ? fix_cvec[n] : kParamCenter);
+  if constexpr (FIX) {
+    if (n < fix_S + fix_P) v += (scale * tb) * (n < fix_S ? fix_cvec[n] : kParamCenter);
   }
   dw[(size_t)m * ld + n] = v;
 }
@@ -2099,8 +2103,12 @@ void launch_clip_adam(const AdamArgs& a, cudaStream_t st) {
 void launch_dw_reduce(const float* part, int tiles_m, int tiles_n, int splits, float* dw, int ld, int m_valid,
                       int n_valid, float scale, int bias_col, float* db, cudaStream_t st, const float* fix_cvec,
                       int fix_S, int fix_P) {
-  launch_k(dw_reduce_kernel, dim3(tiles_n, m_valid), 256, 0, st, part, tiles_m, tiles_n, splits, dw, ld, m_valid,
-           n_valid, scale, bias_col, db, fix_cvec, fix_S, fix_P);
+  if (fix_cvec != nullptr)
+    launch_k(dw_reduce_kernel<true>, dim3(tiles_n, m_valid), 256, 0, st, part, tiles_m, tiles_n, splits, dw, ld, m_valid,
+             n_valid, scale, bias_col, db, fix_cvec, fix_S, fix_P);
+  else
+    launch_k(dw_reduce_kernel<false>, dim3(tiles_n, m_valid), 256, 0, st, part, tiles_m, tiles_n, splits, dw, ld,
+             m_valid, n_valid, scale, bias_col, db, fix_cvec, fix_S, fix_P);
 }
 void launch_dw_fixup(float* dw, int ld, int S, int P, const float* db, const float* cvec, int rows,
                      cudaStream_t st) {

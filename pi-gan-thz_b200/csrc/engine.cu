@@ -295,16 +295,16 @@ int linear_store_colstats(const __half* a, int64_t rows, int k, const __half* w,
   ep.colpart = partials;
   ep.col_groups = n / 256;
   PIGAN_TRY((run_tn<CfgL1, Epi>(ep, a, rows, k, k, w, n, k, st)));
-  // launch_gemm's grid: min(units, SMs) rounded down to a multiple of the n-groups; 8 partial rows per CTA group
+  // launch_gemm's grid: min(units, SMs) rounded down to a multiple of the n-groups; one partial row per CTA group
   const int groups = n / 256;
   const int units = ceil_div((int)rows, kBlockM) * groups;
   int grid = units < sm_count() ? units : sm_count();
   if (grid > groups) grid -= grid % groups;
   if (defer_blocks) {   // the caller reduces and finalises in one launch (launch_bn_reduce_finalize)
-    *defer_blocks = grid / groups * 8;
+    *defer_blocks = grid / groups;
     return PIGAN_OK;
   }
-  ReduceArgs r{partials, grid / groups * 8, 2 * n, 2, {{sum, n, 1.f}, {sumsq, n, 1.f}}};
+  ReduceArgs r{partials, grid / groups, 2 * n, 2, {{sum, n, 1.f}, {sumsq, n, 1.f}}};
   launch_reduce_columns(r, st);
   return PIGAN_OK;
 }

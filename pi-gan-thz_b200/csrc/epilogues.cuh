@@ -202,7 +202,7 @@ __device__ __forceinline__ void drain_blocks32_unrolled(uint32_t tacc, F&& f) {
 // one partial row per warp for reduce_partials_kernel.  Replaces colstats_kernel's second pass over the tensor (67 MB
 // re-read per layer at B = 65 536).  A CTA must see ONE n-group for its whole life (FIXED_NGROUP: the launcher makes
 // the grid a multiple of the number of n-groups, so n_group = blockIdx.x % groups); partial matrix: row
-// (blockIdx.x / groups) * 8 + warp, columns [sums of N | sums of squares of N].
+// blockIdx.x / groups, columns [sums of N | sums of squares of N].
 template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false,
           bool COLSTATS = false>
 struct EpiStore {
@@ -220,7 +220,7 @@ struct EpiStore {
     uint32_t* mask;   // MASKOUT: [M][N/32] sign bits of the stored value (bit i of word c: column 32c+i > 0) —
                       // all the LeakyReLU backward needs, at 1/16 of the activation's bytes
     int mask_words;   // words per row (N / 32)
-    float* colpart;   // COLSTATS: [gridDim.x / col_groups * 8][2 * N] partial rows
+    float* colpart;   // COLSTATS: [gridDim.x / col_groups][2 * N] partial rows
     int col_groups;   // n-groups of the layer (N / 256)
   };
   static constexpr int kSlabBytes = 8 * 32 * 16;   // per warp: 8 column blocks x 32 lanes x float4
@@ -315,23 +315,29 @@ struct EpiStore {
   }
   __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
     if constexpr (COLSTATS) {
-      // one partial row per warp: this n-group's 256 columns of [sums | sums of squares]
-      const int N = p.col_groups * 256;
-      float* row = p.colpart + ((size_t)(blockIdx.x / p.col_groups) * 8 + (size_t)(cx.group * 4 + (cx.tid >> 5))) * (2 * N) +
-                   st.ng * 256;
+      // one partial row per CTA: the eight warps' slabs (and the two row parities inside each) are added here, in a
+      // fixed order, so that the reduction kernel reads 148 rows instead of 1184
+      asm volatile("bar.sync 5, 256;" ::: "memory");   // both epilogue groups have finished their units
+      const int t = cx.group * 128 + cx.tid;
+      if (t < 128) {
+        const int blk = t >> 4, j = t & 15;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        float o0, o1, o2, o3;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(st.slab + b * 512u) : "memory");
-        o0 += __shfl_xor_sync(0xffffffffu, o0, 16);
-        o1 += __shfl_xor_sync(0xffffffffu, o1, 16);
-        o2 += __shfl_xor_sync(0xffffffffu, o2, 16);
-        o3 += __shfl_xor_sync(0xffffffffu, o3, 16);
-        if (cx.lane < 16) {
-          *reinterpret_cast<float2*>(row + b * 32 + 2 * cx.lane) = make_float2(o0, o2);
-          *reinterpret_cast<float2*>(row + N + b * 32 + 2 * cx.lane) = make_float2(o1, o3);
+        for (int w = 0; w < 8; ++w) {
+          const uint32_t slab = cx.smem0 + (uint32_t)(w >> 2) * SMEM_BYTES + kEpiStagingBytes + (uint32_t)(w & 3) * kSlabBytes +
+                                (uint32_t)blk * 512u;
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            float o0, o1, o2, o3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(slab + (uint32_t)(par * 16 + j) * 16u) : "memory");
+            s0 += o0; s1 += o1; s2 += o2; s3 += o3;
+          }
         }
+        const int N = p.col_groups * 256;
+        float* row = p.colpart + (size_t)(blockIdx.x / p.col_groups) * (2 * N) + st.ng * 256;
+        *reinterpret_cast<float2*>(row + blk * 32 + 2 * j) = make_float2(s0, s2);
+        *reinterpret_cast<float2*>(row + N + blk * 32 + 2 * j) = make_float2(s1, s3);
       }
     }
     WarpStager::drain(cx);
