@@ -569,6 +569,42 @@ int d_layer2(PiganEngine* e, const float* dp, const DL2Opts& o, cudaStream_t st)
   return run_tn<CfgS, Epi>(ep, e->d_z1, o.rows, L.H1, L.H1, e->d_w2h, L.H2, L.H1, st);
 }
 
+// D layers 2+3 + BCE with the backward of layer 3 / layer 2's activation fused in (EpiDiscL2Bwd): writes dh2 instead
+// of z2; param_grads (D-step): dw3 / db2 / db3 accumulate into d_grads.  PIGAN_FUSE_DL2=0: the two-kernel path.
+bool fuse_dl2() {
+  static const bool on = [] { const char* v = getenv("PIGAN_FUSE_DL2"); return !(v && v[0] == '0'); }();
+  return on;
+}
+template <bool PG>
+int d_layer2_bwd(PiganEngine* e, const float* dp, const DL2Opts& o, float* d_grads, float inv_gs, cudaStream_t st) {
+  using Epi = EpiDiscL2Bwd<CfgL1, PG>;
+  const DiscLayout& L = e->dl;
+  typename Epi::Params ep;
+  PIGAN_TRY(out_map(&ep.dh2, e->d_dh2, o.rows, L.H2, L.H2));
+  ep.b2 = dp + L.b2;
+  ep.w3 = dp + L.w3;
+  ep.b3 = dp + L.b3;
+  ep.label_a = o.label_a;
+  ep.label_b = o.label_b;
+  ep.rows_a = (int)o.rows_a;
+  ep.row_gap_begin = (int)o.gap_begin;
+  ep.row_gap_end = (int)o.gap_end;
+  ep.inv_batch = (float)(1.0 / o.global_batch);
+  ep.grad_mult = 1.0f;  // GS == global batch
+  ep.loss_sum = o.loss_sum;
+  ep.part = e->partials;
+  PM("d_l2_bce_gemm");
+  PIGAN_TRY((run_tn<CfgL1, Epi>(ep, e->d_z1, o.rows, L.H1, L.H1, e->d_w2h, L.H2, L.H1, st)));
+  if constexpr (PG) {
+    const int units = ceil_div((int)o.rows, kBlockM);
+    const int grid = units < sm_count() ? units : sm_count();   // launch_gemm's grid: one partial row per CTA
+    ReduceArgs r{e->partials, grid, 2 * L.H2 + 8, 3, {{d_grads + L.w3, L.H2, inv_gs}, {d_grads + L.b2, L.H2, inv_gs},
+                                                        {d_grads + L.b3, 1, inv_gs}}};
+    launch_reduce_columns(r, st);
+  }
+  return PIGAN_OK;
+}
+
 // ------------------------------------------------------------------------------------------ forward model
 struct FOutOpts {
   int target_mode;  // 0 none, 1 one fp32 row (e->cvec holds it, padded), 2 the centred fp16 operand e->xc + e->cvec
@@ -762,10 +798,14 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY(d_layer1(e, B, 0, false, st));
       PIGAN_TRY(d_layer1(e, B, BP, true, st));
       DL2Opts o{BP + B, BP, 0.9f, 0.1f, B, BP, NG, e->sums + kSumD, nullptr, true, true};
-      PIGAN_TRY(d_layer2(e, dp, o, st));
-      PM("d_l2_bwd");
-      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, a.d_grads + D.w3, a.d_grads + D.b2, a.d_grads + D.b3,
-                      BP + B, D.H2, inv_gs, e->partials, st);
+      if (fuse_dl2() && D.H2 == 256) {
+        PIGAN_TRY(d_layer2_bwd<true>(e, dp, o, a.d_grads, inv_gs, st));
+      } else {
+        PIGAN_TRY(d_layer2(e, dp, o, st));
+        PM("d_l2_bwd");
+        launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, a.d_grads + D.w3, a.d_grads + D.b2, a.d_grads + D.b3,
+                        BP + B, D.H2, inv_gs, e->partials, st);
+      }
       {
         PM("d_dh1_gemm");
         using Epi = EpiLeakyMaskStore<CfgSR>;
@@ -794,9 +834,13 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PIGAN_TRY(pack_discriminator(e, dp, true, st));
       PIGAN_TRY(d_layer1(e, B, 0, true, st));
       DL2Opts o{B, B, 1.0f, 1.0f, 0, 0, NG, e->sums + kSumAdv, nullptr, true, true};
-      PIGAN_TRY(d_layer2(e, dp, o, st));
-      PM("d_l2_bwd");
-      launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, e->partials, st);
+      if (fuse_dl2() && D.H2 == 256) {
+        PIGAN_TRY(d_layer2_bwd<false>(e, dp, o, nullptr, inv_gs, st));
+      } else {
+        PIGAN_TRY(d_layer2(e, dp, o, st));
+        PM("d_l2_bwd");
+        launch_d_l2_bwd(e->d_z2, e->dlogit, dp + D.w3, e->d_dh2, nullptr, nullptr, nullptr, B, D.H2, inv_gs, e->partials, st);
+      }
       {
         PM("d_paramgrad_gemm");
         // streamed operands on purpose: the epilogue reads 16 bytes of first-layer weights per accumulator column

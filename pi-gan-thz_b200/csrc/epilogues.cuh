@@ -626,6 +626,173 @@ struct EpiDiscL2 {
 };
 
 // =====================================================================================================
+// Discriminator layers 2+3 + BCE + the BACKWARD of layers 3 and 2's activation in the same epilogue (train step):
+// as EpiDiscL2 up to the logit gradient, then a second pass over the accumulator (still in tensor memory) writes
+//   dh2[r, c] = dlogit_r * w3[c] * LeakyReLU'(x[r, c])      (fp16, scaled by GS like dlogit)
+// instead of the activation - the layer's output never goes to HBM and the separate d_l2_bwd_kernel (a 134 MB round
+// trip per 131 072 rows) disappears.  PG (D-step): the parameter gradients that kernel produced come from here too,
+//   dw3[c] = sum_r dlogit_r * a[r, c],  db2[c] = sum_r dh2[r, c],  db3 = sum_r dlogit_r
+// as per-CTA partial rows [dw3 (256) | db2 (256) | db3 | pad 7] for reduce_partials_kernel: every warp stages dh2
+// (the block the TMA store takes) and dlogit * a as fp16 [32 x 32] blocks and reads them back column-wise (lane =
+// column pair, half-warp = row parity), exactly like EpiStore's COLSTATS; the eight warps' sums meet in finish().
+// =====================================================================================================
+template <class Cfg, bool PG>
+struct EpiDiscL2Bwd {
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1, "EpiDiscL2Bwd needs the whole row in one tile");
+  struct Params {
+    OutTile dh2;          // [rows, 256] fp16 out
+    const float* b2;      // [256]
+    const float* w3;      // [256]
+    const float* b3;      // [1]
+    float label_a, label_b;
+    int rows_a;
+    int row_gap_begin, row_gap_end;  // rows in [gap_begin, gap_end) are padding between the two halves
+    float inv_batch;      // 1 / global batch (loss mean)
+    float grad_mult;      // GS / global batch
+    double* loss_sum;     // += sum over rows of BCE * inv_batch
+    float* part;          // PG: [gridDim.x][2 * 256 + 8] partial rows
+  };
+  static constexpr int kSlabBytes = 8 * 32 * 16;    // per warp: 8 column blocks x 32 lanes x float4
+  static constexpr int kAuxOff = kEpiStagingBytes;  // second staging block per warp (dlogit * a)
+  static constexpr int kSlabOff = kAuxOff + (PG ? 4 * kWarpBlockBytes : 0);
+  static constexpr int SMEM_BYTES = PG ? kSlabOff + 4 * kSlabBytes : kEpiStagingBytes;
+  static_assert(SMEM_BYTES % 1024 == 0, "group regions stay 1024-aligned");
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
+  struct State {
+    WarpStager stg;
+    float loss, dl_sum;
+    uint32_t aux, slab;
+  };
+  __device__ static void init(const Params&, State& st, const GemmShape&, const EpiCtx& cx) {
+    st.stg.init(cx);
+    st.loss = 0.f;
+    st.dl_sum = 0.f;
+    if constexpr (PG) {
+      const uint32_t wq = (uint32_t)(cx.tid >> 5);
+      st.aux = cx.smem + kAuxOff + wq * kWarpBlockBytes;
+      st.slab = cx.smem + kSlabOff + wq * kSlabBytes + (uint32_t)cx.lane * 16u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(st.slab + b * 512u), "f"(0.f) : "memory");
+    }
+  }
+  // column sums of a staged [32 x 32] fp16 block: this lane's two columns over the rows of its parity
+  __device__ static void colsum2(uint32_t buf, int lane, float& a, float& b) {
+    const int j = lane & 15, par = lane >> 4;
+    a = 0.f;
+    b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t hw;
+      asm volatile("ld.shared.b32 %0, [%1];"
+                   : "=r"(hw)
+                   : "r"(buf + (uint32_t)(2 * i + par) * 64u + (uint32_t)(((j >> 2) ^ (i & 3)) << 4) + (uint32_t)(j & 3) * 4u)
+                   : "memory");
+      const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+      a += x.x;
+      b += x.y;
+    }
+  }
+  __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
+                              uint32_t tacc, const EpiCtx& cx) {
+    const int r = cx.q * 32 + cx.lane;
+    const int row = w.m_tile * kBlockM + r;
+    const bool valid = row < g.M && !(row >= p.row_gap_begin && row < p.row_gap_end);
+    // ---- pass 1: logit
+    float lg[4] = {0.f, 0.f, 0.f, 0.f};
+    drain_blocks32<256>(tacc, [&](int c, int, float* v) {
+      float b[32], w3[32];
+      load_cols32(p.b2 + c, b);
+      load_cols32(p.w3 + c, w3);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) lg[i & 3] = fmaf(lrelu(v[i] + b[i]), w3[i], lg[i & 3]);
+    });
+    float dl = 0.f;
+    if (valid) {
+      const float logit = (lg[0] + lg[1]) + (lg[2] + lg[3]) + __ldg(p.b3);
+      const float prob = 1.f / (1.f + expf(-logit));
+      const float y = row < p.rows_a ? p.label_a : p.label_b;
+      // nn.BCELoss forward (log clamped at -100) and autograd's backward (denominator clamped at 1e-12)
+      const float lp = fmaxf(logf(prob), -100.f);
+      const float l1p = fmaxf(log1pf(-prob), -100.f);
+      st.loss += -(y * lp + (1.f - y) * l1p) * p.inv_batch;
+      const float pq = prob * (1.f - prob);
+      dl = (prob - y) / fmaxf(pq, 1e-12f) * pq * p.grad_mult;
+    }
+    st.dl_sum += dl;
+    // ---- pass 2: gradient with respect to the layer's pre-activation, straight from the accumulator
+    drain_blocks32<256>(tacc, [&](int c, int, float* v) {
+      float b[32], w3[32], t[32];
+      load_cols32(p.b2 + c, b);
+      load_cols32(p.w3 + c, w3);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = v[i] + b[i];
+        const float slope = x > 0.f ? 1.f : kLeaky;
+        if constexpr (PG) t[i] = dl * (x * slope);
+        v[i] = dl * w3[i] * slope;
+      }
+      const uint32_t buf = st.stg.acquire(cx);
+      WarpStager::put32(buf, cx.lane, v);
+      if constexpr (PG) {
+        __syncwarp();   // the previous block's column reads of the aux block are done
+        WarpStager::put32(st.aux, cx.lane, t);
+      }
+      st.stg.commit(cx, buf, p.dh2, c, w.m_tile * kBlockM);
+      if constexpr (PG) {
+        float d0, d1, w0, w1;
+        colsum2(buf, cx.lane, d0, d1);      // db2: columns 2j, 2j+1 of dh2
+        colsum2(st.aux, cx.lane, w0, w1);   // dw3: the same columns of dlogit * a
+        const uint32_t sl = st.slab + (uint32_t)(c >> 5) * 512u;
+        float o0, o1, o2, o3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(sl) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sl), "f"(o0 + w0), "f"(o1 + d0), "f"(o2 + w1), "f"(o3 + d1)
+                     : "memory");
+      }
+    });
+  }
+  __device__ static void finish(const Params& p, State& st, const GemmShape&, const EpiCtx& cx) {
+    const float l = warp_sum(st.loss);
+    if (cx.lane == 0 && l != 0.f && p.loss_sum) atomicAdd(p.loss_sum, (double)l);
+    if constexpr (PG) {
+      const float ds = warp_sum(st.dl_sum);
+      WarpStager::drain(cx);   // the warp's staging blocks are free after this: the first one carries its sum of dlogit
+      __syncwarp();
+      if (cx.lane == 0) sts_f32(cx.smem + (uint32_t)(cx.tid >> 5) * 2u * kWarpBlockBytes, ds);
+      asm volatile("bar.sync 5, 256;" ::: "memory");   // both epilogue groups have finished their units
+      const int t = cx.group * 128 + cx.tid;
+      float* row = p.part + (size_t)blockIdx.x * (2 * 256 + 8);
+      if (t < 128) {
+        const int blk = t >> 4, j = t & 15;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const uint32_t slab = cx.smem0 + (uint32_t)(w >> 2) * SMEM_BYTES + kSlabOff + (uint32_t)(w & 3) * kSlabBytes +
+                                (uint32_t)blk * 512u;
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            float o0, o1, o2, o3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(o0), "=f"(o1), "=f"(o2), "=f"(o3) : "r"(slab + (uint32_t)(par * 16 + j) * 16u) : "memory");
+            s0 += o0; s1 += o1; s2 += o2; s3 += o3;
+          }
+        }
+        *reinterpret_cast<float2*>(row + blk * 32 + 2 * j) = make_float2(s0, s2);         // dw3
+        *reinterpret_cast<float2*>(row + 256 + blk * 32 + 2 * j) = make_float2(s1, s3);   // db2
+      } else if (t == 128) {
+        float d = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          d += lds_f32(cx.smem0 + (uint32_t)(w >> 2) * SMEM_BYTES + (uint32_t)(w & 3) * 2u * kWarpBlockBytes);
+        row[512] = d;                                                                      // db3
+      }
+    }
+    WarpStager::drain(cx);
+  }
+};
+
+// =====================================================================================================
 // dX through an in-place LeakyReLU (autograd of discriminator.py:23): out = acc * slope(sign of the saved
 // activation z).  Used for dH1 = (dH2.W2) * LeakyReLU'(z1) in the D-step.
 // =====================================================================================================
