@@ -131,3 +131,71 @@ def test_running_statistics_and_eval_mode():
         G(x)
     with torch.no_grad():
         assert G(x).shape == (256, 4)
+
+
+def test_interleaved_forwards_and_ragged_sizes():
+    """The backward passes recompute the forward from the saved inputs, so any call order works: two generator
+    forwards on different batches (130 and 257 rows: ragged row tiles), a discriminator forward in between, then the
+    backward passes in reverse order; every gradient equals the one of an isolated call."""
+    from oracle import fixtures
+    (G, D, _), _ = _modules()
+    G.train(); D.train()
+    xs = [fixtures.make_batch(n, seed=s)[0].to(DEV) for n, s in ((130, 1), (257, 2))]
+    pr = fixtures.make_batch(130, seed=1)[1].to(DEV)
+    ws = [torch.randn(x.shape[0], 4, device=DEV) for x in xs]
+    wd = torch.randn(130, 1, device=DEV)
+
+    def isolated_g(i):
+        G.zero_grad()
+        (G(xs[i]) * ws[i]).sum().backward()
+        return [p.grad.clone() for p in G.parameters()]
+
+    ref = [isolated_g(0), isolated_g(1)]
+    D.zero_grad()
+    (D(xs[0], pr) * wd).sum().backward()
+    ref_d = [p.grad.clone() for p in D.parameters()]
+    G.zero_grad(); D.zero_grad()
+    p0 = G(xs[0])
+    out = D(xs[0], pr)
+    p1 = G(xs[1])
+    (p1 * ws[1]).sum().backward()
+    g1 = [p.grad.clone() for p in G.parameters()]
+    G.zero_grad()
+    (out * wd).sum().backward()
+    (p0 * ws[0]).sum().backward()
+    g0 = [p.grad.clone() for p in G.parameters()]
+    for a, b in zip(g0, ref[0]):
+        assert torch.equal(a, b)
+    for a, b in zip(g1, ref[1]):
+        assert torch.equal(a, b)
+    for a, b in zip([p.grad for p in D.parameters()], ref_d):
+        assert torch.equal(a, b)
+    # gradients accumulate across backward calls like any autograd leaf
+    G.zero_grad()
+    (G(xs[0]) * ws[0]).sum().backward()
+    (G(xs[0]) * ws[0]).sum().backward()
+    for p, b in zip(G.parameters(), ref[0]):
+        assert torch.allclose(p.grad, 2 * b, rtol=1e-6, atol=0)
+
+
+def test_backward_entry_points_validate_their_arguments():
+    from pigan_b200 import engine as E
+    from pigan_b200 import native
+    eng = E.Engine(256, torch.device(DEV))
+    g = torch.zeros(native.lib.pigan_generator_param_count(None), device=DEV)
+    d = torch.zeros(native.lib.pigan_discriminator_param_count(None), device=DEV)
+    x = torch.zeros(128, 250, device=DEV)
+    gp = torch.zeros(128, 4, device=DEV)
+    st = native.current_stream()
+    bad = [
+        lambda: native.lib.pigan_generator_backward(eng.handle, g.data_ptr(), x.data_ptr(), 1, gp.data_ptr(), 1.0, g.data_ptr(), st),
+        lambda: native.lib.pigan_generator_backward(eng.handle, g.data_ptr(), x.data_ptr(), 128, gp.data_ptr(), 0.0, g.data_ptr(), st),
+        lambda: native.lib.pigan_generator_backward(eng.handle, g.data_ptr(), None, 128, gp.data_ptr(), 1.0, g.data_ptr(), st),
+        lambda: native.lib.pigan_generator_backward(eng.handle, g.data_ptr(), x.data_ptr(), 257, gp.data_ptr(), 1.0, g.data_ptr(), st),
+        lambda: native.lib.pigan_discriminator_backward(eng.handle, d.data_ptr(), x.data_ptr(), gp.data_ptr(), 0, gp.data_ptr(), 1.0, d.data_ptr(), None, st),
+        lambda: native.lib.pigan_discriminator_backward(eng.handle, d.data_ptr(), x.data_ptr(), None, 128, gp.data_ptr(), 1.0, d.data_ptr(), None, st),
+        lambda: native.lib.pigan_discriminator_backward(eng.handle, d.data_ptr(), x.data_ptr(), gp.data_ptr(), 128, gp.data_ptr(), -1.0, d.data_ptr(), None, st),
+    ]
+    for f in bad:
+        assert f() != native.PIGAN_OK and native.last_error()
+    torch.cuda.synchronize()
