@@ -250,23 +250,14 @@ int out_map(OutTile* m, __half* ptr, int64_t rows, int cols, int ld) {
   return make_tmap_f16_store(&m->map, ptr, (uint64_t)cols, (uint64_t)rows, (uint64_t)ld);
 }
 
-// out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
-template <bool BIAS, bool LRELU, bool RS, bool MASKOUT = false>
-int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
-                 float* rowstats, cudaStream_t st, const __half* a_tail = nullptr, uint32_t* mask = nullptr) {
-  if (k <= CfgSR::B_RES_KB * kBlockK) {
-    using Epi = EpiStore<CfgSR, BIAS, LRELU, RS, MASKOUT>;
-    typename Epi::Params ep;
-    PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
-    ep.bias = bias;
-    ep.scale = nullptr;
-    ep.rowstats = rowstats;
-    ep.n_tiles = ceil_div(n, 256);
-    ep.mask = mask;
-    ep.mask_words = n / 32;
-    return run_tn<CfgSR, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
-  }
-  using Epi = EpiStore<CfgS, BIAS, LRELU, RS, MASKOUT>;
+// PIGAN_STORE_GROUPS=2: two epilogue groups for the plain store epilogues (default four, see EpiStore)
+bool store_groups4() {
+  static const bool on = [] { const char* v = getenv("PIGAN_STORE_GROUPS"); return !(v && v[0] == '2'); }();
+  return on;
+}
+template <class Cfg, class Epi>
+int linear_store_run(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
+                     float* rowstats, cudaStream_t st, const __half* a_tail, uint32_t* mask) {
   typename Epi::Params ep;
   PIGAN_TRY(out_map(&ep.out, out, rows, n, n));
   ep.bias = bias;
@@ -275,7 +266,28 @@ int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, c
   ep.n_tiles = ceil_div(n, 256);
   ep.mask = mask;
   ep.mask_words = n / 32;
-  return run_tn<CfgS, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
+  ep.colpart = nullptr;
+  ep.col_groups = 0;
+  return run_tn<Cfg, Epi>(ep, a, rows, k, k, w, n, k, st, a_tail);
+}
+// out[rows, n] = act(a . w^T + bias) (+ LayerNorm row partials)
+template <bool BIAS, bool LRELU, bool RS, bool MASKOUT = false>
+int linear_store(const __half* a, int64_t rows, int k, const __half* w, int n, const float* bias, __half* out,
+                 float* rowstats, cudaStream_t st, const __half* a_tail = nullptr, uint32_t* mask = nullptr) {
+  if constexpr (!RS) {
+    if (store_groups4()) {
+      if (k <= CfgSR::B_RES_KB * kBlockK)
+        return linear_store_run<CfgSR, EpiStore<CfgSR, BIAS, LRELU, false, MASKOUT, false, false, 4>>(
+            a, rows, k, w, n, bias, out, rowstats, st, a_tail, mask);
+      return linear_store_run<CfgS, EpiStore<CfgS, BIAS, LRELU, false, MASKOUT, false, false, 4>>(
+          a, rows, k, w, n, bias, out, rowstats, st, a_tail, mask);
+    }
+  }
+  if (k <= CfgSR::B_RES_KB * kBlockK)
+    return linear_store_run<CfgSR, EpiStore<CfgSR, BIAS, LRELU, RS, MASKOUT>>(a, rows, k, w, n, bias, out, rowstats, st,
+                                                                             a_tail, mask);
+  return linear_store_run<CfgS, EpiStore<CfgS, BIAS, LRELU, RS, MASKOUT>>(a, rows, k, w, n, bias, out, rowstats, st, a_tail,
+                                                                         mask);
 }
 
 // out[rows, n] = fp16(a . w^T) and, from the same epilogue, the column sums / sums of squares of the stored values
@@ -499,16 +511,22 @@ int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cud
   const GenLayout& G = e->gl;
   {
     PM("g_l1_gemm");
-    using Epi = EpiStore<CfgSR, false, false, false, false, true>;
-    Epi::Params ep;
-    PIGAN_TRY(out_map(&ep.out, e->g_a1, n, G.H1, G.H1));
-    ep.bias = e->bias1;
-    ep.scale = e->scale1;
-    ep.rowstats = nullptr;
-    ep.n_tiles = 0;
-    ep.mask = nullptr;
-    ep.mask_words = 0;
-    PIGAN_TRY((run_tn<CfgSR, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st)));
+    auto run = [&](auto epi_tag) -> int {
+      using Epi = decltype(epi_tag);
+      typename Epi::Params ep;
+      PIGAN_TRY(out_map(&ep.out, e->g_a1, n, G.H1, G.H1));
+      ep.bias = e->bias1;
+      ep.scale = e->scale1;
+      ep.rowstats = nullptr;
+      ep.n_tiles = 0;
+      ep.mask = nullptr;
+      ep.mask_words = 0;
+      ep.colpart = nullptr;
+      ep.col_groups = 0;
+      return run_tn<CfgSR, Epi>(ep, e->xc, n, kKp, kKp, e->g_w1h, G.H1, kKp, st);
+    };
+    if (store_groups4()) PIGAN_TRY(run(EpiStore<CfgSR, false, false, false, false, true, false, 4>{}));
+    else PIGAN_TRY(run(EpiStore<CfgSR, false, false, false, false, true>{}));
   }
   if (with_f1 && fused_head(e)) {
     PM("g_l2_head_f1_gemm");

@@ -162,18 +162,30 @@ using WarpStager = WarpStagerT<2>;
 // GROUP = columns per trip of the (not unrolled) loop: 64, or 128 when f collects something per 128 columns in
 // registers (mask words); the loop is deliberately NOT unrolled across trips - ptxas would hoist the next trip's
 // load above this trip's arithmetic and run out of registers.
-template <int NCOLS, int GROUP = 64, class F>
+// X32 = true: one tcgen05.ld.x32 per block (32 live registers instead of 64) for the 16-warp epilogues, whose threads
+// have 96 registers each.
+template <int NCOLS, int GROUP = 64, bool X32 = false, class F>
 __device__ __forceinline__ void drain_blocks32(uint32_t tacc, F&& f) {
   static_assert(NCOLS % GROUP == 0 && GROUP % 64 == 0, "pairs of 32-column blocks");
 #pragma unroll 1
   for (int c0 = 0; c0 < NCOLS; c0 += GROUP) {
+    if constexpr (X32) {
 #pragma unroll
-    for (int c = 0; c < GROUP; c += 64) {
-      float v[64];
-      tmem_ld64(tacc + c0 + c, v);
-      tmem_ld_wait();
-      f(c0 + c, c / 32, v);
-      f(c0 + c + 32, c / 32 + 1, v + 32);
+      for (int c = 0; c < GROUP; c += 32) {
+        float v[32];
+        tmem_ld32(tacc + c0 + c, v);
+        tmem_ld_wait();
+        f(c0 + c, c / 32, v);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < GROUP; c += 64) {
+        float v[64];
+        tmem_ld64(tacc + c0 + c, v);
+        tmem_ld_wait();
+        f(c0 + c, c / 32, v);
+        f(c0 + c + 32, c / 32 + 1, v + 32);
+      }
     }
   }
 }
@@ -203,9 +215,17 @@ __device__ __forceinline__ void drain_blocks32_unrolled(uint32_t tacc, F&& f) {
 // re-read per layer at B = 65 536).  A CTA must see ONE n-group for its whole life (FIXED_NGROUP: the launcher makes
 // the grid a multiple of the number of n-groups, so n_group = blockIdx.x % groups); partial matrix: row
 // blockIdx.x / groups, columns [sums of N | sums of squares of N].
+// GROUPS_ = 4: four epilogue groups (16 warps); groups g and g + 2 share the units of accumulator buffer g & 1 and take
+// 128 of the 256 columns each - twice the warps to hide the latency of the TMEM loads and the constant loads behind
+// (no row or column statistics in this variant: those need the halves to meet).
 template <class Cfg, bool BIAS, bool LRELU, bool ROWSTATS, bool MASKOUT = false, bool AFFINE_RELU = false,
-          bool COLSTATS = false>
+          bool COLSTATS = false, int GROUPS_ = 2>
 struct EpiStore {
+  static_assert(GROUPS_ == 2 || (GROUPS_ == 4 && !ROWSTATS && !COLSTATS && Cfg::BLOCK_N == 256 && Cfg::ACC_BUFS == 2),
+                "four groups: plain store variants on 256-column tiles");
+  static constexpr int GROUPS = GROUPS_;
+  static constexpr int NT = Cfg::BLOCK_N / (GROUPS_ / 2);   // columns per thread
+  static constexpr int NBUF = GROUPS_ == 2 ? 2 : 1;         // staging blocks per warp
   static_assert(Cfg::BLOCK_N % 64 == 0 && Cfg::ACC_TILES == 1 && (!MASKOUT || Cfg::BLOCK_N % 128 == 0), "EpiStore tile shape");
   static_assert(!COLSTATS || (Cfg::BLOCK_N == 256 && !BIAS && !AFFINE_RELU && !LRELU),
                 "column statistics: 256-column n-groups, rows beyond M must store zeros");
@@ -224,11 +244,12 @@ struct EpiStore {
     int col_groups;   // n-groups of the layer (N / 256)
   };
   static constexpr int kSlabBytes = 8 * 32 * 16;   // per warp: 8 column blocks x 32 lanes x float4
-  static constexpr int SMEM_BYTES = kEpiStagingBytes + (COLSTATS ? 4 * kSlabBytes : 0);
+  static constexpr int SMEM_BYTES = 4 * NBUF * kWarpBlockBytes + (COLSTATS ? 4 * kSlabBytes : 0);
   static constexpr bool SPLIT = false;
   static constexpr int CLUSTER = 1;
+  using Stager = WarpStagerT<NBUF>;
   struct State {
-    WarpStager stg;
+    Stager stg;
     uint32_t slab;
     int ng;
   };
@@ -245,11 +266,12 @@ struct EpiStore {
   __device__ static void unit(const Params& p, State& st, const GemmShape& g, const UnitInfo& w,
                               uint32_t tacc, const EpiCtx& cx) {
     const int r = cx.q * 32 + cx.lane;
-    const int n0 = w.n_group * Cfg::BLOCK_N;
+    const int half = GROUPS_ == 4 ? (cx.group >> 1) : 0;
+    const int n0 = w.n_group * Cfg::BLOCK_N + half * NT;
     float s1 = 0.f, s2 = 0.f;
-    uint32_t mw[4];
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
     const int row = w.m_tile * kBlockM + r;
-    drain_blocks32<Cfg::BLOCK_N, MASKOUT ? 128 : 64>(tacc, [&](int c, int k, float* v) {
+    drain_blocks32<NT, 64, GROUPS_ == 4>(tacc + (uint32_t)(half * NT), [&](int c, int, float* v) {
       if constexpr (AFFINE_RELU) {
         float b[32], sc[32];
         load_cols32(p.bias + n0 + c, b);
@@ -277,13 +299,14 @@ struct EpiStore {
         uint32_t bits = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-        mw[k] = bits;
-        if (k == 3 && row < g.M)   // 128 columns done: one 16-byte store
+        // the last four words travel in a shift register (no indexing by a loop counter: the loop is rolled)
+        mw[0] = mw[1]; mw[1] = mw[2]; mw[2] = mw[3]; mw[3] = bits;
+        if ((c & 127) == 96 && row < g.M)   // 128 columns done: one 16-byte store
           *reinterpret_cast<uint4*>(p.mask + (size_t)row * p.mask_words + (n0 + c - 96) / 32) =
               make_uint4(mw[0], mw[1], mw[2], mw[3]);
       }
       const uint32_t buf = st.stg.acquire(cx);
-      WarpStager::put32(buf, cx.lane, v);
+      Stager::put32(buf, cx.lane, v);
       st.stg.commit(cx, buf, p.out, n0 + c, w.m_tile * kBlockM);
       if constexpr (COLSTATS) {
         // after commit's __syncwarp the whole block is visible: this lane sums columns 2j, 2j+1 over the rows of
@@ -340,7 +363,7 @@ struct EpiStore {
         *reinterpret_cast<float2*>(row + N + blk * 32 + 2 * j) = make_float2(s1, s3);
       }
     }
-    WarpStager::drain(cx);
+    Stager::drain(cx);
   }
 };
 
