@@ -155,8 +155,10 @@ int pigan_forward_model_forward(PiganEngine* engine, const float* params_norm, i
  *   phase 1  ... up to BatchNorm-2 statistics           -> reduce bn_sums[2*h1 .. 2*h1+2*h2)
  *   phase 2  G head, D-step forward/backward            -> reduce d_grads
  *   phase 3  D clip+Adam; G-step D/F forward, losses, head backward -> reduce bn_bwd_sums[0 .. 2*h2)
- *   phase 4  BatchNorm-2 backward, dW2, dX              -> reduce bn_bwd_sums[2*h2 .. 2*h2+2*h1)
- *   phase 5  BatchNorm-1 backward, dW1                  -> reduce g_grads, loss_sums[0:8] (all loss numerators)
+ *   phase 4  BatchNorm-2 backward, dW2, dX              -> reduce bn_bwd_sums[2*h2 .. 2*h2+2*h1) and loss_sums[0:8]
+ *                                                          (all loss numerators are complete after phase 3; any
+ *                                                          point before phase 6 will do)
+ *   phase 5  BatchNorm-1 backward, dW1                  -> reduce g_grads
  *   phase 6  G clip+Adam, loss finalisation
  * With one process, pigan_train_step runs phases 0..6 back to back. */
 typedef struct PiganTrainArgs {
