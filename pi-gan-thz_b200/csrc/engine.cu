@@ -675,8 +675,28 @@ int f_out_loss(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, c
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
+// candidate search: one target row, spectrum columns only, double-buffered 128 x 256 tiles (EpiFwdScore);
+// PIGAN_SCORE_TILE=288 keeps the 288-column loss epilogue for this mode too
+int f_out_score(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
+  using Epi = EpiFwdScore<CfgS>;
+  Epi::Params ep;
+  ep.bias = e->f_bias_out;
+  ep.tcen = e->cvec;
+  ep.S = L.S;
+  ep.row_err = o.row_err;
+  PM("f_out_gemm");
+  // weight map over the S spectrum rows only: the tile's remaining columns are zero-filled by TMA
+  PIGAN_TRY((run_tn<CfgS, Epi>(ep, a5, n, L.H[4], L.H[4], e->f_wh[5], L.S, L.H[4], st)));
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
 int f_out_layer(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st) {
   const FwdLayout& L = e->fl;
+  static const bool wide_score = [] { const char* v = getenv("PIGAN_SCORE_TILE"); return v && v[0] == '2' && v[1] == '8'; }();
+  if (o.out_full == nullptr && o.sums == nullptr && o.row_err != nullptr && o.target_mode == 1 && L.S <= 256 &&
+      L.H[4] % 64 == 0 && !wide_score)
+    return f_out_score(e, a5, n, o, st);
   // the loss / scoring modes have their own lean epilogue; the generic one keeps the fp32 dump of the output
   if (o.out_full == nullptr && L.S <= 256 && L.OUT <= 288) {
     if (o.sums != nullptr && o.target_mode == 2 && o.row_err == nullptr) return f_out_loss<2, true>(e, a5, n, o, st);

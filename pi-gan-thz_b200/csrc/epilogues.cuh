@@ -1265,6 +1265,55 @@ struct EpiFwdOut {
 };
 
 // =====================================================================================================
+// Candidate search (unified_evaluator.py:387 with ONE target spectrum for all rows): per-row reconstruction error
+// row_err[r] = mean_j (F(p_r)[j] - target[j])^2 from the surrogate's output layer, spectrum columns only.  The 8
+// metric columns are not needed here, so the tile is a plain 128 x 256 one (the weight map is built over the S = 250
+// spectrum rows: TMA zero-fills the other six) and the accumulator is DOUBLE-buffered - EpiFwdLoss' 288 columns fill
+// tensor memory once, so its epilogue and the next unit's MMAs take turns (ncu source view of the scoring launch: the
+// epilogue warps wait for the accumulator in 39 % of their samples).  One per-column constant (bias - target), staged
+// per group in shared memory; no smoothness term (train-time only).
+// =====================================================================================================
+template <class Cfg>
+struct EpiFwdScore {
+  static_assert(Cfg::BLOCK_N == 256 && Cfg::ACC_TILES == 1 && Cfg::ACC_BUFS == 2, "EpiFwdScore tile shape");
+  struct Params {
+    const float* bias;   // [>= 256] output-layer bias, zero-padded
+    const float* tcen;   // [256] the target row, zero-padded
+    int S;
+    float* row_err;      // [M]
+  };
+  static constexpr int SMEM_BYTES = 1024;   // per group: (bias - target)[256]
+  static constexpr bool SPLIT = false;
+  static constexpr int CLUSTER = 1;
+  struct State {};
+  __device__ static void init(const Params& p, State&, const GemmShape&, const EpiCtx& cx) {
+    for (int j = cx.tid; j < 256; j += 128)
+      sts_f32(cx.smem + 4u * (uint32_t)j, j < p.S ? __ldg(p.bias + j) - __ldg(p.tcen + j) : 0.f);
+    epi_bar_sync(cx, 0);
+  }
+  __device__ static void unit(const Params& p, State&, const GemmShape& g, const UnitInfo& w, uint32_t tacc,
+                              const EpiCtx& cx) {
+    const int row = w.m_tile * kBlockM + cx.q * 32 + cx.lane;
+    float rec4[4] = {0.f, 0.f, 0.f, 0.f};
+    drain_blocks32<256>(tacc, [&](int c, int, float* v) {
+#pragma unroll
+      for (int i4 = 0; i4 < 32; i4 += 4) {
+        float4 t;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(cx.smem + 4u * (uint32_t)(c + i4)));
+        const float d0 = v[i4] + t.x, d1 = v[i4 + 1] + t.y, d2 = v[i4 + 2] + t.z, d3 = v[i4 + 3] + t.w;
+        rec4[0] = fmaf(d0, d0, rec4[0]);
+        rec4[1] = fmaf(d1, d1, rec4[1]);
+        rec4[2] = fmaf(d2, d2, rec4[2]);
+        rec4[3] = fmaf(d3, d3, rec4[3]);
+      }
+    });
+    if (row < g.M) p.row_err[row] = ((rec4[0] + rec4[1]) + (rec4[2] + rec4[3])) / (float)p.S;
+  }
+  __device__ static void finish(const Params&, State&, const GemmShape&, const EpiCtx&) {}
+};
+
+// =====================================================================================================
 // The loss / scoring variants of the forward-model output layer (same tile shape and column split as EpiFwdOut, which
 // keeps the generic path with the fp32 dump).  Round 1 ran every mode through one epilogue with run-time switches:
 // 34 instructions per accumulator element, 7.7 % tensor-pipe activity (profiles/r02_fwd_gemms_ncu_before.csv).  Here
