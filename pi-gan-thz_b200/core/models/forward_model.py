@@ -35,11 +35,18 @@ class _SurrogateFn(torch.autograd.Function):
 
 
 class ForwardModel(nn.Module):
-    def __init__(self, input_param_dim: int, output_spectrum_dim: int, output_metrics_dim: int):
+    REFERENCE_WIDTHS = (256, 512, 1024, 512, 256)
+
+    def __init__(self, input_param_dim: int, output_spectrum_dim: int, output_metrics_dim: int, hidden=None):
+        """``hidden``: five hidden widths (default: the reference's).  Other widths - 256/512/1024/2048 each, e.g.
+        the widened surrogate of BASELINE config 5 with 2048-point spectra - run on an engine created for them."""
         super().__init__()
         self.output_spectrum_dim = output_spectrum_dim
         self.output_metrics_dim = output_metrics_dim
-        widths = (256, 512, 1024, 512, 256)
+        widths = tuple(int(w) for w in (hidden if hidden is not None else self.REFERENCE_WIDTHS))
+        if len(widths) != 5:
+            raise ValueError("ForwardModel: five hidden widths")
+        self.hidden = widths
         layers = []
         fan_in = input_param_dim
         for w in widths:
@@ -47,6 +54,14 @@ class ForwardModel(nn.Module):
             fan_in = w
         layers.append(nn.Linear(fan_in, output_spectrum_dim + output_metrics_dim))
         self.model = nn.Sequential(*layers)
+
+    def engine_dims(self):
+        """None at the reference dims (the process-wide full engine), else the PiganDims of a surrogate-only engine."""
+        if (self.hidden == self.REFERENCE_WIDTHS and self.output_spectrum_dim == 250 and self.output_metrics_dim == 8):
+            return None
+        from pigan_b200 import native
+        return native.make_dims(spectrum_dim=self.output_spectrum_dim, metrics_dim=self.output_metrics_dim,
+                                f_hidden=self.hidden)
 
     def forward(self, structural_params_norm: torch.Tensor):
         # under autograd the surrogate is differentiable with respect to its INPUT; its own parameters get no
@@ -58,7 +73,7 @@ class ForwardModel(nn.Module):
                                       "path; call .eval() as train_pigan does (core/train/train_pigan.py:75)")
         eng, flat = _pkg()
         st = flat.net_state(self, "forward_model")
-        engine = eng.get_engine(structural_params_norm.device, structural_params_norm.shape[0])
+        engine = eng.get_engine(structural_params_norm.device, structural_params_norm.shape[0], self.engine_dims())
         if torch.is_grad_enabled() and structural_params_norm.requires_grad:
             out = _SurrogateFn.apply(structural_params_norm.float().contiguous(), engine, st.params.tensor())
         else:

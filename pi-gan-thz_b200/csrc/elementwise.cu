@@ -1895,6 +1895,227 @@ __global__ void f_train_losses_kernel(const float* __restrict__ sums, double n_s
   out[2] = lm;
 }
 
+
+// ------------------------------------------------------------------------------------------ widened surrogate
+// BASELINE config 5 (hidden 2048, 2048-point spectra): the surrogate's streaming kernels for any hidden width
+// N = 256 * NCH (NCH = 1, 2, 4, 8).  Same arithmetic as the reference-width kernels above; a lane owns 8 columns of
+// every 256-column chunk of its row.
+// First layer (K = 4, forward_model.py:30-33), eval (TRAIN = false: act = LeakyReLU(LayerNorm(h))) or training mode
+// (xhat, 1/std, Dropout keep-bits as in f_l1_train_kernel).  The 16 N-byte weight rows come from L1/L2 per row.
+template <int NCH, bool TRAIN>
+__global__ void __launch_bounds__(kThreads) f_l1_wide_kernel(const float* __restrict__ p, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1,
+                                                             const float* __restrict__ lnw,
+                                                             const float* __restrict__ lnb, __half* __restrict__ xhat,
+                                                             __half* __restrict__ act, float* __restrict__ rstd_out,
+                                                             unsigned char* __restrict__ mask_out,
+                                                             unsigned char* __restrict__ keepbits, long long rows,
+                                                             DropoutArgs dr) {
+  pdl_wait();
+  constexpr int N = NCH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
+    float h[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float b[8];
+      ld_f8(b1 + c0, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c0 + i);
+        h[j][i] = fmaf(q.w, w.w, fmaf(q.z, w.z, fmaf(q.y, w.y, fmaf(q.x, w.x, b[i]))));
+        s += h[j][i];
+      }
+    }
+    const float mean = warp_sum_f(s) * (1.0f / N);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[j][i] -= mean;
+        v = fmaf(h[j][i], h[j][i], v);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum_f(v) * (1.0f / N) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float gm[8], bt[8], a[8];
+      ld_f8(lnw + c0, gm);
+      ld_f8(lnb + c0, bt);
+      if constexpr (TRAIN) {
+        const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, c0 >> 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          h[j][i] *= rstd;
+          a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[j][i], gm[i], bt[i])) * dr.keep_scale : 0.f;
+        }
+        st_h8(xhat + row * N + c0, h[j]);
+        keepbits[row * (N / 8) + (c0 >> 3)] = (unsigned char)keep;
+        if (mask_out) {
+          unsigned long long m = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
+          *reinterpret_cast<unsigned long long*>(mask_out + row * N + c0) = m;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = lrelu_f(fmaf(h[j][i] * rstd, gm[i], bt[i]));
+      }
+      st_h8(act + row * N + c0, a);
+    }
+    if (TRAIN && lane == 0) rstd_out[row] = rstd;
+  }
+}
+
+// dW1 (k-major partials [4][N]) = sum_r dh1[r, c] * p[r, j]: the first layer's weight gradient when its LayerNorm
+// backward ran through the generic kernel (ln_bwd_kernel<NCH, false>, dh kept in place).  A thread owns 8 columns.
+__global__ void __launch_bounds__(kThreads) f_dw1_wide_kernel(const __half* __restrict__ dh1, const float* __restrict__ p,
+                                                              long long rows, int N, float* __restrict__ part) {
+  pdl_wait();
+  __shared__ float sm[kThreads * 8];
+  const ColMap m(N);
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) zero8(acc[k]);
+  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < rows; r += (long long)gridDim.x * m.rpb) {
+    float d[8];
+    ld_h8(dh1 + r * N + m.ch * 8, d);
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] = fmaf(d[i], q.x, acc[0][i]);
+      acc[1][i] = fmaf(d[i], q.y, acc[1][i]);
+      acc[2][i] = fmaf(d[i], q.z, acc[2][i]);
+      acc[3][i] = fmaf(d[i], q.w, acc[3][i]);
+    }
+  }
+  float* prow = part + (size_t)blockIdx.x * (4 * N);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) block_colsum_partial(acc[k], prow + k * N, m, sm);
+}
+
+// dp[r, j] = scale * sum_c dh1[r, c] * W1[c, j] for any N = 256 * NCH; a warp per row
+__global__ void __launch_bounds__(kThreads) f_dp_wide_kernel(const __half* __restrict__ dh1, const float* __restrict__ w1,
+                                                             float* __restrict__ dp, long long rows, int nch,
+                                                             float scale) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int N = nch * 256;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = 0; j < nch; ++j) {
+      const int c0 = j * 256 + lane * 8;
+      float d[8];
+      ld_h8(dh1 + row * N + c0, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c0 + i);
+        a0 = fmaf(d[i], w.x, a0);
+        a1 = fmaf(d[i], w.y, a1);
+        a2 = fmaf(d[i], w.z, a2);
+        a3 = fmaf(d[i], w.w, a3);
+      }
+    }
+    a0 = warp_sum_f(a0); a1 = warp_sum_f(a1); a2 = warp_sum_f(a2); a3 = warp_sum_f(a3);
+    if (lane == 0) *reinterpret_cast<float4*>(dp + row * 4) = make_float4(a0 * scale, a1 * scale, a2 * scale, a3 * scale);
+  }
+}
+
+__global__ void f_dw1_transpose_wide_kernel(const float* __restrict__ src, float* __restrict__ dw1, int N) {
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dw1[c * 4 + j] = src[j * N + c];
+}
+
+// The widened output layer leaves its fp32 accumulators as [128 x 256] slabs (EpiWeightGradPartial on a TN GEMM):
+// element (r, c) of the [rows, OUT] product sits at slab[((r / 128) * ngroups + c / 256) * 32768 + (r % 128) * 256 + c % 256].
+__device__ __forceinline__ size_t slab_index(long long r, int c, int ngroups) {
+  return ((size_t)(r >> 7) * ngroups + (size_t)(c >> 8)) * 32768u + (size_t)(r & 127) * 256u + (size_t)(c & 255);
+}
+// out[r, c] = slab(r, c) + bias[c]: the row-major fp32 output of pigan_forward_model_forward
+__global__ void __launch_bounds__(kThreads) f_unslab_kernel(const float* __restrict__ slab, int ngroups,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            long long rows, int OUT) {
+  pdl_wait();
+  const int pairs = OUT >> 1;   // OUT is even
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int q = threadIdx.x; q < pairs; q += blockDim.x) {
+      const int c = 2 * q;
+      const float2 v = *reinterpret_cast<const float2*>(slab + slab_index(r, c, ngroups));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + c));
+      *reinterpret_cast<float2*>(out + r * OUT + c) = make_float2(v.x + b.x, v.y + b.y);
+    }
+}
+// f_out_loss_kernel for the slab layout and any width (ld <= 512 * kWideJ): a block walks rows, a thread owns the
+// column pairs (2 t + 512 j, +1).  Same outputs: dout (fp16, GS-scaled, zero padded to ld), per-block column sums of
+// dout in part[block][0 .. OUT) and the two sums of squares in part[block][ld_part - 2 .. ld_part).
+constexpr int kWideJ = 5;
+__global__ void __launch_bounds__(kThreads) f_out_loss_slab_kernel(const float* __restrict__ slab, int ngroups,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ spectrum,
+                                                                   const float* __restrict__ metrics,
+                                                                   __half* __restrict__ dout, int ld, long long rows,
+                                                                   int S, int Mt, float* __restrict__ part,
+                                                                   int ld_part, float w_spec, float w_met) {
+  pdl_wait();
+  __shared__ float sm[8];
+  const int OUT = S + Mt;
+  const float gs_spec = w_spec * 2.0f / (float)S, gs_met = w_met * 2.0f / (float)Mt;
+  float colsum[kWideJ][2];
+  float2 bj[kWideJ];
+#pragma unroll
+  for (int j = 0; j < kWideJ; ++j) {
+    colsum[j][0] = colsum[j][1] = 0.f;
+    const int c = j * 512 + 2 * (int)threadIdx.x;
+    bj[j] = c < OUT ? __ldg(reinterpret_cast<const float2*>(bias + c)) : make_float2(0.f, 0.f);
+  }
+  float sq_spec = 0.f, sq_met = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+#pragma unroll
+    for (int j = 0; j < kWideJ; ++j) {
+      const int c = j * 512 + 2 * (int)threadIdx.x;
+      if (c >= ld) continue;
+      float g0 = 0.f, g1 = 0.f;
+      if (c < OUT) {
+        const float2 o = *reinterpret_cast<const float2*>(slab + slab_index(r, c, ngroups));
+        const float2 t = c < S ? __ldg(reinterpret_cast<const float2*>(spectrum + r * S + c))
+                               : __ldg(reinterpret_cast<const float2*>(metrics + r * Mt + (c - S)));
+        const float d0 = o.x + bj[j].x - t.x, d1 = o.y + bj[j].y - t.y;
+        const float sq = fmaf(d0, d0, d1 * d1);
+        if (c < S) sq_spec += sq;
+        else sq_met += sq;
+        const float gsc = c < S ? gs_spec : gs_met;
+        g0 = d0 * gsc;
+        g1 = d1 * gsc;
+        colsum[j][0] += g0;
+        colsum[j][1] += g1;
+      }
+      *reinterpret_cast<__half2*>(dout + r * ld + c) = __floats2half2_rn(g0, g1);
+    }
+  }
+  float* prow = part + (size_t)blockIdx.x * ld_part;
+#pragma unroll
+  for (int j = 0; j < kWideJ; ++j) {
+    const int c = j * 512 + 2 * (int)threadIdx.x;
+    if (c < OUT) *reinterpret_cast<float2*>(prow + c) = make_float2(colsum[j][0], colsum[j][1]);
+  }
+  for (int c = OUT + (int)threadIdx.x; c < ld_part - 2; c += blockDim.x) prow[c] = 0.f;
+  const float t0 = block_sum(sq_spec, sm);
+  const float t1 = block_sum(sq_met, sm);
+  if (threadIdx.x == 0) {
+    prow[ld_part - 2] = t0;
+    prow[ld_part - 1] = t1;
+  }
+}
+
 }  // namespace
 
 // =========================================================================================== launchers
@@ -2142,7 +2363,8 @@ void launch_ln_train(__half* xhat, const float* rowstats, const float* gamma, co
   const int grid = grid_for_rows(rows, 8 * 4, 148 * 4);
   if (N == 256) launch_k(ln_train_kernel<1>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
   else if (N == 512) launch_k(ln_train_kernel<2>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
-  else launch_k(ln_train_kernel<4>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
+  else if (N == 1024) launch_k(ln_train_kernel<4>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
+  else launch_k(ln_train_kernel<8>, grid, kThreads, 0, st, xhat, rowstats, gamma, beta, act, rstd, mask, keepbits, (long long)rows, layer, dr);
 }
 void launch_f_out_loss(const float* out, const float* spectrum, const float* metrics, __half* dout, int ld,
                        int64_t rows, int S, int Mt, float* part, float* db_out, float* loss_sums, float inv_gs,
@@ -2170,7 +2392,8 @@ void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const floa
   if (p_in) launch_k(ln_bwd_kernel<1, true>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
   else if (N == 256) launch_k(ln_bwd_kernel<1, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
   else if (N == 512) launch_k(ln_bwd_kernel<2, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
-  else launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
+  else if (N == 1024) launch_k(ln_bwd_kernel<4, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
+  else launch_k(ln_bwd_kernel<8, false>, grid, kThreads, 0, st, da, xhat, rstd, gamma, beta, p_in, keepbits, (long long)rows, keep_scale, part, store_dh);
   ReduceArgs r;
   r.part = part; r.nblocks = grid; r.ld = nq * N; r.nseg = p_in ? 4 : 3;
   r.seg[0] = {dbeta, N, inv_gs};
@@ -2184,6 +2407,65 @@ void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, fl
 }
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st) {
   launch_k(f_dw1_transpose_kernel, 1, 256, 0, st, src, dw1);
+}
+template <bool TRAIN>
+static void launch_f_l1_wide_t(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
+                               __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
+                               int64_t rows, int N, const DropoutArgs& dr, cudaStream_t st) {
+  const int grid = grid_for_rows(rows, 8 * 4, 148 * 4);
+  auto go = [&](auto kern) {
+    launch_k(kern, grid, kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd, mask, keepbits, (long long)rows, dr);
+  };
+  if (N == 256) go(f_l1_wide_kernel<1, TRAIN>);
+  else if (N == 512) go(f_l1_wide_kernel<2, TRAIN>);
+  else if (N == 1024) go(f_l1_wide_kernel<4, TRAIN>);
+  else go(f_l1_wide_kernel<8, TRAIN>);
+}
+void launch_f_l1_wide(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
+                      __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
+                      int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st) {
+  if (dr) {
+    launch_f_l1_wide_t<true>(p, w1, b1, lnw, lnb, xhat, act, rstd, mask, keepbits, rows, N, *dr, st);
+  } else {
+    DropoutArgs none = {};
+    launch_f_l1_wide_t<false>(p, w1, b1, lnw, lnb, nullptr, act, nullptr, nullptr, nullptr, rows, N, none, st);
+  }
+}
+void launch_f_dw1_wide(const __half* dh1, const float* p, int64_t rows, int N, float* part, float* dw1_kmajor,
+                       float* dw1, float inv_gs, cudaStream_t st) {
+  int cap = (int)(((size_t)kPartBlocks * kPartCols) / ((size_t)4 * N));
+  if (cap > 148 * 2) cap = 148 * 2;
+  const int grid = grid_for_rows(rows, (kThreads / (N / 8)) * 8, cap);
+  launch_k(f_dw1_wide_kernel, grid, kThreads, 0, st, dh1, p, (long long)rows, N, part);
+  ReduceArgs r;
+  r.part = part; r.nblocks = grid; r.ld = 4 * N; r.nseg = 1;
+  r.seg[0] = {dw1_kmajor, 4 * N, inv_gs};
+  launch_reduce_partials(r, st);
+  launch_k(f_dw1_transpose_wide_kernel, (N + 255) / 256, 256, 0, st, (const float*)dw1_kmajor, dw1, N);
+}
+void launch_f_dp_wide(const __half* dh1, const float* w1, float* dp, int64_t rows, int N, float scale,
+                      cudaStream_t st) {
+  launch_k(f_dp_wide_kernel, grid_for_rows(rows, 8 * 4, 148 * 4), kThreads, 0, st, dh1, w1, dp, (long long)rows, N / 256,
+           scale);
+}
+void launch_f_unslab(const float* slab, int ngroups, const float* bias, float* out, int64_t rows, int OUT,
+                     cudaStream_t st) {
+  launch_k(f_unslab_kernel, grid_for_rows(rows, 4, 148 * 8), kThreads, 0, st, slab, ngroups, bias, out, (long long)rows,
+           OUT);
+}
+void launch_f_out_loss_slab(const float* slab, int ngroups, const float* bias, const float* spectrum,
+                            const float* metrics, __half* dout, int ld, int64_t rows, int S, int Mt, float* part,
+                            float* db_out, float* loss_sums, float inv_gs, cudaStream_t st, float w_spec, float w_met) {
+  const int OUT = S + Mt, ld_part = (OUT + 2 + 7) / 8 * 8;
+  const int grid = grid_for_rows(rows, 16, kPartBlocks);
+  launch_k(f_out_loss_slab_kernel, grid, kThreads, 0, st, slab, ngroups, bias, spectrum, metrics, dout, ld,
+           (long long)rows, S, Mt, part, ld_part, w_spec, w_met);
+  ReduceArgs r;
+  r.part = part; r.nblocks = grid; r.ld = ld_part; r.nseg = 3;
+  r.seg[0] = {db_out, OUT, inv_gs};
+  r.seg[1] = {nullptr, ld_part - 2 - OUT, 0.f};
+  r.seg[2] = {loss_sums, 2, 1.f};
+  launch_reduce_partials(r, st);
 }
 void launch_f_input_grad_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st) {
   launch_k(f_input_grad_losses_kernel, 1, 32, 0, st, sums, n_spec, n_met, out);

@@ -267,6 +267,23 @@ void launch_ln_bwd(__half* da, const __half* xhat, const float* rstd, const floa
 // dp[r, 0:4] = scale * dh1[r, :] . W1   (input gradient of the first layer; dh1 kept by launch_ln_bwd(store_dh = 1))
 void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, float scale, cudaStream_t st);
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st);
+// ---- widened surrogate (BASELINE config 5): any hidden width N in {256, 512, 1024, 2048}, any even S / Mt with
+// round_up(S + Mt, 64) <= 2560.  dr == nullptr: eval mode (act only).
+void launch_f_l1_wide(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
+                      __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
+                      int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st);
+// dw1[N][4] += inv_gs * dh1^T p (dw1_kmajor: [4][N] scratch, zero on entry)
+void launch_f_dw1_wide(const __half* dh1, const float* p, int64_t rows, int N, float* part, float* dw1_kmajor,
+                       float* dw1, float inv_gs, cudaStream_t st);
+void launch_f_dp_wide(const __half* dh1, const float* w1, float* dp, int64_t rows, int N, float scale,
+                      cudaStream_t st);
+// fp32 output-layer accumulators stored as [128 x 256] slabs (see slab_index in elementwise.cu)
+void launch_f_unslab(const float* slab, int ngroups, const float* bias, float* out, int64_t rows, int OUT,
+                     cudaStream_t st);
+void launch_f_out_loss_slab(const float* slab, int ngroups, const float* bias, const float* spectrum,
+                            const float* metrics, __half* dout, int ld, int64_t rows, int S, int Mt, float* part,
+                            float* db_out, float* loss_sums, float inv_gs, cudaStream_t st, float w_spec = 1.f,
+                            float w_met = 1.f);
 void launch_f_input_grad_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 

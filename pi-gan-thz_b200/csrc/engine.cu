@@ -96,6 +96,12 @@ struct PiganEngine {
   FwdLayout fl;
   int64_t max_batch, bp;  // bp = max_batch rounded up to 128: row offset of the fake half in stacked tensors
   size_t ws_bytes;
+  // full = the reference widths: every entry point.  Otherwise the engine serves the surrogate's paths only
+  // (forward, VJP, training step) at the widened dims of BASELINE config 5 - see check_dims
+  bool full = true;
+  int dout_ld = 320;      // output-layer gradient operand: S + Mt columns padded to a multiple of 64
+  int out_groups = 2;     // 256-column groups of the output layer (widened path: fp32 accumulator slabs)
+  float* f_slab = nullptr;   // widened path: [bp / 128][out_groups][128][256] fp32 output-layer accumulators
   bool f_loaded = false;
   const float* f_params = nullptr;
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
@@ -129,29 +135,34 @@ struct PiganEngine {
   float *f_bias_out;                   // [288] zero padded
   double* sums;
 
-  PiganEngine(const PiganDims& dims) : d(dims), gl(dims), dl(dims), fl(dims) {}
+  PiganEngine(const PiganDims& dims) : d(dims), gl(dims), dl(dims), fl(dims) {
+    full = dims_are_default(dims);
+    dout_ld = (int)((fl.OUT + 63) / 64 * 64);
+    out_groups = (fl.OUT + 255) / 256;
+  }
 
   size_t carve(void* ws) {
     Carver c(ws);
     const int64_t B = bp;
+    const int64_t Bg = full ? bp : 0;   // generator / discriminator activations: not on the widened (surrogate-only) path
     const int H1 = gl.H1, H2 = gl.H2, D1 = dl.H1, D2 = dl.H2;
     xc_own = c.take<__half>(B * kKp);
     xc = xc_own;
     tail_f = c.take<__half>(B * 64);
-    g_h1 = c.take<__half>(B * H1);
-    g_a1 = c.take<__half>(B * H1);
-    g_h2 = c.take<__half>(B * H2);
-    d_z1 = c.take<__half>(2 * B * D1);
-    d_z2 = c.take<__half>(2 * B * D2);
-    d_dh2 = c.take<__half>(2 * B * D2);
-    d_dh1 = c.take<__half>(2 * B * D1);
+    g_h1 = c.take<__half>(Bg * H1);
+    g_a1 = c.take<__half>(Bg * H1);
+    g_h2 = c.take<__half>(Bg * H2);
+    d_z1 = c.take<__half>(2 * Bg * D1);
+    d_z2 = c.take<__half>(2 * Bg * D2);
+    d_dh2 = c.take<__half>(2 * Bg * D2);
+    d_dh1 = c.take<__half>(2 * Bg * D1);
     f_a1 = c.take<__half>(B * fl.H[0]);
     f_a2 = c.take<__half>(B * fl.H[1]);
     f_a3 = c.take<__half>(B * fl.H[2]);
     f_a4 = c.take<__half>(B * fl.H[3]);
     f_a5 = c.take<__half>(B * fl.H[4]);
-    g_dy2 = c.take<__half>(B * H2);
-    g_da1 = c.take<__half>(B * H1);
+    g_dy2 = c.take<__half>(Bg * H2);
+    g_da1 = c.take<__half>(Bg * H1);
     g_w1h = c.take<__half>((size_t)H1 * kKp);
     g_w2h = c.take<__half>((size_t)H2 * H1);
     g_w2th = c.take<__half>((size_t)H1 * H2);
@@ -165,7 +176,7 @@ struct PiganEngine {
       f_wh[i] = c.take<__half>((size_t)out * in);
       in = out;
     }
-    d_mask1 = c.take<uint32_t>((size_t)2 * B * (D1 / 32));
+    d_mask1 = c.take<uint32_t>((size_t)2 * Bg * (D1 / 32));
     dw_part = c.take<float>((size_t)kDwPartSlabs * kBlockM * 256);
     partials = c.take<float>((size_t)kPartBlocks * kPartCols);
     dpre = c.take<float>(B * 4);
@@ -189,8 +200,9 @@ struct PiganEngine {
     bn_bwd_sums = zero_blk ? zero_blk + 32 + 2 * H1 + 2 * H2 : nullptr;
     mean1 = c.take<float>(H1); rstd1 = c.take<float>(H1); scale1 = c.take<float>(H1); bias1 = c.take<float>(H1);
     mean2 = c.take<float>(H2); rstd2 = c.take<float>(H2); scale2 = c.take<float>(H2); bias2 = c.take<float>(H2);
-    f_bias_out = c.take<float>(288);
+    f_bias_out = c.take<float>(dout_ld > 288 ? dout_ld : 288);
     head_img = c.take<float>(kHeadImgFloats);
+    f_slab = full ? nullptr : c.take<float>((size_t)(B / kBlockM) * out_groups * kBlockM * 256);
     return (c.off + 255) & ~size_t(255);
   }
 };
@@ -213,11 +225,33 @@ void prof_mark(PiganEngine* e, const char* name, cudaStream_t st) {
 }
 #define PM(name) prof_mark(e, name, st)
 
+// Widened dims (BASELINE config 5: hidden 2048, 2048-point spectra; the widths of enhanced_forward_model.py:42-49):
+// the surrogate's forward, VJP and training step run at any hidden width of 256/512/1024/2048 and any even S / Mt
+// with round_up(S + Mt, 64) <= 2560, built from the plain store GEMMs + the streaming LayerNorm kernels (no fused
+// LayerNorm / loss epilogues: at these widths the GEMMs are 126 MFLOP per sample and dominate).  The generator /
+// discriminator / PI-GAN step / search entry points stay at the reference widths (need_full).
+bool surrogate_dims_ok(const PiganDims& d) {
+  if (d.param_dim != 4 || d.spectrum_dim < 2 || d.metrics_dim < 2 || d.spectrum_dim % 2 || d.metrics_dim % 2) return false;
+  if ((d.spectrum_dim + d.metrics_dim + 63) / 64 * 64 > 2560) return false;
+  for (int i = 0; i < 5; ++i) {
+    const int h = d.f_hidden[i];
+    if (h != 256 && h != 512 && h != 1024 && h != 2048) return false;
+  }
+  return true;
+}
 int check_dims(const PiganDims& d) {
-  if (!dims_are_default(d))
+  if (!dims_are_default(d) && !surrogate_dims_ok(d))
     return fail(PIGAN_ERR_UNSUPPORTED,
-                "this build implements the reference widths only (S=250, P=4, Mt=8, G 512/256, D 512/256, "
-                "F 256/512/1024/512/256)");
+                "dimensions: the full path implements the reference widths (S=250, P=4, Mt=8, G 512/256, D 512/256, "
+                "F 256/512/1024/512/256); the surrogate-only path takes P=4, even S / Mt with S + Mt <= 2560 and "
+                "hidden widths of 256/512/1024/2048");
+  return PIGAN_OK;
+}
+int need_full(const PiganEngine* e) {
+  if (e && !e->full)
+    return fail(PIGAN_ERR_UNSUPPORTED,
+                "this engine was created with widened dimensions: only the surrogate's entry points "
+                "(pigan_forward_model_forward / _vjp / _input_grad, pigan_fwd_train_step) run at those");
   return PIGAN_OK;
 }
 
@@ -636,9 +670,48 @@ struct FOutOpts {
   int f1_idx, f2_idx;
 };
 int f_out_layer(PiganEngine* e, const __half* a5, int64_t n, const FOutOpts& o, cudaStream_t st);
+// Widened output layer (any S + Mt): the fp32 accumulators leave tensor memory as [128 x 256] slabs in e->f_slab
+// (TMA stores of EpiWeightGradPartial, here on a TN product); the consumers add the bias in fp32
+// (f_unslab_kernel / f_out_loss_slab_kernel).  Weights w6h: fp16 [OUT, H5] - rows beyond OUT are zero-filled by TMA.
+int f_out_slab(PiganEngine* e, const __half* a5, int64_t n, const __half* w6h, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
+  using Epi = EpiWeightGradPartial<CfgS>;
+  Epi::Params ep;
+  const int m_tiles = ceil_div((int)n, kBlockM);
+  PIGAN_TRY(make_tmap_f32_2d(&ep.part, e->f_slab, 256, (uint64_t)m_tiles * e->out_groups * kBlockM, 256, kBlockM));
+  PM("f_out_gemm");
+  return run_tn<CfgS, Epi>(ep, a5, n, L.H[4], L.H[4], w6h, L.OUT, L.H[4], st);
+}
+// Eval-mode surrogate at widened dims: first layer (streaming), four Linear GEMMs with LayerNorm row partials from
+// the epilogue + the in-place LayerNorm/LeakyReLU pass, output layer through the slabs.
+int f_forward_wide(PiganEngine* e, const float* p_norm, int64_t n, float* out_full, cudaStream_t st) {
+  const FwdLayout& L = e->fl;
+  const float* fp = e->f_params;
+  PM("f_l1");
+  launch_f_l1_wide(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], nullptr, e->f_a1, nullptr, nullptr,
+                   nullptr, n, L.H[0], nullptr, st);
+  __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
+  for (int i = 1; i < 5; ++i) {
+    PM("f_hidden_gemm");
+    PIGAN_TRY((linear_store<true, false, true>(acts[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], acts[i],
+                                               e->f_rowstats, st)));
+    PM("f_ln_apply");
+    launch_ln_lrelu_apply(acts[i], e->f_rowstats, L.H[i] / 256, fp + L.ln_w[i], fp + L.ln_b[i], n, L.H[i], st);
+  }
+  PIGAN_TRY(f_out_slab(e, e->f_a5, n, e->f_wh[5], st));
+  PM("f_out_unslab");
+  launch_f_unslab(e->f_slab, e->out_groups, fp + L.b[5], out_full, n, L.OUT, st);
+  PIGAN_CUDA_OK(cudaGetLastError());
+  return PIGAN_OK;
+}
 int f_forward(PiganEngine* e, const float* p_norm, int64_t n, const FOutOpts& o, cudaStream_t st,
               bool have_a1 = false) {
   if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
+  if (!e->full) {
+    if (o.out_full == nullptr || o.sums != nullptr || o.row_err != nullptr || o.target_mode != 0 || have_a1)
+      return need_full(e);
+    return f_forward_wide(e, p_norm, n, o.out_full, st);
+  }
   const FwdLayout& L = e->fl;
   const float* fp = e->f_params;
   PM("f_l1");
@@ -949,6 +1022,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
 
 int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
   PIGAN_CHECK_ARG(e != nullptr && a != nullptr);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG(a->batch >= 2 && a->batch <= e->max_batch && a->global_batch >= a->batch);
   PIGAN_CHECK_ARG(a->metrics_norm != nullptr);
   PIGAN_CHECK_ARG(a->spectrum_operand ? (a->spectrum_center != nullptr &&
@@ -973,7 +1047,7 @@ int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
 extern "C" size_t pigan_engine_workspace_bytes(const PiganDims* dims, int64_t max_batch) {
   PiganDims d;
   if (dims) d = *dims; else pigan_default_dims(&d);
-  if (!dims_are_default(d) || max_batch < 1) return 0;
+  if ((!dims_are_default(d) && !surrogate_dims_ok(d)) || max_batch < 1) return 0;
   PiganEngine e(d);
   e.max_batch = max_batch;
   e.bp = round_up(max_batch, 128);
@@ -1031,7 +1105,7 @@ extern "C" int pigan_engine_load_forward_model(PiganEngine* e, const float* fp, 
     launch_cast_pad(fp + L.w[i], in, in, e->f_wh[i], in, out, st);
     in = out;
   }
-  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
+  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, e->dout_ld > 288 ? e->dout_ld : 288, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   e->f_params = fp;
   e->f_loaded = true;
@@ -1061,6 +1135,7 @@ extern "C" int pigan_engine_set_spectrum_center(PiganEngine* e, const float* cen
 extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* bn, int64_t* nbt, const float* x,
                                        int64_t n, int32_t training, float* out, void* stream) {
   PIGAN_CHECK_ARG(e && gp && x && out && n >= 1 && n <= e->max_batch);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG(training ? n >= 2 : bn != nullptr);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GenLayout& G = e->gl;
@@ -1091,6 +1166,7 @@ extern "C" int pigan_generator_forward(PiganEngine* e, const float* gp, float* b
 extern "C" int pigan_discriminator_forward(PiganEngine* e, const float* dp, const float* x, const float* params,
                                            int64_t n, float* out_prob, void* stream) {
   PIGAN_CHECK_ARG(e && dp && x && params && out_prob && n >= 1 && n <= e->max_batch);
+  PIGAN_TRY(need_full(e));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PIGAN_TRY(prep_spectrum(e, x, params, n, st));
   PIGAN_TRY(pack_discriminator(e, dp, false, st));
@@ -1115,6 +1191,7 @@ extern "C" int pigan_discriminator_forward(PiganEngine* e, const float* dp, cons
 extern "C" int pigan_generator_backward(PiganEngine* e, const float* gp, const float* x, int64_t n, const float* grad_p,
                                         float grad_scale, float* g_grads, void* stream) {
   PIGAN_CHECK_ARG(e && gp && x && grad_p && g_grads && n >= 2 && n <= e->max_batch && grad_scale > 0.f);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(g_grads) & 15u) == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GenLayout& G = e->gl;
@@ -1170,6 +1247,7 @@ extern "C" int pigan_discriminator_backward(PiganEngine* e, const float* dp, con
                                             int64_t n, const float* grad_out, float grad_scale, float* d_grads,
                                             float* grad_params, void* stream) {
   PIGAN_CHECK_ARG(e && dp && x && params && grad_out && d_grads && n >= 1 && n <= e->max_batch && grad_scale > 0.f);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_grads) & 15u) == 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DiscLayout& D = e->dl;
@@ -1299,6 +1377,7 @@ extern "C" int pigan_score_candidates(PiganEngine* e, const float* gp, const flo
                                       float* out_p, int32_t* out_viol, float* out_err, float* out_cons,
                                       void* stream) {
   PIGAN_CHECK_ARG(e && gp && bn && n >= 1 && n <= e->max_batch);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG((spectra != nullptr) != (target != nullptr && noise != nullptr));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GenLayout& G = e->gl;
@@ -1332,6 +1411,7 @@ extern "C" int pigan_validate_model(PiganEngine* e, const float* gp, const float
                                     const float* noise, float sigma, int64_t n, float* out_p, float* out_cycle_error,
                                     float* out_stability, float* out_plausibility, void* stream) {
   PIGAN_CHECK_ARG(e && gp && bn && spectra && noise && n >= 1 && n <= e->max_batch);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG(out_cycle_error && out_stability && out_plausibility);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GenLayout& G = e->gl;
@@ -1364,7 +1444,6 @@ extern "C" int pigan_validate_model(PiganEngine* e, const float* gp, const float
 // Activations a_i reuse the engine's f_a1..f_a5 and packed-weight buffers, so the frozen-surrogate state of the
 // engine is invalidated: call pigan_engine_load_forward_model again before PI-GAN steps or scoring.
 namespace {
-constexpr int kDoutLd = 320;   // output-layer gradient operand: S + Mt = 258 columns padded to a multiple of 64
 struct FTrainWs {
   __half* xhat[5];
   float* rstd[5];
@@ -1379,9 +1458,10 @@ struct FTrainWs {
   float* loss_sums;   // [2] (used when the caller passes none)
   uint8_t* zero_from; // dw1_tmp .. loss_sums are cleared every step
   size_t zero_bytes;
-  size_t carve(void* base, const FwdLayout& L, int64_t B) {
+  size_t carve(void* base, const FwdLayout& L, int64_t B, bool wide = false) {
     Carver c(base);
     const int64_t Bp = round_up(B, 128);
+    const int kDoutLd = (int)round_up(L.OUT, 64);   // 320 at the reference widths
     int wmax = 0;
     for (int i = 0; i < 5; ++i) {
       xhat[i] = c.take<__half>((size_t)Bp * L.H[i]);
@@ -1389,7 +1469,7 @@ struct FTrainWs {
       keepbits[i] = c.take<uint8_t>((size_t)Bp * (L.H[i] / 8));
       wmax = L.H[i] > wmax ? L.H[i] : wmax;
     }
-    out32 = c.take<float>((size_t)Bp * L.OUT);
+    out32 = c.take<float>(wide ? 0 : (size_t)Bp * L.OUT);   // widened path: the engine's accumulator slabs instead
     dout = c.take<__half>((size_t)Bp * kDoutLd);
     dbuf[0] = c.take<__half>((size_t)Bp * wmax);
     dbuf[1] = c.take<__half>((size_t)Bp * wmax);
@@ -1418,6 +1498,8 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
                     const FwdRunOpts& opt = FwdRunOpts()) {
   const FwdLayout& L = e->fl;
   const int64_t n = a.batch;
+  const int kDoutLd = e->dout_ld;
+  const bool wide = !e->full;   // widened dims: generic first-layer / loss kernels, output layer through the slabs
   float* fp = a.f_params;
   float* gr = opt.input_grad ? w.grads_scratch : a.f_grads;
   float* loss_sums = a.loss_sums ? a.loss_sums : w.loss_sums;
@@ -1462,7 +1544,7 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
     launch_cast_pad(fp + L.w[i], in, in, e->f_wh[i], in, out, st);
     launch_transpose_cast(fp + L.w[i], out, in, in, w.wth[i], i < 5 ? out : kDoutLd, st);
   }
-  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, 288, st);
+  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, kDoutLd > 288 ? kDoutLd : 288, st);
   // ---- forward (train mode)
   __half* act[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   size_t moff[5];
@@ -1473,8 +1555,12 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   }
   auto mask = [&](int i) { return a.mask_dump ? a.mask_dump + moff[i] : nullptr; };
   PM("f_l1");
-  launch_f_l1_train(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
-                    w.rstd[0], mask(0), w.keepbits[0], n, dr, st);
+  if (wide)
+    launch_f_l1_wide(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
+                     w.rstd[0], mask(0), w.keepbits[0], n, L.H[0], &dr, st);
+  else
+    launch_f_l1_train(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
+                      w.rstd[0], mask(0), w.keepbits[0], n, dr, st);
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
     PIGAN_TRY((linear_store<true, false, true>(act[i - 1], n, L.H[i - 1], e->f_wh[i], L.H[i], fp + L.b[i], w.xhat[i],
@@ -1484,11 +1570,18 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
                     n, L.H[i], i, dr, st);
   }
   PM("f_out_gemm");
-  FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, w.out32, nullptr, 0, 1};
-  PIGAN_TRY(f_out_layer(e, act[4], n, fo, st));
+  if (wide) {
+    if (opt.upstream == nullptr) PIGAN_TRY(f_out_slab(e, act[4], n, e->f_wh[5], st));   // a VJP does not need the output
+  } else {
+    FOutOpts fo{0, nullptr, nullptr, nullptr, nullptr, 0.f, w.out32, nullptr, 0, 1};
+    PIGAN_TRY(f_out_layer(e, act[4], n, fo, st));
+  }
   PM("f_out_loss");
   if (opt.upstream != nullptr)
     launch_f_upstream_cast(opt.upstream, L.OUT, w.dout, kDoutLd, n, (float)a.global_batch, st);
+  else if (wide)
+    launch_f_out_loss_slab(e->f_slab, e->out_groups, fp + L.b[5], a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S,
+                           L.Mt, e->partials, gr + L.b[5], loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
   else
     launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
                       loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
@@ -1503,12 +1596,20 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   PIGAN_TRY((linear_store<false, false, false>(w.dout, n, kDoutLd, w.wth[5], L.H[4], nullptr, d, nullptr, st)));
   for (int i = 4; i >= 0; --i) {
     PM("f_ln_bwd");
-    launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], i == 0 ? a.params_norm : nullptr,
+    // (widened dims: the first layer goes through the generic kernel too - dh stays in place - and its thin
+    // weight / input gradients come from their own streaming kernels)
+    launch_ln_bwd(d, w.xhat[i], w.rstd[i], fp + L.ln_w[i], fp + L.ln_b[i], (i == 0 && !wide) ? a.params_norm : nullptr,
                   w.keepbits[i], n, L.H[i], dr.keep_scale, e->partials, gr + L.ln_w[i], gr + L.ln_b[i], gr + L.b[i],
                   w.dw1_tmp, inv_gs, st, (i == 0 && opt.input_grad) ? 1 : 0);
     if (i == 0) {
-      if (opt.input_grad) launch_f_dp(d, fp + L.w[0], opt.dp_out, n, inv_gs, st);
-      else launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
+      if (wide) {
+        if (opt.input_grad) launch_f_dp_wide(d, fp + L.w[0], opt.dp_out, n, L.H[0], inv_gs, st);
+        else launch_f_dw1_wide(d, a.params_norm, n, L.H[0], e->partials, w.dw1_tmp, gr + L.w[0], inv_gs, st);
+      } else if (opt.input_grad) {
+        launch_f_dp(d, fp + L.w[0], opt.dp_out, n, inv_gs, st);
+      } else {
+        launch_f_dw1_transpose(w.dw1_tmp, gr + L.w[0], st);
+      }
       break;
     }
     PM("f_wgrad_gemm");
@@ -1535,7 +1636,7 @@ int check_fwd_train_args(const PiganEngine* e, const PiganFwdTrainArgs* a, const
   PIGAN_CHECK_ARG(a->step >= 1 && a->dropout_p >= 0.f && a->dropout_p < 1.f);
   PIGAN_CHECK_ARG(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->max_norm > 0.f);
   FTrainWs w;
-  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch, !e->full);
   if (ws_bytes < need) return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", ws_bytes, need);
   return PIGAN_OK;
 }
@@ -1549,10 +1650,10 @@ extern "C" int pigan_forward_model_input_grad(PiganEngine* e, const float* f_par
   PIGAN_CHECK_ARG(n >= 1 && n <= e->max_batch && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
   PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dp) & 15u) == 0);
   FTrainWs w;
-  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch, !e->full);
   if (workspace_bytes < need)
     return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", workspace_bytes, need);
-  w.carve(workspace, e->fl, e->max_batch);
+  w.carve(workspace, e->fl, e->max_batch, !e->full);
   PiganFwdTrainArgs a;
   memset(&a, 0, sizeof(a));
   a.params_norm = params_norm; a.spectrum = spectrum; a.metrics_norm = metrics_norm;
@@ -1581,10 +1682,10 @@ extern "C" int pigan_forward_model_vjp(PiganEngine* e, const float* f_params, co
   PIGAN_CHECK_ARG(n >= 1 && n <= e->max_batch && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
   PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(out_dp) & 15u) == 0);
   FTrainWs w;
-  const size_t need = w.carve(nullptr, e->fl, e->max_batch);
+  const size_t need = w.carve(nullptr, e->fl, e->max_batch, !e->full);
   if (workspace_bytes < need)
     return fail(PIGAN_ERR_WORKSPACE, "surrogate-training workspace too small: %zu < %zu", workspace_bytes, need);
-  w.carve(workspace, e->fl, e->max_batch);
+  w.carve(workspace, e->fl, e->max_batch, !e->full);
   PiganFwdTrainArgs a;
   memset(&a, 0, sizeof(a));
   a.params_norm = params_norm;
@@ -1604,7 +1705,7 @@ extern "C" int pigan_forward_model_vjp(PiganEngine* e, const float* f_params, co
 extern "C" size_t pigan_fwd_train_workspace_bytes(const PiganEngine* e) {
   if (!e) return 0;
   FTrainWs w;
-  return w.carve(nullptr, e->fl, e->max_batch);
+  return w.carve(nullptr, e->fl, e->max_batch, !e->full);
 }
 
 extern "C" int pigan_fwd_train_step_phase(PiganEngine* e, const PiganFwdTrainArgs* a, int32_t phase, void* workspace,
@@ -1612,7 +1713,7 @@ extern "C" int pigan_fwd_train_step_phase(PiganEngine* e, const PiganFwdTrainArg
   PIGAN_TRY(check_fwd_train_args(e, a, workspace, workspace_bytes));
   if (phase < 0 || phase > 1) return fail(PIGAN_ERR_INVALID, "surrogate-training phase %d out of range", phase);
   FTrainWs w;
-  w.carve(workspace, e->fl, e->max_batch);
+  w.carve(workspace, e->fl, e->max_batch, !e->full);
   return fwd_train_phase(e, *a, phase, w, static_cast<cudaStream_t>(stream));
 }
 
@@ -1620,7 +1721,7 @@ extern "C" int pigan_fwd_train_step(PiganEngine* e, const PiganFwdTrainArgs* a, 
                                     size_t workspace_bytes, void* stream) {
   PIGAN_TRY(check_fwd_train_args(e, a, workspace, workspace_bytes));
   FTrainWs w;
-  w.carve(workspace, e->fl, e->max_batch);
+  w.carve(workspace, e->fl, e->max_batch, !e->full);
   for (int ph = 0; ph <= 1; ++ph) PIGAN_TRY(fwd_train_phase(e, *a, ph, w, static_cast<cudaStream_t>(stream)));
   return PIGAN_OK;
 }
@@ -1668,6 +1769,7 @@ extern "C" int pigan_inverse_design_search(PiganEngine* e, const float* gp, cons
                                            float* noise_dump, void* workspace, size_t workspace_bytes,
                                            void* stream) {
   PIGAN_CHECK_ARG(e && gp && bn && target && out_scores && out_indices && out_params && workspace);
+  PIGAN_TRY(need_full(e));
   PIGAN_CHECK_ARG(k >= 1 && k <= 4096 && count >= 0 && first_candidate >= 0);
   PIGAN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0);
   if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");

@@ -28,12 +28,12 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 class Engine:
     """One engine per (process, device).  ``max_batch`` bounds the rows of any later call."""
 
-    def __init__(self, max_batch: int, device: Optional[torch.device] = None):
+    def __init__(self, max_batch: int, device: Optional[torch.device] = None, dims: Optional[native.PiganDims] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("pigan_b200: no CUDA device — the B200 path has no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.max_batch = int(max_batch)
-        self.dims = native.default_dims()
+        self.dims = dims if dims is not None else native.default_dims()
         with torch.cuda.device(self.device):
             nbytes = lib.pigan_engine_workspace_bytes(C.byref(self.dims), self.max_batch)
             if nbytes == 0:
@@ -290,18 +290,19 @@ def launch_count() -> int:
     return int(lib.pigan_launch_count())
 
 
-_ENGINES: Dict[int, Engine] = {}
+_ENGINES: Dict[tuple, Engine] = {}
 
 
-def get_engine(device, min_batch: int) -> Engine:
-    """Process-wide engine per device, grown (re-created) when a larger batch shows up."""
+def get_engine(device, min_batch: int, dims: Optional[native.PiganDims] = None) -> Engine:
+    """Process-wide engine per (device, dims), grown (re-created) when a larger batch shows up."""
     dev = torch.device(device)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    eng = _ENGINES.get(idx)
+    key = (idx, native.dims_key(dims) if dims is not None else None)
+    eng = _ENGINES.get(key)
     if eng is None or eng.max_batch < min_batch:
         cap = max(int(min_batch), 1024)
         if eng is not None:
             cap = max(cap, 2 * eng.max_batch)
-        eng = Engine(cap, torch.device("cuda", idx))
-        _ENGINES[idx] = eng
+        eng = Engine(cap, torch.device("cuda", idx), dims)
+        _ENGINES[key] = eng
     return eng

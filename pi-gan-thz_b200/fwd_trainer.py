@@ -31,7 +31,10 @@ class ForwardTrainer:
             raise RuntimeError("ForwardTrainer needs a CUDA device — the B200 path has no CPU fallback")
         self.f = forward_model.to(self.device)
         self.fs = _flat.net_state(forward_model, "forward_model")
-        self.engine = engine if engine is not None else _engine.Engine(max_batch, self.device)
+        if engine is None:
+            dims = forward_model.engine_dims() if hasattr(forward_model, "engine_dims") else None
+            engine = _engine.Engine(max_batch, self.device, dims)   # widened dims: a surrogate-only engine
+        self.engine = engine
         fp = self.fs.params.tensor()
         self.grads, self.m, self.v = (torch.zeros_like(fp) for _ in range(3))
         self.losses = torch.zeros(3, device=self.device, dtype=torch.float32)

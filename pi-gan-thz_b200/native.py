@@ -180,3 +180,23 @@ def default_dims() -> PiganDims:
     d = PiganDims()
     lib.pigan_default_dims(C.byref(d))
     return d
+
+
+def make_dims(spectrum_dim=None, metrics_dim=None, f_hidden=None, g_hidden=None, d_hidden=None) -> PiganDims:
+    """The reference dims with some widths replaced (BASELINE config 5: hidden 2048, 2048-point spectra).  Engines
+    with non-reference dims serve the surrogate's entry points only (include/pigan_b200.h)."""
+    d = default_dims()
+    if spectrum_dim is not None:
+        d.spectrum_dim = int(spectrum_dim)
+    if metrics_dim is not None:
+        d.metrics_dim = int(metrics_dim)
+    for name, val, n in (("f_hidden", f_hidden, 5), ("g_hidden", g_hidden, 2), ("d_hidden", d_hidden, 2)):
+        if val is not None:
+            if len(val) != n:
+                raise ValueError(f"{name} needs {n} widths")
+            setattr(d, name, (_i32 * n)(*[int(v) for v in val]))
+    return d
+
+
+def dims_key(d: PiganDims) -> tuple:
+    return (d.spectrum_dim, d.param_dim, d.metrics_dim, tuple(d.g_hidden), tuple(d.d_hidden), tuple(d.f_hidden))
