@@ -129,6 +129,51 @@ def cpu_pretrain_baseline(batch: int, budget_s: float, threads: int):
     return batch * n / el, n, el
 
 
+def cpu_wide_pretrain_baseline(batch: int, budget_s: float, threads: int, max_steps: int = 50):
+    """The same loop body (oracle/models.py: pretrain_step, width-agnostic) at the BASELINE config-5 widths on the
+    host cores: (samples/s, steps, seconds)."""
+    import numpy as np
+    from oracle import models as O
+    torch.set_num_threads(threads)
+    f_sd = O.init_forward_model(4, WIDE_S, WIDE_MT, WIDE_HIDDEN, gen=torch.Generator().manual_seed(3))
+    names = [f"model.{i}.{s}" for i in sorted(O.F_LINEAR + O.F_NORM) for s in ("weight", "bias")]
+    opt = O.Adam(names, betas=(0.9, 0.999))
+    g = torch.Generator().manual_seed(4)
+    pnorm = torch.rand(batch, 4, generator=g) * 2 - 1
+    spec = -3.0 * torch.rand(batch, WIDE_S, generator=g)
+    mnorm = torch.rand(batch, WIDE_MT, generator=g)
+    rng = np.random.Generator(np.random.PCG64(5))
+    masks = [torch.from_numpy((rng.random((batch, h)) >= 0.2).astype(np.float32)) for h in WIDE_HIDDEN]
+    O.pretrain_step(f_sd, opt, pnorm, spec, mnorm, 1e-3, masks)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.pretrain_step(f_sd, opt, pnorm, spec, mnorm, 1e-3, masks)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= max_steps:
+            break
+    return batch * n / el, n, el
+
+
+def run_reference_wide(args):
+    """--impl reference --config wide: the oracle port of the surrogate's training loop body at the config-5 widths."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 1024
+    v, n, el = cpu_wide_pretrain_baseline(sample, 1e9, cores, max_steps=max(1, min(args.steps, 10)))
+    out = {"impl": "reference", "metric": "widened forward-surrogate train samples/s", "value": v, "unit": "samples/s",
+           "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": el / n * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "forward-surrogate training step at the BASELINE config-5 widths", "sample_batch": sample},
+           "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                            "sample": f"{n} steps of batch {sample} (oracle/models.py pretrain_step at 2048-wide layers, "
+                                      f"fp32, torch CPU)"},
+           "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
 def cpu_train_baseline(batch: int, budget_s: float, threads: int):
     """The oracle port of the reference train step (oracle/models.py, pinned to the reference by tests/golden)
     on the host cores: returns (samples/s, steps timed)."""
@@ -208,6 +253,177 @@ def bind_to_gpu_numa_node(device_index: int):
     except Exception:
         pass
     return 0
+
+
+# ---------------------------------------------------------------------------------------------- widened surrogate
+WIDE_S, WIDE_MT, WIDE_HIDDEN = 2048, 8, (2048, 2048, 2048, 2048, 2048)   # BASELINE config 5 widths
+
+
+def wide_flop_per_sample(S=WIDE_S, Mt=WIDE_MT, hidden=WIDE_HIDDEN) -> int:
+    """Forward + dX + dW of the Linear layers (MACs x 2); the first layer has no dX."""
+    dims = [4, *hidden, S + Mt]
+    macs = [dims[i] * dims[i + 1] for i in range(6)]
+    return 2 * (3 * sum(macs) - macs[0])
+
+
+def wide_surrogate_block(dev, world, rank, B, K, W, peaks, barrier, with_e2e: bool):
+    """Training step of the surrogate at the config-5 widths (4 -> 2048 x 5 -> 2048 + 8) on a surrogate-only engine:
+    replicas + NCCL all-reduce of the 84 MB gradient under data parallelism (fwd_trainer.ForwardTrainer)."""
+    import torch.distributed as dist
+    from core.models.forward_model import ForwardModel
+    from pigan_b200 import engine as E
+    from pigan_b200.fwd_trainer import ForwardTrainer
+    torch.manual_seed(7)
+    Fw = ForwardModel(4, WIDE_S, WIDE_MT, hidden=WIDE_HIDDEN)
+    ftr = ForwardTrainer(Fw, dev, max_batch=B)
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    NS = 2   # 2 x 537 MB of spectra > 126 MB L2
+    sets = [(torch.rand(B, 4, device=dev, generator=g) * 2 - 1,
+             -3.0 * torch.rand(B, WIDE_S, device=dev, generator=g),
+             torch.rand(B, WIDE_MT, device=dev, generator=g)) for _ in range(NS)]
+    for i in range(W):
+        ftr.step(*sets[i % NS], 1e-3)
+    barrier()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        ftr.step(*sets[i % NS], 1e-3)
+    e1.record()
+    barrier()
+    launches = E.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    # the hidden-layer GEMMs (forward, dX, dW of the four 2048 x 2048 layers) timed on their own stream sections
+    ftr.engine.profile_begin(["f_hidden_gemm", "f_dgrad_gemm", "f_wgrad_gemm", "f_out_gemm"])
+    for i in range(K):
+        ftr.step(*sets[i % NS], 1e-3)
+    barrier()
+    prof = ftr.engine.profile_end()
+    gemm_ms = sum(v[1] for v in prof.values()) / K
+    hid_cnt, hid_ms = prof.get("f_hidden_gemm", (0, 0.0))
+    flop = wide_flop_per_sample()
+    tfl = B * flop / (ms * 1e-3) / 1e12
+    info = {"metric": "widened forward-surrogate train samples/s", "value": B * world / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "steps": K,
+            "widths": {"spectrum_dim": WIDE_S, "metrics_dim": WIDE_MT, "hidden": list(WIDE_HIDDEN)},
+            "params": int(ftr.grads.numel()), "gradient_exchange": "none (one GPU)" if world == 1 else
+            f"NCCL all-reduce of {ftr.grads.numel() * 4 / 1e6:.0f} MB per step",
+            "flop_per_sample": flop, "gpu_launches_per_step": launches / K,
+            "step_roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tflops"], "unit": "TFLOP/s per GPU",
+                              "frac": tfl / peaks["tflops"], "frac_of_burst_peak": tfl / peaks["tflops_burst"]},
+            "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms if ms else None,
+            "loss_last_step": float(ftr.losses[0])}
+    if hid_cnt:
+        ach = 2 * 2048 * 2048 * B / (hid_ms / hid_cnt * 1e-3) / 1e12
+        info["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiStore, row statistics> (forward hidden "
+                            "layers 2048 -> 2048: Linear + bias + LayerNorm row partials)", "achieved": ach,
+                            "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                            "frac_of_burst_peak": ach / peaks["tflops_burst"], "traffic": None,
+                            "launches_timed": hid_cnt, "share_of_step": hid_ms / K / ms}
+    if with_e2e:
+        # the same step fed from pinned host tensors (H2D of params / spectra / metrics inside the timed region)
+        host = [tuple(x.cpu().pin_memory() for x in s_) for s_ in sets]
+        devb = [tuple(torch.empty_like(x) for x in s_) for s_ in sets]
+        copy_stream = torch.cuda.Stream(device=dev)
+        h2d_bytes = sum(x.numel() * 4 for x in host[0])
+
+        def h2d(i):
+            with torch.cuda.stream(copy_stream):
+                for d_, h_ in zip(devb[i % NS], host[i % NS]):
+                    d_.copy_(h_, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
+
+        KE = max(3, K // 2)
+        for rep_ in range(2):
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            ev = h2d(0)
+            last = None
+            for i in range(KE):
+                torch.cuda.current_stream().wait_event(ev)
+                out = ftr.step(*devb[i % NS], 1e-3)
+                done = torch.cuda.Event()
+                done.record()
+                if i + 1 < KE:
+                    if NS == 2 and i >= 1:
+                        copy_stream.wait_event(prev_done)   # buffer (i+1) % 2 was read by step i-1
+                    ev = h2d(i + 1)
+                prev_done = done
+                last = out.tolist()     # D2H of the three losses every step
+            x1.record()
+            barrier()
+        te = torch.tensor([x0.elapsed_time(x1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ems = float(te.item()) / KE
+        info["e2e"] = {"value": B * world / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                       "d2h_bytes_per_step": 12, "ms_per_step": ems, "steps": KE,
+                       "api": "ForwardTrainer.step on batches copied from pinned host tensors (copy stream, double "
+                              "buffered), 3 losses read back every step",
+                       "h2d_gbs": h2d_bytes / (ems * 1e-3) / 1e9}
+        del host, devb
+    del sets, ftr
+    torch.cuda.empty_cache()
+    return info
+
+
+def run_wide(args):
+    """--config wide: the widened surrogate's training step as the line (BASELINE config 5 widths)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        bind_to_gpu_numa_node(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = read_peaks()
+    clocks = ClockSampler(local)
+    clocks.start()
+    info = wide_surrogate_block(dev, world, rank, args.batch, args.steps, max(3, args.warmup), peaks, barrier, True)
+    clk = clocks.stop()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, n, el = cpu_wide_pretrain_baseline(1024, 12.0, cores)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{n} steps of batch 1024 in {el:.1f} s (oracle/models.py pretrain_step at the same widths, "
+                         f"fp32, torch CPU)"}
+    if rank == 0:
+        out = {"metric": info["metric"], "value": info["value"], "unit": "samples/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": info["ms_per_step"],
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
+               "config": {"workload": f"forward-surrogate training step at the BASELINE config-5 widths (4 -> 2048 x 5 "
+                                      f"-> 2048 + 8, Dropout 0.2, 2 MSE losses, clip + Adam), batch {args.batch} per GPU",
+                          "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                          "exchange": info["gradient_exchange"],
+                          "l2": "2 distinct input batches rotated (1.07 GB > 126 MB L2)",
+                          "scope": "the surrogate only: generator / discriminator stay at the reference widths "
+                                   "(DESIGN.md section 7)"},
+               "roofline": info.get("roofline"), "step_roofline": info["step_roofline"], "cpu_baseline": cpu,
+               "e2e": info.get("e2e"), "gpu_launches": int(info["gpu_launches_per_step"] * args.steps),
+               "clocks": clk, "wide_surrogate_training": info}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------- native arm
@@ -701,6 +917,12 @@ def run_native(args):
                 "loss_last_step": float(ftr.losses[0])}
     del pnorm_sets, ftr
 
+    # ---- widened surrogate (BASELINE config 5 widths: hidden 2048, 2048-point spectra) on its own surrogate-only
+    # engine, a few steps (the `--config wide` line times it on its own, with an end-to-end leg)
+    wide_info = None
+    if not args.no_wide:
+        wide_info = wide_surrogate_block(dev, world, rank, min(B, 65536), max(3, min(K, 8)), 3, peaks, barrier, False)
+
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -739,6 +961,7 @@ def run_native(args):
             "scoring": score_info,
             "physics": phys_info,
             "surrogate_training": fwd_info,
+            "wide_surrogate_training": wide_info,
             "evaluator_reductions": eval_info,
             "data_pipeline": pipe_info,
             "wave_quantisation_probe": quant,
@@ -762,10 +985,15 @@ def main():
     ap.add_argument("--physics-sweep", default="1048576,4194304,16777216,67108864",
                     help="total spectra of the physics-kernel sweep (BASELINE config 3), comma separated; '' skips")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="default", choices=["default", "wide"],
+                    help="wide: the line is the widened surrogate's training step (BASELINE config 5 widths)")
+    ap.add_argument("--no-wide", action="store_true", help="skip the widened-surrogate block of the default line")
     ap.add_argument("--no-quant-probe", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference_wide(args) if args.config == "wide" else run_reference(args)
+    elif args.config == "wide":
+        run_wide(args)
     else:
         run_native(args)
 
