@@ -1900,75 +1900,114 @@ __global__ void f_train_losses_kernel(const float* __restrict__ sums, double n_s
 // BASELINE config 5 (hidden 2048, 2048-point spectra): the surrogate's streaming kernels for any hidden width
 // N = 256 * NCH (NCH = 1, 2, 4, 8).  Same arithmetic as the reference-width kernels above; a lane owns 8 columns of
 // every 256-column chunk of its row.
-// First layer (K = 4, forward_model.py:30-33), eval (TRAIN = false: act = LeakyReLU(LayerNorm(h))) or training mode
-// (xhat, 1/std, Dropout keep-bits as in f_l1_train_kernel).  The 16 N-byte weight rows come from L1/L2 per row.
-template <int NCH, bool TRAIN>
+// First layer (K = 4, forward_model.py:30-33).  With K = 4 the LayerNorm statistics of a row are a closed form in its
+// four inputs: h_c - mean = U_c . p + v_c with the CENTRED weights U_c = W_c - mean_c(W), v_c = b_c - mean(b), so
+//   var = p^T A p + 2 p^T B + C,   A = mean_c(U_c^T U_c), B = mean_c(U_c v_c), C = mean_c(v_c^2)
+// (a positive semi-definite form: no cancellation).  f_l1_consts_kernel computes the 20 constants in fp64 once per
+// call; the row kernel then needs no reduction over the row at all - a thread owns 8 columns (their centred weights
+// stay in registers for the whole kernel) and walks the rows.  (The first version gave a warp a row and re-read the
+// 32 KB weight matrix per row from L1: 655 us for a 540 MB output at B = 65 536, N = 2048.)
+constexpr int kL1Consts = 20;   // [0:4] mean_c(W), [4] mean(b), [5:15] A (upper triangle, row-major), [15:19] B, [19] C
+__global__ void __launch_bounds__(256) f_l1_consts_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          int N, float* __restrict__ out) {
+  pdl_wait();
+  __shared__ double sm[256][15];
+  __shared__ double mean[5];
+  const int t = threadIdx.x;
+  double a[15];
+  for (int k = 0; k < 5; ++k) a[k] = 0.0;
+  for (int c = t; c < N; c += 256) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c);
+    a[0] += w.x; a[1] += w.y; a[2] += w.z; a[3] += w.w; a[4] += b1[c];
+  }
+  for (int k = 0; k < 5; ++k) sm[t][k] = a[k];
+  __syncthreads();
+  if (t < 5) {
+    double s = 0.0;
+    for (int i = 0; i < 256; ++i) s += sm[i][t];
+    mean[t] = s / N;
+  }
+  __syncthreads();
+  for (int k = 0; k < 15; ++k) a[k] = 0.0;
+  for (int c = t; c < N; c += 256) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c);
+    const double u[4] = {w.x - mean[0], w.y - mean[1], w.z - mean[2], w.w - mean[3]};
+    const double v = b1[c] - mean[4];
+    int k = 0;
+    for (int i = 0; i < 4; ++i)
+      for (int j = i; j < 4; ++j) a[k++] += u[i] * u[j];
+    for (int i = 0; i < 4; ++i) a[10 + i] += u[i] * v;
+    a[14] += v * v;
+  }
+  for (int k = 0; k < 15; ++k) sm[t][k] = a[k];
+  __syncthreads();
+  if (t < 15) {
+    double s = 0.0;
+    for (int i = 0; i < 256; ++i) s += sm[i][t];
+    out[5 + t] = (float)(s / N);
+  }
+  if (t < 5) out[t] = (float)mean[t];
+}
+
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads) f_l1_wide_kernel(const float* __restrict__ p, const float* __restrict__ w1,
                                                              const float* __restrict__ b1,
                                                              const float* __restrict__ lnw,
-                                                             const float* __restrict__ lnb, __half* __restrict__ xhat,
-                                                             __half* __restrict__ act, float* __restrict__ rstd_out,
+                                                             const float* __restrict__ lnb,
+                                                             const float* __restrict__ consts,
+                                                             __half* __restrict__ xhat, __half* __restrict__ act,
+                                                             float* __restrict__ rstd_out,
                                                              unsigned char* __restrict__ mask_out,
                                                              unsigned char* __restrict__ keepbits, long long rows,
-                                                             DropoutArgs dr) {
+                                                             int N, DropoutArgs dr) {
   pdl_wait();
-  constexpr int N = NCH * 256;
-  const int lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+  const ColMap m(N);
+  const int c0 = m.ch * 8;
+  float k[kL1Consts];
+#pragma unroll
+  for (int i = 0; i < kL1Consts; ++i) k[i] = __ldg(consts + i);
+  float4 u[8];
+  float v[8], gm[8], bt[8];
+  ld_f8(b1 + c0, v);
+  ld_f8(lnw + c0, gm);
+  ld_f8(lnb + c0, bt);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c0 + i);
+    u[i] = make_float4(w.x - k[0], w.y - k[1], w.z - k[2], w.w - k[3]);
+    v[i] -= k[4];
+  }
+  for (long long row = (long long)blockIdx.x * m.rpb + m.rg; row < rows; row += (long long)gridDim.x * m.rpb) {
     const float4 q = __ldg(reinterpret_cast<const float4*>(p) + row);
-    float h[NCH][8];
-    float s = 0.f;
+    // var = q^T A q + 2 q^T B + C
+    float var = k[19];
+    var = fmaf(q.x, fmaf(q.x, k[5], 2.f * fmaf(q.y, k[6], fmaf(q.z, k[7], fmaf(q.w, k[8], k[15])))), var);
+    var = fmaf(q.y, fmaf(q.y, k[9], 2.f * fmaf(q.z, k[10], fmaf(q.w, k[11], k[16]))), var);
+    var = fmaf(q.z, fmaf(q.z, k[12], 2.f * fmaf(q.w, k[13], k[17])), var);
+    var = fmaf(q.w, fmaf(q.w, k[14], 2.f * k[18]), var);
+    const float rstd = 1.0f / sqrtf(fmaxf(var, 0.f) + kLnEps);
+    float xh[8], a[8];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int c0 = j * 256 + lane * 8;
-      float b[8];
-      ld_f8(b1 + c0, b);
+    for (int i = 0; i < 8; ++i)
+      xh[i] = fmaf(q.w, u[i].w, fmaf(q.z, u[i].z, fmaf(q.y, u[i].y, fmaf(q.x, u[i].x, v[i])))) * rstd;
+    if constexpr (TRAIN) {
+      const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, c0 >> 3);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(w1) + c0 + i);
-        h[j][i] = fmaf(q.w, w.w, fmaf(q.z, w.z, fmaf(q.y, w.y, fmaf(q.x, w.x, b[i]))));
-        s += h[j][i];
+      for (int i = 0; i < 8; ++i) a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(xh[i], gm[i], bt[i])) * dr.keep_scale : 0.f;
+      st_h8(xhat + row * N + c0, xh);
+      keepbits[row * (N / 8) + (c0 >> 3)] = (unsigned char)keep;
+      if (mask_out) {
+        unsigned long long mk = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
+        *reinterpret_cast<unsigned long long*>(mask_out + row * N + c0) = mk;
       }
+      if (m.ch == 0) rstd_out[row] = rstd;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = lrelu_f(fmaf(xh[i], gm[i], bt[i]));
     }
-    const float mean = warp_sum_f(s) * (1.0f / N);
-    float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < NCH; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        h[j][i] -= mean;
-        v = fmaf(h[j][i], h[j][i], v);
-      }
-    const float rstd = 1.0f / sqrtf(warp_sum_f(v) * (1.0f / N) + kLnEps);
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int c0 = j * 256 + lane * 8;
-      float gm[8], bt[8], a[8];
-      ld_f8(lnw + c0, gm);
-      ld_f8(lnb + c0, bt);
-      if constexpr (TRAIN) {
-        const unsigned int keep = drop_keep8(dr, dr.first_row + row, 0, c0 >> 3);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          h[j][i] *= rstd;
-          a[i] = (keep >> i) & 1u ? lrelu_f(fmaf(h[j][i], gm[i], bt[i])) * dr.keep_scale : 0.f;
-        }
-        st_h8(xhat + row * N + c0, h[j]);
-        keepbits[row * (N / 8) + (c0 >> 3)] = (unsigned char)keep;
-        if (mask_out) {
-          unsigned long long m = 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) m |= (unsigned long long)((keep >> i) & 1u) << (8 * i);
-          *reinterpret_cast<unsigned long long*>(mask_out + row * N + c0) = m;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = lrelu_f(fmaf(h[j][i] * rstd, gm[i], bt[i]));
-      }
-      st_h8(act + row * N + c0, a);
-    }
-    if (TRAIN && lane == 0) rstd_out[row] = rstd;
+    st_h8(act + row * N + c0, a);
   }
 }
 
@@ -2408,27 +2447,20 @@ void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, fl
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st) {
   launch_k(f_dw1_transpose_kernel, 1, 256, 0, st, src, dw1);
 }
-template <bool TRAIN>
-static void launch_f_l1_wide_t(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
-                               __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
-                               int64_t rows, int N, const DropoutArgs& dr, cudaStream_t st) {
-  const int grid = grid_for_rows(rows, 8 * 4, 148 * 4);
-  auto go = [&](auto kern) {
-    launch_k(kern, grid, kThreads, 0, st, p, w1, b1, lnw, lnb, xhat, act, rstd, mask, keepbits, (long long)rows, dr);
-  };
-  if (N == 256) go(f_l1_wide_kernel<1, TRAIN>);
-  else if (N == 512) go(f_l1_wide_kernel<2, TRAIN>);
-  else if (N == 1024) go(f_l1_wide_kernel<4, TRAIN>);
-  else go(f_l1_wide_kernel<8, TRAIN>);
-}
 void launch_f_l1_wide(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
-                      __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
-                      int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st) {
+                      float* consts, __half* xhat, __half* act, float* rstd, unsigned char* mask,
+                      unsigned char* keepbits, int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st) {
+  launch_k(f_l1_consts_kernel, 1, 256, 0, st, w1, b1, N, consts);
+  const int rpb = kThreads / (N / 8);
+  const int grid = grid_for_rows(rows, rpb * 16, 148 * 8);
   if (dr) {
-    launch_f_l1_wide_t<true>(p, w1, b1, lnw, lnb, xhat, act, rstd, mask, keepbits, rows, N, *dr, st);
+    launch_k(f_l1_wide_kernel<true>, grid, kThreads, 0, st, p, w1, b1, lnw, lnb, (const float*)consts, xhat, act, rstd,
+             mask, keepbits, (long long)rows, N, *dr);
   } else {
     DropoutArgs none = {};
-    launch_f_l1_wide_t<false>(p, w1, b1, lnw, lnb, nullptr, act, nullptr, nullptr, nullptr, rows, N, none, st);
+    launch_k(f_l1_wide_kernel<false>, grid, kThreads, 0, st, p, w1, b1, lnw, lnb, (const float*)consts,
+             (__half*)nullptr, act, (float*)nullptr, (unsigned char*)nullptr, (unsigned char*)nullptr,
+             (long long)rows, N, none);
   }
 }
 void launch_f_dw1_wide(const __half* dh1, const float* p, int64_t rows, int N, float* part, float* dw1_kmajor,

@@ -269,9 +269,10 @@ void launch_f_dp(const __half* dh1, const float* w1, float* dp, int64_t rows, fl
 void launch_f_dw1_transpose(const float* src, float* dw1, cudaStream_t st);
 // ---- widened surrogate (BASELINE config 5): any hidden width N in {256, 512, 1024, 2048}, any even S / Mt with
 // round_up(S + Mt, 64) <= 2560.  dr == nullptr: eval mode (act only).
+// consts: 20 floats of scratch (closed-form LayerNorm statistics of the K = 4 layer, written by this call)
 void launch_f_l1_wide(const float* p, const float* w1, const float* b1, const float* lnw, const float* lnb,
-                      __half* xhat, __half* act, float* rstd, unsigned char* mask, unsigned char* keepbits,
-                      int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st);
+                      float* consts, __half* xhat, __half* act, float* rstd, unsigned char* mask,
+                      unsigned char* keepbits, int64_t rows, int N, const DropoutArgs* dr, cudaStream_t st);
 // dw1[N][4] += inv_gs * dh1^T p (dw1_kmajor: [4][N] scratch, zero on entry)
 void launch_f_dw1_wide(const __half* dh1, const float* p, int64_t rows, int N, float* part, float* dw1_kmajor,
                        float* dw1, float inv_gs, cudaStream_t st);

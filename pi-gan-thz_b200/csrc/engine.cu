@@ -102,6 +102,7 @@ struct PiganEngine {
   int dout_ld = 320;      // output-layer gradient operand: S + Mt columns padded to a multiple of 64
   int out_groups = 2;     // 256-column groups of the output layer (widened path: fp32 accumulator slabs)
   float* f_slab = nullptr;   // widened path: [bp / 128][out_groups][128][256] fp32 output-layer accumulators
+  float* f_l1c = nullptr;    // widened path: closed-form LayerNorm constants of the first layer (launch_f_l1_wide)
   bool f_loaded = false;
   const float* f_params = nullptr;
   const float* center = nullptr;  // caller-provided spectrum centring row (pigan_engine_set_spectrum_center)
@@ -203,6 +204,7 @@ struct PiganEngine {
     f_bias_out = c.take<float>(dout_ld > 288 ? dout_ld : 288);
     head_img = c.take<float>(kHeadImgFloats);
     f_slab = full ? nullptr : c.take<float>((size_t)(B / kBlockM) * out_groups * kBlockM * 256);
+    f_l1c = c.take<float>(32);
     return (c.off + 255) & ~size_t(255);
   }
 };
@@ -688,8 +690,8 @@ int f_forward_wide(PiganEngine* e, const float* p_norm, int64_t n, float* out_fu
   const FwdLayout& L = e->fl;
   const float* fp = e->f_params;
   PM("f_l1");
-  launch_f_l1_wide(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], nullptr, e->f_a1, nullptr, nullptr,
-                   nullptr, n, L.H[0], nullptr, st);
+  launch_f_l1_wide(p_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_l1c, nullptr, e->f_a1,
+                   nullptr, nullptr, nullptr, n, L.H[0], nullptr, st);
   __half* acts[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   for (int i = 1; i < 5; ++i) {
     PM("f_hidden_gemm");
@@ -1556,8 +1558,8 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   auto mask = [&](int i) { return a.mask_dump ? a.mask_dump + moff[i] : nullptr; };
   PM("f_l1");
   if (wide)
-    launch_f_l1_wide(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
-                     w.rstd[0], mask(0), w.keepbits[0], n, L.H[0], &dr, st);
+    launch_f_l1_wide(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], e->f_l1c, w.xhat[0],
+                     act[0], w.rstd[0], mask(0), w.keepbits[0], n, L.H[0], &dr, st);
   else
     launch_f_l1_train(a.params_norm, fp + L.w[0], fp + L.b[0], fp + L.ln_w[0], fp + L.ln_b[0], w.xhat[0], act[0],
                       w.rstd[0], mask(0), w.keepbits[0], n, dr, st);
