@@ -32,9 +32,15 @@ class _DiscriminatorFn(torch.autograd.Function):
 
 
 class Discriminator(nn.Module):
-    def __init__(self, input_spec_dim, input_param_dim):
+    REFERENCE_WIDTHS = (512, 256)
+
+    def __init__(self, input_spec_dim, input_param_dim, hidden=None):
+        """``hidden``: the two hidden widths (default: the reference's 512, 256); see ``Generator``."""
         super().__init__()
-        widths = (512, 256)
+        widths = tuple(int(w) for w in (hidden if hidden is not None else self.REFERENCE_WIDTHS))
+        if len(widths) != 2:
+            raise ValueError("Discriminator: two hidden widths")
+        self.hidden = widths
         self.main = nn.Sequential(
             nn.Linear(input_spec_dim + input_param_dim, widths[0]), nn.LeakyReLU(0.2, inplace=True),
             nn.Linear(widths[0], widths[1]), nn.LeakyReLU(0.2, inplace=True),

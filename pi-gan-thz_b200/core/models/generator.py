@@ -32,9 +32,17 @@ class _GeneratorFn(torch.autograd.Function):
 
 
 class Generator(nn.Module):
-    def __init__(self, input_dim, output_dim):
+    REFERENCE_WIDTHS = (512, 256)
+
+    def __init__(self, input_dim, output_dim, hidden=None):
+        """``hidden``: the two hidden widths (default: the reference's 512, 256).  Other widths (BASELINE config 5:
+        2048, 2048 on 2048-point spectra) train through ``NativeTrainer`` - the fused step - only; the stand-alone
+        module forward / backward entry points exist at the reference widths."""
         super().__init__()
-        widths = (512, 256)
+        widths = tuple(int(w) for w in (hidden if hidden is not None else self.REFERENCE_WIDTHS))
+        if len(widths) != 2:
+            raise ValueError("Generator: two hidden widths")
+        self.hidden = widths
         self.main = nn.Sequential(
             nn.Linear(input_dim, widths[0]), nn.BatchNorm1d(widths[0]), nn.ReLU(True),
             nn.Linear(widths[0], widths[1]), nn.BatchNorm1d(widths[1]), nn.ReLU(True),

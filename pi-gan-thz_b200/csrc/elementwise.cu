@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a)
       for (int u = 0; u < U; ++u) {
         const long long r = r0 + u * stride;
         if (r < a.rows) {
-          ld_h4(a.h2 + r * a.C + c0, h[u]);
+          ld_h4(a.h2 + r * a.ld + c0, h[u]);
           dq[u] = __ldg(reinterpret_cast<const float4*>(a.dpre) + r);
         } else {
           h[u][0] = h[u][1] = h[u][2] = h[u][3] = 0.f;
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a)
   } else {
     float w[4][4], A[4], Bc[4], C0[4], sdh[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ld_f4(a.w3 + j * a.C + c0, w[j]);
+    for (int j = 0; j < 4; ++j) ld_f4(a.w3 + j * a.ld + c0, w[j]);
     {
       float gm[4], rs[4], mu[4], m1[4], m2[4];
       ld_f4(a.gamma + c0, gm);
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a)
       for (int u = 0; u < U; ++u) {
         const long long r = r0 + u * stride;
         if (r < a.rows) {
-          ld_h4(a.h2 + r * a.C + c0, h[u]);
+          ld_h4(a.h2 + r * a.ld + c0, h[u]);
           dq[u] = __ldg(reinterpret_cast<const float4*>(a.dpre) + r);
         }
       }
@@ -938,7 +938,7 @@ __global__ void __launch_bounds__(kThreads, 2) g_head_bwd_kernel(GHeadBwdArgs a)
           out[i] = dh;
           sdh[i] += dh;
         }
-        st_h4(a.dy2 + r * a.C + c0, out);
+        st_h4(a.dy2 + r * a.ld + c0, out);
       }
     }
     block_colsum_partial4(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
@@ -992,11 +992,11 @@ __global__ void __launch_bounds__(1024) g_head_moments_kernel(GHeadBwdArgs a, co
   float sdy = 0.f, sdyh = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float w = a.w3[j * a.C + c];
+    const float w = a.w3[j * a.ld + c];
     const float t0 = tot[j][cl], t1 = tot[4 + j][cl];
     sdy = fmaf(w, t0, sdy);
     sdyh = fmaf(w, t1, sdyh);
-    a.dw3[j * a.C + c] += a.inv_gs * (sc * t1 + bi * t0);   // sum dpre_j * relu(sc*h+bi)
+    a.dw3[j * a.ld + c] += a.inv_gs * (sc * t1 + bi * t0);   // sum dpre_j * relu(sc*h+bi)
   }
   a.sum_dy[c] += sdy;
   a.sum_dyx[c] += rs * (sdyh - mu * sdy);
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(1024) g_head_moments_kernel(GHeadBwdArgs a, co
 __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
     const __half* __restrict__ da, const __half* __restrict__ h, const float* __restrict__ scale,
     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ rstd,
-    float* __restrict__ part, long long rows, int C) {
+    float* __restrict__ part, long long rows, int C, int ld) {
   pdl_wait();
   __shared__ float sm[kThreads * 4];
   const ColMap4 m(C);
@@ -1022,8 +1022,8 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_stats_kernel(
       long long r = r0 + u * stride;
       const bool ok = r < rows;
       r = ok ? r : rows - 1;
-      ld_h4(da + r * C + c0, g[u]);
-      ld_h4(h + r * C + c0, x[u]);
+      ld_h4(da + r * ld + c0, g[u]);
+      ld_h4(h + r * ld + c0, x[u]);
       if (!ok) g[u][0] = g[u][1] = g[u][2] = g[u][3] = 0.f;   // dy = 0: contributes nothing
     }
 #pragma unroll
@@ -1084,8 +1084,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) 
     for (int u = 0; u < kU; ++u) {  // clamped index: all loads issue back to back, no branches
       long long r = r0 + u * stride;
       r = r < a.rows ? r : a.rows - 1;
-      ld_h4(a.dy + r * a.C + c0, g[u]);
-      ld_h4(a.h + r * a.C + c0, x[u]);
+      ld_h4(a.dy + r * a.ld + c0, g[u]);
+      ld_h4(a.h + r * a.ld + c0, x[u]);
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -1099,7 +1099,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(BnBwdArgs a) 
         g[u][i] = dh;
         sdh[i] += dh;
       }
-      st_h4(a.dh + r * a.C + c0, g[u]);
+      st_h4(a.dh + r * a.ld + c0, g[u]);
     }
   }
   if (a.dbias) block_colsum_partial4(sdh, a.part + (size_t)blockIdx.x * a.C, m, sm);
@@ -2155,6 +2155,174 @@ __global__ void __launch_bounds__(kThreads) f_out_loss_slab_kernel(const float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ widened PI-GAN step
+// Generic-width versions of the pieces the reference-width step fuses into GEMM epilogues (BASELINE config 5: hidden
+// 2048, 2048-point spectra).  At those widths the GEMMs carry 193 MFLOP per sample and these passes a few percent.
+// Generator head (generator.py:22-25) for any C = 256 k: a warp per row, a lane owns 8 columns of every 256-column
+// chunk.  Same outputs as g_head_fwd_kernel (p, denormalised p, the fake-row tail of the spectrum operand).
+__global__ void __launch_bounds__(kThreads) wide_head_fwd_kernel(
+    const __half* __restrict__ h2, const float* __restrict__ scale, const float* __restrict__ bias,
+    const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ p_out,
+    float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
+    int C, int Kp, int S) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float h[8], sc[8], bi[8];
+      ld_h8(h2 + row * C + c0, h);
+      ld_f8(scale + c0, sc);
+      ld_f8(bias + c0, bi);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = fmaxf(fmaf(sc[i], h[i], bi[i]), 0.f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float w[8];
+        ld_f8(w3 + (size_t)e * C + c0, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[e] = fmaf(h[i], w[i], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = warp_sum_f(acc[e]);
+    const float mine = (lane & 3) == 0 ? acc[0] : (lane & 3) == 1 ? acc[1] : (lane & 3) == 2 ? acc[2] : acc[3];
+    const float pv = tanhf(mine + __ldg(b3 + (lane & 3)));        // every lane: parameter lane % 4
+    const float pd = (pv + 1.0f) / 2.0f * 0.6f + 2.2f;             // data_loader.py:238-252
+    if (lane < 4) {
+      p_out[row * 4 + lane] = pv;
+      if (pden_out) pden_out[row * 4 + lane] = pd;
+    }
+    if (tail_fake != nullptr) {
+      // last 64 operand columns of the row (8 chunks of 16 bytes), parameter columns replaced
+      const int t0 = Kp - 64;
+      float pr[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pr[e] = __shfl_sync(0xffffffffu, pd, e);
+      if (lane < 8) {
+        float v[8];
+        ld_h8(xc + row * Kp + t0 + lane * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = t0 + lane * 8 + k - S;
+          if (e >= 0 && e < 4) v[k] = pr[e] - kParamCenter;
+        }
+        st_h8(tail_fake + row * 64 + lane * 8, v);
+      }
+    }
+  }
+}
+
+// Discriminator layer 3 + Sigmoid + BCE (discriminator.py:26-28, loss.py:8-17) on the stored layer-2 activation
+// z2 [rows, C]: logit = z2 . w3 + b3; rows < rows_a carry label_a, the others label_b; rows in [gap_begin, gap_end) are
+// padding.  Same arithmetic as EpiDiscL2: loss_sum += sum BCE / global batch, dlogit (scaled by GS = global batch).
+__global__ void __launch_bounds__(kThreads) d_logit_bce_kernel(const __half* __restrict__ z2,
+                                                               const float* __restrict__ w3,
+                                                               const float* __restrict__ b3, long long rows, int C,
+                                                               long long rows_a, float label_a, float label_b,
+                                                               long long gap_begin, long long gap_end,
+                                                               float inv_batch, double* __restrict__ loss_sum,
+                                                               float* __restrict__ dlogit,
+                                                               float* __restrict__ prob_out) {
+  pdl_wait();
+  __shared__ float sm[8];
+  const int lane = threadIdx.x & 31;
+  float loss = 0.f;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const bool valid = !(row >= gap_begin && row < gap_end);
+    float lg = 0.f;
+    if (valid) {
+      for (int c0 = lane * 8; c0 < C; c0 += 256) {
+        float z[8], w[8];
+        ld_h8(z2 + row * C + c0, z);
+        ld_f8(w3 + c0, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lg = fmaf(z[i], w[i], lg);
+      }
+    }
+    lg = warp_sum_f(lg);
+    if (lane != 0) continue;
+    if (valid) {
+      const float logit = lg + __ldg(b3);
+      const float prob = 1.f / (1.f + expf(-logit));
+      const float y = row < rows_a ? label_a : label_b;
+      const float lp = fmaxf(logf(prob), -100.f);
+      const float l1p = fmaxf(log1pf(-prob), -100.f);
+      loss += -(y * lp + (1.f - y) * l1p) * inv_batch;
+      const float pq = prob * (1.f - prob);
+      if (dlogit) dlogit[row] = (prob - y) / fmaxf(pq, 1e-12f) * pq;
+      if (prob_out) prob_out[row] = prob;
+    } else if (dlogit) {
+      dlogit[row] = 0.f;
+    }
+  }
+  const float t = block_sum(loss, sm);
+  if (threadIdx.x == 0 && t != 0.f && loss_sum) atomicAdd(loss_sum, (double)t);
+}
+
+// Surrogate losses of the G-step (train_pigan.py:156-172) from the widened output layer's fp32 slabs: per row
+// recon = slab + bias; sums[0] += sum (recon - x)^2, [1] += sum (pm - m)^2, [2] += sum of squared second differences
+// (loss.py:29-64), [3], [4] += the two LC terms (loss.py:67-101); dp_lc [rows, 4] = lambda_lc * dLC/dp * GS (no gradient
+// through F: the reference evaluates it under no_grad).  A block per row; the row is staged in shared memory.
+__global__ void __launch_bounds__(kThreads) f_pigan_loss_slab_kernel(const float* __restrict__ slab, int ngroups,
+                                                                     const float* __restrict__ bias,
+                                                                     const float* __restrict__ spectrum,
+                                                                     const float* __restrict__ metrics,
+                                                                     const float* __restrict__ p_norm, long long rows,
+                                                                     int S, int Mt, int f1_idx, int f2_idx,
+                                                                     float lc_grad_mult, double* __restrict__ sums,
+                                                                     float* __restrict__ dp_lc) {
+  pdl_wait();
+  extern __shared__ float row_sm[];   // [S + Mt]
+  __shared__ float red[8];
+  const int OUT = S + Mt;
+  float rec = 0.f, met = 0.f, mx = 0.f, lc1 = 0.f, lc2 = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    __syncthreads();   // the previous row has been consumed
+    for (int c = 2 * (int)threadIdx.x; c < OUT; c += 2 * (int)blockDim.x) {
+      const float2 v = *reinterpret_cast<const float2*>(slab + slab_index(r, c, ngroups));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + c));
+      row_sm[c] = v.x + b.x;
+      row_sm[c + 1] = v.y + b.y;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < OUT; c += blockDim.x) {
+      const float o = row_sm[c];
+      if (c < S) {
+        const float d = o - __ldg(spectrum + r * S + c);
+        rec = fmaf(d, d, rec);
+        if (c >= 2) {
+          const float d2 = (o - row_sm[c - 1]) - (row_sm[c - 1] - row_sm[c - 2]);
+          mx = fmaf(d2, d2, mx);
+        }
+      } else {
+        const float d = o - __ldg(metrics + r * Mt + (c - S));
+        met = fmaf(d, d, met);
+      }
+    }
+    if (threadIdx.x == 0 && p_norm != nullptr) {
+      const float4 pn = __ldg(reinterpret_cast<const float4*>(p_norm) + r);
+      const float e1 = row_sm[S + f1_idx] - (0.4f * pn.x + 0.6f * pn.z);
+      const float e2 = row_sm[S + f2_idx] - (0.3f * pn.y + 0.7f * pn.w);
+      lc1 = fmaf(e1, e1, lc1);
+      lc2 = fmaf(e2, e2, lc2);
+      if (dp_lc) {
+        const float m = -2.f * lc_grad_mult;
+        *reinterpret_cast<float4*>(dp_lc + r * 4) = make_float4(m * e1 * 0.4f, m * e2 * 0.3f, m * e1 * 0.6f, m * e2 * 0.7f);
+      }
+    }
+  }
+  const float v[5] = {rec, met, mx, lc1, lc2};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float t = block_sum(v[k], red);
+    if (threadIdx.x == 0 && t != 0.f) atomicAdd(sums + k, (double)t);
+  }
+}
+
 }  // namespace
 
 // =========================================================================================== launchers
@@ -2278,48 +2446,117 @@ void launch_bn_relu_apply(const __half* h, const float* scale, const float* bias
 void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, const float* w3, const float* b3,
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
+  if (C != 256) {   // the register layout of g_head_fwd_kernel is the reference width's
+    launch_k(wide_head_fwd_kernel, grid_for_rows(rows, 8 * 4, 148 * 8), kThreads, 0, st, h2, scale, bias, w3, b3, p_out,
+             pden_out, xc, tail_fake, (long long)rows, C, Kp, S);
+    return;
+  }
   launch_k(g_head_fwd_kernel, grid_for_rows(rows, 8 * kHeadRows * 2, 148 * 2), kThreads, 0, st, h2, scale, bias, w3, b3,
            p_out, pden_out, xc, tail_fake, (long long)rows, C, Kp, S);
 }
+void launch_d_logit_bce(const __half* z2, const float* w3, const float* b3, int64_t rows, int C, int64_t rows_a,
+                        float label_a, float label_b, int64_t gap_begin, int64_t gap_end, double global_batch,
+                        double* loss_sum, float* dlogit, float* prob_out, cudaStream_t st) {
+  launch_k(d_logit_bce_kernel, grid_for_rows(rows, 8 * 4, 148 * 8), kThreads, 0, st, z2, w3, b3, (long long)rows, C,
+           (long long)rows_a, label_a, label_b, (long long)gap_begin, (long long)gap_end,
+           (float)(1.0 / global_batch), loss_sum, dlogit, prob_out);
+}
+void launch_f_pigan_loss_slab(const float* slab, int ngroups, const float* bias, const float* spectrum,
+                              const float* metrics, const float* p_norm, int64_t rows, int S, int Mt, int f1_idx,
+                              int f2_idx, float lc_grad_mult, double* sums, float* dp_lc, cudaStream_t st) {
+  launch_k(f_pigan_loss_slab_kernel, grid_for_rows(rows, 8, 148 * 8), kThreads, (size_t)(S + Mt) * sizeof(float), st,
+           slab, ngroups, bias, spectrum, metrics, p_norm, (long long)rows, S, Mt, f1_idx, f2_idx, lc_grad_mult, sums,
+           dp_lc);
+}
+// Column segment [off, off + w) of the head's arguments: the thread-owns-4-columns kernels cover at most 1024 columns
+// per launch (256 threads a row), wider layers (the widened generator, C = 2048) run them once per segment with the
+// row pitch ld = C.  One segment (C <= 1024, ld = C) is the reference-width path, unchanged.
+static GHeadBwdArgs head_segment(const GHeadBwdArgs& a, int off, int w) {
+  GHeadBwdArgs b = a;
+  b.C = w;
+  b.ld = a.C;
+  b.h2 = a.h2 + off; b.dy2 = a.dy2 ? a.dy2 + off : nullptr;
+  b.scale = a.scale + off; b.bias = a.bias + off; b.mean = a.mean + off; b.rstd = a.rstd + off;
+  b.w3 = a.w3 + off; b.dw3 = a.dw3 + off; b.sum_dy = a.sum_dy + off; b.sum_dyx = a.sum_dyx + off;
+  b.gamma = a.gamma ? a.gamma + off : nullptr; b.dbias = a.dbias ? a.dbias + off : nullptr;
+  b.dgamma = a.dgamma ? a.dgamma + off : nullptr; b.dbeta = a.dbeta ? a.dbeta + off : nullptr;
+  return b;
+}
 void launch_g_head_bwd(const GHeadBwdArgs& a, bool apply, cudaStream_t st) {
-  const int rpb = kThreads / (a.C / 4);
-  const int grid = grid_for_rows(a.rows, rpb * (apply ? 4 : 6) * 2, kPartBlocks);
+  const int seg = a.C > 1024 ? 1024 : a.C;
+  const int rpb = kThreads / (seg / 4);
+  // partial scratch: [grid][8 * seg] moment rows, then 8 * seg totals, then the dpre partials (<= 296 x 8)
+  const size_t scratch = (size_t)kPartBlocks * kPartCols;
+  int cap = (int)((scratch - 8 * (size_t)seg - 8 * 296) / (8 * (size_t)seg));
+  if (cap > kPartBlocks) cap = kPartBlocks;
+  const int grid = grid_for_rows(a.rows, rpb * (apply ? 4 : 6) * 2, cap);
   if (apply) {
-    launch_k(g_head_bwd_kernel<true>, grid, kThreads, 0, st, a);
-    ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
-    launch_reduce_partials(r, st);
+    for (int off = 0; off < a.C; off += seg) {
+      const GHeadBwdArgs b = head_segment(a, off, seg);
+      launch_k(g_head_bwd_kernel<true>, grid, kThreads, 0, st, b);
+      ReduceArgs r{a.part, grid, seg, 1, {{b.dbias, seg, a.inv_gs}}};
+      launch_reduce_partials(r, st);
+    }
   } else {
-    GHeadBwdArgs b = a;
-    float* tot = a.part + (size_t)kPartBlocks * 8 * a.C;   // after the partial rows
-    b.dpre_part = tot + 8 * a.C;                            // [dpre blocks][8] after the moment totals
+    float* tot = a.part + (size_t)cap * 8 * seg;   // after the partial rows
+    float* dpre_part = tot + 8 * seg;              // [dpre blocks][8] after the moment totals
     const int dpre_blocks = grid_for_rows(a.rows, kThreads, 148 * 2);
-    launch_k(g_head_dpre_kernel, dpre_blocks, kThreads, 0, st, b);
-    launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, b);
-    launch_k(g_head_moments_kernel, (a.C + 7) / 8 + 1, 1024, 0, st, b, a.part, grid, dpre_blocks);
+    {
+      GHeadBwdArgs b = a;
+      b.ld = a.C;
+      b.dpre_part = dpre_part;
+      launch_k(g_head_dpre_kernel, dpre_blocks, kThreads, 0, st, b);
+    }
+    for (int off = 0; off < a.C; off += seg) {
+      GHeadBwdArgs b = head_segment(a, off, seg);
+      b.dpre_part = dpre_part;
+      launch_k(g_head_bwd_kernel<false>, grid, kThreads, 0, st, b);
+      // db3 and the range-loss sum (the dpre partials) are added by the first segment's launch only
+      launch_k(g_head_moments_kernel, (seg + 7) / 8 + 1, 1024, 0, st, b, (const float*)a.part, grid,
+               off == 0 ? dpre_blocks : 0);
+    }
   }
 }
 void launch_bn_bwd_stats(const __half* da, const __half* h, const float* scale, const float* bias,
                          const float* mean, const float* rstd, float* sum_dy, float* sum_dyx, int64_t rows, int C,
                          float* part, cudaStream_t st) {
-  const int rpb = kThreads / (C / 4);
+  const int seg = C > 1024 ? 1024 : C;   // column segments of <= 1024 (thread-owns-4-columns mapping), pitch C
+  const int rpb = kThreads / (seg / 4);
   const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
-  launch_k(bn_bwd_stats_kernel, grid, kThreads, 0, st, da, h, scale, bias, mean, rstd, part, rows, C);
-  ReduceArgs r{part, grid, 2 * C, 2, {{sum_dy, C, 1.f}, {sum_dyx, C, 1.f}}};
-  launch_reduce_partials(r, st);
+  for (int off = 0; off < C; off += seg) {
+    launch_k(bn_bwd_stats_kernel, grid, kThreads, 0, st, da + off, h + off, scale + off, bias + off, mean + off,
+             rstd + off, part, rows, seg, C);
+    ReduceArgs r{part, grid, 2 * seg, 2, {{sum_dy + off, seg, 1.f}, {sum_dyx + off, seg, 1.f}}};
+    launch_reduce_partials(r, st);
+  }
 }
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st) {
-  const int rpb = kThreads / (a.C / 4);
+  const int seg = a.C > 1024 ? 1024 : a.C;   // see launch_bn_bwd_stats
+  const int rpb = kThreads / (seg / 4);
   const int grid = grid_for_rows(a.rows, rpb * kU * 2, kPartBlocks);
-  launch_k(bn_bwd_apply_kernel, grid, kThreads, 0, st, a);
-  if (a.dbias) {
-    ReduceArgs r{a.part, grid, a.C, 1, {{a.dbias, a.C, a.inv_gs}}};
-    launch_reduce_partials(r, st);
+  for (int off = 0; off < a.C; off += seg) {
+    BnBwdArgs b = a;
+    b.C = seg;
+    b.ld = a.C;
+    b.dy = a.dy + off; b.h = a.h + off; b.dh = a.dh + off;
+    b.scale = a.scale + off; b.bias = a.bias + off; b.mean = a.mean + off; b.rstd = a.rstd + off;
+    b.gamma = a.gamma + off; b.sum_dy = a.sum_dy + off; b.sum_dyx = a.sum_dyx + off;
+    b.dbias = a.dbias ? a.dbias + off : nullptr;
+    b.dgamma = a.dgamma ? a.dgamma + off : nullptr;
+    b.dbeta = a.dbeta ? a.dbeta + off : nullptr;
+    launch_k(bn_bwd_apply_kernel, grid, kThreads, 0, st, b);
+    if (b.dbias) {
+      ReduceArgs r{a.part, grid, seg, 1, {{b.dbias, seg, a.inv_gs}}};
+      launch_reduce_partials(r, st);
+    }
   }
 }
 void launch_d_l2_bwd(const __half* z2, const float* dlogit, const float* w3, __half* dh2, float* dw3, float* db2,
                      float* db3, int64_t rows, int C, float inv_gs, float* part, cudaStream_t st) {
   const int rpb = kThreads / (C / 8);
-  const int grid = grid_for_rows(rows, rpb * kU * 2, kPartBlocks);
+  int cap = (int)(((size_t)kPartBlocks * kPartCols) / (size_t)(2 * C + 8));   // partial rows inside the scratch
+  if (cap > kPartBlocks) cap = kPartBlocks;
+  const int grid = grid_for_rows(rows, rpb * kU * 2, cap);
   launch_k(d_l2_bwd_kernel, grid, kThreads, 0, st, z2, dlogit, w3, dh2, dw3, db2, db3, rows, C, inv_gs, part);
   if (dw3 != nullptr) {
     ReduceArgs r{part, grid, 2 * C + 8, 3, {{dw3, C, inv_gs}, {db2, C, inv_gs}, {db3, 1, inv_gs}}};

@@ -135,6 +135,8 @@ struct GHeadBwdArgs {
   float inv_gs;
   int64_t rows;
   int C;
+  int ld;                 // row pitch of h2 / dy2 and of w3 / dw3 (set by launch_g_head_bwd: = C, or the full width when
+                          // the launcher splits a layer wider than 1024 columns into segments)
   // apply pass only
   const float* gamma;     // BN2 weight
   float* dbias;           // [C] += sum dh / GS   (main.3.bias)
@@ -169,6 +171,7 @@ struct BnBwdArgs {
   float inv_gs;
   int64_t rows;
   int C;
+  int ld;             // row pitch of dy / h / dh (set by launch_bn_bwd_apply, see GHeadBwdArgs::ld)
   float* part;        // partial-sum scratch (kPartBlocks x C floats)
 };
 void launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t st);
@@ -285,6 +288,15 @@ void launch_f_out_loss_slab(const float* slab, int ngroups, const float* bias, c
                             const float* metrics, __half* dout, int ld, int64_t rows, int S, int Mt, float* part,
                             float* db_out, float* loss_sums, float inv_gs, cudaStream_t st, float w_spec = 1.f,
                             float w_met = 1.f);
+// ---- widened PI-GAN step: generic-width versions of what the reference-width step fuses into GEMM epilogues
+// layer 3 + Sigmoid + BCE of the discriminator on the stored activation z2 [rows, C] (EpiDiscL2's arithmetic)
+void launch_d_logit_bce(const __half* z2, const float* w3, const float* b3, int64_t rows, int C, int64_t rows_a,
+                        float label_a, float label_b, int64_t gap_begin, int64_t gap_end, double global_batch,
+                        double* loss_sum, float* dlogit, float* prob_out, cudaStream_t st);
+// the G-step's surrogate losses from the output layer's fp32 slabs (EpiFwdLoss' sums and dp_lc)
+void launch_f_pigan_loss_slab(const float* slab, int ngroups, const float* bias, const float* spectrum,
+                              const float* metrics, const float* p_norm, int64_t rows, int S, int Mt, int f1_idx,
+                              int f2_idx, float lc_grad_mult, double* sums, float* dp_lc, cudaStream_t st);
 void launch_f_input_grad_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 void launch_f_train_losses(const float* sums, double n_spec, double n_met, float* out, cudaStream_t st);
 

@@ -34,6 +34,24 @@ enum { kSumD = 0, kSumAdv = 1, kSumRec = 2, kSumMet = 3, kSumMaxwell = 4, kSumLc
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// Widened dims on which the PI-GAN step runs (BASELINE config 5: hidden 2048, 2048-point spectra): the surrogate's
+// conditions (surrogate_dims_ok) plus a spectrum length that is a multiple of 64 - the parameter / bias columns then
+// fill the operand's last 64-column k-block, which is what the discriminator's fake rows swap - and generator /
+// discriminator hidden widths that are multiples of 256 up to 2048.
+inline bool wide_gan_dims_ok(const PiganDims& d) {
+  if (d.param_dim != 4 || d.metrics_dim < 2 || d.metrics_dim % 2 || d.spectrum_dim < 64 || d.spectrum_dim % 64) return false;
+  if ((d.spectrum_dim + d.metrics_dim + 63) / 64 * 64 > 2560 || d.spectrum_dim > 2048) return false;
+  for (int i = 0; i < 5; ++i) {
+    const int h = d.f_hidden[i];
+    if (h != 256 && h != 512 && h != 1024 && h != 2048) return false;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (d.g_hidden[i] % 256 || d.g_hidden[i] < 256 || d.g_hidden[i] > 2048) return false;
+    if (d.d_hidden[i] % 256 || d.d_hidden[i] < 256 || d.d_hidden[i] > 2048) return false;
+  }
+  return true;
+}
+
 struct Carver {
   uint8_t* base;
   size_t off = 0;
@@ -99,6 +117,11 @@ struct PiganEngine {
   // full = the reference widths: every entry point.  Otherwise the engine serves the surrogate's paths only
   // (forward, VJP, training step) at the widened dims of BASELINE config 5 - see check_dims
   bool full = true;
+  // gan = the PI-GAN train step runs on this engine: the reference widths (fused epilogues), or widened dims the
+  // generic-width pieces cover (wide_gan_dims_ok) - then pigan_train_step[_phase] work, the module / scoring entry
+  // points still need `full`
+  bool gan = true;
+  int kp = 256;           // spectrum operand width: S + P + 2 spare columns rounded up to 64 (256 at the reference dims)
   int dout_ld = 320;      // output-layer gradient operand: S + Mt columns padded to a multiple of 64
   int out_groups = 2;     // 256-column groups of the output layer (widened path: fp32 accumulator slabs)
   float* f_slab = nullptr;   // widened path: [bp / 128][out_groups][128][256] fp32 output-layer accumulators
@@ -138,6 +161,8 @@ struct PiganEngine {
 
   PiganEngine(const PiganDims& dims) : d(dims), gl(dims), dl(dims), fl(dims) {
     full = dims_are_default(dims);
+    gan = full || wide_gan_dims_ok(dims);
+    kp = full ? 256 : (int)((dims.spectrum_dim + dims.param_dim + 2 + 63) / 64 * 64);
     dout_ld = (int)((fl.OUT + 63) / 64 * 64);
     out_groups = (fl.OUT + 255) / 256;
   }
@@ -145,9 +170,11 @@ struct PiganEngine {
   size_t carve(void* ws) {
     Carver c(ws);
     const int64_t B = bp;
-    const int64_t Bg = full ? bp : 0;   // generator / discriminator activations: not on the widened (surrogate-only) path
+    const int64_t Bg = gan ? bp : 0;    // generator / discriminator activations: not on a surrogate-only engine
     const int H1 = gl.H1, H2 = gl.H2, D1 = dl.H1, D2 = dl.H2;
-    xc_own = c.take<__half>(B * kKp);
+    // widened step: rows [bp, 2 bp) hold the fake rows' operand (the weight-gradient GEMM reads real and fake rows as
+    // one matrix; at the reference widths a 64-column tail operand inside the GEMM does that)
+    xc_own = c.take<__half>((full ? B : 2 * Bg) * kp);
     xc = xc_own;
     tail_f = c.take<__half>(B * 64);
     g_h1 = c.take<__half>(Bg * H1);
@@ -164,10 +191,10 @@ struct PiganEngine {
     f_a5 = c.take<__half>(B * fl.H[4]);
     g_dy2 = c.take<__half>(Bg * H2);
     g_da1 = c.take<__half>(Bg * H1);
-    g_w1h = c.take<__half>((size_t)H1 * kKp);
+    g_w1h = c.take<__half>((size_t)H1 * kp);
     g_w2h = c.take<__half>((size_t)H2 * H1);
     g_w2th = c.take<__half>((size_t)H1 * H2);
-    d_w1h = c.take<__half>((size_t)D1 * kKp);
+    d_w1h = c.take<__half>((size_t)D1 * kp);
     d_w2h = c.take<__half>((size_t)D2 * D1);
     d_w2th = c.take<__half>((size_t)D1 * D2);
     f_wh[0] = nullptr;
@@ -189,7 +216,7 @@ struct PiganEngine {
     prob = c.take<float>(2 * B);
     row_err = c.take<float>(B);
     f_rowstats = c.take<float>(B * 8 * 2);
-    cvec = c.take<float>(kKp);
+    cvec = c.take<float>(kp);
     g_beff = c.take<float>(H1);
     d_beff = c.take<float>(D1);
     d_wp = c.take<float>((size_t)D1 * 4);
@@ -434,9 +461,9 @@ int weight_grad(const __half* a, int64_t kd, int m_out, const __half* b, int64_t
 int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n, cudaStream_t st) {
   PM("prep_cast");
   e->xc = e->xc_own;
-  if (e->center != nullptr) launch_copy_pad_f32(e->center, e->gl.S, e->cvec, kKp, st);
-  else launch_center_vec(x, n, e->gl.S, (int)(n < 512 ? n : 512), e->cvec, kKp, st);
-  launch_cast_center(x, e->cvec, params, e->xc, n, e->gl.S, e->gl.P, kKp, st);
+  if (e->center != nullptr) launch_copy_pad_f32(e->center, e->gl.S, e->cvec, e->kp, st);
+  else launch_center_vec(x, n, e->gl.S, (int)(n < 512 ? n : 512), e->cvec, e->kp, st);
+  launch_cast_center(x, e->cvec, params, e->xc, n, e->gl.S, e->gl.P, e->kp, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -444,7 +471,7 @@ int prep_spectrum(PiganEngine* e, const float* x, const float* params, int64_t n
 int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStream_t st) {
   const GenLayout& L = e->gl;
   PM("pack_weights");
-  launch_pack_net(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, kKp, e->g_beff, L.H1, gp + L.w2, L.H2,
+  launch_pack_net(gp + L.w1, L.S, L.S, L.P, 0, 0, gp + L.b1, e->cvec, e->g_w1h, e->kp, e->g_beff, L.H1, gp + L.w2, L.H2,
                   e->g_w2h, need_backward ? e->g_w2th : nullptr, nullptr, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
@@ -453,7 +480,7 @@ int pack_generator(PiganEngine* e, const float* gp, bool need_backward, cudaStre
 int pack_discriminator(PiganEngine* e, const float* dp, bool need_backward, cudaStream_t st) {
   const DiscLayout& L = e->dl;
   PM("pack_weights");
-  launch_pack_net(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, kKp, e->d_beff, L.H1, dp + L.w2, L.H2,
+  launch_pack_net(dp + L.w1, L.IN, L.S, L.P, 1, 1, dp + L.b1, e->cvec, e->d_w1h, e->kp, e->d_beff, L.H1, dp + L.w2, L.H2,
                   e->d_w2h, need_backward ? e->d_w2th : nullptr, need_backward ? e->d_wp : nullptr, st);
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
@@ -469,9 +496,9 @@ static bool gemm_colstats(const PiganEngine* e) {
 int g_layer1(PiganEngine* e, int64_t n, cudaStream_t st, bool train = false) {
   PM("g_l1_gemm");
   if (train && gemm_colstats(e))
-    return linear_store_colstats(e->xc, n, kKp, e->g_w1h, e->gl.H1, e->g_h1, e->bn_sums, e->bn_sums + e->gl.H1,
+    return linear_store_colstats(e->xc, n, e->kp, e->g_w1h, e->gl.H1, e->g_h1, e->bn_sums, e->bn_sums + e->gl.H1,
                                  e->partials, st, e->whole_step ? &e->bn_pending_blocks : nullptr);
-  return linear_store<false, false, false>(e->xc, n, kKp, e->g_w1h, e->gl.H1, nullptr, e->g_h1, nullptr, st);
+  return linear_store<false, false, false>(e->xc, n, e->kp, e->g_w1h, e->gl.H1, nullptr, e->g_h1, nullptr, st);
 }
 int g_layer2(PiganEngine* e, const float* gp, int64_t n, cudaStream_t st, bool train = false) {
   PM("g_bn_relu_apply");
@@ -585,7 +612,7 @@ int g_eval_forward(PiganEngine* e, const float* gp, int64_t n, float* p_out, cud
 // z1 rows [row0, row0+n) = LeakyReLU([xc | tail] . w1h^T)   (bias and parameter columns inside the MMA)
 int d_layer1(PiganEngine* e, int64_t n, int64_t row0, bool fake, cudaStream_t st) {
   PM("d_l1_gemm");
-  return linear_store<false, true, false, true>(e->xc, n, kKp, e->d_w1h, e->dl.H1, nullptr,
+  return linear_store<false, true, false, true>(e->xc, n, e->kp, e->d_w1h, e->dl.H1, nullptr,
                                                 e->d_z1 + row0 * e->dl.H1, nullptr, st, fake ? e->tail_f : nullptr,
                                                 e->d_mask1 + row0 * (e->dl.H1 / 32));
 }
@@ -603,6 +630,17 @@ struct DL2Opts {
 int d_layer2(PiganEngine* e, const float* dp, const DL2Opts& o, cudaStream_t st) {
   using Epi = EpiDiscL2<CfgS>;
   const DiscLayout& L = e->dl;
+  if (L.H2 != 256) {
+    // widened discriminator: the row's logit needs all H2 columns, which no longer sit in one accumulator tile -
+    // layer 2 as a plain Linear + LeakyReLU store, layer 3 + Sigmoid + BCE as a streaming pass over z2
+    PM("d_l2_gemm");
+    PIGAN_TRY((linear_store<true, true, false>(e->d_z1, o.rows, L.H1, e->d_w2h, L.H2, dp + L.b2, e->d_z2, nullptr, st)));
+    PM("d_logit_bce");
+    launch_d_logit_bce(e->d_z2, dp + L.w3, dp + L.b3, o.rows, L.H2, o.rows_a, o.label_a, o.label_b, o.gap_begin,
+                       o.gap_end, o.global_batch, o.loss_sum, o.want_dlogit ? e->dlogit : nullptr, o.prob_out, st);
+    PIGAN_CUDA_OK(cudaGetLastError());
+    return PIGAN_OK;
+  }
   Epi::Params ep;
   PIGAN_TRY(out_map(&ep.z2, e->d_z2, o.rows, L.H2, L.H2));
   ep.b2 = dp + L.b2;
@@ -701,8 +739,10 @@ int f_forward_wide(PiganEngine* e, const float* p_norm, int64_t n, float* out_fu
     launch_ln_lrelu_apply(acts[i], e->f_rowstats, L.H[i] / 256, fp + L.ln_w[i], fp + L.ln_b[i], n, L.H[i], st);
   }
   PIGAN_TRY(f_out_slab(e, e->f_a5, n, e->f_wh[5], st));
-  PM("f_out_unslab");
-  launch_f_unslab(e->f_slab, e->out_groups, fp + L.b[5], out_full, n, L.OUT, st);
+  if (out_full != nullptr) {   // (the G-step's loss pass reads the slabs themselves)
+    PM("f_out_unslab");
+    launch_f_unslab(e->f_slab, e->out_groups, fp + L.b[5], out_full, n, L.OUT, st);
+  }
   PIGAN_CUDA_OK(cudaGetLastError());
   return PIGAN_OK;
 }
@@ -832,6 +872,17 @@ bool overlap_enabled() {
 }
 // surrogate forward of the G-step + its fused losses (train_pigan.py:156-172)
 int g_step_surrogate(PiganEngine* e, const PiganTrainArgs& a, cudaStream_t st) {
+  if (!e->full) {
+    // widened: eval-mode chain into the fp32 slabs, then the loss pass (no gradient through F: train_pigan.py:156-157)
+    if (!e->f_loaded) return fail(PIGAN_ERR_INVALID, "forward model not loaded (pigan_engine_load_forward_model)");
+    PIGAN_TRY(f_forward_wide(e, e->p, a.batch, nullptr, st));
+    PM("f_pigan_loss");
+    const FwdLayout& L = e->fl;
+    launch_f_pigan_loss_slab(e->f_slab, e->out_groups, e->f_params + L.b[5], a.spectrum, a.metrics_norm, e->p, a.batch,
+                             L.S, L.Mt, a.f1_idx, a.f2_idx, a.lambda_lc, e->sums + kSumRec, e->dp_lc, st);
+    PIGAN_CUDA_OK(cudaGetLastError());
+    return PIGAN_OK;
+  }
   FOutOpts fo{2, a.metrics_norm, e->p, e->sums + kSumRec, e->dp_lc, a.lambda_lc, nullptr, nullptr, a.f1_idx, a.f2_idx};
   return f_forward(e, e->p, a.batch, fo, st);
 }
@@ -883,7 +934,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
         // row it centred on: nothing to cast, half the bytes to move
         PM("prep_cast");
         e->xc = const_cast<__half*>(static_cast<const __half*>(a.spectrum_operand));
-        launch_copy_pad_f32(a.spectrum_center, G.S, e->cvec, kKp, st);
+        launch_copy_pad_f32(a.spectrum_center, G.S, e->cvec, e->kp, st);
       } else {
         PIGAN_TRY(prep_spectrum(e, a.spectrum, a.params_denorm, B, st));
       }
@@ -904,8 +955,19 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       g_bn_finalize(e, 2, gp, gp + G.b2, a.g_bn_buffers, a.g_num_batches_tracked, NG, 2, st);
       PM("g_head_fwd");
       launch_g_head_fwd(e->g_h2, e->scale2, e->bias2, gp + G.w3, gp + G.b3, e->p, e->pden, e->xc, e->tail_f, B, G.H2,
-                        kKp, G.S, st);
+                        e->kp, G.S, st);
       PIGAN_TRY(fork_surrogate(e, a, st));
+      if (!e->full) {
+        // widened: the fake rows' operand = the real rows' spectrum columns + the head's 64-column tail (generated
+        // parameters, the two constant-one columns), as rows [BP, BP + B) of the same matrix - read by the
+        // discriminator's first-layer weight-gradient GEMM (the forward GEMM takes the tail as its last k-block)
+        PM("d_fake_rows");
+        const size_t pitch = (size_t)e->kp * sizeof(__half);
+        PIGAN_CUDA_OK(cudaMemcpy2DAsync(e->xc + (size_t)BP * e->kp, pitch, e->xc, pitch, pitch - 128, (size_t)B,
+                                        cudaMemcpyDeviceToDevice, st));
+        PIGAN_CUDA_OK(cudaMemcpy2DAsync(e->xc + (size_t)BP * e->kp + (e->kp - 64), pitch, e->tail_f, 128, 128, (size_t)B,
+                                        cudaMemcpyDeviceToDevice, st));
+      }
       // ---- D-step (train_pigan.py:123-143)
       PIGAN_TRY(pack_discriminator(e, dp, true, st));
       PIGAN_TRY(d_layer1(e, B, 0, false, st));
@@ -921,19 +983,28 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       }
       {
         PM("d_dh1_gemm");
-        using Epi = EpiLeakyMaskStore<CfgSR>;
-        Epi::Params ep;
-        PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
-        ep.mask = e->d_mask1;
-        ep.mask_words = D.H1 / 32;
-        PIGAN_TRY((run_tn<CfgSR, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st)));
+        auto run = [&](auto cfg_tag) -> int {
+          using Cfg = decltype(cfg_tag);
+          using Epi = EpiLeakyMaskStore<Cfg>;
+          typename Epi::Params ep;
+          PIGAN_TRY(out_map(&ep.out, e->d_dh1, BP + B, D.H1, D.H1));
+          ep.mask = e->d_mask1;
+          ep.mask_words = D.H1 / 32;
+          return run_tn<Cfg, Epi>(ep, e->d_dh2, BP + B, D.H2, D.H2, e->d_w2th, D.H1, D.H2, st);
+        };
+        if (D.H2 <= CfgSR::B_RES_KB * kBlockK) PIGAN_TRY(run(CfgSR{}));
+        else PIGAN_TRY(run(CfgS{}));   // widened: K = H2 streams
       }
       PM("d_dw2_gemm");
       PIGAN_TRY(weight_grad(e->d_dh2, BP + B, D.H2, e->d_z1, BP + B, D.H1, a.d_grads + D.w2, D.H1, D.H1, inv_gs, -1,
                             nullptr, 0, nullptr, 0, e->dw_part, st));
       PM("d_dw1_gemm");
-      PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
-                            a.d_grads + D.b1, BP, e->tail_f, BP, e->dw_part, st, 0, e->cvec, D.S, D.P));
+      if (e->full)
+        PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP, kKp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
+                              a.d_grads + D.b1, BP, e->tail_f, BP, e->dw_part, st, 0, e->cvec, D.S, D.P));
+      else   // widened: rows [BP, BP + B) of the operand are the fake rows (built above), one plain product
+        PIGAN_TRY(weight_grad(e->d_dh1, BP + B, D.H1, e->xc, BP + B, e->kp, a.d_grads + D.w1, D.IN, D.IN, inv_gs, D.IN,
+                              a.d_grads + D.b1, 0, nullptr, 0, e->dw_part, st, 0, e->cvec, D.S, D.P));
       break;
     }
     case 3: {
@@ -995,7 +1066,7 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
       PM("g_bn_bwd_apply");
       launch_bn_bwd_apply(bb, st);
       PM("g_dw1_gemm");
-      PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, kKp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
+      PIGAN_TRY(weight_grad(e->g_da1, B, G.H1, e->xc, B, e->kp, a.g_grads + G.w1, G.S, G.S, inv_gs, G.S + G.P,
                             a.g_grads + G.b1, 0, nullptr, 0, e->dw_part, st, 0, e->cvec, G.S, 0));
       break;
     }
@@ -1024,7 +1095,12 @@ int train_phase(PiganEngine* e, const PiganTrainArgs& a, int phase, cudaStream_t
 
 int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
   PIGAN_CHECK_ARG(e != nullptr && a != nullptr);
-  PIGAN_TRY(need_full(e));
+  if (!e->gan)
+    return fail(PIGAN_ERR_UNSUPPORTED, "this engine's dimensions serve the surrogate only (PI-GAN step: the reference "
+                                       "widths, or widened dims with spectrum_dim % 64 == 0 and generator / discriminator "
+                                       "widths that are multiples of 256 up to 2048)");
+  if (!e->full && (a->spectrum_operand != nullptr || a->spectrum == nullptr || a->params_denorm == nullptr))
+    return fail(PIGAN_ERR_UNSUPPORTED, "widened PI-GAN step: pass fp32 spectrum / params_denorm (no prepared operand)");
   PIGAN_CHECK_ARG(a->batch >= 2 && a->batch <= e->max_batch && a->global_batch >= a->batch);
   PIGAN_CHECK_ARG(a->metrics_norm != nullptr);
   PIGAN_CHECK_ARG(a->spectrum_operand ? (a->spectrum_center != nullptr &&

@@ -77,7 +77,8 @@ class NativeTrainer:
         self.gs = _flat.net_state(generator, "generator")
         self.ds = _flat.net_state(discriminator, "discriminator")
         self.fs = _flat.net_state(forward_model, "forward_model")
-        self.engine = _engine.Engine(max_batch, self.device)
+        self.engine = _engine.Engine(max_batch, self.device, self._dims_of(generator, discriminator, forward_model))
+        self.wide = self.engine.dims is not None and native.dims_key(self.engine.dims) != native.dims_key(native.default_dims())
         self.engine.load_forward_model(self.fs.params.tensor())
         gp, dp = self.gs.params.tensor(), self.ds.params.tensor()
         self.g_grads, self.g_m, self.g_v = (torch.zeros_like(gp) for _ in range(3))
@@ -106,8 +107,10 @@ class NativeTrainer:
         self.exchange_events = None      # set to [] to collect (name, start, end) CUDA events of every peer exchange
         # data parallel: gradients are produced straight into an NVLink-mapped exchange region and summed by the
         # library's one-shot kernels (dp.py); NCCL all-reduce is the fallback when peers cannot be mapped
+        # (widened dims: 8.4 M-float gradients are bandwidth-, not latency-bound - NCCL's all-reduce, not the one-shot
+        # peer kernels that read every peer's whole buffer)
         self.xchg = _dp.DpExchange.create(max(gp.numel(), dp.numel()), self.device, process_group) \
-            if self.world > 1 else None
+            if (self.world > 1 and not self.wide) else None
         if self.xchg is not None:
             self._slots = {(net, par): self.xchg.grad_slot(net, par, n)
                            for net, n in ((0, gp.numel()), (1, dp.numel())) for par in (0, 1)}
@@ -116,6 +119,21 @@ class NativeTrainer:
             p.grad = gview
         for p, gview in zip(self.ds.params._tensors(), self.ds.params.views_like(self.d_grads)):
             p.grad = gview
+
+    @staticmethod
+    def _dims_of(generator, discriminator, forward_model):
+        """None at the reference dims; else the PiganDims of the three modules (BASELINE config 5: widened MLPs and
+        2048-point spectra) - the engine then runs the generic-width step (include/pigan_b200.h)."""
+        g_h = tuple(getattr(generator, "hidden", (512, 256)))
+        d_h = tuple(getattr(discriminator, "hidden", (512, 256)))
+        f_h = tuple(getattr(forward_model, "hidden", (256, 512, 1024, 512, 256)))
+        S = generator.main[0].in_features
+        Mt = forward_model.output_metrics_dim
+        if (g_h, d_h, f_h, S, Mt) == ((512, 256), (512, 256), (256, 512, 1024, 512, 256), 250, 8):
+            return None
+        if discriminator.main[0].in_features != S + 4 or forward_model.output_spectrum_dim != S:
+            raise ValueError("generator / discriminator / forward model disagree on the spectrum length")
+        return native.make_dims(spectrum_dim=S, metrics_dim=Mt, f_hidden=f_h, g_hidden=g_h, d_hidden=d_h)
 
     # ------------------------------------------------------------------
     def _args(self, spectrum, params_denorm, metrics_norm, lr_g, lr_d, operand=None, center=None):
@@ -152,6 +170,8 @@ class NativeTrainer:
                       lr_d: float) -> torch.Tensor:
         """step() on a batch whose operand rows were prepared by prepare_operand (same ``center`` for every batch
         and, under data parallelism, every rank)."""
+        if self.wide:
+            raise RuntimeError("step_prepared: the prepared fp16 operand exists at the reference widths only")
         if (not operand.is_cuda or operand.dtype != torch.float16 or not operand.is_contiguous()
                 or operand.shape[1] != 256):
             raise RuntimeError("step_prepared: operand must be a contiguous fp16 CUDA tensor [B,256]")

@@ -194,3 +194,116 @@ def test_wide_engine_serves_the_surrogate_only():
     with pytest.raises(native.PiganError) as ei:
         eng.generator_forward(gflat, bn, nbt, x, False)
     assert "widened" in str(ei.value)
+
+
+# ------------------------------------------------------------------------------------------ widened PI-GAN step
+GAN_S, GAN_MT, GAN_H = 2048, 8, 2048
+# Gradient bounds by tensor group (norm-wise, against the fp32 oracle); the generator's layers below the last
+# BatchNorm carry the fp16-forward floor of tests/test_quantisation_floor.py (it falls with the batch size)
+# measured on B200: discriminator 7e-4 ... 9e-4; generator head / BatchNorm-2 1.0e-3 ... 1.7e-3; generator below the last
+# BatchNorm 2.0e-3 ... 3.2e-3 at B = 4096, 4.2e-3 ... 6.0e-3 at B = 1000
+TOL_GAN_D = 1.5e-3
+TOL_GAN_G_HEAD = 2.5e-3
+TOL_GAN_G_BODY = {1000: 1e-2, 4096: 5e-3}
+
+
+def _gan_weights(seed=9):
+    from oracle import models as O
+    gen = torch.Generator().manual_seed(seed)
+    g_sd = O.init_generator(GAN_S, 4, (GAN_H, GAN_H), gen)
+    d_sd = O.init_discriminator(GAN_S, 4, (GAN_H, GAN_H), gen)
+    for bi in (1, 4):   # non-trivial BatchNorm affines and running statistics
+        g_sd[f"main.{bi}.weight"] = 1.0 + (torch.rand(GAN_H, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.bias"] = 0.4 * (torch.rand(GAN_H, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.running_mean"] = 0.6 * (torch.rand(GAN_H, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.running_var"] = 1.0 + 0.8 * (torch.rand(GAN_H, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
+    f_sd = _weights(GAN_S, GAN_MT, (GAN_H,) * 5)
+    return g_sd, d_sd, f_sd
+
+
+def _gan_trainer(g_sd, d_sd, f_sd, B):
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from pigan_b200.trainer import NativeTrainer
+    G = Generator(GAN_S, 4, hidden=(GAN_H, GAN_H))
+    D = Discriminator(GAN_S, 4, hidden=(GAN_H, GAN_H))
+    F = ForwardModel(4, GAN_S, GAN_MT, hidden=(GAN_H,) * 5)
+    G.load_state_dict(g_sd); D.load_state_dict(d_sd); F.load_state_dict(f_sd)
+    F.eval()
+    tr = NativeTrainer(G, D, F, torch.device(DEV), max_batch=B)
+    assert tr.wide and tuple(tr.engine.dims.g_hidden) == (GAN_H, GAN_H)
+    return tr, G, D
+
+
+@pytest.mark.parametrize("B", [1000, 4096])
+def test_wide_pigan_step_matches_oracle(B):
+    """The PI-GAN train step (train_pigan.py:114-187) at the BASELINE config-5 widths - generator 2048 -> 2048 -> 2048
+    -> 4, discriminator 2052 -> 2048 -> 2048 -> 1, surrogate 4 -> 2048 x 5 -> 2056 - against the width-agnostic oracle:
+    unclipped D gradients (after phase 2), unclipped G gradients (after phase 5), then a whole step: the nine losses,
+    the generator output and the BatchNorm buffers.  B = 1000 exercises the padding rows between the real and the
+    fake half of the discriminator's stacked tensors."""
+    from oracle import fixtures
+    from oracle import models as O
+    from pigan_b200.trainer import LOSS_KEYS
+    torch.set_num_threads(os.cpu_count() or 1)
+    g_sd, d_sd, f_sd = _gan_weights()
+    spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=21, num_points=GAN_S)
+    batch = (spec, praw, pnorm, None, mnorm)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    g2, d2 = copy.deepcopy(g_sd), copy.deepcopy(d_sd)
+    ref_losses, ex = O.train_step(g2, d2, f_sd, og, od, batch, 2e-4, 2e-4)
+    dev_batch = (spec.to(DEV), praw.to(DEV), mnorm.to(DEV))
+
+    def phases(upto):
+        tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B)
+        tr.step_count += 1
+        a = tr._args(*dev_batch, 2e-4, 2e-4)
+        for ph in range(upto + 1):
+            tr.engine.train_step_phase(a, ph)
+        torch.cuda.synchronize()
+        return tr
+
+    report = {}
+    tr = phases(2)
+    dv = dict(zip(tr.ds.params.names, tr.ds.params.views_like(tr.d_grads.clone())))
+    for name, ref in ex["d_grads"].items():
+        report["d." + name] = rel(dv[name], ref)
+    assert rel(tr.engine.generator_output(B), ex["pred_params_norm"]) < 2e-3
+    del tr
+    tr = phases(5)
+    gv = dict(zip(tr.gs.params.names, tr.gs.params.views_like(tr.g_grads.clone())))
+    gnorm = float(torch.cat([v.reshape(-1) for v in ex["g_grads"].values()]).norm())
+    zero = ("main.0.bias", "main.3.bias")   # feed a BatchNorm: the true gradient is zero
+    for name, ref in ex["g_grads"].items():
+        if name in zero:
+            assert float(gv[name].norm()) < 1e-3 * gnorm, name
+            continue
+        report["g." + name] = rel(gv[name], ref)
+    del tr
+    print(f"\n[wide PI-GAN step B={B}] gradient distance from the fp32 oracle, per tensor")
+    for k, v in report.items():
+        print(f"   {k:16s} {v:.2e}")
+    for k, v in report.items():
+        if k.startswith("d."):
+            assert v < TOL_GAN_D, (k, v)
+        elif k in ("g.main.6.weight", "g.main.6.bias", "g.main.4.weight", "g.main.4.bias"):
+            assert v < TOL_GAN_G_HEAD, (k, v)
+        else:
+            assert v < TOL_GAN_G_BODY[B], (k, v)
+    # whole step
+    tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B)
+    losses = tr.step(*dev_batch, 2e-4, 2e-4).cpu()
+    for i, k in enumerate(LOSS_KEYS):
+        ref = ref_losses[k]
+        tol = 2e-3 if k == "lc_losses" else TOL_LOSS
+        assert abs(float(losses[i]) - ref) <= tol * abs(ref) + 1e-7, (k, float(losses[i]), ref)
+    print("   losses " + " ".join(f"{k}={float(losses[i]):.5g}" for i, k in enumerate(LOSS_KEYS)))
+    assert int(G.main[1].num_batches_tracked) == 5 and int(G.main[4].num_batches_tracked) == 5
+    for k in ("main.1.running_mean", "main.1.running_var", "main.4.running_mean", "main.4.running_var"):
+        assert rel(G.state_dict()[k], g2[k]) < 2e-3, (k, rel(G.state_dict()[k], g2[k]))
+    # first Adam step: every weight moves by ~lr * sign(g); compare the updated discriminator in units of lr
+    for name in ("main.2.weight", "main.4.weight"):
+        d = (D.state_dict()[name].cpu() - d2[name]).abs() / 2e-4
+        assert float((d > 0.1).float().mean()) < 0.02, (name, float((d > 0.1).float().mean()))
