@@ -162,13 +162,13 @@ def run_reference_wide(args):
         return
     cores = os.cpu_count() or 1
     sample = 1024
-    v, n, el = cpu_wide_pretrain_baseline(sample, 1e9, cores, max_steps=max(1, min(args.steps, 10)))
-    out = {"impl": "reference", "metric": "widened forward-surrogate train samples/s", "value": v, "unit": "samples/s",
+    v, n, el = cpu_wide_train_baseline(sample, 1e9, cores, max_steps=max(1, min(args.steps, 10)))
+    out = {"impl": "reference", "metric": "widened PI-GAN train samples/s", "value": v, "unit": "samples/s",
            "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": el / n * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "forward-surrogate training step at the BASELINE config-5 widths", "sample_batch": sample},
+           "config": {"workload": "PI-GAN train step at the BASELINE config-5 widths", "sample_batch": sample},
            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                            "sample": f"{n} steps of batch {sample} (oracle/models.py pretrain_step at 2048-wide layers, "
+                            "sample": f"{n} steps of batch {sample} (oracle/models.py train_step at 2048-wide layers, "
                                       f"fp32, torch CPU)"},
            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -266,6 +266,169 @@ def wide_flop_per_sample(S=WIDE_S, Mt=WIDE_MT, hidden=WIDE_HIDDEN) -> int:
     return 2 * (3 * sum(macs) - macs[0])
 
 
+def e2e_from_host(dev, world, sets, step_fn, KE, barrier):
+    """The step fed from pinned host copies of `sets` (tuples of device tensors): H2D of every input on a copy stream,
+    double buffered, inside the timed region; the step's losses are read back (D2H) every step.  Returns
+    (ms per step as the max over ranks, H2D bytes per step, steps timed)."""
+    import torch.distributed as dist
+    NS = len(sets)
+    host = [tuple(x.cpu().pin_memory() for x in s_) for s_ in sets]
+    devb = [tuple(torch.empty_like(x) for x in s_) for s_ in sets]
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_bytes = sum(x.numel() * x.element_size() for x in host[0])
+
+    def h2d(i):
+        with torch.cuda.stream(copy_stream):
+            for d_, h_ in zip(devb[i % NS], host[i % NS]):
+                d_.copy_(h_, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev
+
+    for rep_ in range(2):   # the second pass is the timed one
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        ev = h2d(0)
+        done = [None] * KE
+        for i in range(KE):
+            torch.cuda.current_stream().wait_event(ev)
+            out = step_fn(devb[i % NS])
+            done[i] = torch.cuda.Event()
+            done[i].record()
+            if i + 1 < KE:
+                if i + 1 >= NS:
+                    copy_stream.wait_event(done[i + 1 - NS])   # the buffer's previous reader has finished
+                ev = h2d(i + 1)
+            out.tolist()     # D2H of the losses every step
+        x1.record()
+        barrier()
+    te = torch.tensor([x0.elapsed_time(x1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    return float(te.item()) / KE, h2d_bytes, KE
+
+
+def wide_gan_flop_per_sample(S=WIDE_S, P=4, Mt=WIDE_MT, gh=(2048, 2048), dh=(2048, 2048), fh=WIDE_HIDDEN) -> int:
+    """Minimal necessary FLOPs of one PI-GAN step per sample, the formula behind FLOP_PER_TRAIN_SAMPLE:
+    G forward once (the two forwards of the reference see the same weights and batch) + backward; D forward on real and
+    fake rows + dW + dX of its upper layers (D-step); D forward + dX down to the 4 parameter inputs (G-step); surrogate
+    forward (no gradient flows through it: train_pigan.py:156-157)."""
+    g1, g2, g3 = S * gh[0], gh[0] * gh[1], gh[1] * P
+    d1, d2, d3 = (S + P) * dh[0], dh[0] * dh[1], dh[1]
+    G, D = g1 + g2 + g3, d1 + d2 + d3
+    dims = [P, *fh, S + Mt]
+    F = sum(dims[i] * dims[i + 1] for i in range(6))
+    macs = (2 * G + g2 + g3) + (4 * D + 2 * (d2 + d3)) + (D + d3 + d2 + P * dh[0]) + F
+    return 2 * macs
+
+
+def wide_gan_block(dev, world, rank, B, K, W, peaks, barrier, with_e2e: bool):
+    """PI-GAN train step at the BASELINE config-5 widths: generator 2048 -> 2048 -> 2048 -> 4, discriminator
+    2052 -> 2048 -> 2048 -> 1, frozen surrogate 4 -> 2048 x 5 -> 2056, 2048-point spectra; data parallel = the engine's
+    seven phases with NCCL all-reduces of the BatchNorm sums, the two 34 MB gradients and the loss sums between them."""
+    import torch.distributed as dist
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from pigan_b200 import engine as E
+    from pigan_b200.trainer import NativeTrainer
+    torch.manual_seed(11)
+    G = Generator(WIDE_S, 4, hidden=(2048, 2048))
+    D = Discriminator(WIDE_S, 4, hidden=(2048, 2048))
+    F = ForwardModel(4, WIDE_S, WIDE_MT, hidden=WIDE_HIDDEN)
+    F.eval()
+    tr = NativeTrainer(G, D, F, dev, max_batch=B)
+    g = torch.Generator(device=dev)
+    g.manual_seed(200 + rank)
+    NS = 2   # 2 x 537 MB of spectra > 126 MB L2
+    sets = [(-3.0 * torch.rand(B, WIDE_S, device=dev, generator=g),
+             2.2 + 0.6 * torch.rand(B, 4, device=dev, generator=g),
+             torch.rand(B, WIDE_MT, device=dev, generator=g)) for _ in range(NS)]
+    lr = 2e-4
+    for i in range(W):
+        tr.step(*sets[i % NS], lr, lr)
+    barrier()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        tr.step(*sets[i % NS], lr, lr)
+    e1.record()
+    barrier()
+    launches = E.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    losses = tr.losses.tolist()
+    tr.engine.profile_begin(None)   # every section, one stream
+    for i in range(K):
+        tr.step(*sets[i % NS], lr, lr)
+    barrier()
+    prof = tr.engine.profile_end()
+    sections = {k: round(v[1] / K, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    gemm_ms = sum(v for k, v in sections.items() if k.endswith("_gemm"))
+    hid_cnt, hid_ms = prof.get("f_hidden_gemm", (0, 0.0))
+    flop = wide_gan_flop_per_sample()
+    tfl = B * flop / (ms * 1e-3) / 1e12
+    info = {"metric": "widened PI-GAN train samples/s", "value": B * world / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "batch_per_gpu": B, "ms_per_step": ms, "steps": K,
+            "widths": {"spectrum_dim": WIDE_S, "metrics_dim": WIDE_MT, "generator": [2048, 2048],
+                       "discriminator": [2048, 2048], "surrogate": list(WIDE_HIDDEN)},
+            "params": {"generator": int(tr.g_grads.numel()), "discriminator": int(tr.d_grads.numel())},
+            "exchange": "none (one GPU)" if world == 1 else
+            "NCCL all-reduce between the engine's phases: BatchNorm sums (4 x 16 KB), the discriminator's and the "
+            "generator's gradients (34 MB each), loss sums",
+            "flop_per_sample": flop, "gpu_launches_per_step": launches / K,
+            "step_roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tflops"], "unit": "TFLOP/s per GPU",
+                              "frac": tfl / peaks["tflops"], "frac_of_burst_peak": tfl / peaks["tflops_burst"]},
+            "section_ms_per_step_one_stream": sections, "gemm_ms_per_step": gemm_ms,
+            "losses_last_step": {"d": losses[0], "g": losses[1], "adv": losses[2]}}
+    if hid_cnt:
+        ach = 2 * 2048 * 2048 * B / (hid_ms / hid_cnt * 1e-3) / 1e12
+        info["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel<EpiStore, row statistics> (frozen surrogate's "
+                            "hidden layers 2048 -> 2048; the generator's / discriminator's 2048-wide layers run the same "
+                            "kernel family)", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": ach / peaks["tflops"], "frac_of_burst_peak": ach / peaks["tflops_burst"],
+                            "traffic": None, "launches_timed": hid_cnt, "share_of_step": hid_ms / K / ms}
+    if with_e2e:
+        ems, h2d_bytes, KE = e2e_from_host(dev, world, sets, lambda t_: tr.step(*t_, lr, lr), max(3, K // 2), barrier)
+        info["e2e"] = {"value": B * world / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
+                       "d2h_bytes_per_step": 36, "ms_per_step": ems, "steps": KE,
+                       "api": "NativeTrainer.step(spectrum, params_denorm, metrics_norm) on batches copied from pinned "
+                              "host tensors (copy stream, double buffered), 9 losses read back every step",
+                       "h2d_gbs": h2d_bytes / (ems * 1e-3) / 1e9}
+    del sets, tr
+    torch.cuda.empty_cache()
+    return info
+
+
+def cpu_wide_train_baseline(batch: int, budget_s: float, threads: int, max_steps: int = 20):
+    """oracle/models.py train_step (width-agnostic) at the config-5 widths on the host cores."""
+    from oracle import models as O
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(3)
+    g_sd = O.init_generator(WIDE_S, 4, (2048, 2048), gen)
+    d_sd = O.init_discriminator(WIDE_S, 4, (2048, 2048), gen)
+    f_sd = O.init_forward_model(4, WIDE_S, WIDE_MT, WIDE_HIDDEN, gen=gen)
+    og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
+    spec = -3.0 * torch.rand(batch, WIDE_S, generator=gen)
+    praw = 2.2 + 0.6 * torch.rand(batch, 4, generator=gen)
+    mnorm = torch.rand(batch, WIDE_MT, generator=gen)
+    b = (spec, praw, (praw - 2.2) / 0.6 * 2 - 1, None, mnorm)
+    O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        O.train_step(g_sd, d_sd, f_sd, og, od, b, 2e-4, 2e-4)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= max_steps:
+            break
+    return batch * n / el, n, el
+
+
 def wide_surrogate_block(dev, world, rank, B, K, W, peaks, barrier, with_e2e: bool):
     """Training step of the surrogate at the config-5 widths (4 -> 2048 x 5 -> 2048 + 8) on a surrogate-only engine:
     replicas + NCCL all-reduce of the 84 MB gradient under data parallelism (fwd_trainer.ForwardTrainer)."""
@@ -325,50 +488,12 @@ def wide_surrogate_block(dev, world, rank, B, K, W, peaks, barrier, with_e2e: bo
                             "frac_of_burst_peak": ach / peaks["tflops_burst"], "traffic": None,
                             "launches_timed": hid_cnt, "share_of_step": hid_ms / K / ms}
     if with_e2e:
-        # the same step fed from pinned host tensors (H2D of params / spectra / metrics inside the timed region)
-        host = [tuple(x.cpu().pin_memory() for x in s_) for s_ in sets]
-        devb = [tuple(torch.empty_like(x) for x in s_) for s_ in sets]
-        copy_stream = torch.cuda.Stream(device=dev)
-        h2d_bytes = sum(x.numel() * 4 for x in host[0])
-
-        def h2d(i):
-            with torch.cuda.stream(copy_stream):
-                for d_, h_ in zip(devb[i % NS], host[i % NS]):
-                    d_.copy_(h_, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return ev
-
-        KE = max(3, K // 2)
-        for rep_ in range(2):
-            barrier()
-            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            x0.record()
-            ev = h2d(0)
-            last = None
-            for i in range(KE):
-                torch.cuda.current_stream().wait_event(ev)
-                out = ftr.step(*devb[i % NS], 1e-3)
-                done = torch.cuda.Event()
-                done.record()
-                if i + 1 < KE:
-                    if NS == 2 and i >= 1:
-                        copy_stream.wait_event(prev_done)   # buffer (i+1) % 2 was read by step i-1
-                    ev = h2d(i + 1)
-                prev_done = done
-                last = out.tolist()     # D2H of the three losses every step
-            x1.record()
-            barrier()
-        te = torch.tensor([x0.elapsed_time(x1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ems = float(te.item()) / KE
+        ems, h2d_bytes, KE = e2e_from_host(dev, world, sets, lambda t: ftr.step(*t, 1e-3), max(3, K // 2), barrier)
         info["e2e"] = {"value": B * world / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                        "d2h_bytes_per_step": 12, "ms_per_step": ems, "steps": KE,
                        "api": "ForwardTrainer.step on batches copied from pinned host tensors (copy stream, double "
                               "buffered), 3 losses read back every step",
                        "h2d_gbs": h2d_bytes / (ems * 1e-3) / 1e9}
-        del host, devb
     del sets, ftr
     torch.cuda.empty_cache()
     return info
@@ -395,32 +520,36 @@ def run_wide(args):
         torch.cuda.synchronize()
 
     peaks = read_peaks()
+    K, W = args.steps, max(3, args.warmup)
     clocks = ClockSampler(local)
     clocks.start()
-    info = wide_surrogate_block(dev, world, rank, args.batch, args.steps, max(3, args.warmup), peaks, barrier, True)
+    info = wide_gan_block(dev, world, rank, args.batch, K, W, peaks, barrier, True)
     clk = clocks.stop()
+    sur = wide_surrogate_block(dev, world, rank, args.batch, max(3, min(K, 10)), 3, peaks, barrier, world == 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, n, el = cpu_wide_pretrain_baseline(1024, 12.0, cores)
+        v, n, el = cpu_wide_train_baseline(1024, 15.0, cores)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": f"{n} steps of batch 1024 in {el:.1f} s (oracle/models.py pretrain_step at the same widths, "
-                         f"fp32, torch CPU)"}
+               "sample": f"{n} steps of batch 1024 in {el:.1f} s (oracle/models.py train_step at the same widths, fp32, "
+                         f"torch CPU)"}
+        v, n, el = cpu_wide_pretrain_baseline(1024, 8.0, cores)
+        sur["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} steps of batch 1024 in {el:.1f} s (oracle/models.py pretrain_step)"}
     if rank == 0:
         out = {"metric": info["metric"], "value": info["value"], "unit": "samples/s", "n_gpus": world,
-               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": info["ms_per_step"],
+               "steps": K, "warmup": W, "ms_per_step": info["ms_per_step"],
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f16 operands, f32 accumulate/master", "data": "synthetic",
-               "config": {"workload": f"forward-surrogate training step at the BASELINE config-5 widths (4 -> 2048 x 5 "
-                                      f"-> 2048 + 8, Dropout 0.2, 2 MSE losses, clip + Adam), batch {args.batch} per GPU",
+               "config": {"workload": f"PI-GAN train step (D-step + G-step, frozen surrogate, 7 losses, clip+Adam) at the "
+                                      f"BASELINE config-5 widths: generator 2048-2048-2048-4, discriminator "
+                                      f"2052-2048-2048-1, surrogate 4-2048x5-2056, S=2048, batch {args.batch} per GPU",
                           "global_batch": args.batch * world, "parallelism": f"dp{world}",
-                          "exchange": info["gradient_exchange"],
-                          "l2": "2 distinct input batches rotated (1.07 GB > 126 MB L2)",
-                          "scope": "the surrogate only: generator / discriminator stay at the reference widths "
-                                   "(DESIGN.md section 7)"},
+                          "exchange": info["exchange"],
+                          "l2": "2 distinct input batches rotated (1.07 GB > 126 MB L2)"},
                "roofline": info.get("roofline"), "step_roofline": info["step_roofline"], "cpu_baseline": cpu,
-               "e2e": info.get("e2e"), "gpu_launches": int(info["gpu_launches_per_step"] * args.steps),
-               "clocks": clk, "wide_surrogate_training": info}
+               "e2e": info.get("e2e"), "gpu_launches": int(info["gpu_launches_per_step"] * K),
+               "clocks": clk, "wide_pigan_training": info, "wide_surrogate_training": sur}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -919,9 +1048,10 @@ def run_native(args):
 
     # ---- widened surrogate (BASELINE config 5 widths: hidden 2048, 2048-point spectra) on its own surrogate-only
     # engine, a few steps (the `--config wide` line times it on its own, with an end-to-end leg)
-    wide_info = None
+    wide_info = wide_gan_info = None
     if not args.no_wide:
         wide_info = wide_surrogate_block(dev, world, rank, min(B, 65536), max(3, min(K, 8)), 3, peaks, barrier, False)
+        wide_gan_info = wide_gan_block(dev, world, rank, min(B, 65536), max(3, min(K, 6)), 3, peaks, barrier, False)
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None
@@ -961,6 +1091,7 @@ def run_native(args):
             "scoring": score_info,
             "physics": phys_info,
             "surrogate_training": fwd_info,
+            "wide_pigan_training": wide_gan_info,
             "wide_surrogate_training": wide_info,
             "evaluator_reductions": eval_info,
             "data_pipeline": pipe_info,
