@@ -97,11 +97,15 @@ int pigan_physics_metrics_backward(const float* spectra, int64_t n, int32_t s, c
  * same engine.  max_batch bounds the rows any later call may pass.
  *
  * dims: NULL or pigan_default_dims() = the reference widths: every entry point below.  Other dims (BASELINE config 5:
- * hidden 2048, 2048-point spectra; the ForwardModel stack of core/models/forward_model.py:28-60 at other widths)
- * create a SURROGATE-ONLY engine: param_dim 4, even spectrum_dim / metrics_dim with their sum padded to 64 <= 2560,
- * every f_hidden width one of 256 / 512 / 1024 / 2048 (g_hidden / d_hidden are ignored).  Such an engine serves
- * pigan_engine_load_forward_model, pigan_forward_model_forward / _vjp / _input_grad and pigan_fwd_train_step[_phase];
- * the generator / discriminator / train-step / scoring / search entry points return PIGAN_ERR_UNSUPPORTED on it.
+ * hidden 2048, 2048-point spectra; the reference's Generator / Discriminator / ForwardModel stacks at other widths)
+ * select generic-width code paths:
+ *   - param_dim 4, even spectrum_dim / metrics_dim with their sum padded to 64 <= 2560, every f_hidden width one of
+ *     256 / 512 / 1024 / 2048: the surrogate's entry points - pigan_engine_load_forward_model,
+ *     pigan_forward_model_forward / _vjp / _input_grad, pigan_fwd_train_step[_phase];
+ *   - in addition spectrum_dim a multiple of 64 (<= 2048) and g_hidden / d_hidden multiples of 256 (<= 2048): the
+ *     PI-GAN step, pigan_train_step[_phase], with fp32 spectrum / params_denorm inputs (no prepared operand).
+ * The stand-alone generator / discriminator forward and backward entry points, scoring, model validation and the
+ * inverse-design search run at the reference widths only and return PIGAN_ERR_UNSUPPORTED otherwise.
  * Anything else: pigan_engine_workspace_bytes returns 0 and pigan_engine_create PIGAN_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct PiganEngine PiganEngine;

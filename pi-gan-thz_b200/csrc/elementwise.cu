@@ -1248,21 +1248,50 @@ __global__ void __launch_bounds__(kThreads) ln_lrelu_apply_kernel(__half* __rest
   ld_f8(gamma + m.ch * 8, gm);
   ld_f8(beta + m.ch * 8, bt);
   const float inv_n = 1.0f / (float)N;
-  for (long long r = (long long)blockIdx.x * m.rpb + m.rg; r < rows; r += (long long)gridDim.x * m.rpb) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const float2 st = __ldg(reinterpret_cast<const float2*>(rowstats) + r * n_tiles + t);
-      s1 += st.x;
-      s2 += st.y;
-    }
-    const float mean = s1 * inv_n;
-    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-    const float rstd = 1.0f / sqrtf(var + kLnEps);
-    float v[8];
-    ld_h8(h + r * N + m.ch * 8, v);
+  constexpr int U = 4;   // rows in flight per thread (one was latency-bound: 40 % of the HBM peak at N = 2048)
+  const long long stride = (long long)gridDim.x * m.rpb;
+  for (long long r0 = (long long)blockIdx.x * m.rpb + m.rg; r0 < rows; r0 += U * stride) {
+    uint4 raw[U];
+    float mean[U], rstd[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = lrelu_f(fmaf((v[i] - mean) * rstd, gm[i], bt[i]));
-    st_h8(h + r * N + m.ch * 8, v);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride < rows ? r0 + u * stride : rows - 1;
+      raw[u] = *reinterpret_cast<const uint4*>(h + r * N + m.ch * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride < rows ? r0 + u * stride : rows - 1;
+      // up to 8 partials per row (N <= 2048), fully unrolled and predicated: the loads issue back to back (the rolled
+      // loop paid one L2 latency per partial)
+      float s1 = 0.f, s2 = 0.f;
+      const float2* rs = reinterpret_cast<const float2*>(rowstats) + r * n_tiles;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < n_tiles) {
+          const float2 st = __ldg(rs + t);
+          s1 += st.x;
+          s2 += st.y;
+        }
+      }
+      mean[u] = s1 * inv_n;
+      rstd[u] = 1.0f / sqrtf(fmaxf(s2 * inv_n - mean[u] * mean[u], 0.f) + kLnEps);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      if (r >= rows) break;
+      const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = lrelu_f(fmaf((v[i] - mean[u]) * rstd[u], gm[i], bt[i]));
+      st_h8(h + r * N + m.ch * 8, v);
+    }
   }
 }
 
@@ -2167,49 +2196,67 @@ __global__ void __launch_bounds__(kThreads) wide_head_fwd_kernel(
     float* __restrict__ pden_out, const __half* __restrict__ xc, __half* __restrict__ tail_fake, long long rows,
     int C, int Kp, int S) {
   pdl_wait();
+  constexpr int R = 4;   // rows per warp and trip: the per-column constants (BatchNorm affine, 4 rows of W3) are
+                         // fetched once per chunk for all of them (one row per trip was bound by those L1 reads)
   const int lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * R;
+  for (long long r0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; r0 < rows; r0 += wstride) {
+    float acc[R][4];
+#pragma unroll
+    for (int u = 0; u < R; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
     for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float h[8], sc[8], bi[8];
-      ld_h8(h2 + row * C + c0, h);
+      float sc[8], bi[8], w[4][8], h[R][8];
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const long long row = r0 + u < rows ? r0 + u : rows - 1;
+        ld_h8(h2 + row * C + c0, h[u]);
+      }
       ld_f8(scale + c0, sc);
       ld_f8(bias + c0, bi);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) h[i] = fmaxf(fmaf(sc[i], h[i], bi[i]), 0.f);
+      for (int e = 0; e < 4; ++e) ld_f8(w3 + (size_t)e * C + c0, w[e]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float w[8];
-        ld_f8(w3 + (size_t)e * C + c0, w);
+      for (int u = 0; u < R; ++u) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[e] = fmaf(h[i], w[i], acc[e]);
+        for (int i = 0; i < 8; ++i) h[u][i] = fmaxf(fmaf(sc[i], h[u][i], bi[i]), 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[u][e] = fmaf(h[u][i], w[e][i], acc[u][e]);
       }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] = warp_sum_f(acc[e]);
-    const float mine = (lane & 3) == 0 ? acc[0] : (lane & 3) == 1 ? acc[1] : (lane & 3) == 2 ? acc[2] : acc[3];
-    const float pv = tanhf(mine + __ldg(b3 + (lane & 3)));        // every lane: parameter lane % 4
-    const float pd = (pv + 1.0f) / 2.0f * 0.6f + 2.2f;             // data_loader.py:238-252
-    if (lane < 4) {
-      p_out[row * 4 + lane] = pv;
-      if (pden_out) pden_out[row * 4 + lane] = pd;
-    }
-    if (tail_fake != nullptr) {
-      // last 64 operand columns of the row (8 chunks of 16 bytes), parameter columns replaced
-      const int t0 = Kp - 64;
-      float pr[4];
+    for (int u = 0; u < R; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pr[e] = __shfl_sync(0xffffffffu, pd, e);
-      if (lane < 8) {
-        float v[8];
-        ld_h8(xc + row * Kp + t0 + lane * 8, v);
+      for (int e = 0; e < 4; ++e) acc[u][e] = warp_sum_f(acc[u][e]);
+    const float b3l = __ldg(b3 + (lane & 3));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int e = t0 + lane * 8 + k - S;
-          if (e >= 0 && e < 4) v[k] = pr[e] - kParamCenter;
+    for (int u = 0; u < R; ++u) {
+      const long long row = r0 + u;
+      if (row >= rows) break;   // uniform across the warp
+      const float mine = (lane & 3) == 0 ? acc[u][0] : (lane & 3) == 1 ? acc[u][1] : (lane & 3) == 2 ? acc[u][2] : acc[u][3];
+      const float pv = tanhf(mine + b3l);                            // every lane: parameter lane % 4
+      const float pd = (pv + 1.0f) / 2.0f * 0.6f + 2.2f;             // data_loader.py:238-252
+      if (lane < 4) {
+        p_out[row * 4 + lane] = pv;
+        if (pden_out) pden_out[row * 4 + lane] = pd;
+      }
+      if (tail_fake != nullptr) {
+        // last 64 operand columns of the row (8 chunks of 16 bytes), parameter columns replaced
+        const int t0 = Kp - 64;
+        float pr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pr[e] = __shfl_sync(0xffffffffu, pd, e);
+        if (lane < 8) {
+          float v[8];
+          ld_h8(xc + row * Kp + t0 + lane * 8, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int e = t0 + lane * 8 + k - S;
+            if (e >= 0 && e < 4) v[k] = pr[e] - kParamCenter;
+          }
+          st_h8(tail_fake + row * 64 + lane * 8, v);
         }
-        st_h8(tail_fake + row * 64 + lane * 8, v);
       }
     }
   }
@@ -2266,7 +2313,7 @@ __global__ void __launch_bounds__(kThreads) d_logit_bce_kernel(const __half* __r
 // Surrogate losses of the G-step (train_pigan.py:156-172) from the widened output layer's fp32 slabs: per row
 // recon = slab + bias; sums[0] += sum (recon - x)^2, [1] += sum (pm - m)^2, [2] += sum of squared second differences
 // (loss.py:29-64), [3], [4] += the two LC terms (loss.py:67-101); dp_lc [rows, 4] = lambda_lc * dLC/dp * GS (no gradient
-// through F: the reference evaluates it under no_grad).  A block per row; the row is staged in shared memory.
+// through F: the reference evaluates it under no_grad).
 __global__ void __launch_bounds__(kThreads) f_pigan_loss_slab_kernel(const float* __restrict__ slab, int ngroups,
                                                                      const float* __restrict__ bias,
                                                                      const float* __restrict__ spectrum,
@@ -2276,42 +2323,67 @@ __global__ void __launch_bounds__(kThreads) f_pigan_loss_slab_kernel(const float
                                                                      float lc_grad_mult, double* __restrict__ sums,
                                                                      float* __restrict__ dp_lc) {
   pdl_wait();
-  extern __shared__ float row_sm[];   // [S + Mt]
+  // A warp per row, a lane owns the column pairs (2 lane + 64 j, +1): S and Mt are even, so a pair never straddles the
+  // spectrum / metrics boundary.  The second difference at a column needs its two left neighbours: they are the
+  // previous lane's pair (a shuffle) or, for lane 0, the last pair of the previous 64-column chunk (carried along).
   __shared__ float red[8];
+  const int lane = threadIdx.x & 31;
   const int OUT = S + Mt;
   float rec = 0.f, met = 0.f, mx = 0.f, lc1 = 0.f, lc2 = 0.f;
-  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
-    __syncthreads();   // the previous row has been consumed
-    for (int c = 2 * (int)threadIdx.x; c < OUT; c += 2 * (int)blockDim.x) {
-      const float2 v = *reinterpret_cast<const float2*>(slab + slab_index(r, c, ngroups));
-      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + c));
-      row_sm[c] = v.x + b.x;
-      row_sm[c + 1] = v.y + b.y;
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < OUT; c += blockDim.x) {
-      const float o = row_sm[c];
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+    float carry_x = 0.f, carry_y = 0.f;   // recon[c0 - 2], recon[c0 - 1] of the chunk being processed
+    float f1 = 0.f, f2 = 0.f;
+#pragma unroll 2
+    for (int c0 = 0; c0 < OUT; c0 += 64) {
+      const int c = c0 + 2 * lane;
+      const bool in = c < OUT;
+      float2 o = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
+      if (in) {
+        const float2 v = *reinterpret_cast<const float2*>(slab + slab_index(r, c, ngroups));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(bias + c));
+        o = make_float2(v.x + b.x, v.y + b.y);
+        t = c < S ? __ldg(reinterpret_cast<const float2*>(spectrum + r * S + c))
+                  : __ldg(reinterpret_cast<const float2*>(metrics + r * Mt + (c - S)));
+      }
+      float left_x = __shfl_up_sync(0xffffffffu, o.x, 1), left_y = __shfl_up_sync(0xffffffffu, o.y, 1);
+      if (lane == 0) {
+        left_x = carry_x;
+        left_y = carry_y;
+      }
+      carry_x = __shfl_sync(0xffffffffu, o.x, 31);
+      carry_y = __shfl_sync(0xffffffffu, o.y, 31);
+      if (!in) continue;
+      const float d0 = o.x - t.x, d1 = o.y - t.y;
       if (c < S) {
-        const float d = o - __ldg(spectrum + r * S + c);
-        rec = fmaf(d, d, rec);
-        if (c >= 2) {
-          const float d2 = (o - row_sm[c - 1]) - (row_sm[c - 1] - row_sm[c - 2]);
-          mx = fmaf(d2, d2, mx);
+        rec = fmaf(d0, d0, fmaf(d1, d1, rec));
+        if (c >= 2) {   // loss.py:51-53: difference of differences at columns c and c + 1
+          const float da = (o.x - left_y) - (left_y - left_x);
+          const float db = (o.y - o.x) - (o.x - left_y);
+          mx = fmaf(da, da, fmaf(db, db, mx));
         }
       } else {
-        const float d = o - __ldg(metrics + r * Mt + (c - S));
-        met = fmaf(d, d, met);
+        met = fmaf(d0, d0, fmaf(d1, d1, met));
+        const int k = c - S;
+        if (k == f1_idx) f1 = o.x;
+        if (k + 1 == f1_idx) f1 = o.y;
+        if (k == f2_idx) f2 = o.x;
+        if (k + 1 == f2_idx) f2 = o.y;
       }
     }
-    if (threadIdx.x == 0 && p_norm != nullptr) {
-      const float4 pn = __ldg(reinterpret_cast<const float4*>(p_norm) + r);
-      const float e1 = row_sm[S + f1_idx] - (0.4f * pn.x + 0.6f * pn.z);
-      const float e2 = row_sm[S + f2_idx] - (0.3f * pn.y + 0.7f * pn.w);
-      lc1 = fmaf(e1, e1, lc1);
-      lc2 = fmaf(e2, e2, lc2);
-      if (dp_lc) {
-        const float m = -2.f * lc_grad_mult;
-        *reinterpret_cast<float4*>(dp_lc + r * 4) = make_float4(m * e1 * 0.4f, m * e2 * 0.3f, m * e1 * 0.6f, m * e2 * 0.7f);
+    if (p_norm != nullptr) {
+      f1 = warp_sum_f(f1);   // one lane holds each value, the others zero
+      f2 = warp_sum_f(f2);
+      if (lane == 0) {
+        const float4 pn = __ldg(reinterpret_cast<const float4*>(p_norm) + r);
+        const float e1 = f1 - (0.4f * pn.x + 0.6f * pn.z);
+        const float e2 = f2 - (0.3f * pn.y + 0.7f * pn.w);
+        lc1 = fmaf(e1, e1, lc1);
+        lc2 = fmaf(e2, e2, lc2);
+        if (dp_lc) {
+          const float m = -2.f * lc_grad_mult;
+          *reinterpret_cast<float4*>(dp_lc + r * 4) = make_float4(m * e1 * 0.4f, m * e2 * 0.3f, m * e1 * 0.6f, m * e2 * 0.7f);
+        }
       }
     }
   }
@@ -2447,7 +2519,7 @@ void launch_g_head_fwd(const __half* h2, const float* scale, const float* bias, 
                        float* p_out, float* pden_out, const __half* xc, __half* tail_fake, int64_t rows, int C,
                        int Kp, int S, cudaStream_t st) {
   if (C != 256) {   // the register layout of g_head_fwd_kernel is the reference width's
-    launch_k(wide_head_fwd_kernel, grid_for_rows(rows, 8 * 4, 148 * 8), kThreads, 0, st, h2, scale, bias, w3, b3, p_out,
+    launch_k(wide_head_fwd_kernel, grid_for_rows(rows, 8 * 4 * 2, 148 * 8), kThreads, 0, st, h2, scale, bias, w3, b3, p_out,
              pden_out, xc, tail_fake, (long long)rows, C, Kp, S);
     return;
   }
@@ -2464,7 +2536,7 @@ void launch_d_logit_bce(const __half* z2, const float* w3, const float* b3, int6
 void launch_f_pigan_loss_slab(const float* slab, int ngroups, const float* bias, const float* spectrum,
                               const float* metrics, const float* p_norm, int64_t rows, int S, int Mt, int f1_idx,
                               int f2_idx, float lc_grad_mult, double* sums, float* dp_lc, cudaStream_t st) {
-  launch_k(f_pigan_loss_slab_kernel, grid_for_rows(rows, 8, 148 * 8), kThreads, (size_t)(S + Mt) * sizeof(float), st,
+  launch_k(f_pigan_loss_slab_kernel, grid_for_rows(rows, 8 * 4, 148 * 8), kThreads, 0, st,
            slab, ngroups, bias, spectrum, metrics, p_norm, (long long)rows, S, Mt, f1_idx, f2_idx, lc_grad_mult, sums,
            dp_lc);
 }
@@ -2570,7 +2642,7 @@ void launch_f_l1(const float* p, const float* w1, const float* b1, const float* 
 void launch_ln_lrelu_apply(__half* h, const float* rowstats, int n_tiles, const float* gamma, const float* beta,
                            int64_t rows, int N, cudaStream_t st) {
   const int rpb = kThreads / (N / 8);
-  launch_k(ln_lrelu_apply_kernel, grid_for_rows(rows, rpb * 4), kThreads, 0, st, h, rowstats, n_tiles, gamma, beta, rows, N);
+  launch_k(ln_lrelu_apply_kernel, grid_for_rows(rows, rpb * 4 * 2), kThreads, 0, st, h, rowstats, n_tiles, gamma, beta, rows, N);
 }
 void launch_zero_buffers(float* const* ptrs, const int64_t* nfloat, int count, cudaStream_t st) {
   ZeroArgs a;
