@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PI-GAN-THz hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B] [--config wide]
 
 Native arm: one "step" is one D-step + G-step of train_pigan's inner loop (core/train/train_pigan.py:114-187) at
 batch B per GPU (default 65 536 = BASELINE config 2) on synthetic spectra of the dataset's shape, through the C ABI
@@ -10,6 +10,11 @@ buffers (H2D of the batch and D2H of the 9 losses inside the timed region).  The
 inverse-design scoring throughput (candidates/s, `scoring`), the roofline of the dominant kernel measured with CUDA
 events inside the timed region, a CPU baseline (the oracle port of the reference step on the host cores) and the
 clocks seen during the timed region.
+
+--config wide: the line is the same step at the BASELINE config-5 widths (generator 2048-2048-2048-4, discriminator
+2052-2048-2048-1, surrogate 4-2048x5-2056, 2048-point spectra; 193 MFLOP per sample) with its own roofline, e2e and
+CPU-port legs, and the widened surrogate-training step beside it; the default line carries both as side blocks
+(`wide_pigan_training`, `wide_surrogate_training`).
 
 Reference arm (--impl reference): the reference's CPU PyTorch path — restated in oracle/models.py and pinned to the
 reference itself by tests/golden — timed on the host cores, on a bounded sample of the same workload.
@@ -1050,8 +1055,15 @@ def run_native(args):
     # engine, a few steps (the `--config wide` line times it on its own, with an end-to-end leg)
     wide_info = wide_gan_info = None
     if not args.no_wide:
-        wide_info = wide_surrogate_block(dev, world, rank, min(B, 65536), max(3, min(K, 8)), 3, peaks, barrier, False)
-        wide_gan_info = wide_gan_block(dev, world, rank, min(B, 65536), max(3, min(K, 6)), 3, peaks, barrier, False)
+        # (side blocks of the line: a host-side failure here must not cost the headline numbers above)
+        try:
+            wide_info = wide_surrogate_block(dev, world, rank, min(B, 65536), max(3, min(K, 8)), 3, peaks, barrier, False)
+        except Exception as exc:   # noqa: BLE001
+            wide_info = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            wide_gan_info = wide_gan_block(dev, world, rank, min(B, 65536), max(3, min(K, 6)), 3, peaks, barrier, False)
+        except Exception as exc:   # noqa: BLE001
+            wide_gan_info = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port of the reference step on the host cores
     cpu = None
