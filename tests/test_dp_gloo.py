@@ -21,10 +21,9 @@ def _init(rank, world, port):
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
 
-def _schedule_worker(rank, world, port, out):
+def _schedule_worker(rank, world, port, out, h1=512, h2=256):
     _init(rank, world, port)
     from pigan_b200.trainer import dp_phase_plan, run_dp_step
-    h1, h2 = 512, 256
     g = torch.Generator().manual_seed(100 + rank)
     bufs = {"bn_sums": torch.rand(2 * h1 + 2 * h2, generator=g), "bn_bwd_sums": torch.rand(2 * h1 + 2 * h2, generator=g),
             "d_grads": torch.rand(1000, generator=g), "g_grads": torch.rand(1200, generator=g),
@@ -84,6 +83,15 @@ def _spawn(fn, port):
 
 def test_dp_schedule_reduces_every_buffer_once_in_phase_order():
     assert _spawn(_schedule_worker, 29611) == {0: True, 1: True}
+
+
+def _wide_schedule_worker(rank, world, port, out):
+    _schedule_worker(rank, world, port, out, h1=2048, h2=2048)
+
+
+def test_dp_schedule_at_the_widened_generator_widths():
+    """BASELINE config 5 (generator 2048 / 2048): the same seven phases, the BatchNorm slices follow the widths."""
+    assert _spawn(_wide_schedule_worker, 29617) == {0: True, 1: True}
 
 
 def test_sharded_topk_gather_merge_matches_global_topk():

@@ -51,3 +51,26 @@ def test_module_takes_widths():
     assert d.spectrum_dim == 2048 and tuple(d.f_hidden) == (2048,) * 5
     with pytest.raises(ValueError):
         ForwardModel(4, 250, 8, hidden=(256, 512))
+
+
+def test_trainer_reads_the_dims_off_the_modules():
+    from core.models.discriminator import Discriminator
+    from core.models.forward_model import ForwardModel
+    from core.models.generator import Generator
+    from pigan_b200 import native
+    from pigan_b200.trainer import NativeTrainer, dp_phase_plan
+    assert NativeTrainer._dims_of(Generator(250, 4), Discriminator(250, 4), ForwardModel(4, 250, 8)) is None
+    G, D = Generator(2048, 4, hidden=(2048, 2048)), Discriminator(2048, 4, hidden=(2048, 2048))
+    F = ForwardModel(4, 2048, 8, hidden=(2048,) * 5)
+    d = NativeTrainer._dims_of(G, D, F)
+    assert (d.spectrum_dim, d.metrics_dim, tuple(d.g_hidden), tuple(d.d_hidden)) == (2048, 8, (2048, 2048), (2048, 2048))
+    assert list(G.state_dict()) == list(Generator(250, 4).state_dict())
+    assert list(D.state_dict()) == list(Discriminator(250, 4).state_dict())
+    # flat layouts of the widened generator / discriminator = the modules' parameter counts
+    assert native.lib.pigan_generator_param_count(C.byref(d)) == sum(p.numel() for p in G.parameters())
+    assert native.lib.pigan_discriminator_param_count(C.byref(d)) == sum(p.numel() for p in D.parameters())
+    with pytest.raises(ValueError):
+        NativeTrainer._dims_of(G, Discriminator(250, 4), F)
+    # the data-parallel plan exchanges BatchNorm slices of the widened widths
+    plan = dict(dp_phase_plan(2048, 2048))
+    assert plan[0] == [("bn_sums", slice(0, 4096))] and plan[1] == [("bn_sums", slice(4096, 8192))]
