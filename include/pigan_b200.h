@@ -102,7 +102,7 @@ int pigan_physics_metrics_backward(const float* spectra, int64_t n, int32_t s, c
  *   - param_dim 4, even spectrum_dim / metrics_dim with their sum padded to 64 <= 2560, every f_hidden width one of
  *     256 / 512 / 1024 / 2048: the surrogate's entry points - pigan_engine_load_forward_model,
  *     pigan_forward_model_forward / _vjp / _input_grad, pigan_fwd_train_step[_phase];
- *   - in addition spectrum_dim a multiple of 64 (<= 2048) and g_hidden / d_hidden multiples of 256 (<= 2048): the
+ *   - in addition spectrum_dim a multiple of 64 (<= 2048) and g_hidden / d_hidden widths of 256 / 512 / 1024 / 2048: the
  *     PI-GAN step, pigan_train_step[_phase], with fp32 spectrum / params_denorm inputs (no prepared operand).
  * The stand-alone generator / discriminator forward and backward entry points, scoring, model validation and the
  * inverse-design search run at the reference widths only and return PIGAN_ERR_UNSUPPORTED otherwise.

@@ -37,7 +37,7 @@ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 // Widened dims on which the PI-GAN step runs (BASELINE config 5: hidden 2048, 2048-point spectra): the surrogate's
 // conditions (surrogate_dims_ok) plus a spectrum length that is a multiple of 64 - the parameter / bias columns then
 // fill the operand's last 64-column k-block, which is what the discriminator's fake rows swap - and generator /
-// discriminator hidden widths that are multiples of 256 up to 2048.
+// discriminator hidden widths of 256 / 512 / 1024 / 2048.
 inline bool wide_gan_dims_ok(const PiganDims& d) {
   if (d.param_dim != 4 || d.metrics_dim < 2 || d.metrics_dim % 2 || d.spectrum_dim < 64 || d.spectrum_dim % 64) return false;
   if ((d.spectrum_dim + d.metrics_dim + 63) / 64 * 64 > 2560 || d.spectrum_dim > 2048) return false;
@@ -45,9 +45,12 @@ inline bool wide_gan_dims_ok(const PiganDims& d) {
     const int h = d.f_hidden[i];
     if (h != 256 && h != 512 && h != 1024 && h != 2048) return false;
   }
+  // (the streaming kernels give a thread 8 or 4 consecutive columns and a block whole rows: widths whose column
+  // chunks divide the 256 threads of a block)
   for (int i = 0; i < 2; ++i) {
-    if (d.g_hidden[i] % 256 || d.g_hidden[i] < 256 || d.g_hidden[i] > 2048) return false;
-    if (d.d_hidden[i] % 256 || d.d_hidden[i] < 256 || d.d_hidden[i] > 2048) return false;
+    const int g = d.g_hidden[i], h = d.d_hidden[i];
+    if (g != 256 && g != 512 && g != 1024 && g != 2048) return false;
+    if (h != 256 && h != 512 && h != 1024 && h != 2048) return false;
   }
   return true;
 }
@@ -1098,7 +1101,7 @@ int check_train_args(PiganEngine* e, const PiganTrainArgs* a) {
   if (!e->gan)
     return fail(PIGAN_ERR_UNSUPPORTED, "this engine's dimensions serve the surrogate only (PI-GAN step: the reference "
                                        "widths, or widened dims with spectrum_dim % 64 == 0 and generator / discriminator "
-                                       "widths that are multiples of 256 up to 2048)");
+                                       "widths of 256 / 512 / 1024 / 2048)");
   if (!e->full && (a->spectrum_operand != nullptr || a->spectrum == nullptr || a->params_denorm == nullptr))
     return fail(PIGAN_ERR_UNSUPPORTED, "widened PI-GAN step: pass fp32 spectrum / params_denorm (no prepared operand)");
   PIGAN_CHECK_ARG(a->batch >= 2 && a->batch <= e->max_batch && a->global_batch >= a->batch);

@@ -198,47 +198,57 @@ def test_wide_engine_serves_the_surrogate_only():
 
 # ------------------------------------------------------------------------------------------ widened PI-GAN step
 GAN_S, GAN_MT, GAN_H = 2048, 8, 2048
+# name -> (spectrum points, generator hidden, discriminator hidden, surrogate hidden)
+GAN_CONFIGS = {
+    "config5": (2048, (2048, 2048), (2048, 2048), (2048,) * 5),
+    "mixed": (512, (1024, 512), (1024, 512), (512, 1024, 2048, 1024, 256)),
+}
 # Gradient bounds by tensor group (norm-wise, against the fp32 oracle); the generator's layers below the last
 # BatchNorm carry the fp16-forward floor of tests/test_quantisation_floor.py (it falls with the batch size)
 # measured on B200: discriminator 7e-4 ... 9e-4; generator head / BatchNorm-2 1.0e-3 ... 1.7e-3; generator below the last
 # BatchNorm 2.0e-3 ... 3.2e-3 at B = 4096, 4.2e-3 ... 6.0e-3 at B = 1000
 TOL_GAN_D = 1.5e-3
 TOL_GAN_G_HEAD = 2.5e-3
-TOL_GAN_G_BODY = {1000: 1e-2, 4096: 5e-3}
+TOL_GAN_G_BODY = {("config5", 1000): 1e-2, ("config5", 4096): 5e-3,
+                  # narrower layers, same batch: 8.5e-3 ... 1.2e-2 measured (the reference widths sit at 8e-3 ... 1.2e-2
+                  # at B = 4096, tests/golden/quantisation_floor.json)
+                  ("mixed", 1000): 2e-2}
 
 
-def _gan_weights(seed=9):
+def _gan_weights(cfg="config5", seed=9):
     from oracle import models as O
+    S, gh, dh, fh = GAN_CONFIGS[cfg]
     gen = torch.Generator().manual_seed(seed)
-    g_sd = O.init_generator(GAN_S, 4, (GAN_H, GAN_H), gen)
-    d_sd = O.init_discriminator(GAN_S, 4, (GAN_H, GAN_H), gen)
-    for bi in (1, 4):   # non-trivial BatchNorm affines and running statistics
-        g_sd[f"main.{bi}.weight"] = 1.0 + (torch.rand(GAN_H, generator=gen) - 0.5)
-        g_sd[f"main.{bi}.bias"] = 0.4 * (torch.rand(GAN_H, generator=gen) - 0.5)
-        g_sd[f"main.{bi}.running_mean"] = 0.6 * (torch.rand(GAN_H, generator=gen) - 0.5)
-        g_sd[f"main.{bi}.running_var"] = 1.0 + 0.8 * (torch.rand(GAN_H, generator=gen) - 0.5)
+    g_sd = O.init_generator(S, 4, gh, gen)
+    d_sd = O.init_discriminator(S, 4, dh, gen)
+    for bi, h in zip((1, 4), gh):   # non-trivial BatchNorm affines and running statistics
+        g_sd[f"main.{bi}.weight"] = 1.0 + (torch.rand(h, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.bias"] = 0.4 * (torch.rand(h, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.running_mean"] = 0.6 * (torch.rand(h, generator=gen) - 0.5)
+        g_sd[f"main.{bi}.running_var"] = 1.0 + 0.8 * (torch.rand(h, generator=gen) - 0.5)
         g_sd[f"main.{bi}.num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
-    f_sd = _weights(GAN_S, GAN_MT, (GAN_H,) * 5)
+    f_sd = _weights(S, GAN_MT, fh)
     return g_sd, d_sd, f_sd
 
 
-def _gan_trainer(g_sd, d_sd, f_sd, B):
+def _gan_trainer(g_sd, d_sd, f_sd, B, cfg="config5"):
     from core.models.discriminator import Discriminator
     from core.models.forward_model import ForwardModel
     from core.models.generator import Generator
     from pigan_b200.trainer import NativeTrainer
-    G = Generator(GAN_S, 4, hidden=(GAN_H, GAN_H))
-    D = Discriminator(GAN_S, 4, hidden=(GAN_H, GAN_H))
-    F = ForwardModel(4, GAN_S, GAN_MT, hidden=(GAN_H,) * 5)
+    S, gh, dh, fh = GAN_CONFIGS[cfg]
+    G = Generator(S, 4, hidden=gh)
+    D = Discriminator(S, 4, hidden=dh)
+    F = ForwardModel(4, S, GAN_MT, hidden=fh)
     G.load_state_dict(g_sd); D.load_state_dict(d_sd); F.load_state_dict(f_sd)
     F.eval()
     tr = NativeTrainer(G, D, F, torch.device(DEV), max_batch=B)
-    assert tr.wide and tuple(tr.engine.dims.g_hidden) == (GAN_H, GAN_H)
+    assert tr.wide and tuple(tr.engine.dims.g_hidden) == tuple(gh)
     return tr, G, D
 
 
-@pytest.mark.parametrize("B", [1000, 4096])
-def test_wide_pigan_step_matches_oracle(B):
+@pytest.mark.parametrize("cfg,B", [("config5", 1000), ("config5", 4096), ("mixed", 1000)])
+def test_wide_pigan_step_matches_oracle(cfg, B):
     """The PI-GAN train step (train_pigan.py:114-187) at the BASELINE config-5 widths - generator 2048 -> 2048 -> 2048
     -> 4, discriminator 2052 -> 2048 -> 2048 -> 1, surrogate 4 -> 2048 x 5 -> 2056 - against the width-agnostic oracle:
     unclipped D gradients (after phase 2), unclipped G gradients (after phase 5), then a whole step: the nine losses,
@@ -248,8 +258,8 @@ def test_wide_pigan_step_matches_oracle(B):
     from oracle import models as O
     from pigan_b200.trainer import LOSS_KEYS
     torch.set_num_threads(os.cpu_count() or 1)
-    g_sd, d_sd, f_sd = _gan_weights()
-    spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=21, num_points=GAN_S)
+    g_sd, d_sd, f_sd = _gan_weights(cfg)
+    spec, praw, pnorm, mnorm = fixtures.make_batch(B, seed=21, num_points=GAN_CONFIGS[cfg][0])
     batch = (spec, praw, pnorm, None, mnorm)
     og, od = O.Adam(O.G_TRAINABLE), O.Adam(O.D_TRAINABLE)
     g2, d2 = copy.deepcopy(g_sd), copy.deepcopy(d_sd)
@@ -257,7 +267,7 @@ def test_wide_pigan_step_matches_oracle(B):
     dev_batch = (spec.to(DEV), praw.to(DEV), mnorm.to(DEV))
 
     def phases(upto):
-        tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B)
+        tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B, cfg)
         tr.step_count += 1
         a = tr._args(*dev_batch, 2e-4, 2e-4)
         for ph in range(upto + 1):
@@ -282,7 +292,7 @@ def test_wide_pigan_step_matches_oracle(B):
             continue
         report["g." + name] = rel(gv[name], ref)
     del tr
-    print(f"\n[wide PI-GAN step B={B}] gradient distance from the fp32 oracle, per tensor")
+    print(f"\n[wide PI-GAN step {cfg} B={B}] gradient distance from the fp32 oracle, per tensor")
     for k, v in report.items():
         print(f"   {k:16s} {v:.2e}")
     for k, v in report.items():
@@ -291,9 +301,9 @@ def test_wide_pigan_step_matches_oracle(B):
         elif k in ("g.main.6.weight", "g.main.6.bias", "g.main.4.weight", "g.main.4.bias"):
             assert v < TOL_GAN_G_HEAD, (k, v)
         else:
-            assert v < TOL_GAN_G_BODY[B], (k, v)
+            assert v < TOL_GAN_G_BODY[(cfg, B)], (k, v)
     # whole step
-    tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B)
+    tr, G, D = _gan_trainer(g_sd, d_sd, f_sd, B, cfg)
     losses = tr.step(*dev_batch, 2e-4, 2e-4).cpu()
     for i, k in enumerate(LOSS_KEYS):
         ref = ref_losses[k]
