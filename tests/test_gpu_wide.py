@@ -1,7 +1,7 @@
-"""Widened surrogate (BASELINE config 5: hidden 2048, 2048-point spectra; the ForwardModel stack of
-core/models/forward_model.py:28-60 at other widths): forward, training step and VJP of a surrogate-only engine
-against the CPU oracle (oracle/models.py is width-agnostic and pinned to the reference at the reference widths by
-tests/test_oracle_golden.py).
+"""Widened variant (BASELINE config 5: hidden 2048, 2048-point spectra; the reference's Generator / Discriminator /
+ForwardModel stacks at other widths): the PI-GAN train step (train_pigan.py:114-187) and the surrogate's forward,
+training step and VJP against the CPU oracle (oracle/models.py is width-agnostic and pinned to the reference at the
+reference widths by tests/test_oracle_golden.py).
 
 Tolerances as in test_gpu_fwd_train.py: fp16 operands / fp32 accumulation, outputs and losses 1e-3; gradients are
 compared norm-wise with batch-dependent bounds (per-sample fp16 rounding noise that averages out with the batch).
@@ -182,7 +182,9 @@ def test_wide_vjp_matches_autograd():
     assert F.model[0].weight.grad is None   # weights frozen on this path
 
 
-def test_wide_engine_serves_the_surrogate_only():
+def test_wide_engine_refuses_the_stand_alone_module_entry_points():
+    """Widened engines run the train step and the surrogate's paths; the generator / discriminator module forwards,
+    scoring and search exist at the reference widths only and must fail loudly, not fall back."""
     from pigan_b200 import engine as E
     from pigan_b200 import native
     dims = native.make_dims(spectrum_dim=2048, f_hidden=(2048,) * 5, g_hidden=(2048, 2048), d_hidden=(2048, 2048))
