@@ -117,8 +117,9 @@ struct PiganEngine {
   FwdLayout fl;
   int64_t max_batch, bp;  // bp = max_batch rounded up to 128: row offset of the fake half in stacked tensors
   size_t ws_bytes;
-  // full = the reference widths: every entry point.  Otherwise the engine serves the surrogate's paths only
-  // (forward, VJP, training step) at the widened dims of BASELINE config 5 - see check_dims
+  // full = the reference widths: every entry point, fused epilogues.  Otherwise (widened dims, BASELINE config 5 -
+  // see check_dims) the engine serves the surrogate's paths (forward, VJP, training step) and, when `gan`, the PI-GAN
+  // train step, all through generic-width pieces
   bool full = true;
   // gan = the PI-GAN train step runs on this engine: the reference widths (fused epilogues), or widened dims the
   // generic-width pieces cover (wide_gan_dims_ok) - then pigan_train_step[_phase] work, the module / scoring entry
@@ -260,8 +261,9 @@ void prof_mark(PiganEngine* e, const char* name, cudaStream_t st) {
 // Widened dims (BASELINE config 5: hidden 2048, 2048-point spectra; the widths of enhanced_forward_model.py:42-49):
 // the surrogate's forward, VJP and training step run at any hidden width of 256/512/1024/2048 and any even S / Mt
 // with round_up(S + Mt, 64) <= 2560, built from the plain store GEMMs + the streaming LayerNorm kernels (no fused
-// LayerNorm / loss epilogues: at these widths the GEMMs are 126 MFLOP per sample and dominate).  The generator /
-// discriminator / PI-GAN step / search entry points stay at the reference widths (need_full).
+// LayerNorm / loss epilogues: at these widths the GEMMs are 126 MFLOP per sample and dominate).  The PI-GAN step
+// runs on the subset wide_gan_dims_ok accepts; the stand-alone generator / discriminator module entry points, scoring
+// and search stay at the reference widths (need_full).
 bool surrogate_dims_ok(const PiganDims& d) {
   if (d.param_dim != 4 || d.spectrum_dim < 2 || d.metrics_dim < 2 || d.spectrum_dim % 2 || d.metrics_dim % 2) return false;
   if ((d.spectrum_dim + d.metrics_dim + 63) / 64 * 64 > 2560) return false;
@@ -275,15 +277,16 @@ int check_dims(const PiganDims& d) {
   if (!dims_are_default(d) && !surrogate_dims_ok(d))
     return fail(PIGAN_ERR_UNSUPPORTED,
                 "dimensions: the full path implements the reference widths (S=250, P=4, Mt=8, G 512/256, D 512/256, "
-                "F 256/512/1024/512/256); the surrogate-only path takes P=4, even S / Mt with S + Mt <= 2560 and "
-                "hidden widths of 256/512/1024/2048");
+                "F 256/512/1024/512/256); the widened paths take P=4, even S / Mt with S + Mt <= 2560 and hidden widths "
+                "of 256/512/1024/2048 (include/pigan_b200.h)");
   return PIGAN_OK;
 }
 int need_full(const PiganEngine* e) {
   if (e && !e->full)
     return fail(PIGAN_ERR_UNSUPPORTED,
-                "this engine was created with widened dimensions: only the surrogate's entry points "
-                "(pigan_forward_model_forward / _vjp / _input_grad, pigan_fwd_train_step) run at those");
+                "this engine was created with widened dimensions: the train step (pigan_train_step[_phase]) and the "
+                "surrogate's entry points (pigan_forward_model_forward / _vjp / _input_grad, pigan_fwd_train_step) run "
+                "at those; this entry point exists at the reference widths only");
   return PIGAN_OK;
 }
 
