@@ -1535,7 +1535,7 @@ struct FTrainWs {
   float* out32;
   __half* dout;
   __half* dbuf[2];
-  __half* wth[6];     // transposed fp16 weights: [in_i, out_i] (layer 5: [256, kDoutLd])
+  __half* wth[6];     // transposed fp16 weights: [in_i, out_i] (layer 5: [256, dout_ld])
   float* grads_scratch;   // [L.total] parameter-gradient sink of pigan_forward_model_input_grad (weights frozen)
   float* dw1_tmp;     // [4][256]
   double* sumsq;
@@ -1545,7 +1545,7 @@ struct FTrainWs {
   size_t carve(void* base, const FwdLayout& L, int64_t B, bool wide = false) {
     Carver c(base);
     const int64_t Bp = round_up(B, 128);
-    const int kDoutLd = (int)round_up(L.OUT, 64);   // 320 at the reference widths
+    const int dout_ld = (int)round_up(L.OUT, 64);   // 320 at the reference widths
     int wmax = 0;
     for (int i = 0; i < 5; ++i) {
       xhat[i] = c.take<__half>((size_t)Bp * L.H[i]);
@@ -1554,12 +1554,12 @@ struct FTrainWs {
       wmax = L.H[i] > wmax ? L.H[i] : wmax;
     }
     out32 = c.take<float>(wide ? 0 : (size_t)Bp * L.OUT);   // widened path: the engine's accumulator slabs instead
-    dout = c.take<__half>((size_t)Bp * kDoutLd);
+    dout = c.take<__half>((size_t)Bp * dout_ld);
     dbuf[0] = c.take<__half>((size_t)Bp * wmax);
     dbuf[1] = c.take<__half>((size_t)Bp * wmax);
     wth[0] = nullptr;
     for (int i = 1; i < 5; ++i) wth[i] = c.take<__half>((size_t)L.H[i - 1] * L.H[i]);
-    wth[5] = c.take<__half>((size_t)L.H[4] * kDoutLd);
+    wth[5] = c.take<__half>((size_t)L.H[4] * dout_ld);
     grads_scratch = c.take<float>((size_t)L.total);
     dw1_tmp = c.take<float>(4 * L.H[0]);
     zero_from = reinterpret_cast<uint8_t*>(dw1_tmp);
@@ -1582,7 +1582,7 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
                     const FwdRunOpts& opt = FwdRunOpts()) {
   const FwdLayout& L = e->fl;
   const int64_t n = a.batch;
-  const int kDoutLd = e->dout_ld;
+  const int dout_ld = e->dout_ld;
   const bool wide = !e->full;   // widened dims: generic first-layer / loss kernels, output layer through the slabs
   float* fp = a.f_params;
   float* gr = opt.input_grad ? w.grads_scratch : a.f_grads;
@@ -1613,22 +1613,22 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
       w.zero_bytes % sizeof(float) == 0) {
     // one kernel instead of four memset stream operations
     float* ptrs[4] = {gr, reinterpret_cast<float*>(w.zero_from), reinterpret_cast<float*>(w.wth[5]), a.loss_sums};
-    const int64_t nf[4] = {L.total, (int64_t)(w.zero_bytes / sizeof(float)), (int64_t)L.H[4] * kDoutLd / 2,
+    const int64_t nf[4] = {L.total, (int64_t)(w.zero_bytes / sizeof(float)), (int64_t)L.H[4] * dout_ld / 2,
                            a.loss_sums ? 2 : 0};
     launch_zero_buffers(ptrs, nf, 4, st);
   } else {
     PIGAN_CUDA_OK(cudaMemsetAsync(gr, 0, (size_t)L.total * sizeof(float), st));
     PIGAN_CUDA_OK(cudaMemsetAsync(w.zero_from, 0, w.zero_bytes, st));
     if (a.loss_sums) PIGAN_CUDA_OK(cudaMemsetAsync(a.loss_sums, 0, 2 * sizeof(float), st));
-    PIGAN_CUDA_OK(cudaMemsetAsync(w.wth[5], 0, (size_t)L.H[4] * kDoutLd * sizeof(__half), st));
+    PIGAN_CUDA_OK(cudaMemsetAsync(w.wth[5], 0, (size_t)L.H[4] * dout_ld * sizeof(__half), st));
   }
   PM("pack_weights");
   for (int i = 1; i < 6; ++i) {
     const int in = L.H[i - 1], out = i < 5 ? L.H[i] : L.OUT;
     launch_cast_pad(fp + L.w[i], in, in, e->f_wh[i], in, out, st);
-    launch_transpose_cast(fp + L.w[i], out, in, in, w.wth[i], i < 5 ? out : kDoutLd, st);
+    launch_transpose_cast(fp + L.w[i], out, in, in, w.wth[i], i < 5 ? out : dout_ld, st);
   }
-  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, kDoutLd > 288 ? kDoutLd : 288, st);
+  launch_copy_pad_f32(fp + L.b[5], L.OUT, e->f_bias_out, dout_ld > 288 ? dout_ld : 288, st);
   // ---- forward (train mode)
   __half* act[5] = {e->f_a1, e->f_a2, e->f_a3, e->f_a4, e->f_a5};
   size_t moff[5];
@@ -1662,22 +1662,22 @@ int fwd_train_phase(PiganEngine* e, const PiganFwdTrainArgs& a, int phase, FTrai
   }
   PM("f_out_loss");
   if (opt.upstream != nullptr)
-    launch_f_upstream_cast(opt.upstream, L.OUT, w.dout, kDoutLd, n, (float)a.global_batch, st);
+    launch_f_upstream_cast(opt.upstream, L.OUT, w.dout, dout_ld, n, (float)a.global_batch, st);
   else if (wide)
-    launch_f_out_loss_slab(e->f_slab, e->out_groups, fp + L.b[5], a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S,
+    launch_f_out_loss_slab(e->f_slab, e->out_groups, fp + L.b[5], a.spectrum, a.metrics_norm, w.dout, dout_ld, n, L.S,
                            L.Mt, e->partials, gr + L.b[5], loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
   else
-    launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, kDoutLd, n, L.S, L.Mt, e->partials, gr + L.b[5],
+    launch_f_out_loss(w.out32, a.spectrum, a.metrics_norm, w.dout, dout_ld, n, L.S, L.Mt, e->partials, gr + L.b[5],
                       loss_sums, inv_gs, st, opt.w_spec, opt.w_met);
   // ---- backward
   PM("f_wgrad_gemm");
   if (!opt.input_grad)
     PIGAN_TRY(weight_grad(w.dout, n, L.OUT, act[4], n, L.H[4], gr + L.w[5], L.H[4], L.H[4], inv_gs, -1, nullptr, 0,
-                          nullptr, 0, e->dw_part, st, kDoutLd));
+                          nullptr, 0, e->dw_part, st, dout_ld));
   PM("f_dgrad_gemm");
   __half* d = w.dbuf[0];
   __half* d2 = w.dbuf[1];
-  PIGAN_TRY((linear_store<false, false, false>(w.dout, n, kDoutLd, w.wth[5], L.H[4], nullptr, d, nullptr, st)));
+  PIGAN_TRY((linear_store<false, false, false>(w.dout, n, dout_ld, w.wth[5], L.H[4], nullptr, d, nullptr, st)));
   for (int i = 4; i >= 0; --i) {
     PM("f_ln_bwd");
     // (widened dims: the first layer goes through the generic kernel too - dh stays in place - and its thin
