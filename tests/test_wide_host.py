@@ -74,3 +74,16 @@ def test_trainer_reads_the_dims_off_the_modules():
     # the data-parallel plan exchanges BatchNorm slices of the widened widths
     plan = dict(dp_phase_plan(2048, 2048))
     assert plan[0] == [("bn_sums", slice(0, 4096))] and plan[1] == [("bn_sums", slice(4096, 8192))]
+
+
+def test_bench_flop_formulas_reproduce_the_reference_width_constants():
+    """bench.py's per-sample FLOP formulas for the widened blocks are the ones behind the reference-width constants
+    (SURVEY 8(d)): evaluated at the reference dims they must give exactly those."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    ref_f = (256, 512, 1024, 512, 256)
+    assert bench.wide_gan_flop_per_sample(250, 4, 8, (512, 256), (512, 256), ref_f) == bench.FLOP_PER_TRAIN_SAMPLE
+    assert bench.wide_flop_per_sample(250, 8, ref_f) == bench.FLOP_PER_PRETRAIN_SAMPLE
+    assert bench.wide_gan_flop_per_sample() == 193_167_360       # BASELINE config 5: "193 MFLOP per sample"
+    assert bench.wide_flop_per_sample() == 125_960_192
