@@ -87,3 +87,28 @@ def test_bench_flop_formulas_reproduce_the_reference_width_constants():
     assert bench.wide_flop_per_sample(250, 8, ref_f) == bench.FLOP_PER_PRETRAIN_SAMPLE
     assert bench.wide_gan_flop_per_sample() == 193_167_360       # BASELINE config 5: "193 MFLOP per sample"
     assert bench.wide_flop_per_sample() == 125_960_192
+
+
+def test_closed_form_layernorm_statistics_of_the_k4_layer():
+    """csrc/elementwise.cu: f_l1_consts_kernel / f_l1_wide_kernel.  For h = W p + b with K = 4 the row statistics over
+    the N columns are closed-form in p: mean = mean_c(W) . p + mean(b), var = p^T A p + 2 p^T B + C with the centred
+    second moments A, B, C (fp64 constants, fp32 evaluation).  Restated in numpy and held to the direct two-pass
+    statistics, also when a large common offset would make E[h^2] - mean^2 cancel."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(0))
+    for N, offset in ((256, 0.0), (2048, 0.0), (2048, 300.0)):
+        W = rng.uniform(-0.5, 0.5, size=(N, 4)).astype(np.float32)
+        b = (rng.uniform(-0.5, 0.5, size=N) + offset).astype(np.float32)
+        p = rng.uniform(-1, 1, size=(64, 4)).astype(np.float32)
+        Wd, bd = W.astype(np.float64), b.astype(np.float64)
+        U, v = Wd - Wd.mean(0), bd - bd.mean()
+        A, Bv, Cc = (U.T @ U) / N, (U * v[:, None]).mean(0), (v * v).mean()
+        A32, B32, C32 = A.astype(np.float32), Bv.astype(np.float32), np.float32(Cc)
+        var_cf = np.einsum("ri,ij,rj->r", p, A32, p) + 2 * (p @ B32) + C32            # fp32, as the row kernel does
+        h = p.astype(np.float64) @ Wd.T + bd
+        var_ref = h.var(axis=1)
+        assert np.all(var_cf > 0)
+        np.testing.assert_allclose(var_cf, var_ref, rtol=2e-5)
+        xhat_cf = (p @ U.astype(np.float32).T + v.astype(np.float32)) / np.sqrt(var_cf + 1e-5)[:, None]
+        xhat_ref = (h - h.mean(1, keepdims=True)) / np.sqrt(var_ref + 1e-5)[:, None]
+        assert np.abs(xhat_cf - xhat_ref).max() < 2e-5
